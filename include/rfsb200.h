@@ -1,0 +1,208 @@
+/*
+ * rfsb200.h — C ABI of the B200-native PHD measurement-update path.
+ *
+ * This is the drop-in boundary for ONE path of kykleung/RFS-SLAM: the body of
+ * rfs::RBPHDFilter<...>::update() (reference include/RBPHDFilter.hpp:444-541), i.e.
+ * the "#pragma omp parallel" region :469-520 (updateMap :543-725, importanceWeighting
+ * :728-819 with rfsMeasurementLikelihood :821-997, GaussianMixture::merge / prune
+ * include/GaussianMixture.hpp:394-521) plus the weight normalisation that follows it
+ * (include/ParticleFilter.hpp:352-363, ESS :406-411).
+ *
+ * Everything crossing this boundary is plain C: pointers, sizes, PODs.  Host-side
+ * numbers are fp64 (the reference's arithmetic type); the device keeps fp32
+ * particle-major SoA (precision = 32, the product) or fp64 (precision = 64, the
+ * verification build used for structural parity).  No torch / Eigen / Boost types.
+ *
+ * Conventions
+ *   - All functions return 0 (RFSB200_OK) or a negative RFSB200_E* code and never
+ *     throw.  rfsb200_last_error() gives a human-readable message.
+ *   - The caller owns every host buffer.  The ctx owns device memory and its stream.
+ *   - One ctx = one GPU = one shard of particles; a ctx is driven by one host thread
+ *     at a time (the reference calls update() from one thread; its OpenMP team is
+ *     what the GPU replaces).
+ *   - Symmetric covariances are passed as their upper triangle, row-major:
+ *     2-D: (xx, xy, yy); 3-D: (xx, xy, xz, yy, yz, zz).
+ *   - Gaussian mixtures are passed "packed": count[i] Gaussians of particle i follow
+ *     those of particle i-1 with no padding.
+ */
+#ifndef RFSB200_H
+#define RFSB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RFSB200_ABI_VERSION 1
+
+/* ---- error codes -------------------------------------------------------------- */
+#define RFSB200_OK            0
+#define RFSB200_EINVAL       -1  /* bad argument / NULL pointer / size out of range   */
+#define RFSB200_ECUDA        -2  /* a CUDA runtime call failed (see last_error)       */
+#define RFSB200_ENOMEM       -3  /* host or device allocation failed                  */
+#define RFSB200_ECAPACITY    -4  /* an input does not fit the capacities of the ctx   */
+#define RFSB200_EUNSUPPORTED -5  /* model / configuration not implemented on device   */
+#define RFSB200_ESTATE       -6  /* call sequence error (e.g. update before set_model)*/
+#define RFSB200_ENODEVICE    -7  /* no CUDA device: there is NO CPU fallback          */
+
+/* ---- measurement-model ids (plugin classes of the reference) ---------------- */
+#define RFSB200_MODEL_RNGBRG 1   /* rfs::MeasurementModel_RngBrg + KalmanFilter_RngBrg */
+
+/* ---- update flags -------------------------------------------------------------- */
+#define RFSB200_UPDATE_DEFAULT    0u
+#define RFSB200_UPDATE_NO_COMMIT  1u  /* compute the step into the back buffers but keep the
+                                         current state as the state (benchmark / replay aid) */
+#define RFSB200_UPDATE_NO_NORMALIZE 2u /* stop after the local [sum w, sum w^2] reduction so the
+                                         caller can all-reduce rfsb200_weight_sums_device() across
+                                         GPUs and then call rfsb200_normalize()               */
+
+typedef struct rfsb200_ctx rfsb200_ctx;
+
+/* Sizes fixed for the life of a ctx. */
+typedef struct rfsb200_dims {
+  int32_t n_particles;    /* particles in THIS shard                                        */
+  int32_t gm_capacity;    /* max Gaussians per particle held in HBM between steps (<= 1024) */
+  int32_t work_capacity;  /* max Gaussians per particle inside a step: inputs + Gaussians
+                             created by the corrector (>= gm_capacity, <= 1024)            */
+  int32_t z_capacity;     /* max measurements per update (<= 64)                            */
+  int32_t lmk_dim;        /* 2                                                              */
+  int32_t meas_dim;       /* 2                                                              */
+  int32_t pose_dim;       /* 3                                                              */
+  int32_t device;         /* CUDA device ordinal                                            */
+  int32_t precision;      /* 32 = fp32 SoA (product), 64 = fp64 SoA (verification)          */
+  int32_t reserved[7];
+} rfsb200_dims;
+
+/*
+ * POD mirror of the live plugin objects, refreshed by the host before every update()
+ * because the reference's configs are mutable public structs
+ * (MeasurementModel_RngBrg::config include/MeasurementModel_RngBrg.hpp:65-71,
+ *  KalmanFilter_RngBrg::config include/KalmanFilter_RngBrg.hpp:55-60,
+ *  MeasurementModel::R_ via getNoise include/MeasurementModel.hpp).
+ */
+typedef struct rfsb200_model_desc {
+  int32_t model_id;            /* RFSB200_MODEL_*                                               */
+  int32_t reserved0;
+  double  R[9];                /* measurement noise, row-major meas_dim x meas_dim              */
+  double  Pd;                  /* config.probabilityOfDetection_                                */
+  double  clutter_intensity;   /* clutterIntensity(z, nZ): uniform (RngBrg: config.uniformClutterIntensity_) */
+  double  clutter_integral;    /* clutterIntensityIntegral(nZ) as evaluated by the host plugin  */
+  double  range_min;           /* config.rangeLimMin_                                           */
+  double  range_max;           /* config.rangeLimMax_                                           */
+  double  range_buffer;        /* config.rangeLimBuffer_                                        */
+  double  innov_thr_range;     /* KalmanFilter_RngBrg config.rangeInnovationThreshold_  (<=0 off)*/
+  double  innov_thr_bearing;   /* KalmanFilter_RngBrg config.bearingInnovationThreshold_ (<=0 off)*/
+  double  reserved[8];
+} rfsb200_model_desc;
+
+/* Mirror of rfs::RBPHDFilter::Config (include/RBPHDFilter.hpp:90-146), update-path fields only. */
+typedef struct rfsb200_filter_cfg {
+  double  birth_gaussian_weight;                 /* birthGaussianWeight_ (used by updateMap :692) */
+  double  new_gaussian_create_innov_md_threshold;/* newGaussianCreateInnovMDThreshold_            */
+  double  eval_point_gaussian_weight;            /* importanceWeightingEvalPointGuassianWeight_   */
+  double  meas_likelihood_md_threshold;          /* importanceWeightingMeasurementLikelihoodMDThreshold_ */
+  double  merging_threshold;                     /* gaussianMergingThreshold_                     */
+  double  merging_cov_inflation_factor;          /* gaussianMergingCovarianceInflationFactor_     */
+  double  pruning_threshold;                     /* gaussianPruningThreshold_ (must be > 0)       */
+  int32_t eval_point_count;                      /* importanceWeightingEvalPointCount_ (0..32)    */
+  int32_t use_cluster_process;                   /* useClusterProcess_                            */
+  int32_t assignment_sum_method;                 /* 0 = enumeration order of the reference
+                                                    (PermutationLexicographic / Murty-200),
+                                                    1 = matrix-permanent identity (MatPerm path)  */
+  int32_t reserved_i[3];
+  double  reserved[6];
+} rfsb200_filter_cfg;
+
+/* Scalars that come back from one update (filled only when the pointer is non-NULL,
+ * which makes the call synchronous). */
+typedef struct rfsb200_step_out {
+  double  sum_w;              /* sum_i w_i of the unnormalised weights of this shard (after all-reduce if the caller did one) */
+  double  sum_w2;             /* sum_i w_i^2                                                                             */
+  double  n_eff;              /* (sum_w)^2 / sum_w2 : effective particle count (include/ParticleFilter.hpp:406-411)        */
+  int64_t gm_total_in;        /* sum_i nM_in(i)                                                                          */
+  int64_t gm_total_out;       /* sum_i nM_out(i)                                                                         */
+  int32_t gm_max_out;         /* max_i nM_out(i)                                                                         */
+  int32_t n_overflow;         /* particles whose work set exceeded work_capacity or output exceeded gm_capacity           */
+  int32_t n_murty;            /* particles that took the k-best (Murty, nR+nC>8) branch of rfsMeasurementLikelihood        */
+  int32_t n_launches;         /* kernels launched by this call                                                           */
+  float   elapsed_us;         /* device time of the step (CUDA events on the ctx stream)                                  */
+  int32_t reserved[7];
+} rfsb200_step_out;
+
+/* ---- lifetime ------------------------------------------------------------------ */
+int rfsb200_abi_version(void);
+int rfsb200_device_count(void);
+int rfsb200_create(rfsb200_ctx** out, const rfsb200_dims* dims);
+int rfsb200_destroy(rfsb200_ctx* ctx);
+const char* rfsb200_last_error(const rfsb200_ctx* ctx); /* ctx may be NULL: last creation error */
+
+/* Use an external CUDA stream (cudaStream_t as void*), e.g. torch's current stream.
+ * NULL restores the ctx-owned stream. */
+int rfsb200_set_stream(rfsb200_ctx* ctx, void* cuda_stream);
+int rfsb200_synchronize(rfsb200_ctx* ctx);
+
+/* ---- configuration (replaces the plugin virtual calls inside updateMap) --------- */
+int rfsb200_set_model(rfsb200_ctx* ctx, const rfsb200_model_desc* desc);
+int rfsb200_set_filter_cfg(rfsb200_ctx* ctx, const rfsb200_filter_cfg* cfg);
+
+/* ---- state in --------------------------------------------------------------------
+ * Replaces the host AoS-of-pointers maps (GaussianMixture::gList_,
+ * include/GaussianMixture.hpp:60-64,191) by device SoA.  Host pointers may be pageable
+ * or pinned (rfsb200_host_alloc); copies run on the ctx stream. */
+int rfsb200_upload_maps(rfsb200_ctx* ctx, const int32_t* count /*[N]*/,
+                        const double* mean /*[sum count][lmk_dim]*/,
+                        const double* cov  /*[sum count][lmk_dim*(lmk_dim+1)/2]*/,
+                        const double* w    /*[sum count]*/);
+/* pose_cov_mode: 0 = none (zero pose covariance), 1 = one shared [6], 2 = per particle [N][6]
+ * (Q1: the reference adds Hx*Sigma_x*Hx^T to S, src/MeasurementModel_RngBrg.cpp:102). */
+int rfsb200_set_poses(rfsb200_ctx* ctx, const double* pose /*[N][pose_dim]*/,
+                      const double* pose_cov, int pose_cov_mode,
+                      const double* weight /*[N] or NULL = keep*/);
+
+/* ---- the hot path ----------------------------------------------------------------
+ * One call = RBPHDFilter::update() for all particles of the shard
+ * (include/RBPHDFilter.hpp:444-541 minus the resampling itself):
+ * map update, particle weighting (SC-PHD or multi-feature), merge, prune,
+ * [sum w, sum w^2] reduction and (unless NO_NORMALIZE) weight normalisation.
+ * nZ == 0 returns immediately and changes nothing (reference :451-452).
+ * out == NULL: fully asynchronous on the ctx stream. */
+int rfsb200_update(rfsb200_ctx* ctx, const double* Z /*[nZ][meas_dim]*/, int32_t nZ,
+                   uint32_t flags, rfsb200_step_out* out);
+
+/* Device address of the double[2] {sum w, sum w^2} of the last update, for the caller's
+ * cross-GPU all-reduce (NCCL / torch.distributed) on the ctx stream; then normalize. */
+int rfsb200_weight_sums_device(rfsb200_ctx* ctx, void** dev_ptr);
+int rfsb200_normalize(rfsb200_ctx* ctx);
+/* After NO_COMMIT: results live in the back buffers; which=0 reads the committed state,
+ * which=1 the back buffers of the last update. */
+
+/* ---- state out --------------------------------------------------------------------
+ * Replace getGMSize / getLandmark (include/RBPHDFilter.hpp:1153-1178) and
+ * Particle::getWeight; "which" = 0 committed state, 1 = result of the last NO_COMMIT update. */
+int rfsb200_get_weights(rfsb200_ctx* ctx, int which, double* w /*[N]*/);
+int rfsb200_get_gm_sizes(rfsb200_ctx* ctx, int which, int32_t* n /*[N]*/);
+int rfsb200_get_map(rfsb200_ctx* ctx, int which, int32_t i, int32_t cap, int32_t* n,
+                    double* mean, double* cov, double* w);
+int rfsb200_download_maps(rfsb200_ctx* ctx, int which, int64_t cap_total, int32_t* count /*[N]*/,
+                          double* mean, double* cov, double* w);
+/* unused_measurements_[i] and nLandmarksInFOV_[i] (include/RBPHDFilter.hpp:269-272,709-720),
+ * consumed by addBirthGaussians on the host. unused_mask bit z set = measurement z unused. */
+int rfsb200_get_unused(rfsb200_ctx* ctx, uint64_t* unused_mask /*[N]*/, int32_t* n_in_fov /*[N]*/);
+/* per-particle status bits of the last update: 1 = capacity overflow, 2 = Murty branch taken */
+int rfsb200_get_flags(rfsb200_ctx* ctx, int32_t* flags /*[N]*/);
+
+/* ---- utilities --------------------------------------------------------------------
+ * rfs::MatPerm::calc (src/MatrixPermanent.cpp:41-113) for a batch of n x n matrices, on the
+ * device, fp64.  Non-square input cannot be expressed here; n must be in [1, 24]. */
+int rfsb200_permanent(rfsb200_ctx* ctx, const double* A /*[batch][n][n]*/, int32_t n,
+                      int32_t batch, double* out /*[batch]*/);
+
+/* Pinned host memory helpers (so H2D/D2H copies can overlap and run at PCIe speed). */
+int rfsb200_host_alloc(void** ptr, uint64_t bytes);
+int rfsb200_host_free(void* ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RFSB200_H */

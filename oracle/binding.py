@@ -1,0 +1,192 @@
+"""ctypes binding of the CPU oracle — TEST INFRASTRUCTURE, NOT PRODUCT.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module.  Two libraries share one entry-point signature (oracle/phd_oracle.h):
+
+  libphd_oracle.so        phd_oracle_update  — our fp64 restatement (oracle/phd_oracle.cpp)
+  _ref/libphd_ref.so      phd_ref_update     — the reference's own sources compiled against
+                                               oracle/compat shims (oracle/ref_harness.cpp)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import importlib
+import os
+import sys
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+if _ROOT not in sys.path:
+    sys.path.insert(0, _ROOT)
+
+ORACLE_LIB = os.path.join(_HERE, "libphd_oracle.so")
+REF_LIB = os.path.join(_HERE, "_ref", "libphd_ref.so")
+
+STAGE_UPDATE_MAP, STAGE_WEIGHTING, STAGE_MERGE, STAGE_FULL = 1, 2, 3, 4
+SORT_STD, SORT_STABLE = 0, 1
+
+
+def _capi():
+    return importlib.import_module("rfs_slam_b200.capi")
+
+
+class PhdIO(C.Structure):
+    _fields_ = [
+        ("N", C.c_int32), ("count_in", C.c_void_p), ("mean_in", C.c_void_p), ("cov_in", C.c_void_p),
+        ("w_in", C.c_void_p), ("pose", C.c_void_p), ("pose_cov", C.c_void_p),
+        ("pose_cov_mode", C.c_int32), ("weight_in", C.c_void_p), ("Z", C.c_void_p), ("nZ", C.c_int32),
+        ("model", C.c_void_p), ("cfg", C.c_void_p), ("sort_mode", C.c_int32), ("stage", C.c_int32),
+        ("n_threads", C.c_int32),
+        ("cap_total", C.c_int64), ("count_out", C.c_void_p), ("mean_out", C.c_void_p),
+        ("cov_out", C.c_void_p), ("w_out", C.c_void_p), ("wprev_out", C.c_void_p),
+        ("weight_out", C.c_void_p), ("unused_mask", C.c_void_p), ("n_in_fov", C.c_void_p),
+        ("flags", C.c_void_p), ("elapsed_s", C.c_double),
+    ]
+
+
+_libs = {}
+
+
+def _load(which: str):
+    if which in _libs:
+        return _libs[which]
+    path = ORACLE_LIB if which == "oracle" else REF_LIB
+    if not os.path.exists(path):
+        raise FileNotFoundError(path)
+    lib = C.CDLL(path)
+    fn = getattr(lib, "phd_oracle_update" if which == "oracle" else "phd_ref_update")
+    fn.restype = C.c_int
+    fn.argtypes = [C.POINTER(PhdIO)]
+    if which == "oracle":
+        lib.phd_oracle_permanent.restype = C.c_double
+        lib.phd_oracle_permanent.argtypes = [C.c_void_p, C.c_int]
+        lib.phd_oracle_lexi_count.restype = C.c_int64
+        lib.phd_oracle_lexi_count.argtypes = [C.c_int, C.c_int]
+        lib.phd_oracle_partition_likelihood.restype = C.c_double
+        lib.phd_oracle_partition_likelihood.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                                        C.c_void_p, C.c_void_p]
+        lib.phd_oracle_murty_sum.restype = C.c_double
+        lib.phd_oracle_murty_sum.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    else:
+        for name in ("phd_ref_permanent",):
+            if hasattr(lib, name):
+                getattr(lib, name).restype = C.c_double
+                getattr(lib, name).argtypes = [C.c_void_p, C.c_int]
+    _libs[which] = (lib, fn)
+    return _libs[which]
+
+
+def have_ref() -> bool:
+    return os.path.exists(REF_LIB)
+
+
+def have_oracle() -> bool:
+    return os.path.exists(ORACLE_LIB)
+
+
+class Result:
+    """Packed posterior state returned by an oracle run."""
+
+    def __init__(self, count, mean, cov, w, wprev, weight, unused_mask, n_in_fov, flags, elapsed_s):
+        self.count, self.mean, self.cov, self.w, self.wprev = count, mean, cov, w, wprev
+        self.weight, self.unused_mask, self.n_in_fov, self.flags = weight, unused_mask, n_in_fov, flags
+        self.elapsed_s = elapsed_s
+
+    @property
+    def offsets(self):
+        o = np.zeros(len(self.count) + 1, dtype=np.int64)
+        np.cumsum(self.count, out=o[1:])
+        return o
+
+    def particle(self, i):
+        o = self.offsets
+        a, b = int(o[i]), int(o[i + 1])
+        return self.mean[a:b], self.cov[a:b], self.w[a:b]
+
+
+def run(wl, *, which: str = "oracle", stage: int = STAGE_FULL, sort_mode: int = SORT_STABLE,
+        n_threads: int = 0, cap_factor: float = 2.0) -> Result:
+    """Run one RBPHDFilter::update() on a synth.Workload through the oracle or the reference."""
+    capi = _capi()
+    lib, fn = _load(which)
+    N = wl.N
+    total_in = int(wl.count.sum())
+    cap_total = int(total_in * cap_factor) + 64 * N + 1024
+    md = capi.model_desc(wl.model)
+    fc = capi.filter_cfg(wl.cfg)
+    count_in = np.ascontiguousarray(wl.count, dtype=np.int32)
+    arrs = dict(mean_in=np.ascontiguousarray(wl.mean, dtype=np.float64),
+                cov_in=np.ascontiguousarray(wl.cov, dtype=np.float64),
+                w_in=np.ascontiguousarray(wl.w, dtype=np.float64),
+                pose=np.ascontiguousarray(wl.pose, dtype=np.float64),
+                weight_in=np.ascontiguousarray(wl.weight, dtype=np.float64),
+                Z=np.ascontiguousarray(wl.Z, dtype=np.float64).reshape(-1, 2))
+    pose_cov = None if wl.pose_cov is None else np.ascontiguousarray(wl.pose_cov, dtype=np.float64)
+    if pose_cov is None:
+        mode = 0
+    elif pose_cov.ndim == 1:
+        mode = 1
+    else:
+        mode = 2
+    out = dict(count_out=np.zeros(N, np.int32), mean_out=np.zeros((cap_total, 2)),
+               cov_out=np.zeros((cap_total, 3)), w_out=np.zeros(cap_total), wprev_out=np.zeros(cap_total),
+               weight_out=np.zeros(N), unused_mask=np.zeros(N, np.uint64), n_in_fov=np.zeros(N, np.int32),
+               flags=np.zeros(N, np.int32))
+    io = PhdIO()
+    io.N = N
+    io.count_in = count_in.ctypes.data
+    for k, a in arrs.items():
+        setattr(io, k, a.ctypes.data)
+    io.pose_cov = None if pose_cov is None else pose_cov.ctypes.data
+    io.pose_cov_mode = mode
+    io.nZ = arrs["Z"].shape[0]
+    io.model = C.addressof(md)
+    io.cfg = C.addressof(fc)
+    io.sort_mode = sort_mode
+    io.stage = stage
+    io.n_threads = n_threads
+    io.cap_total = cap_total
+    for k, a in out.items():
+        setattr(io, k, a.ctypes.data)
+    rc = fn(C.byref(io))
+    if rc != 0:
+        raise RuntimeError(f"{which} update failed rc={rc}")
+    tot = int(out["count_out"].sum())
+    return Result(out["count_out"], out["mean_out"][:tot].copy(), out["cov_out"][:tot].copy(),
+                  out["w_out"][:tot].copy(), out["wprev_out"][:tot].copy(), out["weight_out"],
+                  out["unused_mask"], out["n_in_fov"], out["flags"], io.elapsed_s)
+
+
+def permanent(A: np.ndarray, which: str = "oracle") -> float:
+    lib, _ = _load(which)
+    A = np.ascontiguousarray(A, dtype=np.float64)
+    f = lib.phd_oracle_permanent if which == "oracle" else lib.phd_ref_permanent
+    return float(f(A.ctypes.data, A.shape[0]))
+
+
+def lexi_count(nM: int, nZ: int) -> int:
+    lib, _ = _load("oracle")
+    return int(lib.phd_oracle_lexi_count(nM, nZ))
+
+
+def partition_likelihood(L: np.ndarray, evalPd: np.ndarray, clutter: np.ndarray):
+    lib, _ = _load("oracle")
+    L = np.ascontiguousarray(L, dtype=np.float64)
+    evalPd = np.ascontiguousarray(evalPd, dtype=np.float64)
+    clutter = np.ascontiguousarray(clutter, dtype=np.float64)
+    flags = np.zeros(1, np.int32)
+    nE, nZ = L.shape
+    v = lib.phd_oracle_partition_likelihood(L.ctypes.data, nE, nZ, evalPd.ctypes.data,
+                                            clutter.ctypes.data, flags.ctypes.data)
+    return float(v), int(flags[0])
+
+
+def murty_sum(Lp: np.ndarray, rowPd: np.ndarray, colClutter: np.ndarray) -> float:
+    lib, _ = _load("oracle")
+    Lp = np.ascontiguousarray(Lp, dtype=np.float64)
+    rowPd = np.ascontiguousarray(rowPd, dtype=np.float64)
+    colClutter = np.ascontiguousarray(colClutter, dtype=np.float64)
+    return float(lib.phd_oracle_murty_sum(Lp.ctypes.data, Lp.shape[0], Lp.shape[1],
+                                          rowPd.ctypes.data, colClutter.ctypes.data))

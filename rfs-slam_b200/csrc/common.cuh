@@ -1,0 +1,130 @@
+// common.cuh — sm_100a building blocks used by the PHD update kernels:
+// 1-D TMA bulk copies (cp.async.bulk, SASS UBLKCP) completing on an mbarrier, bulk-group
+// stores, proxy fences, warp reductions / scans.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rfsb200 {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// ---- mbarrier ---------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+
+// ---- TMA 1-D bulk copies ------------------------------------------------------------------
+// global -> shared, completion counted in bytes on an mbarrier. 16-byte aligned, size % 16 == 0.
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+// shared -> global, tracked by the per-thread bulk async-group.
+__device__ __forceinline__ void tma_store_1d(void* gmem_dst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst),
+               "r"(smem_u32(smem_src)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// wait until the bulk stores of this thread have finished READING shared memory
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// order generic-proxy shared-memory accesses against the async proxy (TMA)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- warp helpers -------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  return v;
+}
+template <typename T>
+__device__ __forceinline__ T warp_max(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    T u = __shfl_xor_sync(FULL, v, o);
+    v = u > v ? u : v;
+  }
+  return v;
+}
+template <typename T>
+__device__ __forceinline__ T warp_min(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    T u = __shfl_xor_sync(FULL, v, o);
+    v = u < v ? u : v;
+  }
+  return v;
+}
+// inclusive scan of an int across the warp
+__device__ __forceinline__ int warp_incl_scan(int v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int u = __shfl_up_sync(FULL, v, o);
+    if (lane >= o) v += u;
+  }
+  return v;
+}
+
+// ---- scalar math dispatch (fp32 product / fp64 verification) -----------------------------------
+template <typename T> struct M;
+template <> struct M<float> {
+  static __device__ __forceinline__ float sqrt_(float x) { return sqrtf(x); }
+  static __device__ __forceinline__ float exp_(float x) { return expf(x); }
+  static __device__ __forceinline__ float log_(float x) { return logf(x); }
+  static __device__ __forceinline__ float atan2_(float y, float x) { return atan2f(y, x); }
+  static __device__ __forceinline__ float abs_(float x) { return fabsf(x); }
+  static __device__ __forceinline__ float max_(float a, float b) { return fmaxf(a, b); }
+  static __device__ __forceinline__ float inf() { return __int_as_float(0x7f800000); }
+  static constexpr float PI = 3.14159265358979323846f;
+  static constexpr float TWO_PI = 6.28318530717958647692f;
+};
+template <> struct M<double> {
+  static __device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
+  static __device__ __forceinline__ double exp_(double x) { return exp(x); }
+  static __device__ __forceinline__ double log_(double x) { return log(x); }
+  static __device__ __forceinline__ double atan2_(double y, double x) { return atan2(y, x); }
+  static __device__ __forceinline__ double abs_(double x) { return fabs(x); }
+  static __device__ __forceinline__ double max_(double a, double b) { return fmax(a, b); }
+  static __device__ __forceinline__ double inf() { return __longlong_as_double(0x7ff0000000000000LL); }
+  static constexpr double PI = 3.14159265358979323846;
+  static constexpr double TWO_PI = 6.28318530717958647692;
+};
+
+}  // namespace rfsb200

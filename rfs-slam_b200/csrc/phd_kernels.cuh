@@ -1,0 +1,1051 @@
+// phd_kernels.cuh — the fused per-particle PHD measurement update for sm_100a.
+//
+// One launch processes every particle of the shard: ONE WARP PER PARTICLE, persistent CTAs.
+// Per particle (reference include/RBPHDFilter.hpp):
+//   S0  TMA bulk loads (cp.async.bulk + mbarrier) of the particle's 6 SoA planes HBM -> smem
+//   S1  GM-PHD corrector, updateMap :597-641 — EKF innovation / likelihood between every Gaussian
+//       and every measurement in registers; gated survivors appended (m-major, z-minor)
+//   S2  per-measurement normalisers kappa + sum_m W (:644-659) and SC-PHD weight (:661-668)
+//   S3  posterior weights of the new Gaussians, S4 missed-detection weights + sensing-limit
+//       heuristic (:686-706), unused-measurement mask (:709-720)
+//   S5  multi-feature importance weighting (:728-819, rfsMeasurementLikelihood :821-997)
+//   S6  greedy GaussianMixture::merge (include/GaussianMixture.hpp:394-475), exact order
+//   S7  prune (:477-521): keep w >= t, weight-descending; TMA bulk store smem -> HBM
+//   S8  deterministic [sum w, sum w^2] reduction by the last CTA (ParticleFilter.hpp:352-363,406-411)
+//
+// No tensor cores: the 2x2 / 2x3 EKF blocks are register math, the path is HBM/ALU bound.
+#pragma once
+#include "common.cuh"
+
+namespace rfsb200 {
+
+constexpr int WARPS_PER_CTA = 4;
+constexpr int MAX_Z = 64;
+constexpr int MAX_EVAL = 32;
+constexpr int DP_MAXB = 7;     // assignment-sum DP: the smaller side of a partition has <= 7 members
+constexpr int MAX_COMP = 96;   // connected components of the (eval point, measurement) graph
+constexpr int MAX_PAIRS = 256; // merge pre-pass: candidate pairs kept per particle
+
+// flag bits written per particle
+constexpr int FLAG_OVERFLOW = 1;
+constexpr int FLAG_MURTY = 2;       // a partition with nR + nC > 8 (reference would use Murty-200)
+constexpr int FLAG_DP_OVERFLOW = 4; // partition too large for the on-chip DP
+
+template <typename T>
+struct KParams {
+  // model (MeasurementModel_RngBrg / KalmanFilter_RngBrg configs)
+  T R00, R01, R11;
+  T Pd, kappa;
+  T rmin, rmax, rbuf;
+  T thr_r, thr_b;
+  // filter config
+  T birth_w, gate2, eval_min_w, wl_gate2, merge_t2, merge_f, prune_t;
+  int n_eval, use_sc, sum_method, merge_algo;
+  double log_clutter_integral;
+  double log_kappa;
+  // shapes
+  int N, cap, W, nZ, pose_cov_mode;
+  int warp_bytes;  // shared memory per warp
+  // state in / out
+  const T* gm_in;
+  const int* cnt_in;
+  const double* w_in;
+  const T* pose;      // [N][4]
+  const T* pose_cov;  // [8] or [N][8]
+  const T* Z;         // [nZ][2]
+  T* gm_out;
+  int* cnt_out;
+  double* w_out;
+  unsigned long long* unused;
+  int* nfov;
+  int* flags;
+  // reductions
+  double* sums;                   // [2]
+  unsigned long long* totals;     // [0]=gm_in total [1]=gm_out total
+  int* istats;                    // [0]=max out [1]=n_overflow [2]=n_murty
+  unsigned int* ticket;
+};
+
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ T wrap_pi(T a) {
+  while (a > M<T>::PI) a -= M<T>::TWO_PI;
+  while (a < -M<T>::PI) a += M<T>::TWO_PI;
+  return a;
+}
+
+// ordering used by every sort: weight descending, then position ascending (stable)
+template <typename T>
+__device__ __forceinline__ bool before(T wa, unsigned ia, T wb, unsigned ib) {
+  return (wa > wb) || (wa == wb && ia < ib);
+}
+
+// Bitonic sort of P (power of two) (key, idx) pairs in shared memory by one warp.
+template <typename T>
+__device__ __forceinline__ void warp_bitonic(T* kw, unsigned* ki, int P, int lane) {
+  for (int k = 2; k <= P; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = lane; t < (P >> 1); t += 32) {
+        int i = ((t / j) * (j << 1)) + (t % j);
+        int q = i + j;
+        bool up = ((i & k) == 0);
+        T wa = kw[i], wb = kw[q];
+        unsigned ia = ki[i], ib = ki[q];
+        bool a_first = before(wa, ia, wb, ib);
+        if (a_first != up) {
+          kw[i] = wb; kw[q] = wa;
+          ki[i] = ib; ki[q] = ia;
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+__device__ __forceinline__ int next_pow2(int n) {
+  int p = 1;
+  while (p < n) p <<= 1;
+  return p;
+}
+
+// ------------------------------------------------------------------------------------------------
+// S6: GaussianMixture::merge.  cur = 7 planes of W; holes are marked by weight < 0.
+// Exact reference semantics: rows i ascending; for each live i, j ascending from i+1; test with
+// the CURRENT state of i; on success i absorbs j (moment matching with inflation f) and j dies.
+template <typename T>
+struct MergeRow {
+  T x, y, pxx, pxy, pyy, w, i00, i01, i11;
+};
+
+template <typename T>
+__device__ __forceinline__ void inv_sym2(T a, T b, T c, T& i00, T& i01, T& i11) {
+  T invdet = T(1) / (a * c - b * b);
+  i00 = c * invdet;
+  i01 = -b * invdet;
+  i11 = a * invdet;
+}
+
+template <typename T>
+__device__ __forceinline__ bool merge_test(const MergeRow<T>& r, const T* cur, int W, int j, T t2) {
+  T dx = cur[j] - r.x, dy = cur[W + j] - r.y;
+  T d1 = (dx * r.i00 + dy * r.i01) * dx + (dx * r.i01 + dy * r.i11) * dy;
+  if (!(d1 > t2)) return true;
+  T j00, j01, j11;
+  inv_sym2(cur[2 * W + j], cur[3 * W + j], cur[4 * W + j], j00, j01, j11);
+  T d2 = (dx * j00 + dy * j01) * dx + (dx * j01 + dy * j11) * dy;
+  return !(d2 > t2);
+}
+
+template <typename T>
+__device__ __forceinline__ void load_row(MergeRow<T>& r, const T* cur, int W, int i) {
+  r.x = cur[i]; r.y = cur[W + i];
+  r.pxx = cur[2 * W + i]; r.pxy = cur[3 * W + i]; r.pyy = cur[4 * W + i];
+  r.w = cur[5 * W + i];
+  inv_sym2(r.pxx, r.pxy, r.pyy, r.i00, r.i01, r.i11);
+}
+
+// absorb j into row r (all lanes compute the same values; lane 0 writes). returns false if w_m == 0.
+template <typename T>
+__device__ __forceinline__ bool merge_absorb(MergeRow<T>& r, T* cur, int W, int i, int j, T f, int lane) {
+  T w1 = r.w, w2 = cur[5 * W + j];
+  T wm = w1 + w2;
+  if (wm == T(0)) return false;
+  T x2 = cur[j], y2 = cur[W + j];
+  T q00 = cur[2 * W + j], q01 = cur[3 * W + j], q11 = cur[4 * W + j];
+  T xm = (r.x * w1 + x2 * w2) / wm, ym = (r.y * w1 + y2 * w2) / wm;
+  T ax = xm - r.x, ay = ym - r.y, bx = xm - x2, by = ym - y2;
+  T s00 = (w1 * (r.pxx + f * ax * ax) + w2 * (q00 + f * bx * bx)) / wm;
+  T s01 = (w1 * (r.pxy + f * ax * ay) + w2 * (q01 + f * bx * by)) / wm;
+  T s11 = (w1 * (r.pyy + f * ay * ay) + w2 * (q11 + f * by * by)) / wm;
+  r.x = xm; r.y = ym; r.pxx = s00; r.pxy = s01; r.pyy = s11; r.w = wm;
+  inv_sym2(s00, s01, s11, r.i00, r.i01, r.i11);
+  __syncwarp();
+  if (lane == 0) {
+    cur[i] = xm; cur[W + i] = ym;
+    cur[2 * W + i] = s00; cur[3 * W + i] = s01; cur[4 * W + i] = s11;
+    cur[5 * W + i] = wm; cur[6 * W + i] = T(0);
+    cur[5 * W + j] = T(-1);  // hole
+    cur[6 * W + j] = T(0);
+  }
+  __syncwarp();
+  return true;
+}
+
+// scan j in [jstart, n) for the first live j passing the test against row r (rad2 = optional
+// conservative pre-filter plane: reject when |d|^2 > max(rad2_i, rad2_j)); returns -1 if none
+template <typename T, bool PREFILTER>
+__device__ __forceinline__ int merge_scan(const MergeRow<T>& r, const T* cur, const T* rad2, T rad2_i,
+                                          int W, int jstart, int n, T t2, int lane) {
+  for (int base = jstart; base < n; base += 32) {
+    int j = base + lane;
+    bool pass = false;
+    if (j < n) {
+      T wj = cur[5 * W + j];
+      if (wj >= T(0)) {
+        bool cand = true;
+        if (PREFILTER) {
+          T dx = cur[j] - r.x, dy = cur[W + j] - r.y;
+          T rr = M<T>::max_(rad2_i, rad2[j]);
+          cand = !(dx * dx + dy * dy > rr);
+        }
+        if (cand) pass = merge_test(r, cur, W, j, t2);
+      }
+    }
+    unsigned b = __ballot_sync(FULL, pass);
+    if (b) return base + __ffs(b) - 1;
+  }
+  return -1;
+}
+
+// conservative squared reach of a component for the merge test: d_mahalanobis >= |d|^2 / lambda_max
+// and lambda_max <= trace for a PSD matrix; non-PD covariances get an infinite reach.
+template <typename T>
+__device__ __forceinline__ T merge_reach2(T pxx, T pxy, T pyy, T t2) {
+  bool pd = (pxx > T(0)) && (pyy > T(0)) && (pxx * pyy - pxy * pxy > T(0));
+  return pd ? t2 * (pxx + pyy) * T(1.001) : M<T>::inf();
+}
+
+template <typename T>
+__device__ void merge_bruteforce(T* cur, int W, int n, T t2, T f, int lane) {
+  for (int i = 0; i < n; i++) {
+    if (cur[5 * W + i] < T(0)) continue;
+    MergeRow<T> r;
+    load_row(r, cur, W, i);
+    int jstart = i + 1;
+    while (true) {
+      int j = merge_scan<T, false>(r, cur, nullptr, T(0), W, jstart, n, t2, lane);
+      if (j < 0) break;
+      merge_absorb(r, cur, W, i, j, f, lane);
+      jstart = j + 1;
+    }
+  }
+}
+
+// Culled merge (same results as merge_bruteforce):
+//  pre-pass: counting sort of the live components on a 256-cell grid over x, every component
+//            scans the cells its own reach covers and runs the exact test (original parameters)
+//            on the candidates -> short list of passing pairs (i<j), key = i<<16 | j
+//  sequential phase: rows are visited in ascending i only if they own a passing pair; the first
+//            merge of a row is its smallest live j in the list (everything is still original
+//            then); after an absorb the row changed, so j > jmin is re-scanned exhaustively.
+//  scratch: rad2[W] T, cellStart[258] u16 + cursor[257] u16, order[W] u16, pairs[MAX_PAIRS] u32
+template <typename T>
+__device__ void merge_culled(T* cur, T* scratch, int W, int n, T t2, T f, int lane) {
+  T* rad2 = scratch;                                     // W
+  unsigned* pairs = reinterpret_cast<unsigned*>(scratch + W);      // MAX_PAIRS
+  unsigned short* cellStart = reinterpret_cast<unsigned short*>(pairs + MAX_PAIRS);  // 258
+  unsigned short* cursor = cellStart + 258;              // 258
+  unsigned short* order = cursor + 258;                  // W
+  unsigned* npairs = reinterpret_cast<unsigned*>(order + W + (W & 1));  // 1 (4-byte aligned)
+  // reach + bounding interval
+  T xmin = M<T>::inf(), xmax = -M<T>::inf();
+  for (int j = lane; j < n; j += 32) {
+    T w = cur[5 * W + j];
+    T rr = T(0);
+    if (w >= T(0)) {
+      rr = merge_reach2(cur[2 * W + j], cur[3 * W + j], cur[4 * W + j], t2);
+      T x = cur[j];
+      xmin = x < xmin ? x : xmin;
+      xmax = x > xmax ? x : xmax;
+    }
+    rad2[j] = rr;
+  }
+  for (int c = lane; c < 258; c += 32) { cellStart[c] = 0; }
+  if (lane == 0) *npairs = 0;
+  xmin = warp_min(xmin);
+  xmax = warp_max(xmax);
+  T span = xmax - xmin;
+  T invw = (span > T(0)) ? T(255.999) / span : T(0);
+  __syncwarp();
+  // histogram (counts at cell+1 for the exclusive prefix)
+  for (int j = lane; j < n; j += 32) {
+    if (cur[5 * W + j] >= T(0)) {
+      int c = (int)((cur[j] - xmin) * invw);
+      c = c < 0 ? 0 : (c > 255 ? 255 : c);
+      // 16-bit counters packed in 32-bit words: atomicAdd on the containing word
+      unsigned* wd = reinterpret_cast<unsigned*>(cellStart) + ((c + 1) >> 1);
+      atomicAdd(wd, ((c + 1) & 1) ? 0x10000u : 1u);
+    }
+  }
+  __syncwarp();
+  {  // exclusive prefix over 257 entries: lane owns 8 consecutive cells (+ tail by lane 0)
+    int loc[8];
+    int s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) { loc[k] = cellStart[1 + lane * 8 + k]; s += loc[k]; }
+    int incl = warp_incl_scan(s, lane);
+    int run = incl - s;
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 8; k++) { run += loc[k]; cellStart[1 + lane * 8 + k] = (unsigned short)run; }
+    if (lane == 0) cellStart[0] = 0;
+    __syncwarp();
+    if (lane == 0) cellStart[257] = cellStart[256];
+  }
+  for (int c = lane; c < 258; c += 32) cursor[c] = cellStart[c];
+  __syncwarp();
+  for (int j = lane; j < n; j += 32) {
+    if (cur[5 * W + j] >= T(0)) {
+      int c = (int)((cur[j] - xmin) * invw);
+      c = c < 0 ? 0 : (c > 255 ? 255 : c);
+      unsigned* wd = reinterpret_cast<unsigned*>(cursor) + (c >> 1);
+      unsigned old = atomicAdd(wd, (c & 1) ? 0x10000u : 1u);
+      unsigned pos = (c & 1) ? (old >> 16) : (old & 0xffffu);
+      order[pos] = (unsigned short)j;
+    }
+  }
+  __syncwarp();
+  // neighbour scan with exact test on original parameters
+  bool overflow = false;
+  for (int j = lane; j < n; j += 32) {
+    T wj = cur[5 * W + j];
+    if (!(wj >= T(0))) continue;
+    T rj2 = rad2[j];
+    T xj = cur[j], yj = cur[W + j];
+    int clo = 0, chi = 255;
+    if (rj2 < M<T>::inf() && invw > T(0)) {
+      T rj = M<T>::sqrt_(rj2);
+      int a = (int)((xj - rj - xmin) * invw) - 1;
+      int b = (int)((xj + rj - xmin) * invw) + 1;
+      clo = a < 0 ? 0 : (a > 255 ? 255 : a);
+      chi = b < 0 ? 0 : (b > 255 ? 255 : b);
+    }
+    int k0 = cellStart[clo], k1 = cellStart[chi + 1];
+    for (int k = k0; k < k1; k++) {
+      int c = order[k];
+      if (c == j) continue;
+      T dx = cur[c] - xj, dy = cur[W + c] - yj;
+      if (dx * dx + dy * dy > rj2) continue;   // found from the side whose reach covers the pair
+      int i0 = j < c ? j : c, j0 = j < c ? c : j;
+      MergeRow<T> r;
+      load_row(r, cur, W, i0);
+      if (merge_test(r, cur, W, j0, t2)) {
+        unsigned slot = atomicAdd(npairs, 1u);
+        if (slot < (unsigned)MAX_PAIRS) pairs[slot] = ((unsigned)i0 << 16) | (unsigned)j0;
+        else overflow = true;
+      }
+    }
+  }
+  __syncwarp();
+  if (__any_sync(FULL, overflow)) {  // too many candidate pairs: exact fallback
+    merge_bruteforce(cur, W, n, t2, f, lane);
+    return;
+  }
+  int np = (int)*npairs;
+  // sequential phase
+  unsigned curkey = 0;
+  while (true) {
+    unsigned best = 0xffffffffu;
+    for (int k = lane; k < np; k += 32) {
+      unsigned key = pairs[k];
+      if (key >= curkey && key < best) {
+        int i = key >> 16, j = key & 0xffff;
+        if (cur[5 * W + i] >= T(0) && cur[5 * W + j] >= T(0)) best = key;
+      }
+    }
+    best = warp_min(best);
+    if (best == 0xffffffffu) break;
+    int i = best >> 16, j = best & 0xffff;
+    MergeRow<T> r;
+    load_row(r, cur, W, i);
+    if (!merge_absorb(r, cur, W, i, j, f, lane)) {  // w_m == 0: the reference moves on to j+1
+      curkey = best + 1;
+      continue;
+    }
+    int jstart = j + 1;
+    while (true) {
+      T ri2 = merge_reach2(r.pxx, r.pxy, r.pyy, t2);
+      int jj = merge_scan<T, true>(r, cur, rad2, ri2, W, jstart, n, t2, lane);
+      if (jj < 0) break;
+      merge_absorb(r, cur, W, i, jj, f, lane);
+      jstart = jj + 1;
+    }
+    curkey = ((unsigned)(i + 1)) << 16;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// S5 helpers: assignment sum of one partition by DP over subsets of its smaller side (fp64).
+//  rows: eval points (miss factor 1-Pd), cols: measurements (clutter factor kappa), L = Pd*pdf.
+//  Equals the reference's exhaustive enumeration (include/RBPHDFilter.hpp:961-988).
+template <typename T>
+__device__ double partition_dp(const T* L, int nZ, unsigned rmask, unsigned long long cmask,
+                               const T* evalPd, double kappa, double* f0, double* f1, int lane) {
+  int nR = __popc(rmask), nC = __popcll(cmask);
+  bool rowsSmall = nR <= nC;
+  int b = rowsSmall ? nR : nC;
+  int S = 1 << b;
+  // index lists
+  int small[DP_MAXB];
+  {
+    int k = 0;
+    if (rowsSmall) { unsigned m = rmask; while (m) { int r = __ffs(m) - 1; m &= m - 1; if (k < DP_MAXB) small[k] = r; k++; } }
+    else { unsigned long long m = cmask; while (m) { int c = __ffsll((long long)m) - 1; m &= m - 1; if (k < DP_MAXB) small[k] = c; k++; } }
+  }
+  for (int s = lane; s < S; s += 32) f0[s] = (s == 0) ? 1.0 : 0.0;
+  __syncwarp();
+  double* fa = f0;
+  double* fb = f1;
+  if (rowsSmall) {
+    unsigned long long m = cmask;
+    while (m) {  // columns one at a time: clutter, or assigned to a row in the mask
+      int c = __ffsll((long long)m) - 1; m &= m - 1;
+      for (int s = lane; s < S; s += 32) {
+        double v = fa[s] * kappa;
+        for (int k = 0; k < b; k++) if (s & (1 << k)) v += fa[s ^ (1 << k)] * (double)L[small[k] * nZ + c];
+        fb[s] = v;
+      }
+      __syncwarp();
+      double* t = fa; fa = fb; fb = t;
+    }
+    double tot = 0;
+    for (int s = lane; s < S; s += 32) {
+      double v = fa[s];
+      for (int k = 0; k < b; k++) if (!(s & (1 << k))) v *= (1.0 - (double)evalPd[small[k]]);
+      tot += v;
+    }
+    tot = warp_sum(tot);
+    __syncwarp();
+    return tot;
+  } else {
+    unsigned m = rmask;
+    while (m) {  // rows one at a time: missed, or assigned to a free column in the mask
+      int r = __ffs(m) - 1; m &= m - 1;
+      double miss = 1.0 - (double)evalPd[r];
+      for (int s = lane; s < S; s += 32) {
+        double v = fa[s] * miss;
+        for (int k = 0; k < b; k++) if (s & (1 << k)) v += fa[s ^ (1 << k)] * (double)L[r * nZ + small[k]];
+        fb[s] = v;
+      }
+      __syncwarp();
+      double* t = fa; fa = fb; fb = t;
+    }
+    double tot = 0;
+    for (int s = lane; s < S; s += 32) {
+      double v = fa[s];
+      for (int k = 0; k < b; k++) if (!(s & (1 << k))) v *= kappa;
+      tot += v;
+    }
+    tot = warp_sum(tot);
+    __syncwarp();
+    return tot;
+  }
+}
+
+// Nijenhuis-Wilf / Gray-code permanent (src/MatrixPermanent.cpp:41-113) of an n x n fp64 matrix in
+// shared or global memory, evaluated by one warp: the 2^(n-1) subsets are split across lanes.
+__device__ inline double warp_permanent(const double* A, int n, int lane) {
+  if (n == 1) return A[0];
+  // Glynn-style formula equivalent to the reference's NW walk:
+  // perm = 2 * (-1)^n... evaluated as sum over delta in {+-1}^(n-1) (last column sign fixed)
+  // x_i(S) = A(i,n-1) - 1/2 sum_j A(i,j) + sum_{j in S} A(i,j);  perm = (-1)^(n-1) * 2 * sum_S (-1)^|S| prod_i x_i(S)
+  unsigned long long total = 1ull << (n - 1);
+  double acc = 0;
+  for (unsigned long long s = lane; s < total; s += 32) {
+    double prod = 1;
+    for (int i = 0; i < n; i++) {
+      double rs = 0, xs = 0;
+      for (int j = 0; j < n; j++) {
+        double a = A[i * n + j];
+        rs += a;
+        if (j < n - 1 && ((s >> j) & 1)) xs += a;
+      }
+      prod *= (A[i * n + n - 1] - 0.5 * rs + xs);
+    }
+    acc += (__popcll(s) & 1) ? -prod : prod;
+  }
+  acc = warp_sum(acc);
+  double r = 2 * acc;
+  if ((n - 1) & 1) r = -r;
+  return r;
+}
+
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+phd_update_kernel(const __grid_constant__ KParams<T> p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int W = p.W;
+  const int nZ = p.nZ;
+
+  T* zs = reinterpret_cast<T*>(smem_raw);  // [2*MAX_Z]: zr[z] at 2z, zb[z] at 2z+1
+  unsigned char* wb = smem_raw + 2 * MAX_Z * sizeof(T) + (size_t)warp * p.warp_bytes;
+  T* bufA = reinterpret_cast<T*>(wb);
+  T* bufB = bufA + 7 * W;
+  unsigned* aux = reinterpret_cast<unsigned*>(bufB + 7 * W);  // [W]
+  T* colsum = reinterpret_cast<T*>(aux + W);                  // [MAX_Z]
+  int* evalIdx = reinterpret_cast<int*>(colsum + MAX_Z);      // [MAX_EVAL]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(evalIdx + MAX_EVAL);
+
+  for (int k = threadIdx.x; k < 2 * nZ; k += blockDim.x) zs[k] = p.Z[k];
+  if (lane == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  uint32_t phase = 0;
+  unsigned long long tot_in = 0, tot_out = 0;
+  int max_out = 0, n_over = 0, n_murty = 0;
+
+  const int gw = blockIdx.x * WARPS_PER_CTA + warp;
+  const int gstride = gridDim.x * WARPS_PER_CTA;
+
+  for (int pi = gw; pi < p.N; pi += gstride) {
+    T* cur = bufA;
+    T* alt = bufB;
+    int nM = p.cnt_in[pi];
+    nM = nM < 0 ? 0 : (nM > p.cap ? p.cap : nM);
+    int flags = 0;
+    if (nM > W) { nM = W; flags |= FLAG_OVERFLOW; }
+    const double w_prev_particle = p.w_in[pi];
+
+    // previous particle's bulk stores must have finished reading bufB before it is reused
+    if (lane == 0) tma_store_wait_read();
+    __syncwarp();
+
+    // ---------------- S0: TMA bulk loads -------------------------------------------------
+    if (nM > 0) {
+      if (lane == 0) {
+        uint32_t bytes = (uint32_t)(((nM + 3) & ~3) * sizeof(T));
+        fence_proxy_async();
+        mbar_expect_tx(bar, 6 * bytes);
+        const T* src = p.gm_in + (size_t)pi * 6 * p.cap;
+#pragma unroll
+        for (int k = 0; k < 6; k++) tma_load_1d(cur + k * W, src + (size_t)k * p.cap, bytes, bar);
+      }
+      mbar_wait(bar, phase);
+      phase ^= 1;
+    }
+
+    const T px = p.pose[4 * pi], py = p.pose[4 * pi + 1], pth = p.pose[4 * pi + 2];
+    T c00 = 0, c01 = 0, c02 = 0, c11 = 0, c12 = 0, c22 = 0;
+    if (p.pose_cov_mode) {
+      const T* pc = p.pose_cov + (p.pose_cov_mode == 2 ? (size_t)pi * 8 : 0);
+      c00 = pc[0]; c01 = pc[1]; c02 = pc[2]; c11 = pc[3]; c12 = pc[4]; c22 = pc[5];
+    }
+
+    // ---------------- S1: corrector --------------------------------------------------------
+    int nS = 0;                 // survivors appended so far
+    double wsum_d = 0;          // sum of pre-update weights (SC-PHD)
+    int nfov = 0;
+    bool over = false;
+    for (int base = 0; base < nM; base += 32) {
+      const int m = base + lane;
+      unsigned long long mask = 0;
+      T x = 0, y = 0, pxx = 0, pxy = 0, pyy = 0, w = 0;
+      T zr_hat = 0, zb_hat = 0, i00 = 0, i01 = 0, i11 = 0, norm = 0, Pdw = 0;
+      T hp00 = 0, hp01 = 0, hp10 = 0, hp11 = 0;
+      if (m < nM) {
+        x = cur[m]; y = cur[W + m];
+        pxx = cur[2 * W + m]; pxy = cur[3 * W + m]; pyy = cur[4 * W + m];
+        w = cur[5 * W + m];
+        wsum_d += (double)w;
+        const T dx = x - px, dy = y - py;
+        const T r2 = dx * dx + dy * dy;
+        const T r = M<T>::sqrt_(r2);
+        // probabilityOfDetection (src/MeasurementModel_RngBrg.cpp:138-167) + Q2 override
+        T Pd;
+        bool close = false;
+        const bool inrange = (r <= p.rmax) && (r >= p.rmin);
+        if (inrange) {
+          Pd = p.Pd;
+          close = (r >= p.rmax - p.rbuf) || (r <= p.rmin + p.rbuf);
+        } else {
+          Pd = T(0);
+          close = (r <= p.rmax + p.rbuf) && (r >= p.rmin - p.rbuf);
+        }
+        if (close) Pd = T(1);
+        if (Pd != T(0)) nfov++;
+        // missed-detection weight (:686-706); the sensing-limit heuristic is patched in S4
+        cur[6 * W + m] = w;                       // weight_prev
+        cur[5 * W + m] = (T(1) - Pd) * w;
+        aux[m] = (close && (w > p.birth_w)) ? 1u : 0u;
+        if (Pd != T(0) && inrange) {              // measure() returns false outside [rmin,rmax]
+          const T invr = T(1) / r;
+          const T c = dx * invr, s = dy * invr;
+          const T h10 = -s * invr, h11 = c * invr;   // -dy/r^2, dx/r^2
+          zr_hat = r;
+          zb_hat = wrap_pi<T>(M<T>::atan2_(dy, dx) - pth);
+          hp00 = c * pxx + s * pxy;  hp01 = c * pxy + s * pyy;
+          hp10 = h10 * pxx + h11 * pxy;  hp11 = h10 * pxy + h11 * pyy;
+          T s00 = hp00 * c + hp01 * s + p.R00;
+          T s01 = hp00 * h10 + hp01 * h11 + p.R01;
+          T s11 = hp10 * h10 + hp11 * h11 + p.R11;
+          if (p.pose_cov_mode) {   // Hx Sigma_x Hx^T, Hx = [[-c,-s,0],[s/r,-c/r,-1]]  (Q1)
+            const T g0 = -c, g1 = -s, k0 = s * invr, k1 = -c * invr, k2 = T(-1);
+            const T a0 = g0 * c00 + g1 * c01, a1 = g0 * c01 + g1 * c11, a2 = g0 * c02 + g1 * c12;
+            const T b0 = k0 * c00 + k1 * c01 + k2 * c02, b1 = k0 * c01 + k1 * c11 + k2 * c12,
+                    b2 = k0 * c02 + k1 * c12 + k2 * c22;
+            s00 += a0 * g0 + a1 * g1;
+            s01 += a0 * k0 + a1 * k1 + a2 * k2;
+            s11 += b0 * k0 + b1 * k1 + b2 * k2;
+          }
+          const T det = s00 * s11 - s01 * s01;
+          const T invdet = T(1) / det;
+          i00 = s11 * invdet; i01 = -s01 * invdet; i11 = s00 * invdet;
+          norm = T(1) / M<T>::sqrt_(M<T>::TWO_PI * M<T>::TWO_PI * det);
+          Pdw = Pd * w;
+          const T cheap = p.gate2 * s00 * T(1.0001);  // md2 >= nu_r^2 / S_rr
+          for (int z = 0; z < nZ; z++) {
+            const T nr = zs[2 * z] - zr_hat;
+            if (nr * nr > cheap) continue;
+            if (p.thr_r > T(0) && M<T>::abs_(nr) > p.thr_r) continue;
+            const T nb_raw = zs[2 * z + 1] - zb_hat;
+            const T nb = wrap_pi<T>(nb_raw);
+            if (p.thr_b > T(0) && M<T>::abs_(nb) > p.thr_b) continue;
+            // Q3: likelihood and gate use the UNWRAPPED difference
+            const T md2 = (nr * i00 + nb_raw * i01) * nr + (nr * i01 + nb_raw * i11) * nb_raw;
+            if (md2 > p.gate2) continue;
+            T lik = M<T>::exp_(T(-0.5) * md2) * norm;
+            if (!(lik == lik) || lik == T(0)) continue;
+            if (!(Pdw * lik > T(0))) continue;
+            mask |= (1ull << z);
+          }
+        }
+      }
+      const int cnt = __popcll(mask);
+      const int incl = warp_incl_scan(cnt, lane);
+      int off = nM + nS + incl - cnt;
+      nS += __shfl_sync(FULL, incl, 31);
+      if (cnt) {
+        // K = P H^T S^-1 ; P+ = sym((I-KH)P)  (include/KalmanFilter.hpp:297-302)
+        const T k00 = hp00 * i00 + hp10 * i01, k01 = hp00 * i01 + hp10 * i11;
+        const T k10 = hp01 * i00 + hp11 * i01, k11 = hp01 * i01 + hp11 * i11;
+        const T n00 = pxx - (k00 * hp00 + k01 * hp10);
+        const T n01a = pxy - (k00 * hp01 + k01 * hp11);
+        const T n01b = pxy - (k10 * hp00 + k11 * hp10);
+        const T n11 = pyy - (k10 * hp01 + k11 * hp11);
+        const T n01 = (n01a + n01b) * T(0.5);
+        while (mask) {
+          const int z = __ffsll((long long)mask) - 1;
+          mask &= mask - 1;
+          if (off >= W) { over = true; break; }
+          const T nr = zs[2 * z] - zr_hat;
+          const T nb_raw = zs[2 * z + 1] - zb_hat;
+          const T nb = wrap_pi<T>(nb_raw);
+          const T md2 = (nr * i00 + nb_raw * i01) * nr + (nr * i01 + nb_raw * i11) * nb_raw;
+          const T lik = M<T>::exp_(T(-0.5) * md2) * norm;
+          cur[off] = x + (k00 * nr + k01 * nb);
+          cur[W + off] = y + (k10 * nr + k11 * nb);
+          cur[2 * W + off] = n00; cur[3 * W + off] = n01; cur[4 * W + off] = n11;
+          cur[5 * W + off] = Pdw * lik;   // un-normalised; divided by the column sum in S3
+          cur[6 * W + off] = T(0);
+          aux[off] = ((unsigned)m << 8) | (unsigned)z;
+          off++;
+        }
+      }
+    }
+    if (__any_sync(FULL, over)) flags |= FLAG_OVERFLOW;
+    if (nM + nS > W) nS = W - nM;
+    const int n = nM + nS;
+    nfov = warp_sum(nfov);
+    wsum_d = warp_sum(wsum_d);
+    __syncwarp();
+
+    double weight_new = w_prev_particle;
+    unsigned long long unused_mask = 0;
+    if (nM == 0) {
+      // :559-564 all measurements unused; SC weight untouched (Q10)
+      unused_mask = (nZ >= 64) ? ~0ull : ((1ull << nZ) - 1ull);
+    } else {
+      // ---------------- S2: per-measurement normalisers ------------------------------------
+      double ll = 0;
+      for (int zb0 = 0; zb0 < nZ; zb0 += 32) {
+        const int z = zb0 + lane;
+        bool used = false;
+        if (z < nZ) {
+          T sum = p.kappa;
+          for (int s = nM; s < n; s++) {
+            const unsigned u = aux[s];
+            if ((int)(u & 0xffu) == z) { sum += cur[5 * W + s]; used = true; }
+          }
+          colsum[z] = sum;
+          ll += log((double)sum);
+        }
+        const unsigned b = __ballot_sync(FULL, (z < nZ) && !used);
+        unused_mask |= ((unsigned long long)b) << zb0;
+      }
+      ll = warp_sum(ll);
+      __syncwarp();
+      if (p.use_sc) {  // :661-668 (Q4): exp(sum w) * prod_z(kappa + sum_m W) * w_prev
+        weight_new = exp(wsum_d + ll) * w_prev_particle;
+      }
+      // ---------------- S3: posterior weights of the new Gaussians --------------------------
+      for (int s = nM + lane; s < n; s += 32) {
+        const unsigned u = aux[s];
+        cur[5 * W + s] = cur[5 * W + s] / colsum[u & 0xffu];
+      }
+      __syncwarp();
+      // ---------------- S4: sensing-limit heuristic (:692-703, Q2) --------------------------
+      for (int m = lane; m < nM; m += 32) {
+        if (aux[m] & 1u) {
+          const T w_km = cur[6 * W + m];
+          T rowsum = T(0);
+          for (int s = nM; s < n; s++)
+            if ((int)(aux[s] >> 8) == m) rowsum += cur[5 * W + s];
+          const T delta = w_km - rowsum;   // Pd[m] == 1 here
+          T w_k = cur[5 * W + m];
+          if (delta > T(0)) {
+            w_k += delta;
+            if (w_k > T(1)) w_k = T(1);
+          }
+          cur[5 * W + m] = w_k;
+        }
+      }
+      __syncwarp();
+    }
+
+    // ---------------- S5: multi-feature importance weighting ----------------------------------
+    if (!p.use_sc) {
+      int nEvalCfg = p.n_eval < n ? p.n_eval : n;
+      if (nEvalCfg == 0) {
+        weight_new = 4.9406564584124654e-324;  // denorm_min (:742-745, Q10)
+      } else {
+        // sortByWeight (:746): weight descending, ties by position
+        {
+          T* kw = alt + 6 * W;
+          const int P = next_pow2(n);
+          for (int k = lane; k < P; k += 32) {
+            kw[k] = (k < n) ? cur[5 * W + k] : -M<T>::inf();
+            aux[k] = (unsigned)k;
+          }
+          __syncwarp();
+          warp_bitonic(kw, aux, P, lane);
+          for (int pl = 0; pl < 6; pl++)
+            for (int k = lane; k < n; k += 32) alt[pl * W + k] = cur[pl * W + aux[k]];
+          __syncwarp();
+          for (int k = lane; k < n; k += 32) alt[6 * W + k] = cur[6 * W + aux[k]];
+          __syncwarp();
+          T* t = cur; cur = alt; alt = t;
+        }
+        // eval points (:747-762): sorted order, w >= min weight, raw Pd > 0, first nEvalCfg
+        int nE = 0;
+        for (int base = 0; base < n && nE < nEvalCfg; base += 32) {
+          const int m = base + lane;
+          bool elig = false;
+          bool heavy = false;
+          if (m < n) {
+            heavy = !(cur[5 * W + m] < p.eval_min_w);
+            if (heavy) {
+              const T dx = cur[m] - px, dy = cur[W + m] - py;
+              const T r = M<T>::sqrt_(dx * dx + dy * dy);
+              elig = (r <= p.rmax) && (r >= p.rmin) && (p.Pd > T(0));
+            }
+          }
+          const unsigned be = __ballot_sync(FULL, elig);
+          const int rank = nE + __popc(be & ((1u << lane) - 1u));
+          if (elig && rank < nEvalCfg) evalIdx[rank] = m;
+          nE += __popc(be);
+          if (!__all_sync(FULL, heavy)) break;
+        }
+        if (nE > nEvalCfg) nE = nEvalCfg;
+        __syncwarp();
+        // sums of weights (:765-773)
+        double sw_prev = 0, sw_now = 0;
+        for (int m = lane; m < n; m += 32) { sw_prev += (double)cur[6 * W + m]; sw_now += (double)cur[5 * W + m]; }
+        sw_prev = warp_sum(sw_prev);
+        sw_now = warp_sum(sw_now);
+        // intensity at the eval points before / after the update (:776-800), log domain
+        T* ia = alt;            // inverse covariance + log pdf factor + log weights of every component
+        for (int m = lane; m < n; m += 32) {
+          T a = cur[2 * W + m], b = cur[3 * W + m], c = cur[4 * W + m];
+          T det = a * c - b * b;
+          T invdet = T(1) / det;
+          ia[m] = c * invdet; ia[W + m] = -b * invdet; ia[2 * W + m] = a * invdet;
+          ia[3 * W + m] = M<T>::log_(M<T>::TWO_PI * M<T>::sqrt_(det));
+          ia[4 * W + m] = M<T>::log_(cur[6 * W + m]);   // log w_prev (-inf for new Gaussians)
+          ia[5 * W + m] = M<T>::log_(cur[5 * W + m]);   // log w
+        }
+        __syncwarp();
+        double lp_before = 0, lp_after = 0;
+        const T CUT = sizeof(T) == 4 ? T(25) : T(45);
+        const T LOG_DENORM_MIN = T(-744.4400719213812);
+        for (int e = 0; e < nE; e++) {
+          const int ei = evalIdx[e];
+          const T xe = cur[ei], ye = cur[W + ei];
+          T mb = -M<T>::inf(), sb = 0, ma = -M<T>::inf(), sa = 0;
+          for (int m = lane; m < n; m += 32) {
+            const T dx = xe - cur[m], dy = ye - cur[W + m];
+            const T md2 = (dx * ia[m] + dy * ia[W + m]) * dx + (dx * ia[W + m] + dy * ia[2 * W + m]) * dy;
+            const T t = T(-0.5) * md2 - ia[3 * W + m];
+            const T lb = ia[4 * W + m] + t, la = ia[5 * W + m] + t;
+            if (lb > mb) { sb = sb * M<T>::exp_(mb - lb) + T(1); mb = lb; }
+            else if (lb > mb - CUT) sb += M<T>::exp_(lb - mb);
+            if (la > ma) { sa = sa * M<T>::exp_(ma - la) + T(1); ma = la; }
+            else if (la > ma - CUT) sa += M<T>::exp_(la - ma);
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            T mo = __shfl_xor_sync(FULL, mb, o), so = __shfl_xor_sync(FULL, sb, o);
+            T mx = mo > mb ? mo : mb;
+            if (mx > -M<T>::inf()) { sb = sb * M<T>::exp_(mb - mx) + so * M<T>::exp_(mo - mx); }
+            mb = mx;
+            mo = __shfl_xor_sync(FULL, ma, o); so = __shfl_xor_sync(FULL, sa, o);
+            mx = mo > ma ? mo : ma;
+            if (mx > -M<T>::inf()) { sa = sa * M<T>::exp_(ma - mx) + so * M<T>::exp_(mo - mx); }
+            ma = mx;
+          }
+          T lvb = (mb > -M<T>::inf()) ? mb + M<T>::log_(sb) : LOG_DENORM_MIN;
+          T lva = (ma > -M<T>::inf()) ? ma + M<T>::log_(sa) : LOG_DENORM_MIN;
+          if (lvb < LOG_DENORM_MIN) lvb = LOG_DENORM_MIN;
+          if (lva < LOG_DENORM_MIN) lva = LOG_DENORM_MIN;
+          lp_before += (double)lvb;
+          lp_after += (double)lva;
+        }
+        __syncwarp();
+        // rfsMeasurementLikelihood (:821-997): L table with the landmark covariance zeroed
+        T* ep = alt;                    // [MAX_EVAL][8]: zr, zb, i00, i01, i11, Pd*norm, Pd
+        T* L = alt + MAX_EVAL * 8;      // [nE][nZ]
+        unsigned long long* rowmask = reinterpret_cast<unsigned long long*>(L + ((nE * nZ + 3) & ~3));  // [MAX_EVAL]
+        unsigned* compR = reinterpret_cast<unsigned*>(rowmask + MAX_EVAL);          // [MAX_COMP]
+        unsigned long long* compC = reinterpret_cast<unsigned long long*>(compR + MAX_COMP);  // [MAX_COMP]
+        double* f0 = reinterpret_cast<double*>(compC + MAX_COMP);                   // [1<<DP_MAXB]
+        double* f1 = f0 + (1 << DP_MAXB);
+        T* evalPd = ep + MAX_EVAL * 7;  // stride-1 array of Pd per eval point (slot 7 of the ep block region)
+        if (lane < nE) {
+          const int ei = evalIdx[lane];
+          const T dx = cur[ei] - px, dy = cur[W + ei] - py;
+          const T r2 = dx * dx + dy * dy;
+          const T r = M<T>::sqrt_(r2);
+          const T invr = T(1) / r;
+          const T c = dx * invr, s = dy * invr;
+          T s00 = p.R00, s01 = p.R01, s11 = p.R11;
+          if (p.pose_cov_mode) {
+            const T g0 = -c, g1 = -s, k0 = s * invr, k1 = -c * invr, k2 = T(-1);
+            const T a0 = g0 * c00 + g1 * c01, a1 = g0 * c01 + g1 * c11, a2 = g0 * c02 + g1 * c12;
+            const T b0 = k0 * c00 + k1 * c01 + k2 * c02, b1 = k0 * c01 + k1 * c11 + k2 * c12,
+                    b2 = k0 * c02 + k1 * c12 + k2 * c22;
+            s00 += a0 * g0 + a1 * g1;
+            s01 += a0 * k0 + a1 * k1 + a2 * k2;
+            s11 += b0 * k0 + b1 * k1 + b2 * k2;
+          }
+          const T det = s00 * s11 - s01 * s01;
+          const T invdet = T(1) / det;
+          ep[lane * 7 + 0] = r;
+          ep[lane * 7 + 1] = wrap_pi<T>(M<T>::atan2_(dy, dx) - pth);
+          ep[lane * 7 + 2] = s11 * invdet;
+          ep[lane * 7 + 3] = -s01 * invdet;
+          ep[lane * 7 + 4] = s00 * invdet;
+          ep[lane * 7 + 5] = p.Pd / M<T>::sqrt_(M<T>::TWO_PI * M<T>::TWO_PI * det);
+          evalPd[lane] = p.Pd;   // raw model Pd of an in-range landmark (Q12)
+        }
+        __syncwarp();
+        for (int k = lane; k < nE * nZ; k += 32) {
+          const int e = k / nZ, z = k - e * nZ;
+          const T nr = zs[2 * z] - ep[e * 7], nb = zs[2 * z + 1] - ep[e * 7 + 1];
+          const T j00 = ep[e * 7 + 2], j01 = ep[e * 7 + 3], j11 = ep[e * 7 + 4];
+          const T md2 = (nr * j00 + nb * j01) * nr + (nr * j01 + nb * j11) * nb;
+          T l = M<T>::exp_(T(-0.5) * md2) * ep[e * 7 + 5];
+          if (!(l == l)) l = T(0);
+          if (md2 > p.wl_gate2) l = T(0);
+          L[k] = l;
+        }
+        __syncwarp();
+        if (lane < nE) {
+          unsigned long long rm = 0;
+          for (int z = 0; z < nZ; z++) if (L[lane * nZ + z] != T(0)) rm |= (1ull << z);
+          rowmask[lane] = rm;
+        }
+        __syncwarp();
+        // connected components, numbered by lowest vertex (rows first, then columns) like
+        // boost::connected_components (src/CostMatrix.cpp:98-109). Computed redundantly by all lanes.
+        int ncc = 0;
+        {
+          unsigned doneR = 0;
+          unsigned long long doneC = 0;
+          for (int v = 0; v < nE + nZ; v++) {
+            unsigned cr = 0;
+            unsigned long long cc = 0;
+            if (v < nE) { if ((doneR >> v) & 1u) continue; cr = 1u << v; }
+            else { const int z = v - nE; if ((doneC >> z) & 1ull) continue; cc = 1ull << z; }
+            if (v < nE) {
+              bool grow = true;
+              while (grow) {
+                grow = false;
+                unsigned m = cr;
+                unsigned long long nc = cc;
+                while (m) { const int r = __ffs(m) - 1; m &= m - 1; nc |= rowmask[r]; }
+                unsigned nr = cr;
+                for (int r = 0; r < nE; r++) if (rowmask[r] & nc) nr |= 1u << r;
+                if (nr != cr || nc != cc) { cr = nr; cc = nc; grow = true; }
+              }
+            }
+            // a column reached here is isolated (otherwise a row would have claimed it already)
+            doneR |= cr; doneC |= cc;
+            if (ncc < MAX_COMP && lane == 0) { compR[ncc] = cr; compC[ncc] = cc; }
+            ncc++;
+          }
+        }
+        __syncwarp();
+        // CostMatrixGeneral::partition (:111-144): one-sided components fold into the first one
+        int combinedZero = -1, nMerged = 0;
+        unsigned zeroR = 0;
+        unsigned long long zeroC = 0;
+        for (int c = 0; c < ncc; c++) {
+          const unsigned cr = compR[c];
+          const unsigned long long cc = compC[c];
+          if (cr == 0 || cc == 0) {
+            if (combinedZero == -1) { combinedZero = c; zeroR = cr; zeroC = cc; }
+            else { zeroR |= cr; zeroC |= cc; nMerged++; }
+          }
+        }
+        const int nP = ncc - nMerged;
+        double logL = 0;
+        for (int pp = 0; pp < nP; pp++) {   // Q6: original labels, only p < nP are visited
+          double pl;
+          if (pp == combinedZero) {   // :891-900 (Q5: Pd, not 1-Pd)
+            pl = 0;  // log domain here
+            unsigned m = zeroR;
+            while (m) { const int r = __ffs(m) - 1; m &= m - 1; pl += log((double)evalPd[r]); }
+            pl += (double)__popcll(zeroC) * p.log_kappa;
+            logL += pl;
+          } else {
+            const unsigned cr = compR[pp];
+            const unsigned long long cc = compC[pp];
+            const int nR = __popc(cr), nC = __popcll(cc);
+            if (nR + nC > 8) flags |= FLAG_MURTY;
+            const int b = nR < nC ? nR : nC;
+            if (b > DP_MAXB) { flags |= FLAG_DP_OVERFLOW; continue; }
+            if (p.sum_method == 1 && nR + nC <= 12) {
+              // MatPerm path: sum = (prod kappa) * perm([[L/kappa, diag(1-Pd)],[ones]]) / nC!
+              const int nn = nR + nC;
+              double* Am = f0;   // nn*nn <= 144 doubles  (f0/f1 hold 256)
+              int ridx[12], cidx[12];
+              { int k = 0; unsigned m = cr; while (m) { ridx[k++] = __ffs(m) - 1; m &= m - 1; }
+                k = 0; unsigned long long mc = cc; while (mc) { cidx[k++] = __ffsll((long long)mc) - 1; mc &= mc - 1; } }
+              const double kap = exp(p.log_kappa);
+              for (int k = lane; k < nn * nn; k += 32) {
+                const int r = k / nn, c = k - r * nn;
+                double v;
+                if (r < nR) {
+                  if (c < nC) v = (double)L[ridx[r] * nZ + cidx[c]] / kap;
+                  else v = (c - nC == r) ? 1.0 - (double)evalPd[ridx[r]] : 0.0;
+                } else v = 1.0;
+                Am[k] = v;
+              }
+              __syncwarp();
+              double perm = warp_permanent(Am, nn, lane);
+              double fact = 1; for (int k = 2; k <= nC; k++) fact *= k;
+              pl = perm / fact;
+              logL += log(pl) + (double)nC * p.log_kappa;
+              __syncwarp();
+            } else {
+              pl = partition_dp<T>(L, nZ, cr, cc, evalPd, exp(p.log_kappa), f0, f1, lane);
+              logL += log(pl);
+            }
+          }
+        }
+        logL -= p.log_clutter_integral;
+        // :808-812
+        weight_new = exp(logL + (lp_before - lp_after) + (sw_now - sw_prev)) * w_prev_particle;
+        __syncwarp();
+      }
+    }
+
+    // ---------------- S6: merge ------------------------------------------------------------------
+    if (n > 1) {
+      if (p.merge_algo == 0) merge_bruteforce<T>(cur, W, n, p.merge_t2, p.merge_f, lane);
+      else merge_culled<T>(cur, alt, W, n, p.merge_t2, p.merge_f, lane);
+    }
+    __syncwarp();
+
+    // ---------------- S7: prune + store ------------------------------------------------------------
+    int n_out = 0;
+    {
+      T* kw = alt + 6 * W;
+      for (int base = 0; base < n; base += 32) {
+        const int k = base + lane;
+        bool keep = false;
+        T w = 0;
+        if (k < n) { w = cur[5 * W + k]; keep = (w >= p.prune_t) && (w >= T(0)); }
+        const unsigned b = __ballot_sync(FULL, keep);
+        if (keep) {
+          const int pos = n_out + __popc(b & ((1u << lane) - 1u));
+          kw[pos] = w;
+          aux[pos] = (unsigned)k;
+        }
+        n_out += __popc(b);
+      }
+      const int P = next_pow2(n_out);
+      for (int k = n_out + lane; k < P; k += 32) { kw[k] = -M<T>::inf(); aux[k] = 0xffffffffu; }
+      __syncwarp();
+      if (n_out > 1) warp_bitonic(kw, aux, P, lane);
+      if (n_out > p.cap) { n_out = p.cap; flags |= FLAG_OVERFLOW; }
+      for (int pl = 0; pl < 6; pl++)
+        for (int k = lane; k < n_out; k += 32) alt[pl * W + k] = cur[pl * W + aux[k]];
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0 && n_out > 0) {
+        const uint32_t bytes = (uint32_t)(((n_out + 3) & ~3) * sizeof(T));
+        T* dst = p.gm_out + (size_t)pi * 6 * p.cap;
+#pragma unroll
+        for (int k = 0; k < 6; k++) tma_store_1d(dst + (size_t)k * p.cap, alt + k * W, bytes);
+        tma_store_commit();
+      }
+    }
+    if (lane == 0) {
+      p.cnt_out[pi] = n_out;
+      p.w_out[pi] = weight_new;
+      p.unused[pi] = unused_mask;
+      p.nfov[pi] = nfov;
+      p.flags[pi] = flags;
+    }
+    tot_in += (unsigned long long)nM;
+    tot_out += (unsigned long long)n_out;
+    max_out = n_out > max_out ? n_out : max_out;
+    if (flags & (FLAG_OVERFLOW | FLAG_DP_OVERFLOW)) n_over++;
+    if (flags & FLAG_MURTY) n_murty++;
+    // note: bufA/bufB roles are fixed per iteration start (cur=bufA); the store reads `alt`,
+    // which may be bufA or bufB, so the wait at the top of the loop covers both.
+  }
+  if (lane == 0) {
+    tma_store_wait_all();
+    if (tot_in) atomicAdd(&p.totals[0], tot_in);
+    if (tot_out) atomicAdd(&p.totals[1], tot_out);
+    atomicMax(&p.istats[0], max_out);
+    if (n_over) atomicAdd(&p.istats[1], n_over);
+    if (n_murty) atomicAdd(&p.istats[2], n_murty);
+  }
+
+  // ---------------- S8: deterministic [sum w, sum w^2] by the last CTA ----------------------------
+  __shared__ bool is_last;
+  __shared__ double red[2][WARPS_PER_CTA];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned t = atomicAdd(p.ticket, 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    double s1 = 0, s2 = 0;
+    for (int i = threadIdx.x; i < p.N; i += blockDim.x) {
+      const double w = __ldcg(p.w_out + i);
+      s1 += w;
+      s2 += w * w;
+    }
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    if (lane == 0) { red[0][warp] = s1; red[1][warp] = s2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double a = 0, b = 0;
+      for (int k = 0; k < WARPS_PER_CTA; k++) { a += red[0][k]; b += red[1][k]; }
+      p.sums[0] = a;
+      p.sums[1] = b;
+      *p.ticket = 0;
+    }
+  }
+}
+
+// w_i /= sum  (ParticleFilter::normalizeWeights, include/ParticleFilter.hpp:352-363)
+__global__ void normalize_kernel(double* w, const double* sums, int N) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) w[i] = w[i] / sums[0];
+}
+
+}  // namespace rfsb200

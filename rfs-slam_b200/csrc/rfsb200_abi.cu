@@ -1,0 +1,665 @@
+// rfsb200_abi.cu — extern "C" entry points of include/rfsb200.h.
+// Host side of the drop-in boundary: owns device state (particle-major SoA in HBM), converts the
+// reference's fp64 host representation to the device layout on the GPU, launches the fused update
+// kernel (phd_kernels.cuh) and serves state reads.  There is no CPU fallback anywhere in here.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/rfsb200.h"
+#include "phd_kernels.cuh"
+
+using namespace rfsb200;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+struct StateBuf {
+  void* gm = nullptr;       // T [N][6][cap]
+  int* cnt = nullptr;       // [N]
+  double* weight = nullptr; // [N]
+};
+
+}  // namespace
+
+struct rfsb200_ctx {
+  rfsb200_dims dims{};
+  int N = 0, cap = 0, W = 0, prec = 32;
+  size_t tsize = 4;
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  StateBuf st[2];
+  int front = 0;     // committed state
+  int last_out = 0;  // buffer written by the last update (== front unless NO_COMMIT)
+  void* pose = nullptr;      // T [N][4]
+  void* pose_cov = nullptr;  // T [N][8]
+  int pose_cov_mode = 0;
+  void* Zdev = nullptr;      // T [64][2]
+  unsigned long long* unused = nullptr;
+  int* nfov = nullptr;
+  int* flags = nullptr;
+  double* sums = nullptr;                 // [2]
+  unsigned long long* totals = nullptr;   // [2]
+  int* istats = nullptr;                  // [4]
+  unsigned int* ticket = nullptr;
+  // staging (device): packed fp64 + offsets
+  double* stg = nullptr;       // N*cap*6 doubles
+  long long* offs = nullptr;   // [N+1]
+  double* stg_small = nullptr; // N*16 doubles (poses, covs, weights)
+  // pinned host scratch
+  unsigned char* hpin = nullptr;
+  size_t hpin_bytes = 0;
+  bool have_model = false, have_cfg = false, have_maps = false, have_poses = false;
+  rfsb200_model_desc model{};
+  rfsb200_filter_cfg cfg{};
+  int merge_algo = 1;
+  int grid = 0;
+  size_t smem_bytes = 0;
+  int warp_bytes = 0;
+  std::string err;
+};
+
+namespace {
+
+int fail(rfsb200_ctx* ctx, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (ctx) ctx->err = buf;
+  g_last_error = buf;
+  return code;
+}
+
+#define CU(ctx, call)                                                                         \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess)                                                                    \
+      return fail(ctx, RFSB200_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                  __FILE__, __LINE__);                                                        \
+  } while (0)
+
+// ---- layout conversion kernels (device side of upload / download) ------------------------------
+// packed fp64 (mean[k][2], cov[k][3], w[k]) -> particle-major SoA planes of T. One warp per particle.
+template <typename T>
+__global__ void pack_soa_kernel(const int* __restrict__ cnt, const long long* __restrict__ offs,
+                                const double* __restrict__ mean, const double* __restrict__ cov,
+                                const double* __restrict__ w, T* __restrict__ gm, int N, int cap) {
+  const int lane = threadIdx.x & 31;
+  const int pi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (pi >= N) return;
+  const int n = cnt[pi];
+  const long long o = offs[pi];
+  T* g = gm + (size_t)pi * 6 * cap;
+  for (int k = lane; k < n; k += 32) {
+    const long long s = o + k;
+    g[k] = (T)mean[2 * s];
+    g[cap + k] = (T)mean[2 * s + 1];
+    g[2 * cap + k] = (T)cov[3 * s];
+    g[3 * cap + k] = (T)cov[3 * s + 1];
+    g[4 * cap + k] = (T)cov[3 * s + 2];
+    g[5 * cap + k] = (T)w[s];
+  }
+}
+
+template <typename T>
+__global__ void unpack_soa_kernel(const int* __restrict__ cnt, const long long* __restrict__ offs,
+                                  const T* __restrict__ gm, double* __restrict__ mean,
+                                  double* __restrict__ cov, double* __restrict__ w, int N, int cap) {
+  const int lane = threadIdx.x & 31;
+  const int pi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (pi >= N) return;
+  const int n = cnt[pi];
+  const long long o = offs[pi];
+  const T* g = gm + (size_t)pi * 6 * cap;
+  for (int k = lane; k < n; k += 32) {
+    const long long s = o + k;
+    mean[2 * s] = (double)g[k];
+    mean[2 * s + 1] = (double)g[cap + k];
+    cov[3 * s] = (double)g[2 * cap + k];
+    cov[3 * s + 1] = (double)g[3 * cap + k];
+    cov[3 * s + 2] = (double)g[4 * cap + k];
+    w[s] = (double)g[5 * cap + k];
+  }
+}
+
+// exclusive scan of counts -> offsets[N+1]; single CTA (N is at most a few 10^5)
+__global__ void scan_counts_kernel(const int* __restrict__ cnt, long long* __restrict__ offs, int N) {
+  __shared__ long long part[1024];
+  const int t = threadIdx.x, nt = blockDim.x;
+  const int per = (N + nt - 1) / nt;
+  const int lo = t * per, hi = min(N, lo + per);
+  long long s = 0;
+  for (int i = lo; i < hi; i++) s += cnt[i];
+  part[t] = s;
+  __syncthreads();
+  if (t == 0) {
+    long long run = 0;
+    for (int i = 0; i < nt; i++) { long long v = part[i]; part[i] = run; run += v; }
+    offs[N] = run;
+  }
+  __syncthreads();
+  long long run = part[t];
+  for (int i = lo; i < hi; i++) { offs[i] = run; run += cnt[i]; }
+}
+
+template <typename T>
+__global__ void pose_convert_kernel(const double* __restrict__ pose, const double* __restrict__ pcov,
+                                    int mode, T* __restrict__ pose_out, T* __restrict__ pcov_out, int N) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) {
+    pose_out[4 * i] = (T)pose[3 * i];
+    pose_out[4 * i + 1] = (T)pose[3 * i + 1];
+    pose_out[4 * i + 2] = (T)pose[3 * i + 2];
+    pose_out[4 * i + 3] = T(0);
+    if (mode == 2) {
+      for (int k = 0; k < 6; k++) pcov_out[8 * i + k] = (T)pcov[6 * i + k];
+      pcov_out[8 * i + 6] = pcov_out[8 * i + 7] = T(0);
+    }
+  }
+  if (mode == 1 && i == 0) {
+    for (int k = 0; k < 6; k++) pcov_out[k] = (T)pcov[k];
+    pcov_out[6] = pcov_out[7] = T(0);
+  }
+}
+
+// rfs::MatPerm::calc for a batch: one warp per matrix
+__global__ void permanent_kernel(const double* __restrict__ A, int n, int batch, double* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (b >= batch) return;
+  const double r = warp_permanent(A + (size_t)b * n * n, n, lane);
+  if (lane == 0) out[b] = r;
+}
+
+int round_pow2(int v) {
+  int p = 32;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+template <typename T>
+int warp_smem_bytes(int W) {
+  size_t b = (size_t)14 * W * sizeof(T) + (size_t)W * 4 + MAX_Z * sizeof(T) + MAX_EVAL * 4 + 16;
+  return (int)((b + 127) & ~(size_t)127);
+}
+
+template <typename T>
+int configure_launch(rfsb200_ctx* c) {
+  c->warp_bytes = warp_smem_bytes<T>(c->W);
+  c->smem_bytes = 2 * MAX_Z * sizeof(T) + (size_t)WARPS_PER_CTA * c->warp_bytes;
+  // scratch requirements inside one 7*W plane block
+  const size_t blk = (size_t)7 * c->W * sizeof(T);
+  const size_t merge_need = (size_t)c->W * sizeof(T) + MAX_PAIRS * 4 + 2 * 258 * 2 + (size_t)(c->W + 2) * 2 + 8;
+  if (merge_need > blk) return fail(c, RFSB200_EINVAL, "work_capacity too small for merge scratch");
+  if (c->smem_bytes > 227 * 1024) return fail(c, RFSB200_ECAPACITY, "work_capacity %d needs %zu B shared memory per CTA (> 227 KB)", c->W, c->smem_bytes);
+  CU(c, cudaFuncSetAttribute(phd_update_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
+  int occ = 0;
+  CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, phd_update_kernel<T>, WARPS_PER_CTA * 32, c->smem_bytes));
+  if (occ < 1) return fail(c, RFSB200_ECAPACITY, "kernel does not fit on an SM");
+  const int need = (c->N + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+  c->grid = std::max(1, std::min(need, occ * c->sm_count));
+  return RFSB200_OK;
+}
+
+template <typename T>
+int launch_update(rfsb200_ctx* c, int nZ, int out_idx) {
+  KParams<T> p{};
+  const rfsb200_model_desc& m = c->model;
+  const rfsb200_filter_cfg& f = c->cfg;
+  p.R00 = (T)m.R[0]; p.R01 = (T)m.R[1]; p.R11 = (T)m.R[3];
+  p.Pd = (T)m.Pd; p.kappa = (T)m.clutter_intensity;
+  p.rmin = (T)m.range_min; p.rmax = (T)m.range_max; p.rbuf = (T)m.range_buffer;
+  p.thr_r = (T)m.innov_thr_range; p.thr_b = (T)m.innov_thr_bearing;
+  p.birth_w = (T)f.birth_gaussian_weight;
+  p.gate2 = (T)(f.new_gaussian_create_innov_md_threshold * f.new_gaussian_create_innov_md_threshold);
+  p.eval_min_w = (T)f.eval_point_gaussian_weight;
+  p.wl_gate2 = (T)(f.meas_likelihood_md_threshold * f.meas_likelihood_md_threshold);
+  p.merge_t2 = (T)(f.merging_threshold * f.merging_threshold);
+  p.merge_f = (T)f.merging_cov_inflation_factor;
+  p.prune_t = (T)f.pruning_threshold;
+  p.n_eval = f.eval_point_count; p.use_sc = f.use_cluster_process ? 1 : 0;
+  p.sum_method = f.assignment_sum_method; p.merge_algo = c->merge_algo;
+  p.log_clutter_integral = log(m.clutter_integral);
+  p.log_kappa = log(m.clutter_intensity);
+  p.N = c->N; p.cap = c->cap; p.W = c->W; p.nZ = nZ; p.pose_cov_mode = c->pose_cov_mode;
+  p.warp_bytes = c->warp_bytes;
+  const StateBuf& in = c->st[c->front];
+  const StateBuf& out = c->st[out_idx];
+  p.gm_in = (const T*)in.gm; p.cnt_in = in.cnt; p.w_in = in.weight;
+  p.pose = (const T*)c->pose; p.pose_cov = (const T*)c->pose_cov; p.Z = (const T*)c->Zdev;
+  p.gm_out = (T*)out.gm; p.cnt_out = out.cnt; p.w_out = out.weight;
+  p.unused = c->unused; p.nfov = c->nfov; p.flags = c->flags;
+  p.sums = c->sums; p.totals = c->totals; p.istats = c->istats; p.ticket = c->ticket;
+  phd_update_kernel<T><<<c->grid, WARPS_PER_CTA * 32, c->smem_bytes, c->stream>>>(p);
+  CU(c, cudaGetLastError());
+  return RFSB200_OK;
+}
+
+int ensure_pinned(rfsb200_ctx* c, size_t bytes) {
+  if (c->hpin_bytes >= bytes) return RFSB200_OK;
+  if (c->hpin) cudaFreeHost(c->hpin);
+  c->hpin = nullptr;
+  c->hpin_bytes = 0;
+  CU(c, cudaMallocHost((void**)&c->hpin, bytes));
+  c->hpin_bytes = bytes;
+  return RFSB200_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+int rfsb200_abi_version(void) { return RFSB200_ABI_VERSION; }
+
+int rfsb200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+const char* rfsb200_last_error(const rfsb200_ctx* ctx) {
+  if (ctx) return ctx->err.c_str();
+  return g_last_error.c_str();
+}
+
+int rfsb200_create(rfsb200_ctx** out, const rfsb200_dims* d) {
+  if (!out || !d) return fail(nullptr, RFSB200_EINVAL, "rfsb200_create: NULL argument");
+  *out = nullptr;
+  if (d->n_particles <= 0 || d->gm_capacity <= 0 || d->gm_capacity > 1024 || d->work_capacity > 1024 ||
+      d->z_capacity <= 0 || d->z_capacity > MAX_Z)
+    return fail(nullptr, RFSB200_EINVAL, "rfsb200_create: sizes out of range");
+  if (d->lmk_dim != 2 || d->meas_dim != 2 || d->pose_dim != 3)
+    return fail(nullptr, RFSB200_EUNSUPPORTED, "only 2-D landmarks / 2-D measurements / 3-D poses are implemented");
+  if (d->precision != 32 && d->precision != 64)
+    return fail(nullptr, RFSB200_EINVAL, "precision must be 32 or 64");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(nullptr, RFSB200_ENODEVICE, "no CUDA device: the PHD update path has no CPU fallback");
+  if (d->device < 0 || d->device >= ndev) return fail(nullptr, RFSB200_EINVAL, "bad device ordinal %d", d->device);
+  rfsb200_ctx* c = new (std::nothrow) rfsb200_ctx();
+  if (!c) return fail(nullptr, RFSB200_ENOMEM, "out of host memory");
+  c->dims = *d;
+  c->N = d->n_particles;
+  c->cap = (d->gm_capacity + 7) & ~7;
+  c->W = round_pow2(std::max(d->work_capacity, c->cap));
+  c->prec = d->precision;
+  c->tsize = d->precision == 32 ? 4 : 8;
+  c->device = d->device;
+  int rc = RFSB200_OK;
+  auto body = [&]() -> int {
+    CU(c, cudaSetDevice(c->device));
+    cudaDeviceProp prop;
+    CU(c, cudaGetDeviceProperties(&prop, c->device));
+    c->sm_count = prop.multiProcessorCount;
+    if (prop.major < 10)
+      return fail(c, RFSB200_EUNSUPPORTED, "device sm_%d%d is not Blackwell (built for sm_100a only)", prop.major, prop.minor);
+    CU(c, cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
+    CU(c, cudaEventCreate(&c->ev0));
+    CU(c, cudaEventCreate(&c->ev1));
+    const size_t gm_bytes = (size_t)c->N * 6 * c->cap * c->tsize;
+    for (int k = 0; k < 2; k++) {
+      CU(c, cudaMalloc(&c->st[k].gm, gm_bytes));
+      CU(c, cudaMemset(c->st[k].gm, 0, gm_bytes));
+      CU(c, cudaMalloc((void**)&c->st[k].cnt, (size_t)c->N * 4));
+      CU(c, cudaMemset(c->st[k].cnt, 0, (size_t)c->N * 4));
+      CU(c, cudaMalloc((void**)&c->st[k].weight, (size_t)c->N * 8));
+      CU(c, cudaMemset(c->st[k].weight, 0, (size_t)c->N * 8));
+    }
+    CU(c, cudaMalloc(&c->pose, (size_t)c->N * 4 * c->tsize));
+    CU(c, cudaMalloc(&c->pose_cov, (size_t)c->N * 8 * c->tsize));
+    CU(c, cudaMemset(c->pose_cov, 0, (size_t)c->N * 8 * c->tsize));
+    CU(c, cudaMalloc(&c->Zdev, (size_t)MAX_Z * 2 * c->tsize));
+    CU(c, cudaMalloc((void**)&c->unused, (size_t)c->N * 8));
+    CU(c, cudaMalloc((void**)&c->nfov, (size_t)c->N * 4));
+    CU(c, cudaMalloc((void**)&c->flags, (size_t)c->N * 4));
+    CU(c, cudaMemset(c->unused, 0, (size_t)c->N * 8));
+    CU(c, cudaMemset(c->nfov, 0, (size_t)c->N * 4));
+    CU(c, cudaMemset(c->flags, 0, (size_t)c->N * 4));
+    CU(c, cudaMalloc((void**)&c->sums, 16));
+    CU(c, cudaMalloc((void**)&c->totals, 16));
+    CU(c, cudaMalloc((void**)&c->istats, 16));
+    CU(c, cudaMalloc((void**)&c->ticket, 4));
+    CU(c, cudaMemset(c->sums, 0, 16));
+    CU(c, cudaMemset(c->ticket, 0, 4));
+    CU(c, cudaMalloc((void**)&c->stg, (size_t)c->N * c->cap * 6 * 8));
+    CU(c, cudaMalloc((void**)&c->offs, (size_t)(c->N + 1) * 8));
+    CU(c, cudaMalloc((void**)&c->stg_small, (size_t)c->N * 16 * 8));
+    int r = ensure_pinned(c, 1 << 16);
+    if (r) return r;
+    if (c->prec == 32) r = configure_launch<float>(c);
+    else r = configure_launch<double>(c);
+    if (r) return r;
+    CU(c, cudaDeviceSynchronize());
+    return RFSB200_OK;
+  };
+  rc = body();
+  if (rc != RFSB200_OK) {
+    g_last_error = c->err;
+    rfsb200_destroy(c);
+    return rc;
+  }
+  *out = c;
+  return RFSB200_OK;
+}
+
+int rfsb200_destroy(rfsb200_ctx* c) {
+  if (!c) return RFSB200_OK;
+  cudaSetDevice(c->device);
+  if (c->own_stream) cudaStreamSynchronize(c->own_stream);
+  for (int k = 0; k < 2; k++) {
+    cudaFree(c->st[k].gm); cudaFree(c->st[k].cnt); cudaFree(c->st[k].weight);
+  }
+  cudaFree(c->pose); cudaFree(c->pose_cov); cudaFree(c->Zdev);
+  cudaFree(c->unused); cudaFree(c->nfov); cudaFree(c->flags);
+  cudaFree(c->sums); cudaFree(c->totals); cudaFree(c->istats); cudaFree(c->ticket);
+  cudaFree(c->stg); cudaFree(c->offs); cudaFree(c->stg_small);
+  if (c->hpin) cudaFreeHost(c->hpin);
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  delete c;
+  return RFSB200_OK;
+}
+
+int rfsb200_set_stream(rfsb200_ctx* c, void* s) {
+  if (!c) return fail(nullptr, RFSB200_EINVAL, "NULL ctx");
+  c->stream = s ? (cudaStream_t)s : c->own_stream;
+  return RFSB200_OK;
+}
+
+int rfsb200_synchronize(rfsb200_ctx* c) {
+  if (!c) return fail(nullptr, RFSB200_EINVAL, "NULL ctx");
+  CU(c, cudaSetDevice(c->device));
+  CU(c, cudaStreamSynchronize(c->stream));
+  return RFSB200_OK;
+}
+
+int rfsb200_set_model(rfsb200_ctx* c, const rfsb200_model_desc* m) {
+  if (!c || !m) return fail(c, RFSB200_EINVAL, "NULL argument");
+  if (m->model_id != RFSB200_MODEL_RNGBRG)
+    return fail(c, RFSB200_EUNSUPPORTED, "model id %d has no device descriptor (only MeasurementModel_RngBrg)", m->model_id);
+  if (!(m->clutter_intensity > 0) || !(m->clutter_integral > 0))
+    return fail(c, RFSB200_EINVAL, "clutter intensity / integral must be > 0");
+  c->model = *m;
+  c->have_model = true;
+  return RFSB200_OK;
+}
+
+int rfsb200_set_filter_cfg(rfsb200_ctx* c, const rfsb200_filter_cfg* f) {
+  if (!c || !f) return fail(c, RFSB200_EINVAL, "NULL argument");
+  if (f->eval_point_count < 0 || f->eval_point_count > MAX_EVAL)
+    return fail(c, RFSB200_EUNSUPPORTED, "eval_point_count %d outside [0,%d]", f->eval_point_count, MAX_EVAL);
+  if (!(f->pruning_threshold > 0)) return fail(c, RFSB200_EINVAL, "pruning_threshold must be > 0");
+  if (!f->use_cluster_process) {
+    // scratch for the likelihood table of rfsMeasurementLikelihood
+    const size_t blk = (size_t)7 * c->W * c->tsize;
+    const size_t need = (size_t)MAX_EVAL * 8 * c->tsize + (size_t)((f->eval_point_count * c->dims.z_capacity + 3) & ~3) * c->tsize +
+                        MAX_EVAL * 8 + MAX_COMP * 12 + 2 * (1 << DP_MAXB) * 8;
+    if (need > blk) return fail(c, RFSB200_ECAPACITY, "eval_point_count x z_capacity needs %zu B scratch (> %zu)", need, blk);
+  }
+  c->cfg = *f;
+  c->merge_algo = (f->reserved_i[0] == 1) ? 0 : 1;  // reserved_i[0] == 1 selects the brute-force merge (debug)
+  c->have_cfg = true;
+  return RFSB200_OK;
+}
+
+int rfsb200_upload_maps(rfsb200_ctx* c, const int32_t* count, const double* mean, const double* cov, const double* w) {
+  if (!c || !count) return fail(c, RFSB200_EINVAL, "NULL argument");
+  CU(c, cudaSetDevice(c->device));
+  long long total = 0;
+  for (int i = 0; i < c->N; i++) {
+    if (count[i] < 0 || count[i] > c->dims.gm_capacity)
+      return fail(c, RFSB200_ECAPACITY, "particle %d has %d Gaussians (gm_capacity %d)", i, count[i], c->dims.gm_capacity);
+    total += count[i];
+  }
+  if (total > 0 && (!mean || !cov || !w)) return fail(c, RFSB200_EINVAL, "NULL map arrays");
+  StateBuf& s = c->st[c->front];
+  CU(c, cudaMemcpyAsync(s.cnt, count, (size_t)c->N * 4, cudaMemcpyHostToDevice, c->stream));
+  scan_counts_kernel<<<1, 1024, 0, c->stream>>>(s.cnt, c->offs, c->N);
+  double* dm = c->stg;
+  double* dc = dm + (size_t)c->N * c->cap * 2;
+  double* dw = dc + (size_t)c->N * c->cap * 3;
+  if (total > 0) {
+    CU(c, cudaMemcpyAsync(dm, mean, (size_t)total * 2 * 8, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(dc, cov, (size_t)total * 3 * 8, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(dw, w, (size_t)total * 8, cudaMemcpyHostToDevice, c->stream));
+    const int blocks = (c->N * 32 + 255) / 256;
+    if (c->prec == 32) pack_soa_kernel<float><<<blocks, 256, 0, c->stream>>>(s.cnt, c->offs, dm, dc, dw, (float*)s.gm, c->N, c->cap);
+    else pack_soa_kernel<double><<<blocks, 256, 0, c->stream>>>(s.cnt, c->offs, dm, dc, dw, (double*)s.gm, c->N, c->cap);
+  }
+  CU(c, cudaGetLastError());
+  c->last_out = c->front;
+  c->have_maps = true;
+  return RFSB200_OK;
+}
+
+int rfsb200_set_poses(rfsb200_ctx* c, const double* pose, const double* pose_cov, int mode, const double* weight) {
+  if (!c || !pose) return fail(c, RFSB200_EINVAL, "NULL argument");
+  if (mode < 0 || mode > 2 || (mode > 0 && !pose_cov)) return fail(c, RFSB200_EINVAL, "bad pose_cov_mode");
+  CU(c, cudaSetDevice(c->device));
+  double* dp = c->stg_small;
+  double* dcov = dp + (size_t)c->N * 3;
+  CU(c, cudaMemcpyAsync(dp, pose, (size_t)c->N * 3 * 8, cudaMemcpyHostToDevice, c->stream));
+  if (mode == 1) CU(c, cudaMemcpyAsync(dcov, pose_cov, 6 * 8, cudaMemcpyHostToDevice, c->stream));
+  if (mode == 2) CU(c, cudaMemcpyAsync(dcov, pose_cov, (size_t)c->N * 6 * 8, cudaMemcpyHostToDevice, c->stream));
+  const int blocks = (c->N + 255) / 256;
+  if (c->prec == 32) pose_convert_kernel<float><<<blocks, 256, 0, c->stream>>>(dp, dcov, mode, (float*)c->pose, (float*)c->pose_cov, c->N);
+  else pose_convert_kernel<double><<<blocks, 256, 0, c->stream>>>(dp, dcov, mode, (double*)c->pose, (double*)c->pose_cov, c->N);
+  CU(c, cudaGetLastError());
+  c->pose_cov_mode = mode;
+  if (weight) CU(c, cudaMemcpyAsync(c->st[c->front].weight, weight, (size_t)c->N * 8, cudaMemcpyHostToDevice, c->stream));
+  c->have_poses = true;
+  return RFSB200_OK;
+}
+
+int rfsb200_update(rfsb200_ctx* c, const double* Z, int32_t nZ, uint32_t flags, rfsb200_step_out* out) {
+  if (!c) return fail(nullptr, RFSB200_EINVAL, "NULL ctx");
+  if (!c->have_model || !c->have_cfg || !c->have_maps || !c->have_poses)
+    return fail(c, RFSB200_ESTATE, "update before set_model / set_filter_cfg / upload_maps / set_poses");
+  if (nZ < 0 || nZ > c->dims.z_capacity) return fail(c, RFSB200_ECAPACITY, "nZ %d > z_capacity %d", nZ, c->dims.z_capacity);
+  if (out) memset(out, 0, sizeof(*out));
+  if (nZ == 0) return RFSB200_OK;  // include/RBPHDFilter.hpp:451-452 (Q11)
+  if (!Z) return fail(c, RFSB200_EINVAL, "NULL Z");
+  CU(c, cudaSetDevice(c->device));
+  // Z -> T in pinned scratch -> device
+  if (c->prec == 32) {
+    float* h = (float*)c->hpin;
+    for (int k = 0; k < 2 * nZ; k++) h[k] = (float)Z[k];
+  } else {
+    memcpy(c->hpin, Z, (size_t)nZ * 16);
+  }
+  int launches = 0;
+  if (out) CU(c, cudaEventRecord(c->ev0, c->stream));
+  CU(c, cudaMemcpyAsync(c->Zdev, c->hpin, (size_t)nZ * 2 * c->tsize, cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaMemsetAsync(c->totals, 0, 16, c->stream));
+  CU(c, cudaMemsetAsync(c->istats, 0, 16, c->stream));
+  const int out_idx = c->front ^ 1;
+  int rc = (c->prec == 32) ? launch_update<float>(c, nZ, out_idx) : launch_update<double>(c, nZ, out_idx);
+  if (rc) return rc;
+  launches++;
+  c->last_out = out_idx;
+  if (!(flags & RFSB200_UPDATE_NO_NORMALIZE)) {
+    normalize_kernel<<<(c->N + 255) / 256, 256, 0, c->stream>>>(c->st[out_idx].weight, c->sums, c->N);
+    CU(c, cudaGetLastError());
+    launches++;
+  }
+  if (!(flags & RFSB200_UPDATE_NO_COMMIT)) c->front = out_idx;
+  if (out) {
+    CU(c, cudaEventRecord(c->ev1, c->stream));
+    unsigned char* h = c->hpin + 4096;
+    CU(c, cudaMemcpyAsync(h, c->sums, 16, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaMemcpyAsync(h + 16, c->totals, 16, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaMemcpyAsync(h + 32, c->istats, 16, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    const double* s = (const double*)h;
+    const unsigned long long* t = (const unsigned long long*)(h + 16);
+    const int* is = (const int*)(h + 32);
+    out->sum_w = s[0];
+    out->sum_w2 = s[1];
+    out->n_eff = s[1] > 0 ? s[0] * s[0] / s[1] : 0;
+    out->gm_total_in = (int64_t)t[0];
+    out->gm_total_out = (int64_t)t[1];
+    out->gm_max_out = is[0];
+    out->n_overflow = is[1];
+    out->n_murty = is[2];
+    out->n_launches = launches;
+    float ms = 0;
+    CU(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    out->elapsed_us = ms * 1000.f;
+  }
+  return RFSB200_OK;
+}
+
+int rfsb200_weight_sums_device(rfsb200_ctx* c, void** p) {
+  if (!c || !p) return fail(c, RFSB200_EINVAL, "NULL argument");
+  *p = c->sums;
+  return RFSB200_OK;
+}
+
+int rfsb200_normalize(rfsb200_ctx* c) {
+  if (!c) return fail(nullptr, RFSB200_EINVAL, "NULL ctx");
+  CU(c, cudaSetDevice(c->device));
+  normalize_kernel<<<(c->N + 255) / 256, 256, 0, c->stream>>>(c->st[c->last_out].weight, c->sums, c->N);
+  CU(c, cudaGetLastError());
+  return RFSB200_OK;
+}
+
+static int which_buf(rfsb200_ctx* c, int which) { return which == 0 ? c->front : c->last_out; }
+
+int rfsb200_get_weights(rfsb200_ctx* c, int which, double* w) {
+  if (!c || !w) return fail(c, RFSB200_EINVAL, "NULL argument");
+  CU(c, cudaSetDevice(c->device));
+  CU(c, cudaMemcpyAsync(w, c->st[which_buf(c, which)].weight, (size_t)c->N * 8, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  return RFSB200_OK;
+}
+
+int rfsb200_get_gm_sizes(rfsb200_ctx* c, int which, int32_t* n) {
+  if (!c || !n) return fail(c, RFSB200_EINVAL, "NULL argument");
+  CU(c, cudaSetDevice(c->device));
+  CU(c, cudaMemcpyAsync(n, c->st[which_buf(c, which)].cnt, (size_t)c->N * 4, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  return RFSB200_OK;
+}
+
+int rfsb200_get_map(rfsb200_ctx* c, int which, int32_t i, int32_t cap, int32_t* n, double* mean, double* cov, double* w) {
+  if (!c || !n) return fail(c, RFSB200_EINVAL, "NULL argument");
+  if (i < 0 || i >= c->N) return fail(c, RFSB200_EINVAL, "particle index %d out of range", i);
+  CU(c, cudaSetDevice(c->device));
+  const StateBuf& s = c->st[which_buf(c, which)];
+  int cnt = 0;
+  CU(c, cudaMemcpyAsync(&cnt, s.cnt + i, 4, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  *n = cnt;
+  if (cnt == 0) return RFSB200_OK;
+  if (cnt > cap) return fail(c, RFSB200_ECAPACITY, "particle %d has %d Gaussians, caller capacity %d", i, cnt, cap);
+  if (!mean || !cov || !w) return fail(c, RFSB200_EINVAL, "NULL output arrays");
+  std::vector<unsigned char> tmp((size_t)6 * c->cap * c->tsize);
+  CU(c, cudaMemcpyAsync(tmp.data(), (const unsigned char*)s.gm + (size_t)i * 6 * c->cap * c->tsize, tmp.size(), cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  for (int k = 0; k < cnt; k++) {
+    auto get = [&](int plane) -> double {
+      size_t idx = (size_t)plane * c->cap + k;
+      return c->prec == 32 ? (double)((const float*)tmp.data())[idx] : ((const double*)tmp.data())[idx];
+    };
+    mean[2 * k] = get(0); mean[2 * k + 1] = get(1);
+    cov[3 * k] = get(2); cov[3 * k + 1] = get(3); cov[3 * k + 2] = get(4);
+    w[k] = get(5);
+  }
+  return RFSB200_OK;
+}
+
+int rfsb200_download_maps(rfsb200_ctx* c, int which, int64_t cap_total, int32_t* count, double* mean, double* cov, double* w) {
+  if (!c || !count) return fail(c, RFSB200_EINVAL, "NULL argument");
+  CU(c, cudaSetDevice(c->device));
+  const StateBuf& s = c->st[which_buf(c, which)];
+  scan_counts_kernel<<<1, 1024, 0, c->stream>>>(s.cnt, c->offs, c->N);
+  double* dm = c->stg;
+  double* dc = dm + (size_t)c->N * c->cap * 2;
+  double* dw = dc + (size_t)c->N * c->cap * 3;
+  const int blocks = (c->N * 32 + 255) / 256;
+  if (c->prec == 32) unpack_soa_kernel<float><<<blocks, 256, 0, c->stream>>>(s.cnt, c->offs, (const float*)s.gm, dm, dc, dw, c->N, c->cap);
+  else unpack_soa_kernel<double><<<blocks, 256, 0, c->stream>>>(s.cnt, c->offs, (const double*)s.gm, dm, dc, dw, c->N, c->cap);
+  CU(c, cudaGetLastError());
+  long long total = 0;
+  CU(c, cudaMemcpyAsync(count, s.cnt, (size_t)c->N * 4, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaMemcpyAsync(&total, c->offs + c->N, 8, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  if (total > cap_total) return fail(c, RFSB200_ECAPACITY, "%lld Gaussians do not fit caller capacity %lld", total, (long long)cap_total);
+  if (total > 0) {
+    if (!mean || !cov || !w) return fail(c, RFSB200_EINVAL, "NULL output arrays");
+    CU(c, cudaMemcpyAsync(mean, dm, (size_t)total * 16, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaMemcpyAsync(cov, dc, (size_t)total * 24, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaMemcpyAsync(w, dw, (size_t)total * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+  }
+  return RFSB200_OK;
+}
+
+int rfsb200_get_unused(rfsb200_ctx* c, uint64_t* mask, int32_t* nfov) {
+  if (!c) return fail(nullptr, RFSB200_EINVAL, "NULL ctx");
+  CU(c, cudaSetDevice(c->device));
+  if (mask) CU(c, cudaMemcpyAsync(mask, c->unused, (size_t)c->N * 8, cudaMemcpyDeviceToHost, c->stream));
+  if (nfov) CU(c, cudaMemcpyAsync(nfov, c->nfov, (size_t)c->N * 4, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  return RFSB200_OK;
+}
+
+int rfsb200_get_flags(rfsb200_ctx* c, int32_t* flags) {
+  if (!c || !flags) return fail(c, RFSB200_EINVAL, "NULL argument");
+  CU(c, cudaSetDevice(c->device));
+  CU(c, cudaMemcpyAsync(flags, c->flags, (size_t)c->N * 4, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  return RFSB200_OK;
+}
+
+int rfsb200_permanent(rfsb200_ctx* c, const double* A, int32_t n, int32_t batch, double* out) {
+  if (!c || !A || !out) return fail(c, RFSB200_EINVAL, "NULL argument");
+  if (n < 1 || n > 24 || batch < 1) return fail(c, RFSB200_EINVAL, "n must be in [1,24], batch >= 1");
+  CU(c, cudaSetDevice(c->device));
+  double* dA = nullptr;
+  double* dO = nullptr;
+  const size_t bytes = (size_t)batch * n * n * 8;
+  CU(c, cudaMalloc((void**)&dA, bytes));
+  CU(c, cudaMalloc((void**)&dO, (size_t)batch * 8));
+  cudaError_t e = cudaMemcpyAsync(dA, A, bytes, cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess) {
+    permanent_kernel<<<(batch * 32 + 127) / 128, 128, 0, c->stream>>>(dA, n, batch, dO);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out, dO, (size_t)batch * 8, cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  cudaFree(dA);
+  cudaFree(dO);
+  if (e != cudaSuccess) return fail(c, RFSB200_ECUDA, "rfsb200_permanent: %s", cudaGetErrorString(e));
+  return RFSB200_OK;
+}
+
+int rfsb200_host_alloc(void** ptr, uint64_t bytes) {
+  if (!ptr) return fail(nullptr, RFSB200_EINVAL, "NULL argument");
+  cudaError_t e = cudaMallocHost(ptr, bytes);
+  if (e != cudaSuccess) return fail(nullptr, RFSB200_ENOMEM, "cudaMallocHost(%llu): %s", (unsigned long long)bytes, cudaGetErrorString(e));
+  return RFSB200_OK;
+}
+
+int rfsb200_host_free(void* ptr) {
+  if (ptr) cudaFreeHost(ptr);
+  return RFSB200_OK;
+}
+
+}  // extern "C"

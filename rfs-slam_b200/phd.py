@@ -1,0 +1,190 @@
+"""PHDUpdater — host-side mirror of rfs::RBPHDFilter<...>::update() over the C ABI.
+
+Names follow the reference (include/RBPHDFilter.hpp:183-251): update(Z), getGMSize(i),
+getLandmark(i, m), particle weights; configs are the reference's public config structs as
+dicts (synth.DEFAULT_MODEL / DEFAULT_CFG).  All compute happens in librfsb200.so on the GPU;
+this class only marshals numpy arrays.  No CPU fallback: construction raises without a GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+
+
+class RFSB200Error(RuntimeError):
+    pass
+
+
+def _check(lib, ctx, rc, what):
+    if rc != 0:
+        msg = lib.rfsb200_last_error(ctx)
+        raise RFSB200Error(f"{what}: {capi.ERRORS.get(rc, rc)}: {msg.decode() if msg else ''}")
+
+
+class PHDUpdater:
+    def __init__(self, n_particles: int, gm_capacity: int = 256, work_capacity: int = 0,
+                 z_capacity: int = 64, device: int = 0, precision: int = 32):
+        self.lib = capi.load_library()
+        self.N = int(n_particles)
+        self.gm_capacity = int(gm_capacity)
+        d = capi.Dims()
+        d.n_particles = self.N
+        d.gm_capacity = self.gm_capacity
+        d.work_capacity = int(work_capacity) if work_capacity else self.gm_capacity
+        d.z_capacity = int(z_capacity)
+        d.lmk_dim, d.meas_dim, d.pose_dim = 2, 2, 3
+        d.device = int(device)
+        d.precision = int(precision)
+        self.ctx = C.c_void_p()
+        rc = self.lib.rfsb200_create(C.byref(self.ctx), C.byref(d))
+        if rc != 0:
+            msg = self.lib.rfsb200_last_error(None)
+            self.ctx = None
+            raise RFSB200Error(f"rfsb200_create: {capi.ERRORS.get(rc, rc)}: {msg.decode() if msg else ''}")
+        self._keep = []
+
+    # ---- lifetime -------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.rfsb200_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- configuration ----------------------------------------------------------------------
+    def set_model(self, md: dict):
+        d = capi.model_desc(md)
+        _check(self.lib, self.ctx, self.lib.rfsb200_set_model(self.ctx, C.byref(d)), "set_model")
+
+    def set_filter_cfg(self, fc: dict, brute_force_merge: bool = False):
+        c = capi.filter_cfg(fc)
+        c.reserved_i[0] = 1 if brute_force_merge else 0
+        _check(self.lib, self.ctx, self.lib.rfsb200_set_filter_cfg(self.ctx, C.byref(c)), "set_filter_cfg")
+
+    def set_stream(self, cuda_stream: int | None):
+        _check(self.lib, self.ctx, self.lib.rfsb200_set_stream(self.ctx, C.c_void_p(cuda_stream or 0)), "set_stream")
+
+    def synchronize(self):
+        _check(self.lib, self.ctx, self.lib.rfsb200_synchronize(self.ctx), "synchronize")
+
+    # ---- state in --------------------------------------------------------------------------------
+    def upload_maps(self, count, mean, cov, w):
+        count = np.ascontiguousarray(count, dtype=np.int32)
+        mean = np.ascontiguousarray(mean, dtype=np.float64)
+        cov = np.ascontiguousarray(cov, dtype=np.float64)
+        w = np.ascontiguousarray(w, dtype=np.float64)
+        assert count.shape[0] == self.N
+        self._keep = [count, mean, cov, w]  # async copies read these until the next sync
+        _check(self.lib, self.ctx,
+               self.lib.rfsb200_upload_maps(self.ctx, capi.ptr(count), capi.ptr(mean), capi.ptr(cov), capi.ptr(w)),
+               "upload_maps")
+
+    def set_poses(self, pose, pose_cov=None, weight=None):
+        pose = np.ascontiguousarray(pose, dtype=np.float64)
+        mode = 0
+        pc = None
+        if pose_cov is not None:
+            pc = np.ascontiguousarray(pose_cov, dtype=np.float64)
+            mode = 1 if pc.ndim == 1 else 2
+        wt = None if weight is None else np.ascontiguousarray(weight, dtype=np.float64)
+        self._keep += [pose, pc, wt]
+        _check(self.lib, self.ctx,
+               self.lib.rfsb200_set_poses(self.ctx, capi.ptr(pose), capi.ptr(pc), mode, capi.ptr(wt)),
+               "set_poses")
+
+    def load_workload(self, wl):
+        self.set_model(wl.model)
+        self.set_filter_cfg(wl.cfg)
+        self.upload_maps(wl.count, wl.mean, wl.cov, wl.w)
+        self.set_poses(wl.pose, wl.pose_cov, wl.weight)
+
+    # ---- the hot path ---------------------------------------------------------------------------
+    def update(self, Z, flags: int = capi.UPDATE_DEFAULT, want_stats: bool = True):
+        """RBPHDFilter::update(Z) for all particles.  Returns a StepOut (or None if async)."""
+        Z = np.ascontiguousarray(Z, dtype=np.float64).reshape(-1, 2)
+        out = capi.StepOut() if want_stats else None
+        rc = self.lib.rfsb200_update(self.ctx, capi.ptr(Z), Z.shape[0], flags,
+                                     C.byref(out) if out is not None else None)
+        _check(self.lib, self.ctx, rc, "update")
+        return out
+
+    def weight_sums_device_ptr(self) -> int:
+        p = C.c_void_p()
+        _check(self.lib, self.ctx, self.lib.rfsb200_weight_sums_device(self.ctx, C.byref(p)), "weight_sums_device")
+        return int(p.value)
+
+    def normalize(self):
+        _check(self.lib, self.ctx, self.lib.rfsb200_normalize(self.ctx), "normalize")
+
+    # ---- state out -------------------------------------------------------------------------------
+    def get_weights(self, which: int = 0) -> np.ndarray:
+        w = np.zeros(self.N)
+        _check(self.lib, self.ctx, self.lib.rfsb200_get_weights(self.ctx, which, capi.ptr(w)), "get_weights")
+        return w
+
+    def get_gm_sizes(self, which: int = 0) -> np.ndarray:
+        n = np.zeros(self.N, dtype=np.int32)
+        _check(self.lib, self.ctx, self.lib.rfsb200_get_gm_sizes(self.ctx, which, capi.ptr(n)), "get_gm_sizes")
+        return n
+
+    def getGMSize(self, i: int, which: int = 0) -> int:
+        if i < 0 or i >= self.N:
+            return -1  # include/RBPHDFilter.hpp:1153-1159
+        return int(self.get_gm_sizes(which)[i])
+
+    def get_map(self, i: int, which: int = 0):
+        cap = self.gm_capacity + 8
+        n = C.c_int32()
+        mean = np.zeros((cap, 2)); cov = np.zeros((cap, 3)); w = np.zeros(cap)
+        _check(self.lib, self.ctx,
+               self.lib.rfsb200_get_map(self.ctx, which, i, cap, C.byref(n), capi.ptr(mean), capi.ptr(cov), capi.ptr(w)),
+               "get_map")
+        k = n.value
+        return mean[:k].copy(), cov[:k].copy(), w[:k].copy()
+
+    def getLandmark(self, i: int, m: int, which: int = 0):
+        """(ok, mean[2], cov[2,2], w) — include/RBPHDFilter.hpp:1161-1178."""
+        if i < 0 or i >= self.N:
+            return False, None, None, None
+        mean, cov, w = self.get_map(i, which)
+        if m < 0 or m >= len(w):
+            return False, None, None, None
+        S = np.array([[cov[m, 0], cov[m, 1]], [cov[m, 1], cov[m, 2]]])
+        return True, mean[m].copy(), S, float(w[m])
+
+    def download_maps(self, which: int = 0):
+        cap_total = self.N * (self.gm_capacity + 8)
+        count = np.zeros(self.N, dtype=np.int32)
+        mean = np.zeros((cap_total, 2)); cov = np.zeros((cap_total, 3)); w = np.zeros(cap_total)
+        _check(self.lib, self.ctx,
+               self.lib.rfsb200_download_maps(self.ctx, which, cap_total, capi.ptr(count), capi.ptr(mean),
+                                              capi.ptr(cov), capi.ptr(w)), "download_maps")
+        t = int(count.sum())
+        return count, mean[:t].copy(), cov[:t].copy(), w[:t].copy()
+
+    def get_unused(self):
+        mask = np.zeros(self.N, dtype=np.uint64)
+        nfov = np.zeros(self.N, dtype=np.int32)
+        _check(self.lib, self.ctx, self.lib.rfsb200_get_unused(self.ctx, capi.ptr(mask), capi.ptr(nfov)), "get_unused")
+        return mask, nfov
+
+    def get_flags(self) -> np.ndarray:
+        f = np.zeros(self.N, dtype=np.int32)
+        _check(self.lib, self.ctx, self.lib.rfsb200_get_flags(self.ctx, capi.ptr(f)), "get_flags")
+        return f
+
+    def permanent(self, A) -> np.ndarray:
+        A = np.ascontiguousarray(A, dtype=np.float64)
+        if A.ndim == 2:
+            A = A[None]
+        out = np.zeros(A.shape[0])
+        _check(self.lib, self.ctx,
+               self.lib.rfsb200_permanent(self.ctx, capi.ptr(A), A.shape[1], A.shape[0], capi.ptr(out)), "permanent")
+        return out
