@@ -53,6 +53,9 @@ struct KParams {
   const T* pose;      // [N][4]
   const T* pose_cov;  // [8] or [N][8]
   const T* Z;         // [nZ][2]
+  const T* Zr_sorted; // [nZ] ranges ascending
+  const T* Zb_sorted; // [nZ] bearing of the same measurement
+  const int* Z_sorted_idx;  // [nZ] original index of the same measurement
   T* gm_out;
   int* cnt_out;
   double* w_out;
@@ -64,13 +67,21 @@ struct KParams {
   unsigned long long* totals;     // [0]=gm_in total [1]=gm_out total
   int* istats;                    // [0]=max out [1]=n_overflow [2]=n_murty
   unsigned int* ticket;
+  unsigned int* work_counter;     // dynamic particle queue, re-armed by the last CTA
+  unsigned long long* stats_out;  // [5] totals/istats of the finished step, published by the last CTA
 };
 
 // ------------------------------------------------------------------------------------------------
 template <typename T>
 __device__ __forceinline__ T wrap_pi(T a) {
-  while (a > M<T>::PI) a -= M<T>::TWO_PI;
-  while (a < -M<T>::PI) a += M<T>::TWO_PI;
+  // same result as the reference's while-loops (src/MeasurementModel_RngBrg.cpp:92-93,
+  // src/KalmanFilter_RngBrg.cpp:58-61); the loops only run for |a| > 3*pi
+  if (a > M<T>::PI) a -= M<T>::TWO_PI;
+  if (a < -M<T>::PI) a += M<T>::TWO_PI;
+  if (!(M<T>::abs_(a) <= M<T>::PI)) {
+    while (a > M<T>::PI) a -= M<T>::TWO_PI;
+    while (a < -M<T>::PI) a += M<T>::TWO_PI;
+  }
   return a;
 }
 
@@ -86,7 +97,7 @@ __device__ __forceinline__ void warp_bitonic(T* kw, unsigned* ki, int P, int lan
   for (int k = 2; k <= P; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
       for (int t = lane; t < (P >> 1); t += 32) {
-        int i = ((t / j) * (j << 1)) + (t % j);
+        int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
         int q = i + j;
         bool up = ((i & k) == 0);
         T wa = kw[i], wb = kw[q];
@@ -152,11 +163,12 @@ __device__ __forceinline__ bool merge_absorb(MergeRow<T>& r, T* cur, int W, int 
   if (wm == T(0)) return false;
   T x2 = cur[j], y2 = cur[W + j];
   T q00 = cur[2 * W + j], q01 = cur[3 * W + j], q11 = cur[4 * W + j];
-  T xm = (r.x * w1 + x2 * w2) / wm, ym = (r.y * w1 + y2 * w2) / wm;
+  const T iw = T(1) / wm;
+  T xm = (r.x * w1 + x2 * w2) * iw, ym = (r.y * w1 + y2 * w2) * iw;
   T ax = xm - r.x, ay = ym - r.y, bx = xm - x2, by = ym - y2;
-  T s00 = (w1 * (r.pxx + f * ax * ax) + w2 * (q00 + f * bx * bx)) / wm;
-  T s01 = (w1 * (r.pxy + f * ax * ay) + w2 * (q01 + f * bx * by)) / wm;
-  T s11 = (w1 * (r.pyy + f * ay * ay) + w2 * (q11 + f * by * by)) / wm;
+  T s00 = (w1 * (r.pxx + f * ax * ax) + w2 * (q00 + f * bx * bx)) * iw;
+  T s01 = (w1 * (r.pxy + f * ax * ay) + w2 * (q01 + f * bx * by)) * iw;
+  T s11 = (w1 * (r.pyy + f * ay * ay) + w2 * (q11 + f * by * by)) * iw;
   r.x = xm; r.y = ym; r.pxx = s00; r.pxy = s01; r.pyy = s11; r.w = wm;
   inv_sym2(s00, s01, s11, r.i00, r.i01, r.i11);
   __syncwarp();
@@ -227,8 +239,54 @@ __device__ void merge_bruteforce(T* cur, int W, int n, T t2, T f, int lane) {
 //            on the candidates -> short list of passing pairs (i<j), key = i<<16 | j
 //  sequential phase: rows are visited in ascending i only if they own a passing pair; the first
 //            merge of a row is its smallest live j in the list (everything is still original
-//            then); after an absorb the row changed, so j > jmin is re-scanned exhaustively.
-//  scratch: rad2[W] T, cellStart[258] u16 + cursor[257] u16, order[W] u16, pairs[MAX_PAIRS] u32
+//            then); after an absorb the row changed, so every live j > jmin inside the cells the
+//            new reach (or the largest reach of any component) covers is re-tested.
+//  scratch: rad2[W] T, pairs[MAX_PAIRS] u32, cellStart[258] u16, cursor[258] u16, order[W] u16, npairs
+template <typename T>
+struct MergeGrid {
+  T xmin, invw, rmax2;
+  const unsigned short* cellStart;
+  const unsigned short* order;
+};
+
+template <typename T>
+__device__ __forceinline__ int grid_cell(const MergeGrid<T>& g, T x) {
+  int c = (int)((x - g.xmin) * g.invw);
+  return c < 0 ? 0 : (c > 255 ? 255 : c);
+}
+
+// smallest live j > jlast passing the merge test against row r, looking only at the cells that can
+// hold a partner: |d|^2 <= max(reach2(row), reach2(j)) <= max(ri2, rmax2)
+template <typename T>
+__device__ __forceinline__ int merge_rescan(const MergeRow<T>& r, T ri2, const MergeGrid<T>& g, const T* cur,
+                                            const T* rad2, int W, int jlast, int n, T t2, int lane) {
+  const T R2 = M<T>::max_(ri2, g.rmax2);
+  if (!(R2 < M<T>::inf())) return merge_scan<T, true>(r, cur, rad2, ri2, W, jlast + 1, n, t2, lane);
+  const T R = M<T>::sqrt_(R2);
+  int clo = 0, chi = 255;
+  if (g.invw > T(0)) {
+    clo = grid_cell(g, r.x - R) - 1;
+    chi = grid_cell(g, r.x + R) + 1;
+    clo = clo < 0 ? 0 : clo;
+    chi = chi > 255 ? 255 : chi;
+  }
+  const int k0 = g.cellStart[clo], k1 = g.cellStart[chi + 1];
+  int best = 0x7fffffff;
+  for (int kb = k0; kb < k1; kb += 32) {
+    const int k = kb + lane;
+    if (k < k1) {
+      const int c = g.order[k];
+      if (c > jlast && cur[5 * W + c] >= T(0)) {
+        const T dx = cur[c] - r.x, dy = cur[W + c] - r.y;
+        const T rr = M<T>::max_(ri2, rad2[c]);
+        if (!(dx * dx + dy * dy > rr) && merge_test(r, cur, W, c, t2)) best = c < best ? c : best;
+      }
+    }
+  }
+  best = warp_min(best);
+  return best == 0x7fffffff ? -1 : best;
+}
+
 template <typename T>
 __device__ void merge_culled(T* cur, T* scratch, int W, int n, T t2, T f, int lane) {
   T* rad2 = scratch;                                     // W
@@ -238,7 +296,7 @@ __device__ void merge_culled(T* cur, T* scratch, int W, int n, T t2, T f, int la
   unsigned short* order = cursor + 258;                  // W
   unsigned* npairs = reinterpret_cast<unsigned*>(order + W + (W & 1));  // 1 (4-byte aligned)
   // reach + bounding interval
-  T xmin = M<T>::inf(), xmax = -M<T>::inf();
+  T xmin = M<T>::inf(), xmax = -M<T>::inf(), rmax2 = T(0);
   for (int j = lane; j < n; j += 32) {
     T w = cur[5 * W + j];
     T rr = T(0);
@@ -247,6 +305,7 @@ __device__ void merge_culled(T* cur, T* scratch, int W, int n, T t2, T f, int la
       T x = cur[j];
       xmin = x < xmin ? x : xmin;
       xmax = x > xmax ? x : xmax;
+      rmax2 = rr > rmax2 ? rr : rmax2;
     }
     rad2[j] = rr;
   }
@@ -254,21 +313,25 @@ __device__ void merge_culled(T* cur, T* scratch, int W, int n, T t2, T f, int la
   if (lane == 0) *npairs = 0;
   xmin = warp_min(xmin);
   xmax = warp_max(xmax);
+  rmax2 = warp_max(rmax2);
   T span = xmax - xmin;
-  T invw = (span > T(0)) ? T(255.999) / span : T(0);
+  MergeGrid<T> g;
+  g.xmin = xmin;
+  g.invw = (span > T(0)) ? T(255.999) / span : T(0);
+  g.rmax2 = rmax2;
+  g.cellStart = cellStart;
+  g.order = order;
   __syncwarp();
-  // histogram (counts at cell+1 for the exclusive prefix)
+  // histogram (counts at cell+1 for the exclusive prefix); 16-bit counters packed in 32-bit words
   for (int j = lane; j < n; j += 32) {
     if (cur[5 * W + j] >= T(0)) {
-      int c = (int)((cur[j] - xmin) * invw);
-      c = c < 0 ? 0 : (c > 255 ? 255 : c);
-      // 16-bit counters packed in 32-bit words: atomicAdd on the containing word
+      const int c = grid_cell(g, cur[j]);
       unsigned* wd = reinterpret_cast<unsigned*>(cellStart) + ((c + 1) >> 1);
       atomicAdd(wd, ((c + 1) & 1) ? 0x10000u : 1u);
     }
   }
   __syncwarp();
-  {  // exclusive prefix over 257 entries: lane owns 8 consecutive cells (+ tail by lane 0)
+  {  // inclusive prefix over entries 1..256: lane owns 8 consecutive entries
     int loc[8];
     int s = 0;
 #pragma unroll
@@ -286,8 +349,7 @@ __device__ void merge_culled(T* cur, T* scratch, int W, int n, T t2, T f, int la
   __syncwarp();
   for (int j = lane; j < n; j += 32) {
     if (cur[5 * W + j] >= T(0)) {
-      int c = (int)((cur[j] - xmin) * invw);
-      c = c < 0 ? 0 : (c > 255 ? 255 : c);
+      const int c = grid_cell(g, cur[j]);
       unsigned* wd = reinterpret_cast<unsigned*>(cursor) + (c >> 1);
       unsigned old = atomicAdd(wd, (c & 1) ? 0x10000u : 1u);
       unsigned pos = (c & 1) ? (old >> 16) : (old & 0xffffu);
@@ -295,70 +357,71 @@ __device__ void merge_culled(T* cur, T* scratch, int W, int n, T t2, T f, int la
     }
   }
   __syncwarp();
-  // neighbour scan with exact test on original parameters
+  // neighbour scan with the exact test on the original parameters
   bool overflow = false;
-  for (int j = lane; j < n; j += 32) {
-    T wj = cur[5 * W + j];
-    if (!(wj >= T(0))) continue;
-    T rj2 = rad2[j];
-    T xj = cur[j], yj = cur[W + j];
-    int clo = 0, chi = 255;
-    if (rj2 < M<T>::inf() && invw > T(0)) {
-      T rj = M<T>::sqrt_(rj2);
-      int a = (int)((xj - rj - xmin) * invw) - 1;
-      int b = (int)((xj + rj - xmin) * invw) + 1;
-      clo = a < 0 ? 0 : (a > 255 ? 255 : a);
-      chi = b < 0 ? 0 : (b > 255 ? 255 : b);
-    }
-    int k0 = cellStart[clo], k1 = cellStart[chi + 1];
-    for (int k = k0; k < k1; k++) {
-      int c = order[k];
-      if (c == j) continue;
-      T dx = cur[c] - xj, dy = cur[W + c] - yj;
-      if (dx * dx + dy * dy > rj2) continue;   // found from the side whose reach covers the pair
-      int i0 = j < c ? j : c, j0 = j < c ? c : j;
-      MergeRow<T> r;
-      load_row(r, cur, W, i0);
-      if (merge_test(r, cur, W, j0, t2)) {
-        unsigned slot = atomicAdd(npairs, 1u);
-        if (slot < (unsigned)MAX_PAIRS) pairs[slot] = ((unsigned)i0 << 16) | (unsigned)j0;
-        else overflow = true;
+  for (int jb = 0; jb < n; jb += 32) {
+    const int j = jb + lane;
+    if (j < n && cur[5 * W + j] >= T(0)) {
+      const T rj2 = rad2[j];
+      const T xj = cur[j], yj = cur[W + j];
+      int clo = 0, chi = 255;
+      if (rj2 < M<T>::inf() && g.invw > T(0)) {
+        const T rj = M<T>::sqrt_(rj2);
+        clo = grid_cell(g, xj - rj) - 1;
+        chi = grid_cell(g, xj + rj) + 1;
+        clo = clo < 0 ? 0 : clo;
+        chi = chi > 255 ? 255 : chi;
+      }
+      const int k0 = cellStart[clo], k1 = cellStart[chi + 1];
+      for (int k = k0; k < k1; k++) {
+        const int c = order[k];
+        if (c == j) continue;
+        const T dx = cur[c] - xj, dy = cur[W + c] - yj;
+        if (dx * dx + dy * dy > rj2) continue;   // found from the side whose reach covers the pair
+        const int i0 = j < c ? j : c, j0 = j < c ? c : j;
+        MergeRow<T> r;
+        load_row(r, cur, W, i0);
+        if (merge_test(r, cur, W, j0, t2)) {
+          unsigned slot = atomicAdd(npairs, 1u);
+          if (slot < (unsigned)MAX_PAIRS) pairs[slot] = ((unsigned)i0 << 16) | (unsigned)j0;
+          else overflow = true;
+        }
       }
     }
+    __syncwarp();  // reconverge: the inner loops have different trip counts per lane
   }
-  __syncwarp();
   if (__any_sync(FULL, overflow)) {  // too many candidate pairs: exact fallback
     merge_bruteforce(cur, W, n, t2, f, lane);
     return;
   }
-  int np = (int)*npairs;
+  const int np = (int)*npairs;
   // sequential phase
   unsigned curkey = 0;
   while (true) {
     unsigned best = 0xffffffffu;
     for (int k = lane; k < np; k += 32) {
-      unsigned key = pairs[k];
+      const unsigned key = pairs[k];
       if (key >= curkey && key < best) {
-        int i = key >> 16, j = key & 0xffff;
+        const int i = key >> 16, j = key & 0xffff;
         if (cur[5 * W + i] >= T(0) && cur[5 * W + j] >= T(0)) best = key;
       }
     }
     best = warp_min(best);
     if (best == 0xffffffffu) break;
-    int i = best >> 16, j = best & 0xffff;
+    const int i = best >> 16, j = best & 0xffff;
     MergeRow<T> r;
     load_row(r, cur, W, i);
     if (!merge_absorb(r, cur, W, i, j, f, lane)) {  // w_m == 0: the reference moves on to j+1
       curkey = best + 1;
       continue;
     }
-    int jstart = j + 1;
+    int jlast = j;
     while (true) {
-      T ri2 = merge_reach2(r.pxx, r.pxy, r.pyy, t2);
-      int jj = merge_scan<T, true>(r, cur, rad2, ri2, W, jstart, n, t2, lane);
+      const T ri2 = merge_reach2(r.pxx, r.pxy, r.pyy, t2);
+      const int jj = merge_rescan<T>(r, ri2, g, cur, rad2, W, jlast, n, t2, lane);
       if (jj < 0) break;
       merge_absorb(r, cur, W, i, jj, f, lane);
-      jstart = jj + 1;
+      jlast = jj;
     }
     curkey = ((unsigned)(i + 1)) << 16;
   }
@@ -461,25 +524,55 @@ __device__ inline double warp_permanent(const double* A, int n, int lane) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// shared-memory carve-up of one warp (bytes), host and device agree through these helpers
 template <typename T>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+__host__ __device__ inline int scratch_bytes(int W) {
+  // merge scratch: rad2[W] T, pairs, cellStart+cursor, order[W], npairs ; prune keys reuse rad2
+  return (int)((W * sizeof(T) + MAX_PAIRS * 4 + 2 * 258 * 2 + (W + 2) * 2 + 16 + 15) & ~15);
+}
+template <typename T>
+__host__ __device__ inline int warp_bytes_for(int W, int multi_feature) {
+  const int planes = multi_feature ? 14 : 6;   // MF keeps a second 7-plane block for the sort
+  int b = planes * W * (int)sizeof(T) + scratch_bytes<T>(W) + W * 4 + MAX_Z * (int)sizeof(T) + MAX_EVAL * 4 + 16;
+  return (b + 127) & ~127;
+}
+// Z block in shared memory: original (zr,zb) pairs, then range-sorted zr / zb / original index
+template <typename T>
+__host__ __device__ inline int z_bytes() {
+  return (int)((4 * MAX_Z * sizeof(T) + MAX_Z * 4 + 127) & ~127);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4)
 phd_update_kernel(const __grid_constant__ KParams<T> p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int W = p.W;
   const int nZ = p.nZ;
+  const bool MF = !p.use_sc;
+  const int NPL = MF ? 7 : 6;
 
-  T* zs = reinterpret_cast<T*>(smem_raw);  // [2*MAX_Z]: zr[z] at 2z, zb[z] at 2z+1
-  unsigned char* wb = smem_raw + 2 * MAX_Z * sizeof(T) + (size_t)warp * p.warp_bytes;
+  T* zs = reinterpret_cast<T*>(smem_raw);          // [2*MAX_Z]: zr[z] at 2z, zb[z] at 2z+1
+  T* zrs = zs + 2 * MAX_Z;                           // [MAX_Z] ranges ascending
+  T* zbs = zrs + MAX_Z;                              // [MAX_Z] bearing of the same measurement
+  int* zid = reinterpret_cast<int*>(zbs + MAX_Z);    // [MAX_Z] its original index
+  unsigned char* wb = smem_raw + z_bytes<T>() + (size_t)warp * p.warp_bytes;
   T* bufA = reinterpret_cast<T*>(wb);
-  T* bufB = bufA + 7 * W;
-  unsigned* aux = reinterpret_cast<unsigned*>(bufB + 7 * W);  // [W]
+  T* bufB = bufA + NPL * W;                           // only present in multi-feature mode
+  unsigned char* after = reinterpret_cast<unsigned char*>(MF ? bufB + 7 * W : bufB);
+  T* scratch = reinterpret_cast<T*>(after);
+  unsigned* aux = reinterpret_cast<unsigned*>(after + scratch_bytes<T>(W));  // [W]
   T* colsum = reinterpret_cast<T*>(aux + W);                  // [MAX_Z]
   int* evalIdx = reinterpret_cast<int*>(colsum + MAX_Z);      // [MAX_EVAL]
   uint64_t* bar = reinterpret_cast<uint64_t*>(evalIdx + MAX_EVAL);
 
   for (int k = threadIdx.x; k < 2 * nZ; k += blockDim.x) zs[k] = p.Z[k];
+  for (int k = threadIdx.x; k < nZ; k += blockDim.x) {
+    zrs[k] = p.Zr_sorted[k];
+    zbs[k] = p.Zb_sorted[k];
+    zid[k] = p.Z_sorted_idx[k];
+  }
   if (lane == 0) {
     mbar_init(bar, 1);
     fence_mbar_init();
@@ -490,10 +583,13 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
   unsigned long long tot_in = 0, tot_out = 0;
   int max_out = 0, n_over = 0, n_murty = 0;
 
-  const int gw = blockIdx.x * WARPS_PER_CTA + warp;
-  const int gstride = gridDim.x * WARPS_PER_CTA;
+  while (true) {
+    // dynamic particle queue: one atomic per particle, broadcast to the warp
+    int pi = 0;
+    if (lane == 0) pi = (int)atomicAdd(p.work_counter, 1u);
+    pi = __shfl_sync(FULL, pi, 0);
+    if (pi >= p.N) break;
 
-  for (int pi = gw; pi < p.N; pi += gstride) {
     T* cur = bufA;
     T* alt = bufB;
     int nM = p.cnt_in[pi];
@@ -501,10 +597,6 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
     int flags = 0;
     if (nM > W) { nM = W; flags |= FLAG_OVERFLOW; }
     const double w_prev_particle = p.w_in[pi];
-
-    // previous particle's bulk stores must have finished reading bufB before it is reused
-    if (lane == 0) tma_store_wait_read();
-    __syncwarp();
 
     // ---------------- S0: TMA bulk loads -------------------------------------------------
     if (nM > 0) {
@@ -516,15 +608,16 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
 #pragma unroll
         for (int k = 0; k < 6; k++) tma_load_1d(cur + k * W, src + (size_t)k * p.cap, bytes, bar);
       }
-      mbar_wait(bar, phase);
-      phase ^= 1;
     }
-
     const T px = p.pose[4 * pi], py = p.pose[4 * pi + 1], pth = p.pose[4 * pi + 2];
     T c00 = 0, c01 = 0, c02 = 0, c11 = 0, c12 = 0, c22 = 0;
     if (p.pose_cov_mode) {
       const T* pc = p.pose_cov + (p.pose_cov_mode == 2 ? (size_t)pi * 8 : 0);
       c00 = pc[0]; c01 = pc[1]; c02 = pc[2]; c11 = pc[3]; c12 = pc[4]; c22 = pc[5];
+    }
+    if (nM > 0) {
+      mbar_wait(bar, phase);
+      phase ^= 1;
     }
 
     // ---------------- S1: corrector --------------------------------------------------------
@@ -534,7 +627,7 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
     bool over = false;
     for (int base = 0; base < nM; base += 32) {
       const int m = base + lane;
-      unsigned long long mask = 0;
+      unsigned long long cand = 0;
       T x = 0, y = 0, pxx = 0, pxy = 0, pyy = 0, w = 0;
       T zr_hat = 0, zb_hat = 0, i00 = 0, i01 = 0, i11 = 0, norm = 0, Pdw = 0;
       T hp00 = 0, hp01 = 0, hp10 = 0, hp11 = 0;
@@ -559,10 +652,12 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
         }
         if (close) Pd = T(1);
         if (Pd != T(0)) nfov++;
-        // missed-detection weight (:686-706); the sensing-limit heuristic is patched in S4
-        cur[6 * W + m] = w;                       // weight_prev
-        cur[5 * W + m] = (T(1) - Pd) * w;
-        aux[m] = (close && (w > p.birth_w)) ? 1u : 0u;
+        // missed-detection weight (:686-706); the sensing-limit heuristic is patched in S4,
+        // which still finds the pre-update weight of the flagged components in the weight plane
+        if (MF) cur[6 * W + m] = w;              // weight_prev (only importanceWeighting reads it)
+        const bool fix = close && (w > p.birth_w);
+        cur[5 * W + m] = fix ? w : (T(1) - Pd) * w;
+        aux[m] = fix ? 1u : 0u;
         if (Pd != T(0) && inrange) {              // measure() returns false outside [rmin,rmax]
           const T invr = T(1) / r;
           const T c = dx * invr, s = dy * invr;
@@ -588,23 +683,48 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
           i00 = s11 * invdet; i01 = -s01 * invdet; i11 = s00 * invdet;
           norm = T(1) / M<T>::sqrt_(M<T>::TWO_PI * M<T>::TWO_PI * det);
           Pdw = Pd * w;
-          const T cheap = p.gate2 * s00 * T(1.0001);  // md2 >= nu_r^2 / S_rr
-          for (int z = 0; z < nZ; z++) {
-            const T nr = zs[2 * z] - zr_hat;
-            if (nr * nr > cheap) continue;
-            if (p.thr_r > T(0) && M<T>::abs_(nr) > p.thr_r) continue;
-            const T nb_raw = zs[2 * z + 1] - zb_hat;
-            const T nb = wrap_pi<T>(nb_raw);
-            if (p.thr_b > T(0) && M<T>::abs_(nb) > p.thr_b) continue;
-            // Q3: likelihood and gate use the UNWRAPPED difference
-            const T md2 = (nr * i00 + nb_raw * i01) * nr + (nr * i01 + nb_raw * i11) * nb_raw;
-            if (md2 > p.gate2) continue;
-            T lik = M<T>::exp_(T(-0.5) * md2) * norm;
-            if (!(lik == lik) || lik == T(0)) continue;
-            if (!(Pdw * lik > T(0))) continue;
-            mask |= (1ull << z);
+          // candidate measurements: md2 >= nu_r^2/S_rr and md2 >= nu_b^2/S_bb for a PD S, so only the
+          // measurements inside the range window of the range-sorted batch whose bearing is close too
+          // can pass the gate (both bounds slightly widened against rounding).
+          if (det > T(0) && s00 > T(0) && s11 > T(0)) {
+            const T dr = M<T>::sqrt_(p.gate2 * s00 * T(1.0002));
+            const T cb = p.gate2 * s11 * T(1.0002);
+            const T rlo = zr_hat - dr, rhi = zr_hat + dr;
+            int lo = 0;
+#pragma unroll
+            for (int step = MAX_Z / 2; step >= 1; step >>= 1) {
+              const int k = lo + step;
+              if (k <= nZ && zrs[k - 1] < rlo) lo = k;
+            }
+            if (lo < nZ && zrs[lo] < rlo) lo++;
+            for (int k = lo; k < nZ; k++) {
+              if (zrs[k] > rhi) break;
+              const T nb = zbs[k] - zb_hat;
+              if (!(nb * nb > cb)) cand |= (1ull << zid[k]);
+            }
+          } else {
+            cand = (nZ >= 64) ? ~0ull : ((1ull << nZ) - 1ull);   // degenerate S: test everything
           }
         }
+      }
+      __syncwarp();
+      // full gate on the candidates, ascending z
+      unsigned long long mask = 0;
+      while (cand) {
+        const int z = __ffsll((long long)cand) - 1;
+        cand &= cand - 1;
+        const T nr = zs[2 * z] - zr_hat;
+        if (p.thr_r > T(0) && M<T>::abs_(nr) > p.thr_r) continue;
+        const T nb_raw = zs[2 * z + 1] - zb_hat;
+        const T nb = wrap_pi<T>(nb_raw);
+        if (p.thr_b > T(0) && M<T>::abs_(nb) > p.thr_b) continue;
+        // Q3: likelihood and gate use the UNWRAPPED difference
+        const T md2 = (nr * i00 + nb_raw * i01) * nr + (nr * i01 + nb_raw * i11) * nb_raw;
+        if (md2 > p.gate2) continue;
+        const T lik = M<T>::exp_(T(-0.5) * md2) * norm;
+        if (!(lik == lik) || lik == T(0)) continue;
+        if (!(Pdw * lik > T(0))) continue;
+        mask |= (1ull << z);
       }
       const int cnt = __popcll(mask);
       const int incl = warp_incl_scan(cnt, lane);
@@ -632,11 +752,12 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
           cur[W + off] = y + (k10 * nr + k11 * nb);
           cur[2 * W + off] = n00; cur[3 * W + off] = n01; cur[4 * W + off] = n11;
           cur[5 * W + off] = Pdw * lik;   // un-normalised; divided by the column sum in S3
-          cur[6 * W + off] = T(0);
+          if (MF) cur[6 * W + off] = T(0);
           aux[off] = ((unsigned)m << 8) | (unsigned)z;
           off++;
         }
       }
+      __syncwarp();
     }
     if (__any_sync(FULL, over)) flags |= FLAG_OVERFLOW;
     if (nM + nS > W) nS = W - nM;
@@ -680,19 +801,23 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
       }
       __syncwarp();
       // ---------------- S4: sensing-limit heuristic (:692-703, Q2) --------------------------
-      for (int m = lane; m < nM; m += 32) {
-        if (aux[m] & 1u) {
-          const T w_km = cur[6 * W + m];
-          T rowsum = T(0);
-          for (int s = nM; s < n; s++)
-            if ((int)(aux[s] >> 8) == m) rowsum += cur[5 * W + s];
-          const T delta = w_km - rowsum;   // Pd[m] == 1 here
-          T w_k = cur[5 * W + m];
-          if (delta > T(0)) {
-            w_k += delta;
-            if (w_k > T(1)) w_k = T(1);
+      for (int mb = 0; mb < nM; mb += 32) {
+        const int m = mb + lane;
+        const unsigned am = (m < nM) ? aux[m] : 0u;
+        if (__any_sync(FULL, am != 0u)) {
+          if (am) {
+            const T w_km = cur[5 * W + m];   // still the pre-update weight (see S1)
+            T rowsum = T(0);
+            for (int s = nM; s < n; s++)
+              if ((int)(aux[s] >> 8) == m) rowsum += cur[5 * W + s];
+            const T delta = w_km - rowsum;   // Pd[m] == 1 here
+            T w_k = (T(1) - T(1)) * w_km;
+            if (delta > T(0)) {
+              w_k += delta;
+              if (w_k > T(1)) w_k = T(1);
+            }
+            cur[5 * W + m] = w_k;
           }
-          cur[5 * W + m] = w_k;
         }
       }
       __syncwarp();
@@ -948,14 +1073,14 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
     // ---------------- S6: merge ------------------------------------------------------------------
     if (n > 1) {
       if (p.merge_algo == 0) merge_bruteforce<T>(cur, W, n, p.merge_t2, p.merge_f, lane);
-      else merge_culled<T>(cur, alt, W, n, p.merge_t2, p.merge_f, lane);
+      else merge_culled<T>(cur, scratch, W, n, p.merge_t2, p.merge_f, lane);
     }
     __syncwarp();
 
     // ---------------- S7: prune + store ------------------------------------------------------------
     int n_out = 0;
     {
-      T* kw = alt + 6 * W;
+      T* kw = scratch;   // [W] sort keys (the merge scratch is dead)
       for (int base = 0; base < n; base += 32) {
         const int k = base + lane;
         bool keep = false;
@@ -974,16 +1099,12 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
       __syncwarp();
       if (n_out > 1) warp_bitonic(kw, aux, P, lane);
       if (n_out > p.cap) { n_out = p.cap; flags |= FLAG_OVERFLOW; }
-      for (int pl = 0; pl < 6; pl++)
-        for (int k = lane; k < n_out; k += 32) alt[pl * W + k] = cur[pl * W + aux[k]];
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0 && n_out > 0) {
-        const uint32_t bytes = (uint32_t)(((n_out + 3) & ~3) * sizeof(T));
-        T* dst = p.gm_out + (size_t)pi * 6 * p.cap;
+      // gather from shared memory, 128-byte coalesced stores to the particle's planes in HBM
+      T* dst = p.gm_out + (size_t)pi * 6 * p.cap;
+      for (int k = lane; k < n_out; k += 32) {
+        const unsigned src = aux[k];
 #pragma unroll
-        for (int k = 0; k < 6; k++) tma_store_1d(dst + (size_t)k * p.cap, alt + k * W, bytes);
-        tma_store_commit();
+        for (int pl = 0; pl < 6; pl++) dst[(size_t)pl * p.cap + k] = cur[pl * W + src];
       }
     }
     if (lane == 0) {
@@ -998,11 +1119,9 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
     max_out = n_out > max_out ? n_out : max_out;
     if (flags & (FLAG_OVERFLOW | FLAG_DP_OVERFLOW)) n_over++;
     if (flags & FLAG_MURTY) n_murty++;
-    // note: bufA/bufB roles are fixed per iteration start (cur=bufA); the store reads `alt`,
-    // which may be bufA or bufB, so the wait at the top of the loop covers both.
+    __syncwarp();
   }
   if (lane == 0) {
-    tma_store_wait_all();
     if (tot_in) atomicAdd(&p.totals[0], tot_in);
     if (tot_out) atomicAdd(&p.totals[1], tot_out);
     atomicMax(&p.istats[0], max_out);
@@ -1037,7 +1156,16 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
       for (int k = 0; k < WARPS_PER_CTA; k++) { a += red[0][k]; b += red[1][k]; }
       p.sums[0] = a;
       p.sums[1] = b;
+      // publish the step statistics and re-arm the accumulators / queue for the next launch
+      p.stats_out[0] = __ldcg(&p.totals[0]);
+      p.stats_out[1] = __ldcg(&p.totals[1]);
+      p.stats_out[2] = (unsigned long long)(unsigned)__ldcg(&p.istats[0]);
+      p.stats_out[3] = (unsigned long long)(unsigned)__ldcg(&p.istats[1]);
+      p.stats_out[4] = (unsigned long long)(unsigned)__ldcg(&p.istats[2]);
+      p.totals[0] = 0; p.totals[1] = 0;
+      p.istats[0] = 0; p.istats[1] = 0; p.istats[2] = 0;
       *p.ticket = 0;
+      *p.work_counter = 0;
     }
   }
 }

@@ -39,6 +39,8 @@ struct rfsb200_ctx {
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t zev[8] = {};   // one per pinned Z staging slot: the H2D copy that last read it
+  unsigned zslot = 0;
   StateBuf st[2];
   int front = 0;     // committed state
   int last_out = 0;  // buffer written by the last update (== front unless NO_COMMIT)
@@ -53,6 +55,9 @@ struct rfsb200_ctx {
   unsigned long long* totals = nullptr;   // [2]
   int* istats = nullptr;                  // [4]
   unsigned int* ticket = nullptr;
+  unsigned int* work_counter = nullptr;
+  unsigned long long* stats_out = nullptr;  // [8]
+  int cfg_mode_mf = -1;                      // launch configuration was computed for this mode
   // staging (device): packed fp64 + offsets
   double* stg = nullptr;       // N*cap*6 doubles
   long long* offs = nullptr;   // [N+1]
@@ -191,19 +196,10 @@ int round_pow2(int v) {
 }
 
 template <typename T>
-int warp_smem_bytes(int W) {
-  size_t b = (size_t)14 * W * sizeof(T) + (size_t)W * 4 + MAX_Z * sizeof(T) + MAX_EVAL * 4 + 16;
-  return (int)((b + 127) & ~(size_t)127);
-}
-
-template <typename T>
-int configure_launch(rfsb200_ctx* c) {
-  c->warp_bytes = warp_smem_bytes<T>(c->W);
-  c->smem_bytes = 2 * MAX_Z * sizeof(T) + (size_t)WARPS_PER_CTA * c->warp_bytes;
-  // scratch requirements inside one 7*W plane block
-  const size_t blk = (size_t)7 * c->W * sizeof(T);
-  const size_t merge_need = (size_t)c->W * sizeof(T) + MAX_PAIRS * 4 + 2 * 258 * 2 + (size_t)(c->W + 2) * 2 + 8;
-  if (merge_need > blk) return fail(c, RFSB200_EINVAL, "work_capacity too small for merge scratch");
+int configure_launch(rfsb200_ctx* c, int mf) {
+  if (c->cfg_mode_mf == mf) return RFSB200_OK;
+  c->warp_bytes = warp_bytes_for<T>(c->W, mf);
+  c->smem_bytes = (size_t)z_bytes<T>() + (size_t)WARPS_PER_CTA * c->warp_bytes;
   if (c->smem_bytes > 227 * 1024) return fail(c, RFSB200_ECAPACITY, "work_capacity %d needs %zu B shared memory per CTA (> 227 KB)", c->W, c->smem_bytes);
   CU(c, cudaFuncSetAttribute(phd_update_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
   int occ = 0;
@@ -211,6 +207,7 @@ int configure_launch(rfsb200_ctx* c) {
   if (occ < 1) return fail(c, RFSB200_ECAPACITY, "kernel does not fit on an SM");
   const int need = (c->N + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
   c->grid = std::max(1, std::min(need, occ * c->sm_count));
+  c->cfg_mode_mf = mf;
   return RFSB200_OK;
 }
 
@@ -239,10 +236,19 @@ int launch_update(rfsb200_ctx* c, int nZ, int out_idx) {
   const StateBuf& in = c->st[c->front];
   const StateBuf& out = c->st[out_idx];
   p.gm_in = (const T*)in.gm; p.cnt_in = in.cnt; p.w_in = in.weight;
-  p.pose = (const T*)c->pose; p.pose_cov = (const T*)c->pose_cov; p.Z = (const T*)c->Zdev;
+  p.pose = (const T*)c->pose; p.pose_cov = (const T*)c->pose_cov;
+  p.Z = (const T*)c->Zdev;
+  p.Zr_sorted = p.Z + 2 * MAX_Z; p.Zb_sorted = p.Z + 3 * MAX_Z;
+  p.Z_sorted_idx = (const int*)(p.Z + 4 * MAX_Z);
   p.gm_out = (T*)out.gm; p.cnt_out = out.cnt; p.w_out = out.weight;
   p.unused = c->unused; p.nfov = c->nfov; p.flags = c->flags;
   p.sums = c->sums; p.totals = c->totals; p.istats = c->istats; p.ticket = c->ticket;
+  p.work_counter = c->work_counter; p.stats_out = c->stats_out;
+  {
+    int rc = configure_launch<T>(c, f.use_cluster_process ? 0 : 1);
+    if (rc) return rc;
+    p.warp_bytes = c->warp_bytes;
+  }
   phd_update_kernel<T><<<c->grid, WARPS_PER_CTA * 32, c->smem_bytes, c->stream>>>(p);
   CU(c, cudaGetLastError());
   return RFSB200_OK;
@@ -311,6 +317,7 @@ int rfsb200_create(rfsb200_ctx** out, const rfsb200_dims* d) {
     c->stream = c->own_stream;
     CU(c, cudaEventCreate(&c->ev0));
     CU(c, cudaEventCreate(&c->ev1));
+    for (int k = 0; k < 8; k++) CU(c, cudaEventCreateWithFlags(&c->zev[k], cudaEventDisableTiming));
     const size_t gm_bytes = (size_t)c->N * 6 * c->cap * c->tsize;
     for (int k = 0; k < 2; k++) {
       CU(c, cudaMalloc(&c->st[k].gm, gm_bytes));
@@ -323,7 +330,7 @@ int rfsb200_create(rfsb200_ctx** out, const rfsb200_dims* d) {
     CU(c, cudaMalloc(&c->pose, (size_t)c->N * 4 * c->tsize));
     CU(c, cudaMalloc(&c->pose_cov, (size_t)c->N * 8 * c->tsize));
     CU(c, cudaMemset(c->pose_cov, 0, (size_t)c->N * 8 * c->tsize));
-    CU(c, cudaMalloc(&c->Zdev, (size_t)MAX_Z * 2 * c->tsize));
+    CU(c, cudaMalloc(&c->Zdev, (size_t)MAX_Z * 4 * c->tsize + MAX_Z * 4));
     CU(c, cudaMalloc((void**)&c->unused, (size_t)c->N * 8));
     CU(c, cudaMalloc((void**)&c->nfov, (size_t)c->N * 4));
     CU(c, cudaMalloc((void**)&c->flags, (size_t)c->N * 4));
@@ -334,6 +341,12 @@ int rfsb200_create(rfsb200_ctx** out, const rfsb200_dims* d) {
     CU(c, cudaMalloc((void**)&c->totals, 16));
     CU(c, cudaMalloc((void**)&c->istats, 16));
     CU(c, cudaMalloc((void**)&c->ticket, 4));
+    CU(c, cudaMalloc((void**)&c->work_counter, 4));
+    CU(c, cudaMalloc((void**)&c->stats_out, 64));
+    CU(c, cudaMemset(c->work_counter, 0, 4));
+    CU(c, cudaMemset(c->stats_out, 0, 64));
+    CU(c, cudaMemset(c->totals, 0, 16));
+    CU(c, cudaMemset(c->istats, 0, 16));
     CU(c, cudaMemset(c->sums, 0, 16));
     CU(c, cudaMemset(c->ticket, 0, 4));
     CU(c, cudaMalloc((void**)&c->stg, (size_t)c->N * c->cap * 6 * 8));
@@ -341,8 +354,8 @@ int rfsb200_create(rfsb200_ctx** out, const rfsb200_dims* d) {
     CU(c, cudaMalloc((void**)&c->stg_small, (size_t)c->N * 16 * 8));
     int r = ensure_pinned(c, 1 << 16);
     if (r) return r;
-    if (c->prec == 32) r = configure_launch<float>(c);
-    else r = configure_launch<double>(c);
+    if (c->prec == 32) r = configure_launch<float>(c, 0);
+    else r = configure_launch<double>(c, 0);
     if (r) return r;
     CU(c, cudaDeviceSynchronize());
     return RFSB200_OK;
@@ -367,10 +380,12 @@ int rfsb200_destroy(rfsb200_ctx* c) {
   cudaFree(c->pose); cudaFree(c->pose_cov); cudaFree(c->Zdev);
   cudaFree(c->unused); cudaFree(c->nfov); cudaFree(c->flags);
   cudaFree(c->sums); cudaFree(c->totals); cudaFree(c->istats); cudaFree(c->ticket);
+  cudaFree(c->work_counter); cudaFree(c->stats_out);
   cudaFree(c->stg); cudaFree(c->offs); cudaFree(c->stg_small);
   if (c->hpin) cudaFreeHost(c->hpin);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
+  for (int k = 0; k < 8; k++) if (c->zev[k]) cudaEventDestroy(c->zev[k]);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
   return RFSB200_OK;
@@ -476,18 +491,41 @@ int rfsb200_update(rfsb200_ctx* c, const double* Z, int32_t nZ, uint32_t flags, 
   if (nZ == 0) return RFSB200_OK;  // include/RBPHDFilter.hpp:451-452 (Q11)
   if (!Z) return fail(c, RFSB200_EINVAL, "NULL Z");
   CU(c, cudaSetDevice(c->device));
-  // Z -> T in pinned scratch -> device
-  if (c->prec == 32) {
-    float* h = (float*)c->hpin;
-    for (int k = 0; k < 2 * nZ; k++) h[k] = (float)Z[k];
-  } else {
-    memcpy(c->hpin, Z, (size_t)nZ * 16);
+  // Z -> T in pinned scratch -> device: original pairs + the batch sorted by range (for the
+  // corrector's window search)
+  unsigned char* zsrc = nullptr;
+  unsigned zslot_used = 0;
+  {
+    int order[MAX_Z];
+    for (int k = 0; k < nZ; k++) order[k] = k;
+    std::stable_sort(order, order + nZ, [&](int a, int b) { return Z[2 * a] < Z[2 * b]; });
+    const unsigned slot = (c->zslot++) & 7u;
+    CU(c, cudaEventSynchronize(c->zev[slot]));   // the copy that last read this slot has finished
+    unsigned char* hb = c->hpin + 16384 + (size_t)slot * 4096;
+    zsrc = hb;
+    zslot_used = slot;
+    int* hidx = (int*)(hb + (size_t)4 * MAX_Z * c->tsize);
+    if (c->prec == 32) {
+      float* h = (float*)hb;
+      for (int k = 0; k < 2 * nZ; k++) h[k] = (float)Z[k];
+      for (int k = 0; k < nZ; k++) {
+        h[2 * MAX_Z + k] = (float)Z[2 * order[k]];
+        h[3 * MAX_Z + k] = (float)Z[2 * order[k] + 1];
+      }
+    } else {
+      double* h = (double*)hb;
+      for (int k = 0; k < 2 * nZ; k++) h[k] = Z[k];
+      for (int k = 0; k < nZ; k++) {
+        h[2 * MAX_Z + k] = Z[2 * order[k]];
+        h[3 * MAX_Z + k] = Z[2 * order[k] + 1];
+      }
+    }
+    for (int k = 0; k < nZ; k++) hidx[k] = order[k];
   }
   int launches = 0;
   if (out) CU(c, cudaEventRecord(c->ev0, c->stream));
-  CU(c, cudaMemcpyAsync(c->Zdev, c->hpin, (size_t)nZ * 2 * c->tsize, cudaMemcpyHostToDevice, c->stream));
-  CU(c, cudaMemsetAsync(c->totals, 0, 16, c->stream));
-  CU(c, cudaMemsetAsync(c->istats, 0, 16, c->stream));
+  CU(c, cudaMemcpyAsync(c->Zdev, zsrc, (size_t)4 * MAX_Z * c->tsize + MAX_Z * 4, cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaEventRecord(c->zev[zslot_used], c->stream));
   const int out_idx = c->front ^ 1;
   int rc = (c->prec == 32) ? launch_update<float>(c, nZ, out_idx) : launch_update<double>(c, nZ, out_idx);
   if (rc) return rc;
@@ -501,22 +539,20 @@ int rfsb200_update(rfsb200_ctx* c, const double* Z, int32_t nZ, uint32_t flags, 
   if (!(flags & RFSB200_UPDATE_NO_COMMIT)) c->front = out_idx;
   if (out) {
     CU(c, cudaEventRecord(c->ev1, c->stream));
-    unsigned char* h = c->hpin + 4096;
+    unsigned char* h = c->hpin + 8192;
     CU(c, cudaMemcpyAsync(h, c->sums, 16, cudaMemcpyDeviceToHost, c->stream));
-    CU(c, cudaMemcpyAsync(h + 16, c->totals, 16, cudaMemcpyDeviceToHost, c->stream));
-    CU(c, cudaMemcpyAsync(h + 32, c->istats, 16, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaMemcpyAsync(h + 16, c->stats_out, 40, cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
     const double* s = (const double*)h;
     const unsigned long long* t = (const unsigned long long*)(h + 16);
-    const int* is = (const int*)(h + 32);
     out->sum_w = s[0];
     out->sum_w2 = s[1];
     out->n_eff = s[1] > 0 ? s[0] * s[0] / s[1] : 0;
     out->gm_total_in = (int64_t)t[0];
     out->gm_total_out = (int64_t)t[1];
-    out->gm_max_out = is[0];
-    out->n_overflow = is[1];
-    out->n_murty = is[2];
+    out->gm_max_out = (int32_t)t[2];
+    out->n_overflow = (int32_t)t[3];
+    out->n_murty = (int32_t)t[4];
     out->n_launches = launches;
     float ms = 0;
     CU(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));

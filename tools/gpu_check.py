@@ -33,7 +33,7 @@ wl = synth.make_workload(N=a.N, nM=a.nM, nZ=a.nZ, use_cluster_process=a.sc, worl
 t = time.time()
 ref = ob.run(wl, sort_mode=ob.SORT_STABLE)
 print(f"oracle: {time.time()-t:.3f}s  mean nM_out {ref.count.mean():.2f}")
-up = PHDUpdater(a.N, gm_capacity=max(256, a.nM + 56), precision=a.prec)
+up = PHDUpdater(a.N, gm_capacity=max(256, a.nM + 56), precision=a.prec, z_capacity=max(32, a.nZ))
 up.set_model(wl.model)
 up.set_filter_cfg(wl.cfg, brute_force_merge=bool(a.brute))
 up.upload_maps(wl.count, wl.mean, wl.cov, wl.w)
