@@ -67,6 +67,8 @@ def _load(which: str):
         lib.phd_oracle_partition_likelihood.restype = C.c_double
         lib.phd_oracle_partition_likelihood.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p,
                                                         C.c_void_p, C.c_void_p]
+        lib.phd_oracle_partition.restype = C.c_int
+        lib.phd_oracle_partition.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.phd_oracle_murty_sum.restype = C.c_double
         lib.phd_oracle_murty_sum.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     else:
@@ -190,3 +192,13 @@ def murty_sum(Lp: np.ndarray, rowPd: np.ndarray, colClutter: np.ndarray) -> floa
     colClutter = np.ascontiguousarray(colClutter, dtype=np.float64)
     return float(lib.phd_oracle_murty_sum(Lp.ctypes.data, Lp.shape[0], Lp.shape[1],
                                           rowPd.ctypes.data, colClutter.ctypes.data))
+
+
+def partition(L: np.ndarray):
+    """(nP, nRows[nP], nCols[nP], isZero[nP]) as the reference's caller sees them (Q6)."""
+    lib, _ = _load("oracle")
+    L = np.ascontiguousarray(L, dtype=np.float64)
+    nR, nC = L.shape
+    a = np.zeros(128, np.int32); b = np.zeros(128, np.int32); z = np.zeros(128, np.int32)
+    nP = lib.phd_oracle_partition(L.ctypes.data, nR, nC, a.ctypes.data, b.ctypes.data, z.ctypes.data)
+    return nP, a[:nP].copy(), b[:nP].copy(), z[:nP].copy()

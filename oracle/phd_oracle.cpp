@@ -716,10 +716,14 @@ double lexi_sum(const double* Lp, int nR, int nC, const double* rowPd, const dou
  * Labels: boost::connected_components numbers components in order of their lowest vertex
  * (vertices = rows 0..nR-1 then columns nR..nR+nC-1).
  */
-double partition_likelihood(const double* L, int nE, int nZ, const double* evalPd,
-                            const double* clutter, int32_t* flags) {
+struct Partitioning {
+  std::vector<std::vector<unsigned>> ci, cj;
+  int combinedZero, nP;
+};
+
+Partitioning partition_table(const double* L, int nE, int nZ) {
+  Partitioning P;
   int nV = nE + nZ;
-  if (nV == 0) return 1;
   std::vector<int> label(nV, -1);
   int ncc = 0;
   for (int v = 0; v < nV; v++) {
@@ -747,24 +751,38 @@ double partition_likelihood(const double* L, int nE, int nZ, const double* evalP
     }
     ncc++;
   }
-  std::vector<std::vector<unsigned>> ci(ncc), cj(ncc);
-  for (int i = 0; i < nE; i++) ci[label[i]].push_back(i);
-  for (int j = nE; j < nV; j++) cj[label[j]].push_back(j - nE);
+  P.ci.assign(ncc, std::vector<unsigned>());
+  P.cj.assign(ncc, std::vector<unsigned>());
+  for (int i = 0; i < nE; i++) P.ci[label[i]].push_back(i);
+  for (int j = nE; j < nV; j++) P.cj[label[j]].push_back(j - nE);
   int combinedZero = -1, nMerged = 0;
   for (int n = 0; n < ncc; n++) {
-    if (ci[n].size() == 0 || cj[n].size() == 0) {
+    if (P.ci[n].size() == 0 || P.cj[n].size() == 0) {
       if (combinedZero == -1)
         combinedZero = n;
-      else if (ci[n].size() != 0) {
-        ci[combinedZero].push_back(ci[n][0]);
+      else if (P.ci[n].size() != 0) {
+        P.ci[combinedZero].push_back(P.ci[n][0]);
         nMerged++;
       } else {
-        cj[combinedZero].push_back(cj[n][0]);
+        P.cj[combinedZero].push_back(P.cj[n][0]);
         nMerged++;
       }
     }
   }
-  int nP = ncc - nMerged;
+  P.combinedZero = combinedZero;
+  P.nP = ncc - nMerged;
+  return P;
+}
+
+double partition_likelihood(const double* L, int nE, int nZ, const double* evalPd,
+                            const double* clutter, int32_t* flags) {
+  int nV = nE + nZ;
+  if (nV == 0) return 1;
+  Partitioning P = partition_table(L, nE, nZ);
+  std::vector<std::vector<unsigned>>& ci = P.ci;
+  std::vector<std::vector<unsigned>>& cj = P.cj;
+  const int combinedZero = P.combinedZero;
+  int nP = P.nP;
   double l = 1;
   for (int p = 0; p < nP; p++) {
     int nRows = ci[p].size(), nCols = cj[p].size();
@@ -1099,6 +1117,16 @@ extern "C" double phd_oracle_partition_likelihood(const double* L, int nE, int n
                                                   const double* evalPd, const double* clutter,
                                                   int32_t* flags) {
   return partition_likelihood(L, nE, nZ, evalPd, clutter, flags);
+}
+
+extern "C" int phd_oracle_partition(const double* L, int nR, int nC, int* nRows, int* nCols, int* isZero) {
+  Partitioning P = partition_table(L, nR, nC);
+  for (int p = 0; p < P.nP; p++) {
+    nRows[p] = (int)P.ci[p].size();
+    nCols[p] = (int)P.cj[p].size();
+    isZero[p] = (p == P.combinedZero) ? 1 : 0;
+  }
+  return P.nP;
 }
 
 extern "C" double phd_oracle_murty_sum(const double* Lp, int nR, int nC, const double* rowPd,

@@ -78,6 +78,9 @@ int64_t phd_oracle_lexi_count(int nM, int nZ);
 double phd_oracle_partition_likelihood(const double* L, int nE, int nZ, const double* evalPd,
                                        const double* clutter, int32_t* flags);
 
+/* CostMatrixGeneral::partition() + getPartitionSize() for p < nP (src/CostMatrix.cpp:92-173) */
+int phd_oracle_partition(const double* L, int nR, int nC, int* nRows, int* nCols, int* isZero);
+
 /* k-best assignment sum exactly as include/RBPHDFilter.hpp:920-959 on one partition
  * Cp [nR][nC] of likelihoods (0 = no edge). */
 double phd_oracle_murty_sum(const double* Lp, int nR, int nC, const double* rowPd,

@@ -115,7 +115,8 @@ class _Rng:
 
 def make_workload(N: int, nM: int, nZ: int, *, use_cluster_process: int = 1, world: str = "dense",
                   config_id: int = 0, parity_extras: bool = False, ragged: float = 0.0,
-                  model: dict | None = None, cfg: dict | None = None, seed: int | None = None) -> Workload:
+                  model: dict | None = None, cfg: dict | None = None, seed: int | None = None,
+                  shard_id: int = 0) -> Workload:
     md = dict(DEFAULT_MODEL)
     if model:
         md.update(model)
@@ -150,7 +151,26 @@ def make_workload(N: int, nM: int, nZ: int, *, use_cluster_process: int = 1, wor
         r[k + 1] = 0.4 * (r_lo + r_hi)
     lmk = np.stack([r * np.cos(b), r * np.sin(b)], axis=1)
 
-    # ---- particles ----
+    # ---- measurements (shared) ----
+    n_real = int(math.floor(0.8 * nZ))
+    rl = np.hypot(lmk[:, 0], lmk[:, 1])
+    in_range = np.nonzero((rl >= rmin) & (rl <= rmax))[0]
+    n_real = min(n_real, len(in_range))
+    perm = rng.g.permutation(len(in_range))[:n_real]
+    sel = in_range[perm]
+    if parity_extras and nM >= 20 and n_real >= 2:
+        k = max(4, nM // 20)
+        sel[0], sel[1] = k, k + 1  # the two landmarks at bearing ~ +-pi are observed
+    zr = rl[sel] + math.sqrt(5e-4) * rng.normal(n_real)
+    zb = np.arctan2(lmk[sel, 1], lmk[sel, 0]) + math.sqrt(5e-5) * rng.normal(n_real)
+    zb = (zb + math.pi) % (2 * math.pi) - math.pi
+    n_cl = nZ - n_real
+    cr = rng.uniform(rmin, rmax, n_cl)
+    cb = rng.uniform(-math.pi, math.pi, n_cl)
+    Z = np.stack([np.concatenate([zr, cr]), np.concatenate([zb, cb])], axis=1)
+
+    # ---- particles (their own stream, so that shards of one job share the world and Z) ----
+    rng = _Rng((0xB2000000 + config_id if seed is None else seed) + 7919 * (1 + shard_id))
     pose = rng.normal((N, 3)) * np.array([0.05, 0.05, 0.01])
     pose_cov = np.array([3e-5, 0.0, 0.0, 3e-5, 0.0, 3e-5])
     weight = np.ones(N)
@@ -177,24 +197,6 @@ def make_workload(N: int, nM: int, nZ: int, *, use_cluster_process: int = 1, wor
     mean = mean[keep]
     cov = cov[keep]
     w = w[keep]
-
-    # ---- measurements (shared) ----
-    n_real = int(math.floor(0.8 * nZ))
-    rl = np.hypot(lmk[:, 0], lmk[:, 1])
-    in_range = np.nonzero((rl >= rmin) & (rl <= rmax))[0]
-    n_real = min(n_real, len(in_range))
-    perm = rng.g.permutation(len(in_range))[:n_real]
-    sel = in_range[perm]
-    if parity_extras and nM >= 20 and n_real >= 2:
-        k = max(4, nM // 20)
-        sel[0], sel[1] = k, k + 1  # the two landmarks at bearing ~ +-pi are observed
-    zr = rl[sel] + math.sqrt(5e-4) * rng.normal(n_real)
-    zb = np.arctan2(lmk[sel, 1], lmk[sel, 0]) + math.sqrt(5e-5) * rng.normal(n_real)
-    zb = (zb + math.pi) % (2 * math.pi) - math.pi
-    n_cl = nZ - n_real
-    cr = rng.uniform(rmin, rmax, n_cl)
-    cb = rng.uniform(-math.pi, math.pi, n_cl)
-    Z = np.stack([np.concatenate([zr, cr]), np.concatenate([zb, cb])], axis=1)
 
     return Workload(count=np.ascontiguousarray(count), mean=np.ascontiguousarray(mean),
                     cov=np.ascontiguousarray(cov), w=np.ascontiguousarray(w),

@@ -65,3 +65,79 @@ def compare_weights(w_dev, w_ref, tol, mask=None):
     return dict(max_dlog=float(dl.max()) if dl.size else 0.0,
                 n_bad=int((dl > tol["logw_abs"]).sum()) + int((mask & ((w_ref > 0) != (w_dev > 0))).sum()),
                 idx_bad=np.nonzero(ok)[0][dl > tol["logw_abs"]] if dl.size else np.array([], dtype=int))
+
+
+# ---- golden fixtures (tests/golden/*.npz, generated from the compiled reference) -----------------
+import json
+import os
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+GOLDEN_CASES = ["sc_dense", "sc_extras", "mf_dense", "mf_extras", "mf_sparse_ragged", "mf_lowpd"]
+
+
+def load_golden(name):
+    """-> (Workload rebuilt from the fixture's inputs, dict of the reference's outputs)."""
+    from rfs_slam_b200 import synth
+    g = np.load(os.path.join(GOLDEN_DIR, f"phd_{name}.npz"), allow_pickle=False)
+    wl = synth.Workload(count=g["count_in"].astype(np.int32), mean=g["mean_in"], cov=g["cov_in"], w=g["w_in"],
+                        pose=g["pose"], pose_cov=g["pose_cov"], weight=g["weight_in"], Z=g["Z"],
+                        model=json.loads(str(g["model_json"])), cfg=json.loads(str(g["cfg_json"])))
+    return wl, g
+
+
+def golden_stage(g, st):
+    return dict(count=g[f"s{st}_count"], mean=g[f"s{st}_mean"], cov=g[f"s{st}_cov"], w=g[f"s{st}_w"],
+                wprev=g[f"s{st}_wprev"], weight=g[f"s{st}_weight"], unused=g[f"s{st}_unused"], nfov=g[f"s{st}_nfov"])
+
+
+# ---- epsilon-band exclusion (SURVEY.md §8d "structural decisions must agree except ...") ---------
+def robust_mask(wl, eps=1e-3):
+    """Particles whose discrete decisions (gate, sensing limit, merge, prune, eval-point cut) do
+    not change when every threshold is moved by +-eps (relative; absolute 1e-5 on range limits):
+    for those an fp32 device result must agree STRUCTURALLY with the fp64 oracle.  The others sit
+    inside the epsilon band of some threshold and are listed / excluded by the caller."""
+    import copy
+    from oracle import binding as ob
+
+    def run(scale):
+        w2 = copy.copy(wl)
+        w2.cfg = dict(wl.cfg)
+        w2.model = dict(wl.model)
+        h = 0.5 * eps * scale  # thresholds are squared inside -> eps on the squared value
+        for k in ("new_gaussian_create_innov_md_threshold", "meas_likelihood_md_threshold", "merging_threshold"):
+            w2.cfg[k] = wl.cfg[k] * (1 + h)
+        for k in ("pruning_threshold", "eval_point_gaussian_weight", "birth_gaussian_weight"):
+            w2.cfg[k] = wl.cfg[k] * (1 + 1e-4 * scale)
+        w2.model["range_max"] = wl.model["range_max"] + 1e-5 * scale
+        w2.model["range_min"] = wl.model["range_min"] - 1e-5 * scale
+        w2.model["range_buffer"] = wl.model["range_buffer"] + 2e-5 * scale
+        for k in ("innov_thr_range", "innov_thr_bearing"):
+            w2.model[k] = wl.model[k] * (1 + 1e-5 * scale)
+        return [ob.run(w2, stage=s, sort_mode=ob.SORT_STABLE) for s in (1, 3, 4)]
+
+    base, up, dn = run(0), run(+1), run(-1)
+    ok = np.ones(wl.N, dtype=bool)
+    for a, b, c in zip(base, up, dn):
+        ok &= (a.count == b.count) & (a.count == c.count)
+        ok &= (a.unused_mask == b.unused_mask) & (a.unused_mask == c.unused_mask)
+        ok &= (a.n_in_fov == b.n_in_fov) & (a.n_in_fov == c.n_in_fov)
+    return ok
+
+
+def run_device(wl, precision=32, flags=None, gm_capacity=None, work_capacity=0, brute=False, z_capacity=None):
+    """One update through the C ABI; returns (step_out, count, mean, cov, w, particle_weights, updater)."""
+    from rfs_slam_b200 import capi
+    from rfs_slam_b200.phd import PHDUpdater
+    cap = gm_capacity or int(max(64, (int(wl.count.max()) + 63) // 8 * 8))
+    up = PHDUpdater(wl.N, gm_capacity=cap, work_capacity=work_capacity, precision=precision,
+                    z_capacity=z_capacity or max(8, wl.nZ))
+    up.set_model(wl.model)
+    up.set_filter_cfg(wl.cfg, brute_force_merge=brute)
+    up.upload_maps(wl.count, wl.mean, wl.cov, wl.w)
+    up.set_poses(wl.pose, wl.pose_cov, wl.weight)
+    f = capi.UPDATE_NO_NORMALIZE if flags is None else flags
+    so = up.update(wl.Z, flags=f)
+    which = 1 if (f & capi.UPDATE_NO_COMMIT) else 0
+    cnt, mean, cov, w = up.download_maps(which)
+    pw = up.get_weights(which)
+    return so, cnt, mean, cov, w, pw, up

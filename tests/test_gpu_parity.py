@@ -1,0 +1,225 @@
+"""Parity tests proper: the CUDA path (through the C ABI) against the golden vectors produced by
+the reference itself and against the pinned fp64 oracle.  Tolerances are SURVEY.md §8(d):
+fp32 device: |dw| <= 1e-5 + 1e-4 w, |dmean| <= 1e-4 m, cov rel Frobenius <= 1e-3, |dlog w_particle| <= 2e-3;
+fp64 device build: 1e-10 relative with identical structure."""
+import numpy as np
+import pytest
+
+import helpers
+from helpers import TOL32, TOL64
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(wl, prec, ref, so, cnt, mean, cov, w, pw, robust=None, max_excluded=0.02):
+    tol = TOL32 if prec == 32 else TOL64
+    r = helpers.compare_maps(cnt, mean, cov, w, ref["count"], ref["mean"], ref["cov"], ref["w"], tol)
+    bad = set(r["bad"])
+    rw = helpers.compare_weights(pw, ref["weight"], tol)
+    bad |= set(int(i) for i in rw["idx_bad"])
+    if prec == 64 or robust is None:
+        assert not bad, f"particles differ from the reference: {sorted(bad)[:10]}"
+    else:
+        # fp32: a particle may only differ if it sits in the epsilon band of a threshold
+        unexplained = [i for i in bad if robust[i]]
+        assert not unexplained, f"robust particles differ: {unexplained[:10]}"
+        assert len(bad) <= max(1, int(max_excluded * wl.N)), f"{len(bad)} particles in an epsilon band"
+    return r, rw
+
+
+@pytest.mark.parametrize("prec", [32, 64])
+@pytest.mark.parametrize("case", helpers.GOLDEN_CASES)
+def test_against_reference_golden(cuda_required, case, prec):
+    wl, g = helpers.load_golden(case)
+    ref = helpers.golden_stage(g, 4)
+    so, cnt, mean, cov, w, pw, up = helpers.run_device(wl, precision=prec)
+    robust = helpers.robust_mask(wl) if prec == 32 else None
+    _check(wl, prec, ref, so, cnt, mean, cov, w, pw, robust)
+    mask, nfov = up.get_unused()
+    ok = robust if robust is not None else np.ones(wl.N, bool)
+    assert np.array_equal(mask[ok], ref["unused"][ok])
+    assert np.array_equal(nfov[ok], ref["nfov"][ok])
+    assert so.n_launches >= 1 and so.n_overflow == 0
+    # normalised weights of the public update() (ParticleFilter::normalizeWeights)
+    up.normalize()
+    wn = up.get_weights()
+    assert wn.sum() == pytest.approx(1.0, abs=1e-12)
+    assert np.allclose(wn, g["s5_weight"], rtol=1e-3 if prec == 32 else 1e-9, atol=1e-300)
+    up.close()
+
+
+@pytest.mark.parametrize("prec", [32, 64])
+@pytest.mark.parametrize("kw", [
+    dict(N=384, nM=200, nZ=30, use_cluster_process=1, config_id=11),
+    dict(N=384, nM=100, nZ=20, use_cluster_process=0, config_id=12),
+    dict(N=384, nM=200, nZ=30, use_cluster_process=1, config_id=13, parity_extras=True),
+    dict(N=384, nM=100, nZ=20, use_cluster_process=0, config_id=14, parity_extras=True, ragged=0.2),
+    dict(N=256, nM=180, nZ=30, use_cluster_process=1, config_id=15, world="sparse"),
+    dict(N=256, nM=120, nZ=24, use_cluster_process=0, config_id=16, world="sparse", ragged=0.3),
+    dict(N=256, nM=100, nZ=20, use_cluster_process=0, config_id=17, model=dict(Pd=0.6, clutter_intensity=5e-3)),
+    dict(N=128, nM=60, nZ=64, use_cluster_process=1, config_id=18),
+    dict(N=64, nM=1, nZ=1, use_cluster_process=0, config_id=19),
+], ids=lambda k: "sc%d_nM%d_nZ%d_id%d" % (k["use_cluster_process"], k["nM"], k["nZ"], k["config_id"]))
+def test_against_oracle(cuda_required, kw, prec):
+    from oracle import binding as ob
+    from rfs_slam_b200 import synth
+    wl = synth.make_workload(**kw)
+    o = ob.run(wl, sort_mode=ob.SORT_STABLE)
+    ref = dict(count=o.count, mean=o.mean, cov=o.cov, w=o.w, weight=o.weight)
+    so, cnt, mean, cov, w, pw, up = helpers.run_device(wl, precision=prec)
+    robust = helpers.robust_mask(wl) if prec == 32 else None
+    _check(wl, prec, ref, so, cnt, mean, cov, w, pw, robust)
+    if prec == 64:
+        # identical structure AND identical order (weight desc, position asc) in the fp64 build
+        assert np.array_equal(cnt, o.count)
+        assert np.allclose(mean, o.mean, rtol=0, atol=1e-9)
+        mask, nfov = up.get_unused()
+        assert np.array_equal(mask, o.unused_mask) and np.array_equal(nfov, o.n_in_fov)
+    assert so.gm_total_in == int(wl.count.sum())
+    assert so.gm_total_out == int(cnt.sum())
+    assert so.sum_w == pytest.approx(float(pw.sum()), rel=1e-12)
+    assert so.sum_w2 == pytest.approx(float((pw * pw).sum()), rel=1e-12)
+    up.close()
+
+
+@pytest.mark.parametrize("sc", [0, 1])
+def test_culled_merge_equals_exhaustive_merge(cuda_required, sc):
+    from rfs_slam_b200 import synth
+    wl = synth.make_workload(N=256, nM=150, nZ=30, use_cluster_process=sc, config_id=21 + sc, parity_extras=True)
+    a = helpers.run_device(wl, precision=32, brute=False)
+    b = helpers.run_device(wl, precision=32, brute=True)
+    for k in range(1, 6):
+        assert np.array_equal(a[k], b[k])  # bit-identical: same tests, same order
+    a[6].close(); b[6].close()
+
+
+def test_matrix_permanent_path_equals_enumeration(cuda_required):
+    from rfs_slam_b200 import synth
+    wl = synth.make_workload(N=256, nM=100, nZ=20, use_cluster_process=0, config_id=23,
+                             model=dict(Pd=0.7, clutter_intensity=5e-3))
+    a = helpers.run_device(wl, precision=64)
+    wl.cfg["assignment_sum_method"] = 1
+    b = helpers.run_device(wl, precision=64)
+    assert np.allclose(a[5], b[5], rtol=1e-9)
+    a[6].close(); b[6].close()
+
+
+def test_multi_step_sequence_matches_chained_oracle(cuda_required):
+    """three committed updates in a row; the oracle is chained on its own outputs"""
+    import copy
+    from oracle import binding as ob
+    from rfs_slam_b200 import capi, synth
+    from rfs_slam_b200.phd import PHDUpdater
+    wl = synth.make_workload(N=128, nM=120, nZ=20, use_cluster_process=1, config_id=31, world="sparse")
+    up = PHDUpdater(wl.N, gm_capacity=192, precision=64, z_capacity=32)
+    up.load_workload(wl)
+    cur = copy.copy(wl)
+    rng = np.random.default_rng(5)
+    for step in range(3):
+        Z = wl.Z + rng.normal(0, [0.02, 0.005], wl.Z.shape)
+        up.update(Z)  # default flags: commit + normalise
+        cur.Z = Z
+        o = ob.run(cur, sort_mode=ob.SORT_STABLE)
+        wn = o.weight / o.weight.sum()
+        cnt, mean, cov, w = up.download_maps()
+        assert np.array_equal(cnt, o.count)
+        assert np.allclose(mean, o.mean, atol=1e-9) and np.allclose(w, o.w, atol=1e-10)
+        assert np.allclose(up.get_weights(), wn, rtol=1e-9)
+        cur = synth.Workload(count=o.count, mean=o.mean, cov=o.cov, w=o.w, pose=wl.pose, pose_cov=wl.pose_cov,
+                             weight=wn, Z=Z, model=wl.model, cfg=wl.cfg)
+    up.close()
+
+
+def test_no_commit_keeps_state_and_empty_Z_is_a_noop(cuda_required):
+    from rfs_slam_b200 import capi, synth
+    from rfs_slam_b200.phd import PHDUpdater
+    wl = synth.make_workload(N=64, nM=40, nZ=8, use_cluster_process=1, config_id=41)
+    up = PHDUpdater(wl.N, gm_capacity=64, precision=32, z_capacity=8)
+    up.load_workload(wl)
+    before = up.download_maps(0)
+    so = up.update(wl.Z, flags=capi.UPDATE_NO_COMMIT)
+    after0 = up.download_maps(0)
+    after1 = up.download_maps(1)
+    for a, b in zip(before, after0):
+        assert np.array_equal(a, b)
+    assert after1[0].sum() == so.gm_total_out and not np.array_equal(after1[0], before[0])
+    # Q11: nZ == 0 -> nothing happens (include/RBPHDFilter.hpp:451-452)
+    so0 = up.update(np.zeros((0, 2)))
+    assert so0.n_launches == 0
+    for a, b in zip(before, up.download_maps(0)):
+        assert np.array_equal(a, b)
+    assert np.array_equal(up.get_weights(0), wl.weight)
+    up.close()
+
+
+def test_pose_covariance_modes(cuda_required):
+    from oracle import binding as ob
+    from rfs_slam_b200 import synth
+    wl = synth.make_workload(N=96, nM=80, nZ=16, use_cluster_process=0, config_id=51)
+    rng = np.random.default_rng(1)
+    for mode in (0, 1, 2):
+        if mode == 0:
+            wl.pose_cov = None
+        elif mode == 1:
+            wl.pose_cov = np.array([4e-5, 1e-5, -5e-6, 6e-5, 2e-6, 3e-5])
+        else:
+            s = rng.uniform(1e-5, 8e-5, (wl.N, 3))
+            wl.pose_cov = np.stack([s[:, 0], 0.1 * s[:, 0], 0 * s[:, 0], s[:, 1], 0.05 * s[:, 1], s[:, 2]], 1)
+        o = ob.run(wl, sort_mode=ob.SORT_STABLE)
+        ref = dict(count=o.count, mean=o.mean, cov=o.cov, w=o.w, weight=o.weight)
+        so, cnt, mean, cov, w, pw, up = helpers.run_device(wl, precision=64)
+        _check(wl, 64, ref, so, cnt, mean, cov, w, pw)
+        up.close()
+
+
+def test_capacity_overflow_is_reported_not_fatal(cuda_required):
+    from rfs_slam_b200 import synth
+    wl = synth.make_workload(N=32, nM=60, nZ=30, use_cluster_process=1, config_id=61)
+    so, cnt, *_rest, up = helpers.run_device(wl, precision=32, gm_capacity=64, work_capacity=64)
+    assert so.n_overflow > 0            # 60 inputs + ~25 new Gaussians do not fit 64
+    assert (cnt <= 64).all()
+    assert (up.get_flags() & 1).sum() == so.n_overflow
+    up.close()
+
+
+def test_reference_api_surface(cuda_required):
+    """getGMSize / getLandmark return conventions (include/RBPHDFilter.hpp:1153-1178) and error codes"""
+    from rfs_slam_b200 import capi, synth
+    from rfs_slam_b200.phd import PHDUpdater, RFSB200Error
+    wl = synth.make_workload(N=16, nM=20, nZ=6, use_cluster_process=1, config_id=71)
+    up = PHDUpdater(wl.N, gm_capacity=32, precision=32, z_capacity=8)
+    with pytest.raises(RFSB200Error, match="ESTATE"):
+        up.update(wl.Z)
+    up.load_workload(wl)
+    assert up.getGMSize(-1) == -1 and up.getGMSize(16) == -1 and up.getGMSize(3) == 20
+    ok, mean, S, w = up.getLandmark(3, 5)
+    k = 3 * 20 + 5
+    assert ok and np.allclose(mean, wl.mean[k], atol=1e-6) and abs(w - wl.w[k]) < 1e-6
+    assert np.allclose(S, [[wl.cov[k, 0], wl.cov[k, 1]], [wl.cov[k, 1], wl.cov[k, 2]]], atol=1e-8)
+    assert up.getLandmark(3, 20)[0] is False and up.getLandmark(99, 0)[0] is False
+    with pytest.raises(RFSB200Error, match="ECAPACITY"):
+        up.update(np.zeros((9, 2)))
+    with pytest.raises(RFSB200Error, match="EUNSUPPORTED"):
+        up.set_model(dict(wl.model, model_id=3))
+    with pytest.raises(RFSB200Error, match="EUNSUPPORTED"):
+        up.set_filter_cfg(dict(wl.cfg, eval_point_count=33))
+    bad = wl.count.copy(); bad[0] = 33
+    with pytest.raises(RFSB200Error, match="ECAPACITY"):
+        up.upload_maps(bad, np.zeros((bad.sum(), 2)), np.zeros((bad.sum(), 3)), np.zeros(bad.sum()))
+    up.close()
+
+
+def test_device_permanent_known_answers(cuda_required):
+    from oracle import binding as ob
+    from rfs_slam_b200.phd import PHDUpdater
+    up = PHDUpdater(4, gm_capacity=32)
+    der = {2: 1, 3: 2, 4: 9, 5: 44, 6: 265, 7: 1854, 8: 14833, 9: 133496, 10: 1334961, 11: 14684570, 12: 176214841}
+    for n, v in der.items():   # test/MatrixPermanentTest.hpp:66-85
+        got = up.permanent(np.ones((n, n)) - np.eye(n))[0]
+        assert got == pytest.approx(v, rel=1e-12)
+    rng = np.random.default_rng(3)
+    A = rng.random((50, 7, 7))
+    got = up.permanent(A)
+    exp = np.array([ob.permanent(a) for a in A])
+    assert np.allclose(got, exp, rtol=1e-11)
+    up.close()
