@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""bench.py — PHD filter updates/s of the B200 PHD measurement-update path.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config C3|C2|C4g] [--impl b200|reference]
+
+A "step" is one RBPHDFilter::update() (map update + particle weighting + merge + prune + weight
+sums (+ all-reduce) + normalisation) over one batch of synthetic particles; an "update" is one
+(particle x GM component x measurement) cell, so  value = N_total * nM_in * nZ / t_step.
+Weak scaling: every GPU owns 8 000 particles (C3); 8 GPUs = BASELINE config C4 (64 000).
+
+One JSON line is printed by rank 0 (see DESIGN.md "Measurement" for every key).
+Only the cpu_baseline leg and --impl reference execute anything under oracle/ (the CPU checker /
+the reference's own sources compiled into oracle/_ref); the timed GPU path never does.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "PHD filter updates/sec (particles x GM x meas)"
+UNIT = "updates/s"
+L2_FLUSH_BYTES = 512 << 20
+
+WORKLOADS = {
+    # name: (synth config, particles per GPU, description)
+    "C3": ("C3", 8000, "C3/C4: 8000 particles per GPU x 200 GM x 30 meas, RngBrg, SC-PHD weighting (8 GPUs = C4, 64000 particles)"),
+    "C2": ("C2", 1000, "C2: 1000 particles per GPU x 100 GM x 20 meas, RngBrg, multi-feature weighting"),
+    "C3mf": ("C3", 8000, "C3 shape with multi-feature weighting: 8000 particles per GPU x 200 GM x 30 meas"),
+    "C3sparse": ("C3", 8000, "C3 shape, sparse world (about 11 % of the components in range), SC-PHD"),
+    "N1k": ("C3", 1000, "north_star sweep: 1000 particles per GPU x 200 GM x 30 meas, SC-PHD"),
+    "N64k": ("C3", 64000, "north_star sweep: 64000 particles per GPU x 200 GM x 30 meas, SC-PHD"),
+}
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def make_workload(name, rank, n_override=0):
+    import rfs_slam_b200  # noqa: F401
+    from rfs_slam_b200 import synth
+    cfgname, n_gpu, desc = WORKLOADS[name]
+    kw = dict(N=n_override or n_gpu, shard_id=rank)
+    if name == "C3mf":
+        kw["use_cluster_process"] = 0
+    if name == "C3sparse":
+        kw["world"] = "sparse"
+    return synth.make_config(cfgname, **kw), desc
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    power_w_max=max(pw) if pw else None, samples=len(sm), reasons=sorted(reasons))
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_run(wl, n_particles, threads, repeats):
+    """Time the reference's own OpenMP RBPHDFilter::update() (oracle/_ref, compiled from the
+    reference sources) — or the oracle port if that library is absent — on the first
+    n_particles particles of the workload.  Returns (kind, best_seconds, list of seconds)."""
+    from oracle import binding as ob
+    sub = wl.shard(0, max(1, wl.N // n_particles)) if n_particles < wl.N else wl
+    kind = "reference" if ob.have_ref() else "port"
+    which = "ref" if kind == "reference" else "oracle"
+    stage = 5 if kind == "reference" else ob.STAGE_FULL   # 5: the public update() incl. normalizeWeights
+    ts = []
+    for _ in range(repeats):
+        r = ob.run(sub, which=which, stage=stage, n_threads=threads)
+        ts.append(r.elapsed_s)
+    return kind, sub, ts
+
+
+def run_reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    wl, desc = make_workload(a.config, 0)
+    nM = int(round(wl.count.mean()))
+    threads = len(os.sched_getaffinity(0))
+    n_s = min(wl.N, a.ref_particles)
+    kind, sub, _ = cpu_reference_run(wl, n_s, threads, max(0, a.warmup))
+    _, _, ts = cpu_reference_run(wl, n_s, threads, a.steps)
+    t = sum(ts) / len(ts)
+    units = int(sub.count.sum()) * sub.nZ
+    v = units / t
+    sample = f"{sub.N} of {wl.N} particles of the workload per step ({'oracle/_ref: reference sources, OpenMP' if kind == 'reference' else 'oracle port'}, {threads} threads)"
+    line = dict(metric=METRIC, value=v, unit=UNIT, n_gpus=a.gpus, steps=a.steps, warmup=a.warmup,
+                ms_per_step=1e3 * t, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
+                data="synthetic", impl="reference",
+                config=dict(workload=desc, particles_per_step=sub.N, gm_per_particle=nM, meas=sub.nZ),
+                cpu_baseline=dict(value=v, unit=UNIT, cores=threads, kind=kind, sample=sample),
+                e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                gpu_launches=0)
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="C3", choices=sorted(WORKLOADS))
+    ap.add_argument("--particles", type=int, default=0, help="override particles per GPU")
+    ap.add_argument("--ref-particles", type=int, default=2000, help="--impl reference: particles per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 0)
+    if a.impl == "reference":
+        return run_reference_arm(a)
+    if a.warmup < 3:
+        a.warmup = 3   # timing rule: at least 3 warm-up steps
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import rfs_slam_b200  # noqa: F401
+    from rfs_slam_b200 import capi
+    from rfs_slam_b200.dist import ShardedUpdater
+    from rfs_slam_b200.phd import PHDUpdater, pinned_array
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the PHD update path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # one non-default stream carries the library's kernels, torch's events / memsets and NCCL
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
+
+    wl, desc = make_workload(a.config, rank, a.particles)
+    N, nZ = wl.N, wl.nZ
+    units_local = int(wl.count.sum()) * nZ
+    up = PHDUpdater(N, gm_capacity=256, z_capacity=32, device=local, precision=32)
+    up.load_workload(wl)
+    sh = ShardedUpdater(up, device=dev)
+    up.synchronize()
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+    FLAGS = capi.UPDATE_NO_COMMIT   # every step starts from the same state, so nM_in is constant
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (also warms NCCL) -------------------------------------------------------------
+    for _ in range(a.warmup):
+        flush.zero_()
+        sh.step(wl.Z, flags=FLAGS)
+    torch.cuda.synchronize()
+    so = up.update(wl.Z, flags=FLAGS | capi.UPDATE_NO_NORMALIZE)   # statistics of one step
+    nM_out_mean = so.gm_total_out / N
+
+    # ---- timed region: K steps, device-timed, L2 flushed between steps -----------------------------
+    K = a.steps
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    up.profile_begin(K)
+    clocks = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        clocks.start()
+    t_wall0 = time.perf_counter()
+    for k in range(K):
+        flush.zero_()                 # > L2 (126 MB): the step reads its inputs from HBM
+        ev[k][0].record()
+        sh.step(wl.Z, flags=FLAGS)    # Z H2D (1.3 KB) + fused update kernel + [all-reduce] + normalise
+        ev[k][1].record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clk = clocks.stop() if rank == 0 else None
+    step_ms = [e0.elapsed_time(e1) for e0, e1 in ev]
+    t_local = sum(step_ms) / 1e3
+    kern_us = up.profile_read()
+    tt = torch.tensor([t_local], dtype=torch.float64, device=dev)
+    uu = torch.tensor([float(units_local)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(uu, op=dist.ReduceOp.SUM)
+    t_max = float(tt.item())
+    units_total = float(uu.item())
+    value = units_total * K / t_max
+
+    # ---- e2e: the same step through the C ABI with HOST buffers -------------------------------------
+    e2e = None
+    if not a.no_e2e:
+        h_pose = pinned_array((N, 3)); h_pose[:] = wl.pose
+        h_w = pinned_array((N,)); h_w[:] = wl.weight
+        h_wout = pinned_array((N,))
+        h_mask = pinned_array((N,), np.uint64)
+        h_nfov = pinned_array((N,), np.int32)
+        pc = wl.pose_cov
+
+        def e2e_step():
+            up.set_poses(h_pose, pc, h_w)                     # H2D: poses + particle weights (pinned)
+            s = sh.step(wl.Z, flags=FLAGS, want_stats=False)  # H2D: Z ; kernels ; all-reduce
+            up.get_weights(1, out=h_wout)                     # D2H: normalised particle weights
+            up.get_unused(h_mask, h_nfov)                     # D2H: unused-measurement masks, nLandmarksInFOV
+            return s
+
+        for _ in range(3):
+            e2e_step()
+        barrier()
+        Ke = K
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        te = 0.0
+        tw0 = time.perf_counter()
+        for _ in range(Ke):
+            flush.zero_()
+            e0.record()
+            e2e_step()
+            e1.record()
+            e1.synchronize()
+            te += e0.elapsed_time(e1) / 1e3
+        barrier()
+        tw = time.perf_counter() - tw0
+        tt = torch.tensor([te], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        te_max = float(tt.item())
+        h2d = N * 3 * 8 + N * 8 + 6 * 8 + nZ * 2 * 8
+        d2h = N * 8 + N * 8 + N * 4
+        e2e = dict(value=units_total * Ke / te_max, unit=UNIT, h2d_bytes_per_step=h2d * world, d2h_bytes_per_step=d2h * world,
+                   ms_per_step=1e3 * te_max / Ke, wall_ms_per_step_incl_flush=1e3 * tw / Ke,
+                   what="per step: rfsb200_set_poses(pinned host poses+weights) + rfsb200_update(host Z) + "
+                        "rfsb200_get_weights + rfsb200_get_unused into pinned host buffers; maps stay resident in HBM")
+
+    # ---- roofline of the dominant kernel (phd_update_kernel), live ------------------------------------
+    peak, peak_src = _peaks()
+    nM_in = int(wl.count.sum()) / N
+    b_alg = N * (24.0 * nM_in + 24.0 * nM_out_mean + 60.0) + 8.0 * nZ      # SURVEY §8(d), DESIGN.md
+    k_us = float(np.mean(kern_us)) if len(kern_us) else float("nan")
+    achieved = b_alg / (k_us * 1e-6) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get(a.config)
+        except Exception:
+            traffic = None
+    roofline = dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic,
+                    kernel="phd_update_kernel<float>", kernel_us=k_us, algorithmic_bytes=b_alg, peak_source=peak_src,
+                    kernel_share_of_step=k_us * 1e-3 / (1e3 * t_local / K))
+
+    line = None
+    if rank == 0:
+        cpu = None
+        if world == 1 and not a.no_cpu_baseline:
+            threads = len(os.sched_getaffinity(0))
+            n_s = min(N, 8000)
+            kind, sub, ts = cpu_reference_run(wl, n_s, threads, 2)
+            t = min(ts)
+            cpu = dict(value=int(sub.count.sum()) * nZ / t, unit=UNIT, cores=threads, kind=kind,
+                       sample=f"{sub.N} particles of the same workload, best of {len(ts)} runs of the reference's OpenMP "
+                              f"RBPHDFilter::update() ({t:.3f} s per step, {threads} threads)")
+        line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=a.warmup,
+                    ms_per_step=1e3 * t_max / K, higher_is_better=True, scaling="weak", vs_baseline=None,
+                    dtype="f32", data="synthetic",
+                    config=dict(workload=desc, particles_total=N * world, particles_per_gpu=N, gm_per_particle=nM_in,
+                                gm_out_per_particle=nM_out_mean, meas=nZ, l2="flushed between steps (512 MiB memset, untimed)",
+                                timing="CUDA events per step on the launch stream, summed; max over ranks",
+                                parallelism=f"particles block-partitioned over {world} GPU(s); one all-reduce of [sum w, sum w^2] per step"),
+                    e2e=e2e, gpu_launches=2 * K, roofline=roofline, cpu_baseline=cpu, clocks=clk,
+                    wall_s_timed_region_incl_flush=t_wall)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    up.close()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

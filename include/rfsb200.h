@@ -137,9 +137,10 @@ int rfsb200_create(rfsb200_ctx** out, const rfsb200_dims* dims);
 int rfsb200_destroy(rfsb200_ctx* ctx);
 const char* rfsb200_last_error(const rfsb200_ctx* ctx); /* ctx may be NULL: last creation error */
 
-/* Use an external CUDA stream (cudaStream_t as void*), e.g. torch's current stream.
- * NULL restores the ctx-owned stream. */
-int rfsb200_set_stream(rfsb200_ctx* ctx, void* cuda_stream);
+/* external != 0: run on the caller's CUDA stream (cudaStream_t as void*; NULL is the legacy
+ * default stream), e.g. torch's current stream, so that the caller's collectives and events
+ * are ordered with the kernels.  external == 0 restores the ctx-owned stream. */
+int rfsb200_set_stream(rfsb200_ctx* ctx, void* cuda_stream, int external);
 int rfsb200_synchronize(rfsb200_ctx* ctx);
 
 /* ---- configuration (replaces the plugin virtual calls inside updateMap) --------- */
@@ -197,6 +198,15 @@ int rfsb200_get_flags(rfsb200_ctx* ctx, int32_t* flags /*[N]*/);
  * device, fp64.  Non-square input cannot be expressed here; n must be in [1, 24]. */
 int rfsb200_permanent(rfsb200_ctx* ctx, const double* A /*[batch][n][n]*/, int32_t n,
                       int32_t batch, double* out /*[batch]*/);
+
+/* ---- measurement aid ----------------------------------------------------------------
+ * rfsb200_profile_begin arms a ring of CUDA event pairs: each of the next max_updates calls of
+ * rfsb200_update() records one pair around the fused update kernel alone, on the ctx stream.
+ * rfsb200_profile_read synchronises, returns the device time of each recorded launch in
+ * microseconds (n = number recorded, at most cap are written) and disarms the ring.  Used by
+ * bench.py for the live roofline figure; costs nothing when not armed. */
+int rfsb200_profile_begin(rfsb200_ctx* ctx, int32_t max_updates);
+int rfsb200_profile_read(rfsb200_ctx* ctx, float* kernel_us /*[cap]*/, int32_t cap, int32_t* n);
 
 /* Pinned host memory helpers (so H2D/D2H copies can overlap and run at PCIe speed). */
 int rfsb200_host_alloc(void** ptr, uint64_t bytes);

@@ -92,7 +92,7 @@ _SIGS = {
     "rfsb200_create": (C.c_int, [C.POINTER(_P), C.POINTER(Dims)]),
     "rfsb200_destroy": (C.c_int, [_P]),
     "rfsb200_last_error": (C.c_char_p, [_P]),
-    "rfsb200_set_stream": (C.c_int, [_P, _P]),
+    "rfsb200_set_stream": (C.c_int, [_P, _P, C.c_int]),
     "rfsb200_synchronize": (C.c_int, [_P]),
     "rfsb200_set_model": (C.c_int, [_P, C.POINTER(ModelDesc)]),
     "rfsb200_set_filter_cfg": (C.c_int, [_P, C.POINTER(FilterCfg)]),
@@ -108,6 +108,8 @@ _SIGS = {
     "rfsb200_get_unused": (C.c_int, [_P, _P, _P]),
     "rfsb200_get_flags": (C.c_int, [_P, _P]),
     "rfsb200_permanent": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P]),
+    "rfsb200_profile_begin": (C.c_int, [_P, C.c_int32]),
+    "rfsb200_profile_read": (C.c_int, [_P, _P, C.c_int32, C.POINTER(C.c_int32)]),
     "rfsb200_host_alloc": (C.c_int, [C.POINTER(_P), C.c_uint64]),
     "rfsb200_host_free": (C.c_int, [_P]),
 }

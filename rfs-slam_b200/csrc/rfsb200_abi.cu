@@ -69,6 +69,8 @@ struct rfsb200_ctx {
   rfsb200_model_desc model{};
   rfsb200_filter_cfg cfg{};
   int merge_algo = 1;
+  std::vector<cudaEvent_t> prof_ev;   // event pairs around the update kernel (rfsb200_profile_*)
+  int prof_cap = 0, prof_n = 0;
   int grid = 0;
   size_t smem_bytes = 0;
   int warp_bytes = 0;
@@ -249,8 +251,14 @@ int launch_update(rfsb200_ctx* c, int nZ, int out_idx) {
     if (rc) return rc;
     p.warp_bytes = c->warp_bytes;
   }
+  const bool prof = c->prof_n < c->prof_cap;
+  if (prof) CU(c, cudaEventRecord(c->prof_ev[2 * c->prof_n], c->stream));
   phd_update_kernel<T><<<c->grid, WARPS_PER_CTA * 32, c->smem_bytes, c->stream>>>(p);
   CU(c, cudaGetLastError());
+  if (prof) {
+    CU(c, cudaEventRecord(c->prof_ev[2 * c->prof_n + 1], c->stream));
+    c->prof_n++;
+  }
   return RFSB200_OK;
 }
 
@@ -386,14 +394,15 @@ int rfsb200_destroy(rfsb200_ctx* c) {
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   for (int k = 0; k < 8; k++) if (c->zev[k]) cudaEventDestroy(c->zev[k]);
+  for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
   return RFSB200_OK;
 }
 
-int rfsb200_set_stream(rfsb200_ctx* c, void* s) {
+int rfsb200_set_stream(rfsb200_ctx* c, void* s, int external) {
   if (!c) return fail(nullptr, RFSB200_EINVAL, "NULL ctx");
-  c->stream = s ? (cudaStream_t)s : c->own_stream;
+  c->stream = external ? (cudaStream_t)s : c->own_stream;   // s == NULL && external: the legacy default stream
   return RFSB200_OK;
 }
 
@@ -425,7 +434,15 @@ int rfsb200_set_filter_cfg(rfsb200_ctx* c, const rfsb200_filter_cfg* f) {
     const size_t blk = (size_t)7 * c->W * c->tsize;
     const size_t need = (size_t)MAX_EVAL * 8 * c->tsize + (size_t)((f->eval_point_count * c->dims.z_capacity + 3) & ~3) * c->tsize +
                         MAX_EVAL * 8 + MAX_COMP * 12 + 2 * (1 << DP_MAXB) * 8;
-    if (need > blk) return fail(c, RFSB200_ECAPACITY, "eval_point_count x z_capacity needs %zu B scratch (> %zu)", need, blk);
+    if (need > blk) {
+      // the table lives in the second 7-plane block of the warp: widen the planes until it fits
+      int W = c->W;
+      while ((size_t)7 * W * c->tsize < need && W < 1024) W <<= 1;
+      if ((size_t)7 * W * c->tsize < need)
+        return fail(c, RFSB200_ECAPACITY, "eval_point_count x z_capacity needs %zu B scratch (> %zu)", need, blk);
+      c->W = W;
+      c->cfg_mode_mf = -1;
+    }
   }
   c->cfg = *f;
   c->merge_algo = (f->reserved_i[0] == 1) ? 0 : 1;  // reserved_i[0] == 1 selects the brute-force merge (debug)
@@ -683,6 +700,35 @@ int rfsb200_permanent(rfsb200_ctx* c, const double* A, int32_t n, int32_t batch,
   cudaFree(dA);
   cudaFree(dO);
   if (e != cudaSuccess) return fail(c, RFSB200_ECUDA, "rfsb200_permanent: %s", cudaGetErrorString(e));
+  return RFSB200_OK;
+}
+
+int rfsb200_profile_begin(rfsb200_ctx* c, int32_t max_updates) {
+  if (!c) return fail(nullptr, RFSB200_EINVAL, "NULL ctx");
+  if (max_updates < 0 || max_updates > 4096) return fail(c, RFSB200_EINVAL, "max_updates must be in [0,4096]");
+  CU(c, cudaSetDevice(c->device));
+  while ((int)c->prof_ev.size() < 2 * max_updates) {
+    cudaEvent_t e;
+    CU(c, cudaEventCreate(&e));
+    c->prof_ev.push_back(e);
+  }
+  c->prof_cap = max_updates;
+  c->prof_n = 0;
+  return RFSB200_OK;
+}
+
+int rfsb200_profile_read(rfsb200_ctx* c, float* us, int32_t cap, int32_t* n) {
+  if (!c || !n) return fail(c, RFSB200_EINVAL, "NULL argument");
+  CU(c, cudaSetDevice(c->device));
+  *n = c->prof_n;
+  for (int k = 0; k < c->prof_n; k++) {
+    CU(c, cudaEventSynchronize(c->prof_ev[2 * k + 1]));
+    float ms = 0;
+    CU(c, cudaEventElapsedTime(&ms, c->prof_ev[2 * k], c->prof_ev[2 * k + 1]));
+    if (us && k < cap) us[k] = ms * 1000.f;
+  }
+  c->prof_cap = 0;
+  c->prof_n = 0;
   return RFSB200_OK;
 }
 

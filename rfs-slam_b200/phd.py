@@ -24,6 +24,18 @@ def _check(lib, ctx, rc, what):
         raise RFSB200Error(f"{what}: {capi.ERRORS.get(rc, rc)}: {msg.decode() if msg else ''}")
 
 
+def pinned_array(shape, dtype=np.float64) -> np.ndarray:
+    """numpy view of page-locked host memory from rfsb200_host_alloc (never freed: bench/test aid)."""
+    lib = capi.load_library()
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    p = C.c_void_p()
+    rc = lib.rfsb200_host_alloc(C.byref(p), max(n, 16))
+    if rc != 0:
+        raise RFSB200Error(f"host_alloc: {capi.ERRORS.get(rc, rc)}")
+    buf = (C.c_char * max(n, 16)).from_address(p.value)
+    return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+
 class PHDUpdater:
     def __init__(self, n_particles: int, gm_capacity: int = 256, work_capacity: int = 0,
                  z_capacity: int = 64, device: int = 0, precision: int = 32):
@@ -69,7 +81,9 @@ class PHDUpdater:
         _check(self.lib, self.ctx, self.lib.rfsb200_set_filter_cfg(self.ctx, C.byref(c)), "set_filter_cfg")
 
     def set_stream(self, cuda_stream: int | None):
-        _check(self.lib, self.ctx, self.lib.rfsb200_set_stream(self.ctx, C.c_void_p(cuda_stream or 0)), "set_stream")
+        """cuda_stream: a cudaStream_t handle (0 = the legacy default stream); None = the ctx-owned stream."""
+        ext = 0 if cuda_stream is None else 1
+        _check(self.lib, self.ctx, self.lib.rfsb200_set_stream(self.ctx, C.c_void_p(cuda_stream or 0), ext), "set_stream")
 
     def synchronize(self):
         _check(self.lib, self.ctx, self.lib.rfsb200_synchronize(self.ctx), "synchronize")
@@ -87,6 +101,8 @@ class PHDUpdater:
                "upload_maps")
 
     def set_poses(self, pose, pose_cov=None, weight=None):
+        """Particle poses (+ optional pose covariance, Q1) and weights; ascontiguousarray keeps a
+        pinned float64 input as it is, so the H2D copy reads the caller's page-locked buffer."""
         pose = np.ascontiguousarray(pose, dtype=np.float64)
         mode = 0
         pc = None
@@ -124,8 +140,8 @@ class PHDUpdater:
         _check(self.lib, self.ctx, self.lib.rfsb200_normalize(self.ctx), "normalize")
 
     # ---- state out -------------------------------------------------------------------------------
-    def get_weights(self, which: int = 0) -> np.ndarray:
-        w = np.zeros(self.N)
+    def get_weights(self, which: int = 0, out: np.ndarray | None = None) -> np.ndarray:
+        w = np.zeros(self.N) if out is None else out
         _check(self.lib, self.ctx, self.lib.rfsb200_get_weights(self.ctx, which, capi.ptr(w)), "get_weights")
         return w
 
@@ -169,9 +185,9 @@ class PHDUpdater:
         t = int(count.sum())
         return count, mean[:t].copy(), cov[:t].copy(), w[:t].copy()
 
-    def get_unused(self):
-        mask = np.zeros(self.N, dtype=np.uint64)
-        nfov = np.zeros(self.N, dtype=np.int32)
+    def get_unused(self, out_mask: np.ndarray | None = None, out_nfov: np.ndarray | None = None):
+        mask = np.zeros(self.N, dtype=np.uint64) if out_mask is None else out_mask
+        nfov = np.zeros(self.N, dtype=np.int32) if out_nfov is None else out_nfov
         _check(self.lib, self.ctx, self.lib.rfsb200_get_unused(self.ctx, capi.ptr(mask), capi.ptr(nfov)), "get_unused")
         return mask, nfov
 
@@ -179,6 +195,15 @@ class PHDUpdater:
         f = np.zeros(self.N, dtype=np.int32)
         _check(self.lib, self.ctx, self.lib.rfsb200_get_flags(self.ctx, capi.ptr(f)), "get_flags")
         return f
+
+    def profile_begin(self, max_updates: int):
+        _check(self.lib, self.ctx, self.lib.rfsb200_profile_begin(self.ctx, int(max_updates)), "profile_begin")
+
+    def profile_read(self) -> np.ndarray:
+        us = np.zeros(4096, dtype=np.float32)
+        n = C.c_int32()
+        _check(self.lib, self.ctx, self.lib.rfsb200_profile_read(self.ctx, capi.ptr(us), 4096, C.byref(n)), "profile_read")
+        return us[:n.value].copy()
 
     def permanent(self, A) -> np.ndarray:
         A = np.ascontiguousarray(A, dtype=np.float64)
