@@ -127,7 +127,8 @@ typedef struct rfsb200_step_out {
   int32_t n_murty;            /* particles that took the k-best (Murty, nR+nC>8) branch of rfsMeasurementLikelihood        */
   int32_t n_launches;         /* kernels launched by this call                                                           */
   float   elapsed_us;         /* device time of the step (CUDA events on the ctx stream)                                  */
-  int32_t reserved[7];
+  int32_t n_merge_redo;       /* particles recomputed with the exhaustive merge (interacting merge clusters)              */
+  int32_t reserved[6];
 } rfsb200_step_out;
 
 /* ---- lifetime ------------------------------------------------------------------ */

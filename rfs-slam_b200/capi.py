@@ -54,7 +54,7 @@ class StepOut(C.Structure):
     _fields_ = [("sum_w", C.c_double), ("sum_w2", C.c_double), ("n_eff", C.c_double),
                 ("gm_total_in", C.c_int64), ("gm_total_out", C.c_int64), ("gm_max_out", C.c_int32),
                 ("n_overflow", C.c_int32), ("n_murty", C.c_int32), ("n_launches", C.c_int32),
-                ("elapsed_us", C.c_float), ("reserved", C.c_int32 * 7)]
+                ("elapsed_us", C.c_float), ("n_merge_redo", C.c_int32), ("reserved", C.c_int32 * 6)]
 
 
 def model_desc(md: dict) -> ModelDesc:

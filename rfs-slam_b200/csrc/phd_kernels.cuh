@@ -24,7 +24,7 @@ constexpr int MAX_Z = 64;
 constexpr int MAX_EVAL = 32;
 constexpr int DP_MAXB = 7;     // assignment-sum DP: the smaller side of a partition has <= 7 members
 constexpr int MAX_COMP = 96;   // connected components of the (eval point, measurement) graph
-constexpr int MAX_PAIRS = 256; // merge pre-pass: candidate pairs kept per particle
+constexpr int MAX_PAIRS = 160; // merge: passing pairs (+ cluster links) kept per particle
 
 // flag bits written per particle
 constexpr int FLAG_OVERFLOW = 1;
@@ -46,6 +46,7 @@ struct KParams {
   // shapes
   int N, cap, W, nZ, pose_cov_mode;
   int warp_bytes;  // shared memory per warp
+  int mf_bytes;    // multi-feature scratch inside it
   // state in / out
   const T* gm_in;
   const int* cnt_in;
@@ -53,9 +54,6 @@ struct KParams {
   const T* pose;      // [N][4]
   const T* pose_cov;  // [8] or [N][8]
   const T* Z;         // [nZ][2]
-  const T* Zr_sorted; // [nZ] ranges ascending
-  const T* Zb_sorted; // [nZ] bearing of the same measurement
-  const int* Z_sorted_idx;  // [nZ] original index of the same measurement
   T* gm_out;
   int* cnt_out;
   double* w_out;
@@ -65,10 +63,11 @@ struct KParams {
   // reductions
   double* sums;                   // [2]
   unsigned long long* totals;     // [0]=gm_in total [1]=gm_out total
-  int* istats;                    // [0]=max out [1]=n_overflow [2]=n_murty
+  int* istats;                    // [0]=max out [1]=n_overflow [2]=n_murty [3]=merge recomputations
+  unsigned int* mstats;           // [8] merge statistics (fallback reasons, pairs, clusters)
   unsigned int* ticket;
   unsigned int* work_counter;     // dynamic particle queue, re-armed by the last CTA
-  unsigned long long* stats_out;  // [5] totals/istats of the finished step, published by the last CTA
+  unsigned long long* stats_out;  // [13] totals/istats/mstats of the finished step, published by the last CTA
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -233,198 +232,387 @@ __device__ void merge_bruteforce(T* cur, int W, int n, T t2, T f, int lane) {
   }
 }
 
-// Culled merge (same results as merge_bruteforce):
-//  pre-pass: counting sort of the live components on a 256-cell grid over x, every component
-//            scans the cells its own reach covers and runs the exact test (original parameters)
-//            on the candidates -> short list of passing pairs (i<j), key = i<<16 | j
-//  sequential phase: rows are visited in ascending i only if they own a passing pair; the first
-//            merge of a row is its smallest live j in the list (everything is still original
-//            then); after an absorb the row changed, so every live j > jmin inside the cells the
-//            new reach (or the largest reach of any component) covers is re-tested.
-//  scratch: rad2[W] T, pairs[MAX_PAIRS] u32, cellStart[258] u16, cursor[258] u16, order[W] u16, npairs
+// Clustered merge: same results as merge_bruteforce, or MERGE_FALLBACK with nothing modified.
+//
+//  The greedy merge only ever changes components that pass the Mahalanobis test with something,
+//  and a component can only pass the test with a partner closer than max(reach_a, reach_b), where
+//  reach^2 = t^2 * trace(P) bounds t^2 * lambda_max(P).  So:
+//   M1  counting sort of the components on <= 256 cells over x whose width is >= the largest
+//       reach: all partners of a component lie in its own and the two adjacent cells.
+//   M2  every component (in cell order) tests the components behind it up to the end of the next
+//       cell: distance pre-filter, then the exact test on the original parameters -> list of
+//       passing pairs.
+//   M3  connected components ("clusters") of the passing-pair graph by label propagation.
+//   M4  ONE LANE PER CLUSTER runs the reference's sequential loop restricted to its cluster: rows
+//       ascending, partners ascending, exact test against the current row (kept in registers).
+//       Once a row has absorbed something it is re-tested against every neighbour (cell lookup):
+//       an unowned neighbour that passes is claimed (CAS) and absorbed, exactly as the reference
+//       would; a neighbour owned by ANOTHER cluster means the two clusters interact and the
+//       lane-parallel schedule could differ from the sequential one.
+//       Nothing is written to the mixture during M4: merged rows go to a log and deaths to a
+//       bitmap, so on a conflict the two clusters are simply linked and M3/M4 run again.
+//   M5  commit the log.
+//  Clusters are independent in the reference's order as long as no row of one ever comes within
+//  reach of a component of another, which is what the conflict test checks, conservatively.
+constexpr int MERGE_OK = 0;
+constexpr int MERGE_FALLBACK = 1;   // nothing modified: run the exhaustive merge instead
+constexpr int MAX_CLUSTERS = 64;
+constexpr int MAX_MEMBERS = 12;
+constexpr int MAX_ROWLOG = 48;
+constexpr int MAX_MERGE_ROUNDS = 4;
+constexpr unsigned NO_OWNER = 0xffffffffu;
+
 template <typename T>
-struct MergeGrid {
-  T xmin, invw, rmax2;
-  const unsigned short* cellStart;
-  const unsigned short* order;
+struct MergeScratch {
+  unsigned* label;           // [W] cluster label (smallest member index) / NO_OWNER   (aliases aux)
+  unsigned short* order;     // [W] cell order -> component index
+  unsigned short* slot;      // [W] component index of a cluster head -> cluster slot
+  unsigned short* cellStart; // [264]
+  unsigned* counters;        // [4]: 0 = number of pairs, 1 = logged rows
+  // --- region that is dead outside the merge (the prune sort keys alias it) ---
+  unsigned* pairs;           // [MAX_PAIRS]
+  unsigned* memberCount;     // [MAX_CLUSTERS]
+  unsigned* deadBits;        // [32] bit per component (W <= 1024)
+  T* rowLog;                 // [MAX_ROWLOG][6]
+  unsigned short* rowIdx;    // [MAX_ROWLOG]
+  unsigned short* members;   // [MAX_CLUSTERS][MAX_MEMBERS]
+  T* keys;                   // [W] prune sort keys (same storage as pairs..members)
 };
 
 template <typename T>
-__device__ __forceinline__ int grid_cell(const MergeGrid<T>& g, T x) {
-  int c = (int)((x - g.xmin) * g.invw);
-  return c < 0 ? 0 : (c > 255 ? 255 : c);
+__host__ __device__ inline int merge_only_bytes(int W) {
+  const int a = MAX_PAIRS * 4 + MAX_CLUSTERS * 4 + 32 * 4 + MAX_ROWLOG * 6 * (int)sizeof(T) + MAX_ROWLOG * 2 +
+                MAX_CLUSTERS * MAX_MEMBERS * 2;
+  const int b = W * (int)sizeof(T);
+  return ((a > b ? a : b) + 15) & ~15;
 }
-
-// smallest live j > jlast passing the merge test against row r, looking only at the cells that can
-// hold a partner: |d|^2 <= max(reach2(row), reach2(j)) <= max(ri2, rmax2)
+// label[] is the caller's aux array and is not counted here
 template <typename T>
-__device__ __forceinline__ int merge_rescan(const MergeRow<T>& r, T ri2, const MergeGrid<T>& g, const T* cur,
-                                            const T* rad2, int W, int jlast, int n, T t2, int lane) {
-  const T R2 = M<T>::max_(ri2, g.rmax2);
-  if (!(R2 < M<T>::inf())) return merge_scan<T, true>(r, cur, rad2, ri2, W, jlast + 1, n, t2, lane);
-  const T R = M<T>::sqrt_(R2);
-  int clo = 0, chi = 255;
-  if (g.invw > T(0)) {
-    clo = grid_cell(g, r.x - R) - 1;
-    chi = grid_cell(g, r.x + R) + 1;
-    clo = clo < 0 ? 0 : clo;
-    chi = chi > 255 ? 255 : chi;
-  }
-  const int k0 = g.cellStart[clo], k1 = g.cellStart[chi + 1];
-  int best = 0x7fffffff;
-  for (int kb = k0; kb < k1; kb += 32) {
-    const int k = kb + lane;
-    if (k < k1) {
-      const int c = g.order[k];
-      if (c > jlast && cur[5 * W + c] >= T(0)) {
-        const T dx = cur[c] - r.x, dy = cur[W + c] - r.y;
-        const T rr = M<T>::max_(ri2, rad2[c]);
-        if (!(dx * dx + dy * dy > rr) && merge_test(r, cur, W, c, t2)) best = c < best ? c : best;
-      }
-    }
-  }
-  best = warp_min(best);
-  return best == 0x7fffffff ? -1 : best;
+__host__ __device__ inline int merge_scratch_bytes(int W) {
+  return (int)((2 * W * 2 + 264 * 2 + 16 + 15) & ~15) + merge_only_bytes<T>(W);
 }
 
 template <typename T>
-__device__ void merge_culled(T* cur, T* scratch, int W, int n, T t2, T f, int lane) {
-  T* rad2 = scratch;                                     // W
-  unsigned* pairs = reinterpret_cast<unsigned*>(scratch + W);      // MAX_PAIRS
-  unsigned short* cellStart = reinterpret_cast<unsigned short*>(pairs + MAX_PAIRS);  // 258
-  unsigned short* cursor = cellStart + 258;              // 258
-  unsigned short* order = cursor + 258;                  // W
-  unsigned* npairs = reinterpret_cast<unsigned*>(order + W + (W & 1));  // 1 (4-byte aligned)
-  // reach + bounding interval
+__device__ __forceinline__ MergeScratch<T> carve_merge_scratch(unsigned char* base, unsigned* aux, int W) {
+  MergeScratch<T> m;
+  m.label = aux;
+  m.counters = reinterpret_cast<unsigned*>(base);
+  m.order = reinterpret_cast<unsigned short*>(m.counters + 4);
+  m.slot = m.order + W;
+  m.cellStart = m.slot + W;
+  unsigned char* r = base + ((2 * W * 2 + 264 * 2 + 16 + 15) & ~15);
+  m.keys = reinterpret_cast<T*>(r);
+  m.rowLog = reinterpret_cast<T*>(r);
+  m.pairs = reinterpret_cast<unsigned*>(m.rowLog + MAX_ROWLOG * 6);
+  m.memberCount = m.pairs + MAX_PAIRS;
+  m.deadBits = m.memberCount + MAX_CLUSTERS;
+  m.rowIdx = reinterpret_cast<unsigned short*>(m.deadBits + 32);
+  m.members = m.rowIdx + MAX_ROWLOG;
+  return m;
+}
+
+// exact test of the pair (a, b) on the parameters stored in cur (include/GaussianMixture.hpp:435-442,
+// the row is a)
+template <typename T>
+__device__ __forceinline__ bool merge_test_pair(const T* cur, int W, int a, int b, T t2) {
+  const T dx = cur[b] - cur[a], dy = cur[W + b] - cur[W + a];
+  T i00, i01, i11;
+  inv_sym2(cur[2 * W + a], cur[3 * W + a], cur[4 * W + a], i00, i01, i11);
+  const T d1 = (dx * i00 + dy * i01) * dx + (dx * i01 + dy * i11) * dy;
+  if (!(d1 > t2)) return true;
+  inv_sym2(cur[2 * W + b], cur[3 * W + b], cur[4 * W + b], i00, i01, i11);
+  const T d2 = (dx * i00 + dy * i01) * dx + (dx * i01 + dy * i11) * dy;
+  return !(d2 > t2);
+}
+
+// lane-local absorb: row r (registers) takes component j (read-only); false if the weights sum to 0
+template <typename T>
+__device__ __forceinline__ bool lane_absorb(MergeRow<T>& r, const T* cur, int W, int j, T f) {
+  const T w1 = r.w, w2 = cur[5 * W + j];
+  const T wm = w1 + w2;
+  if (wm == T(0)) return false;
+  const T x2 = cur[j], y2 = cur[W + j];
+  const T q00 = cur[2 * W + j], q01 = cur[3 * W + j], q11 = cur[4 * W + j];
+  const T iw = T(1) / wm;
+  const T xm = (r.x * w1 + x2 * w2) * iw, ym = (r.y * w1 + y2 * w2) * iw;
+  const T ax = xm - r.x, ay = ym - r.y, bx = xm - x2, by = ym - y2;
+  const T s00 = (w1 * (r.pxx + f * ax * ax) + w2 * (q00 + f * bx * bx)) * iw;
+  const T s01 = (w1 * (r.pxy + f * ax * ay) + w2 * (q01 + f * bx * by)) * iw;
+  const T s11 = (w1 * (r.pyy + f * ay * ay) + w2 * (q11 + f * by * by)) * iw;
+  r.x = xm; r.y = ym; r.pxx = s00; r.pxy = s01; r.pyy = s11; r.w = wm;
+  inv_sym2(s00, s01, s11, r.i00, r.i01, r.i11);
+  return true;
+}
+
+template <typename T>
+__device__ int merge_clustered(T* cur, const MergeScratch<T>& ms, int W, int n, T t2, T f, bool has_wprev,
+                               int lane, unsigned (&mstat)[8]) {
+  // ---- M1: reach, bounding interval, counting sort on cells ------------------------------------
   T xmin = M<T>::inf(), xmax = -M<T>::inf(), rmax2 = T(0);
+  bool bad = false;
   for (int j = lane; j < n; j += 32) {
-    T w = cur[5 * W + j];
-    T rr = T(0);
-    if (w >= T(0)) {
-      rr = merge_reach2(cur[2 * W + j], cur[3 * W + j], cur[4 * W + j], t2);
-      T x = cur[j];
-      xmin = x < xmin ? x : xmin;
-      xmax = x > xmax ? x : xmax;
-      rmax2 = rr > rmax2 ? rr : rmax2;
-    }
-    rad2[j] = rr;
+    const T a = cur[2 * W + j], b = cur[3 * W + j], c = cur[4 * W + j];
+    const bool pd = (a > T(0)) && (c > T(0)) && (a * c - b * b > T(0));
+    bad |= !pd;
+    const T rr = a + c;
+    const T x = cur[j];
+    xmin = x < xmin ? x : xmin;
+    xmax = x > xmax ? x : xmax;
+    rmax2 = rr > rmax2 ? rr : rmax2;
+    ms.label[j] = NO_OWNER;
   }
-  for (int c = lane; c < 258; c += 32) { cellStart[c] = 0; }
-  if (lane == 0) *npairs = 0;
+  for (int c = lane; c < 132; c += 32) reinterpret_cast<unsigned*>(ms.cellStart)[c] = 0u;
+  for (int c = lane; c < MAX_CLUSTERS; c += 32) ms.memberCount[c] = 0u;
+  ms.deadBits[lane] = 0u;
+  if (lane < 4) ms.counters[lane] = 0u;
+  if (__any_sync(FULL, bad)) { mstat[0]++; return MERGE_FALLBACK; }   // a non-PD covariance has no finite reach
   xmin = warp_min(xmin);
   xmax = warp_max(xmax);
-  rmax2 = warp_max(rmax2);
-  T span = xmax - xmin;
-  MergeGrid<T> g;
-  g.xmin = xmin;
-  g.invw = (span > T(0)) ? T(255.999) / span : T(0);
-  g.rmax2 = rmax2;
-  g.cellStart = cellStart;
-  g.order = order;
+  const T tt = t2 * T(1.001);                // reach^2 of a component = tt * trace(P)
+  rmax2 = warp_max(rmax2) * tt;
+  if (!(rmax2 < M<T>::inf()) || !(xmax - xmin < M<T>::inf())) { mstat[0]++; return MERGE_FALLBACK; }
+  const T span = xmax - xmin;
+  const T rmax = M<T>::sqrt_(rmax2) * T(1.001);
+  T cw = span * T(1.0 / 255.5);
+  cw = cw > rmax ? cw : rmax;
+  const T invw = cw > T(0) ? T(1) / cw : T(0);
+  auto cell_of = [&](T x) -> int {
+    const T v = (x - xmin) * invw;
+    int c = (v >= T(255)) ? 255 : (int)v;
+    return c < 0 ? 0 : c;
+  };
   __syncwarp();
-  // histogram (counts at cell+1 for the exclusive prefix); 16-bit counters packed in 32-bit words
-  for (int j = lane; j < n; j += 32) {
-    if (cur[5 * W + j] >= T(0)) {
-      const int c = grid_cell(g, cur[j]);
-      unsigned* wd = reinterpret_cast<unsigned*>(cellStart) + ((c + 1) >> 1);
-      atomicAdd(wd, ((c + 1) & 1) ? 0x10000u : 1u);
-    }
+  for (int j = lane; j < n; j += 32) {   // histogram at cell+1; 16-bit counters packed in words
+    const int c = cell_of(cur[j]) + 1;
+    atomicAdd(reinterpret_cast<unsigned*>(ms.cellStart) + (c >> 1), (c & 1) ? 0x10000u : 1u);
   }
   __syncwarp();
   {  // inclusive prefix over entries 1..256: lane owns 8 consecutive entries
     int loc[8];
     int s = 0;
 #pragma unroll
-    for (int k = 0; k < 8; k++) { loc[k] = cellStart[1 + lane * 8 + k]; s += loc[k]; }
-    int incl = warp_incl_scan(s, lane);
+    for (int k = 0; k < 8; k++) { loc[k] = ms.cellStart[1 + lane * 8 + k]; s += loc[k]; }
+    const int incl = warp_incl_scan(s, lane);
     int run = incl - s;
     __syncwarp();
 #pragma unroll
-    for (int k = 0; k < 8; k++) { run += loc[k]; cellStart[1 + lane * 8 + k] = (unsigned short)run; }
-    if (lane == 0) cellStart[0] = 0;
+    for (int k = 0; k < 8; k++) { run += loc[k]; ms.cellStart[1 + lane * 8 + k] = (unsigned short)run; }
     __syncwarp();
-    if (lane == 0) cellStart[257] = cellStart[256];
+    if (lane == 0) { ms.cellStart[257] = (unsigned short)n; ms.cellStart[258] = (unsigned short)n; }
   }
-  for (int c = lane; c < 258; c += 32) cursor[c] = cellStart[c];
+  // scatter: per-cell cursors (cell c -> next free position), 16-bit counters packed in words
+  unsigned* cursor = ms.pairs;   // the pair list is not in use yet (MAX_PAIRS >= 128 words)
+  for (int c = lane; c < 128; c += 32) {
+    cursor[c] = (unsigned)ms.cellStart[2 * c] | ((unsigned)ms.cellStart[2 * c + 1] << 16);
+  }
   __syncwarp();
   for (int j = lane; j < n; j += 32) {
-    if (cur[5 * W + j] >= T(0)) {
-      const int c = grid_cell(g, cur[j]);
-      unsigned* wd = reinterpret_cast<unsigned*>(cursor) + (c >> 1);
-      unsigned old = atomicAdd(wd, (c & 1) ? 0x10000u : 1u);
-      unsigned pos = (c & 1) ? (old >> 16) : (old & 0xffffu);
-      order[pos] = (unsigned short)j;
-    }
+    const int c = cell_of(cur[j]);
+    const unsigned old = atomicAdd(cursor + (c >> 1), (c & 1) ? 0x10000u : 1u);
+    const unsigned pos = (c & 1) ? (old >> 16) : (old & 0xffffu);
+    ms.order[pos] = (unsigned short)j;
   }
   __syncwarp();
-  // neighbour scan with the exact test on the original parameters
+  // (the order inside a cell is schedule dependent; nothing below depends on it: M2 visits every
+  //  pair of one cell or of adjacent cells exactly once, M4 takes minima over index)
+  // ---- M2: passing pairs ----------------------------------------------------------------------------
   bool overflow = false;
-  for (int jb = 0; jb < n; jb += 32) {
-    const int j = jb + lane;
-    if (j < n && cur[5 * W + j] >= T(0)) {
-      const T rj2 = rad2[j];
+  for (int sb = 0; sb < n; sb += 32) {
+    const int s = sb + lane;
+    if (s < n) {
+      const int j = ms.order[s];
       const T xj = cur[j], yj = cur[W + j];
-      int clo = 0, chi = 255;
-      if (rj2 < M<T>::inf() && g.invw > T(0)) {
-        const T rj = M<T>::sqrt_(rj2);
-        clo = grid_cell(g, xj - rj) - 1;
-        chi = grid_cell(g, xj + rj) + 1;
-        clo = clo < 0 ? 0 : clo;
-        chi = chi > 255 ? 255 : chi;
-      }
-      const int k0 = cellStart[clo], k1 = cellStart[chi + 1];
-      for (int k = k0; k < k1; k++) {
-        const int c = order[k];
-        if (c == j) continue;
-        const T dx = cur[c] - xj, dy = cur[W + c] - yj;
-        if (dx * dx + dy * dy > rj2) continue;   // found from the side whose reach covers the pair
-        const int i0 = j < c ? j : c, j0 = j < c ? c : j;
-        MergeRow<T> r;
-        load_row(r, cur, W, i0);
-        if (merge_test(r, cur, W, j0, t2)) {
-          unsigned slot = atomicAdd(npairs, 1u);
-          if (slot < (unsigned)MAX_PAIRS) pairs[slot] = ((unsigned)i0 << 16) | (unsigned)j0;
+      const T rj = tt * (cur[2 * W + j] + cur[4 * W + j]);
+      const int end = ms.cellStart[cell_of(xj) + 2];
+      for (int t = s + 1; t < end; t++) {
+        const int k = ms.order[t];
+        const T dx = cur[k] - xj, dy = cur[W + k] - yj;
+        const T d2 = dx * dx + dy * dy;
+        if (d2 > rmax2) continue;
+        if (d2 > M<T>::max_(rj, tt * (cur[2 * W + k] + cur[4 * W + k]))) continue;
+        const int a = j < k ? j : k, b = j < k ? k : j;
+        if (merge_test_pair(cur, W, a, b, t2)) {
+          const unsigned q = atomicAdd(&ms.counters[0], 1u);
+          if (q < (unsigned)MAX_PAIRS) ms.pairs[q] = ((unsigned)a << 16) | (unsigned)b;
           else overflow = true;
         }
       }
     }
-    __syncwarp();  // reconverge: the inner loops have different trip counts per lane
+    __syncwarp();
   }
-  if (__any_sync(FULL, overflow)) {  // too many candidate pairs: exact fallback
-    merge_bruteforce(cur, W, n, t2, f, lane);
-    return;
-  }
-  const int np = (int)*npairs;
-  // sequential phase
-  unsigned curkey = 0;
-  while (true) {
-    unsigned best = 0xffffffffu;
+  if (__any_sync(FULL, overflow)) { mstat[1]++; return MERGE_FALLBACK; }
+  if (ms.counters[0] == 0u) return MERGE_OK;
+  mstat[5] += ms.counters[0];
+
+  for (int round = 0; round < MAX_MERGE_ROUNDS; round++) {
+    const int np = (int)ms.counters[0];
+    // ---- M3: clusters by label propagation (converges to the smallest index of each cluster) ------
     for (int k = lane; k < np; k += 32) {
-      const unsigned key = pairs[k];
-      if (key >= curkey && key < best) {
-        const int i = key >> 16, j = key & 0xffff;
-        if (cur[5 * W + i] >= T(0) && cur[5 * W + j] >= T(0)) best = key;
+      const unsigned key = ms.pairs[k];
+      ms.label[key >> 16] = key >> 16;
+      ms.label[key & 0xffffu] = key & 0xffffu;
+    }
+    __syncwarp();
+    while (true) {
+      bool changed = false;
+      for (int k = lane; k < np; k += 32) {
+        const unsigned key = ms.pairs[k];
+        const unsigned a = key >> 16, b = key & 0xffffu;
+        const unsigned la = ms.label[a], lb = ms.label[b];
+        if (la != lb) {
+          const unsigned m = la < lb ? la : lb;
+          atomicMin(&ms.label[a], m);
+          atomicMin(&ms.label[b], m);
+          changed = true;
+        }
+      }
+      __syncwarp();
+      if (!__any_sync(FULL, changed)) break;
+    }
+    // ---- cluster slots (heads in ascending order) and member lists ----------------------------------
+    int nclusters = 0;
+    for (int jb = 0; jb < n; jb += 32) {
+      const int j = jb + lane;
+      const bool head = (j < n) && (ms.label[j] == (unsigned)j);
+      const unsigned bh = __ballot_sync(FULL, head);
+      if (head) ms.slot[j] = (unsigned short)(nclusters + __popc(bh & ((1u << lane) - 1u)));
+      nclusters += __popc(bh);
+    }
+    if (nclusters > MAX_CLUSTERS) { mstat[2]++; return MERGE_FALLBACK; }
+    __syncwarp();
+    bool big = false;
+    for (int j = lane; j < n; j += 32) {
+      const unsigned l = ms.label[j];
+      if (l != NO_OWNER) {
+        const int sl = ms.slot[l];
+        const unsigned pos = atomicAdd(&ms.memberCount[sl], 1u);
+        if (pos < (unsigned)MAX_MEMBERS) ms.members[sl * MAX_MEMBERS + pos] = (unsigned short)j;
+        else big = true;
       }
     }
-    best = warp_min(best);
-    if (best == 0xffffffffu) break;
-    const int i = best >> 16, j = best & 0xffff;
-    MergeRow<T> r;
-    load_row(r, cur, W, i);
-    if (!merge_absorb(r, cur, W, i, j, f, lane)) {  // w_m == 0: the reference moves on to j+1
-      curkey = best + 1;
-      continue;
+    if (__any_sync(FULL, big)) { mstat[3]++; return MERGE_FALLBACK; }
+    __syncwarp();
+    // ---- M4: one lane per cluster; read-only on the mixture -----------------------------------------
+    bool conflict = false, logfull = false;
+    auto is_dead = [&](int k) -> bool { return (ms.deadBits[k >> 5] >> (k & 31)) & 1u; };
+    for (int cb = 0; cb < nclusters; cb += 32) {
+      const int sl = cb + lane;
+      if (sl < nclusters) {
+        unsigned short* mem = ms.members + sl * MAX_MEMBERS;
+        const int nm = (int)ms.memberCount[sl];
+        for (int u = 1; u < nm; u++) {   // members ascending
+          const unsigned short v = mem[u];
+          int q = u - 1;
+          while (q >= 0 && mem[q] > v) { mem[q + 1] = mem[q]; q--; }
+          mem[q + 1] = v;
+        }
+        const unsigned myLabel = mem[0];
+        for (int a = 0; a < nm && !conflict; a++) {
+          const int i = mem[a];
+          if (is_dead(i)) continue;
+          MergeRow<T> r;
+          load_row(r, cur, W, i);
+          bool changed = false;
+          int jlast = i;
+          while (true) {
+            int best = 0x7fffffff;
+            for (int b = a + 1; b < nm; b++) {       // members, ascending: the first hit is the smallest
+              const int k = mem[b];
+              if (k > jlast && !is_dead(k) && merge_test(r, cur, W, k, t2)) { best = k; break; }
+            }
+            if (changed) {
+              // neighbours of the changed row: every partner lies within sqrt(max(reach_row, rmax2))
+              const T ri2 = tt * (r.pxx + r.pyy);
+              const bool pd = (r.pxx > T(0)) && (r.pyy > T(0)) && (r.pxx * r.pyy - r.pxy * r.pxy > T(0));
+              if (!pd) { logfull = true; break; }
+              const T R2 = M<T>::max_(ri2, rmax2);
+              const T R = M<T>::sqrt_(R2) * T(1.001);
+              int clo = cell_of(r.x - R) - 1, chi = cell_of(r.x + R) + 1;
+              clo = clo < 0 ? 0 : clo;
+              chi = chi > 255 ? 255 : chi;
+              const int t0 = ms.cellStart[clo], t1 = ms.cellStart[chi + 1];
+              for (int t = t0; t < t1; t++) {
+                const int k = ms.order[t];
+                if (k <= jlast || k >= best) continue;
+                const T dx = cur[k] - r.x, dy = cur[W + k] - r.y;
+                const T d2 = dx * dx + dy * dy;
+                if (d2 > R2) continue;
+                if (d2 > M<T>::max_(ri2, tt * (cur[2 * W + k] + cur[4 * W + k]))) continue;
+                const unsigned owner = ms.label[k];
+                if (owner == myLabel) continue;            // a member (tested above) or already absorbed
+                if (owner != NO_OWNER) {                   // another cluster: link the two and redo M3/M4
+                  conflict = true;
+                  const unsigned q = atomicAdd(&ms.counters[0], 1u);
+                  const unsigned lo = owner < myLabel ? owner : myLabel, hi = owner < myLabel ? myLabel : owner;
+                  if (q < (unsigned)MAX_PAIRS) ms.pairs[q] = (lo << 16) | hi;
+                  else logfull = true;
+                  break;
+                }
+                if (merge_test(r, cur, W, k, t2)) best = k;
+              }
+              if (conflict) break;
+            }
+            if (best == 0x7fffffff) break;
+            if (ms.label[best] != myLabel) {
+              const unsigned prev = atomicCAS(&ms.label[best], NO_OWNER, myLabel);
+              if (prev != NO_OWNER) {                      // claimed by another cluster meanwhile
+                conflict = true;
+                const unsigned q = atomicAdd(&ms.counters[0], 1u);
+                const unsigned lo = prev < myLabel ? prev : myLabel, hi = prev < myLabel ? myLabel : prev;
+                if (q < (unsigned)MAX_PAIRS) ms.pairs[q] = (lo << 16) | hi;
+                else logfull = true;
+                break;
+              }
+            }
+            jlast = best;
+            if (lane_absorb(r, cur, W, best, f)) {   // w == 0: the reference moves on to j+1
+              changed = true;
+              atomicOr(&ms.deadBits[best >> 5], 1u << (best & 31));
+            }
+          }
+          if (changed && !conflict) {
+            const unsigned q = atomicAdd(&ms.counters[1], 1u);
+            if (q < (unsigned)MAX_ROWLOG) {
+              ms.rowIdx[q] = (unsigned short)i;
+              T* e = ms.rowLog + q * 6;
+              e[0] = r.x; e[1] = r.y; e[2] = r.pxx; e[3] = r.pxy; e[4] = r.pyy; e[5] = r.w;
+            } else {
+              logfull = true;
+            }
+          }
+        }
+      }
+      __syncwarp();
     }
-    int jlast = j;
-    while (true) {
-      const T ri2 = merge_reach2(r.pxx, r.pxy, r.pyy, t2);
-      const int jj = merge_rescan<T>(r, ri2, g, cur, rad2, W, jlast, n, t2, lane);
-      if (jj < 0) break;
-      merge_absorb(r, cur, W, i, jj, f, lane);
-      jlast = jj;
+    if (__any_sync(FULL, logfull)) { mstat[3]++; return MERGE_FALLBACK; }
+    if (!__any_sync(FULL, conflict)) {
+      // ---- M5: commit --------------------------------------------------------------------------------
+      mstat[6] += (unsigned)nclusters;
+      const int nrows = (int)ms.counters[1];
+      for (int q = lane; q < nrows; q += 32) {
+        const int i = ms.rowIdx[q];
+        const T* e = ms.rowLog + q * 6;
+        cur[i] = e[0]; cur[W + i] = e[1];
+        cur[2 * W + i] = e[2]; cur[3 * W + i] = e[3]; cur[4 * W + i] = e[4];
+        cur[5 * W + i] = e[5];
+        if (has_wprev) cur[6 * W + i] = T(0);
+      }
+      for (int j = lane; j < n; j += 32)
+        if (is_dead(j)) cur[5 * W + j] = T(-1);   // hole
+      __syncwarp();
+      return MERGE_OK;
     }
-    curkey = ((unsigned)(i + 1)) << 16;
+    // interacting clusters: their heads were linked in the pair list; reset and go round again
+    mstat[4]++;
+    for (int j = lane; j < n; j += 32) ms.label[j] = NO_OWNER;
+    for (int c = lane; c < MAX_CLUSTERS; c += 32) ms.memberCount[c] = 0u;
+    ms.deadBits[lane] = 0u;
+    if (lane == 0) ms.counters[1] = 0u;
+    __syncwarp();
+    if ((int)ms.counters[0] > MAX_PAIRS) { mstat[1]++; return MERGE_FALLBACK; }
   }
+  mstat[2]++;
+  return MERGE_FALLBACK;   // still interacting after MAX_MERGE_ROUNDS
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -524,22 +712,27 @@ __device__ inline double warp_permanent(const double* A, int n, int lane) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// shared-memory carve-up of one warp (bytes), host and device agree through these helpers
+// shared-memory carve-up (bytes); host and device agree through these helpers
+//  per warp: planes A [NPL][W] | planes B [7][W] (multi-feature only) | merge scratch | aux u32[W] |
+//            colsum T[MAX_Z] | evalIdx int[MAX_EVAL] | mbarrier | multi-feature scratch
+//  per CTA : the measurement batch + the two window tables of the corrector
 template <typename T>
-__host__ __device__ inline int scratch_bytes(int W) {
-  // merge scratch: rad2[W] T, pairs, cellStart+cursor, order[W], npairs ; prune keys reuse rad2
-  return (int)((W * sizeof(T) + MAX_PAIRS * 4 + 2 * 258 * 2 + (W + 2) * 2 + 16 + 15) & ~15);
+__host__ __device__ inline int mf_scratch_bytes(int n_eval, int zcap) {
+  const int ltab = (n_eval * zcap + 3) & ~3;
+  return (int)(8 * (MAX_EVAL + MAX_COMP + 2 * (1 << DP_MAXB)) + 4 * MAX_COMP + sizeof(T) * (MAX_EVAL * 8 + ltab) + 15) & ~15;
 }
 template <typename T>
-__host__ __device__ inline int warp_bytes_for(int W, int multi_feature) {
+__host__ __device__ inline int warp_bytes_for(int W, int multi_feature, int mf_bytes) {
   const int planes = multi_feature ? 14 : 6;   // MF keeps a second 7-plane block for the sort
-  int b = planes * W * (int)sizeof(T) + scratch_bytes<T>(W) + W * 4 + MAX_Z * (int)sizeof(T) + MAX_EVAL * 4 + 16;
+  int b = planes * W * (int)sizeof(T) + merge_scratch_bytes<T>(W) + W * 4 + MAX_Z * (int)sizeof(T) + MAX_EVAL * 4 + 16 +
+          (multi_feature ? mf_bytes : 0);
   return (b + 127) & ~127;
 }
-// Z block in shared memory: original (zr,zb) pairs, then range-sorted zr / zb / original index
+constexpr int NBINS = 256;   // bins of the range / bearing window tables
+// Z block: (zr,zb) pairs T[2*MAX_Z] | range table u64[NBINS+1] | bearing table u64[NBINS+1] | bin params T[4] | bins u8[2*MAX_Z]
 template <typename T>
 __host__ __device__ inline int z_bytes() {
-  return (int)((4 * MAX_Z * sizeof(T) + MAX_Z * 4 + 127) & ~127);
+  return (int)((2 * MAX_Z * sizeof(T) + 2 * (NBINS + 1) * 8 + 4 * sizeof(T) + 2 * MAX_Z + 127) & ~127);
 }
 
 template <typename T>
@@ -554,34 +747,70 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
   const int NPL = MF ? 7 : 6;
 
   T* zs = reinterpret_cast<T*>(smem_raw);          // [2*MAX_Z]: zr[z] at 2z, zb[z] at 2z+1
-  T* zrs = zs + 2 * MAX_Z;                           // [MAX_Z] ranges ascending
-  T* zbs = zrs + MAX_Z;                              // [MAX_Z] bearing of the same measurement
-  int* zid = reinterpret_cast<int*>(zbs + MAX_Z);    // [MAX_Z] its original index
+  unsigned long long* tabR = reinterpret_cast<unsigned long long*>(zs + 2 * MAX_Z);   // [NBINS+1]
+  unsigned long long* tabB = tabR + (NBINS + 1);                                      // [NBINS+1]
+  T* binp = reinterpret_cast<T*>(tabB + (NBINS + 1));   // r0, inv_r, b0, inv_b
+  unsigned char* zbin = reinterpret_cast<unsigned char*>(binp + 4);                   // [2*MAX_Z]
   unsigned char* wb = smem_raw + z_bytes<T>() + (size_t)warp * p.warp_bytes;
   T* bufA = reinterpret_cast<T*>(wb);
   T* bufB = bufA + NPL * W;                           // only present in multi-feature mode
   unsigned char* after = reinterpret_cast<unsigned char*>(MF ? bufB + 7 * W : bufB);
-  T* scratch = reinterpret_cast<T*>(after);
-  unsigned* aux = reinterpret_cast<unsigned*>(after + scratch_bytes<T>(W));  // [W]
+  unsigned* aux = reinterpret_cast<unsigned*>(after + merge_scratch_bytes<T>(W));  // [W]
+  const MergeScratch<T> ms = carve_merge_scratch<T>(after, aux, W);
   T* colsum = reinterpret_cast<T*>(aux + W);                  // [MAX_Z]
   int* evalIdx = reinterpret_cast<int*>(colsum + MAX_Z);      // [MAX_EVAL]
   uint64_t* bar = reinterpret_cast<uint64_t*>(evalIdx + MAX_EVAL);
+  unsigned char* mfs = reinterpret_cast<unsigned char*>(bar + 2);   // multi-feature scratch (16-byte aligned)
 
+  // ---- the measurement batch and the corrector's window tables (once per CTA) ------------------
+  // tabR[b] = set of measurements whose range bin is < b, tabB likewise on the bearing: the
+  // measurements with range in [lo,hi] are a subset of tabR[bin(hi)+1] & ~tabR[bin(lo)].
   for (int k = threadIdx.x; k < 2 * nZ; k += blockDim.x) zs[k] = p.Z[k];
-  for (int k = threadIdx.x; k < nZ; k += blockDim.x) {
-    zrs[k] = p.Zr_sorted[k];
-    zbs[k] = p.Zb_sorted[k];
-    zid[k] = p.Z_sorted_idx[k];
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    T lo = M<T>::inf(), hi = -M<T>::inf();
+    for (int z = 0; z < nZ; z++) {
+      const T v = zs[2 * z + threadIdx.x];
+      lo = v < lo ? v : lo;
+      hi = v > hi ? v : hi;
+    }
+    const T span = hi - lo;
+    binp[2 * threadIdx.x] = lo;
+    binp[2 * threadIdx.x + 1] = (span > T(0) && span < M<T>::inf()) ? T(NBINS - 0.001) / span : T(0);
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < 2 * nZ; k += blockDim.x) {
+    const int comp = k & 1;
+    const T v = (zs[k] - binp[2 * comp]) * binp[2 * comp + 1];
+    int b = (v >= T(NBINS - 1)) ? NBINS - 1 : (int)v;
+    zbin[k] = (unsigned char)(b < 0 ? 0 : b);
+  }
+  __syncthreads();
+  for (int b = threadIdx.x; b <= NBINS; b += blockDim.x) {
+    unsigned long long mr = 0, mb = 0;
+    for (int z = 0; z < nZ; z++) {
+      if ((int)zbin[2 * z] < b) mr |= 1ull << z;
+      if ((int)zbin[2 * z + 1] < b) mb |= 1ull << z;
+    }
+    tabR[b] = mr;
+    tabB[b] = mb;
   }
   if (lane == 0) {
     mbar_init(bar, 1);
     fence_mbar_init();
   }
   __syncthreads();
+  const T binR0 = binp[0], binRi = binp[1], binB0 = binp[2], binBi = binp[3];
+  auto bin_of = [](T v, T v0, T inv) -> int {
+    const T u = (v - v0) * inv;
+    const int b = (u >= T(NBINS - 1)) ? NBINS - 1 : (int)u;
+    return b < 0 ? 0 : b;
+  };
 
   uint32_t phase = 0;
   unsigned long long tot_in = 0, tot_out = 0;
-  int max_out = 0, n_over = 0, n_murty = 0;
+  int max_out = 0, n_over = 0, n_murty = 0, n_fallback = 0;
+  unsigned mstat[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // merge statistics: fallbacks by reason, pairs, clusters
 
   while (true) {
     // dynamic particle queue: one atomic per particle, broadcast to the warp
@@ -590,13 +819,13 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
     pi = __shfl_sync(FULL, pi, 0);
     if (pi >= p.N) break;
 
+    const double w_prev_particle = p.w_in[pi];
     T* cur = bufA;
     T* alt = bufB;
     int nM = p.cnt_in[pi];
     nM = nM < 0 ? 0 : (nM > p.cap ? p.cap : nM);
     int flags = 0;
     if (nM > W) { nM = W; flags |= FLAG_OVERFLOW; }
-    const double w_prev_particle = p.w_in[pi];
 
     // ---------------- S0: TMA bulk loads -------------------------------------------------
     if (nM > 0) {
@@ -684,24 +913,14 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
           norm = T(1) / M<T>::sqrt_(M<T>::TWO_PI * M<T>::TWO_PI * det);
           Pdw = Pd * w;
           // candidate measurements: md2 >= nu_r^2/S_rr and md2 >= nu_b^2/S_bb for a PD S, so only the
-          // measurements inside the range window of the range-sorted batch whose bearing is close too
-          // can pass the gate (both bounds slightly widened against rounding).
+          // measurements inside both windows can pass the gate (bounds slightly widened against
+          // rounding); the windows are looked up in the per-CTA tables.
           if (det > T(0) && s00 > T(0) && s11 > T(0)) {
-            const T dr = M<T>::sqrt_(p.gate2 * s00 * T(1.0002));
-            const T cb = p.gate2 * s11 * T(1.0002);
-            const T rlo = zr_hat - dr, rhi = zr_hat + dr;
-            int lo = 0;
-#pragma unroll
-            for (int step = MAX_Z / 2; step >= 1; step >>= 1) {
-              const int k = lo + step;
-              if (k <= nZ && zrs[k - 1] < rlo) lo = k;
-            }
-            if (lo < nZ && zrs[lo] < rlo) lo++;
-            for (int k = lo; k < nZ; k++) {
-              if (zrs[k] > rhi) break;
-              const T nb = zbs[k] - zb_hat;
-              if (!(nb * nb > cb)) cand |= (1ull << zid[k]);
-            }
+            const T dr = M<T>::sqrt_(p.gate2 * s00) * T(1.0002);
+            const T db = M<T>::sqrt_(p.gate2 * s11) * T(1.0002);
+            const unsigned long long mr = tabR[bin_of(zr_hat + dr, binR0, binRi) + 1] & ~tabR[bin_of(zr_hat - dr, binR0, binRi)];
+            const unsigned long long mb = tabB[bin_of(zb_hat + db, binB0, binBi) + 1] & ~tabB[bin_of(zb_hat - db, binB0, binBi)];
+            cand = mr & mb;
           } else {
             cand = (nZ >= 64) ? ~0ull : ((1ull << nZ) - 1ull);   // degenerate S: test everything
           }
@@ -922,13 +1141,13 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
         }
         __syncwarp();
         // rfsMeasurementLikelihood (:821-997): L table with the landmark covariance zeroed
-        T* ep = alt;                    // [MAX_EVAL][8]: zr, zb, i00, i01, i11, Pd*norm, Pd
-        T* L = alt + MAX_EVAL * 8;      // [nE][nZ]
-        unsigned long long* rowmask = reinterpret_cast<unsigned long long*>(L + ((nE * nZ + 3) & ~3));  // [MAX_EVAL]
-        unsigned* compR = reinterpret_cast<unsigned*>(rowmask + MAX_EVAL);          // [MAX_COMP]
-        unsigned long long* compC = reinterpret_cast<unsigned long long*>(compR + MAX_COMP);  // [MAX_COMP]
+        unsigned long long* rowmask = reinterpret_cast<unsigned long long*>(mfs);   // [MAX_EVAL]
+        unsigned long long* compC = rowmask + MAX_EVAL;                             // [MAX_COMP]
         double* f0 = reinterpret_cast<double*>(compC + MAX_COMP);                   // [1<<DP_MAXB]
         double* f1 = f0 + (1 << DP_MAXB);
+        unsigned* compR = reinterpret_cast<unsigned*>(f1 + (1 << DP_MAXB));         // [MAX_COMP]
+        T* ep = reinterpret_cast<T*>(compR + MAX_COMP);   // [MAX_EVAL][8]: zr, zb, i00, i01, i11, Pd*norm, -, Pd
+        T* L = ep + MAX_EVAL * 8;                         // [nE][nZ]
         T* evalPd = ep + MAX_EVAL * 7;  // stride-1 array of Pd per eval point (slot 7 of the ep block region)
         if (lane < nE) {
           const int ei = evalIdx[lane];
@@ -1072,15 +1291,18 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
 
     // ---------------- S6: merge ------------------------------------------------------------------
     if (n > 1) {
-      if (p.merge_algo == 0) merge_bruteforce<T>(cur, W, n, p.merge_t2, p.merge_f, lane);
-      else merge_culled<T>(cur, scratch, W, n, p.merge_t2, p.merge_f, lane);
+      int st = MERGE_FALLBACK;
+      if (p.merge_algo != 0) st = merge_clustered<T>(cur, ms, W, n, p.merge_t2, p.merge_f, MF, lane, mstat);
+      __syncwarp();
+      if (st == MERGE_FALLBACK && p.merge_algo != 0) n_fallback++;
+      if (st == MERGE_FALLBACK) merge_bruteforce<T>(cur, W, n, p.merge_t2, p.merge_f, lane);
     }
     __syncwarp();
 
     // ---------------- S7: prune + store ------------------------------------------------------------
     int n_out = 0;
     {
-      T* kw = scratch;   // [W] sort keys (the merge scratch is dead)
+      T* kw = ms.keys;   // [W] sort keys (the merge-only scratch is dead)
       for (int base = 0; base < n; base += 32) {
         const int k = base + lane;
         bool keep = false;
@@ -1127,6 +1349,10 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
     atomicMax(&p.istats[0], max_out);
     if (n_over) atomicAdd(&p.istats[1], n_over);
     if (n_murty) atomicAdd(&p.istats[2], n_murty);
+    if (n_fallback) atomicAdd(&p.istats[3], n_fallback);
+#pragma unroll
+    for (int k = 0; k < 7; k++)
+      if (mstat[k]) atomicAdd(&p.mstats[k], mstat[k]);
   }
 
   // ---------------- S8: deterministic [sum w, sum w^2] by the last CTA ----------------------------
@@ -1162,8 +1388,10 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
       p.stats_out[2] = (unsigned long long)(unsigned)__ldcg(&p.istats[0]);
       p.stats_out[3] = (unsigned long long)(unsigned)__ldcg(&p.istats[1]);
       p.stats_out[4] = (unsigned long long)(unsigned)__ldcg(&p.istats[2]);
+      p.stats_out[5] = (unsigned long long)(unsigned)__ldcg(&p.istats[3]);
+      for (int k = 0; k < 7; k++) { p.stats_out[6 + k] = (unsigned long long)__ldcg(&p.mstats[k]); p.mstats[k] = 0u; }
       p.totals[0] = 0; p.totals[1] = 0;
-      p.istats[0] = 0; p.istats[1] = 0; p.istats[2] = 0;
+      p.istats[0] = 0; p.istats[1] = 0; p.istats[2] = 0; p.istats[3] = 0;
       *p.ticket = 0;
       *p.work_counter = 0;
     }

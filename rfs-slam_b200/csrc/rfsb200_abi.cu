@@ -54,6 +54,7 @@ struct rfsb200_ctx {
   double* sums = nullptr;                 // [2]
   unsigned long long* totals = nullptr;   // [2]
   int* istats = nullptr;                  // [4]
+  unsigned int* mstats = nullptr;         // [8]
   unsigned int* ticket = nullptr;
   unsigned int* work_counter = nullptr;
   unsigned long long* stats_out = nullptr;  // [8]
@@ -74,6 +75,7 @@ struct rfsb200_ctx {
   int grid = 0;
   size_t smem_bytes = 0;
   int warp_bytes = 0;
+  int mf_bytes = 0;
   std::string err;
 };
 
@@ -200,7 +202,8 @@ int round_pow2(int v) {
 template <typename T>
 int configure_launch(rfsb200_ctx* c, int mf) {
   if (c->cfg_mode_mf == mf) return RFSB200_OK;
-  c->warp_bytes = warp_bytes_for<T>(c->W, mf);
+  c->mf_bytes = mf ? mf_scratch_bytes<T>(MAX_EVAL, c->dims.z_capacity) : 0;
+  c->warp_bytes = warp_bytes_for<T>(c->W, mf, c->mf_bytes);
   c->smem_bytes = (size_t)z_bytes<T>() + (size_t)WARPS_PER_CTA * c->warp_bytes;
   if (c->smem_bytes > 227 * 1024) return fail(c, RFSB200_ECAPACITY, "work_capacity %d needs %zu B shared memory per CTA (> 227 KB)", c->W, c->smem_bytes);
   CU(c, cudaFuncSetAttribute(phd_update_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
@@ -240,16 +243,15 @@ int launch_update(rfsb200_ctx* c, int nZ, int out_idx) {
   p.gm_in = (const T*)in.gm; p.cnt_in = in.cnt; p.w_in = in.weight;
   p.pose = (const T*)c->pose; p.pose_cov = (const T*)c->pose_cov;
   p.Z = (const T*)c->Zdev;
-  p.Zr_sorted = p.Z + 2 * MAX_Z; p.Zb_sorted = p.Z + 3 * MAX_Z;
-  p.Z_sorted_idx = (const int*)(p.Z + 4 * MAX_Z);
   p.gm_out = (T*)out.gm; p.cnt_out = out.cnt; p.w_out = out.weight;
   p.unused = c->unused; p.nfov = c->nfov; p.flags = c->flags;
-  p.sums = c->sums; p.totals = c->totals; p.istats = c->istats; p.ticket = c->ticket;
+  p.sums = c->sums; p.totals = c->totals; p.istats = c->istats; p.ticket = c->ticket; p.mstats = c->mstats;
   p.work_counter = c->work_counter; p.stats_out = c->stats_out;
   {
     int rc = configure_launch<T>(c, f.use_cluster_process ? 0 : 1);
     if (rc) return rc;
     p.warp_bytes = c->warp_bytes;
+    p.mf_bytes = c->mf_bytes;
   }
   const bool prof = c->prof_n < c->prof_cap;
   if (prof) CU(c, cudaEventRecord(c->prof_ev[2 * c->prof_n], c->stream));
@@ -349,10 +351,12 @@ int rfsb200_create(rfsb200_ctx** out, const rfsb200_dims* d) {
     CU(c, cudaMalloc((void**)&c->totals, 16));
     CU(c, cudaMalloc((void**)&c->istats, 16));
     CU(c, cudaMalloc((void**)&c->ticket, 4));
+    CU(c, cudaMalloc((void**)&c->mstats, 32));
+    CU(c, cudaMemset(c->mstats, 0, 32));
     CU(c, cudaMalloc((void**)&c->work_counter, 4));
-    CU(c, cudaMalloc((void**)&c->stats_out, 64));
+    CU(c, cudaMalloc((void**)&c->stats_out, 128));
     CU(c, cudaMemset(c->work_counter, 0, 4));
-    CU(c, cudaMemset(c->stats_out, 0, 64));
+    CU(c, cudaMemset(c->stats_out, 0, 128));
     CU(c, cudaMemset(c->totals, 0, 16));
     CU(c, cudaMemset(c->istats, 0, 16));
     CU(c, cudaMemset(c->sums, 0, 16));
@@ -388,7 +392,7 @@ int rfsb200_destroy(rfsb200_ctx* c) {
   cudaFree(c->pose); cudaFree(c->pose_cov); cudaFree(c->Zdev);
   cudaFree(c->unused); cudaFree(c->nfov); cudaFree(c->flags);
   cudaFree(c->sums); cudaFree(c->totals); cudaFree(c->istats); cudaFree(c->ticket);
-  cudaFree(c->work_counter); cudaFree(c->stats_out);
+  cudaFree(c->work_counter); cudaFree(c->stats_out); cudaFree(c->mstats);
   cudaFree(c->stg); cudaFree(c->offs); cudaFree(c->stg_small);
   if (c->hpin) cudaFreeHost(c->hpin);
   if (c->ev0) cudaEventDestroy(c->ev0);
@@ -429,21 +433,6 @@ int rfsb200_set_filter_cfg(rfsb200_ctx* c, const rfsb200_filter_cfg* f) {
   if (f->eval_point_count < 0 || f->eval_point_count > MAX_EVAL)
     return fail(c, RFSB200_EUNSUPPORTED, "eval_point_count %d outside [0,%d]", f->eval_point_count, MAX_EVAL);
   if (!(f->pruning_threshold > 0)) return fail(c, RFSB200_EINVAL, "pruning_threshold must be > 0");
-  if (!f->use_cluster_process) {
-    // scratch for the likelihood table of rfsMeasurementLikelihood
-    const size_t blk = (size_t)7 * c->W * c->tsize;
-    const size_t need = (size_t)MAX_EVAL * 8 * c->tsize + (size_t)((f->eval_point_count * c->dims.z_capacity + 3) & ~3) * c->tsize +
-                        MAX_EVAL * 8 + MAX_COMP * 12 + 2 * (1 << DP_MAXB) * 8;
-    if (need > blk) {
-      // the table lives in the second 7-plane block of the warp: widen the planes until it fits
-      int W = c->W;
-      while ((size_t)7 * W * c->tsize < need && W < 1024) W <<= 1;
-      if ((size_t)7 * W * c->tsize < need)
-        return fail(c, RFSB200_ECAPACITY, "eval_point_count x z_capacity needs %zu B scratch (> %zu)", need, blk);
-      c->W = W;
-      c->cfg_mode_mf = -1;
-    }
-  }
   c->cfg = *f;
   c->merge_algo = (f->reserved_i[0] == 1) ? 0 : 1;  // reserved_i[0] == 1 selects the brute-force merge (debug)
   c->have_cfg = true;
@@ -508,40 +497,26 @@ int rfsb200_update(rfsb200_ctx* c, const double* Z, int32_t nZ, uint32_t flags, 
   if (nZ == 0) return RFSB200_OK;  // include/RBPHDFilter.hpp:451-452 (Q11)
   if (!Z) return fail(c, RFSB200_EINVAL, "NULL Z");
   CU(c, cudaSetDevice(c->device));
-  // Z -> T in pinned scratch -> device: original pairs + the batch sorted by range (for the
-  // corrector's window search)
+  // Z -> T in a pinned staging slot -> device
   unsigned char* zsrc = nullptr;
   unsigned zslot_used = 0;
   {
-    int order[MAX_Z];
-    for (int k = 0; k < nZ; k++) order[k] = k;
-    std::stable_sort(order, order + nZ, [&](int a, int b) { return Z[2 * a] < Z[2 * b]; });
     const unsigned slot = (c->zslot++) & 7u;
     CU(c, cudaEventSynchronize(c->zev[slot]));   // the copy that last read this slot has finished
     unsigned char* hb = c->hpin + 16384 + (size_t)slot * 4096;
     zsrc = hb;
     zslot_used = slot;
-    int* hidx = (int*)(hb + (size_t)4 * MAX_Z * c->tsize);
     if (c->prec == 32) {
       float* h = (float*)hb;
       for (int k = 0; k < 2 * nZ; k++) h[k] = (float)Z[k];
-      for (int k = 0; k < nZ; k++) {
-        h[2 * MAX_Z + k] = (float)Z[2 * order[k]];
-        h[3 * MAX_Z + k] = (float)Z[2 * order[k] + 1];
-      }
     } else {
       double* h = (double*)hb;
       for (int k = 0; k < 2 * nZ; k++) h[k] = Z[k];
-      for (int k = 0; k < nZ; k++) {
-        h[2 * MAX_Z + k] = Z[2 * order[k]];
-        h[3 * MAX_Z + k] = Z[2 * order[k] + 1];
-      }
     }
-    for (int k = 0; k < nZ; k++) hidx[k] = order[k];
   }
   int launches = 0;
   if (out) CU(c, cudaEventRecord(c->ev0, c->stream));
-  CU(c, cudaMemcpyAsync(c->Zdev, zsrc, (size_t)4 * MAX_Z * c->tsize + MAX_Z * 4, cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaMemcpyAsync(c->Zdev, zsrc, (size_t)2 * nZ * c->tsize, cudaMemcpyHostToDevice, c->stream));
   CU(c, cudaEventRecord(c->zev[zslot_used], c->stream));
   const int out_idx = c->front ^ 1;
   int rc = (c->prec == 32) ? launch_update<float>(c, nZ, out_idx) : launch_update<double>(c, nZ, out_idx);
@@ -558,7 +533,7 @@ int rfsb200_update(rfsb200_ctx* c, const double* Z, int32_t nZ, uint32_t flags, 
     CU(c, cudaEventRecord(c->ev1, c->stream));
     unsigned char* h = c->hpin + 8192;
     CU(c, cudaMemcpyAsync(h, c->sums, 16, cudaMemcpyDeviceToHost, c->stream));
-    CU(c, cudaMemcpyAsync(h + 16, c->stats_out, 40, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaMemcpyAsync(h + 16, c->stats_out, 104, cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
     const double* s = (const double*)h;
     const unsigned long long* t = (const unsigned long long*)(h + 16);
@@ -570,6 +545,8 @@ int rfsb200_update(rfsb200_ctx* c, const double* Z, int32_t nZ, uint32_t flags, 
     out->gm_max_out = (int32_t)t[2];
     out->n_overflow = (int32_t)t[3];
     out->n_murty = (int32_t)t[4];
+    out->n_merge_redo = (int32_t)t[5];
+    for (int k = 0; k < 6; k++) out->reserved[k] = (int32_t)t[6 + k];   // merge diagnostics
     out->n_launches = launches;
     float ms = 0;
     CU(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
