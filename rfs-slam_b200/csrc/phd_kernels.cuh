@@ -786,14 +786,30 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
     zbin[k] = (unsigned char)(b < 0 ? 0 : b);
   }
   __syncthreads();
-  for (int b = threadIdx.x; b <= NBINS; b += blockDim.x) {
-    unsigned long long mr = 0, mb = 0;
-    for (int z = 0; z < nZ; z++) {
-      if ((int)zbin[2 * z] < b) mr |= 1ull << z;
-      if ((int)zbin[2 * z + 1] < b) mb |= 1ull << z;
+  for (int b = threadIdx.x; b <= NBINS; b += blockDim.x) { tabR[b] = 0ull; tabB[b] = 0ull; }
+  __syncthreads();
+  // exact bin sets at [bin+1], then an exclusive prefix-OR: tab[b] = measurements with bin < b
+  for (int k = threadIdx.x; k < 2 * nZ; k += blockDim.x) {
+    unsigned long long* tab = (k & 1) ? tabB : tabR;
+    atomicOr(&tab[(int)zbin[k] + 1], 1ull << (k >> 1));
+  }
+  __syncthreads();
+  if (warp < 2) {
+    unsigned long long* tab = warp ? tabB : tabR;
+    unsigned long long loc[8];
+    unsigned long long acc = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) { acc |= tab[1 + lane * 8 + k]; loc[k] = acc; }
+    unsigned long long run = acc;   // inclusive OR-scan of the lane totals
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long u = __shfl_up_sync(FULL, run, o);
+      if (lane >= o) run |= u;
     }
-    tabR[b] = mr;
-    tabB[b] = mb;
+    unsigned long long before_me = __shfl_up_sync(FULL, run, 1);
+    if (lane == 0) before_me = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) tab[1 + lane * 8 + k] = loc[k] | before_me;
   }
   if (lane == 0) {
     mbar_init(bar, 1);
@@ -854,15 +870,21 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
     double wsum_d = 0;          // sum of pre-update weights (SC-PHD)
     int nfov = 0;
     bool over = false;
+    // S1a: every component — detection probability, missed-detection weight, and a CHEAP conservative
+    // test for "some measurement could pass the gate": S_rr <= tr(P) + tr(Sigma_xy) + R_rr and
+    // S_bb <= tr(P)/r^2 + tr(Sigma)(1/r^2 + 1) + R_bb for PSD P and Sigma, so a component whose
+    // widened windows hold no measurement is finished here.  The others are queued for S1b.
+    unsigned short* candIdx = ms.order;   // [W] (free until the merge)
+    T* candW = ms.keys;                    // [W] pre-update weight of the queued components
+    int ncand = 0;
+    const T pc_xy = c00 + c11, pc_all = c00 + c11 + c22;
+    const bool pc_ok = (c00 >= T(0)) && (c11 >= T(0)) && (c22 >= T(0));
     for (int base = 0; base < nM; base += 32) {
       const int m = base + lane;
-      unsigned long long cand = 0;
-      T x = 0, y = 0, pxx = 0, pxy = 0, pyy = 0, w = 0;
-      T zr_hat = 0, zb_hat = 0, i00 = 0, i01 = 0, i11 = 0, norm = 0, Pdw = 0;
-      T hp00 = 0, hp01 = 0, hp10 = 0, hp11 = 0;
+      bool queue = false;
+      T w = 0;
       if (m < nM) {
-        x = cur[m]; y = cur[W + m];
-        pxx = cur[2 * W + m]; pxy = cur[3 * W + m]; pyy = cur[4 * W + m];
+        const T x = cur[m], y = cur[W + m];
         w = cur[5 * W + m];
         wsum_d += (double)w;
         const T dx = x - px, dy = y - py;
@@ -888,6 +910,51 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
         cur[5 * W + m] = fix ? w : (T(1) - Pd) * w;
         aux[m] = fix ? 1u : 0u;
         if (Pd != T(0) && inrange) {              // measure() returns false outside [rmin,rmax]
+          const T pxx = cur[2 * W + m], pxy = cur[3 * W + m], pyy = cur[4 * W + m];
+          const bool pd = (pxx > T(0)) && (pyy > T(0)) && (pxx * pyy - pxy * pxy > T(0));
+          queue = true;
+          if (pd && pc_ok) {
+            const T zb_hat = wrap_pi<T>(M<T>::atan2_(dy, dx) - pth);
+            const T ir2 = T(1) / r2;
+            const T tr = pxx + pyy;
+            const T srr = (tr + pc_xy + p.R00) * T(1.001);
+            const T sbb = (tr * ir2 + pc_all * (ir2 + T(1)) + p.R11) * T(1.001);
+            const T dr = M<T>::sqrt_(p.gate2 * srr);
+            const T db = M<T>::sqrt_(p.gate2 * sbb);
+            const unsigned long long mr = tabR[bin_of(r + dr, binR0, binRi) + 1] & ~tabR[bin_of(r - dr, binR0, binRi)];
+            const unsigned long long mb = tabB[bin_of(zb_hat + db, binB0, binBi) + 1] & ~tabB[bin_of(zb_hat - db, binB0, binBi)];
+            queue = (mr & mb) != 0ull;
+          }
+        }
+      }
+      const unsigned bq = __ballot_sync(FULL, queue);
+      if (queue) {
+        const int pos = ncand + __popc(bq & ((1u << lane) - 1u));
+        candIdx[pos] = (unsigned short)m;
+        candW[pos] = w;
+      }
+      ncand += __popc(bq);
+    }
+    __syncwarp();
+    // S1b: the queued components (ascending m) — EKF innovation, exact gate, posterior Gaussians
+    for (int base = 0; base < ncand; base += 32) {
+      const int q = base + lane;
+      unsigned long long cand = 0;
+      int m = 0;
+      T x = 0, y = 0, pxx = 0, pxy = 0, pyy = 0;
+      T zr_hat = 0, zb_hat = 0, i00 = 0, i01 = 0, i11 = 0, norm = 0, Pdw = 0;
+      T hp00 = 0, hp01 = 0, hp10 = 0, hp11 = 0;
+      if (q < ncand) {
+        m = candIdx[q];
+        const T w = candW[q];
+        x = cur[m]; y = cur[W + m];
+        pxx = cur[2 * W + m]; pxy = cur[3 * W + m]; pyy = cur[4 * W + m];
+        const T dx = x - px, dy = y - py;
+        const T r2 = dx * dx + dy * dy;
+        const T r = M<T>::sqrt_(r2);
+        const bool close = (r >= p.rmax - p.rbuf) || (r <= p.rmin + p.rbuf);   // in range here
+        const T Pd = close ? T(1) : p.Pd;
+        {
           const T invr = T(1) / r;
           const T c = dx * invr, s = dy * invr;
           const T h10 = -s * invr, h11 = c * invr;   // -dy/r^2, dx/r^2
@@ -1316,15 +1383,35 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
         }
         n_out += __popc(b);
       }
-      const int P = next_pow2(n_out);
-      for (int k = n_out + lane; k < P; k += 32) { kw[k] = -M<T>::inf(); aux[k] = 0xffffffffu; }
+      unsigned short* sorted = ms.order;   // [W] component index by output position
       __syncwarp();
-      if (n_out > 1) warp_bitonic(kw, aux, P, lane);
+      if (n_out <= 64) {
+        // rank sort: position = number of kept components that come before (weight desc, index asc)
+        const int e0 = lane, e1 = lane + 32;
+        const T w0 = e0 < n_out ? kw[e0] : T(0), w1 = e1 < n_out ? kw[e1] : T(0);
+        const unsigned i0 = e0 < n_out ? aux[e0] : 0u, i1 = e1 < n_out ? aux[e1] : 0u;
+        int r0 = 0, r1 = 0;
+        for (int q = 0; q < n_out; q++) {
+          const T wq = kw[q];
+          const unsigned iq = aux[q];
+          r0 += before(wq, iq, w0, i0) ? 1 : 0;
+          r1 += before(wq, iq, w1, i1) ? 1 : 0;
+        }
+        if (e0 < n_out) sorted[r0] = (unsigned short)i0;
+        if (e1 < n_out) sorted[r1] = (unsigned short)i1;
+      } else {
+        const int P = next_pow2(n_out);
+        for (int k = n_out + lane; k < P; k += 32) { kw[k] = -M<T>::inf(); aux[k] = 0xffffffffu; }
+        __syncwarp();
+        warp_bitonic(kw, aux, P, lane);
+        for (int k = lane; k < n_out; k += 32) sorted[k] = (unsigned short)aux[k];
+      }
+      __syncwarp();
       if (n_out > p.cap) { n_out = p.cap; flags |= FLAG_OVERFLOW; }
       // gather from shared memory, 128-byte coalesced stores to the particle's planes in HBM
       T* dst = p.gm_out + (size_t)pi * 6 * p.cap;
       for (int k = lane; k < n_out; k += 32) {
-        const unsigned src = aux[k];
+        const unsigned src = sorted[k];
 #pragma unroll
         for (int pl = 0; pl < 6; pl++) dst[(size_t)pl * p.cap + k] = cur[pl * W + src];
       }
