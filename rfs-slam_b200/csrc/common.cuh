@@ -108,7 +108,27 @@ template <> struct M<float> {
   static __device__ __forceinline__ float sqrt_(float x) { return sqrtf(x); }
   static __device__ __forceinline__ float exp_(float x) { return expf(x); }
   static __device__ __forceinline__ float log_(float x) { return logf(x); }
-  static __device__ __forceinline__ float atan2_(float y, float x) { return atan2f(y, x); }
+  // atan2 to ~1 ulp of pi/2 (1.1e-7 abs): min/max reduction to [0,1], degree-8 minimax in a^2
+  static __device__ __forceinline__ float atan2_(float y, float x) {
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    float a = __fdividef(mn, mx);
+    if (mx == 0.f) a = 0.f;
+    const float s = a * a;
+    float q = 0.0028340641874819994f;
+    q = fmaf(q, s, -0.016005029901862144f);
+    q = fmaf(q, s, 0.042587608098983765f);
+    q = fmaf(q, s, -0.07495445758104324f);
+    q = fmaf(q, s, 0.10636754333972931f);
+    q = fmaf(q, s, -0.14202570915222168f);
+    q = fmaf(q, s, 0.19992484152317047f);
+    q = fmaf(q, s, -0.3333306610584259f);
+    q = fmaf(q, s, 1.0f);
+    float r = q * a;
+    if (ay > ax) r = 1.5707963267948966f - r;
+    if (x < 0.f) r = 3.14159265358979323846f - r;
+    return copysignf(r, y);
+  }
   static __device__ __forceinline__ float abs_(float x) { return fabsf(x); }
   static __device__ __forceinline__ float max_(float a, float b) { return fmaxf(a, b); }
   static __device__ __forceinline__ float inf() { return __int_as_float(0x7f800000); }

@@ -112,6 +112,22 @@ __device__ __forceinline__ void warp_bitonic(T* kw, unsigned* ki, int P, int lan
   }
 }
 
+// Bitonic sort, DESCENDING, of P (power of two) packed u64 keys in shared memory by one warp.
+__device__ __forceinline__ void warp_bitonic_desc64(unsigned long long* key, int P, int lane) {
+  for (int k = 2; k <= P; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = lane; t < (P >> 1); t += 32) {
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        const int q = i + j;
+        const bool up = ((i & k) == 0);
+        const unsigned long long a = key[i], b = key[q];
+        if ((a > b) != up) { key[i] = b; key[q] = a; }
+      }
+      __syncwarp();
+    }
+  }
+}
+
 __device__ __forceinline__ int next_pow2(int n) {
   int p = 1;
   while (p < n) p <<= 1;
@@ -263,27 +279,36 @@ constexpr int MAX_MERGE_ROUNDS = 4;
 constexpr unsigned NO_OWNER = 0xffffffffu;
 
 template <typename T>
+struct XY { T x, y; };
+
+template <typename T>
 struct MergeScratch {
   unsigned* label;           // [W] cluster label (smallest member index) / NO_OWNER   (aliases aux)
   unsigned short* order;     // [W] cell order -> component index
-  unsigned short* slot;      // [W] component index of a cluster head -> cluster slot
+  unsigned short* slot;      // [W] M1/M2: cell of a component; M3+: cluster slot of a cluster head
   unsigned short* cellStart; // [264]
   unsigned* counters;        // [4]: 0 = number of pairs, 1 = logged rows
-  // --- region that is dead outside the merge (the prune sort keys alias it) ---
+  // --- region that is dead outside the merge (the prune sort keys alias all of it) ---
+  XY<T>* sxy;                // [W] M1/M2 only: (x, y) in cell order   } same storage
+  T* rowLog;                 // [MAX_ROWLOG][6]                         } (rowLog, members, rowIdx
+  unsigned short* members;   // [MAX_CLUSTERS][MAX_MEMBERS]             }  are M3+ only)
+  unsigned short* rowIdx;    // [MAX_ROWLOG]                            }
   unsigned* pairs;           // [MAX_PAIRS]
   unsigned* memberCount;     // [MAX_CLUSTERS]
   unsigned* deadBits;        // [32] bit per component (W <= 1024)
-  T* rowLog;                 // [MAX_ROWLOG][6]
-  unsigned short* rowIdx;    // [MAX_ROWLOG]
-  unsigned short* members;   // [MAX_CLUSTERS][MAX_MEMBERS]
-  T* keys;                   // [W] prune sort keys (same storage as pairs..members)
+  T* keys;                   // [W] prune sort keys (fp64) / packed u64 keys (fp32)
 };
 
 template <typename T>
+__host__ __device__ inline int merge_region_a_bytes(int W) {
+  const int a = MAX_ROWLOG * 6 * (int)sizeof(T) + MAX_CLUSTERS * MAX_MEMBERS * 2 + MAX_ROWLOG * 2;
+  const int b = 2 * W * (int)sizeof(T);
+  return ((a > b ? a : b) + 15) & ~15;
+}
+template <typename T>
 __host__ __device__ inline int merge_only_bytes(int W) {
-  const int a = MAX_PAIRS * 4 + MAX_CLUSTERS * 4 + 32 * 4 + MAX_ROWLOG * 6 * (int)sizeof(T) + MAX_ROWLOG * 2 +
-                MAX_CLUSTERS * MAX_MEMBERS * 2;
-  const int b = W * (int)sizeof(T);
+  const int a = merge_region_a_bytes<T>(W) + MAX_PAIRS * 4 + MAX_CLUSTERS * 4 + 32 * 4;
+  const int b = W * 8;   // prune sort keys: T[W] (fp64) or packed u64[W] (fp32)
   return ((a > b ? a : b) + 15) & ~15;
 }
 // label[] is the caller's aux array and is not counted here
@@ -302,12 +327,13 @@ __device__ __forceinline__ MergeScratch<T> carve_merge_scratch(unsigned char* ba
   m.cellStart = m.slot + W;
   unsigned char* r = base + ((2 * W * 2 + 264 * 2 + 16 + 15) & ~15);
   m.keys = reinterpret_cast<T*>(r);
+  m.sxy = reinterpret_cast<XY<T>*>(r);
   m.rowLog = reinterpret_cast<T*>(r);
-  m.pairs = reinterpret_cast<unsigned*>(m.rowLog + MAX_ROWLOG * 6);
+  m.members = reinterpret_cast<unsigned short*>(m.rowLog + MAX_ROWLOG * 6);
+  m.rowIdx = m.members + MAX_CLUSTERS * MAX_MEMBERS;
+  m.pairs = reinterpret_cast<unsigned*>(r + merge_region_a_bytes<T>(W));
   m.memberCount = m.pairs + MAX_PAIRS;
   m.deadBits = m.memberCount + MAX_CLUSTERS;
-  m.rowIdx = reinterpret_cast<unsigned short*>(m.deadBits + 32);
-  m.members = m.rowIdx + MAX_ROWLOG;
   return m;
 }
 
@@ -346,30 +372,17 @@ __device__ __forceinline__ bool lane_absorb(MergeRow<T>& r, const T* cur, int W,
 
 template <typename T>
 __device__ int merge_clustered(T* cur, const MergeScratch<T>& ms, int W, int n, T t2, T f, bool has_wprev,
-                               int lane, unsigned (&mstat)[8]) {
-  // ---- M1: reach, bounding interval, counting sort on cells ------------------------------------
-  T xmin = M<T>::inf(), xmax = -M<T>::inf(), rmax2 = T(0);
-  bool bad = false;
-  for (int j = lane; j < n; j += 32) {
-    const T a = cur[2 * W + j], b = cur[3 * W + j], c = cur[4 * W + j];
-    const bool pd = (a > T(0)) && (c > T(0)) && (a * c - b * b > T(0));
-    bad |= !pd;
-    const T rr = a + c;
-    const T x = cur[j];
-    xmin = x < xmin ? x : xmin;
-    xmax = x > xmax ? x : xmax;
-    rmax2 = rr > rmax2 ? rr : rmax2;
-    ms.label[j] = NO_OWNER;
-  }
+                               int lane, unsigned (&mstat)[8], T xmin, T xmax, T trmax, bool bad) {
+  // ---- M1: counting sort on cells.  xmin / xmax / trmax (largest trace(P)) / bad (some covariance
+  //      is not PD) over the n components were gathered by the corrector (warp-uniform values). ----
+  for (int j = lane; j < n; j += 32) ms.label[j] = NO_OWNER;
   for (int c = lane; c < 132; c += 32) reinterpret_cast<unsigned*>(ms.cellStart)[c] = 0u;
   for (int c = lane; c < MAX_CLUSTERS; c += 32) ms.memberCount[c] = 0u;
   ms.deadBits[lane] = 0u;
   if (lane < 4) ms.counters[lane] = 0u;
-  if (__any_sync(FULL, bad)) { mstat[0]++; return MERGE_FALLBACK; }   // a non-PD covariance has no finite reach
-  xmin = warp_min(xmin);
-  xmax = warp_max(xmax);
+  if (bad) { mstat[0]++; return MERGE_FALLBACK; }   // a non-PD covariance has no finite reach
   const T tt = t2 * T(1.001);                // reach^2 of a component = tt * trace(P)
-  rmax2 = warp_max(rmax2) * tt;
+  const T rmax2 = trmax * tt;
   if (!(rmax2 < M<T>::inf()) || !(xmax - xmin < M<T>::inf())) { mstat[0]++; return MERGE_FALLBACK; }
   const T span = xmax - xmin;
   const T rmax = M<T>::sqrt_(rmax2) * T(1.001);
@@ -383,17 +396,18 @@ __device__ int merge_clustered(T* cur, const MergeScratch<T>& ms, int W, int n, 
   };
   __syncwarp();
   for (int j = lane; j < n; j += 32) {   // histogram at cell+1; 16-bit counters packed in words
-    const int c = cell_of(cur[j]) + 1;
-    atomicAdd(reinterpret_cast<unsigned*>(ms.cellStart) + (c >> 1), (c & 1) ? 0x10000u : 1u);
+    const int c = cell_of(cur[j]);
+    ms.slot[j] = (unsigned short)c;
+    atomicAdd(reinterpret_cast<unsigned*>(ms.cellStart) + ((c + 1) >> 1), ((c + 1) & 1) ? 0x10000u : 1u);
   }
   __syncwarp();
   {  // inclusive prefix over entries 1..256: lane owns 8 consecutive entries
     int loc[8];
-    int s = 0;
+    int sum = 0;
 #pragma unroll
-    for (int k = 0; k < 8; k++) { loc[k] = ms.cellStart[1 + lane * 8 + k]; s += loc[k]; }
-    const int incl = warp_incl_scan(s, lane);
-    int run = incl - s;
+    for (int k = 0; k < 8; k++) { loc[k] = ms.cellStart[1 + lane * 8 + k]; sum += loc[k]; }
+    const int incl = warp_incl_scan(sum, lane);
+    int run = incl - sum;
     __syncwarp();
 #pragma unroll
     for (int k = 0; k < 8; k++) { run += loc[k]; ms.cellStart[1 + lane * 8 + k] = (unsigned short)run; }
@@ -407,42 +421,62 @@ __device__ int merge_clustered(T* cur, const MergeScratch<T>& ms, int W, int n, 
   }
   __syncwarp();
   for (int j = lane; j < n; j += 32) {
-    const int c = cell_of(cur[j]);
+    const int c = ms.slot[j];
     const unsigned old = atomicAdd(cursor + (c >> 1), (c & 1) ? 0x10000u : 1u);
     const unsigned pos = (c & 1) ? (old >> 16) : (old & 0xffffu);
     ms.order[pos] = (unsigned short)j;
+    XY<T> q;
+    q.x = cur[j]; q.y = cur[W + j];
+    ms.sxy[pos] = q;
   }
   __syncwarp();
   // (the order inside a cell is schedule dependent; nothing below depends on it: M2 visits every
   //  pair of one cell or of adjacent cells exactly once, M4 takes minima over index)
-  // ---- M2: passing pairs ----------------------------------------------------------------------------
-  bool overflow = false;
+  // ---- M2: candidate pairs by distance, then the exact test lane-parallel over the candidates ------
   for (int sb = 0; sb < n; sb += 32) {
     const int s = sb + lane;
     if (s < n) {
+      const XY<T> me = ms.sxy[s];
       const int j = ms.order[s];
-      const T xj = cur[j], yj = cur[W + j];
-      const T rj = tt * (cur[2 * W + j] + cur[4 * W + j]);
-      const int end = ms.cellStart[cell_of(xj) + 2];
+      const int end = ms.cellStart[ms.slot[j] + 2];
       for (int t = s + 1; t < end; t++) {
-        const int k = ms.order[t];
-        const T dx = cur[k] - xj, dy = cur[W + k] - yj;
+        const XY<T> q = ms.sxy[t];
+        const T dx = q.x - me.x, dy = q.y - me.y;
         const T d2 = dx * dx + dy * dy;
         if (d2 > rmax2) continue;
+        const int k = ms.order[t];
+        const T rj = tt * (cur[2 * W + j] + cur[4 * W + j]);
         if (d2 > M<T>::max_(rj, tt * (cur[2 * W + k] + cur[4 * W + k]))) continue;
+        const unsigned slotq = atomicAdd(&ms.counters[0], 1u);
         const int a = j < k ? j : k, b = j < k ? k : j;
-        if (merge_test_pair(cur, W, a, b, t2)) {
-          const unsigned q = atomicAdd(&ms.counters[0], 1u);
-          if (q < (unsigned)MAX_PAIRS) ms.pairs[q] = ((unsigned)a << 16) | (unsigned)b;
-          else overflow = true;
-        }
+        if (slotq < (unsigned)MAX_PAIRS) ms.pairs[slotq] = ((unsigned)a << 16) | (unsigned)b;
       }
     }
     __syncwarp();
   }
-  if (__any_sync(FULL, overflow)) { mstat[1]++; return MERGE_FALLBACK; }
-  if (ms.counters[0] == 0u) return MERGE_OK;
-  mstat[5] += ms.counters[0];
+  {
+    const int ncand = (int)ms.counters[0];
+    if (ncand > MAX_PAIRS) { mstat[1]++; return MERGE_FALLBACK; }
+    int npass = 0;
+    for (int base = 0; base < ncand; base += 32) {
+      const int k = base + lane;
+      unsigned key = 0;
+      bool pass = false;
+      if (k < ncand) {
+        key = ms.pairs[k];
+        pass = merge_test_pair(cur, W, (int)(key >> 16), (int)(key & 0xffffu), t2);
+      }
+      __syncwarp();
+      const unsigned bp = __ballot_sync(FULL, pass);
+      if (pass) ms.pairs[npass + __popc(bp & ((1u << lane) - 1u))] = key;
+      npass += __popc(bp);
+    }
+    __syncwarp();
+    if (lane == 0) ms.counters[0] = (unsigned)npass;
+    __syncwarp();
+    if (npass == 0) return MERGE_OK;
+    mstat[5] += (unsigned)npass;
+  }
 
   for (int round = 0; round < MAX_MERGE_ROUNDS; round++) {
     const int np = (int)ms.counters[0];
@@ -735,7 +769,7 @@ __host__ __device__ inline int z_bytes() {
   return (int)((2 * MAX_Z * sizeof(T) + 2 * (NBINS + 1) * 8 + 4 * sizeof(T) + 2 * MAX_Z + 127) & ~127);
 }
 
-template <typename T>
+template <typename T, bool MF>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4)
 phd_update_kernel(const __grid_constant__ KParams<T> p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -743,8 +777,7 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
   const int warp = threadIdx.x >> 5;
   const int W = p.W;
   const int nZ = p.nZ;
-  const bool MF = !p.use_sc;
-  const int NPL = MF ? 7 : 6;
+  constexpr int NPL = MF ? 7 : 6;   // MF = multi-feature weighting (p.use_sc == 0)
 
   T* zs = reinterpret_cast<T*>(smem_raw);          // [2*MAX_Z]: zr[z] at 2z, zb[z] at 2z+1
   unsigned long long* tabR = reinterpret_cast<unsigned long long*>(zs + 2 * MAX_Z);   // [NBINS+1]
@@ -877,6 +910,9 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
     unsigned short* candIdx = ms.order;   // [W] (free until the merge)
     T* candW = ms.keys;                    // [W] pre-update weight of the queued components
     int ncand = 0;
+    // statistics the merge needs over all n components (gathered here while the data is in registers)
+    T g_xmin = M<T>::inf(), g_xmax = -M<T>::inf(), g_trmax = T(0);
+    bool g_bad = false;
     const T pc_xy = c00 + c11, pc_all = c00 + c11 + c22;
     const bool pc_ok = (c00 >= T(0)) && (c11 >= T(0)) && (c22 >= T(0));
     for (int base = 0; base < nM; base += 32) {
@@ -885,6 +921,12 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
       T w = 0;
       if (m < nM) {
         const T x = cur[m], y = cur[W + m];
+        const T pxx = cur[2 * W + m], pxy = cur[3 * W + m], pyy = cur[4 * W + m];
+        const bool pd = (pxx > T(0)) && (pyy > T(0)) && (pxx * pyy - pxy * pxy > T(0));
+        g_bad |= !pd;
+        g_xmin = x < g_xmin ? x : g_xmin;
+        g_xmax = x > g_xmax ? x : g_xmax;
+        g_trmax = M<T>::max_(g_trmax, pxx + pyy);
         w = cur[5 * W + m];
         wsum_d += (double)w;
         const T dx = x - px, dy = y - py;
@@ -910,8 +952,6 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
         cur[5 * W + m] = fix ? w : (T(1) - Pd) * w;
         aux[m] = fix ? 1u : 0u;
         if (Pd != T(0) && inrange) {              // measure() returns false outside [rmin,rmax]
-          const T pxx = cur[2 * W + m], pxy = cur[3 * W + m], pyy = cur[4 * W + m];
-          const bool pd = (pxx > T(0)) && (pyy > T(0)) && (pxx * pyy - pxy * pxy > T(0));
           queue = true;
           if (pd && pc_ok) {
             const T zb_hat = wrap_pi<T>(M<T>::atan2_(dy, dx) - pth);
@@ -1025,6 +1065,8 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
         const T n01b = pxy - (k10 * hp00 + k11 * hp10);
         const T n11 = pyy - (k10 * hp01 + k11 * hp11);
         const T n01 = (n01a + n01b) * T(0.5);
+        g_bad |= !((n00 > T(0)) && (n11 > T(0)) && (n00 * n11 - n01 * n01 > T(0)));
+        g_trmax = M<T>::max_(g_trmax, n00 + n11);
         while (mask) {
           const int z = __ffsll((long long)mask) - 1;
           mask &= mask - 1;
@@ -1034,7 +1076,10 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
           const T nb = wrap_pi<T>(nb_raw);
           const T md2 = (nr * i00 + nb_raw * i01) * nr + (nr * i01 + nb_raw * i11) * nb_raw;
           const T lik = M<T>::exp_(T(-0.5) * md2) * norm;
-          cur[off] = x + (k00 * nr + k01 * nb);
+          const T xn = x + (k00 * nr + k01 * nb);
+          g_xmin = xn < g_xmin ? xn : g_xmin;
+          g_xmax = xn > g_xmax ? xn : g_xmax;
+          cur[off] = xn;
           cur[W + off] = y + (k10 * nr + k11 * nb);
           cur[2 * W + off] = n00; cur[3 * W + off] = n01; cur[4 * W + off] = n11;
           cur[5 * W + off] = Pdw * lik;   // un-normalised; divided by the column sum in S3
@@ -1050,6 +1095,10 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
     const int n = nM + nS;
     nfov = warp_sum(nfov);
     wsum_d = warp_sum(wsum_d);
+    g_xmin = warp_min(g_xmin);
+    g_xmax = warp_max(g_xmax);
+    g_trmax = warp_max(g_trmax);
+    g_bad = __any_sync(FULL, g_bad);
     __syncwarp();
 
     double weight_new = w_prev_particle;
@@ -1110,7 +1159,7 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
     }
 
     // ---------------- S5: multi-feature importance weighting ----------------------------------
-    if (!p.use_sc) {
+    if constexpr (MF) {
       int nEvalCfg = p.n_eval < n ? p.n_eval : n;
       if (nEvalCfg == 0) {
         weight_new = 4.9406564584124654e-324;  // denorm_min (:742-745, Q10)
@@ -1359,7 +1408,7 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
     // ---------------- S6: merge ------------------------------------------------------------------
     if (n > 1) {
       int st = MERGE_FALLBACK;
-      if (p.merge_algo != 0) st = merge_clustered<T>(cur, ms, W, n, p.merge_t2, p.merge_f, MF, lane, mstat);
+      if (p.merge_algo != 0) st = merge_clustered<T>(cur, ms, W, n, p.merge_t2, p.merge_f, MF, lane, mstat, g_xmin, g_xmax, g_trmax, g_bad);
       __syncwarp();
       if (st == MERGE_FALLBACK && p.merge_algo != 0) n_fallback++;
       if (st == MERGE_FALLBACK) merge_bruteforce<T>(cur, W, n, p.merge_t2, p.merge_f, lane);
@@ -1370,40 +1419,47 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
     int n_out = 0;
     {
       T* kw = ms.keys;   // [W] sort keys (the merge-only scratch is dead)
-      for (int base = 0; base < n; base += 32) {
-        const int k = base + lane;
-        bool keep = false;
-        T w = 0;
-        if (k < n) { w = cur[5 * W + k]; keep = (w >= p.prune_t) && (w >= T(0)); }
-        const unsigned b = __ballot_sync(FULL, keep);
-        if (keep) {
-          const int pos = n_out + __popc(b & ((1u << lane) - 1u));
-          kw[pos] = w;
-          aux[pos] = (unsigned)k;
-        }
-        n_out += __popc(b);
-      }
       unsigned short* sorted = ms.order;   // [W] component index by output position
-      __syncwarp();
-      if (n_out <= 64) {
-        // rank sort: position = number of kept components that come before (weight desc, index asc)
-        const int e0 = lane, e1 = lane + 32;
-        const T w0 = e0 < n_out ? kw[e0] : T(0), w1 = e1 < n_out ? kw[e1] : T(0);
-        const unsigned i0 = e0 < n_out ? aux[e0] : 0u, i1 = e1 < n_out ? aux[e1] : 0u;
-        int r0 = 0, r1 = 0;
-        for (int q = 0; q < n_out; q++) {
-          const T wq = kw[q];
-          const unsigned iq = aux[q];
-          r0 += before(wq, iq, w0, i0) ? 1 : 0;
-          r1 += before(wq, iq, w1, i1) ? 1 : 0;
+      if constexpr (sizeof(T) == 4) {
+        // fp32: weights are positive, so (weight bits, ~index) packs into one u64 whose descending
+        // order is "weight descending, then index ascending"
+        unsigned long long* k64 = reinterpret_cast<unsigned long long*>(ms.keys);   // [W] fits: see merge_only_bytes
+        for (int base = 0; base < n; base += 32) {
+          const int k = base + lane;
+          bool keep = false;
+          T w = 0;
+          if (k < n) { w = cur[5 * W + k]; keep = (w >= p.prune_t) && (w >= T(0)); }
+          const unsigned b = __ballot_sync(FULL, keep);
+          if (keep) {
+            const int pos = n_out + __popc(b & ((1u << lane) - 1u));
+            k64[pos] = ((unsigned long long)__float_as_uint((float)w) << 32) | (unsigned long long)(0xffffffffu - (unsigned)k);
+          }
+          n_out += __popc(b);
         }
-        if (e0 < n_out) sorted[r0] = (unsigned short)i0;
-        if (e1 < n_out) sorted[r1] = (unsigned short)i1;
+        __syncwarp();
+        const int P = next_pow2(n_out);
+        for (int k = n_out + lane; k < P; k += 32) k64[k] = 0ull;   // below every real key
+        __syncwarp();
+        if (n_out > 1) warp_bitonic_desc64(k64, P, lane);
+        for (int k = lane; k < n_out; k += 32) sorted[k] = (unsigned short)(0xffffffffu - (unsigned)(k64[k] & 0xffffffffull));
       } else {
+        for (int base = 0; base < n; base += 32) {
+          const int k = base + lane;
+          bool keep = false;
+          T w = 0;
+          if (k < n) { w = cur[5 * W + k]; keep = (w >= p.prune_t) && (w >= T(0)); }
+          const unsigned b = __ballot_sync(FULL, keep);
+          if (keep) {
+            const int pos = n_out + __popc(b & ((1u << lane) - 1u));
+            kw[pos] = w;
+            aux[pos] = (unsigned)k;
+          }
+          n_out += __popc(b);
+        }
         const int P = next_pow2(n_out);
         for (int k = n_out + lane; k < P; k += 32) { kw[k] = -M<T>::inf(); aux[k] = 0xffffffffu; }
         __syncwarp();
-        warp_bitonic(kw, aux, P, lane);
+        if (n_out > 1) warp_bitonic(kw, aux, P, lane);
         for (int k = lane; k < n_out; k += 32) sorted[k] = (unsigned short)aux[k];
       }
       __syncwarp();

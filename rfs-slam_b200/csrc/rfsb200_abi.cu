@@ -199,21 +199,26 @@ int round_pow2(int v) {
   return p;
 }
 
-template <typename T>
-int configure_launch(rfsb200_ctx* c, int mf) {
+template <typename T, bool MF>
+int configure_launch_t(rfsb200_ctx* c) {
+  const int mf = MF ? 1 : 0;
   if (c->cfg_mode_mf == mf) return RFSB200_OK;
   c->mf_bytes = mf ? mf_scratch_bytes<T>(MAX_EVAL, c->dims.z_capacity) : 0;
   c->warp_bytes = warp_bytes_for<T>(c->W, mf, c->mf_bytes);
   c->smem_bytes = (size_t)z_bytes<T>() + (size_t)WARPS_PER_CTA * c->warp_bytes;
   if (c->smem_bytes > 227 * 1024) return fail(c, RFSB200_ECAPACITY, "work_capacity %d needs %zu B shared memory per CTA (> 227 KB)", c->W, c->smem_bytes);
-  CU(c, cudaFuncSetAttribute(phd_update_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
+  CU(c, cudaFuncSetAttribute(phd_update_kernel<T, MF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
   int occ = 0;
-  CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, phd_update_kernel<T>, WARPS_PER_CTA * 32, c->smem_bytes));
+  CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, phd_update_kernel<T, MF>, WARPS_PER_CTA * 32, c->smem_bytes));
   if (occ < 1) return fail(c, RFSB200_ECAPACITY, "kernel does not fit on an SM");
   const int need = (c->N + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
   c->grid = std::max(1, std::min(need, occ * c->sm_count));
   c->cfg_mode_mf = mf;
   return RFSB200_OK;
+}
+template <typename T>
+int configure_launch(rfsb200_ctx* c, int mf) {
+  return mf ? configure_launch_t<T, true>(c) : configure_launch_t<T, false>(c);
 }
 
 template <typename T>
@@ -237,7 +242,6 @@ int launch_update(rfsb200_ctx* c, int nZ, int out_idx) {
   p.log_clutter_integral = log(m.clutter_integral);
   p.log_kappa = log(m.clutter_intensity);
   p.N = c->N; p.cap = c->cap; p.W = c->W; p.nZ = nZ; p.pose_cov_mode = c->pose_cov_mode;
-  p.warp_bytes = c->warp_bytes;
   const StateBuf& in = c->st[c->front];
   const StateBuf& out = c->st[out_idx];
   p.gm_in = (const T*)in.gm; p.cnt_in = in.cnt; p.w_in = in.weight;
@@ -247,15 +251,17 @@ int launch_update(rfsb200_ctx* c, int nZ, int out_idx) {
   p.unused = c->unused; p.nfov = c->nfov; p.flags = c->flags;
   p.sums = c->sums; p.totals = c->totals; p.istats = c->istats; p.ticket = c->ticket; p.mstats = c->mstats;
   p.work_counter = c->work_counter; p.stats_out = c->stats_out;
+  const int mf = f.use_cluster_process ? 0 : 1;
   {
-    int rc = configure_launch<T>(c, f.use_cluster_process ? 0 : 1);
+    int rc = configure_launch<T>(c, mf);
     if (rc) return rc;
     p.warp_bytes = c->warp_bytes;
     p.mf_bytes = c->mf_bytes;
   }
   const bool prof = c->prof_n < c->prof_cap;
   if (prof) CU(c, cudaEventRecord(c->prof_ev[2 * c->prof_n], c->stream));
-  phd_update_kernel<T><<<c->grid, WARPS_PER_CTA * 32, c->smem_bytes, c->stream>>>(p);
+  if (mf) phd_update_kernel<T, true><<<c->grid, WARPS_PER_CTA * 32, c->smem_bytes, c->stream>>>(p);
+  else phd_update_kernel<T, false><<<c->grid, WARPS_PER_CTA * 32, c->smem_bytes, c->stream>>>(p);
   CU(c, cudaGetLastError());
   if (prof) {
     CU(c, cudaEventRecord(c->prof_ev[2 * c->prof_n + 1], c->stream));
