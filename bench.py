@@ -42,6 +42,15 @@ WORKLOADS = {
 }
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
+
 def _peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -154,7 +163,7 @@ def run_reference_arm(a):
                 cpu_baseline=dict(value=v, unit=UNIT, cores=threads, kind=kind, sample=sample),
                 e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 gpu_launches=0)
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -172,6 +181,12 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 0)
+    # stdout carries exactly ONE JSON line: everything libraries print (NCCL's version banner, ...)
+    # goes to stderr, the line itself is written to the saved descriptor at the end
+    sys.stdout.flush()
+    global _REAL_STDOUT
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if a.impl == "reference":
         return run_reference_arm(a)
     if a.warmup < 3:
@@ -332,7 +347,7 @@ def main():
                                 parallelism=f"particles block-partitioned over {world} GPU(s); one all-reduce of [sum w, sum w^2] per step"),
                     e2e=e2e, gpu_launches=2 * K, roofline=roofline, cpu_baseline=cpu, clocks=clk,
                     wall_s_timed_region_incl_flush=t_wall)
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -1,0 +1,502 @@
+/*
+ * RBPHDFilter.hpp (B200 drop-in) — rfs::RBPHDFilter<RobotProcessModel, LmkProcessModel,
+ * MeasurementModel, KalmanFilter> with the reference's public surface
+ * (reference include/RBPHDFilter.hpp:72-251), whose update() runs on the GPU through the C ABI of
+ * include/rfsb200.h instead of the OpenMP region of the reference (:469-520).
+ *
+ * How to use: put this directory BEFORE the reference's include/ on the include path
+ * (-I<repo>/include/rfs_b200 -I<reference>/include) and link librfsb200.so.  Every other header
+ * (ParticleFilter.hpp, GaussianMixture.hpp, the plugin classes ...) is the reference's own,
+ * unmodified; drivers such as src/rbphdslam2dSim.cpp compile unchanged.
+ *
+ * What lives where
+ *   host (unchanged reference code): particle poses / weights / trajectories (ParticleFilter),
+ *     particle propagation (ProcessModel::sample), the resampling decision (one drand48()).
+ *   device (librfsb200.so): every particle's Gaussian mixture, resident in HBM between calls;
+ *     predict()'s map part (birth Gaussians + landmark process noise), update() (map update,
+ *     particle weighting, merge, prune, weight sums), the data movement of resampling.
+ *   The host-side GaussianMixture objects of the particles stay EMPTY; getGMSize / getLandmark
+ *     read the device state (one particle's planes per call, cached until the next mutation).
+ *
+ * Plugin objects cannot be called from the device, so before every update the live plugin
+ * objects are read into a POD (rfs::b200::ModelTraits<MeasurementModel, KalmanFilter>::describe).
+ * A traits specialisation exists for MeasurementModel_RngBrg + KalmanFilter_RngBrg; other plugin
+ * types do not compile against this header (static_assert) — they keep using the reference header.
+ */
+#ifndef RBPHDFILTER_HPP
+#define RBPHDFILTER_HPP
+
+#include <Eigen/Core>
+#include <math.h>
+#include <stdio.h>
+#include <cmath>
+#include <cstdlib>
+#include <ctime>
+#include <fstream>
+#include <iomanip>
+#include <iostream>
+#include <limits>
+#include <list>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "GaussianMixture.hpp"
+#include "KalmanFilter.hpp"
+#include "ParticleFilter.hpp"
+#include "Timer.hpp"
+
+#include "../rfsb200.h"
+
+namespace rfs {
+
+namespace b200 {
+
+/** Reads the live plugin objects into the device descriptor.  Specialise per plugin pair. */
+template <class MeasurementModel, class KalmanFilter>
+struct ModelTraits {
+  static const bool supported = false;
+};
+
+}  // namespace b200
+}  // namespace rfs
+
+/* The RngBrg specialisation is only compiled when the plugin headers are in the translation unit
+ * (the reference's drivers include KalmanFilter_RngBrg.hpp themselves, after this header, so the
+ * specialisation is declared against forward declarations and defined where both are complete). */
+namespace rfs {
+class MeasurementModel_RngBrg;
+class KalmanFilter_RngBrg;
+
+namespace b200 {
+template <>
+struct ModelTraits<MeasurementModel_RngBrg, KalmanFilter_RngBrg> {
+  static const bool supported = true;
+  static const int lmk_dim = 2, meas_dim = 2, pose_dim = 3;
+  /* defined as a template so that the plugin classes only need to be complete at the call site */
+  template <class MM, class KF>
+  static void describe(MM& mm, KF& kf, unsigned nZ, rfsb200_model_desc& d) {
+    d = rfsb200_model_desc();
+    d.model_id = RFSB200_MODEL_RNGBRG;
+    typename MM::TMeasurement::Mat R;
+    mm.getNoise(R);
+    for (int i = 0; i < 2; i++)
+      for (int j = 0; j < 2; j++) d.R[i * 2 + j] = R(i, j);
+    d.Pd = mm.config.probabilityOfDetection_;
+    typename MM::TMeasurement z;   /* uniform clutter: the value does not depend on z */
+    d.clutter_intensity = mm.clutterIntensity(z, (int)nZ);
+    d.clutter_integral = mm.clutterIntensityIntegral((int)nZ);
+    d.range_min = mm.config.rangeLimMin_;
+    d.range_max = mm.config.rangeLimMax_;
+    d.range_buffer = mm.config.rangeLimBuffer_;
+    d.innov_thr_range = kf.config.rangeInnovationThreshold_;
+    d.innov_thr_bearing = kf.config.bearingInnovationThreshold_;
+  }
+};
+}  // namespace b200
+
+template <class RobotProcessModel, class LmkProcessModel, class MeasurementModel, class KalmanFilter>
+class RBPHDFilter : public ParticleFilter<RobotProcessModel, MeasurementModel,
+                                          GaussianMixture<typename MeasurementModel::TLandmark> > {
+ public:
+  EIGEN_MAKE_ALIGNED_OPERATOR_NEW;
+
+  typedef typename RobotProcessModel::TState TPose;
+  typedef typename RobotProcessModel::TInput TInput;
+  typedef typename MeasurementModel::TLandmark TLandmark;
+  typedef typename MeasurementModel::TMeasurement TMeasurement;
+  typedef GaussianMixture<TLandmark> TGM;
+  typedef typename TGM::Gaussian TGaussian;
+  typedef b200::ModelTraits<MeasurementModel, KalmanFilter> Traits;
+
+  /** Same fields, same names as the reference (include/RBPHDFilter.hpp:90-146). */
+  struct Config {
+    double birthGaussianWeight_;
+    uint birthGaussianMeasurementCountThreshold_;
+    uint birthGaussianMeasurementCheckThreshold_;
+    double birthGaussianMeasurementSupportDist_;
+    uint birthGaussianCurrentMeasurementCountThreshold_;
+    double newGaussianCreateInnovMDThreshold_;
+    int importanceWeightingEvalPointCount_;
+    double importanceWeightingEvalPointGuassianWeight_;
+    double importanceWeightingMeasurementLikelihoodMDThreshold_;
+    double gaussianMergingThreshold_;
+    double gaussianMergingCovarianceInflationFactor_;
+    double gaussianPruningThreshold_;
+    int minUpdatesBeforeResample_;
+    int minMeasurementsBeforeResample_;
+    bool useClusterProcess_;
+  } config;
+
+  /** include/RBPHDFilter.hpp:152-167; the *_wall fields are filled from CUDA events (ns). */
+  struct TimingInfo {
+    long long predict_wall, predict_cpu;
+    long long mapUpdate_wall, mapUpdate_cpu;
+    long long mapUpdate_kf_wall, mapUpdate_kf_cpu;
+    long long particleWeighting_wall, particleWeighting_cpu;
+    long long mapMerge_wall, mapMerge_cpu;
+    long long mapPrune_wall, mapPrune_cpu;
+    long long particleResample_wall, particleResample_cpu;
+  } timingInfo_;
+
+  class BirthGaussianCandidate : public TLandmark {
+   public:
+    uint nSupportingMeasurements;
+    uint nChecks;
+  };
+
+  /** Device-side capacities; change before the first predict()/update() if the defaults do not fit. */
+  struct DeviceConfig {
+    int gmCapacity;     /**< Gaussians per particle kept between steps */
+    int workCapacity;   /**< Gaussians per particle inside one update (inputs + created) */
+    int zCapacity;      /**< measurements per update (<= 64) */
+    int device;         /**< CUDA device ordinal */
+    int precision;      /**< 32 (product) or 64 (verification build) */
+  } deviceConfig;
+
+  RBPHDFilter(int n);
+  ~RBPHDFilter();
+
+  LmkProcessModel* getLmkProcessModel() { return lmkModelPtr_; }
+  void predict(TInput u, TimeStamp const& dT, bool useModelNoise = true, bool useInputNoise = false,
+               bool birthGaussianCheck = true);
+  void update(std::vector<TMeasurement>& Z);
+  int getGMSize(int i);
+  bool getLandmark(const int i, const int m, typename TLandmark::Vec& u, typename TLandmark::Mat& S, double& w);
+  KalmanFilter* getKalmanFilter() { return &kf_; }
+  void setParticlePose(int i, TPose& p) { *(this->particleSet_[i]) = p; }
+  TimingInfo* getTimingInfo();
+
+  /** Hides ParticleFilter::resample (same decisions, same single drand48()); the particle copies on
+   *  the host carry poses / trajectories / ids, the maps are moved on the device. */
+  bool resample(unsigned int n = 0, bool forceResample = false);
+
+  /** Diagnostics of the last update (n_overflow, n_murty, device time ...). */
+  const rfsb200_step_out& lastStep() const { return lastStep_; }
+  const char* lastError() const { return ctx_ ? rfsb200_last_error(ctx_) : rfsb200_last_error(NULL); }
+
+ private:
+  static_assert(Traits::supported,
+                "rfs::b200 has no device descriptor for this MeasurementModel/KalmanFilter pair: "
+                "use the reference RBPHDFilter.hpp for it");
+
+  rfsb200_ctx* ctx_;
+  int nAlloc_;                 /* particle count the ctx was created for */
+  KalmanFilter kf_;            /* the reference keeps one per thread; getKalmanFilter() returns [0] */
+  LmkProcessModel* lmkModelPtr_;
+  unsigned int nUpdatesSinceResample_;
+  unsigned int nMeasurementsSinceResample_;
+  bool resampleOccured_;
+  std::vector<int> pendingAuxSrc_;   /* Q: parent-id lookup of addBirthGaussians after a resample */
+  rfsb200_step_out lastStep_;
+  Timer timer_predict_, timer_particleResample_;
+  long long ns_update_;
+  /* one-particle cache for getLandmark */
+  int cacheIdx_;
+  std::vector<double> cMean_, cCov_, cW_;
+  int cN_;
+  std::vector<double> hPose_, hPoseCov_, hW_;
+
+  void ensureCtx();
+  void check(int rc, const char* what) {
+    if (rc != RFSB200_OK) {
+      std::string msg = std::string("rfs::RBPHDFilter (B200): ") + what + ": " + lastError();
+      throw std::runtime_error(msg);
+    }
+  }
+  void uploadPoses();
+  void invalidateCache() { cacheIdx_ = -1; }
+  /* ParticleFilter declares this pure virtual; the weighting of every particle happens inside
+   * rfsb200_update (reference :728-819), so the per-particle host hook has nothing to do */
+  void importanceWeighting(const uint) {}
+};
+
+////////// Implementation //////////
+
+template <class R, class L, class M, class K>
+RBPHDFilter<R, L, M, K>::RBPHDFilter(int n)
+    : ParticleFilter<R, M, GaussianMixture<typename M::TLandmark> >(n),
+      ctx_(NULL), nAlloc_(0), kf_(), lmkModelPtr_(new L), nUpdatesSinceResample_(0), nMeasurementsSinceResample_(0),
+      resampleOccured_(false), ns_update_(0), cacheIdx_(-1), cN_(0) {
+  kf_ = K(lmkModelPtr_, this->getMeasurementModel());
+  for (int i = 0; i < n; i++) this->particleSet_[i]->setData(boost::shared_ptr<TGM>(new TGM()));
+  /* reference defaults (include/RBPHDFilter.hpp:370-382); the two it leaves uninitialised get
+   * defined values */
+  config.birthGaussianWeight_ = 0.25;
+  config.birthGaussianMeasurementCountThreshold_ = 1;
+  config.birthGaussianMeasurementCheckThreshold_ = 1;
+  config.birthGaussianMeasurementSupportDist_ = 1;
+  config.birthGaussianCurrentMeasurementCountThreshold_ = 1;
+  config.gaussianMergingThreshold_ = 0.5;
+  config.gaussianMergingCovarianceInflationFactor_ = 1.5;
+  config.gaussianPruningThreshold_ = 0.2;
+  config.importanceWeightingEvalPointCount_ = 8;
+  config.importanceWeightingEvalPointGuassianWeight_ = 0.75;
+  config.importanceWeightingMeasurementLikelihoodMDThreshold_ = 3.0;
+  config.newGaussianCreateInnovMDThreshold_ = 0.2;
+  config.minUpdatesBeforeResample_ = 1;
+  config.minMeasurementsBeforeResample_ = 1;
+  config.useClusterProcess_ = false;
+  deviceConfig.gmCapacity = 256;
+  deviceConfig.workCapacity = 384;
+  deviceConfig.zCapacity = 64;
+  deviceConfig.device = 0;
+  deviceConfig.precision = 32;
+  lastStep_ = rfsb200_step_out();
+  timingInfo_ = TimingInfo();
+}
+
+template <class R, class L, class M, class K>
+RBPHDFilter<R, L, M, K>::~RBPHDFilter() {
+  for (int i = 0; i < this->nParticles_; i++) this->particleSet_[i]->deleteData();
+  delete lmkModelPtr_;
+  if (ctx_) rfsb200_destroy(ctx_);
+}
+
+template <class R, class L, class M, class K>
+void RBPHDFilter<R, L, M, K>::ensureCtx() {
+  if (ctx_ && nAlloc_ == this->nParticles_) return;
+  if (ctx_) throw std::runtime_error("rfs::RBPHDFilter (B200): the particle count changed after the device state was created");
+  rfsb200_dims d = rfsb200_dims();
+  d.n_particles = this->nParticles_;
+  d.gm_capacity = deviceConfig.gmCapacity;
+  d.work_capacity = deviceConfig.workCapacity;
+  d.z_capacity = deviceConfig.zCapacity;
+  d.lmk_dim = Traits::lmk_dim;
+  d.meas_dim = Traits::meas_dim;
+  d.pose_dim = Traits::pose_dim;
+  d.device = deviceConfig.device;
+  d.precision = deviceConfig.precision;
+  int rc = rfsb200_create(&ctx_, &d);
+  if (rc != RFSB200_OK) {
+    ctx_ = NULL;
+    check(rc, "rfsb200_create");
+  }
+  nAlloc_ = this->nParticles_;
+  /* empty maps */
+  std::vector<int32_t> cnt(nAlloc_, 0);
+  check(rfsb200_upload_maps(ctx_, cnt.data(), NULL, NULL, NULL), "rfsb200_upload_maps");
+  check(rfsb200_synchronize(ctx_), "rfsb200_synchronize");
+}
+
+template <class R, class L, class M, class K>
+void RBPHDFilter<R, L, M, K>::uploadPoses() {
+  const int N = this->nParticles_;
+  hPose_.resize((size_t)N * 3);
+  hPoseCov_.resize((size_t)N * 6);
+  hW_.resize(N);
+  bool anyCov = false;
+  for (int i = 0; i < N; i++) {
+    typename TPose::Vec x;
+    typename TPose::Mat S;
+    this->particleSet_[i]->get(x, S);
+    for (int k = 0; k < 3; k++) hPose_[3 * i + k] = x(k);
+    double* c = &hPoseCov_[6 * i];
+    c[0] = S(0, 0); c[1] = S(0, 1); c[2] = S(0, 2); c[3] = S(1, 1); c[4] = S(1, 2); c[5] = S(2, 2);
+    for (int k = 0; k < 6; k++) anyCov = anyCov || (c[k] != 0.0);
+    hW_[i] = this->particleSet_[i]->getWeight();
+  }
+  check(rfsb200_set_poses(ctx_, hPose_.data(), anyCov ? hPoseCov_.data() : NULL, anyCov ? 2 : 0, hW_.data()),
+        "rfsb200_set_poses");
+}
+
+template <class R, class L, class M, class K>
+void RBPHDFilter<R, L, M, K>::predict(TInput u, TimeStamp const& dT, bool useModelNoise, bool useInputNoise,
+                                      bool birthGaussianCheck) {
+  timer_predict_.resume();
+  ensureCtx();
+  invalidateCache();
+  if (birthGaussianCheck && config.birthGaussianMeasurementCountThreshold_ != 1)
+    throw std::runtime_error("rfs::RBPHDFilter (B200): birthGaussianMeasurementCountThreshold_ != 1 (candidate-list births) is not implemented on the device");
+  /* landmark process noise: StaticProcessModel::step adds Q only if it was set (ProcessModel.hpp:198) */
+  typename TLandmark::Mat Q;
+  const double nan = std::numeric_limits<double>::quiet_NaN();
+  for (int i = 0; i < Q.rows(); i++)
+    for (int j = 0; j < Q.cols(); j++) Q(i, j) = nan;
+  lmkModelPtr_->getNoise(Q);
+  const bool haveQ = (Q(0, 0) == Q(0, 0));
+  double q[3] = {0, 0, 0};
+  if (haveQ) { q[0] = Q(0, 0); q[1] = Q(0, 1); q[2] = Q(1, 1); }
+  /* births use the pose BEFORE the propagation = the pose of the last update, still on the device
+   * (addBirthGaussians runs first in the reference too, :425-427) */
+  check(rfsb200_predict_maps(ctx_, haveQ ? q : NULL, birthGaussianCheck ? 1 : 0, config.birthGaussianWeight_),
+        "rfsb200_predict_maps");
+  this->propagate(u, dT, useModelNoise, useInputNoise, true);
+  timer_predict_.stop();
+}
+
+template <class R, class L, class M, class K>
+void RBPHDFilter<R, L, M, K>::update(std::vector<TMeasurement>& Z) {
+  nUpdatesSinceResample_++;
+  this->setMeasurements(Z);   /* Z is cleared, as in the reference */
+  const unsigned nZ = this->measurements_.size();
+  if (nZ == 0) return;        /* include/RBPHDFilter.hpp:451-452 */
+  nMeasurementsSinceResample_ += nZ;
+  ensureCtx();
+  invalidateCache();
+
+  rfsb200_model_desc md;
+  Traits::describe(*this->pMeasurementModel_, kf_, nZ, md);
+  check(rfsb200_set_model(ctx_, &md), "rfsb200_set_model");
+  rfsb200_filter_cfg fc = rfsb200_filter_cfg();
+  fc.birth_gaussian_weight = config.birthGaussianWeight_;
+  fc.new_gaussian_create_innov_md_threshold = config.newGaussianCreateInnovMDThreshold_;
+  fc.eval_point_gaussian_weight = config.importanceWeightingEvalPointGuassianWeight_;
+  fc.meas_likelihood_md_threshold = config.importanceWeightingMeasurementLikelihoodMDThreshold_;
+  fc.merging_threshold = config.gaussianMergingThreshold_;
+  fc.merging_cov_inflation_factor = config.gaussianMergingCovarianceInflationFactor_;
+  fc.pruning_threshold = config.gaussianPruningThreshold_;
+  fc.eval_point_count = config.importanceWeightingEvalPointCount_ < 0 ? 32 : config.importanceWeightingEvalPointCount_;  /* Q14 */
+  fc.use_cluster_process = config.useClusterProcess_ ? 1 : 0;
+  check(rfsb200_set_filter_cfg(ctx_, &fc), "rfsb200_set_filter_cfg");
+
+  uploadPoses();
+  std::vector<double> z((size_t)nZ * 2);
+  for (unsigned k = 0; k < nZ; k++) {
+    typename TMeasurement::Vec v;
+    this->measurements_[k].get(v);
+    z[2 * k] = v(0);
+    z[2 * k + 1] = v(1);
+  }
+  /* all particles: map update, weighting, merge, prune, weight sums — no normalisation yet, the
+   * resampling gate needs the unnormalised weights exactly like the reference */
+  check(rfsb200_update(ctx_, z.data(), (int32_t)nZ, RFSB200_UPDATE_NO_NORMALIZE, &lastStep_), "rfsb200_update");
+  ns_update_ += (long long)(lastStep_.elapsed_us * 1000.0);
+  check(rfsb200_get_weights(ctx_, 0, hW_.data()), "rfsb200_get_weights");
+  for (int i = 0; i < this->nParticles_; i++) this->particleSet_[i]->setWeight(hW_[i]);
+
+  timer_particleResample_.resume();
+  resampleOccured_ = false;
+  if (nUpdatesSinceResample_ >= (unsigned)config.minUpdatesBeforeResample_ &&
+      nMeasurementsSinceResample_ >= (unsigned)config.minMeasurementsBeforeResample_) {
+    resampleOccured_ = resample();
+  }
+  if (resampleOccured_) {
+    nUpdatesSinceResample_ = 0;
+    nMeasurementsSinceResample_ = 0;
+  } else {
+    this->normalizeWeights();   /* host copy; the device copy is refreshed by the next uploadPoses() */
+  }
+  timer_particleResample_.stop();
+}
+
+template <class R, class L, class M, class K>
+bool RBPHDFilter<R, L, M, K>::resample(unsigned int n, bool forceResample) {
+  /* Restates ParticleFilter::resample (include/ParticleFilter.hpp:399-492) so that the slot each new
+   * particle was copied from is known; arithmetic and the single drand48() are the same. */
+  const int N = this->nParticles_;
+  this->normalizeWeights();
+  if (!forceResample) {
+    double s2 = 0;
+    for (int i = 0; i < N; i++) {
+      const double w = this->particleSet_[i]->getWeight();
+      s2 += w * w;
+    }
+    const double nEff = 1.0 / s2;
+    if (nEff > this->effNParticles_t_ && nEff / N > this->effNParticles_t_percent_) return false;
+  }
+  if (n == 0 || n > (unsigned)N) n = N;
+  if ((int)n != N) throw std::runtime_error("rfs::RBPHDFilter (B200): resampling to a smaller particle set is not supported");
+  ensureCtx();
+  invalidateCache();
+  const double r01 = drand48();
+  const double interval = 1.0 / double(n);
+  double samplePoint = interval * r01;
+  unsigned idx = 0;
+  double cumulative = this->particleSet_[idx]->getWeight();
+  std::vector<char> sampled(N, 0);
+  std::vector<unsigned> sampledIdx(n, 0);
+  for (unsigned i = 0; i < n; i++) {
+    while (samplePoint > cumulative) {
+      idx++;
+      cumulative += this->particleSet_[idx]->getWeight();
+    }
+    sampledIdx[i] = idx;
+    sampled[idx] = 1;
+    samplePoint += interval;
+  }
+  std::vector<int> mapSrc(N);
+  for (int i = 0; i < N; i++) mapSrc[i] = i;
+  unsigned idxPrev = 0, nextFree = 0;
+  for (unsigned i = 0; i < n; i++) {
+    idx = sampledIdx[i];
+    const bool first = !(i > 0 && idx == idxPrev);
+    idxPrev = idx;
+    if (idx < n && first) {
+      this->particleSet_[idx]->setParentId(this->particleSet_[idx]->getId());
+    } else {
+      while (nextFree < (unsigned)N && sampled[nextFree] == 1) nextFree++;
+      this->particleSet_[nextFree] = this->particleSet_[idx]->copy();   /* host part: pose, trajectory, ids (empty GM) */
+      this->particleSet_[nextFree]->setParentId(this->particleSet_[idx]->getId());
+      mapSrc[nextFree] = (int)idx;
+      nextFree++;
+    }
+  }
+  /* addBirthGaussians looks the unused measurements up through getParentId() (:1005-1011) */
+  /* ... in place and in ascending particle order, so a parent slot below i has already been
+   * re-pointed when i reads it; the ids it uses are those the particle copies carry (they are not
+   * slot numbers any more after the first resampling — reproduced as is) */
+  std::vector<int> auxSrc(N);
+  for (int i = 0; i < N; i++) {
+    const unsigned parent = this->particleSet_[i]->getParentId();
+    if (parent != (unsigned)i && parent < (unsigned)N) auxSrc[i] = (parent < (unsigned)i) ? auxSrc[parent] : (int)parent;
+    else auxSrc[i] = i;
+  }
+  for (int i = 0; i < N; i++) this->particleSet_[i]->setWeight(1);
+  const double one = 1.0;
+  check(rfsb200_resample(ctx_, mapSrc.data(), auxSrc.data(), &one), "rfsb200_resample");
+  return true;
+}
+
+template <class R, class L, class M, class K>
+int RBPHDFilter<R, L, M, K>::getGMSize(int i) {
+  if (i < 0 || i >= this->nParticles_) return -1;
+  ensureCtx();
+  if (cacheIdx_ != i) {
+    typename TLandmark::Vec u;
+    typename TLandmark::Mat S;
+    double w;
+    getLandmark(i, 0, u, S, w);   /* fills the cache */
+  }
+  return cN_;
+}
+
+template <class R, class L, class M, class K>
+bool RBPHDFilter<R, L, M, K>::getLandmark(const int i, const int m, typename TLandmark::Vec& u,
+                                          typename TLandmark::Mat& S, double& w) {
+  if (i < 0 || i >= this->nParticles_) return false;
+  ensureCtx();
+  if (cacheIdx_ != i) {
+    const int cap = deviceConfig.gmCapacity + 8;
+    cMean_.resize((size_t)cap * 2);
+    cCov_.resize((size_t)cap * 3);
+    cW_.resize(cap);
+    int32_t n = 0;
+    check(rfsb200_get_map(ctx_, 0, i, cap, &n, cMean_.data(), cCov_.data(), cW_.data()), "rfsb200_get_map");
+    cN_ = n;
+    cacheIdx_ = i;
+  }
+  if (m < 0 || m >= cN_) return false;
+  u(0) = cMean_[2 * m];
+  u(1) = cMean_[2 * m + 1];
+  S(0, 0) = cCov_[3 * m];
+  S(0, 1) = S(1, 0) = cCov_[3 * m + 1];
+  S(1, 1) = cCov_[3 * m + 2];
+  w = cW_[m];
+  return true;
+}
+
+template <class R, class L, class M, class K>
+typename RBPHDFilter<R, L, M, K>::TimingInfo* RBPHDFilter<R, L, M, K>::getTimingInfo() {
+  timer_predict_.elapsed(timingInfo_.predict_wall, timingInfo_.predict_cpu);
+  timer_particleResample_.elapsed(timingInfo_.particleResample_wall, timingInfo_.particleResample_cpu);
+  /* the whole device step is booked under mapUpdate, like the reference does when it runs with more
+   * than one thread (include/RBPHDFilter.hpp:466-468,521-523) */
+  timingInfo_.mapUpdate_wall = ns_update_;
+  timingInfo_.mapUpdate_cpu = 0;
+  return &timingInfo_;
+}
+
+}  // namespace rfs
+
+#endif

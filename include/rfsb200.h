@@ -172,6 +172,28 @@ int rfsb200_set_poses(rfsb200_ctx* ctx, const double* pose /*[N][pose_dim]*/,
 int rfsb200_update(rfsb200_ctx* ctx, const double* Z /*[nZ][meas_dim]*/, int32_t nZ,
                    uint32_t flags, rfsb200_step_out* out);
 
+/* ---- the callers either side of the hot path -------------
+ * rfsb200_predict_maps = the map part of RBPHDFilter::predict() (include/RBPHDFilter.hpp:415-442):
+ *   add_births != 0: addBirthGaussians() in its direct form (:1013-1052 with
+ *     birthGaussianMeasurementCountThreshold_ == 1, the 2-D simulator's setting): for every particle,
+ *     every measurement of the LAST update that no Gaussian used (unused_measurements_, consumed from
+ *     the back, i.e. descending index) becomes a Gaussian at inverseMeasure(pose of the last update, z)
+ *     (src/MeasurementModel_RngBrg.cpp:117-136) with weight birth_weight; the masks are cleared.
+ *   Q_lmk != NULL: StaticProcessModel::staticStep on every Gaussian incl. the births: P += Q
+ *     (include/ProcessModel.hpp:195-219); Q_lmk = upper triangle (xx, xy, yy), already scaled by the
+ *     caller exactly as it scales the plugin's Q.
+ * Runs on the committed state, in place.  Births that do not fit gm_capacity set flag bit 1. */
+int rfsb200_predict_maps(rfsb200_ctx* ctx, const double* Q_lmk /*[3] or NULL*/, int32_t add_births,
+                         double birth_weight);
+
+/* The data movement of ParticleFilter::resample() (include/ParticleFilter.hpp:446-479): particle i
+ * of the new set takes the map of particle map_src[i] and the unused-measurement mask / in-FOV count of
+ * particle aux_src[i] (NULL = map_src; the reference looks those up through Particle::getParentId(),
+ * include/RBPHDFilter.hpp:1005-1011).  weight != NULL sets every particle weight to *weight (the
+ * reference resets them to 1, :486-488).  The sampling itself (one drand48()) stays with the caller. */
+int rfsb200_resample(rfsb200_ctx* ctx, const int32_t* map_src /*[N]*/, const int32_t* aux_src /*[N] or NULL*/,
+                     const double* weight /*scalar or NULL*/);
+
 /* Device address of the double[2] {sum w, sum w^2} of the last update, for the caller's
  * cross-GPU all-reduce (NCCL / torch.distributed) on the ctx stream; then normalize. */
 int rfsb200_weight_sums_device(rfsb200_ctx* ctx, void** dev_ptr);

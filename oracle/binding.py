@@ -202,3 +202,72 @@ def partition(L: np.ndarray):
     a = np.zeros(128, np.int32); b = np.zeros(128, np.int32); z = np.zeros(128, np.int32)
     nP = lib.phd_oracle_partition(L.ctypes.data, nR, nC, a.ctypes.data, b.ctypes.data, z.ctypes.data)
     return nP, a[:nP].copy(), b[:nP].copy(), z[:nP].copy()
+
+
+# ---- scripted sequences through the PUBLIC filter API (oracle/seq_harness.cpp) --------------------
+SEQ_REF_LIB = os.path.join(_HERE, "_ref", "libseq_ref.so")
+SEQ_B200_LIB = os.path.join(_HERE, "_ref", "libseq_b200.so")
+
+
+class SeqIO(C.Structure):
+    _fields_ = [
+        ("N", C.c_int32), ("n_steps", C.c_int32), ("nZ_max", C.c_int32),
+        ("poses", C.c_void_p), ("pose_cov", C.c_void_p), ("Z", C.c_void_p), ("nZ", C.c_void_p),
+        ("R", C.c_void_p), ("Q_lmk", C.c_void_p),
+        ("Pd", C.c_double), ("clutter", C.c_double), ("range_min", C.c_double), ("range_max", C.c_double),
+        ("range_buffer", C.c_double), ("thr_r", C.c_double), ("thr_b", C.c_double),
+        ("birth_w", C.c_double), ("gate", C.c_double), ("eval_w", C.c_double), ("wl_gate", C.c_double),
+        ("merge_t", C.c_double), ("merge_f", C.c_double), ("prune_t", C.c_double),
+        ("n_eval", C.c_int32), ("use_sc", C.c_int32), ("min_updates_before_resample", C.c_int32),
+        ("neff_threshold", C.c_double), ("precision", C.c_int32), ("seed48", C.c_uint32),
+        ("cap_total", C.c_int64), ("count_out", C.c_void_p), ("mean_out", C.c_void_p), ("cov_out", C.c_void_p),
+        ("w_out", C.c_void_p), ("weight_out", C.c_void_p), ("n_resampled", C.c_void_p), ("gm_size_trace", C.c_void_p),
+    ]
+
+
+def have_seq() -> bool:
+    return os.path.exists(SEQ_REF_LIB) and os.path.exists(SEQ_B200_LIB)
+
+
+def run_sequence(which: str, poses, Z, nZ, model: dict, cfg: dict, *, pose_cov, Q_lmk=None, neff_threshold=0.0,
+                 min_updates_before_resample=1, precision=64, seed48=1):
+    """which = 'ref' (the reference's RBPHDFilter.hpp) or 'b200' (include/rfs_b200/RBPHDFilter.hpp).
+    poses [K][N][3], Z [K][nZmax][2], nZ [K].  Returns (Result, n_resampled, gm_size_trace)."""
+    lib = C.CDLL(SEQ_REF_LIB if which == "ref" else SEQ_B200_LIB)
+    fn = lib.seq_run_ref if which == "ref" else lib.seq_run_b200
+    fn.restype = C.c_int
+    fn.argtypes = [C.POINTER(SeqIO)]
+    poses = np.ascontiguousarray(poses, dtype=np.float64)
+    Z = np.ascontiguousarray(Z, dtype=np.float64)
+    nZ = np.ascontiguousarray(nZ, dtype=np.int32)
+    K, N = poses.shape[0], poses.shape[1]
+    R = np.ascontiguousarray(np.array(model["R"], dtype=np.float64).reshape(4))
+    pc = np.ascontiguousarray(pose_cov, dtype=np.float64)
+    Q = None if Q_lmk is None else np.ascontiguousarray(np.array(Q_lmk, dtype=np.float64).reshape(4))
+    cap_total = N * 512
+    out = dict(count_out=np.zeros(N, np.int32), mean_out=np.zeros((cap_total, 2)), cov_out=np.zeros((cap_total, 3)),
+               w_out=np.zeros(cap_total), weight_out=np.zeros(N), n_resampled=np.zeros(1, np.int32),
+               gm_size_trace=np.zeros(K, np.int32))
+    io = SeqIO()
+    io.N, io.n_steps, io.nZ_max = N, K, Z.shape[1]
+    io.poses, io.pose_cov, io.Z, io.nZ, io.R = poses.ctypes.data, pc.ctypes.data, Z.ctypes.data, nZ.ctypes.data, R.ctypes.data
+    io.Q_lmk = None if Q is None else Q.ctypes.data
+    io.Pd, io.clutter = model["Pd"], model["clutter_intensity"]
+    io.range_min, io.range_max, io.range_buffer = model["range_min"], model["range_max"], model["range_buffer"]
+    io.thr_r, io.thr_b = model["innov_thr_range"], model["innov_thr_bearing"]
+    io.birth_w, io.gate = cfg["birth_gaussian_weight"], cfg["new_gaussian_create_innov_md_threshold"]
+    io.eval_w, io.wl_gate = cfg["eval_point_gaussian_weight"], cfg["meas_likelihood_md_threshold"]
+    io.merge_t, io.merge_f, io.prune_t = cfg["merging_threshold"], cfg["merging_cov_inflation_factor"], cfg["pruning_threshold"]
+    io.n_eval, io.use_sc = cfg["eval_point_count"], cfg["use_cluster_process"]
+    io.min_updates_before_resample = min_updates_before_resample
+    io.neff_threshold, io.precision, io.seed48 = neff_threshold, precision, seed48
+    io.cap_total = cap_total
+    for k, a in out.items():
+        setattr(io, k, a.ctypes.data)
+    rc = fn(C.byref(io))
+    if rc != 0:
+        raise RuntimeError(f"sequence harness ({which}) failed rc={rc}")
+    tot = int(out["count_out"].sum())
+    res = Result(out["count_out"], out["mean_out"][:tot].copy(), out["cov_out"][:tot].copy(), out["w_out"][:tot].copy(),
+                 None, out["weight_out"], None, None, None, 0.0)
+    return res, int(out["n_resampled"][0]), out["gm_size_trace"]

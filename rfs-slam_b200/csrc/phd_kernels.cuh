@@ -1541,6 +1541,102 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Map part of RBPHDFilter::predict() (include/RBPHDFilter.hpp:415-442), one warp per particle, in place:
+// births from the unused measurements of the last update (descending index, as the reference pops
+// them from the back of unused_measurements_, :1013-1052) at inverseMeasure(pose, z)
+// (src/MeasurementModel_RngBrg.cpp:117-136), then P += Q on everything (include/ProcessModel.hpp:195-219).
+template <typename T>
+struct PredictParams {
+  T* gm; int* cnt; unsigned long long* unused; int* flags;
+  const T* pose; const T* Z;
+  int N, cap, nZ, add_births, add_q;
+  T R00, R01, R10, R11, q00, q01, q11, birth_w;
+};
+
+template <typename T>
+__global__ void predict_maps_kernel(const PredictParams<T> p) {
+  const int lane = threadIdx.x & 31;
+  const int pi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (pi >= p.N) return;
+  T* g = p.gm + (size_t)pi * 6 * p.cap;
+  int n = p.cnt[pi];
+  n = n < 0 ? 0 : (n > p.cap ? p.cap : n);
+  if (p.add_births) {
+    unsigned long long mask = p.unused[pi];
+    if (p.nZ < 64) mask &= (1ull << p.nZ) - 1ull;
+    const int nb = __popcll(mask);
+    const T px = p.pose[4 * pi], py = p.pose[4 * pi + 1], pth = p.pose[4 * pi + 2];
+    bool over = false;
+    for (int k = lane; k < nb; k += 32) {
+      unsigned long long m = mask;   // k-th highest set bit
+      for (int s = 0; s < k; s++) m &= ~(1ull << (63 - __clzll((long long)m)));
+      const int z = 63 - __clzll((long long)m);
+      const T r = p.Z[2 * z], b = p.Z[2 * z + 1];
+      T sn, cs;
+      if constexpr (sizeof(T) == 4) sincosf(pth + b, &sn, &cs); else sincos(pth + b, &sn, &cs);
+      // Hinv = [[c, -r s], [s, r c]] ; cov = Hinv R Hinv^T
+      const T h00 = cs, h01 = -r * sn, h10 = sn, h11 = r * cs;
+      const T a00 = h00 * p.R00 + h01 * p.R10, a01 = h00 * p.R01 + h01 * p.R11;
+      const T a10 = h10 * p.R00 + h11 * p.R10, a11 = h10 * p.R01 + h11 * p.R11;
+      const int idx = n + k;
+      if (idx < p.cap) {
+        g[idx] = px + r * cs;
+        g[p.cap + idx] = py + r * sn;
+        g[2 * p.cap + idx] = a00 * h00 + a01 * h01;
+        g[3 * p.cap + idx] = a00 * h10 + a01 * h11;
+        g[4 * p.cap + idx] = a10 * h10 + a11 * h11;
+        g[5 * p.cap + idx] = p.birth_w;
+      } else {
+        over = true;
+      }
+    }
+    over = __any_sync(FULL, over);
+    n = (n + nb > p.cap) ? p.cap : n + nb;
+    if (lane == 0) {
+      p.cnt[pi] = n;
+      p.unused[pi] = 0ull;
+      if (over) p.flags[pi] |= FLAG_OVERFLOW;
+    }
+    __syncwarp();
+  }
+  if (p.add_q) {
+    for (int j = lane; j < n; j += 32) {
+      g[2 * p.cap + j] += p.q00;
+      g[3 * p.cap + j] += p.q01;
+      g[4 * p.cap + j] += p.q11;
+    }
+  }
+}
+
+// Data movement of ParticleFilter::resample(): new particle i <- map of src[i], aux of asrc[i].
+template <typename T>
+__global__ void resample_gather_kernel(const T* __restrict__ gm_in, const int* __restrict__ cnt_in,
+                                       const unsigned long long* __restrict__ unused_in, const int* __restrict__ nfov_in,
+                                       const double* __restrict__ w_in, const int* __restrict__ src,
+                                       const int* __restrict__ asrc, T* __restrict__ gm_out, int* __restrict__ cnt_out,
+                                       unsigned long long* __restrict__ unused_out, int* __restrict__ nfov_out,
+                                       double* __restrict__ w_out, int set_w, double w_value, int N, int cap) {
+  const int lane = threadIdx.x & 31;
+  const int pi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (pi >= N) return;
+  int s = src[pi];
+  s = s < 0 ? 0 : (s >= N ? N - 1 : s);
+  int a = asrc ? asrc[pi] : s;
+  a = a < 0 ? 0 : (a >= N ? N - 1 : a);
+  const int n = cnt_in[s];
+  const T* gi = gm_in + (size_t)s * 6 * cap;
+  T* go = gm_out + (size_t)pi * 6 * cap;
+  for (int pl = 0; pl < 6; pl++)
+    for (int j = lane; j < n; j += 32) go[(size_t)pl * cap + j] = gi[(size_t)pl * cap + j];
+  if (lane == 0) {
+    cnt_out[pi] = n;
+    unused_out[pi] = unused_in[a];
+    nfov_out[pi] = nfov_in[pi];   // nLandmarksInFOV_ stays with the slot in the reference
+    w_out[pi] = set_w ? w_value : w_in[s];
+  }
+}
+
 // w_i /= sum  (ParticleFilter::normalizeWeights, include/ParticleFilter.hpp:352-363)
 __global__ void normalize_kernel(double* w, const double* sums, int N) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;

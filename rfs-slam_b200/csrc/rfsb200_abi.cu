@@ -50,6 +50,10 @@ struct rfsb200_ctx {
   void* Zdev = nullptr;      // T [64][2]
   unsigned long long* unused = nullptr;
   int* nfov = nullptr;
+  unsigned long long* unused_alt = nullptr;   // resample target (swapped with unused)
+  int* nfov_alt = nullptr;
+  int* src_dev = nullptr;                     // [2][N] resample sources
+  int last_nZ = 0;                            // size of the measurement batch still held in Zdev
   int* flags = nullptr;
   double* sums = nullptr;                 // [2]
   unsigned long long* totals = nullptr;   // [2]
@@ -282,6 +286,28 @@ int ensure_pinned(rfsb200_ctx* c, size_t bytes) {
 
 }  // namespace
 
+namespace {
+template <typename T>
+int do_predict(rfsb200_ctx* c, const double* Q, int add_births, double birth_w) {
+  PredictParams<T> p{};
+  const StateBuf& st = c->st[c->front];
+  p.gm = (T*)st.gm; p.cnt = st.cnt; p.unused = c->unused; p.flags = c->flags;
+  p.pose = (const T*)c->pose; p.Z = (const T*)c->Zdev;
+  p.N = c->N; p.cap = c->cap; p.nZ = c->last_nZ;
+  p.add_births = (add_births && c->last_nZ > 0) ? 1 : 0;
+  p.add_q = Q ? 1 : 0;
+  const double* R = c->model.R;
+  p.R00 = (T)R[0]; p.R01 = (T)R[1]; p.R10 = (T)R[2]; p.R11 = (T)R[3];
+  if (Q) { p.q00 = (T)Q[0]; p.q01 = (T)Q[1]; p.q11 = (T)Q[2]; }
+  p.birth_w = (T)birth_w;
+  if (!p.add_births && !p.add_q) return RFSB200_OK;
+  predict_maps_kernel<T><<<(c->N * 32 + 127) / 128, 128, 0, c->stream>>>(p);
+  CU(c, cudaGetLastError());
+  return RFSB200_OK;
+}
+}  // namespace
+
+
 // ================================================================================================
 extern "C" {
 
@@ -350,6 +376,11 @@ int rfsb200_create(rfsb200_ctx** out, const rfsb200_dims* d) {
     CU(c, cudaMalloc((void**)&c->unused, (size_t)c->N * 8));
     CU(c, cudaMalloc((void**)&c->nfov, (size_t)c->N * 4));
     CU(c, cudaMalloc((void**)&c->flags, (size_t)c->N * 4));
+    CU(c, cudaMalloc((void**)&c->unused_alt, (size_t)c->N * 8));
+    CU(c, cudaMalloc((void**)&c->nfov_alt, (size_t)c->N * 4));
+    CU(c, cudaMalloc((void**)&c->src_dev, (size_t)c->N * 8));
+    CU(c, cudaMemset(c->unused_alt, 0, (size_t)c->N * 8));
+    CU(c, cudaMemset(c->nfov_alt, 0, (size_t)c->N * 4));
     CU(c, cudaMemset(c->unused, 0, (size_t)c->N * 8));
     CU(c, cudaMemset(c->nfov, 0, (size_t)c->N * 4));
     CU(c, cudaMemset(c->flags, 0, (size_t)c->N * 4));
@@ -397,6 +428,7 @@ int rfsb200_destroy(rfsb200_ctx* c) {
   }
   cudaFree(c->pose); cudaFree(c->pose_cov); cudaFree(c->Zdev);
   cudaFree(c->unused); cudaFree(c->nfov); cudaFree(c->flags);
+  cudaFree(c->unused_alt); cudaFree(c->nfov_alt); cudaFree(c->src_dev);
   cudaFree(c->sums); cudaFree(c->totals); cudaFree(c->istats); cudaFree(c->ticket);
   cudaFree(c->work_counter); cudaFree(c->stats_out); cudaFree(c->mstats);
   cudaFree(c->stg); cudaFree(c->offs); cudaFree(c->stg_small);
@@ -529,6 +561,7 @@ int rfsb200_update(rfsb200_ctx* c, const double* Z, int32_t nZ, uint32_t flags, 
   if (rc) return rc;
   launches++;
   c->last_out = out_idx;
+  c->last_nZ = nZ;
   if (!(flags & RFSB200_UPDATE_NO_NORMALIZE)) {
     normalize_kernel<<<(c->N + 255) / 256, 256, 0, c->stream>>>(c->st[out_idx].weight, c->sums, c->N);
     CU(c, cudaGetLastError());
@@ -558,6 +591,46 @@ int rfsb200_update(rfsb200_ctx* c, const double* Z, int32_t nZ, uint32_t flags, 
     CU(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
     out->elapsed_us = ms * 1000.f;
   }
+  return RFSB200_OK;
+}
+
+int rfsb200_predict_maps(rfsb200_ctx* c, const double* Q, int32_t add_births, double birth_w) {
+  if (!c) return fail(nullptr, RFSB200_EINVAL, "NULL ctx");
+  if (!c->have_maps) return fail(c, RFSB200_ESTATE, "predict_maps before upload_maps");
+  if (add_births && (!c->have_model || !c->have_poses))
+    return fail(c, RFSB200_ESTATE, "births need set_model and set_poses (pose and R of the last update)");
+  CU(c, cudaSetDevice(c->device));
+  c->last_out = c->front;
+  return c->prec == 32 ? do_predict<float>(c, Q, add_births, birth_w) : do_predict<double>(c, Q, add_births, birth_w);
+}
+
+int rfsb200_resample(rfsb200_ctx* c, const int32_t* map_src, const int32_t* aux_src, const double* weight) {
+  if (!c || !map_src) return fail(c, RFSB200_EINVAL, "NULL argument");
+  if (!c->have_maps) return fail(c, RFSB200_ESTATE, "resample before upload_maps");
+  for (int i = 0; i < c->N; i++)
+    if (map_src[i] < 0 || map_src[i] >= c->N || (aux_src && (aux_src[i] < 0 || aux_src[i] >= c->N)))
+      return fail(c, RFSB200_EINVAL, "resample source %d of particle %d out of range", map_src[i], i);
+  CU(c, cudaSetDevice(c->device));
+  CU(c, cudaMemcpyAsync(c->src_dev, map_src, (size_t)c->N * 4, cudaMemcpyHostToDevice, c->stream));
+  if (aux_src) CU(c, cudaMemcpyAsync(c->src_dev + c->N, aux_src, (size_t)c->N * 4, cudaMemcpyHostToDevice, c->stream));
+  const StateBuf& in = c->st[c->front];
+  const StateBuf& out = c->st[c->front ^ 1];
+  const int blocks = (c->N * 32 + 127) / 128;
+  const int* asrc = aux_src ? c->src_dev + c->N : nullptr;
+  if (c->prec == 32)
+    resample_gather_kernel<float><<<blocks, 128, 0, c->stream>>>((const float*)in.gm, in.cnt, c->unused, c->nfov, in.weight, c->src_dev, asrc,
+                                                                 (float*)out.gm, out.cnt, c->unused_alt, c->nfov_alt, out.weight,
+                                                                 weight ? 1 : 0, weight ? *weight : 0.0, c->N, c->cap);
+  else
+    resample_gather_kernel<double><<<blocks, 128, 0, c->stream>>>((const double*)in.gm, in.cnt, c->unused, c->nfov, in.weight, c->src_dev, asrc,
+                                                                  (double*)out.gm, out.cnt, c->unused_alt, c->nfov_alt, out.weight,
+                                                                  weight ? 1 : 0, weight ? *weight : 0.0, c->N, c->cap);
+  CU(c, cudaGetLastError());
+  CU(c, cudaStreamSynchronize(c->stream));   // map_src / aux_src are the caller's (pageable) buffers
+  std::swap(c->unused, c->unused_alt);
+  std::swap(c->nfov, c->nfov_alt);
+  c->front ^= 1;
+  c->last_out = c->front;
   return RFSB200_OK;
 }
 

@@ -131,6 +131,20 @@ class PHDUpdater:
         _check(self.lib, self.ctx, rc, "update")
         return out
 
+    # ---- the callers either side (predict's map part, resampling's data movement) -----------------
+    def predict_maps(self, Q_lmk=None, add_births: bool = True, birth_weight: float = 0.0):
+        """RBPHDFilter::predict() minus the particle propagation: births, then P += Q."""
+        q = None if Q_lmk is None else np.ascontiguousarray(Q_lmk, dtype=np.float64).reshape(3)
+        _check(self.lib, self.ctx,
+               self.lib.rfsb200_predict_maps(self.ctx, capi.ptr(q), 1 if add_births else 0, float(birth_weight)),
+               "predict_maps")
+
+    def resample(self, map_src, aux_src=None, weight: float | None = 1.0):
+        ms = np.ascontiguousarray(map_src, dtype=np.int32)
+        au = None if aux_src is None else np.ascontiguousarray(aux_src, dtype=np.int32)
+        wv = None if weight is None else np.array([weight], dtype=np.float64)
+        _check(self.lib, self.ctx, self.lib.rfsb200_resample(self.ctx, capi.ptr(ms), capi.ptr(au), capi.ptr(wv)), "resample")
+
     def weight_sums_device_ptr(self) -> int:
         p = C.c_void_p()
         _check(self.lib, self.ctx, self.lib.rfsb200_weight_sums_device(self.ctx, C.byref(p)), "weight_sums_device")

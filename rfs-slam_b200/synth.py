@@ -133,11 +133,19 @@ def make_workload(N: int, nM: int, nZ: int, *, use_cluster_process: int = 1, wor
         r_lo, r_hi = rmin + buf, rmax - buf
     elif world == "sparse":
         r_lo, r_hi = 0.0, 3.0 * rmax
+    elif world == "clumped":
+        r_lo, r_hi = rmin + 4 * buf, rmax - 4 * buf
     else:
         raise ValueError(world)
     u = rng.uniform(0.0, 1.0, nM)
     r = np.sqrt(r_lo ** 2 + u * (r_hi ** 2 - r_lo ** 2))  # uniform in area
     b = rng.uniform(-math.pi, math.pi, nM)
+    if world == "clumped":
+        # landmarks in tight groups of 6 (0.1 m): gates overlap, so the (eval point, measurement)
+        # graph has large connected partitions (the reference's Murty branch, nR + nC > 8)
+        g = np.arange(nM) // 6
+        r = r[g * 6] + rng.uniform(-0.1, 0.1, nM)
+        b = b[g * 6] + rng.uniform(-0.1, 0.1, nM) / np.maximum(r, 1.0)
     if parity_extras and nM >= 20:
         # 5 % of the landmarks in the four buffer bands (Q2), two at bearing pi +- 0.01 (Q3)
         k = max(4, nM // 20)

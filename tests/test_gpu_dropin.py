@@ -1,0 +1,74 @@
+"""The drop-in C++ header include/rfs_b200/RBPHDFilter.hpp against the reference class it replaces.
+
+oracle/seq_harness.cpp drives rfs::RBPHDFilter<MotionModel_Odometry2d, StaticProcessModel<Landmark2d>,
+MeasurementModel_RngBrg, KalmanFilter_RngBrg> through its public API only (predict, setParticlePose,
+update, getGMSize, getLandmark, particle weights) for a scripted sequence, compiled once against the
+reference's RBPHDFilter.hpp (CPU) and once against the drop-in (GPU through the C ABI).  Covers birth
+Gaussians, the landmark process noise, resampling (same drand48 stream) and empty measurement sets."""
+import math
+
+import numpy as np
+import pytest
+
+import helpers
+from helpers import TOL32, TOL64
+
+pytestmark = pytest.mark.gpu
+
+
+def _scenario(N=40, K=10, n_lmk=60, nZ_max=16, seed=5, sc=1):
+    from rfs_slam_b200 import synth
+    rng = np.random.default_rng(seed)
+    md = dict(synth.DEFAULT_MODEL)
+    md.update(range_max=6.0, range_buffer=0.2)
+    fc = dict(synth.DEFAULT_CFG)
+    fc.update(use_cluster_process=sc, pruning_threshold=0.005, birth_gaussian_weight=0.05)
+    lm = rng.uniform(-8, 8, (n_lmk, 2))
+    off = rng.normal(0, [0.04, 0.04, 0.008], (N, 3))           # per-particle pose offsets
+    poses = np.zeros((K, N, 3))
+    Z = np.zeros((K, nZ_max, 2))
+    nZ = np.zeros(K, np.int32)
+    for k in range(K):
+        true = np.array([0.4 * k - 1.5, 0.1 * k, 0.05 * k])
+        poses[k] = true + off
+        d = lm - true[:2]
+        r = np.hypot(d[:, 0], d[:, 1])
+        b = np.arctan2(d[:, 1], d[:, 0]) - true[2]
+        b = (b + math.pi) % (2 * math.pi) - math.pi
+        vis = np.nonzero((r > md["range_min"] + 0.3) & (r < md["range_max"] - 0.3))[0]
+        vis = vis[rng.random(len(vis)) < 0.9][:nZ_max - 2]
+        z = np.stack([r[vis] + rng.normal(0, 0.02, len(vis)), b[vis] + rng.normal(0, 0.007, len(vis))], 1)
+        cl = np.stack([rng.uniform(md["range_min"], md["range_max"], 2), rng.uniform(-math.pi, math.pi, 2)], 1)
+        z = np.concatenate([z, cl])
+        if k == 6:
+            z = z[:0]                                          # Q11: an empty measurement set mid-sequence
+        nZ[k] = len(z)
+        Z[k, :len(z)] = z
+    return md, fc, poses, Z, nZ
+
+
+@pytest.mark.parametrize("sc", [1, 0])
+@pytest.mark.parametrize("resample", [False, True])
+def test_dropin_header_matches_reference_class(cuda_required, sc, resample):
+    from oracle import binding as ob
+    if not ob.have_seq():
+        pytest.skip("oracle/_ref/libseq_{ref,b200}.so not built (needs /root/reference at build time)")
+    md, fc, poses, Z, nZ = _scenario(sc=sc)
+    kw = dict(pose_cov=[3e-5, 0, 0, 3e-5, 0, 3e-5], Q_lmk=[1e-5, 0, 0, 1e-5],
+              neff_threshold=(float(poses.shape[1]) if resample else 0.0), seed48=7)
+    ref, nres_ref, trace_ref = ob.run_sequence("ref", poses, Z, nZ, md, fc, **kw)
+    got, nres, trace = ob.run_sequence("b200", poses, Z, nZ, md, fc, precision=64, **kw)
+    assert nres == nres_ref and (nres > 0) == resample
+    assert np.array_equal(trace, trace_ref)
+    assert np.array_equal(got.count, ref.count) and ref.count.max() > 5
+    r = helpers.compare_maps(got.count, got.mean, got.cov, got.w, ref.count, ref.mean, ref.cov, ref.w, TOL64, ordered=False)
+    assert not r["bad"]
+    assert np.allclose(got.weight, ref.weight, rtol=1e-8, atol=0)
+    # the fp32 product build stays within the fp32 tolerances on all but a few particles
+    g32, nres32, _ = ob.run_sequence("b200", poses, Z, nZ, md, fc, precision=32, **kw)
+    if not resample:
+        r32 = helpers.compare_maps(g32.count, g32.mean, g32.cov, g32.w, ref.count, ref.mean, ref.cov, ref.w, TOL32, ordered=False)
+        assert len(r32["bad"]) <= max(2, len(ref.count) // 10)
+        ok = np.ones(len(ref.count), bool)
+        ok[r32["bad"]] = False
+        assert np.allclose(g32.weight[ok], ref.weight[ok], rtol=2e-2)

@@ -223,3 +223,27 @@ def test_device_permanent_known_answers(cuda_required):
     exp = np.array([ob.permanent(a) for a in A])
     assert np.allclose(got, exp, rtol=1e-11)
     up.close()
+
+
+def test_large_partitions_are_flagged_and_summed_exactly(cuda_required):
+    """Partitions with nR + nC > 8: the reference sums Murty's 200 best assignments (Q7, a truncated
+    sum); the device computes the exact sum and flags the particle (bit 2).  The flagged set must be
+    the oracle's Murty set, the exact weight can only be >= the truncated one (same maps), and
+    unflagged particles agree to tolerance."""
+    from oracle import binding as ob
+    from rfs_slam_b200 import synth
+    wl = synth.make_workload(N=64, nM=60, nZ=30, use_cluster_process=0, config_id=23, world="clumped",
+                             model=dict(Pd=0.7, clutter_intensity=5e-3), cfg=dict(eval_point_gaussian_weight=0.1))
+    o = ob.run(wl, sort_mode=ob.SORT_STABLE)
+    murty = (o.flags & 2) > 0
+    assert murty.sum() >= 4, "workload no longer exercises the Murty branch"
+    so, cnt, mean, cov, w, pw, up = helpers.run_device(wl, precision=64)
+    f = up.get_flags()
+    assert np.array_equal((f & 2) > 0, murty)
+    assert so.n_murty == int(murty.sum()) and so.n_overflow == 0
+    r = helpers.compare_maps(cnt, mean, cov, w, o.count, o.mean, o.cov, o.w, TOL64)
+    assert not r["bad"]                                   # maps never depend on the weighting
+    assert np.allclose(pw[~murty], o.weight[~murty], rtol=1e-9)
+    assert (pw[murty] >= o.weight[murty] * (1 - 1e-9)).all()
+    assert np.allclose(pw[murty], o.weight[murty], rtol=0.05)   # the 200 best carry almost all the mass
+    up.close()
