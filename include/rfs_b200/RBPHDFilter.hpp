@@ -237,11 +237,16 @@ RBPHDFilter<R, L, M, K>::RBPHDFilter(int n)
   config.minUpdatesBeforeResample_ = 1;
   config.minMeasurementsBeforeResample_ = 1;
   config.useClusterProcess_ = false;
-  deviceConfig.gmCapacity = 256;
-  deviceConfig.workCapacity = 384;
+  deviceConfig.gmCapacity = 192;
+  deviceConfig.workCapacity = 256;
   deviceConfig.zCapacity = 64;
   deviceConfig.device = 0;
   deviceConfig.precision = 32;
+  /* unchanged drivers cannot reach deviceConfig: the environment can (verification runs) */
+  if (const char* e = getenv("RFSB200_PRECISION")) deviceConfig.precision = atoi(e);
+  if (const char* e = getenv("RFSB200_DEVICE")) deviceConfig.device = atoi(e);
+  if (const char* e = getenv("RFSB200_GM_CAPACITY")) deviceConfig.gmCapacity = atoi(e);
+  if (const char* e = getenv("RFSB200_WORK_CAPACITY")) deviceConfig.workCapacity = atoi(e);
   lastStep_ = rfsb200_step_out();
   timingInfo_ = TimingInfo();
 }
@@ -432,15 +437,16 @@ bool RBPHDFilter<R, L, M, K>::resample(unsigned int n, bool forceResample) {
       nextFree++;
     }
   }
-  /* addBirthGaussians looks the unused measurements up through getParentId() (:1005-1011) */
-  /* ... in place and in ascending particle order, so a parent slot below i has already been
-   * re-pointed when i reads it; the ids it uses are those the particle copies carry (they are not
-   * slot numbers any more after the first resampling — reproduced as is) */
+  /* addBirthGaussians (:1001-1011) looks the unused measurements of particle i up through
+   * getParentId() INSIDE the loop that also consumes them, in ascending i: a parent slot below i has
+   * already been emptied when i copies it (no births for i), a parent slot above i still holds its
+   * list.  The ids are those the particle copies carry (not slot numbers any more after the first
+   * resampling).  Reproduced as is: -1 = empty. */
   std::vector<int> auxSrc(N);
   for (int i = 0; i < N; i++) {
     const unsigned parent = this->particleSet_[i]->getParentId();
-    if (parent != (unsigned)i && parent < (unsigned)N) auxSrc[i] = (parent < (unsigned)i) ? auxSrc[parent] : (int)parent;
-    else auxSrc[i] = i;
+    if (parent == (unsigned)i || parent >= (unsigned)N) auxSrc[i] = i;
+    else auxSrc[i] = (parent > (unsigned)i) ? (int)parent : -1;
   }
   for (int i = 0; i < N; i++) this->particleSet_[i]->setWeight(1);
   const double one = 1.0;

@@ -188,8 +188,8 @@ int rfsb200_predict_maps(rfsb200_ctx* ctx, const double* Q_lmk /*[3] or NULL*/, 
 
 /* The data movement of ParticleFilter::resample() (include/ParticleFilter.hpp:446-479): particle i
  * of the new set takes the map of particle map_src[i] and the unused-measurement mask / in-FOV count of
- * particle aux_src[i] (NULL = map_src; the reference looks those up through Particle::getParentId(),
- * include/RBPHDFilter.hpp:1005-1011).  weight != NULL sets every particle weight to *weight (the
+ * particle aux_src[i] (NULL = map_src, -1 = none; the reference looks those up through
+ * Particle::getParentId() while it consumes them, include/RBPHDFilter.hpp:1001-1011).  weight != NULL sets every particle weight to *weight (the
  * reference resets them to 1, :486-488).  The sampling itself (one drand48()) stays with the caller. */
 int rfsb200_resample(rfsb200_ctx* ctx, const int32_t* map_src /*[N]*/, const int32_t* aux_src /*[N] or NULL*/,
                      const double* weight /*scalar or NULL*/);

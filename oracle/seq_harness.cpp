@@ -73,8 +73,9 @@ extern "C" int SEQ_ENTRY(seq_io* io) {
   Filter f(N);
 #ifdef SEQ_B200
   f.deviceConfig.precision = io->precision;
-  f.deviceConfig.gmCapacity = 256;
-  f.deviceConfig.workCapacity = 384;
+  f.deviceConfig.gmCapacity = 128;
+  f.deviceConfig.zCapacity = 32;
+  f.deviceConfig.workCapacity = 256;
 #else
   f.config.importanceWeightingEvalPointGuassianWeight_ = 0.75;
   f.config.useClusterProcess_ = false;

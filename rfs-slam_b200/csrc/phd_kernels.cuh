@@ -1616,14 +1616,17 @@ __global__ void resample_gather_kernel(const T* __restrict__ gm_in, const int* _
                                        const double* __restrict__ w_in, const int* __restrict__ src,
                                        const int* __restrict__ asrc, T* __restrict__ gm_out, int* __restrict__ cnt_out,
                                        unsigned long long* __restrict__ unused_out, int* __restrict__ nfov_out,
-                                       double* __restrict__ w_out, int set_w, double w_value, int N, int cap) {
+                                       double* __restrict__ w_out, int set_w, double w_value,
+                                       const T* __restrict__ pose_in, const T* __restrict__ pcov_in,
+                                       T* __restrict__ pose_out, T* __restrict__ pcov_out, int pose_cov_mode,
+                                       int N, int cap) {
   const int lane = threadIdx.x & 31;
   const int pi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (pi >= N) return;
   int s = src[pi];
   s = s < 0 ? 0 : (s >= N ? N - 1 : s);
-  int a = asrc ? asrc[pi] : s;
-  a = a < 0 ? 0 : (a >= N ? N - 1 : a);
+  int a = asrc ? asrc[pi] : s;   // -1: the new particle starts with no unused measurements
+  a = a >= N ? N - 1 : a;
   const int n = cnt_in[s];
   const T* gi = gm_in + (size_t)s * 6 * cap;
   T* go = gm_out + (size_t)pi * 6 * cap;
@@ -1631,10 +1634,13 @@ __global__ void resample_gather_kernel(const T* __restrict__ gm_in, const int* _
     for (int j = lane; j < n; j += 32) go[(size_t)pl * cap + j] = gi[(size_t)pl * cap + j];
   if (lane == 0) {
     cnt_out[pi] = n;
-    unused_out[pi] = unused_in[a];
+    unused_out[pi] = a >= 0 ? unused_in[a] : 0ull;
     nfov_out[pi] = nfov_in[pi];   // nLandmarksInFOV_ stays with the slot in the reference
     w_out[pi] = set_w ? w_value : w_in[s];
   }
+  // the copy carries the pose of its source (Particle::copy): the next predict's births use it
+  if (lane < 4) pose_out[4 * pi + lane] = pose_in[4 * s + lane];
+  if (pose_cov_mode == 2 && lane < 8) pcov_out[8 * pi + lane] = pcov_in[8 * s + lane];
 }
 
 // w_i /= sum  (ParticleFilter::normalizeWeights, include/ParticleFilter.hpp:352-363)

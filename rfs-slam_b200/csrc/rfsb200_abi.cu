@@ -46,6 +46,8 @@ struct rfsb200_ctx {
   int last_out = 0;  // buffer written by the last update (== front unless NO_COMMIT)
   void* pose = nullptr;      // T [N][4]
   void* pose_cov = nullptr;  // T [N][8]
+  void* pose_alt = nullptr;      // resample targets (swapped with pose / pose_cov)
+  void* pose_cov_alt = nullptr;
   int pose_cov_mode = 0;
   void* Zdev = nullptr;      // T [64][2]
   unsigned long long* unused = nullptr;
@@ -63,6 +65,7 @@ struct rfsb200_ctx {
   unsigned int* work_counter = nullptr;
   unsigned long long* stats_out = nullptr;  // [8]
   int cfg_mode_mf = -1;                      // launch configuration was computed for this mode
+  int cfg_n_eval = -1;                       //   ... and this eval-point count (multi-feature scratch)
   // staging (device): packed fp64 + offsets
   double* stg = nullptr;       // N*cap*6 doubles
   long long* offs = nullptr;   // [N+1]
@@ -206,8 +209,10 @@ int round_pow2(int v) {
 template <typename T, bool MF>
 int configure_launch_t(rfsb200_ctx* c) {
   const int mf = MF ? 1 : 0;
-  if (c->cfg_mode_mf == mf) return RFSB200_OK;
-  c->mf_bytes = mf ? mf_scratch_bytes<T>(MAX_EVAL, c->dims.z_capacity) : 0;
+  const int n_eval = (MF && c->have_cfg) ? std::max(1, c->cfg.eval_point_count) : MAX_EVAL;
+  if (c->cfg_mode_mf == mf && (!MF || c->cfg_n_eval == n_eval)) return RFSB200_OK;
+  c->cfg_n_eval = n_eval;
+  c->mf_bytes = mf ? mf_scratch_bytes<T>(n_eval, c->dims.z_capacity) : 0;
   c->warp_bytes = warp_bytes_for<T>(c->W, mf, c->mf_bytes);
   c->smem_bytes = (size_t)z_bytes<T>() + (size_t)WARPS_PER_CTA * c->warp_bytes;
   if (c->smem_bytes > 227 * 1024) return fail(c, RFSB200_ECAPACITY, "work_capacity %d needs %zu B shared memory per CTA (> 227 KB)", c->W, c->smem_bytes);
@@ -372,6 +377,11 @@ int rfsb200_create(rfsb200_ctx** out, const rfsb200_dims* d) {
     CU(c, cudaMalloc(&c->pose, (size_t)c->N * 4 * c->tsize));
     CU(c, cudaMalloc(&c->pose_cov, (size_t)c->N * 8 * c->tsize));
     CU(c, cudaMemset(c->pose_cov, 0, (size_t)c->N * 8 * c->tsize));
+    CU(c, cudaMalloc(&c->pose_alt, (size_t)c->N * 4 * c->tsize));
+    CU(c, cudaMalloc(&c->pose_cov_alt, (size_t)c->N * 8 * c->tsize));
+    CU(c, cudaMemset(c->pose, 0, (size_t)c->N * 4 * c->tsize));
+    CU(c, cudaMemset(c->pose_alt, 0, (size_t)c->N * 4 * c->tsize));
+    CU(c, cudaMemset(c->pose_cov_alt, 0, (size_t)c->N * 8 * c->tsize));
     CU(c, cudaMalloc(&c->Zdev, (size_t)MAX_Z * 4 * c->tsize + MAX_Z * 4));
     CU(c, cudaMalloc((void**)&c->unused, (size_t)c->N * 8));
     CU(c, cudaMalloc((void**)&c->nfov, (size_t)c->N * 4));
@@ -427,6 +437,7 @@ int rfsb200_destroy(rfsb200_ctx* c) {
     cudaFree(c->st[k].gm); cudaFree(c->st[k].cnt); cudaFree(c->st[k].weight);
   }
   cudaFree(c->pose); cudaFree(c->pose_cov); cudaFree(c->Zdev);
+  cudaFree(c->pose_alt); cudaFree(c->pose_cov_alt);
   cudaFree(c->unused); cudaFree(c->nfov); cudaFree(c->flags);
   cudaFree(c->unused_alt); cudaFree(c->nfov_alt); cudaFree(c->src_dev);
   cudaFree(c->sums); cudaFree(c->totals); cudaFree(c->istats); cudaFree(c->ticket);
@@ -597,6 +608,7 @@ int rfsb200_update(rfsb200_ctx* c, const double* Z, int32_t nZ, uint32_t flags, 
 int rfsb200_predict_maps(rfsb200_ctx* c, const double* Q, int32_t add_births, double birth_w) {
   if (!c) return fail(nullptr, RFSB200_EINVAL, "NULL ctx");
   if (!c->have_maps) return fail(c, RFSB200_ESTATE, "predict_maps before upload_maps");
+  if (c->last_nZ == 0) add_births = 0;   // no update yet: there is no unused measurement to give birth from
   if (add_births && (!c->have_model || !c->have_poses))
     return fail(c, RFSB200_ESTATE, "births need set_model and set_poses (pose and R of the last update)");
   CU(c, cudaSetDevice(c->device));
@@ -608,7 +620,7 @@ int rfsb200_resample(rfsb200_ctx* c, const int32_t* map_src, const int32_t* aux_
   if (!c || !map_src) return fail(c, RFSB200_EINVAL, "NULL argument");
   if (!c->have_maps) return fail(c, RFSB200_ESTATE, "resample before upload_maps");
   for (int i = 0; i < c->N; i++)
-    if (map_src[i] < 0 || map_src[i] >= c->N || (aux_src && (aux_src[i] < 0 || aux_src[i] >= c->N)))
+    if (map_src[i] < 0 || map_src[i] >= c->N || (aux_src && (aux_src[i] < -1 || aux_src[i] >= c->N)))
       return fail(c, RFSB200_EINVAL, "resample source %d of particle %d out of range", map_src[i], i);
   CU(c, cudaSetDevice(c->device));
   CU(c, cudaMemcpyAsync(c->src_dev, map_src, (size_t)c->N * 4, cudaMemcpyHostToDevice, c->stream));
@@ -620,15 +632,21 @@ int rfsb200_resample(rfsb200_ctx* c, const int32_t* map_src, const int32_t* aux_
   if (c->prec == 32)
     resample_gather_kernel<float><<<blocks, 128, 0, c->stream>>>((const float*)in.gm, in.cnt, c->unused, c->nfov, in.weight, c->src_dev, asrc,
                                                                  (float*)out.gm, out.cnt, c->unused_alt, c->nfov_alt, out.weight,
-                                                                 weight ? 1 : 0, weight ? *weight : 0.0, c->N, c->cap);
+                                                                 weight ? 1 : 0, weight ? *weight : 0.0,
+                                                                 (const float*)c->pose, (const float*)c->pose_cov, (float*)c->pose_alt,
+                                                                 (float*)c->pose_cov_alt, c->pose_cov_mode, c->N, c->cap);
   else
     resample_gather_kernel<double><<<blocks, 128, 0, c->stream>>>((const double*)in.gm, in.cnt, c->unused, c->nfov, in.weight, c->src_dev, asrc,
                                                                   (double*)out.gm, out.cnt, c->unused_alt, c->nfov_alt, out.weight,
-                                                                  weight ? 1 : 0, weight ? *weight : 0.0, c->N, c->cap);
+                                                                  weight ? 1 : 0, weight ? *weight : 0.0,
+                                                                  (const double*)c->pose, (const double*)c->pose_cov, (double*)c->pose_alt,
+                                                                  (double*)c->pose_cov_alt, c->pose_cov_mode, c->N, c->cap);
   CU(c, cudaGetLastError());
   CU(c, cudaStreamSynchronize(c->stream));   // map_src / aux_src are the caller's (pageable) buffers
   std::swap(c->unused, c->unused_alt);
   std::swap(c->nfov, c->nfov_alt);
+  std::swap(c->pose, c->pose_alt);
+  if (c->pose_cov_mode == 2) std::swap(c->pose_cov, c->pose_cov_alt);
   c->front ^= 1;
   c->last_out = c->front;
   return RFSB200_OK;
