@@ -179,6 +179,7 @@ def main():
     ap.add_argument("--ref-particles", type=int, default=2000, help="--impl reference: particles per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-fused", action="store_true", help="NCCL all-reduce + normalise kernel instead of the in-kernel sum over peer memory")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 0)
     # stdout carries exactly ONE JSON line: everything libraries print (NCCL's version banner, ...)
@@ -219,7 +220,8 @@ def main():
     units_local = int(wl.count.sum()) * nZ
     up = PHDUpdater(N, gm_capacity=256, z_capacity=32, device=local, precision=32)
     up.load_workload(wl)
-    sh = ShardedUpdater(up, device=dev)
+    sh = ShardedUpdater(up, device=dev, fused=not a.no_fused)
+    fused = not a.no_fused
     up.synchronize()
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
     FLAGS = capi.UPDATE_NO_COMMIT   # every step starts from the same state, so nM_in is constant
@@ -249,7 +251,7 @@ def main():
     for k in range(K):
         flush.zero_()                 # > L2 (126 MB): the step reads its inputs from HBM
         ev[k][0].record()
-        sh.step(wl.Z, flags=FLAGS)    # Z H2D (1.3 KB) + fused update kernel + [all-reduce] + normalise
+        sh.step(wl.Z, flags=FLAGS)    # Z H2D (1.3 KB) + fused update kernel (+ cross-GPU sum + normalise inside)
         ev[k][1].record()
     barrier()
     t_wall = time.perf_counter() - t_wall0
@@ -344,8 +346,9 @@ def main():
                     config=dict(workload=desc, particles_total=N * world, particles_per_gpu=N, gm_per_particle=nM_in,
                                 gm_out_per_particle=nM_out_mean, meas=nZ, l2="flushed between steps (512 MiB memset, untimed)",
                                 timing="CUDA events per step on the launch stream, summed; max over ranks",
-                                parallelism=f"particles block-partitioned over {world} GPU(s); one all-reduce of [sum w, sum w^2] per step"),
-                    e2e=e2e, gpu_launches=2 * K, roofline=roofline, cpu_baseline=cpu, clocks=clk,
+                                parallelism=f"particles block-partitioned over {world} GPU(s); one all-reduce of [sum w, sum w^2] per step "
+                                            + ("inside the update kernel over NVLink peer memory" if fused else "by NCCL")),
+                    e2e=e2e, gpu_launches=(1 if fused else 2) * K, roofline=roofline, cpu_baseline=cpu, clocks=clk,
                     wall_s_timed_region_incl_flush=t_wall)
         emit(line)
     if world > 1:

@@ -53,6 +53,10 @@ extern "C" {
 #define RFSB200_UPDATE_DEFAULT    0u
 #define RFSB200_UPDATE_NO_COMMIT  1u  /* compute the step into the back buffers but keep the
                                          current state as the state (benchmark / replay aid) */
+#define RFSB200_UPDATE_FUSED_ALLREDUCE 4u /* after rfsb200_comm_connect: the update kernel itself adds the
+                                         [sum w, sum w^2] pairs of all ranks through peer memory (NVLink)
+                                         and normalises, in the same launch; every rank must call
+                                         rfsb200_update with this flag the same number of times      */
 #define RFSB200_UPDATE_NO_NORMALIZE 2u /* stop after the local [sum w, sum w^2] reduction so the
                                          caller can all-reduce rfsb200_weight_sums_device() across
                                          GPUs and then call rfsb200_normalize()               */
@@ -193,6 +197,16 @@ int rfsb200_predict_maps(rfsb200_ctx* ctx, const double* Q_lmk /*[3] or NULL*/, 
  * reference resets them to 1, :486-488).  The sampling itself (one drand48()) stays with the caller. */
 int rfsb200_resample(rfsb200_ctx* ctx, const int32_t* map_src /*[N]*/, const int32_t* aux_src /*[N] or NULL*/,
                      const double* weight /*scalar or NULL*/);
+
+/* ---- fused cross-GPU weight sum (one process per GPU on one node) ---------------------------------
+ * rfsb200_comm_export writes a 64-byte CUDA IPC handle of this ctx's mailbox; the caller exchanges the
+ * handles of all ranks (any transport: MPI, torch.distributed, files) and passes them, in rank
+ * order, to rfsb200_comm_connect, which maps the peers' mailboxes (world <= 8).  From then on
+ * RFSB200_UPDATE_FUSED_ALLREDUCE replaces the caller's all-reduce + rfsb200_normalize(). */
+int rfsb200_comm_export(rfsb200_ctx* ctx, void* handle64);
+int rfsb200_comm_connect(rfsb200_ctx* ctx, int32_t rank, int32_t world, const void* handles /*[world][64]*/);
+/* 1 if a peer did not arrive within 2 s in some fused update since the last call (sums are NaN then) */
+int rfsb200_comm_error(rfsb200_ctx* ctx, int32_t* flag);
 
 /* Device address of the double[2] {sum w, sum w^2} of the last update, for the caller's
  * cross-GPU all-reduce (NCCL / torch.distributed) on the ctx stream; then normalize. */

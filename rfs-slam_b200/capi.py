@@ -17,6 +17,7 @@ OK = 0
 UPDATE_DEFAULT = 0
 UPDATE_NO_COMMIT = 1
 UPDATE_NO_NORMALIZE = 2
+UPDATE_FUSED_ALLREDUCE = 4
 
 ERRORS = {0: "OK", -1: "EINVAL", -2: "ECUDA", -3: "ENOMEM", -4: "ECAPACITY", -5: "EUNSUPPORTED",
           -6: "ESTATE", -7: "ENODEVICE"}
@@ -101,6 +102,9 @@ _SIGS = {
     "rfsb200_update": (C.c_int, [_P, _P, C.c_int32, C.c_uint32, C.POINTER(StepOut)]),
     "rfsb200_predict_maps": (C.c_int, [_P, _P, C.c_int32, C.c_double]),
     "rfsb200_resample": (C.c_int, [_P, _P, _P, _P]),
+    "rfsb200_comm_export": (C.c_int, [_P, _P]),
+    "rfsb200_comm_connect": (C.c_int, [_P, C.c_int32, C.c_int32, _P]),
+    "rfsb200_comm_error": (C.c_int, [_P, C.POINTER(C.c_int32)]),
     "rfsb200_weight_sums_device": (C.c_int, [_P, C.POINTER(_P)]),
     "rfsb200_normalize": (C.c_int, [_P]),
     "rfsb200_get_weights": (C.c_int, [_P, C.c_int, _P]),

@@ -31,6 +31,8 @@ constexpr int FLAG_OVERFLOW = 1;
 constexpr int FLAG_MURTY = 2;       // a partition with nR + nC > 8 (reference would use Murty-200)
 constexpr int FLAG_DP_OVERFLOW = 4; // partition too large for the on-chip DP
 
+struct CommSlot { double s1, s2; unsigned long long epoch; unsigned long long pad; };   // 32 B; mailbox = [2][8]
+
 template <typename T>
 struct KParams {
   // model (MeasurementModel_RngBrg / KalmanFilter_RngBrg configs)
@@ -67,6 +69,11 @@ struct KParams {
   unsigned int* mstats;           // [8] merge statistics (fallback reasons, pairs, clusters)
   unsigned int* ticket;
   unsigned int* work_counter;     // dynamic particle queue, re-armed by the last CTA
+  // fused cross-GPU sum of [sum w, sum w^2] over peer memory (NVLink / NVSwitch), see S8
+  int comm_rank, comm_world, fused_normalize;
+  unsigned long long comm_epoch;
+  void* comm_peer[8];               // mailbox of every rank (own included), mapped into this process
+  int* comm_error;                  // set to 1 if a peer did not arrive in time
   unsigned long long* stats_out;  // [13] totals/istats/mstats of the finished step, published by the last CTA
 };
 
@@ -439,18 +446,32 @@ __device__ int merge_clustered(T* cur, const MergeScratch<T>& ms, int W, int n, 
       const XY<T> me = ms.sxy[s];
       const int j = ms.order[s];
       const int end = ms.cellStart[ms.slot[j] + 2];
-      for (int t = s + 1; t < end; t++) {
-        const XY<T> q = ms.sxy[t];
+      auto consider = [&](int t, const XY<T>& q) {
         const T dx = q.x - me.x, dy = q.y - me.y;
         const T d2 = dx * dx + dy * dy;
-        if (d2 > rmax2) continue;
-        const int k = ms.order[t];
-        const T rj = tt * (cur[2 * W + j] + cur[4 * W + j]);
-        if (d2 > M<T>::max_(rj, tt * (cur[2 * W + k] + cur[4 * W + k]))) continue;
-        const unsigned slotq = atomicAdd(&ms.counters[0], 1u);
-        const int a = j < k ? j : k, b = j < k ? k : j;
-        if (slotq < (unsigned)MAX_PAIRS) ms.pairs[slotq] = ((unsigned)a << 16) | (unsigned)b;
+        if (t < end && !(d2 > rmax2)) {
+          const int k = ms.order[t];
+          const T rj = tt * (cur[2 * W + j] + cur[4 * W + j]);
+          if (!(d2 > M<T>::max_(rj, tt * (cur[2 * W + k] + cur[4 * W + k])))) {
+            const unsigned slotq = atomicAdd(&ms.counters[0], 1u);
+            const int a = j < k ? j : k, b = j < k ? k : j;
+            if (slotq < (unsigned)MAX_PAIRS) ms.pairs[slotq] = ((unsigned)a << 16) | (unsigned)b;
+          }
+        }
+      };
+      // the usual case is 0-3 components behind s in its two cells: look at four positions at once
+      // (loads issued together; positions past `end` are ignored), then a loop for the rare rest
+      {
+        const int t0 = s + 1;
+        const int c1 = t0 + 1 < n ? t0 + 1 : n - 1, c2 = t0 + 2 < n ? t0 + 2 : n - 1, c3 = t0 + 3 < n ? t0 + 3 : n - 1;
+        const int c0 = t0 < n ? t0 : n - 1;
+        const XY<T> q0 = ms.sxy[c0], q1 = ms.sxy[c1], q2 = ms.sxy[c2], q3 = ms.sxy[c3];
+        consider(t0, q0);
+        consider(t0 + 1, q1);
+        consider(t0 + 2, q2);
+        consider(t0 + 3, q3);
       }
+      for (int t = s + 5; t < end; t++) consider(t, ms.sxy[t]);
     }
     __syncwarp();
   }
@@ -1437,11 +1458,29 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
           n_out += __popc(b);
         }
         __syncwarp();
-        const int P = next_pow2(n_out);
-        for (int k = n_out + lane; k < P; k += 32) k64[k] = 0ull;   // below every real key
-        __syncwarp();
-        if (n_out > 1) warp_bitonic_desc64(k64, P, lane);
-        for (int k = lane; k < n_out; k += 32) sorted[k] = (unsigned short)(0xffffffffu - (unsigned)(k64[k] & 0xffffffffull));
+        if (n_out <= 64) {
+          // rank sort: output position = number of larger keys (keys are distinct)
+          const unsigned long long k0 = lane < n_out ? k64[lane] : 0ull;
+          const unsigned long long k1 = lane + 32 < n_out ? k64[lane + 32] : 0ull;
+          int r0 = 0, r1 = 0;
+          if (n_out <= 32) {
+            for (int q = 0; q < n_out; q++) r0 += (k64[q] > k0) ? 1 : 0;
+          } else {
+            for (int q = 0; q < n_out; q++) {
+              const unsigned long long kq = k64[q];
+              r0 += (kq > k0) ? 1 : 0;
+              r1 += (kq > k1) ? 1 : 0;
+            }
+          }
+          if (lane < n_out) sorted[r0] = (unsigned short)(0xffffffffu - (unsigned)(k0 & 0xffffffffull));
+          if (lane + 32 < n_out) sorted[r1] = (unsigned short)(0xffffffffu - (unsigned)(k1 & 0xffffffffull));
+        } else {
+          const int P = next_pow2(n_out);
+          for (int k = n_out + lane; k < P; k += 32) k64[k] = 0ull;   // below every real key
+          __syncwarp();
+          warp_bitonic_desc64(k64, P, lane);
+          for (int k = lane; k < n_out; k += 32) sorted[k] = (unsigned short)(0xffffffffu - (unsigned)(k64[k] & 0xffffffffull));
+        }
       } else {
         for (int base = 0; base < n; base += 32) {
           const int k = base + lane;
@@ -1523,8 +1562,45 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
     if (threadIdx.x == 0) {
       double a = 0, b = 0;
       for (int k = 0; k < WARPS_PER_CTA; k++) { a += red[0][k]; b += red[1][k]; }
+      if (p.comm_world > 1) {
+        // ---- fused all-reduce: every rank writes its pair into slot [parity][rank] of EVERY rank's
+        // mailbox (remote stores over NVLink), then waits until its own mailbox holds this epoch from
+        // all ranks and adds them in rank order — the same bits on every GPU, no extra launch.
+        // Slots are double-buffered on the epoch's parity: a rank can be at most one step ahead.
+        const unsigned long long e = p.comm_epoch;
+        const int par = (int)(e & 1ull);
+        for (int r = 0; r < p.comm_world; r++) {
+          CommSlot* dst = reinterpret_cast<CommSlot*>(p.comm_peer[r]) + par * 8 + p.comm_rank;
+          *reinterpret_cast<volatile double*>(&dst->s1) = a;
+          *reinterpret_cast<volatile double*>(&dst->s2) = b;
+          __threadfence_system();
+          asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(&dst->epoch), "l"(e) : "memory");
+        }
+        const CommSlot* mine = reinterpret_cast<const CommSlot*>(p.comm_peer[p.comm_rank]) + par * 8;
+        double ta = 0, tb = 0;
+        bool ok = true;
+        unsigned long long t0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        for (int r = 0; r < p.comm_world && ok; r++) {
+          while (true) {
+            unsigned long long got;
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(got) : "l"(&mine[r].epoch) : "memory");
+            if (got == e) break;
+            unsigned long long t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > 2000000000ull) { ok = false; break; }   // 2 s: a peer never launched
+          }
+          if (ok) {
+            ta += *reinterpret_cast<const volatile double*>(&mine[r].s1);
+            tb += *reinterpret_cast<const volatile double*>(&mine[r].s2);
+          }
+        }
+        if (ok) { a = ta; b = tb; }
+        else { *p.comm_error = 1; a = __longlong_as_double(0x7ff8000000000000LL); b = a; }
+      }
       p.sums[0] = a;
       p.sums[1] = b;
+      red[0][0] = a;
       // publish the step statistics and re-arm the accumulators / queue for the next launch
       p.stats_out[0] = __ldcg(&p.totals[0]);
       p.stats_out[1] = __ldcg(&p.totals[1]);
@@ -1537,6 +1613,11 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
       p.istats[0] = 0; p.istats[1] = 0; p.istats[2] = 0; p.istats[3] = 0;
       *p.ticket = 0;
       *p.work_counter = 0;
+    }
+    if (p.fused_normalize) {   // ParticleFilter::normalizeWeights, in the same launch
+      __syncthreads();
+      const double total = red[0][0];
+      for (int i = threadIdx.x; i < p.N; i += blockDim.x) p.w_out[i] = __ldcg(p.w_out + i) / total;
     }
   }
 }

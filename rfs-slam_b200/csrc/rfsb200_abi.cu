@@ -55,6 +55,12 @@ struct rfsb200_ctx {
   unsigned long long* unused_alt = nullptr;   // resample target (swapped with unused)
   int* nfov_alt = nullptr;
   int* src_dev = nullptr;                     // [2][N] resample sources
+  // fused all-reduce over peer memory
+  void* comm_mail = nullptr;      // CommSlot[2][8] of this rank
+  void* comm_peer[8] = {};        // every rank's mailbox as seen from this process
+  int comm_rank = 0, comm_world = 1;
+  unsigned long long comm_epoch = 0;
+  int* comm_error = nullptr;
   int last_nZ = 0;                            // size of the measurement batch still held in Zdev
   int* flags = nullptr;
   double* sums = nullptr;                 // [2]
@@ -231,7 +237,7 @@ int configure_launch(rfsb200_ctx* c, int mf) {
 }
 
 template <typename T>
-int launch_update(rfsb200_ctx* c, int nZ, int out_idx) {
+int launch_update(rfsb200_ctx* c, int nZ, int out_idx, unsigned flags) {
   KParams<T> p{};
   const rfsb200_model_desc& m = c->model;
   const rfsb200_filter_cfg& f = c->cfg;
@@ -260,6 +266,13 @@ int launch_update(rfsb200_ctx* c, int nZ, int out_idx) {
   p.unused = c->unused; p.nfov = c->nfov; p.flags = c->flags;
   p.sums = c->sums; p.totals = c->totals; p.istats = c->istats; p.ticket = c->ticket; p.mstats = c->mstats;
   p.work_counter = c->work_counter; p.stats_out = c->stats_out;
+  p.comm_rank = c->comm_rank; p.comm_world = 1; p.fused_normalize = 0; p.comm_epoch = 0; p.comm_error = c->comm_error;
+  if (flags & RFSB200_UPDATE_FUSED_ALLREDUCE) {
+    p.comm_world = c->comm_world;
+    p.fused_normalize = 1;
+    p.comm_epoch = ++c->comm_epoch;
+    for (int r = 0; r < 8; r++) p.comm_peer[r] = c->comm_peer[r];
+  }
   const int mf = f.use_cluster_process ? 0 : 1;
   {
     int rc = configure_launch<T>(c, mf);
@@ -386,6 +399,10 @@ int rfsb200_create(rfsb200_ctx** out, const rfsb200_dims* d) {
     CU(c, cudaMalloc((void**)&c->unused, (size_t)c->N * 8));
     CU(c, cudaMalloc((void**)&c->nfov, (size_t)c->N * 4));
     CU(c, cudaMalloc((void**)&c->flags, (size_t)c->N * 4));
+    CU(c, cudaMalloc(&c->comm_mail, 2 * 8 * sizeof(CommSlot)));
+    CU(c, cudaMemset(c->comm_mail, 0xff, 2 * 8 * sizeof(CommSlot)));   // epoch = ~0: never matches
+    CU(c, cudaMalloc((void**)&c->comm_error, 4));
+    CU(c, cudaMemset(c->comm_error, 0, 4));
     CU(c, cudaMalloc((void**)&c->unused_alt, (size_t)c->N * 8));
     CU(c, cudaMalloc((void**)&c->nfov_alt, (size_t)c->N * 4));
     CU(c, cudaMalloc((void**)&c->src_dev, (size_t)c->N * 8));
@@ -440,6 +457,9 @@ int rfsb200_destroy(rfsb200_ctx* c) {
   cudaFree(c->pose_alt); cudaFree(c->pose_cov_alt);
   cudaFree(c->unused); cudaFree(c->nfov); cudaFree(c->flags);
   cudaFree(c->unused_alt); cudaFree(c->nfov_alt); cudaFree(c->src_dev);
+  for (int r = 0; r < c->comm_world; r++)
+    if (r != c->comm_rank && c->comm_peer[r]) cudaIpcCloseMemHandle(c->comm_peer[r]);
+  cudaFree(c->comm_mail); cudaFree(c->comm_error);
   cudaFree(c->sums); cudaFree(c->totals); cudaFree(c->istats); cudaFree(c->ticket);
   cudaFree(c->work_counter); cudaFree(c->stats_out); cudaFree(c->mstats);
   cudaFree(c->stg); cudaFree(c->offs); cudaFree(c->stg_small);
@@ -568,12 +588,14 @@ int rfsb200_update(rfsb200_ctx* c, const double* Z, int32_t nZ, uint32_t flags, 
   CU(c, cudaMemcpyAsync(c->Zdev, zsrc, (size_t)2 * nZ * c->tsize, cudaMemcpyHostToDevice, c->stream));
   CU(c, cudaEventRecord(c->zev[zslot_used], c->stream));
   const int out_idx = c->front ^ 1;
-  int rc = (c->prec == 32) ? launch_update<float>(c, nZ, out_idx) : launch_update<double>(c, nZ, out_idx);
+  if ((flags & RFSB200_UPDATE_FUSED_ALLREDUCE) && c->comm_world > 1 && !c->comm_peer[0])
+    return fail(c, RFSB200_ESTATE, "RFSB200_UPDATE_FUSED_ALLREDUCE before rfsb200_comm_connect");
+  int rc = (c->prec == 32) ? launch_update<float>(c, nZ, out_idx, flags) : launch_update<double>(c, nZ, out_idx, flags);
   if (rc) return rc;
   launches++;
   c->last_out = out_idx;
   c->last_nZ = nZ;
-  if (!(flags & RFSB200_UPDATE_NO_NORMALIZE)) {
+  if (!(flags & (RFSB200_UPDATE_NO_NORMALIZE | RFSB200_UPDATE_FUSED_ALLREDUCE))) {
     normalize_kernel<<<(c->N + 255) / 256, 256, 0, c->stream>>>(c->st[out_idx].weight, c->sums, c->N);
     CU(c, cudaGetLastError());
     launches++;
@@ -649,6 +671,46 @@ int rfsb200_resample(rfsb200_ctx* c, const int32_t* map_src, const int32_t* aux_
   if (c->pose_cov_mode == 2) std::swap(c->pose_cov, c->pose_cov_alt);
   c->front ^= 1;
   c->last_out = c->front;
+  return RFSB200_OK;
+}
+
+int rfsb200_comm_export(rfsb200_ctx* c, void* handle64) {
+  if (!c || !handle64) return fail(c, RFSB200_EINVAL, "NULL argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle is 64 bytes");
+  CU(c, cudaSetDevice(c->device));
+  cudaIpcMemHandle_t h;
+  CU(c, cudaIpcGetMemHandle(&h, c->comm_mail));
+  memcpy(handle64, &h, 64);
+  return RFSB200_OK;
+}
+
+int rfsb200_comm_connect(rfsb200_ctx* c, int32_t rank, int32_t world, const void* handles) {
+  if (!c || !handles) return fail(c, RFSB200_EINVAL, "NULL argument");
+  if (world < 1 || world > 8 || rank < 0 || rank >= world) return fail(c, RFSB200_EINVAL, "rank %d / world %d out of range (world <= 8)", rank, world);
+  CU(c, cudaSetDevice(c->device));
+  CU(c, cudaStreamSynchronize(c->stream));
+  for (int r = 0; r < world; r++) {
+    if (r == rank) { c->comm_peer[r] = c->comm_mail; continue; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const unsigned char*)handles + (size_t)r * 64, 64);
+    void* ptr = nullptr;
+    CU(c, cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    c->comm_peer[r] = ptr;
+  }
+  c->comm_rank = rank;
+  c->comm_world = world;
+  c->comm_epoch = 0;
+  return RFSB200_OK;
+}
+
+int rfsb200_comm_error(rfsb200_ctx* c, int32_t* flag) {
+  if (!c || !flag) return fail(c, RFSB200_EINVAL, "NULL argument");
+  CU(c, cudaSetDevice(c->device));
+  int f = 0;
+  CU(c, cudaMemcpyAsync(&f, c->comm_error, 4, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaMemsetAsync(c->comm_error, 0, 4, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  *flag = f;
   return RFSB200_OK;
 }
 

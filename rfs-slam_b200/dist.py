@@ -54,10 +54,21 @@ class ShardedUpdater:
     step(Z): local fused update kernel (no normalisation) -> all-reduce of the two weight sums on
     the same CUDA stream -> local normalisation kernel.  No other data-path collective exists."""
 
-    def __init__(self, updater, device=None, group=None):
+    def __init__(self, updater, device=None, group=None, fused: bool = False):
         import torch
+        import torch.distributed as dist
         self.up = updater
         self.group = group
+        self.fused = False
+        if fused and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            # exchange the CUDA IPC handles of the mailboxes once; afterwards the update kernel does the
+            # cross-GPU sum itself through peer memory (RFSB200_UPDATE_FUSED_ALLREDUCE)
+            world, rank = dist.get_world_size(group), dist.get_rank(group)
+            handles = [None] * world
+            dist.all_gather_object(handles, updater.comm_export(), group=group)
+            updater.comm_connect(rank, world, handles)
+            dist.barrier(group)
+        self.fused = bool(fused)   # on one rank the flag still saves the normalisation launch
         self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.sums = device_tensor_from_ptr(updater.weight_sums_device_ptr(), 2, self.device)
         # run the library on torch's current stream so kernels and the collective are ordered
@@ -65,6 +76,8 @@ class ShardedUpdater:
 
     def step(self, Z, flags: int = 0, want_stats: bool = False):
         from . import capi
+        if self.fused:   # one launch: update + cross-GPU sum over NVLink + normalisation
+            return self.up.update(Z, flags=flags | capi.UPDATE_FUSED_ALLREDUCE, want_stats=want_stats)
         so = self.up.update(Z, flags=flags | capi.UPDATE_NO_NORMALIZE, want_stats=want_stats)
         allreduce_sums(self.sums, self.group)
         self.up.normalize()

@@ -145,6 +145,20 @@ class PHDUpdater:
         wv = None if weight is None else np.array([weight], dtype=np.float64)
         _check(self.lib, self.ctx, self.lib.rfsb200_resample(self.ctx, capi.ptr(ms), capi.ptr(au), capi.ptr(wv)), "resample")
 
+    def comm_export(self) -> bytes:
+        h = (C.c_ubyte * 64)()
+        _check(self.lib, self.ctx, self.lib.rfsb200_comm_export(self.ctx, C.cast(h, C.c_void_p)), "comm_export")
+        return bytes(h)
+
+    def comm_connect(self, rank: int, world: int, handles: list[bytes]):
+        buf = (C.c_ubyte * (64 * world)).from_buffer_copy(b"".join(handles))
+        _check(self.lib, self.ctx, self.lib.rfsb200_comm_connect(self.ctx, rank, world, C.cast(buf, C.c_void_p)), "comm_connect")
+
+    def comm_error(self) -> bool:
+        f = C.c_int32()
+        _check(self.lib, self.ctx, self.lib.rfsb200_comm_error(self.ctx, C.byref(f)), "comm_error")
+        return bool(f.value)
+
     def weight_sums_device_ptr(self) -> int:
         p = C.c_void_p()
         _check(self.lib, self.ctx, self.lib.rfsb200_weight_sums_device(self.ctx, C.byref(p)), "weight_sums_device")

@@ -232,12 +232,12 @@ def test_large_partitions_are_flagged_and_summed_exactly(cuda_required):
     unflagged particles agree to tolerance."""
     from oracle import binding as ob
     from rfs_slam_b200 import synth
-    wl = synth.make_workload(N=64, nM=60, nZ=30, use_cluster_process=0, config_id=23, world="clumped",
+    wl = synth.make_workload(N=64, nM=48, nZ=24, use_cluster_process=0, config_id=23, world="clumped",
                              model=dict(Pd=0.7, clutter_intensity=5e-3), cfg=dict(eval_point_gaussian_weight=0.1))
     o = ob.run(wl, sort_mode=ob.SORT_STABLE)
     murty = (o.flags & 2) > 0
     assert murty.sum() >= 4, "workload no longer exercises the Murty branch"
-    so, cnt, mean, cov, w, pw, up = helpers.run_device(wl, precision=64)
+    so, cnt, mean, cov, w, pw, up = helpers.run_device(wl, precision=64, gm_capacity=128, work_capacity=256, z_capacity=24)
     f = up.get_flags()
     assert np.array_equal((f & 2) > 0, murty)
     assert so.n_murty == int(murty.sum()) and so.n_overflow == 0
@@ -247,3 +247,22 @@ def test_large_partitions_are_flagged_and_summed_exactly(cuda_required):
     assert (pw[murty] >= o.weight[murty] * (1 - 1e-9)).all()
     assert np.allclose(pw[murty], o.weight[murty], rtol=0.05)   # the 200 best carry almost all the mass
     up.close()
+
+
+def test_fused_normalisation_equals_two_launch_path(cuda_required):
+    """RFSB200_UPDATE_FUSED_ALLREDUCE on one rank: sums + normalisation inside the update kernel."""
+    from rfs_slam_b200 import capi, synth
+    from rfs_slam_b200.phd import PHDUpdater
+    wl = synth.make_workload(N=300, nM=80, nZ=16, use_cluster_process=1, config_id=81)
+    res = []
+    for flags in (capi.UPDATE_NO_COMMIT, capi.UPDATE_NO_COMMIT | capi.UPDATE_FUSED_ALLREDUCE):
+        up = PHDUpdater(wl.N, gm_capacity=128, precision=32, z_capacity=16)
+        up.load_workload(wl)
+        so = up.update(wl.Z, flags=flags)
+        res.append((so.n_launches, so.sum_w, up.get_weights(1)))
+        assert not up.comm_error()
+        up.close()
+    assert res[0][0] == 2 and res[1][0] == 1
+    assert res[0][1] == res[1][1]
+    assert np.array_equal(res[0][2], res[1][2])
+    assert res[1][2].sum() == pytest.approx(1.0, abs=1e-12)
