@@ -49,6 +49,7 @@ struct KParams {
   int N, cap, W, nZ, pose_cov_mode;
   int warp_bytes;  // shared memory per warp
   int mf_bytes;    // multi-feature scratch inside it
+  int n_eval_cap, zcap;   // sizes the multi-feature scratch was laid out for
   // state in / out
   const T* gm_in;
   const int* cnt_in;
@@ -768,17 +769,23 @@ __device__ inline double warp_permanent(const double* A, int n, int lane) {
 
 // ------------------------------------------------------------------------------------------------
 // shared-memory carve-up (bytes); host and device agree through these helpers
-//  per warp: planes A [NPL][W] | planes B [7][W] (multi-feature only) | merge scratch | aux u32[W] |
+//  per warp: planes [NPL][W] (NPL = 6, or 7 with weight_prev in multi-feature mode) | merge scratch | aux u32[W] |
 //            colsum T[MAX_Z] | evalIdx int[MAX_EVAL] | mbarrier | multi-feature scratch
 //  per CTA : the measurement batch + the two window tables of the corrector
 template <typename T>
-__host__ __device__ inline int mf_scratch_bytes(int n_eval, int zcap) {
+__host__ __device__ inline int mf_fixed_bytes(int n_eval, int zcap) {
   const int ltab = (n_eval * zcap + 3) & ~3;
   return (int)(8 * (MAX_EVAL + MAX_COMP + 2 * (1 << DP_MAXB)) + 4 * MAX_COMP + sizeof(T) * (MAX_EVAL * 8 + ltab) + 15) & ~15;
 }
+// multi-feature scratch: rowmask / components / DP tables / eval-point block / L table, then the 4
+// planes (inverse covariance, log normaliser) of the intensity evaluation
+template <typename T>
+__host__ __device__ inline int mf_scratch_bytes(int n_eval, int zcap, int W) {
+  return mf_fixed_bytes<T>(n_eval, zcap) + 4 * W * (int)sizeof(T);
+}
 template <typename T>
 __host__ __device__ inline int warp_bytes_for(int W, int multi_feature, int mf_bytes) {
-  const int planes = multi_feature ? 14 : 6;   // MF keeps a second 7-plane block for the sort
+  const int planes = multi_feature ? 7 : 6;   // MF carries weight_prev as a 7th plane
   int b = planes * W * (int)sizeof(T) + merge_scratch_bytes<T>(W) + W * 4 + MAX_Z * (int)sizeof(T) + MAX_EVAL * 4 + 16 +
           (multi_feature ? mf_bytes : 0);
   return (b + 127) & ~127;
@@ -807,8 +814,7 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
   unsigned char* zbin = reinterpret_cast<unsigned char*>(binp + 4);                   // [2*MAX_Z]
   unsigned char* wb = smem_raw + z_bytes<T>() + (size_t)warp * p.warp_bytes;
   T* bufA = reinterpret_cast<T*>(wb);
-  T* bufB = bufA + NPL * W;                           // only present in multi-feature mode
-  unsigned char* after = reinterpret_cast<unsigned char*>(MF ? bufB + 7 * W : bufB);
+  unsigned char* after = reinterpret_cast<unsigned char*>(bufA + NPL * W);
   unsigned* aux = reinterpret_cast<unsigned*>(after + merge_scratch_bytes<T>(W));  // [W]
   const MergeScratch<T> ms = carve_merge_scratch<T>(after, aux, W);
   T* colsum = reinterpret_cast<T*>(aux + W);                  // [MAX_Z]
@@ -891,7 +897,6 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
 
     const double w_prev_particle = p.w_in[pi];
     T* cur = bufA;
-    T* alt = bufB;
     int nM = p.cnt_in[pi];
     nM = nM < 0 ? 0 : (nM > p.cap ? p.cap : nM);
     int flags = 0;
@@ -1185,22 +1190,42 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
       if (nEvalCfg == 0) {
         weight_new = 4.9406564584124654e-324;  // denorm_min (:742-745, Q10)
       } else {
-        // sortByWeight (:746): weight descending, ties by position
+        // sortByWeight (:746): weight descending, ties by position.  Keys are sorted in the merge
+        // scratch, then every plane is permuted through one temporary plane.
         {
-          T* kw = alt + 6 * W;
-          const int P = next_pow2(n);
-          for (int k = lane; k < P; k += 32) {
-            kw[k] = (k < n) ? cur[5 * W + k] : -M<T>::inf();
-            aux[k] = (unsigned)k;
+          unsigned short* perm = ms.order;   // [W] sorted position -> current position
+          if constexpr (sizeof(T) == 4) {
+            unsigned long long* k64 = reinterpret_cast<unsigned long long*>(ms.keys);
+            const int P = next_pow2(n);
+            for (int k = lane; k < P; k += 32) {
+              // weights are >= 0 here: the bit pattern orders like the value; low word = ~position
+              k64[k] = (k < n) ? (((unsigned long long)__float_as_uint((float)cur[5 * W + k]) << 32) |
+                                  (unsigned long long)(0xffffffffu - (unsigned)k))
+                               : 0ull;
+            }
+            __syncwarp();
+            warp_bitonic_desc64(k64, P, lane);
+            for (int k = lane; k < n; k += 32) perm[k] = (unsigned short)(0xffffffffu - (unsigned)(k64[k] & 0xffffffffull));
+          } else {
+            T* kw = ms.keys;
+            const int P = next_pow2(n);
+            for (int k = lane; k < P; k += 32) {
+              kw[k] = (k < n) ? cur[5 * W + k] : -M<T>::inf();
+              aux[k] = (unsigned)k;
+            }
+            __syncwarp();
+            warp_bitonic(kw, aux, P, lane);
+            for (int k = lane; k < n; k += 32) perm[k] = (unsigned short)aux[k];
           }
           __syncwarp();
-          warp_bitonic(kw, aux, P, lane);
-          for (int pl = 0; pl < 6; pl++)
-            for (int k = lane; k < n; k += 32) alt[pl * W + k] = cur[pl * W + aux[k]];
-          __syncwarp();
-          for (int k = lane; k < n; k += 32) alt[6 * W + k] = cur[6 * W + aux[k]];
-          __syncwarp();
-          T* t = cur; cur = alt; alt = t;
+          T* tmp = reinterpret_cast<T*>(aux);   // [W] words; T = double uses mf scratch instead
+          if constexpr (sizeof(T) == 8) tmp = reinterpret_cast<T*>(mfs);   // >= W doubles, see mf_scratch_bytes
+          for (int pl = 0; pl < 7; pl++) {
+            for (int k = lane; k < n; k += 32) tmp[k] = cur[pl * W + perm[k]];
+            __syncwarp();
+            for (int k = lane; k < n; k += 32) cur[pl * W + k] = tmp[k];
+            __syncwarp();
+          }
         }
         // eval points (:747-762): sorted order, w >= min weight, raw Pd > 0, first nEvalCfg
         int nE = 0;
@@ -1229,52 +1254,67 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
         for (int m = lane; m < n; m += 32) { sw_prev += (double)cur[6 * W + m]; sw_now += (double)cur[5 * W + m]; }
         sw_prev = warp_sum(sw_prev);
         sw_now = warp_sum(sw_now);
-        // intensity at the eval points before / after the update (:776-800), log domain
-        T* ia = alt;            // inverse covariance + log pdf factor + log weights of every component
+        // intensity at the eval points before / after the update (:776-800):
+        //   v(e) = denorm_min + sum_m w_m N(x_e; x_m, P_m), once with the previous and once with the new weights.
+        // Per-component inverse covariance and log normaliser are precomputed (4 planes in the MF
+        // scratch); then ONE LANE PER EVAL POINT (two lanes, splitting the components, when there are
+        // at most 16 eval points) runs an online log-sum-exp over the components, whose data are
+        // broadcast reads.
+        T* ia = reinterpret_cast<T*>(mfs + mf_fixed_bytes<T>(p.n_eval_cap, p.zcap));   // [4][W]
         for (int m = lane; m < n; m += 32) {
-          T a = cur[2 * W + m], b = cur[3 * W + m], c = cur[4 * W + m];
-          T det = a * c - b * b;
-          T invdet = T(1) / det;
+          const T a = cur[2 * W + m], b = cur[3 * W + m], c = cur[4 * W + m];
+          const T det = a * c - b * b;
+          const T invdet = T(1) / det;
           ia[m] = c * invdet; ia[W + m] = -b * invdet; ia[2 * W + m] = a * invdet;
           ia[3 * W + m] = M<T>::log_(M<T>::TWO_PI * M<T>::sqrt_(det));
-          ia[4 * W + m] = M<T>::log_(cur[6 * W + m]);   // log w_prev (-inf for new Gaussians)
-          ia[5 * W + m] = M<T>::log_(cur[5 * W + m]);   // log w
         }
         __syncwarp();
         double lp_before = 0, lp_after = 0;
-        const T CUT = sizeof(T) == 4 ? T(25) : T(45);
-        const T LOG_DENORM_MIN = T(-744.4400719213812);
-        for (int e = 0; e < nE; e++) {
-          const int ei = evalIdx[e];
-          const T xe = cur[ei], ye = cur[W + ei];
+        {
+          const T CUT = sizeof(T) == 4 ? T(25) : T(45);
+          const T LOG_DENORM_MIN = T(-744.4400719213812);
+          const int groups = (nE <= 16) ? 2 : 1;
+          const int e = groups == 2 ? (lane & 15) : lane;
+          const int h = groups == 2 ? (lane >> 4) : 0;
           T mb = -M<T>::inf(), sb = 0, ma = -M<T>::inf(), sa = 0;
-          for (int m = lane; m < n; m += 32) {
-            const T dx = xe - cur[m], dy = ye - cur[W + m];
-            const T md2 = (dx * ia[m] + dy * ia[W + m]) * dx + (dx * ia[W + m] + dy * ia[2 * W + m]) * dy;
-            const T t = T(-0.5) * md2 - ia[3 * W + m];
-            const T lb = ia[4 * W + m] + t, la = ia[5 * W + m] + t;
-            if (lb > mb) { sb = sb * M<T>::exp_(mb - lb) + T(1); mb = lb; }
-            else if (lb > mb - CUT) sb += M<T>::exp_(lb - mb);
-            if (la > ma) { sa = sa * M<T>::exp_(ma - la) + T(1); ma = la; }
-            else if (la > ma - CUT) sa += M<T>::exp_(la - ma);
+          if (e < nE) {
+            const int ei = evalIdx[e];
+            const T xe = cur[ei], ye = cur[W + ei];
+            const int half = (n + groups - 1) / groups;
+            const int m0 = h * half, m1 = (m0 + half < n) ? m0 + half : n;
+            for (int m = m0; m < m1; m++) {
+              const T dx = xe - cur[m], dy = ye - cur[W + m];
+              const T i01 = ia[W + m];
+              const T md2 = (dx * ia[m] + dy * i01) * dx + (dx * i01 + dy * ia[2 * W + m]) * dy;
+              const T t = T(-0.5) * md2 - ia[3 * W + m];
+              const T wp = cur[6 * W + m], wn = cur[5 * W + m];
+              if (wp > T(0)) {
+                if (t > mb) { sb = sb * M<T>::exp_(mb - t) + wp; mb = t; }
+                else if (t > mb - CUT) sb += wp * M<T>::exp_(t - mb);
+              }
+              if (wn > T(0)) {
+                if (t > ma) { sa = sa * M<T>::exp_(ma - t) + wn; ma = t; }
+                else if (t > ma - CUT) sa += wn * M<T>::exp_(t - ma);
+              }
+            }
           }
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            T mo = __shfl_xor_sync(FULL, mb, o), so = __shfl_xor_sync(FULL, sb, o);
+          if (groups == 2) {   // combine the two halves of each eval point (lanes e and e + 16)
+            T mo = __shfl_xor_sync(FULL, mb, 16), so = __shfl_xor_sync(FULL, sb, 16);
             T mx = mo > mb ? mo : mb;
-            if (mx > -M<T>::inf()) { sb = sb * M<T>::exp_(mb - mx) + so * M<T>::exp_(mo - mx); }
+            if (mx > -M<T>::inf()) sb = sb * M<T>::exp_(mb - mx) + so * M<T>::exp_(mo - mx);
             mb = mx;
-            mo = __shfl_xor_sync(FULL, ma, o); so = __shfl_xor_sync(FULL, sa, o);
+            mo = __shfl_xor_sync(FULL, ma, 16); so = __shfl_xor_sync(FULL, sa, 16);
             mx = mo > ma ? mo : ma;
-            if (mx > -M<T>::inf()) { sa = sa * M<T>::exp_(ma - mx) + so * M<T>::exp_(mo - mx); }
+            if (mx > -M<T>::inf()) sa = sa * M<T>::exp_(ma - mx) + so * M<T>::exp_(mo - mx);
             ma = mx;
           }
-          T lvb = (mb > -M<T>::inf()) ? mb + M<T>::log_(sb) : LOG_DENORM_MIN;
-          T lva = (ma > -M<T>::inf()) ? ma + M<T>::log_(sa) : LOG_DENORM_MIN;
+          T lvb = (mb > -M<T>::inf() && sb > T(0)) ? mb + M<T>::log_(sb) : LOG_DENORM_MIN;
+          T lva = (ma > -M<T>::inf() && sa > T(0)) ? ma + M<T>::log_(sa) : LOG_DENORM_MIN;
           if (lvb < LOG_DENORM_MIN) lvb = LOG_DENORM_MIN;
           if (lva < LOG_DENORM_MIN) lva = LOG_DENORM_MIN;
-          lp_before += (double)lvb;
-          lp_after += (double)lva;
+          const bool mine = (e < nE) && (h == 0);
+          lp_before = warp_sum(mine ? (double)lvb : 0.0);
+          lp_after = warp_sum(mine ? (double)lva : 0.0);
         }
         __syncwarp();
         // rfsMeasurementLikelihood (:821-997): L table with the landmark covariance zeroed

@@ -218,7 +218,7 @@ int configure_launch_t(rfsb200_ctx* c) {
   const int n_eval = (MF && c->have_cfg) ? std::max(1, c->cfg.eval_point_count) : MAX_EVAL;
   if (c->cfg_mode_mf == mf && (!MF || c->cfg_n_eval == n_eval)) return RFSB200_OK;
   c->cfg_n_eval = n_eval;
-  c->mf_bytes = mf ? mf_scratch_bytes<T>(n_eval, c->dims.z_capacity) : 0;
+  c->mf_bytes = mf ? mf_scratch_bytes<T>(n_eval, c->dims.z_capacity, c->W) : 0;
   c->warp_bytes = warp_bytes_for<T>(c->W, mf, c->mf_bytes);
   c->smem_bytes = (size_t)z_bytes<T>() + (size_t)WARPS_PER_CTA * c->warp_bytes;
   if (c->smem_bytes > 227 * 1024) return fail(c, RFSB200_ECAPACITY, "work_capacity %d needs %zu B shared memory per CTA (> 227 KB)", c->W, c->smem_bytes);
@@ -279,6 +279,8 @@ int launch_update(rfsb200_ctx* c, int nZ, int out_idx, unsigned flags) {
     if (rc) return rc;
     p.warp_bytes = c->warp_bytes;
     p.mf_bytes = c->mf_bytes;
+    p.n_eval_cap = c->cfg_n_eval;
+    p.zcap = c->dims.z_capacity;
   }
   const bool prof = c->prof_n < c->prof_cap;
   if (prof) CU(c, cudaEventRecord(c->prof_ev[2 * c->prof_n], c->stream));

@@ -66,8 +66,16 @@ class ShardedUpdater:
             world, rank = dist.get_world_size(group), dist.get_rank(group)
             handles = [None] * world
             dist.all_gather_object(handles, updater.comm_export(), group=group)
-            updater.comm_connect(rank, world, handles)
-            dist.barrier(group)
+            ok = 1
+            try:
+                updater.comm_connect(rank, world, handles)
+            except Exception as e:   # e.g. no peer access between two of the GPUs
+                import sys
+                print(f"[rfs_slam_b200.dist] rank {rank}: peer mailboxes unavailable ({e}); using the NCCL all-reduce", file=sys.stderr)
+                ok = 0
+            flag = torch.tensor([ok], dtype=torch.int32, device=device if device is not None else "cuda")
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)   # all ranks take the same path
+            fused = bool(flag.item())
         self.fused = bool(fused)   # on one rank the flag still saves the normalisation launch
         self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.sums = device_tensor_from_ptr(updater.weight_sums_device_ptr(), 2, self.device)
