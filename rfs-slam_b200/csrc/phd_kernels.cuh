@@ -1371,33 +1371,53 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
           rowmask[lane] = rm;
         }
         __syncwarp();
-        // connected components, numbered by lowest vertex (rows first, then columns) like
-        // boost::connected_components (src/CostMatrix.cpp:98-109). Computed redundantly by all lanes.
+        // connected components of the (eval point, measurement) graph, numbered by their lowest vertex
+        // (rows first, then columns) like boost::connected_components (src/CostMatrix.cpp:98-109):
+        // label propagation, lane = row; a label converges to the smallest vertex of its component.
         int ncc = 0;
         {
-          unsigned doneR = 0;
-          unsigned long long doneC = 0;
-          for (int v = 0; v < nE + nZ; v++) {
+          unsigned* lc = reinterpret_cast<unsigned*>(f0);   // [MAX_Z] column labels (f0 is free until the DP)
+          for (int z = lane; z < nZ; z += 32) lc[z] = (unsigned)(nE + z);
+          const unsigned long long rm = (lane < nE) ? rowmask[lane] : 0ull;
+          unsigned lr = (lane < nE) ? (unsigned)lane : 0xffffffffu;
+          __syncwarp();
+          while (true) {
+            bool ch = false;
+            unsigned long long m = rm;
+            unsigned best = lr;
+            while (m) { const int z = __ffsll((long long)m) - 1; m &= m - 1; const unsigned l = lc[z]; best = l < best ? l : best; }
+            if (best < lr) { lr = best; ch = true; }
+            __syncwarp();
+            m = rm;
+            while (m) { const int z = __ffsll((long long)m) - 1; m &= m - 1; if (lc[z] > lr) { atomicMin(&lc[z], lr); ch = true; } }
+            __syncwarp();
+            if (!__any_sync(FULL, ch)) break;
+          }
+          const unsigned bR = __ballot_sync(FULL, lane < nE && lr == (unsigned)lane);          // row-rooted components
+          const unsigned bC0 = __ballot_sync(FULL, lane < nZ && lc[lane < nZ ? lane : 0] == (unsigned)(nE + lane));
+          const unsigned bC1 = __ballot_sync(FULL, lane + 32 < nZ && lc[lane + 32 < nZ ? lane + 32 : 0] == (unsigned)(nE + lane + 32));
+          const int nRowRoots = __popc(bR);
+          ncc = nRowRoots + __popc(bC0) + __popc(bC1);
+          // masks of the row-rooted components: lane c takes the c-th root
+          {
+            const int root = (lane < nRowRoots) ? (int)__fns(bR, 0, lane + 1) : -1;
             unsigned cr = 0;
-            unsigned long long cc = 0;
-            if (v < nE) { if ((doneR >> v) & 1u) continue; cr = 1u << v; }
-            else { const int z = v - nE; if ((doneC >> z) & 1ull) continue; cc = 1ull << z; }
-            if (v < nE) {
-              bool grow = true;
-              while (grow) {
-                grow = false;
-                unsigned m = cr;
-                unsigned long long nc = cc;
-                while (m) { const int r = __ffs(m) - 1; m &= m - 1; nc |= rowmask[r]; }
-                unsigned nr = cr;
-                for (int r = 0; r < nE; r++) if (rowmask[r] & nc) nr |= 1u << r;
-                if (nr != cr || nc != cc) { cr = nr; cc = nc; grow = true; }
-              }
+            for (int e = 0; e < nE; e++) {
+              const unsigned le = __shfl_sync(FULL, lr, e);
+              if ((int)le == root) cr |= 1u << e;
             }
-            // a column reached here is isolated (otherwise a row would have claimed it already)
-            doneR |= cr; doneC |= cc;
-            if (ncc < MAX_COMP && lane == 0) { compR[ncc] = cr; compC[ncc] = cc; }
-            ncc++;
+            unsigned long long cc = 0;
+            for (int z = 0; z < nZ; z++) if ((int)lc[z] == root) cc |= 1ull << z;
+            if (lane < nRowRoots) { compR[lane] = cr; compC[lane] = cc; }
+          }
+          // isolated columns are components of their own, after all the row-rooted ones
+          if ((bC0 >> lane) & 1u) {
+            const int idx = nRowRoots + __popc(bC0 & ((1u << lane) - 1u));
+            compR[idx] = 0u; compC[idx] = 1ull << lane;
+          }
+          if ((bC1 >> lane) & 1u) {
+            const int idx = nRowRoots + __popc(bC0) + __popc(bC1 & ((1u << lane) - 1u));
+            compR[idx] = 0u; compC[idx] = 1ull << (lane + 32);
           }
         }
         __syncwarp();
@@ -1405,59 +1425,114 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
         int combinedZero = -1, nMerged = 0;
         unsigned zeroR = 0;
         unsigned long long zeroC = 0;
-        for (int c = 0; c < ncc; c++) {
-          const unsigned cr = compR[c];
-          const unsigned long long cc = compC[c];
-          if (cr == 0 || cc == 0) {
-            if (combinedZero == -1) { combinedZero = c; zeroR = cr; zeroC = cc; }
-            else { zeroR |= cr; zeroC |= cc; nMerged++; }
+        {
+          int nOne = 0;
+          for (int cb = 0; cb < ncc; cb += 32) {
+            const int c = cb + lane;
+            unsigned cr = 0;
+            unsigned long long cc = 0;
+            bool one = false;
+            if (c < ncc) { cr = compR[c]; cc = compC[c]; one = (cr == 0u) || (cc == 0ull); }
+            const unsigned bo = __ballot_sync(FULL, one);
+            if (bo && combinedZero < 0) combinedZero = cb + __ffs(bo) - 1;
+            nOne += __popc(bo);
+            zeroR |= __reduce_or_sync(FULL, one ? cr : 0u);
+            zeroC |= (unsigned long long)__reduce_or_sync(FULL, one ? (unsigned)(cc & 0xffffffffull) : 0u) |
+                     ((unsigned long long)__reduce_or_sync(FULL, one ? (unsigned)(cc >> 32) : 0u) << 32);
           }
+          nMerged = nOne > 0 ? nOne - 1 : 0;
         }
         const int nP = ncc - nMerged;
+        // Partition likelihoods (Q6: original labels, only p < nP are visited).  Lane-parallel: the
+        // zero partition and partitions with a single row or a single column have closed forms;
+        // the rest go through the warp-wide subset DP (or the matrix-permanent identity).
         double logL = 0;
-        for (int pp = 0; pp < nP; pp++) {   // Q6: original labels, only p < nP are visited
-          double pl;
-          if (pp == combinedZero) {   // :891-900 (Q5: Pd, not 1-Pd)
-            pl = 0;  // log domain here
-            unsigned m = zeroR;
-            while (m) { const int r = __ffs(m) - 1; m &= m - 1; pl += log((double)evalPd[r]); }
-            pl += (double)__popcll(zeroC) * p.log_kappa;
-            logL += pl;
-          } else {
-            const unsigned cr = compR[pp];
-            const unsigned long long cc = compC[pp];
-            const int nR = __popc(cr), nC = __popcll(cc);
-            if (nR + nC > 8) flags |= FLAG_MURTY;
-            const int b = nR < nC ? nR : nC;
-            if (b > DP_MAXB) { flags |= FLAG_DP_OVERFLOW; continue; }
-            if (p.sum_method == 1 && nR + nC <= 12) {
-              // MatPerm path: sum = (prod kappa) * perm([[L/kappa, diag(1-Pd)],[ones]]) / nC!
-              const int nn = nR + nC;
-              double* Am = f0;   // nn*nn <= 144 doubles  (f0/f1 hold 256)
-              int ridx[12], cidx[12];
-              { int k = 0; unsigned m = cr; while (m) { ridx[k++] = __ffs(m) - 1; m &= m - 1; }
-                k = 0; unsigned long long mc = cc; while (mc) { cidx[k++] = __ffsll((long long)mc) - 1; mc &= mc - 1; } }
-              const double kap = exp(p.log_kappa);
-              for (int k = lane; k < nn * nn; k += 32) {
-                const int r = k / nn, c = k - r * nn;
-                double v;
-                if (r < nR) {
-                  if (c < nC) v = (double)L[ridx[r] * nZ + cidx[c]] / kap;
-                  else v = (c - nC == r) ? 1.0 - (double)evalPd[ridx[r]] : 0.0;
-                } else v = 1.0;
-                Am[k] = v;
+        {
+          const double kap = exp(p.log_kappa);
+          double mylog = 0;
+          for (int pb = 0; pb < nP; pb += 32) {
+            const int pp = pb + lane;
+            bool hard = false;
+            if (pp < nP) {
+              if (pp == combinedZero) {   // :891-900 (Q5: Pd, not 1-Pd)
+                unsigned m = zeroR;
+                while (m) { const int r = __ffs(m) - 1; m &= m - 1; mylog += log((double)evalPd[r]); }
+                mylog += (double)__popcll(zeroC) * p.log_kappa;
+              } else {
+                const unsigned cr = compR[pp];
+                const unsigned long long cc = compC[pp];
+                const int nR = __popc(cr), nC = __popcll(cc);
+                if (nR + nC > 8) flags |= FLAG_MURTY;
+                if (p.sum_method == 0 && nR == 1) {
+                  // one eval point: missed (all measurements clutter) or detected by one of them
+                  const int r = __ffs(cr) - 1;
+                  double sumL = 0;
+                  unsigned long long m = cc;
+                  while (m) { const int c = __ffsll((long long)m) - 1; m &= m - 1; sumL += (double)L[r * nZ + c]; }
+                  double kpow = 1;   // kappa^(nC-1)
+                  for (int k = 1; k < nC; k++) kpow *= kap;
+                  const double miss = 1.0 - (double)evalPd[r];
+                  mylog += log(nC == 0 ? miss : miss * kpow * kap + kpow * sumL);   // nC == 0: a one-sided component revisited (Q6)
+                } else if (p.sum_method == 0 && nC == 1) {
+                  // one measurement: clutter (all eval points missed) or it detects one of them
+                  const int c = __ffsll((long long)cc) - 1;
+                  double allmiss = 1;
+                  unsigned m = cr;
+                  while (m) { const int r = __ffs(m) - 1; m &= m - 1; allmiss *= 1.0 - (double)evalPd[r]; }
+                  double tot = kap * allmiss;
+                  m = cr;
+                  while (m) {
+                    const int r = __ffs(m) - 1; m &= m - 1;
+                    double others = 1;
+                    unsigned m2 = cr & ~(1u << r);
+                    while (m2) { const int r2 = __ffs(m2) - 1; m2 &= m2 - 1; others *= 1.0 - (double)evalPd[r2]; }
+                    tot += (double)L[r * nZ + c] * others;
+                  }
+                  mylog += log(tot);
+                } else {
+                  hard = true;
+                }
               }
+            }
+            unsigned bh = __ballot_sync(FULL, hard);
+            while (bh) {   // warp-wide paths, one partition at a time
+              const int hp = pb + __ffs(bh) - 1;
+              bh &= bh - 1;
+              const unsigned cr = compR[hp];
+              const unsigned long long cc = compC[hp];
+              const int nR = __popc(cr), nC = __popcll(cc);
+              const int bsmall = nR < nC ? nR : nC;
+              if (bsmall > DP_MAXB) { flags |= FLAG_DP_OVERFLOW; continue; }
               __syncwarp();
-              double perm = warp_permanent(Am, nn, lane);
-              double fact = 1; for (int k = 2; k <= nC; k++) fact *= k;
-              pl = perm / fact;
-              logL += log(pl) + (double)nC * p.log_kappa;
-              __syncwarp();
-            } else {
-              pl = partition_dp<T>(L, nZ, cr, cc, evalPd, exp(p.log_kappa), f0, f1, lane);
-              logL += log(pl);
+              if (p.sum_method == 1 && nR + nC <= 12) {
+                // MatPerm path: sum = (prod kappa) * perm([[L/kappa, diag(1-Pd)],[ones]]) / nC!
+                const int nn = nR + nC;
+                double* Am = f0;   // nn*nn <= 144 doubles  (f0/f1 hold 256)
+                int ridx[12], cidx[12];
+                { int k = 0; unsigned m = cr; while (m) { ridx[k++] = __ffs(m) - 1; m &= m - 1; }
+                  k = 0; unsigned long long mc = cc; while (mc) { cidx[k++] = __ffsll((long long)mc) - 1; mc &= mc - 1; } }
+                for (int k = lane; k < nn * nn; k += 32) {
+                  const int r = k / nn, c = k - r * nn;
+                  double v;
+                  if (r < nR) {
+                    if (c < nC) v = (double)L[ridx[r] * nZ + cidx[c]] / kap;
+                    else v = (c - nC == r) ? 1.0 - (double)evalPd[ridx[r]] : 0.0;
+                  } else v = 1.0;
+                  Am[k] = v;
+                }
+                __syncwarp();
+                const double perm = warp_permanent(Am, nn, lane);
+                double fact = 1; for (int k = 2; k <= nC; k++) fact *= k;
+                logL += log(perm / fact) + (double)nC * p.log_kappa;
+                __syncwarp();
+              } else {
+                const double pl = partition_dp<T>(L, nZ, cr, cc, evalPd, kap, f0, f1, lane);
+                logL += log(pl);
+              }
             }
           }
+          logL += warp_sum(mylog);
+          flags = __reduce_or_sync(FULL, (unsigned)flags);
         }
         logL -= p.log_clutter_integral;
         // :808-812
