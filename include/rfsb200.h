@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define RFSB200_ABI_VERSION 1
+#define RFSB200_ABI_VERSION 2
 
 /* ---- error codes -------------------------------------------------------------- */
 #define RFSB200_OK            0
@@ -47,7 +47,11 @@ extern "C" {
 #define RFSB200_ENODEVICE    -7  /* no CUDA device: there is NO CPU fallback          */
 
 /* ---- measurement-model ids (plugin classes of the reference) ---------------- */
-#define RFSB200_MODEL_RNGBRG 1   /* rfs::MeasurementModel_RngBrg + KalmanFilter_RngBrg */
+#define RFSB200_MODEL_RNGBRG 1   /* rfs::MeasurementModel_RngBrg + KalmanFilter_RngBrg: 2-D landmarks (x, y),
+                                    2-D measurements (range, bearing)                              */
+#define RFSB200_MODEL_VICTORIAPARK 2 /* rfs::MeasurementModel_VictoriaPark + KalmanFilter_VictoriaPark
+                                    (BASELINE config 5): 3-D landmarks (x, y, diameter), 3-D
+                                    measurements (range, bearing, diameter); P_D from the lidar scan */
 
 /* ---- update flags -------------------------------------------------------------- */
 #define RFSB200_UPDATE_DEFAULT    0u
@@ -70,8 +74,8 @@ typedef struct rfsb200_dims {
   int32_t work_capacity;  /* max Gaussians per particle inside a step: inputs + Gaussians
                              created by the corrector (>= gm_capacity, <= 1024)            */
   int32_t z_capacity;     /* max measurements per update (<= 64)                            */
-  int32_t lmk_dim;        /* 2                                                              */
-  int32_t meas_dim;       /* 2                                                              */
+  int32_t lmk_dim;        /* 2 (RngBrg) or 3 (VictoriaPark)                                 */
+  int32_t meas_dim;       /* = lmk_dim                                                      */
   int32_t pose_dim;       /* 3                                                              */
   int32_t device;         /* CUDA device ordinal                                            */
   int32_t precision;      /* 32 = fp32 SoA (product), 64 = fp64 SoA (verification)          */
@@ -97,7 +101,21 @@ typedef struct rfsb200_model_desc {
   double  range_buffer;        /* config.rangeLimBuffer_                                        */
   double  innov_thr_range;     /* KalmanFilter_RngBrg config.rangeInnovationThreshold_  (<=0 off)*/
   double  innov_thr_bearing;   /* KalmanFilter_RngBrg config.bearingInnovationThreshold_ (<=0 off)*/
-  double  reserved[8];
+  /* ---- RFSB200_MODEL_VICTORIAPARK only (MeasurementModel_VictoriaPark::Config,
+   *      include/MeasurementModel_VictoriaPark.hpp:148-156; setNoise(R, Slb) src/...VictoriaPark.cpp:66-72;
+   *      setLaserScan :268-281).  For this model R is the full 3x3, Pd / range_buffer are unused,
+   *      clutter_intensity = expectedClutterNumber_ / FoVArea(scan) and clutter_integral =
+   *      expectedClutterNumber_, both as the host plugin evaluates them. ---- */
+  double  bearing_min;         /* config.bearingLimitMin_ (rad)                                 */
+  double  bearing_max;         /* config.bearingLimitMax_ (rad)                                 */
+  double  Slb;                 /* laser bearing variance: S_dd = P_dd + R_dd + r^2 * Slb        */
+  double  buffer_zone_pd;      /* config.bufferZonePd_                                          */
+  double  pd_table[16];        /* config.probabilityOfDetection_[k], k = lidar points on the trunk */
+  int32_t pd_table_n;          /* entries of pd_table (1..16)                                   */
+  int32_t scan_n;              /* entries of scan (<= 720)                                      */
+  const double* scan;          /* laserscan_ (host pointer, copied by rfsb200_set_model); ranges
+                                  at half-degree steps, 0 = no return                           */
+  double  reserved[4];
 } rfsb200_model_desc;
 
 /* Mirror of rfs::RBPHDFilter::Config (include/RBPHDFilter.hpp:90-146), update-path fields only. */

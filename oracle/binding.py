@@ -59,6 +59,14 @@ def _load(which: str):
     fn = getattr(lib, "phd_oracle_update" if which == "oracle" else "phd_ref_update")
     fn.restype = C.c_int
     fn.argtypes = [C.POINTER(PhdIO)]
+    for name in ("phd_oracle_update_vp", "phd_ref_update_vp"):
+        if hasattr(lib, name):
+            getattr(lib, name).restype = C.c_int
+            getattr(lib, name).argtypes = [C.POINTER(PhdIO)]
+    for name in ("phd_oracle_vp_pd", "phd_ref_vp_pd"):
+        if hasattr(lib, name):
+            getattr(lib, name).restype = C.c_double
+            getattr(lib, name).argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     if which == "oracle":
         lib.phd_oracle_permanent.restype = C.c_double
         lib.phd_oracle_permanent.argtypes = [C.c_void_p, C.c_int]
@@ -114,6 +122,10 @@ def run(wl, *, which: str = "oracle", stage: int = STAGE_FULL, sort_mode: int = 
     capi = _capi()
     lib, fn = _load(which)
     N = wl.N
+    D = wl.dim                      # 2: RngBrg, 3: VictoriaPark
+    NC = D * (D + 1) // 2
+    if D == 3:
+        fn = lib.phd_oracle_update_vp if which == "oracle" else lib.phd_ref_update_vp
     total_in = int(wl.count.sum())
     cap_total = int(total_in * cap_factor) + 64 * N + 1024
     md = capi.model_desc(wl.model)
@@ -124,7 +136,7 @@ def run(wl, *, which: str = "oracle", stage: int = STAGE_FULL, sort_mode: int = 
                 w_in=np.ascontiguousarray(wl.w, dtype=np.float64),
                 pose=np.ascontiguousarray(wl.pose, dtype=np.float64),
                 weight_in=np.ascontiguousarray(wl.weight, dtype=np.float64),
-                Z=np.ascontiguousarray(wl.Z, dtype=np.float64).reshape(-1, 2))
+                Z=np.ascontiguousarray(wl.Z, dtype=np.float64).reshape(-1, D))
     pose_cov = None if wl.pose_cov is None else np.ascontiguousarray(wl.pose_cov, dtype=np.float64)
     if pose_cov is None:
         mode = 0
@@ -132,8 +144,8 @@ def run(wl, *, which: str = "oracle", stage: int = STAGE_FULL, sort_mode: int = 
         mode = 1
     else:
         mode = 2
-    out = dict(count_out=np.zeros(N, np.int32), mean_out=np.zeros((cap_total, 2)),
-               cov_out=np.zeros((cap_total, 3)), w_out=np.zeros(cap_total), wprev_out=np.zeros(cap_total),
+    out = dict(count_out=np.zeros(N, np.int32), mean_out=np.zeros((cap_total, D)),
+               cov_out=np.zeros((cap_total, NC)), w_out=np.zeros(cap_total), wprev_out=np.zeros(cap_total),
                weight_out=np.zeros(N), unused_mask=np.zeros(N, np.uint64), n_in_fov=np.zeros(N, np.int32),
                flags=np.zeros(N, np.int32))
     io = PhdIO()
@@ -159,6 +171,20 @@ def run(wl, *, which: str = "oracle", stage: int = STAGE_FULL, sort_mode: int = 
     return Result(out["count_out"], out["mean_out"][:tot].copy(), out["cov_out"][:tot].copy(),
                   out["w_out"][:tot].copy(), out["wprev_out"][:tot].copy(), out["weight_out"],
                   out["unused_mask"], out["n_in_fov"], out["flags"], io.elapsed_s)
+
+
+def vp_pd(model: dict, pose, lx, lcov6, which: str = "oracle"):
+    """MeasurementModel_VictoriaPark::probabilityOfDetection for one landmark -> (Pd, close)."""
+    capi = _capi()
+    lib, _ = _load(which)
+    md = capi.model_desc(model)
+    pose = np.ascontiguousarray(pose, dtype=np.float64)
+    lx = np.ascontiguousarray(lx, dtype=np.float64)
+    lc = np.ascontiguousarray(lcov6, dtype=np.float64)
+    close = C.c_int(0)
+    f = lib.phd_oracle_vp_pd if which == "oracle" else lib.phd_ref_vp_pd
+    pd = f(C.addressof(md), pose.ctypes.data, lx.ctypes.data, lc.ctypes.data, C.addressof(close))
+    return float(pd), bool(close.value)
 
 
 def permanent(A: np.ndarray, which: str = "oracle") -> float:

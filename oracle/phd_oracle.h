@@ -65,6 +65,16 @@ typedef struct phd_io {
 
 int phd_oracle_update(phd_io* io);
 
+/* Victoria Park plugin set (model_id RFSB200_MODEL_VICTORIAPARK): same struct with 3-D arrays —
+ * mean [..][3], cov [..][6] (xx,xy,xz,yy,yz,zz), Z [nZ][3]; pose_cov is ignored (the model builds
+ * a zero-covariance pose, src/MeasurementModel_VictoriaPark.cpp:112-114).
+ *   phd_oracle_update_vp (oracle/phd_oracle_vp.cpp)   restatement
+ *   phd_ref_update_vp    (oracle/ref_harness_vp.cpp)  the reference's own sources */
+int phd_oracle_update_vp(phd_io* io);
+/* MeasurementModel_VictoriaPark::probabilityOfDetection for one landmark (lcov6 = upper triangle) */
+double phd_oracle_vp_pd(const rfsb200_model_desc* md, const double* pose, const double* lx,
+                        const double* lcov6, int* close_out);
+
 /* rfs::MatPerm::calc restatement (src/MatrixPermanent.cpp:41-113); A row-major n x n */
 double phd_oracle_permanent(const double* A, int n);
 

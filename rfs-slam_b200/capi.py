@@ -35,7 +35,11 @@ class ModelDesc(C.Structure):
                 ("Pd", C.c_double), ("clutter_intensity", C.c_double), ("clutter_integral", C.c_double),
                 ("range_min", C.c_double), ("range_max", C.c_double), ("range_buffer", C.c_double),
                 ("innov_thr_range", C.c_double), ("innov_thr_bearing", C.c_double),
-                ("reserved", C.c_double * 8)]
+                # RFSB200_MODEL_VICTORIAPARK only
+                ("bearing_min", C.c_double), ("bearing_max", C.c_double), ("Slb", C.c_double),
+                ("buffer_zone_pd", C.c_double), ("pd_table", C.c_double * 16),
+                ("pd_table_n", C.c_int32), ("scan_n", C.c_int32), ("scan", C.c_void_p),
+                ("reserved", C.c_double * 4)]
 
 
 class FilterCfg(C.Structure):
@@ -58,19 +62,30 @@ class StepOut(C.Structure):
                 ("elapsed_us", C.c_float), ("n_merge_redo", C.c_int32), ("reserved", C.c_int32 * 6)]
 
 
+MODEL_RNGBRG, MODEL_VICTORIAPARK = 1, 2
+
+
 def model_desc(md: dict) -> ModelDesc:
+    """dict -> rfsb200_model_desc.  For the Victoria Park model the returned struct keeps the scan
+    array alive (d._scan) because the descriptor only carries a pointer to it."""
     d = ModelDesc()
     d.model_id = int(md.get("model_id", 1))
-    R = list(md["R"])
-    if len(R) == 4:  # 2x2 row-major -> first 4 slots (row-major meas_dim x meas_dim)
-        for i, v in enumerate(R):
-            d.R[i] = float(v)
-    else:
-        for i, v in enumerate(R):
-            d.R[i] = float(v)
+    for i, v in enumerate(list(md["R"])):   # row-major meas_dim x meas_dim
+        d.R[i] = float(v)
     for k in ("Pd", "clutter_intensity", "clutter_integral", "range_min", "range_max", "range_buffer",
               "innov_thr_range", "innov_thr_bearing"):
-        setattr(d, k, float(md[k]))
+        setattr(d, k, float(md.get(k, 0.0)))
+    if d.model_id == MODEL_VICTORIAPARK:
+        for k in ("bearing_min", "bearing_max", "Slb", "buffer_zone_pd"):
+            setattr(d, k, float(md[k]))
+        tab = list(md["pd_table"])
+        d.pd_table_n = len(tab)
+        for i, v in enumerate(tab):
+            d.pd_table[i] = float(v)
+        scan = np.ascontiguousarray(md["scan"], dtype=np.float64)
+        d._scan = scan
+        d.scan_n = int(scan.shape[0])
+        d.scan = scan.ctypes.data
     return d
 
 

@@ -768,6 +768,293 @@ __device__ inline double warp_permanent(const double* A, int n, int lane) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// S5 helper shared by the 2-D and the Victoria Park kernels: rfsMeasurementLikelihood's partition
+// logic (include/RBPHDFilter.hpp:866-994, src/CostMatrix.cpp:92-227) on a likelihood table
+// L [nE][nZ] (0 = no edge) held in shared memory.  Returns sum over the visited partitions of
+// log(partition likelihood) — the caller subtracts log(clutter integral).  Whole warp; scratch:
+// rowmask [MAX_EVAL], compC [MAX_COMP], f0 / f1 [1 << DP_MAXB], compR [MAX_COMP].
+template <typename T>
+__device__ __forceinline__ double mf_partition_loglik(const T* L, const T* evalPd, int nE, int nZ,
+                                                      unsigned long long* rowmask, unsigned long long* compC,
+                                                      double* f0, double* f1, unsigned* compR, int sum_method,
+                                                      double log_kappa, int& flags, int lane) {
+  double logL = 0;
+  if (lane < nE) {
+    unsigned long long rm = 0;
+    for (int z = 0; z < nZ; z++) if (L[lane * nZ + z] != T(0)) rm |= (1ull << z);
+    rowmask[lane] = rm;
+  }
+  __syncwarp();
+  // connected components of the (eval point, measurement) graph, numbered by their lowest vertex
+  // (rows first, then columns) like boost::connected_components (src/CostMatrix.cpp:98-109):
+  // label propagation, lane = row; a label converges to the smallest vertex of its component.
+  int ncc = 0;
+  {
+    unsigned* lc = reinterpret_cast<unsigned*>(f0);   // [MAX_Z] column labels (f0 is free until the DP)
+    for (int z = lane; z < nZ; z += 32) lc[z] = (unsigned)(nE + z);
+    const unsigned long long rm = (lane < nE) ? rowmask[lane] : 0ull;
+    unsigned lr = (lane < nE) ? (unsigned)lane : 0xffffffffu;
+    __syncwarp();
+    while (true) {
+      bool ch = false;
+      unsigned long long m = rm;
+      unsigned best = lr;
+      while (m) { const int z = __ffsll((long long)m) - 1; m &= m - 1; const unsigned l = lc[z]; best = l < best ? l : best; }
+      if (best < lr) { lr = best; ch = true; }
+      __syncwarp();
+      m = rm;
+      while (m) { const int z = __ffsll((long long)m) - 1; m &= m - 1; if (lc[z] > lr) { atomicMin(&lc[z], lr); ch = true; } }
+      __syncwarp();
+      if (!__any_sync(FULL, ch)) break;
+    }
+    const unsigned bR = __ballot_sync(FULL, lane < nE && lr == (unsigned)lane);          // row-rooted components
+    const unsigned bC0 = __ballot_sync(FULL, lane < nZ && lc[lane < nZ ? lane : 0] == (unsigned)(nE + lane));
+    const unsigned bC1 = __ballot_sync(FULL, lane + 32 < nZ && lc[lane + 32 < nZ ? lane + 32 : 0] == (unsigned)(nE + lane + 32));
+    const int nRowRoots = __popc(bR);
+    ncc = nRowRoots + __popc(bC0) + __popc(bC1);
+    // masks of the row-rooted components: lane c takes the c-th root
+    {
+      const int root = (lane < nRowRoots) ? (int)__fns(bR, 0, lane + 1) : -1;
+      unsigned cr = 0;
+      for (int e = 0; e < nE; e++) {
+        const unsigned le = __shfl_sync(FULL, lr, e);
+        if ((int)le == root) cr |= 1u << e;
+      }
+      unsigned long long cc = 0;
+      for (int z = 0; z < nZ; z++) if ((int)lc[z] == root) cc |= 1ull << z;
+      if (lane < nRowRoots) { compR[lane] = cr; compC[lane] = cc; }
+    }
+    // isolated columns are components of their own, after all the row-rooted ones
+    if ((bC0 >> lane) & 1u) {
+      const int idx = nRowRoots + __popc(bC0 & ((1u << lane) - 1u));
+      compR[idx] = 0u; compC[idx] = 1ull << lane;
+    }
+    if ((bC1 >> lane) & 1u) {
+      const int idx = nRowRoots + __popc(bC0) + __popc(bC1 & ((1u << lane) - 1u));
+      compR[idx] = 0u; compC[idx] = 1ull << (lane + 32);
+    }
+  }
+  __syncwarp();
+  // CostMatrixGeneral::partition (:111-144): one-sided components fold into the first one
+  int combinedZero = -1, nMerged = 0;
+  unsigned zeroR = 0;
+  unsigned long long zeroC = 0;
+  {
+    int nOne = 0;
+    for (int cb = 0; cb < ncc; cb += 32) {
+      const int c = cb + lane;
+      unsigned cr = 0;
+      unsigned long long cc = 0;
+      bool one = false;
+      if (c < ncc) { cr = compR[c]; cc = compC[c]; one = (cr == 0u) || (cc == 0ull); }
+      const unsigned bo = __ballot_sync(FULL, one);
+      if (bo && combinedZero < 0) combinedZero = cb + __ffs(bo) - 1;
+      nOne += __popc(bo);
+      zeroR |= __reduce_or_sync(FULL, one ? cr : 0u);
+      zeroC |= (unsigned long long)__reduce_or_sync(FULL, one ? (unsigned)(cc & 0xffffffffull) : 0u) |
+               ((unsigned long long)__reduce_or_sync(FULL, one ? (unsigned)(cc >> 32) : 0u) << 32);
+    }
+    nMerged = nOne > 0 ? nOne - 1 : 0;
+  }
+  const int nP = ncc - nMerged;
+  // Partition likelihoods (Q6: original labels, only p < nP are visited).  Lane-parallel: the
+  // zero partition and partitions with a single row or a single column have closed forms;
+  // the rest go through the warp-wide subset DP (or the matrix-permanent identity).
+  {
+    const double kap = exp(log_kappa);
+    double mylog = 0;
+    for (int pb = 0; pb < nP; pb += 32) {
+      const int pp = pb + lane;
+      bool hard = false;
+      if (pp < nP) {
+        if (pp == combinedZero) {   // :891-900 (Q5: Pd, not 1-Pd)
+          unsigned m = zeroR;
+          while (m) { const int r = __ffs(m) - 1; m &= m - 1; mylog += log((double)evalPd[r]); }
+          mylog += (double)__popcll(zeroC) * log_kappa;
+        } else {
+          const unsigned cr = compR[pp];
+          const unsigned long long cc = compC[pp];
+          const int nR = __popc(cr), nC = __popcll(cc);
+          if (nR + nC > 8) flags |= FLAG_MURTY;
+          if (sum_method == 0 && nR == 1) {
+            // one eval point: missed (all measurements clutter) or detected by one of them
+            const int r = __ffs(cr) - 1;
+            double sumL = 0;
+            unsigned long long m = cc;
+            while (m) { const int c = __ffsll((long long)m) - 1; m &= m - 1; sumL += (double)L[r * nZ + c]; }
+            double kpow = 1;   // kappa^(nC-1)
+            for (int k = 1; k < nC; k++) kpow *= kap;
+            const double miss = 1.0 - (double)evalPd[r];
+            mylog += log(nC == 0 ? miss : miss * kpow * kap + kpow * sumL);   // nC == 0: a one-sided component revisited (Q6)
+          } else if (sum_method == 0 && nC == 1) {
+            // one measurement: clutter (all eval points missed) or it detects one of them
+            const int c = __ffsll((long long)cc) - 1;
+            double allmiss = 1;
+            unsigned m = cr;
+            while (m) { const int r = __ffs(m) - 1; m &= m - 1; allmiss *= 1.0 - (double)evalPd[r]; }
+            double tot = kap * allmiss;
+            m = cr;
+            while (m) {
+              const int r = __ffs(m) - 1; m &= m - 1;
+              double others = 1;
+              unsigned m2 = cr & ~(1u << r);
+              while (m2) { const int r2 = __ffs(m2) - 1; m2 &= m2 - 1; others *= 1.0 - (double)evalPd[r2]; }
+              tot += (double)L[r * nZ + c] * others;
+            }
+            mylog += log(tot);
+          } else {
+            hard = true;
+          }
+        }
+      }
+      unsigned bh = __ballot_sync(FULL, hard);
+      while (bh) {   // warp-wide paths, one partition at a time
+        const int hp = pb + __ffs(bh) - 1;
+        bh &= bh - 1;
+        const unsigned cr = compR[hp];
+        const unsigned long long cc = compC[hp];
+        const int nR = __popc(cr), nC = __popcll(cc);
+        const int bsmall = nR < nC ? nR : nC;
+        if (bsmall > DP_MAXB) { flags |= FLAG_DP_OVERFLOW; continue; }
+        __syncwarp();
+        if (sum_method == 1 && nR + nC <= 12) {
+          // MatPerm path: sum = (prod kappa) * perm([[L/kappa, diag(1-Pd)],[ones]]) / nC!
+          const int nn = nR + nC;
+          double* Am = f0;   // nn*nn <= 144 doubles  (f0/f1 hold 256)
+          int ridx[12], cidx[12];
+          { int k = 0; unsigned m = cr; while (m) { ridx[k++] = __ffs(m) - 1; m &= m - 1; }
+            k = 0; unsigned long long mc = cc; while (mc) { cidx[k++] = __ffsll((long long)mc) - 1; mc &= mc - 1; } }
+          for (int k = lane; k < nn * nn; k += 32) {
+            const int r = k / nn, c = k - r * nn;
+            double v;
+            if (r < nR) {
+              if (c < nC) v = (double)L[ridx[r] * nZ + cidx[c]] / kap;
+              else v = (c - nC == r) ? 1.0 - (double)evalPd[ridx[r]] : 0.0;
+            } else v = 1.0;
+            Am[k] = v;
+          }
+          __syncwarp();
+          const double perm = warp_permanent(Am, nn, lane);
+          double fact = 1; for (int k = 2; k <= nC; k++) fact *= k;
+          logL += log(perm / fact) + (double)nC * log_kappa;
+          __syncwarp();
+        } else {
+          const double pl = partition_dp<T>(L, nZ, cr, cc, evalPd, kap, f0, f1, lane);
+          logL += log(pl);
+        }
+      }
+    }
+    logL += warp_sum(mylog);
+    flags = __reduce_or_sync(FULL, (unsigned)flags);
+  }
+  return logL;
+}
+
+// ------------------------------------------------------------------------------------------------
+// End of a step, shared by the 2-D and the Victoria Park kernels: per-warp statistics, then S8 —
+// deterministic [sum w, sum w^2] by the last CTA (+ the fused cross-GPU sum and normalisation).
+template <typename T>
+__device__ __forceinline__ void step_epilogue(const KParams<T>& p, int lane, int warp, unsigned long long tot_in,
+                                              unsigned long long tot_out, int max_out, int n_over, int n_murty,
+                                              int n_fallback, const unsigned (&mstat)[8]) {
+  if (lane == 0) {
+    if (tot_in) atomicAdd(&p.totals[0], tot_in);
+    if (tot_out) atomicAdd(&p.totals[1], tot_out);
+    atomicMax(&p.istats[0], max_out);
+    if (n_over) atomicAdd(&p.istats[1], n_over);
+    if (n_murty) atomicAdd(&p.istats[2], n_murty);
+    if (n_fallback) atomicAdd(&p.istats[3], n_fallback);
+#pragma unroll
+    for (int k = 0; k < 7; k++)
+      if (mstat[k]) atomicAdd(&p.mstats[k], mstat[k]);
+  }
+
+  // ---------------- S8: deterministic [sum w, sum w^2] by the last CTA ----------------------------
+  __shared__ bool is_last;
+  __shared__ double red[2][WARPS_PER_CTA];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned t = atomicAdd(p.ticket, 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    double s1 = 0, s2 = 0;
+    for (int i = threadIdx.x; i < p.N; i += blockDim.x) {
+      const double w = __ldcg(p.w_out + i);
+      s1 += w;
+      s2 += w * w;
+    }
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    if (lane == 0) { red[0][warp] = s1; red[1][warp] = s2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double a = 0, b = 0;
+      for (int k = 0; k < WARPS_PER_CTA; k++) { a += red[0][k]; b += red[1][k]; }
+      if (p.comm_world > 1) {
+        // ---- fused all-reduce: every rank writes its pair into slot [parity][rank] of EVERY rank's
+        // mailbox (remote stores over NVLink), then waits until its own mailbox holds this epoch from
+        // all ranks and adds them in rank order — the same bits on every GPU, no extra launch.
+        // Slots are double-buffered on the epoch's parity: a rank can be at most one step ahead.
+        const unsigned long long e = p.comm_epoch;
+        const int par = (int)(e & 1ull);
+        for (int r = 0; r < p.comm_world; r++) {
+          CommSlot* dst = reinterpret_cast<CommSlot*>(p.comm_peer[r]) + par * 8 + p.comm_rank;
+          *reinterpret_cast<volatile double*>(&dst->s1) = a;
+          *reinterpret_cast<volatile double*>(&dst->s2) = b;
+          __threadfence_system();
+          asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(&dst->epoch), "l"(e) : "memory");
+        }
+        const CommSlot* mine = reinterpret_cast<const CommSlot*>(p.comm_peer[p.comm_rank]) + par * 8;
+        double ta = 0, tb = 0;
+        bool ok = true;
+        unsigned long long t0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        for (int r = 0; r < p.comm_world && ok; r++) {
+          while (true) {
+            unsigned long long got;
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(got) : "l"(&mine[r].epoch) : "memory");
+            if (got == e) break;
+            unsigned long long t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > 2000000000ull) { ok = false; break; }   // 2 s: a peer never launched
+          }
+          if (ok) {
+            ta += *reinterpret_cast<const volatile double*>(&mine[r].s1);
+            tb += *reinterpret_cast<const volatile double*>(&mine[r].s2);
+          }
+        }
+        if (ok) { a = ta; b = tb; }
+        else { *p.comm_error = 1; a = __longlong_as_double(0x7ff8000000000000LL); b = a; }
+      }
+      p.sums[0] = a;
+      p.sums[1] = b;
+      red[0][0] = a;
+      // publish the step statistics and re-arm the accumulators / queue for the next launch
+      p.stats_out[0] = __ldcg(&p.totals[0]);
+      p.stats_out[1] = __ldcg(&p.totals[1]);
+      p.stats_out[2] = (unsigned long long)(unsigned)__ldcg(&p.istats[0]);
+      p.stats_out[3] = (unsigned long long)(unsigned)__ldcg(&p.istats[1]);
+      p.stats_out[4] = (unsigned long long)(unsigned)__ldcg(&p.istats[2]);
+      p.stats_out[5] = (unsigned long long)(unsigned)__ldcg(&p.istats[3]);
+      for (int k = 0; k < 7; k++) { p.stats_out[6 + k] = (unsigned long long)__ldcg(&p.mstats[k]); p.mstats[k] = 0u; }
+      p.totals[0] = 0; p.totals[1] = 0;
+      p.istats[0] = 0; p.istats[1] = 0; p.istats[2] = 0; p.istats[3] = 0;
+      *p.ticket = 0;
+      *p.work_counter = 0;
+    }
+    if (p.fused_normalize) {   // ParticleFilter::normalizeWeights, in the same launch
+      __syncthreads();
+      const double total = red[0][0];
+      for (int i = threadIdx.x; i < p.N; i += blockDim.x) p.w_out[i] = __ldcg(p.w_out + i) / total;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // shared-memory carve-up (bytes); host and device agree through these helpers
 //  per warp: planes [NPL][W] (NPL = 6, or 7 with weight_prev in multi-feature mode) | merge scratch | aux u32[W] |
 //            colsum T[MAX_Z] | evalIdx int[MAX_EVAL] | mbarrier | multi-feature scratch
@@ -1365,175 +1652,8 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
           L[k] = l;
         }
         __syncwarp();
-        if (lane < nE) {
-          unsigned long long rm = 0;
-          for (int z = 0; z < nZ; z++) if (L[lane * nZ + z] != T(0)) rm |= (1ull << z);
-          rowmask[lane] = rm;
-        }
-        __syncwarp();
-        // connected components of the (eval point, measurement) graph, numbered by their lowest vertex
-        // (rows first, then columns) like boost::connected_components (src/CostMatrix.cpp:98-109):
-        // label propagation, lane = row; a label converges to the smallest vertex of its component.
-        int ncc = 0;
-        {
-          unsigned* lc = reinterpret_cast<unsigned*>(f0);   // [MAX_Z] column labels (f0 is free until the DP)
-          for (int z = lane; z < nZ; z += 32) lc[z] = (unsigned)(nE + z);
-          const unsigned long long rm = (lane < nE) ? rowmask[lane] : 0ull;
-          unsigned lr = (lane < nE) ? (unsigned)lane : 0xffffffffu;
-          __syncwarp();
-          while (true) {
-            bool ch = false;
-            unsigned long long m = rm;
-            unsigned best = lr;
-            while (m) { const int z = __ffsll((long long)m) - 1; m &= m - 1; const unsigned l = lc[z]; best = l < best ? l : best; }
-            if (best < lr) { lr = best; ch = true; }
-            __syncwarp();
-            m = rm;
-            while (m) { const int z = __ffsll((long long)m) - 1; m &= m - 1; if (lc[z] > lr) { atomicMin(&lc[z], lr); ch = true; } }
-            __syncwarp();
-            if (!__any_sync(FULL, ch)) break;
-          }
-          const unsigned bR = __ballot_sync(FULL, lane < nE && lr == (unsigned)lane);          // row-rooted components
-          const unsigned bC0 = __ballot_sync(FULL, lane < nZ && lc[lane < nZ ? lane : 0] == (unsigned)(nE + lane));
-          const unsigned bC1 = __ballot_sync(FULL, lane + 32 < nZ && lc[lane + 32 < nZ ? lane + 32 : 0] == (unsigned)(nE + lane + 32));
-          const int nRowRoots = __popc(bR);
-          ncc = nRowRoots + __popc(bC0) + __popc(bC1);
-          // masks of the row-rooted components: lane c takes the c-th root
-          {
-            const int root = (lane < nRowRoots) ? (int)__fns(bR, 0, lane + 1) : -1;
-            unsigned cr = 0;
-            for (int e = 0; e < nE; e++) {
-              const unsigned le = __shfl_sync(FULL, lr, e);
-              if ((int)le == root) cr |= 1u << e;
-            }
-            unsigned long long cc = 0;
-            for (int z = 0; z < nZ; z++) if ((int)lc[z] == root) cc |= 1ull << z;
-            if (lane < nRowRoots) { compR[lane] = cr; compC[lane] = cc; }
-          }
-          // isolated columns are components of their own, after all the row-rooted ones
-          if ((bC0 >> lane) & 1u) {
-            const int idx = nRowRoots + __popc(bC0 & ((1u << lane) - 1u));
-            compR[idx] = 0u; compC[idx] = 1ull << lane;
-          }
-          if ((bC1 >> lane) & 1u) {
-            const int idx = nRowRoots + __popc(bC0) + __popc(bC1 & ((1u << lane) - 1u));
-            compR[idx] = 0u; compC[idx] = 1ull << (lane + 32);
-          }
-        }
-        __syncwarp();
-        // CostMatrixGeneral::partition (:111-144): one-sided components fold into the first one
-        int combinedZero = -1, nMerged = 0;
-        unsigned zeroR = 0;
-        unsigned long long zeroC = 0;
-        {
-          int nOne = 0;
-          for (int cb = 0; cb < ncc; cb += 32) {
-            const int c = cb + lane;
-            unsigned cr = 0;
-            unsigned long long cc = 0;
-            bool one = false;
-            if (c < ncc) { cr = compR[c]; cc = compC[c]; one = (cr == 0u) || (cc == 0ull); }
-            const unsigned bo = __ballot_sync(FULL, one);
-            if (bo && combinedZero < 0) combinedZero = cb + __ffs(bo) - 1;
-            nOne += __popc(bo);
-            zeroR |= __reduce_or_sync(FULL, one ? cr : 0u);
-            zeroC |= (unsigned long long)__reduce_or_sync(FULL, one ? (unsigned)(cc & 0xffffffffull) : 0u) |
-                     ((unsigned long long)__reduce_or_sync(FULL, one ? (unsigned)(cc >> 32) : 0u) << 32);
-          }
-          nMerged = nOne > 0 ? nOne - 1 : 0;
-        }
-        const int nP = ncc - nMerged;
-        // Partition likelihoods (Q6: original labels, only p < nP are visited).  Lane-parallel: the
-        // zero partition and partitions with a single row or a single column have closed forms;
-        // the rest go through the warp-wide subset DP (or the matrix-permanent identity).
-        double logL = 0;
-        {
-          const double kap = exp(p.log_kappa);
-          double mylog = 0;
-          for (int pb = 0; pb < nP; pb += 32) {
-            const int pp = pb + lane;
-            bool hard = false;
-            if (pp < nP) {
-              if (pp == combinedZero) {   // :891-900 (Q5: Pd, not 1-Pd)
-                unsigned m = zeroR;
-                while (m) { const int r = __ffs(m) - 1; m &= m - 1; mylog += log((double)evalPd[r]); }
-                mylog += (double)__popcll(zeroC) * p.log_kappa;
-              } else {
-                const unsigned cr = compR[pp];
-                const unsigned long long cc = compC[pp];
-                const int nR = __popc(cr), nC = __popcll(cc);
-                if (nR + nC > 8) flags |= FLAG_MURTY;
-                if (p.sum_method == 0 && nR == 1) {
-                  // one eval point: missed (all measurements clutter) or detected by one of them
-                  const int r = __ffs(cr) - 1;
-                  double sumL = 0;
-                  unsigned long long m = cc;
-                  while (m) { const int c = __ffsll((long long)m) - 1; m &= m - 1; sumL += (double)L[r * nZ + c]; }
-                  double kpow = 1;   // kappa^(nC-1)
-                  for (int k = 1; k < nC; k++) kpow *= kap;
-                  const double miss = 1.0 - (double)evalPd[r];
-                  mylog += log(nC == 0 ? miss : miss * kpow * kap + kpow * sumL);   // nC == 0: a one-sided component revisited (Q6)
-                } else if (p.sum_method == 0 && nC == 1) {
-                  // one measurement: clutter (all eval points missed) or it detects one of them
-                  const int c = __ffsll((long long)cc) - 1;
-                  double allmiss = 1;
-                  unsigned m = cr;
-                  while (m) { const int r = __ffs(m) - 1; m &= m - 1; allmiss *= 1.0 - (double)evalPd[r]; }
-                  double tot = kap * allmiss;
-                  m = cr;
-                  while (m) {
-                    const int r = __ffs(m) - 1; m &= m - 1;
-                    double others = 1;
-                    unsigned m2 = cr & ~(1u << r);
-                    while (m2) { const int r2 = __ffs(m2) - 1; m2 &= m2 - 1; others *= 1.0 - (double)evalPd[r2]; }
-                    tot += (double)L[r * nZ + c] * others;
-                  }
-                  mylog += log(tot);
-                } else {
-                  hard = true;
-                }
-              }
-            }
-            unsigned bh = __ballot_sync(FULL, hard);
-            while (bh) {   // warp-wide paths, one partition at a time
-              const int hp = pb + __ffs(bh) - 1;
-              bh &= bh - 1;
-              const unsigned cr = compR[hp];
-              const unsigned long long cc = compC[hp];
-              const int nR = __popc(cr), nC = __popcll(cc);
-              const int bsmall = nR < nC ? nR : nC;
-              if (bsmall > DP_MAXB) { flags |= FLAG_DP_OVERFLOW; continue; }
-              __syncwarp();
-              if (p.sum_method == 1 && nR + nC <= 12) {
-                // MatPerm path: sum = (prod kappa) * perm([[L/kappa, diag(1-Pd)],[ones]]) / nC!
-                const int nn = nR + nC;
-                double* Am = f0;   // nn*nn <= 144 doubles  (f0/f1 hold 256)
-                int ridx[12], cidx[12];
-                { int k = 0; unsigned m = cr; while (m) { ridx[k++] = __ffs(m) - 1; m &= m - 1; }
-                  k = 0; unsigned long long mc = cc; while (mc) { cidx[k++] = __ffsll((long long)mc) - 1; mc &= mc - 1; } }
-                for (int k = lane; k < nn * nn; k += 32) {
-                  const int r = k / nn, c = k - r * nn;
-                  double v;
-                  if (r < nR) {
-                    if (c < nC) v = (double)L[ridx[r] * nZ + cidx[c]] / kap;
-                    else v = (c - nC == r) ? 1.0 - (double)evalPd[ridx[r]] : 0.0;
-                  } else v = 1.0;
-                  Am[k] = v;
-                }
-                __syncwarp();
-                const double perm = warp_permanent(Am, nn, lane);
-                double fact = 1; for (int k = 2; k <= nC; k++) fact *= k;
-                logL += log(perm / fact) + (double)nC * p.log_kappa;
-                __syncwarp();
-              } else {
-                const double pl = partition_dp<T>(L, nZ, cr, cc, evalPd, kap, f0, f1, lane);
-                logL += log(pl);
-              }
-            }
-          }
-          logL += warp_sum(mylog);
-          flags = __reduce_or_sync(FULL, (unsigned)flags);
-        }
+        double logL = mf_partition_loglik<T>(L, evalPd, nE, nZ, rowmask, compC, f0, f1, compR, p.sum_method,
+                                            p.log_kappa, flags, lane);
         logL -= p.log_clutter_integral;
         // :808-812
         weight_new = exp(logL + (lp_before - lp_after) + (sw_now - sw_prev)) * w_prev_particle;
@@ -1640,101 +1760,7 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
     if (flags & FLAG_MURTY) n_murty++;
     __syncwarp();
   }
-  if (lane == 0) {
-    if (tot_in) atomicAdd(&p.totals[0], tot_in);
-    if (tot_out) atomicAdd(&p.totals[1], tot_out);
-    atomicMax(&p.istats[0], max_out);
-    if (n_over) atomicAdd(&p.istats[1], n_over);
-    if (n_murty) atomicAdd(&p.istats[2], n_murty);
-    if (n_fallback) atomicAdd(&p.istats[3], n_fallback);
-#pragma unroll
-    for (int k = 0; k < 7; k++)
-      if (mstat[k]) atomicAdd(&p.mstats[k], mstat[k]);
-  }
-
-  // ---------------- S8: deterministic [sum w, sum w^2] by the last CTA ----------------------------
-  __shared__ bool is_last;
-  __shared__ double red[2][WARPS_PER_CTA];
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    const unsigned t = atomicAdd(p.ticket, 1u);
-    is_last = (t == gridDim.x - 1);
-  }
-  __syncthreads();
-  if (is_last) {
-    __threadfence();
-    double s1 = 0, s2 = 0;
-    for (int i = threadIdx.x; i < p.N; i += blockDim.x) {
-      const double w = __ldcg(p.w_out + i);
-      s1 += w;
-      s2 += w * w;
-    }
-    s1 = warp_sum(s1);
-    s2 = warp_sum(s2);
-    if (lane == 0) { red[0][warp] = s1; red[1][warp] = s2; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      double a = 0, b = 0;
-      for (int k = 0; k < WARPS_PER_CTA; k++) { a += red[0][k]; b += red[1][k]; }
-      if (p.comm_world > 1) {
-        // ---- fused all-reduce: every rank writes its pair into slot [parity][rank] of EVERY rank's
-        // mailbox (remote stores over NVLink), then waits until its own mailbox holds this epoch from
-        // all ranks and adds them in rank order — the same bits on every GPU, no extra launch.
-        // Slots are double-buffered on the epoch's parity: a rank can be at most one step ahead.
-        const unsigned long long e = p.comm_epoch;
-        const int par = (int)(e & 1ull);
-        for (int r = 0; r < p.comm_world; r++) {
-          CommSlot* dst = reinterpret_cast<CommSlot*>(p.comm_peer[r]) + par * 8 + p.comm_rank;
-          *reinterpret_cast<volatile double*>(&dst->s1) = a;
-          *reinterpret_cast<volatile double*>(&dst->s2) = b;
-          __threadfence_system();
-          asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(&dst->epoch), "l"(e) : "memory");
-        }
-        const CommSlot* mine = reinterpret_cast<const CommSlot*>(p.comm_peer[p.comm_rank]) + par * 8;
-        double ta = 0, tb = 0;
-        bool ok = true;
-        unsigned long long t0;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-        for (int r = 0; r < p.comm_world && ok; r++) {
-          while (true) {
-            unsigned long long got;
-            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(got) : "l"(&mine[r].epoch) : "memory");
-            if (got == e) break;
-            unsigned long long t1;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-            if (t1 - t0 > 2000000000ull) { ok = false; break; }   // 2 s: a peer never launched
-          }
-          if (ok) {
-            ta += *reinterpret_cast<const volatile double*>(&mine[r].s1);
-            tb += *reinterpret_cast<const volatile double*>(&mine[r].s2);
-          }
-        }
-        if (ok) { a = ta; b = tb; }
-        else { *p.comm_error = 1; a = __longlong_as_double(0x7ff8000000000000LL); b = a; }
-      }
-      p.sums[0] = a;
-      p.sums[1] = b;
-      red[0][0] = a;
-      // publish the step statistics and re-arm the accumulators / queue for the next launch
-      p.stats_out[0] = __ldcg(&p.totals[0]);
-      p.stats_out[1] = __ldcg(&p.totals[1]);
-      p.stats_out[2] = (unsigned long long)(unsigned)__ldcg(&p.istats[0]);
-      p.stats_out[3] = (unsigned long long)(unsigned)__ldcg(&p.istats[1]);
-      p.stats_out[4] = (unsigned long long)(unsigned)__ldcg(&p.istats[2]);
-      p.stats_out[5] = (unsigned long long)(unsigned)__ldcg(&p.istats[3]);
-      for (int k = 0; k < 7; k++) { p.stats_out[6 + k] = (unsigned long long)__ldcg(&p.mstats[k]); p.mstats[k] = 0u; }
-      p.totals[0] = 0; p.totals[1] = 0;
-      p.istats[0] = 0; p.istats[1] = 0; p.istats[2] = 0; p.istats[3] = 0;
-      *p.ticket = 0;
-      *p.work_counter = 0;
-    }
-    if (p.fused_normalize) {   // ParticleFilter::normalizeWeights, in the same launch
-      __syncthreads();
-      const double total = red[0][0];
-      for (int i = threadIdx.x; i < p.N; i += blockDim.x) p.w_out[i] = __ldcg(p.w_out + i) / total;
-    }
-  }
+  step_epilogue<T>(p, lane, warp, tot_in, tot_out, max_out, n_over, n_murty, n_fallback, mstat);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1815,7 +1841,7 @@ __global__ void resample_gather_kernel(const T* __restrict__ gm_in, const int* _
                                        double* __restrict__ w_out, int set_w, double w_value,
                                        const T* __restrict__ pose_in, const T* __restrict__ pcov_in,
                                        T* __restrict__ pose_out, T* __restrict__ pcov_out, int pose_cov_mode,
-                                       int N, int cap) {
+                                       int N, int cap, int npl) {
   const int lane = threadIdx.x & 31;
   const int pi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (pi >= N) return;
@@ -1824,9 +1850,9 @@ __global__ void resample_gather_kernel(const T* __restrict__ gm_in, const int* _
   int a = asrc ? asrc[pi] : s;   // -1: the new particle starts with no unused measurements
   a = a >= N ? N - 1 : a;
   const int n = cnt_in[s];
-  const T* gi = gm_in + (size_t)s * 6 * cap;
-  T* go = gm_out + (size_t)pi * 6 * cap;
-  for (int pl = 0; pl < 6; pl++)
+  const T* gi = gm_in + (size_t)s * npl * cap;
+  T* go = gm_out + (size_t)pi * npl * cap;
+  for (int pl = 0; pl < npl; pl++)
     for (int j = lane; j < n; j += 32) go[(size_t)pl * cap + j] = gi[(size_t)pl * cap + j];
   if (lane == 0) {
     cnt_out[pi] = n;

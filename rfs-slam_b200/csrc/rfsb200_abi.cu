@@ -15,6 +15,7 @@
 
 #include "../../include/rfsb200.h"
 #include "phd_kernels.cuh"
+#include "phd_vp_kernels.cuh"
 
 using namespace rfsb200;
 
@@ -23,7 +24,7 @@ namespace {
 thread_local std::string g_last_error;
 
 struct StateBuf {
-  void* gm = nullptr;       // T [N][6][cap]
+  void* gm = nullptr;       // T [N][npl][cap]  (npl = 6: 2-D landmarks, 10: 3-D)
   int* cnt = nullptr;       // [N]
   double* weight = nullptr; // [N]
 };
@@ -33,6 +34,10 @@ struct StateBuf {
 struct rfsb200_ctx {
   rfsb200_dims dims{};
   int N = 0, cap = 0, W = 0, prec = 32;
+  int ld = 2;    // landmark / measurement dimension
+  int nc = 3;    // unique covariance entries
+  int npl = 6;   // planes per particle in HBM: ld means + nc covariance entries + weight
+  double* scan_dev = nullptr;   // Victoria Park: lidar scan [720]
   size_t tsize = 4;
   int device = 0;
   int sm_count = 148;
@@ -118,42 +123,36 @@ int fail(rfsb200_ctx* ctx, int code, const char* fmt, ...) {
 template <typename T>
 __global__ void pack_soa_kernel(const int* __restrict__ cnt, const long long* __restrict__ offs,
                                 const double* __restrict__ mean, const double* __restrict__ cov,
-                                const double* __restrict__ w, T* __restrict__ gm, int N, int cap) {
+                                const double* __restrict__ w, T* __restrict__ gm, int N, int cap, int ld, int nc) {
   const int lane = threadIdx.x & 31;
   const int pi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (pi >= N) return;
   const int n = cnt[pi];
   const long long o = offs[pi];
-  T* g = gm + (size_t)pi * 6 * cap;
+  T* g = gm + (size_t)pi * (ld + nc + 1) * cap;
   for (int k = lane; k < n; k += 32) {
     const long long s = o + k;
-    g[k] = (T)mean[2 * s];
-    g[cap + k] = (T)mean[2 * s + 1];
-    g[2 * cap + k] = (T)cov[3 * s];
-    g[3 * cap + k] = (T)cov[3 * s + 1];
-    g[4 * cap + k] = (T)cov[3 * s + 2];
-    g[5 * cap + k] = (T)w[s];
+    for (int d = 0; d < ld; d++) g[d * cap + k] = (T)mean[ld * s + d];
+    for (int d = 0; d < nc; d++) g[(ld + d) * cap + k] = (T)cov[nc * s + d];
+    g[(ld + nc) * cap + k] = (T)w[s];
   }
 }
 
 template <typename T>
 __global__ void unpack_soa_kernel(const int* __restrict__ cnt, const long long* __restrict__ offs,
                                   const T* __restrict__ gm, double* __restrict__ mean,
-                                  double* __restrict__ cov, double* __restrict__ w, int N, int cap) {
+                                  double* __restrict__ cov, double* __restrict__ w, int N, int cap, int ld, int nc) {
   const int lane = threadIdx.x & 31;
   const int pi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (pi >= N) return;
   const int n = cnt[pi];
   const long long o = offs[pi];
-  const T* g = gm + (size_t)pi * 6 * cap;
+  const T* g = gm + (size_t)pi * (ld + nc + 1) * cap;
   for (int k = lane; k < n; k += 32) {
     const long long s = o + k;
-    mean[2 * s] = (double)g[k];
-    mean[2 * s + 1] = (double)g[cap + k];
-    cov[3 * s] = (double)g[2 * cap + k];
-    cov[3 * s + 1] = (double)g[3 * cap + k];
-    cov[3 * s + 2] = (double)g[4 * cap + k];
-    w[s] = (double)g[5 * cap + k];
+    for (int d = 0; d < ld; d++) mean[ld * s + d] = (double)g[d * cap + k];
+    for (int d = 0; d < nc; d++) cov[nc * s + d] = (double)g[(ld + d) * cap + k];
+    w[s] = (double)g[(ld + nc) * cap + k];
   }
 }
 
@@ -231,8 +230,28 @@ int configure_launch_t(rfsb200_ctx* c) {
   c->cfg_mode_mf = mf;
   return RFSB200_OK;
 }
+template <typename T, bool MF>
+int configure_launch_vp_t(rfsb200_ctx* c) {
+  const int mf = MF ? 1 : 0;
+  const int n_eval = (MF && c->have_cfg) ? std::max(1, c->cfg.eval_point_count) : MAX_EVAL;
+  if (c->cfg_mode_mf == mf && (!MF || c->cfg_n_eval == n_eval)) return RFSB200_OK;
+  c->cfg_n_eval = n_eval;
+  c->mf_bytes = 0;
+  c->warp_bytes = vp_warp_bytes<T>(c->W, mf, n_eval, c->dims.z_capacity);
+  c->smem_bytes = (size_t)vp_cta_bytes<T>() + (size_t)WARPS_PER_CTA * c->warp_bytes;
+  if (c->smem_bytes > 227 * 1024) return fail(c, RFSB200_ECAPACITY, "work_capacity %d needs %zu B shared memory per CTA (> 227 KB)", c->W, c->smem_bytes);
+  CU(c, cudaFuncSetAttribute(phd_update_vp_kernel<T, MF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
+  int occ = 0;
+  CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, phd_update_vp_kernel<T, MF>, WARPS_PER_CTA * 32, c->smem_bytes));
+  if (occ < 1) return fail(c, RFSB200_ECAPACITY, "kernel does not fit on an SM");
+  const int need = (c->N + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+  c->grid = std::max(1, std::min(need, occ * c->sm_count));
+  c->cfg_mode_mf = mf;
+  return RFSB200_OK;
+}
 template <typename T>
 int configure_launch(rfsb200_ctx* c, int mf) {
+  if (c->ld == 3) return mf ? configure_launch_vp_t<T, true>(c) : configure_launch_vp_t<T, false>(c);
   return mf ? configure_launch_t<T, true>(c) : configure_launch_t<T, false>(c);
 }
 
@@ -284,7 +303,18 @@ int launch_update(rfsb200_ctx* c, int nZ, int out_idx, unsigned flags) {
   }
   const bool prof = c->prof_n < c->prof_cap;
   if (prof) CU(c, cudaEventRecord(c->prof_ev[2 * c->prof_n], c->stream));
-  if (mf) phd_update_kernel<T, true><<<c->grid, WARPS_PER_CTA * 32, c->smem_bytes, c->stream>>>(p);
+  if (c->ld == 3) {
+    VPParams<T> v{};
+    v.k = p;
+    v.R00 = (T)m.R[0]; v.R01 = (T)m.R[1]; v.R10 = (T)m.R[3]; v.R11 = (T)m.R[4]; v.R22 = (T)m.R[8];
+    v.Slb = (T)m.Slb;
+    v.rmin = m.range_min; v.rmax = m.range_max; v.bmin = m.bearing_min; v.bmax = m.bearing_max;
+    v.buf_pd = m.buffer_zone_pd;
+    v.pd_n = m.pd_table_n; v.scan_n = m.scan_n; v.scan = c->scan_dev;
+    for (int k = 0; k < VP_PD_MAX; k++) v.pd_table[k] = k < m.pd_table_n ? m.pd_table[k] : 0.0;
+    if (mf) phd_update_vp_kernel<T, true><<<c->grid, WARPS_PER_CTA * 32, c->smem_bytes, c->stream>>>(v);
+    else phd_update_vp_kernel<T, false><<<c->grid, WARPS_PER_CTA * 32, c->smem_bytes, c->stream>>>(v);
+  } else if (mf) phd_update_kernel<T, true><<<c->grid, WARPS_PER_CTA * 32, c->smem_bytes, c->stream>>>(p);
   else phd_update_kernel<T, false><<<c->grid, WARPS_PER_CTA * 32, c->smem_bytes, c->stream>>>(p);
   CU(c, cudaGetLastError());
   if (prof) {
@@ -325,6 +355,24 @@ int do_predict(rfsb200_ctx* c, const double* Q, int add_births, double birth_w) 
   CU(c, cudaGetLastError());
   return RFSB200_OK;
 }
+template <typename T>
+int do_predict_vp(rfsb200_ctx* c, const double* Q, int add_births, double birth_w) {
+  VPPredictParams<T> p{};
+  const StateBuf& st = c->st[c->front];
+  p.gm = (T*)st.gm; p.cnt = st.cnt; p.unused = c->unused; p.flags = c->flags;
+  p.pose = (const T*)c->pose; p.Z = (const T*)c->Zdev;
+  p.N = c->N; p.cap = c->cap; p.nZ = c->last_nZ;
+  p.add_births = (add_births && c->last_nZ > 0) ? 1 : 0;
+  p.add_q = Q ? 1 : 0;
+  const double* R = c->model.R;
+  p.R00 = (T)R[0]; p.R01 = (T)R[1]; p.R10 = (T)R[3]; p.R11 = (T)R[4]; p.R22 = (T)R[8];
+  if (Q) for (int k = 0; k < 6; k++) p.q[k] = (T)Q[k];
+  p.birth_w = (T)birth_w;
+  if (!p.add_births && !p.add_q) return RFSB200_OK;
+  predict_maps_vp_kernel<T><<<(c->N * 32 + 127) / 128, 128, 0, c->stream>>>(p);
+  CU(c, cudaGetLastError());
+  return RFSB200_OK;
+}
 }  // namespace
 
 
@@ -350,8 +398,8 @@ int rfsb200_create(rfsb200_ctx** out, const rfsb200_dims* d) {
   if (d->n_particles <= 0 || d->gm_capacity <= 0 || d->gm_capacity > 1024 || d->work_capacity > 1024 ||
       d->z_capacity <= 0 || d->z_capacity > MAX_Z)
     return fail(nullptr, RFSB200_EINVAL, "rfsb200_create: sizes out of range");
-  if (d->lmk_dim != 2 || d->meas_dim != 2 || d->pose_dim != 3)
-    return fail(nullptr, RFSB200_EUNSUPPORTED, "only 2-D landmarks / 2-D measurements / 3-D poses are implemented");
+  if ((d->lmk_dim != 2 && d->lmk_dim != 3) || d->meas_dim != d->lmk_dim || d->pose_dim != 3)
+    return fail(nullptr, RFSB200_EUNSUPPORTED, "implemented: 2-D landmarks + 2-D measurements (RngBrg) or 3-D + 3-D (VictoriaPark), 3-D poses");
   if (d->precision != 32 && d->precision != 64)
     return fail(nullptr, RFSB200_EINVAL, "precision must be 32 or 64");
   int ndev = 0;
@@ -362,6 +410,9 @@ int rfsb200_create(rfsb200_ctx** out, const rfsb200_dims* d) {
   if (!c) return fail(nullptr, RFSB200_ENOMEM, "out of host memory");
   c->dims = *d;
   c->N = d->n_particles;
+  c->ld = d->lmk_dim;
+  c->nc = c->ld * (c->ld + 1) / 2;
+  c->npl = c->ld + c->nc + 1;
   c->cap = (d->gm_capacity + 7) & ~7;
   c->W = round_pow2(std::max(d->work_capacity, c->cap));
   c->prec = d->precision;
@@ -380,7 +431,7 @@ int rfsb200_create(rfsb200_ctx** out, const rfsb200_dims* d) {
     CU(c, cudaEventCreate(&c->ev0));
     CU(c, cudaEventCreate(&c->ev1));
     for (int k = 0; k < 8; k++) CU(c, cudaEventCreateWithFlags(&c->zev[k], cudaEventDisableTiming));
-    const size_t gm_bytes = (size_t)c->N * 6 * c->cap * c->tsize;
+    const size_t gm_bytes = (size_t)c->N * c->npl * c->cap * c->tsize;
     for (int k = 0; k < 2; k++) {
       CU(c, cudaMalloc(&c->st[k].gm, gm_bytes));
       CU(c, cudaMemset(c->st[k].gm, 0, gm_bytes));
@@ -427,7 +478,9 @@ int rfsb200_create(rfsb200_ctx** out, const rfsb200_dims* d) {
     CU(c, cudaMemset(c->istats, 0, 16));
     CU(c, cudaMemset(c->sums, 0, 16));
     CU(c, cudaMemset(c->ticket, 0, 4));
-    CU(c, cudaMalloc((void**)&c->stg, (size_t)c->N * c->cap * 6 * 8));
+    CU(c, cudaMalloc((void**)&c->stg, (size_t)c->N * c->cap * c->npl * 8));
+    CU(c, cudaMalloc((void**)&c->scan_dev, VP_SCAN_MAX * 8));
+    CU(c, cudaMemset(c->scan_dev, 0, VP_SCAN_MAX * 8));
     CU(c, cudaMalloc((void**)&c->offs, (size_t)(c->N + 1) * 8));
     CU(c, cudaMalloc((void**)&c->stg_small, (size_t)c->N * 16 * 8));
     int r = ensure_pinned(c, 1 << 16);
@@ -464,7 +517,7 @@ int rfsb200_destroy(rfsb200_ctx* c) {
   cudaFree(c->comm_mail); cudaFree(c->comm_error);
   cudaFree(c->sums); cudaFree(c->totals); cudaFree(c->istats); cudaFree(c->ticket);
   cudaFree(c->work_counter); cudaFree(c->stats_out); cudaFree(c->mstats);
-  cudaFree(c->stg); cudaFree(c->offs); cudaFree(c->stg_small);
+  cudaFree(c->stg); cudaFree(c->offs); cudaFree(c->stg_small); cudaFree(c->scan_dev);
   if (c->hpin) cudaFreeHost(c->hpin);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
@@ -490,11 +543,27 @@ int rfsb200_synchronize(rfsb200_ctx* c) {
 
 int rfsb200_set_model(rfsb200_ctx* c, const rfsb200_model_desc* m) {
   if (!c || !m) return fail(c, RFSB200_EINVAL, "NULL argument");
-  if (m->model_id != RFSB200_MODEL_RNGBRG)
-    return fail(c, RFSB200_EUNSUPPORTED, "model id %d has no device descriptor (only MeasurementModel_RngBrg)", m->model_id);
+  if (m->model_id != RFSB200_MODEL_RNGBRG && m->model_id != RFSB200_MODEL_VICTORIAPARK)
+    return fail(c, RFSB200_EUNSUPPORTED, "model id %d has no device descriptor (MeasurementModel_RngBrg, MeasurementModel_VictoriaPark)", m->model_id);
+  if ((m->model_id == RFSB200_MODEL_RNGBRG) != (c->ld == 2))
+    return fail(c, RFSB200_EINVAL, "model id %d does not match the landmark dimension %d of the ctx", m->model_id, c->ld);
   if (!(m->clutter_intensity > 0) || !(m->clutter_integral > 0))
     return fail(c, RFSB200_EINVAL, "clutter intensity / integral must be > 0");
+  if (m->model_id == RFSB200_MODEL_VICTORIAPARK) {
+    if (m->pd_table_n < 1 || m->pd_table_n > VP_PD_MAX) return fail(c, RFSB200_EINVAL, "pd_table_n %d outside [1,%d]", m->pd_table_n, VP_PD_MAX);
+    if (m->scan_n < 0 || m->scan_n > VP_SCAN_MAX || (m->scan_n > 0 && !m->scan))
+      return fail(c, RFSB200_EINVAL, "scan_n %d outside [0,%d] or NULL scan", m->scan_n, VP_SCAN_MAX);
+    CU(c, cudaSetDevice(c->device));
+    if (m->scan_n > 0) {   // the scan changes before every update (src/rbphdslam_VictoriaPark.cpp:582): staged copy
+      int r = ensure_pinned(c, 1 << 16);
+      if (r) return r;
+      CU(c, cudaStreamSynchronize(c->stream));   // the previous copy out of the staging area has finished
+      memcpy(c->hpin + 49152, m->scan, (size_t)m->scan_n * 8);
+      CU(c, cudaMemcpyAsync(c->scan_dev, c->hpin + 49152, (size_t)m->scan_n * 8, cudaMemcpyHostToDevice, c->stream));
+    }
+  }
   c->model = *m;
+  c->model.scan = nullptr;   // the host pointer is not kept
   c->have_model = true;
   return RFSB200_OK;
 }
@@ -524,15 +593,15 @@ int rfsb200_upload_maps(rfsb200_ctx* c, const int32_t* count, const double* mean
   CU(c, cudaMemcpyAsync(s.cnt, count, (size_t)c->N * 4, cudaMemcpyHostToDevice, c->stream));
   scan_counts_kernel<<<1, 1024, 0, c->stream>>>(s.cnt, c->offs, c->N);
   double* dm = c->stg;
-  double* dc = dm + (size_t)c->N * c->cap * 2;
-  double* dw = dc + (size_t)c->N * c->cap * 3;
+  double* dc = dm + (size_t)c->N * c->cap * c->ld;
+  double* dw = dc + (size_t)c->N * c->cap * c->nc;
   if (total > 0) {
-    CU(c, cudaMemcpyAsync(dm, mean, (size_t)total * 2 * 8, cudaMemcpyHostToDevice, c->stream));
-    CU(c, cudaMemcpyAsync(dc, cov, (size_t)total * 3 * 8, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(dm, mean, (size_t)total * c->ld * 8, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(dc, cov, (size_t)total * c->nc * 8, cudaMemcpyHostToDevice, c->stream));
     CU(c, cudaMemcpyAsync(dw, w, (size_t)total * 8, cudaMemcpyHostToDevice, c->stream));
     const int blocks = (c->N * 32 + 255) / 256;
-    if (c->prec == 32) pack_soa_kernel<float><<<blocks, 256, 0, c->stream>>>(s.cnt, c->offs, dm, dc, dw, (float*)s.gm, c->N, c->cap);
-    else pack_soa_kernel<double><<<blocks, 256, 0, c->stream>>>(s.cnt, c->offs, dm, dc, dw, (double*)s.gm, c->N, c->cap);
+    if (c->prec == 32) pack_soa_kernel<float><<<blocks, 256, 0, c->stream>>>(s.cnt, c->offs, dm, dc, dw, (float*)s.gm, c->N, c->cap, c->ld, c->nc);
+    else pack_soa_kernel<double><<<blocks, 256, 0, c->stream>>>(s.cnt, c->offs, dm, dc, dw, (double*)s.gm, c->N, c->cap, c->ld, c->nc);
   }
   CU(c, cudaGetLastError());
   c->last_out = c->front;
@@ -579,15 +648,15 @@ int rfsb200_update(rfsb200_ctx* c, const double* Z, int32_t nZ, uint32_t flags, 
     zslot_used = slot;
     if (c->prec == 32) {
       float* h = (float*)hb;
-      for (int k = 0; k < 2 * nZ; k++) h[k] = (float)Z[k];
+      for (int k = 0; k < c->ld * nZ; k++) h[k] = (float)Z[k];
     } else {
       double* h = (double*)hb;
-      for (int k = 0; k < 2 * nZ; k++) h[k] = Z[k];
+      for (int k = 0; k < c->ld * nZ; k++) h[k] = Z[k];
     }
   }
   int launches = 0;
   if (out) CU(c, cudaEventRecord(c->ev0, c->stream));
-  CU(c, cudaMemcpyAsync(c->Zdev, zsrc, (size_t)2 * nZ * c->tsize, cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaMemcpyAsync(c->Zdev, zsrc, (size_t)c->ld * nZ * c->tsize, cudaMemcpyHostToDevice, c->stream));
   CU(c, cudaEventRecord(c->zev[zslot_used], c->stream));
   const int out_idx = c->front ^ 1;
   if ((flags & RFSB200_UPDATE_FUSED_ALLREDUCE) && c->comm_world > 1 && !c->comm_peer[0])
@@ -637,6 +706,7 @@ int rfsb200_predict_maps(rfsb200_ctx* c, const double* Q, int32_t add_births, do
     return fail(c, RFSB200_ESTATE, "births need set_model and set_poses (pose and R of the last update)");
   CU(c, cudaSetDevice(c->device));
   c->last_out = c->front;
+  if (c->ld == 3) return c->prec == 32 ? do_predict_vp<float>(c, Q, add_births, birth_w) : do_predict_vp<double>(c, Q, add_births, birth_w);
   return c->prec == 32 ? do_predict<float>(c, Q, add_births, birth_w) : do_predict<double>(c, Q, add_births, birth_w);
 }
 
@@ -658,13 +728,13 @@ int rfsb200_resample(rfsb200_ctx* c, const int32_t* map_src, const int32_t* aux_
                                                                  (float*)out.gm, out.cnt, c->unused_alt, c->nfov_alt, out.weight,
                                                                  weight ? 1 : 0, weight ? *weight : 0.0,
                                                                  (const float*)c->pose, (const float*)c->pose_cov, (float*)c->pose_alt,
-                                                                 (float*)c->pose_cov_alt, c->pose_cov_mode, c->N, c->cap);
+                                                                 (float*)c->pose_cov_alt, c->pose_cov_mode, c->N, c->cap, c->npl);
   else
     resample_gather_kernel<double><<<blocks, 128, 0, c->stream>>>((const double*)in.gm, in.cnt, c->unused, c->nfov, in.weight, c->src_dev, asrc,
                                                                   (double*)out.gm, out.cnt, c->unused_alt, c->nfov_alt, out.weight,
                                                                   weight ? 1 : 0, weight ? *weight : 0.0,
                                                                   (const double*)c->pose, (const double*)c->pose_cov, (double*)c->pose_alt,
-                                                                  (double*)c->pose_cov_alt, c->pose_cov_mode, c->N, c->cap);
+                                                                  (double*)c->pose_cov_alt, c->pose_cov_mode, c->N, c->cap, c->npl);
   CU(c, cudaGetLastError());
   CU(c, cudaStreamSynchronize(c->stream));   // map_src / aux_src are the caller's (pageable) buffers
   std::swap(c->unused, c->unused_alt);
@@ -760,17 +830,17 @@ int rfsb200_get_map(rfsb200_ctx* c, int which, int32_t i, int32_t cap, int32_t* 
   if (cnt == 0) return RFSB200_OK;
   if (cnt > cap) return fail(c, RFSB200_ECAPACITY, "particle %d has %d Gaussians, caller capacity %d", i, cnt, cap);
   if (!mean || !cov || !w) return fail(c, RFSB200_EINVAL, "NULL output arrays");
-  std::vector<unsigned char> tmp((size_t)6 * c->cap * c->tsize);
-  CU(c, cudaMemcpyAsync(tmp.data(), (const unsigned char*)s.gm + (size_t)i * 6 * c->cap * c->tsize, tmp.size(), cudaMemcpyDeviceToHost, c->stream));
+  std::vector<unsigned char> tmp((size_t)c->npl * c->cap * c->tsize);
+  CU(c, cudaMemcpyAsync(tmp.data(), (const unsigned char*)s.gm + (size_t)i * c->npl * c->cap * c->tsize, tmp.size(), cudaMemcpyDeviceToHost, c->stream));
   CU(c, cudaStreamSynchronize(c->stream));
   for (int k = 0; k < cnt; k++) {
     auto get = [&](int plane) -> double {
       size_t idx = (size_t)plane * c->cap + k;
       return c->prec == 32 ? (double)((const float*)tmp.data())[idx] : ((const double*)tmp.data())[idx];
     };
-    mean[2 * k] = get(0); mean[2 * k + 1] = get(1);
-    cov[3 * k] = get(2); cov[3 * k + 1] = get(3); cov[3 * k + 2] = get(4);
-    w[k] = get(5);
+    for (int d = 0; d < c->ld; d++) mean[c->ld * k + d] = get(d);
+    for (int d = 0; d < c->nc; d++) cov[c->nc * k + d] = get(c->ld + d);
+    w[k] = get(c->ld + c->nc);
   }
   return RFSB200_OK;
 }
@@ -781,11 +851,11 @@ int rfsb200_download_maps(rfsb200_ctx* c, int which, int64_t cap_total, int32_t*
   const StateBuf& s = c->st[which_buf(c, which)];
   scan_counts_kernel<<<1, 1024, 0, c->stream>>>(s.cnt, c->offs, c->N);
   double* dm = c->stg;
-  double* dc = dm + (size_t)c->N * c->cap * 2;
-  double* dw = dc + (size_t)c->N * c->cap * 3;
+  double* dc = dm + (size_t)c->N * c->cap * c->ld;
+  double* dw = dc + (size_t)c->N * c->cap * c->nc;
   const int blocks = (c->N * 32 + 255) / 256;
-  if (c->prec == 32) unpack_soa_kernel<float><<<blocks, 256, 0, c->stream>>>(s.cnt, c->offs, (const float*)s.gm, dm, dc, dw, c->N, c->cap);
-  else unpack_soa_kernel<double><<<blocks, 256, 0, c->stream>>>(s.cnt, c->offs, (const double*)s.gm, dm, dc, dw, c->N, c->cap);
+  if (c->prec == 32) unpack_soa_kernel<float><<<blocks, 256, 0, c->stream>>>(s.cnt, c->offs, (const float*)s.gm, dm, dc, dw, c->N, c->cap, c->ld, c->nc);
+  else unpack_soa_kernel<double><<<blocks, 256, 0, c->stream>>>(s.cnt, c->offs, (const double*)s.gm, dm, dc, dw, c->N, c->cap, c->ld, c->nc);
   CU(c, cudaGetLastError());
   long long total = 0;
   CU(c, cudaMemcpyAsync(count, s.cnt, (size_t)c->N * 4, cudaMemcpyDeviceToHost, c->stream));
@@ -794,8 +864,8 @@ int rfsb200_download_maps(rfsb200_ctx* c, int which, int64_t cap_total, int32_t*
   if (total > cap_total) return fail(c, RFSB200_ECAPACITY, "%lld Gaussians do not fit caller capacity %lld", total, (long long)cap_total);
   if (total > 0) {
     if (!mean || !cov || !w) return fail(c, RFSB200_EINVAL, "NULL output arrays");
-    CU(c, cudaMemcpyAsync(mean, dm, (size_t)total * 16, cudaMemcpyDeviceToHost, c->stream));
-    CU(c, cudaMemcpyAsync(cov, dc, (size_t)total * 24, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaMemcpyAsync(mean, dm, (size_t)total * c->ld * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaMemcpyAsync(cov, dc, (size_t)total * c->nc * 8, cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaMemcpyAsync(w, dw, (size_t)total * 8, cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
   }

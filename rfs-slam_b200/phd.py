@@ -38,16 +38,20 @@ def pinned_array(shape, dtype=np.float64) -> np.ndarray:
 
 class PHDUpdater:
     def __init__(self, n_particles: int, gm_capacity: int = 256, work_capacity: int = 0,
-                 z_capacity: int = 64, device: int = 0, precision: int = 32):
+                 z_capacity: int = 64, device: int = 0, precision: int = 32, lmk_dim: int = 2):
+        """lmk_dim = 2: MeasurementModel_RngBrg (x, y) / (range, bearing);
+        lmk_dim = 3: MeasurementModel_VictoriaPark (x, y, diameter) / (range, bearing, diameter)."""
         self.lib = capi.load_library()
         self.N = int(n_particles)
+        self.D = int(lmk_dim)
+        self.NC = self.D * (self.D + 1) // 2
         self.gm_capacity = int(gm_capacity)
         d = capi.Dims()
         d.n_particles = self.N
         d.gm_capacity = self.gm_capacity
         d.work_capacity = int(work_capacity) if work_capacity else self.gm_capacity
         d.z_capacity = int(z_capacity)
-        d.lmk_dim, d.meas_dim, d.pose_dim = 2, 2, 3
+        d.lmk_dim, d.meas_dim, d.pose_dim = self.D, self.D, 3
         d.device = int(device)
         d.precision = int(precision)
         self.ctx = C.c_void_p()
@@ -72,6 +76,8 @@ class PHDUpdater:
 
     # ---- configuration ----------------------------------------------------------------------
     def set_model(self, md: dict):
+        """Mirror of the live plugin configuration; call again whenever it changes (the Victoria Park
+        lidar scan changes before every update, src/rbphdslam_VictoriaPark.cpp:582)."""
         d = capi.model_desc(md)
         _check(self.lib, self.ctx, self.lib.rfsb200_set_model(self.ctx, C.byref(d)), "set_model")
 
@@ -124,7 +130,7 @@ class PHDUpdater:
     # ---- the hot path ---------------------------------------------------------------------------
     def update(self, Z, flags: int = capi.UPDATE_DEFAULT, want_stats: bool = True):
         """RBPHDFilter::update(Z) for all particles.  Returns a StepOut (or None if async)."""
-        Z = np.ascontiguousarray(Z, dtype=np.float64).reshape(-1, 2)
+        Z = np.ascontiguousarray(Z, dtype=np.float64).reshape(-1, self.D)
         out = capi.StepOut() if want_stats else None
         rc = self.lib.rfsb200_update(self.ctx, capi.ptr(Z), Z.shape[0], flags,
                                      C.byref(out) if out is not None else None)
@@ -134,7 +140,7 @@ class PHDUpdater:
     # ---- the callers either side (predict's map part, resampling's data movement) -----------------
     def predict_maps(self, Q_lmk=None, add_births: bool = True, birth_weight: float = 0.0):
         """RBPHDFilter::predict() minus the particle propagation: births, then P += Q."""
-        q = None if Q_lmk is None else np.ascontiguousarray(Q_lmk, dtype=np.float64).reshape(3)
+        q = None if Q_lmk is None else np.ascontiguousarray(Q_lmk, dtype=np.float64).reshape(self.NC)
         _check(self.lib, self.ctx,
                self.lib.rfsb200_predict_maps(self.ctx, capi.ptr(q), 1 if add_births else 0, float(birth_weight)),
                "predict_maps")
@@ -186,7 +192,7 @@ class PHDUpdater:
     def get_map(self, i: int, which: int = 0):
         cap = self.gm_capacity + 8
         n = C.c_int32()
-        mean = np.zeros((cap, 2)); cov = np.zeros((cap, 3)); w = np.zeros(cap)
+        mean = np.zeros((cap, self.D)); cov = np.zeros((cap, self.NC)); w = np.zeros(cap)
         _check(self.lib, self.ctx,
                self.lib.rfsb200_get_map(self.ctx, which, i, cap, C.byref(n), capi.ptr(mean), capi.ptr(cov), capi.ptr(w)),
                "get_map")
@@ -200,13 +206,15 @@ class PHDUpdater:
         mean, cov, w = self.get_map(i, which)
         if m < 0 or m >= len(w):
             return False, None, None, None
-        S = np.array([[cov[m, 0], cov[m, 1]], [cov[m, 1], cov[m, 2]]])
+        S = np.zeros((self.D, self.D))
+        S[np.triu_indices(self.D)] = cov[m]
+        S = S + S.T - np.diag(np.diag(S))
         return True, mean[m].copy(), S, float(w[m])
 
     def download_maps(self, which: int = 0):
         cap_total = self.N * (self.gm_capacity + 8)
         count = np.zeros(self.N, dtype=np.int32)
-        mean = np.zeros((cap_total, 2)); cov = np.zeros((cap_total, 3)); w = np.zeros(cap_total)
+        mean = np.zeros((cap_total, self.D)); cov = np.zeros((cap_total, self.NC)); w = np.zeros(cap_total)
         _check(self.lib, self.ctx,
                self.lib.rfsb200_download_maps(self.ctx, which, cap_total, capi.ptr(count), capi.ptr(mean),
                                               capi.ptr(cov), capi.ptr(w)), "download_maps")

@@ -43,7 +43,9 @@ def compare_maps(count_a, mean_a, cov_a, w_a, count_b, mean_b, cov_b, w_b, tol, 
         mb, cb, wb = mb[perm], cb[perm], wb[perm]
         ew = np.abs(wa - wb) - (tol["w_abs"] + tol["w_rel"] * np.abs(wb))
         em = np.abs(ma - mb).max()
-        full = lambda c: np.stack([c[:, 0], c[:, 1], c[:, 1], c[:, 2]], 1)
+        # Frobenius norm of the full symmetric matrix from its upper triangle (2-D: 3 entries, 3-D: 6)
+        offd = np.array([0, 1, 0], bool) if ca.shape[1] == 3 else np.array([0, 1, 1, 0, 1, 0], bool)
+        full = lambda c: np.concatenate([c, c[:, offd]], 1)
         ec = np.linalg.norm(full(ca) - full(cb), axis=1) / np.maximum(np.linalg.norm(full(cb), axis=1), 1e-300)
         if ew.max() > 0 or em > tol["mean_abs"] or ec.max() > tol["cov_rel"]:
             bad.append(i)
@@ -130,7 +132,7 @@ def run_device(wl, precision=32, flags=None, gm_capacity=None, work_capacity=0, 
     from rfs_slam_b200.phd import PHDUpdater
     cap = gm_capacity or int(max(64, (int(wl.count.max()) + 63) // 8 * 8))
     up = PHDUpdater(wl.N, gm_capacity=cap, work_capacity=work_capacity, precision=precision,
-                    z_capacity=z_capacity or max(8, wl.nZ))
+                    z_capacity=z_capacity or max(8, wl.nZ), lmk_dim=wl.dim)
     up.set_model(wl.model)
     up.set_filter_cfg(wl.cfg, brute_force_merge=brute)
     up.upload_maps(wl.count, wl.mean, wl.cov, wl.w)

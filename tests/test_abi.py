@@ -34,7 +34,7 @@ def test_ctypes_mirror_covers_header():
 
 def test_abi_version_and_no_device_behaviour():
     lib = capi.load_library()
-    assert lib.rfsb200_abi_version() == 1
+    assert lib.rfsb200_abi_version() == 2
     n = lib.rfsb200_device_count()
     assert n >= 0
     if n == 0:
