@@ -30,13 +30,21 @@ CASES = {
 }
 
 
+# Victoria Park plugin set (3-D landmarks; rfs::MeasurementModel_VictoriaPark), synth.make_vp_workload
+VP_CASES = {
+    "vp_sc": dict(N=12, nM=70, nZ=10, use_cluster_process=1, config_id=151, parity_extras=True),
+    "vp_mf": dict(N=12, nM=70, nZ=10, use_cluster_process=0, config_id=152, parity_extras=True),
+    "vp_mf_ragged": dict(N=12, nM=90, nZ=14, use_cluster_process=0, config_id=153, ragged=0.3),
+}
+
+
 def main():
     assert ob.have_ref(), "oracle/_ref/libphd_ref.so missing: run `make -C oracle ref` in the build container"
     lib = C.CDLL(ob.REF_LIB)
-    for name, kw in CASES.items():
-        wl = synth.make_workload(**kw)
+    for name, kw in list(CASES.items()) + list(VP_CASES.items()):
+        wl = synth.make_vp_workload(**kw) if name in VP_CASES else synth.make_workload(**kw)
         out = dict(kw_repr=repr(kw), count_in=wl.count, mean_in=wl.mean, cov_in=wl.cov, w_in=wl.w, pose=wl.pose,
-                   pose_cov=wl.pose_cov, weight_in=wl.weight, Z=wl.Z,
+                   pose_cov=(np.zeros(0) if wl.pose_cov is None else wl.pose_cov), weight_in=wl.weight, Z=wl.Z,
                    model_json=json.dumps(wl.model), cfg_json=json.dumps(wl.cfg))
         for st in (1, 2, 3, 4):
             r = ob.run(wl, which="ref", stage=st, n_threads=1)
@@ -66,6 +74,19 @@ def main():
     lib.phd_ref_murty_sum.restype = C.c_double
     lib.phd_ref_murty_sum.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     kat = {}
+    # MeasurementModel_VictoriaPark::probabilityOfDetection on individual landmarks (the scan geometry)
+    wl = synth.make_vp_workload(N=4, nM=160, nZ=10, config_id=154, parity_extras=True)
+    pdv, pdc = [], []
+    for k in range(160):
+        pd, close = ob.vp_pd(wl.model, wl.pose[0], wl.mean[k], wl.cov[k], which="ref")
+        pdv.append(pd); pdc.append(int(close))
+    kat["vp_pd_model_json"] = json.dumps(wl.model)
+    kat["vp_pd_pose"] = wl.pose[0]
+    kat["vp_pd_mean"] = wl.mean[:160]
+    kat["vp_pd_cov"] = wl.cov[:160]
+    kat["vp_pd_vals"] = np.array(pdv)
+    kat["vp_pd_close"] = np.array(pdc)
+    print("vp_pd values:", sorted(set(pdv)), "close:", sum(pdc))
     # permanents of random matrices
     perm_mats, perm_vals = [], []
     for n in range(1, 11):
@@ -116,7 +137,7 @@ def main():
     kat["murty_cl"] = np.concatenate(ms_cl)
     kat["murty_vals"] = np.array(ms_val)
     np.savez_compressed(os.path.join(HERE, "kat_combinatorics.npz"), **kat)
-    print("KATs:", {k: v.shape for k, v in kat.items()})
+    print("KATs:", {k: getattr(v, "shape", None) for k, v in kat.items()})
 
 
 if __name__ == "__main__":
