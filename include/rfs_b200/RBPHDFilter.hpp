@@ -20,8 +20,15 @@
  *
  * Plugin objects cannot be called from the device, so before every update the live plugin
  * objects are read into a POD (rfs::b200::ModelTraits<MeasurementModel, KalmanFilter>::describe).
- * A traits specialisation exists for MeasurementModel_RngBrg + KalmanFilter_RngBrg; other plugin
- * types do not compile against this header (static_assert) — they keep using the reference header.
+ * Traits specialisations exist for MeasurementModel_RngBrg + KalmanFilter_RngBrg (2-D landmarks) and
+ * for MeasurementModel_VictoriaPark + KalmanFilter_VictoriaPark (3-D landmarks, P_D from the lidar
+ * scan); other plugin types do not compile against this header (static_assert) — they keep using the
+ * reference header.
+ *
+ * Birth Gaussians: with birthGaussianMeasurementCountThreshold_ == 1 (the 2-D simulator) they are
+ * created on the device; otherwise (Victoria Park configuration) the candidate lists of
+ * addBirthGaussians() (reference :1000-1080) are kept on the host, evaluated with the live plugin
+ * objects exactly as the reference does, and the promoted candidates are appended to the device maps.
  */
 #ifndef RBPHDFILTER_HPP
 #define RBPHDFILTER_HPP
@@ -45,6 +52,7 @@
 #include "KalmanFilter.hpp"
 #include "ParticleFilter.hpp"
 #include "Timer.hpp"
+#include "KalmanFilter_VictoriaPark.hpp"   /* reference header (also brings MeasurementModel_VictoriaPark.hpp) */
 
 #include "../rfsb200.h"
 
@@ -95,6 +103,67 @@ struct ModelTraits<MeasurementModel_RngBrg, KalmanFilter_RngBrg> {
 };
 }  // namespace b200
 
+/* ---- Victoria Park plugin pair -------------------------------------------------------------------
+ * The lidar scan (setLaserScan) and the beam-angle variance (setNoise(R, Slb)) are private members of
+ * the reference class without getters.  The class is reused UNMODIFIED, so they are read through
+ * member pointers obtained by explicit template instantiation (access checking does not apply to the
+ * arguments of an explicit instantiation, [temp.spec]). */
+namespace b200 {
+namespace detail {
+template <class Tag>
+struct MemberPtr {
+  static typename Tag::type ptr;
+};
+template <class Tag>
+typename Tag::type MemberPtr<Tag>::ptr;
+template <class Tag, typename Tag::type P>
+struct MemberPtrInit {
+  MemberPtrInit() { MemberPtr<Tag>::ptr = P; }
+  static MemberPtrInit instance;
+};
+template <class Tag, typename Tag::type P>
+MemberPtrInit<Tag, P> MemberPtrInit<Tag, P>::instance;
+struct VPScanTag { typedef std::vector<double> MeasurementModel_VictoriaPark::*type; };
+struct VPSlbTag { typedef double MeasurementModel_VictoriaPark::*type; };
+template struct MemberPtrInit<VPScanTag, &MeasurementModel_VictoriaPark::laserscan_>;
+template struct MemberPtrInit<VPSlbTag, &MeasurementModel_VictoriaPark::Slb_>;
+}  // namespace detail
+
+template <>
+struct ModelTraits<MeasurementModel_VictoriaPark, KalmanFilter_VictoriaPark> {
+  static const bool supported = true;
+  static const int lmk_dim = 3, meas_dim = 3, pose_dim = 3;
+  template <class MM, class KF>
+  static void describe(MM& mm, KF& kf, unsigned nZ, rfsb200_model_desc& d) {
+    d = rfsb200_model_desc();
+    d.model_id = RFSB200_MODEL_VICTORIAPARK;
+    typename MM::TMeasurement::Mat R;
+    mm.getNoise(R);
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) d.R[i * 3 + j] = R(i, j);
+    d.Slb = mm.*detail::MemberPtr<detail::VPSlbTag>::ptr;
+    const std::vector<double>& tab = mm.config.probabilityOfDetection_;
+    if (tab.empty() || tab.size() > 16)
+      throw std::runtime_error("rfs::RBPHDFilter (B200): config.probabilityOfDetection_ must hold 1..16 entries");
+    d.pd_table_n = (int32_t)tab.size();
+    for (size_t k = 0; k < tab.size(); k++) d.pd_table[k] = tab[k];
+    typename MM::TMeasurement z;   /* uniform clutter: the value does not depend on z */
+    d.clutter_intensity = mm.clutterIntensity(z, (int)nZ);
+    d.clutter_integral = mm.clutterIntensityIntegral((int)nZ);
+    d.range_min = mm.config.rangeLimMin_;
+    d.range_max = mm.config.rangeLimMax_;
+    d.bearing_min = mm.config.bearingLimitMin_;
+    d.bearing_max = mm.config.bearingLimitMax_;
+    d.buffer_zone_pd = mm.config.bufferZonePd_;
+    const std::vector<double>& scan = mm.*detail::MemberPtr<detail::VPScanTag>::ptr;
+    d.scan = scan.empty() ? NULL : &scan[0];
+    d.scan_n = (int32_t)(scan.size() > 720 ? 720 : scan.size());
+    d.innov_thr_range = kf.config.rangeInnovationThreshold_;
+    d.innov_thr_bearing = kf.config.bearingInnovationThreshold_;
+  }
+};
+}  // namespace b200
+
 template <class RobotProcessModel, class LmkProcessModel, class MeasurementModel, class KalmanFilter>
 class RBPHDFilter : public ParticleFilter<RobotProcessModel, MeasurementModel,
                                           GaussianMixture<typename MeasurementModel::TLandmark> > {
@@ -108,6 +177,8 @@ class RBPHDFilter : public ParticleFilter<RobotProcessModel, MeasurementModel,
   typedef GaussianMixture<TLandmark> TGM;
   typedef typename TGM::Gaussian TGaussian;
   typedef b200::ModelTraits<MeasurementModel, KalmanFilter> Traits;
+  static const int LD = Traits::lmk_dim;          /**< landmark / measurement dimension */
+  static const int NC = LD * (LD + 1) / 2;        /**< unique covariance entries (upper triangle, row-major) */
 
   /** Same fields, same names as the reference (include/RBPHDFilter.hpp:90-146). */
   struct Config {
@@ -188,6 +259,12 @@ class RBPHDFilter : public ParticleFilter<RobotProcessModel, MeasurementModel,
   unsigned int nMeasurementsSinceResample_;
   bool resampleOccured_;
   std::vector<int> pendingAuxSrc_;   /* Q: parent-id lookup of addBirthGaussians after a resample */
+  /* candidate-list births (birthGaussianMeasurementCountThreshold_ != 1), host side as in the reference */
+  std::vector<std::list<BirthGaussianCandidate> > birthGaussians_;
+  std::vector<int> birthParent_;     /* slot whose candidate list slot i takes over after a resample (or i) */
+  bool unusedFresh_;                 /* the device holds unused-measurement masks nobody consumed yet */
+  int nUpdateCalls_;                 /* update() calls with a non-empty measurement set (diagnostics) */
+  void addBirthGaussiansHost();
   rfsb200_step_out lastStep_;
   Timer timer_predict_, timer_particleResample_;
   long long ns_update_;
@@ -217,9 +294,12 @@ template <class R, class L, class M, class K>
 RBPHDFilter<R, L, M, K>::RBPHDFilter(int n)
     : ParticleFilter<R, M, GaussianMixture<typename M::TLandmark> >(n),
       ctx_(NULL), nAlloc_(0), kf_(), lmkModelPtr_(new L), nUpdatesSinceResample_(0), nMeasurementsSinceResample_(0),
-      resampleOccured_(false), ns_update_(0), cacheIdx_(-1), cN_(0) {
+      resampleOccured_(false), unusedFresh_(false), nUpdateCalls_(0), ns_update_(0), cacheIdx_(-1), cN_(0) {
   kf_ = K(lmkModelPtr_, this->getMeasurementModel());
   for (int i = 0; i < n; i++) this->particleSet_[i]->setData(boost::shared_ptr<TGM>(new TGM()));
+  birthGaussians_.resize(n);
+  birthParent_.resize(n);
+  for (int i = 0; i < n; i++) birthParent_[i] = i;
   /* reference defaults (include/RBPHDFilter.hpp:370-382); the two it leaves uninitialised get
    * defined values */
   config.birthGaussianWeight_ = 0.25;
@@ -311,8 +391,8 @@ void RBPHDFilter<R, L, M, K>::predict(TInput u, TimeStamp const& dT, bool useMod
   timer_predict_.resume();
   ensureCtx();
   invalidateCache();
-  if (birthGaussianCheck && config.birthGaussianMeasurementCountThreshold_ != 1)
-    throw std::runtime_error("rfs::RBPHDFilter (B200): birthGaussianMeasurementCountThreshold_ != 1 (candidate-list births) is not implemented on the device");
+  const bool hostBirths = birthGaussianCheck && config.birthGaussianMeasurementCountThreshold_ != 1;
+  if (hostBirths) addBirthGaussiansHost();
   /* landmark process noise: StaticProcessModel::step adds Q only if it was set (ProcessModel.hpp:198) */
   typename TLandmark::Mat Q;
   const double nan = std::numeric_limits<double>::quiet_NaN();
@@ -320,12 +400,14 @@ void RBPHDFilter<R, L, M, K>::predict(TInput u, TimeStamp const& dT, bool useMod
     for (int j = 0; j < Q.cols(); j++) Q(i, j) = nan;
   lmkModelPtr_->getNoise(Q);
   const bool haveQ = (Q(0, 0) == Q(0, 0));
-  double q[3] = {0, 0, 0};
-  if (haveQ) { q[0] = Q(0, 0); q[1] = Q(0, 1); q[2] = Q(1, 1); }
+  double q[NC];
+  for (int r = 0, k = 0; r < LD; r++)
+    for (int c = r; c < LD; c++, k++) q[k] = haveQ ? Q(r, c) : 0.0;
   /* births use the pose BEFORE the propagation = the pose of the last update, still on the device
    * (addBirthGaussians runs first in the reference too, :425-427) */
-  check(rfsb200_predict_maps(ctx_, haveQ ? q : NULL, birthGaussianCheck ? 1 : 0, config.birthGaussianWeight_),
+  check(rfsb200_predict_maps(ctx_, haveQ ? q : NULL, (birthGaussianCheck && !hostBirths) ? 1 : 0, config.birthGaussianWeight_),
         "rfsb200_predict_maps");
+  if (birthGaussianCheck && !hostBirths) unusedFresh_ = false;
   this->propagate(u, dT, useModelNoise, useInputNoise, true);
   timer_predict_.stop();
 }
@@ -356,17 +438,57 @@ void RBPHDFilter<R, L, M, K>::update(std::vector<TMeasurement>& Z) {
   check(rfsb200_set_filter_cfg(ctx_, &fc), "rfsb200_set_filter_cfg");
 
   uploadPoses();
-  std::vector<double> z((size_t)nZ * 2);
+  std::vector<double> z((size_t)nZ * LD);
   for (unsigned k = 0; k < nZ; k++) {
     typename TMeasurement::Vec v;
     this->measurements_[k].get(v);
-    z[2 * k] = v(0);
-    z[2 * k + 1] = v(1);
+    for (int d = 0; d < LD; d++) z[LD * k + d] = v(d);
+  }
+  nUpdateCalls_++;
+  if (const char* e = getenv("RFSB200_DUMP_UPDATE")) {
+    /* diagnostics for unchanged drivers: the complete input of the k-th update() goes to a file that
+     * tools/replay_dump.py feeds to the oracle and to the device (layout documented there) */
+    if (atoi(e) == nUpdateCalls_) {
+      const int N = this->nParticles_;
+      std::vector<int32_t> cnt(N);
+      const int64_t capTotal = (int64_t)N * (deviceConfig.gmCapacity + 8);
+      std::vector<double> mean((size_t)capTotal * LD), cov((size_t)capTotal * NC), w((size_t)capTotal);
+      check(rfsb200_download_maps(ctx_, 0, capTotal, cnt.data(), mean.data(), cov.data(), w.data()), "rfsb200_download_maps");
+      int64_t total = 0;
+      for (int i = 0; i < N; i++) total += cnt[i];
+      char name[64];
+      snprintf(name, sizeof(name), "rfsb200_dump_%d.bin", nUpdateCalls_);
+      FILE* f = fopen(name, "wb");
+      if (f) {
+        int32_t hdr[6] = {0x52465342, N, LD, (int32_t)nZ, (int32_t)sizeof(md), (int32_t)sizeof(fc)};
+        fwrite(hdr, 4, 6, f);
+        fwrite(cnt.data(), 4, N, f);
+        fwrite(&total, 8, 1, f);
+        fwrite(mean.data(), 8, (size_t)total * LD, f);
+        fwrite(cov.data(), 8, (size_t)total * NC, f);
+        fwrite(w.data(), 8, (size_t)total, f);
+        fwrite(hPose_.data(), 8, (size_t)N * 3, f);
+        fwrite(hPoseCov_.data(), 8, (size_t)N * 6, f);
+        fwrite(hW_.data(), 8, N, f);
+        fwrite(z.data(), 8, z.size(), f);
+        fwrite(&md, sizeof(md), 1, f);
+        int32_t sn = md.scan ? md.scan_n : 0;
+        fwrite(&sn, 4, 1, f);
+        if (sn) fwrite(md.scan, 8, sn, f);
+        fwrite(&fc, sizeof(fc), 1, f);
+        fclose(f);
+      }
+    }
   }
   /* all particles: map update, weighting, merge, prune, weight sums — no normalisation yet, the
    * resampling gate needs the unnormalised weights exactly like the reference */
   check(rfsb200_update(ctx_, z.data(), (int32_t)nZ, RFSB200_UPDATE_NO_NORMALIZE, &lastStep_), "rfsb200_update");
   ns_update_ += (long long)(lastStep_.elapsed_us * 1000.0);
+  unusedFresh_ = true;
+  if (getenv("RFSB200_TRACE"))   /* diagnostics for unchanged drivers: one line per update on stderr */
+    fprintf(stderr, "[rfsb200] update nZ=%u gm_in=%lld gm_out=%lld max_out=%d overflow=%d murty=%d device_us=%.1f\n", nZ,
+            (long long)lastStep_.gm_total_in, (long long)lastStep_.gm_total_out, lastStep_.gm_max_out, lastStep_.n_overflow,
+            lastStep_.n_murty, lastStep_.elapsed_us);
   check(rfsb200_get_weights(ctx_, 0, hW_.data()), "rfsb200_get_weights");
   for (int i = 0; i < this->nParticles_; i++) this->particleSet_[i]->setWeight(hW_[i]);
 
@@ -448,6 +570,10 @@ bool RBPHDFilter<R, L, M, K>::resample(unsigned int n, bool forceResample) {
     if (parent == (unsigned)i || parent >= (unsigned)N) auxSrc[i] = i;
     else auxSrc[i] = (parent > (unsigned)i) ? (int)parent : -1;
   }
+  for (int i = 0; i < N; i++) {
+    const unsigned parent = this->particleSet_[i]->getParentId();
+    birthParent_[i] = (parent == (unsigned)i || parent >= (unsigned)N) ? i : (int)parent;
+  }
   for (int i = 0; i < N; i++) this->particleSet_[i]->setWeight(1);
   const double one = 1.0;
   check(rfsb200_resample(ctx_, mapSrc.data(), auxSrc.data(), &one), "rfsb200_resample");
@@ -474,8 +600,8 @@ bool RBPHDFilter<R, L, M, K>::getLandmark(const int i, const int m, typename TLa
   ensureCtx();
   if (cacheIdx_ != i) {
     const int cap = deviceConfig.gmCapacity + 8;
-    cMean_.resize((size_t)cap * 2);
-    cCov_.resize((size_t)cap * 3);
+    cMean_.resize((size_t)cap * LD);
+    cCov_.resize((size_t)cap * NC);
     cW_.resize(cap);
     int32_t n = 0;
     check(rfsb200_get_map(ctx_, 0, i, cap, &n, cMean_.data(), cCov_.data(), cW_.data()), "rfsb200_get_map");
@@ -483,13 +609,93 @@ bool RBPHDFilter<R, L, M, K>::getLandmark(const int i, const int m, typename TLa
     cacheIdx_ = i;
   }
   if (m < 0 || m >= cN_) return false;
-  u(0) = cMean_[2 * m];
-  u(1) = cMean_[2 * m + 1];
-  S(0, 0) = cCov_[3 * m];
-  S(0, 1) = S(1, 0) = cCov_[3 * m + 1];
-  S(1, 1) = cCov_[3 * m + 2];
+  for (int d = 0; d < LD; d++) u(d) = cMean_[LD * m + d];
+  for (int r = 0, k = 0; r < LD; r++)
+    for (int c = r; c < LD; c++, k++) S(r, c) = S(c, r) = cCov_[NC * m + k];
   w = cW_[m];
   return true;
+}
+
+/* addBirthGaussians() of the reference (include/RBPHDFilter.hpp:1000-1080) for the candidate-list
+ * configuration: the unused measurements and nLandmarksInFOV_ of the last update come from the device,
+ * the candidate lists live here, the plugin objects are the live host ones, and the Gaussians that
+ * become real go to the device maps in the order the reference would have appended them. */
+template <class R, class L, class M, class K>
+void RBPHDFilter<R, L, M, K>::addBirthGaussiansHost() {
+  const int N = this->nParticles_;
+  std::vector<uint64_t> mask(N, 0);
+  std::vector<int32_t> nfov(N, 0);
+  if (unusedFresh_) check(rfsb200_get_unused(ctx_, mask.data(), nfov.data()), "rfsb200_get_unused");
+  else check(rfsb200_get_unused(ctx_, NULL, nfov.data()), "rfsb200_get_unused");
+  std::vector<int32_t> addCount(N, 0);
+  std::vector<double> aMean, aCov, aW;
+  const unsigned nZ = this->measurements_.size();
+  for (int i = 0; i < N; i++) {
+    if (resampleOccured_ && birthParent_[i] != i) birthGaussians_[i] = birthGaussians_[birthParent_[i]];   /* :1005-1011 */
+    std::list<BirthGaussianCandidate>& cand = birthGaussians_[i];
+    TPose x = *(this->particleSet_[i]);
+    auto addReal = [&](TLandmark& lm) {
+      typename TLandmark::Vec u;
+      typename TLandmark::Mat S;
+      lm.get(u, S);
+      for (int d = 0; d < LD; d++) aMean.push_back(u(d));
+      for (int r = 0; r < LD; r++)
+        for (int c = r; c < LD; c++) aCov.push_back(S(r, c));
+      aW.push_back(config.birthGaussianWeight_);
+      addCount[i]++;
+    };
+    for (int zi = (int)nZ - 1; zi >= 0; zi--) {   /* the reference pops the list from the back: descending index */
+      if (!((mask[i] >> zi) & 1ull)) continue;
+      TMeasurement unused_z = this->measurements_[zi];
+      bool isNew = true;
+      for (typename std::list<BirthGaussianCandidate>::iterator it = cand.begin(); it != cand.end(); it++) {
+        TMeasurement z_exp;
+        this->pMeasurementModel_->measure(x, *it, z_exp);
+        const double d2 = z_exp.mahalanobisDist2(unused_z);
+        if (d2 <= config.birthGaussianMeasurementSupportDist_ * config.birthGaussianMeasurementSupportDist_) {
+          kf_.correct(x, unused_z, *it, *it);
+          (it->nSupportingMeasurements)++;
+          isNew = false;
+          break;
+        }
+      }
+      if (isNew) {
+        BirthGaussianCandidate c;
+        c.nSupportingMeasurements = 1;
+        c.nChecks = 0;
+        this->pMeasurementModel_->inverseMeasure(x, unused_z, c);
+        if (config.birthGaussianMeasurementCountThreshold_ == 1 ||
+            (unsigned)nfov[i] <= config.birthGaussianCurrentMeasurementCountThreshold_)
+          addReal(c);
+        else
+          cand.push_back(c);
+      }
+    }
+    /* :1056-1075.  When the LAST candidate of the list is erased the reference leaves its while loop with
+     * it == end() and then increments it in the for statement; with libstdc++'s circular list that lands on
+     * begin() again, i.e. the remaining candidates get another pass (nChecks++ each).  Reproduced as built. */
+    typename std::list<BirthGaussianCandidate>::iterator it = cand.begin();
+    while (it != cand.end()) {
+      it->nChecks++;
+      bool wrapped = false;
+      while (it->nSupportingMeasurements >= config.birthGaussianMeasurementCountThreshold_ ||
+             it->nChecks > config.birthGaussianMeasurementCheckThreshold_ ||
+             (unsigned)nfov[i] <= config.birthGaussianCurrentMeasurementCountThreshold_) {
+        if (it->nSupportingMeasurements >= config.birthGaussianMeasurementCountThreshold_) addReal(*it);
+        else if ((unsigned)nfov[i] <= config.birthGaussianCurrentMeasurementCountThreshold_) addReal(*it);
+        it = cand.erase(it);
+        if (it != cand.end()) it->nChecks++;
+        else { wrapped = true; break; }
+      }
+      if (wrapped) it = cand.begin();
+      else ++it;
+    }
+  }
+  check(rfsb200_append_gaussians(ctx_, addCount.data(), aMean.empty() ? NULL : &aMean[0], aCov.empty() ? NULL : &aCov[0],
+                                 aW.empty() ? NULL : &aW[0]),
+        "rfsb200_append_gaussians");
+  if (unusedFresh_) check(rfsb200_predict_maps(ctx_, NULL, -1, 0.0), "rfsb200_predict_maps(clear)");   /* masks consumed */
+  unusedFresh_ = false;
 }
 
 template <class R, class L, class M, class K>

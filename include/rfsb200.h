@@ -204,9 +204,22 @@ int rfsb200_update(rfsb200_ctx* ctx, const double* Z /*[nZ][meas_dim]*/, int32_t
  *   Q_lmk != NULL: StaticProcessModel::staticStep on every Gaussian incl. the births: P += Q
  *     (include/ProcessModel.hpp:195-219); Q_lmk = upper triangle (xx, xy, yy), already scaled by the
  *     caller exactly as it scales the plugin's Q.
+ *   add_births < 0: no births, but the unused-measurement masks are cleared (the host consumed them, see
+ *     rfsb200_append_gaussians).
+ * For RFSB200_MODEL_VICTORIAPARK the births are at MeasurementModel_VictoriaPark::inverseMeasure
+ * (src/MeasurementModel_VictoriaPark.cpp:75-102) and Q_lmk has 6 entries (xx, xy, xz, yy, yz, zz).
  * Runs on the committed state, in place.  Births that do not fit gm_capacity set flag bit 1. */
-int rfsb200_predict_maps(rfsb200_ctx* ctx, const double* Q_lmk /*[3] or NULL*/, int32_t add_births,
+int rfsb200_predict_maps(rfsb200_ctx* ctx, const double* Q_lmk /*[3] / [6] or NULL*/, int32_t add_births,
                          double birth_weight);
+
+/* Appends Gaussians to the committed maps: count[i] Gaussians (packed like rfsb200_upload_maps) go behind the
+ * existing ones of particle i.  This is GaussianMixture::addGaussian (include/GaussianMixture.hpp:267-284)
+ * for the birth Gaussians the HOST decides on — the candidate-list form of addBirthGaussians()
+ * (include/RBPHDFilter.hpp:1023-1080, used when birthGaussianMeasurementCountThreshold_ != 1, e.g. the
+ * Victoria Park configuration) keeps its per-particle candidate lists on the host.  Gaussians that do not
+ * fit gm_capacity are dropped and set flag bit 1 of the particle. */
+int rfsb200_append_gaussians(rfsb200_ctx* ctx, const int32_t* count /*[N]*/, const double* mean,
+                             const double* cov, const double* w);
 
 /* The data movement of ParticleFilter::resample() (include/ParticleFilter.hpp:446-479): particle i
  * of the new set takes the map of particle map_src[i] and the unused-measurement mask / in-FOV count of

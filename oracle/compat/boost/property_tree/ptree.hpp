@@ -17,6 +17,7 @@ class ptree {
   typedef std::pair<std::string, ptree> value_type;
   std::string data_;
   children_t kids_;
+  const std::string& data() const { return data_; }
   const_iterator begin() const { return kids_.begin(); }
   const_iterator end() const { return kids_.end(); }
   iterator begin() { return kids_.begin(); }

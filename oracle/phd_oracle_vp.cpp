@@ -15,7 +15,8 @@
  *
  * One deliberate definition where the reference has undefined behaviour: a lidar-scan index
  * >= scan_n (the reference indexes a 361-entry vector with values up to 719,
- * src/MeasurementModel_VictoriaPark.cpp:249-255) reads as 0 ("no return").
+ * src/MeasurementModel_VictoriaPark.cpp:249-255) counts no lidar point, which is what the reference
+ * binary does in practice (the heap bytes behind the vector are neither > minrange nor == 0).
  */
 #include "phd_oracle.h"
 
@@ -136,7 +137,8 @@ void vp_measure(const rfsb200_model_desc& md, const double* pose, const double* 
 }
 
 inline double scan_at(const rfsb200_model_desc& md, int b) {
-  return (b >= 0 && b < md.scan_n) ? md.scan[b] : 0.0; /* reference: out-of-bounds read */
+  /* reference: out-of-bounds read (heap bytes behind the vector: neither a range nor exactly 0) -> no point */
+  return (b >= 0 && b < md.scan_n) ? md.scan[b] : std::numeric_limits<double>::quiet_NaN();
 }
 
 /* src/MeasurementModel_VictoriaPark.cpp:202-266 */

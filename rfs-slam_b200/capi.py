@@ -114,6 +114,7 @@ _SIGS = {
     "rfsb200_set_filter_cfg": (C.c_int, [_P, C.POINTER(FilterCfg)]),
     "rfsb200_upload_maps": (C.c_int, [_P, _P, _P, _P, _P]),
     "rfsb200_set_poses": (C.c_int, [_P, _P, _P, C.c_int, _P]),
+    "rfsb200_append_gaussians": (C.c_int, [_P, _P, _P, _P, _P]),
     "rfsb200_update": (C.c_int, [_P, _P, C.c_int32, C.c_uint32, C.POINTER(StepOut)]),
     "rfsb200_predict_maps": (C.c_int, [_P, _P, C.c_int32, C.c_double]),
     "rfsb200_resample": (C.c_int, [_P, _P, _P, _P]),

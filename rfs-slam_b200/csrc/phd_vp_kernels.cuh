@@ -73,7 +73,9 @@ __device__ __forceinline__ double vp_pd2(const VPGeom& g, double px, double py, 
   const double minrange = dist - mr - 6 * 0.03;
   if ((maxb - minb + 720) % 720 > 0) {
     for (int b = minb; b != maxb; b = (b + 1) % 720) {
-      const double s = b < g.scan_n ? g.scan[b] : 0.0;   // the reference reads out of bounds here
+      // beyond the scan the reference reads past the end of its vector (361 entries, indices up to 719):
+      // whatever lies there is neither a plausible range nor exactly 0, so such a beam counts no point
+      const double s = b < g.scan_n ? g.scan[b] : __longlong_as_double(0x7ff8000000000000LL);
       if (s > minrange || s == 0.0) numPoints++;
     }
   }

@@ -156,6 +156,35 @@ __global__ void unpack_soa_kernel(const int* __restrict__ cnt, const long long* 
   }
 }
 
+// packed fp64 Gaussians appended behind the existing ones of each particle (births decided by the host)
+template <typename T>
+__global__ void append_soa_kernel(const int* __restrict__ add, const long long* __restrict__ offs,
+                                  const double* __restrict__ mean, const double* __restrict__ cov,
+                                  const double* __restrict__ w, T* __restrict__ gm, int* __restrict__ cnt,
+                                  int* __restrict__ flags, int N, int cap, int ld, int nc) {
+  const int lane = threadIdx.x & 31;
+  const int pi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (pi >= N) return;
+  const int na = add[pi];
+  if (na <= 0) return;
+  const int n0 = cnt[pi];
+  const long long o = offs[pi];
+  T* g = gm + (size_t)pi * (ld + nc + 1) * cap;
+  const int fit = (n0 + na > cap) ? (cap - n0 > 0 ? cap - n0 : 0) : na;
+  for (int k = lane; k < fit; k += 32) {
+    const long long s = o + k;
+    const int j = n0 + k;
+    for (int d = 0; d < ld; d++) g[d * cap + j] = (T)mean[ld * s + d];
+    for (int d = 0; d < nc; d++) g[(ld + d) * cap + j] = (T)cov[nc * s + d];
+    g[(ld + nc) * cap + j] = (T)w[s];
+  }
+  __syncwarp();
+  if (lane == 0) {
+    cnt[pi] = n0 + fit;
+    if (fit < na) flags[pi] |= FLAG_OVERFLOW;
+  }
+}
+
 // exclusive scan of counts -> offsets[N+1]; single CTA (N is at most a few 10^5)
 __global__ void scan_counts_kernel(const int* __restrict__ cnt, long long* __restrict__ offs, int N) {
   __shared__ long long part[1024];
@@ -609,6 +638,37 @@ int rfsb200_upload_maps(rfsb200_ctx* c, const int32_t* count, const double* mean
   return RFSB200_OK;
 }
 
+int rfsb200_append_gaussians(rfsb200_ctx* c, const int32_t* count, const double* mean, const double* cov, const double* w) {
+  if (!c || !count) return fail(c, RFSB200_EINVAL, "NULL argument");
+  if (!c->have_maps) return fail(c, RFSB200_ESTATE, "append_gaussians before upload_maps");
+  CU(c, cudaSetDevice(c->device));
+  long long total = 0;
+  for (int i = 0; i < c->N; i++) {
+    if (count[i] < 0) return fail(c, RFSB200_EINVAL, "negative count for particle %d", i);
+    total += count[i];
+  }
+  if (total == 0) return RFSB200_OK;
+  if (total > (long long)c->N * c->cap) return fail(c, RFSB200_ECAPACITY, "%lld Gaussians exceed the staging capacity", total);
+  if (!mean || !cov || !w) return fail(c, RFSB200_EINVAL, "NULL map arrays");
+  StateBuf& s = c->st[c->front];
+  int* add_dev = c->src_dev;   // [2N] ints of scratch; the resample sources are not live between calls
+  CU(c, cudaMemcpyAsync(add_dev, count, (size_t)c->N * 4, cudaMemcpyHostToDevice, c->stream));
+  scan_counts_kernel<<<1, 1024, 0, c->stream>>>(add_dev, c->offs, c->N);
+  double* dm = c->stg;
+  double* dc = dm + (size_t)c->N * c->cap * c->ld;
+  double* dw = dc + (size_t)c->N * c->cap * c->nc;
+  CU(c, cudaMemcpyAsync(dm, mean, (size_t)total * c->ld * 8, cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaMemcpyAsync(dc, cov, (size_t)total * c->nc * 8, cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaMemcpyAsync(dw, w, (size_t)total * 8, cudaMemcpyHostToDevice, c->stream));
+  const int blocks = (c->N * 32 + 255) / 256;
+  if (c->prec == 32) append_soa_kernel<float><<<blocks, 256, 0, c->stream>>>(add_dev, c->offs, dm, dc, dw, (float*)s.gm, s.cnt, c->flags, c->N, c->cap, c->ld, c->nc);
+  else append_soa_kernel<double><<<blocks, 256, 0, c->stream>>>(add_dev, c->offs, dm, dc, dw, (double*)s.gm, s.cnt, c->flags, c->N, c->cap, c->ld, c->nc);
+  CU(c, cudaGetLastError());
+  CU(c, cudaStreamSynchronize(c->stream));   // the caller's (pageable) buffers may go away
+  c->last_out = c->front;
+  return RFSB200_OK;
+}
+
 int rfsb200_set_poses(rfsb200_ctx* c, const double* pose, const double* pose_cov, int mode, const double* weight) {
   if (!c || !pose) return fail(c, RFSB200_EINVAL, "NULL argument");
   if (mode < 0 || mode > 2 || (mode > 0 && !pose_cov)) return fail(c, RFSB200_EINVAL, "bad pose_cov_mode");
@@ -701,6 +761,11 @@ int rfsb200_update(rfsb200_ctx* c, const double* Z, int32_t nZ, uint32_t flags, 
 int rfsb200_predict_maps(rfsb200_ctx* c, const double* Q, int32_t add_births, double birth_w) {
   if (!c) return fail(nullptr, RFSB200_EINVAL, "NULL ctx");
   if (!c->have_maps) return fail(c, RFSB200_ESTATE, "predict_maps before upload_maps");
+  if (add_births < 0) {   // the host consumed the unused measurements itself (candidate-list births)
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaMemsetAsync(c->unused, 0, (size_t)c->N * 8, c->stream));
+    add_births = 0;
+  }
   if (c->last_nZ == 0) add_births = 0;   // no update yet: there is no unused measurement to give birth from
   if (add_births && (!c->have_model || !c->have_poses))
     return fail(c, RFSB200_ESTATE, "births need set_model and set_poses (pose and R of the last update)");

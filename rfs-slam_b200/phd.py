@@ -106,6 +106,16 @@ class PHDUpdater:
                self.lib.rfsb200_upload_maps(self.ctx, capi.ptr(count), capi.ptr(mean), capi.ptr(cov), capi.ptr(w)),
                "upload_maps")
 
+    def append_gaussians(self, count, mean, cov, w):
+        """GaussianMixture::addGaussian for host-decided births: count[i] packed Gaussians behind the map of particle i."""
+        count = np.ascontiguousarray(count, dtype=np.int32)
+        mean = np.ascontiguousarray(mean, dtype=np.float64)
+        cov = np.ascontiguousarray(cov, dtype=np.float64)
+        w = np.ascontiguousarray(w, dtype=np.float64)
+        _check(self.lib, self.ctx,
+               self.lib.rfsb200_append_gaussians(self.ctx, capi.ptr(count), capi.ptr(mean), capi.ptr(cov), capi.ptr(w)),
+               "append_gaussians")
+
     def set_poses(self, pose, pose_cov=None, weight=None):
         """Particle poses (+ optional pose covariance, Q1) and weights; ascontiguousarray keeps a
         pinned float64 input as it is, so the H2D copy reads the caller's page-locked buffer."""
