@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — PHD filter updates/s of the B200 PHD measurement-update path.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--config C3|C2|C4g] [--impl b200|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config C3|C2|C3mf|C5|...] [--impl b200|reference]
 
 A "step" is one RBPHDFilter::update() (map update + particle weighting + merge + prune + weight
 sums (+ all-reduce) + normalisation) over one batch of synthetic particles; an "update" is one
@@ -39,6 +39,8 @@ WORKLOADS = {
     "C3sparse": ("C3", 8000, "C3 shape, sparse world (about 11 % of the components in range), SC-PHD"),
     "N1k": ("C3", 1000, "north_star sweep: 1000 particles per GPU x 200 GM x 30 meas, SC-PHD"),
     "N64k": ("C3", 64000, "north_star sweep: 64000 particles per GPU x 200 GM x 30 meas, SC-PHD"),
+    "C5": ("C5", 4000, "C5 shape: 4000 particles per GPU x 150 GM (3-D: x, y, diameter) x 12 meas, MeasurementModel_VictoriaPark "
+                       "(P_D from a 720-beam lidar scan), multi-feature weighting"),
 }
 
 
@@ -218,7 +220,9 @@ def main():
     wl, desc = make_workload(a.config, rank, a.particles)
     N, nZ = wl.N, wl.nZ
     units_local = int(wl.count.sum()) * nZ
-    up = PHDUpdater(N, gm_capacity=256, z_capacity=32, device=local, precision=32)
+    D = wl.dim                                  # 2: RngBrg, 3: VictoriaPark
+    gbytes = 4.0 * (D + D * (D + 1) // 2 + 1)   # fp32 bytes per Gaussian: 24 (2-D) / 40 (3-D)
+    up = PHDUpdater(N, gm_capacity=256, z_capacity=32, device=local, precision=32, lmk_dim=D)
     up.load_workload(wl)
     sh = ShardedUpdater(up, device=dev, fused=not a.no_fused)
     fused = not a.no_fused
@@ -278,7 +282,11 @@ def main():
         h_nfov = pinned_array((N,), np.int32)
         pc = wl.pose_cov
 
+        md_desc = capi.model_desc(wl.model)
+
         def e2e_step():
+            if D == 3:                                        # the lidar scan changes before every update
+                up.set_model_desc(md_desc)                    # H2D: scan (staged through pinned memory)
             up.set_poses(h_pose, pc, h_w)                     # H2D: poses + particle weights (pinned)
             s = sh.step(wl.Z, flags=FLAGS, want_stats=False)  # H2D: Z ; kernels ; all-reduce
             up.get_weights(1, out=h_wout)                     # D2H: normalised particle weights
@@ -305,7 +313,7 @@ def main():
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         te_max = float(tt.item())
-        h2d = N * 3 * 8 + N * 8 + 6 * 8 + nZ * 2 * 8
+        h2d = N * 3 * 8 + N * 8 + (6 * 8 if pc is not None else 0) + nZ * D * 8 + (len(wl.model["scan"]) * 8 if D == 3 else 0)
         d2h = N * 8 + N * 8 + N * 4
         e2e = dict(value=units_total * Ke / te_max, unit=UNIT, h2d_bytes_per_step=h2d * world, d2h_bytes_per_step=d2h * world,
                    ms_per_step=1e3 * te_max / Ke, wall_ms_per_step_incl_flush=1e3 * tw / Ke,
@@ -315,7 +323,10 @@ def main():
     # ---- roofline of the dominant kernel (phd_update_kernel), live ------------------------------------
     peak, peak_src = _peaks()
     nM_in = int(wl.count.sum()) / N
-    b_alg = N * (24.0 * nM_in + 24.0 * nM_out_mean + 60.0) + 8.0 * nZ      # SURVEY §8(d), DESIGN.md
+    per_particle = 60.0 if D == 2 else 36.0   # pose 12 + pose cov 24 (2-D model only) + weight r/w 16 + count r/w 8
+    b_alg = N * (gbytes * nM_in + gbytes * nM_out_mean + per_particle) + 4.0 * D * nZ      # SURVEY §8(d), DESIGN.md
+    if D == 3:
+        b_alg += 8.0 * len(wl.model["scan"])
     k_us = float(np.mean(kern_us)) if len(kern_us) else float("nan")
     achieved = b_alg / (k_us * 1e-6) / 1e9
     traffic = None
@@ -326,7 +337,7 @@ def main():
         except Exception:
             traffic = None
     roofline = dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic,
-                    kernel="phd_update_kernel<float>", kernel_us=k_us, algorithmic_bytes=b_alg, peak_source=peak_src,
+                    kernel=("phd_update_kernel<float>" if D == 2 else "phd_update_vp_kernel<float>"), kernel_us=k_us, algorithmic_bytes=b_alg, peak_source=peak_src,
                     kernel_share_of_step=k_us * 1e-3 / (1e3 * t_local / K))
 
     line = None

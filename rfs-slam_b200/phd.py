@@ -81,6 +81,10 @@ class PHDUpdater:
         d = capi.model_desc(md)
         _check(self.lib, self.ctx, self.lib.rfsb200_set_model(self.ctx, C.byref(d)), "set_model")
 
+    def set_model_desc(self, d):
+        """set_model with a prebuilt capi.ModelDesc (no dict conversion on the per-update path)."""
+        _check(self.lib, self.ctx, self.lib.rfsb200_set_model(self.ctx, C.byref(d)), "set_model")
+
     def set_filter_cfg(self, fc: dict, brute_force_merge: bool = False):
         c = capi.filter_cfg(fc)
         c.reserved_i[0] = 1 if brute_force_merge else 0

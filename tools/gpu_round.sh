@@ -11,10 +11,12 @@ if [ "$2" != "notests" ]; then
 fi
 timeout 600 python bench.py --steps 50 --warmup 5 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err
 echo "bench rc=$?"; cat gpurun_out/bench_$TAG.json; tail -3 gpurun_out/bench_$TAG.err
-timeout 300 python bench.py --steps 50 --warmup 5 --config C2 --no-cpu-baseline > gpurun_out/bench_C2_$TAG.json 2>> gpurun_out/bench_$TAG.err
-cat gpurun_out/bench_C2_$TAG.json
-timeout 300 python bench.py --steps 20 --warmup 5 --config C3mf --no-cpu-baseline > gpurun_out/bench_C3mf_$TAG.json 2>> gpurun_out/bench_$TAG.err
-cat gpurun_out/bench_C3mf_$TAG.json
+for C in C2 C3mf C5; do
+  timeout 300 python bench.py --steps 20 --warmup 5 --config $C > gpurun_out/bench_${C}_$TAG.json 2>> gpurun_out/bench_$TAG.err
+  cat gpurun_out/bench_${C}_$TAG.json
+done
+timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref_$TAG.json 2>> gpurun_out/bench_$TAG.err
+cat gpurun_out/bench_ref_$TAG.json
 # launch list of the same bench command (cold-cache, serialised: shares only)
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv \
   python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_launch_$TAG.log 2>&1
