@@ -283,15 +283,14 @@ def main():
         pc = wl.pose_cov
 
         md_desc = capi.model_desc(wl.model)
+        Zc = np.ascontiguousarray(wl.Z, dtype=np.float64)
 
         def e2e_step():
             if D == 3:                                        # the lidar scan changes before every update
                 up.set_model_desc(md_desc)                    # H2D: scan (staged through pinned memory)
-            up.set_poses(h_pose, pc, h_w)                     # H2D: poses + particle weights (pinned)
-            s = sh.step(wl.Z, flags=FLAGS, want_stats=False)  # H2D: Z ; kernels ; all-reduce
-            up.get_weights(1, out=h_wout)                     # D2H: normalised particle weights
-            up.get_unused(h_mask, h_nfov)                     # D2H: unused-measurement masks, nLandmarksInFOV
-            return s
+            # H2D: poses + particle weights (pinned) + Z ; kernels (+ cross-GPU sum) ; D2H: normalised particle
+            # weights, unused-measurement masks, nLandmarksInFOV — one ABI call, one synchronisation (fused path)
+            return sh.step_host(h_pose, pc, h_w, Zc, flags=FLAGS, w_out=h_wout, unused_out=h_mask, nfov_out=h_nfov)
 
         for _ in range(3):
             e2e_step()
@@ -317,8 +316,11 @@ def main():
         d2h = N * 8 + N * 8 + N * 4
         e2e = dict(value=units_total * Ke / te_max, unit=UNIT, h2d_bytes_per_step=h2d * world, d2h_bytes_per_step=d2h * world,
                    ms_per_step=1e3 * te_max / Ke, wall_ms_per_step_incl_flush=1e3 * tw / Ke,
-                   what="per step: rfsb200_set_poses(pinned host poses+weights) + rfsb200_update(host Z) + "
-                        "rfsb200_get_weights + rfsb200_get_unused into pinned host buffers; maps stay resident in HBM")
+                   what=("per step: rfsb200_update_host = pinned host poses + particle weights + Z in, update (+ cross-GPU sum + "
+                         "normalisation), normalised weights + unused-measurement masks + in-FOV counts out into pinned host "
+                         "buffers, one synchronisation; maps stay resident in HBM" if fused else
+                         "per step: rfsb200_set_poses(pinned host poses+weights) + rfsb200_update(host Z) + NCCL all-reduce + "
+                         "rfsb200_normalize + rfsb200_get_weights + rfsb200_get_unused into pinned host buffers; maps stay resident"))
 
     # ---- roofline of the dominant kernel (phd_update_kernel), live ------------------------------------
     peak, peak_src = _peaks()

@@ -194,6 +194,17 @@ int rfsb200_set_poses(rfsb200_ctx* ctx, const double* pose /*[N][pose_dim]*/,
 int rfsb200_update(rfsb200_ctx* ctx, const double* Z /*[nZ][meas_dim]*/, int32_t nZ,
                    uint32_t flags, rfsb200_step_out* out);
 
+/* One host-facing step = rfsb200_set_poses + rfsb200_update + rfsb200_get_weights + rfsb200_get_unused in ONE
+ * call with ONE synchronisation: the copies in, the kernels and the copies out are queued back to back on the
+ * ctx stream.  This is what RBPHDFilter::update() moves per step when the maps stay resident: poses / pose
+ * covariances / particle weights / Z in, particle weights (normalised unless NO_NORMALIZE), the
+ * unused-measurement masks and nLandmarksInFOV_ out.  Host buffers should be page-locked
+ * (rfsb200_host_alloc) so that the copies are asynchronous; w_out / unused_out / n_in_fov_out / out may be NULL. */
+int rfsb200_update_host(rfsb200_ctx* ctx, const double* pose /*[N][3]*/, const double* pose_cov, int pose_cov_mode,
+                        const double* weight /*[N] or NULL = keep*/, const double* Z, int32_t nZ, uint32_t flags,
+                        double* w_out /*[N]*/, uint64_t* unused_out /*[N]*/, int32_t* n_in_fov_out /*[N]*/,
+                        rfsb200_step_out* out);
+
 /* ---- the callers either side of the hot path -------------
  * rfsb200_predict_maps = the map part of RBPHDFilter::predict() (include/RBPHDFilter.hpp:415-442):
  *   add_births != 0: addBirthGaussians() in its direct form (:1013-1052 with

@@ -116,6 +116,7 @@ _SIGS = {
     "rfsb200_set_poses": (C.c_int, [_P, _P, _P, C.c_int, _P]),
     "rfsb200_append_gaussians": (C.c_int, [_P, _P, _P, _P, _P]),
     "rfsb200_update": (C.c_int, [_P, _P, C.c_int32, C.c_uint32, C.POINTER(StepOut)]),
+    "rfsb200_update_host": (C.c_int, [_P, _P, _P, C.c_int, _P, _P, C.c_int32, C.c_uint32, _P, _P, _P, C.POINTER(StepOut)]),
     "rfsb200_predict_maps": (C.c_int, [_P, _P, C.c_int32, C.c_double]),
     "rfsb200_resample": (C.c_int, [_P, _P, _P, _P]),
     "rfsb200_comm_export": (C.c_int, [_P, _P]),

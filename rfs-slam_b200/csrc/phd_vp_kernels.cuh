@@ -618,14 +618,34 @@ phd_update_vp_kernel(const __grid_constant__ VPParams<T> vp) {
         rad2[j] = sym3_pd(Pj) ? tt * (Pj.a00 + Pj.a11 + Pj.a22) : M<T>::inf();
       }
       __syncwarp();
+      // Pre-pass, one lane per row: the first later component within reach of the row (distance test only).
+      // When row i gets its turn it is still in its original state and so is every live j > i (rows are only
+      // modified while they are the absorbing row), so a row without such a partner cannot merge with
+      // anything and is skipped; the others start their exact scan at that partner.
+      unsigned short* firstCand = order;   // [W]: free between the sort of S5 and the prune
+      for (int ib = 0; ib < n; ib += 32) {
+        const int i = ib + lane;
+        unsigned short jm = 0xffffu;
+        if (i < n - 1) {
+          const T xi = cur[i], yi = cur[W + i], di = cur[2 * W + i], ri = rad2[i];
+          for (int j = i + 1; j < n; j++) {
+            const T ex = cur[j] - xi, ey = cur[W + j] - yi, ed = cur[2 * W + j] - di;
+            if (!(ex * ex + ey * ey + ed * ed > M<T>::max_(ri, rad2[j]))) { jm = (unsigned short)j; break; }
+          }
+        }
+        if (i < n) firstCand[i] = jm;
+      }
+      __syncwarp();
       for (int i = 0; i < n - 1; i++) {
+        const int j0 = firstCand[i];
+        if (j0 == 0xffff) continue;    // nothing within reach
         if (wpl[i] < T(0)) continue;   // hole
         VPRow<T> r;
         r.x = cur[i]; r.y = cur[W + i]; r.d = cur[2 * W + i]; r.w = wpl[i];
         load_sym3(r.P, cur, W, i);
         bool have_inv = false, changed = false;
         r.reach2 = rad2[i];
-        int jstart = i + 1;
+        int jstart = j0;
         while (jstart < n) {
           int found = -1;
           for (int base = jstart; base < n; base += 32) {

@@ -688,15 +688,12 @@ int rfsb200_set_poses(rfsb200_ctx* c, const double* pose, const double* pose_cov
   return RFSB200_OK;
 }
 
-int rfsb200_update(rfsb200_ctx* c, const double* Z, int32_t nZ, uint32_t flags, rfsb200_step_out* out) {
-  if (!c) return fail(nullptr, RFSB200_EINVAL, "NULL ctx");
+// queue one update on the ctx stream (Z copy + kernels); no synchronisation
+static int enqueue_update(rfsb200_ctx* c, const double* Z, int32_t nZ, uint32_t flags, bool timed, int* launches_out) {
   if (!c->have_model || !c->have_cfg || !c->have_maps || !c->have_poses)
     return fail(c, RFSB200_ESTATE, "update before set_model / set_filter_cfg / upload_maps / set_poses");
   if (nZ < 0 || nZ > c->dims.z_capacity) return fail(c, RFSB200_ECAPACITY, "nZ %d > z_capacity %d", nZ, c->dims.z_capacity);
-  if (out) memset(out, 0, sizeof(*out));
-  if (nZ == 0) return RFSB200_OK;  // include/RBPHDFilter.hpp:451-452 (Q11)
   if (!Z) return fail(c, RFSB200_EINVAL, "NULL Z");
-  CU(c, cudaSetDevice(c->device));
   // Z -> T in a pinned staging slot -> device
   unsigned char* zsrc = nullptr;
   unsigned zslot_used = 0;
@@ -715,7 +712,7 @@ int rfsb200_update(rfsb200_ctx* c, const double* Z, int32_t nZ, uint32_t flags, 
     }
   }
   int launches = 0;
-  if (out) CU(c, cudaEventRecord(c->ev0, c->stream));
+  if (timed) CU(c, cudaEventRecord(c->ev0, c->stream));
   CU(c, cudaMemcpyAsync(c->Zdev, zsrc, (size_t)c->ld * nZ * c->tsize, cudaMemcpyHostToDevice, c->stream));
   CU(c, cudaEventRecord(c->zev[zslot_used], c->stream));
   const int out_idx = c->front ^ 1;
@@ -732,29 +729,86 @@ int rfsb200_update(rfsb200_ctx* c, const double* Z, int32_t nZ, uint32_t flags, 
     launches++;
   }
   if (!(flags & RFSB200_UPDATE_NO_COMMIT)) c->front = out_idx;
-  if (out) {
-    CU(c, cudaEventRecord(c->ev1, c->stream));
-    unsigned char* h = c->hpin + 8192;
-    CU(c, cudaMemcpyAsync(h, c->sums, 16, cudaMemcpyDeviceToHost, c->stream));
-    CU(c, cudaMemcpyAsync(h + 16, c->stats_out, 104, cudaMemcpyDeviceToHost, c->stream));
-    CU(c, cudaStreamSynchronize(c->stream));
-    const double* s = (const double*)h;
-    const unsigned long long* t = (const unsigned long long*)(h + 16);
-    out->sum_w = s[0];
-    out->sum_w2 = s[1];
-    out->n_eff = s[1] > 0 ? s[0] * s[0] / s[1] : 0;
-    out->gm_total_in = (int64_t)t[0];
-    out->gm_total_out = (int64_t)t[1];
-    out->gm_max_out = (int32_t)t[2];
-    out->n_overflow = (int32_t)t[3];
-    out->n_murty = (int32_t)t[4];
-    out->n_merge_redo = (int32_t)t[5];
-    for (int k = 0; k < 6; k++) out->reserved[k] = (int32_t)t[6 + k];   // merge diagnostics
-    out->n_launches = launches;
-    float ms = 0;
-    CU(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
-    out->elapsed_us = ms * 1000.f;
+  if (timed) CU(c, cudaEventRecord(c->ev1, c->stream));
+  *launches_out = launches;
+  return RFSB200_OK;
+}
+
+// queue the D2H copy of the step scalars; fill `out` after the caller has synchronised
+static int enqueue_stats(rfsb200_ctx* c) {
+  unsigned char* h = c->hpin + 8192;
+  CU(c, cudaMemcpyAsync(h, c->sums, 16, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaMemcpyAsync(h + 16, c->stats_out, 104, cudaMemcpyDeviceToHost, c->stream));
+  return RFSB200_OK;
+}
+static int fill_stats(rfsb200_ctx* c, int launches, rfsb200_step_out* out) {
+  unsigned char* h = c->hpin + 8192;
+  const double* s = (const double*)h;
+  const unsigned long long* t = (const unsigned long long*)(h + 16);
+  out->sum_w = s[0];
+  out->sum_w2 = s[1];
+  out->n_eff = s[1] > 0 ? s[0] * s[0] / s[1] : 0;
+  out->gm_total_in = (int64_t)t[0];
+  out->gm_total_out = (int64_t)t[1];
+  out->gm_max_out = (int32_t)t[2];
+  out->n_overflow = (int32_t)t[3];
+  out->n_murty = (int32_t)t[4];
+  out->n_merge_redo = (int32_t)t[5];
+  for (int k = 0; k < 6; k++) out->reserved[k] = (int32_t)t[6 + k];   // merge diagnostics
+  out->n_launches = launches;
+  float ms = 0;
+  CU(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+  out->elapsed_us = ms * 1000.f;
+  return RFSB200_OK;
+}
+
+int rfsb200_update(rfsb200_ctx* c, const double* Z, int32_t nZ, uint32_t flags, rfsb200_step_out* out) {
+  if (!c) return fail(nullptr, RFSB200_EINVAL, "NULL ctx");
+  if (out) memset(out, 0, sizeof(*out));
+  if (nZ == 0) {   // include/RBPHDFilter.hpp:451-452 (Q11)
+    if (!c->have_model || !c->have_cfg || !c->have_maps || !c->have_poses)
+      return fail(c, RFSB200_ESTATE, "update before set_model / set_filter_cfg / upload_maps / set_poses");
+    return RFSB200_OK;
   }
+  CU(c, cudaSetDevice(c->device));
+  int launches = 0;
+  int rc = enqueue_update(c, Z, nZ, flags, out != nullptr, &launches);
+  if (rc) return rc;
+  if (out) {
+    rc = enqueue_stats(c);
+    if (rc) return rc;
+    CU(c, cudaStreamSynchronize(c->stream));
+    return fill_stats(c, launches, out);
+  }
+  return RFSB200_OK;
+}
+
+int rfsb200_update_host(rfsb200_ctx* c, const double* pose, const double* pose_cov, int mode, const double* weight,
+                        const double* Z, int32_t nZ, uint32_t flags, double* w_out, uint64_t* unused_out,
+                        int32_t* nfov_out, rfsb200_step_out* out) {
+  if (!c || !pose) return fail(c, RFSB200_EINVAL, "NULL argument");
+  if (out) memset(out, 0, sizeof(*out));
+  int rc = rfsb200_set_poses(c, pose, pose_cov, mode, weight);   // queued, no synchronisation
+  if (rc) return rc;
+  int launches = 1;   // pose_convert_kernel
+  if (nZ > 0) {
+    int l = 0;
+    rc = enqueue_update(c, Z, nZ, flags, out != nullptr, &l);
+    if (rc) return rc;
+    launches += l;
+  } else if (nZ < 0) {
+    return fail(c, RFSB200_EINVAL, "negative nZ");
+  }
+  const int which = c->last_out;
+  if (w_out) CU(c, cudaMemcpyAsync(w_out, c->st[nZ > 0 ? which : c->front].weight, (size_t)c->N * 8, cudaMemcpyDeviceToHost, c->stream));
+  if (unused_out) CU(c, cudaMemcpyAsync(unused_out, c->unused, (size_t)c->N * 8, cudaMemcpyDeviceToHost, c->stream));
+  if (nfov_out) CU(c, cudaMemcpyAsync(nfov_out, c->nfov, (size_t)c->N * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (out && nZ > 0) {
+    rc = enqueue_stats(c);
+    if (rc) return rc;
+  }
+  CU(c, cudaStreamSynchronize(c->stream));
+  if (out && nZ > 0) return fill_stats(c, launches, out);
   return RFSB200_OK;
 }
 

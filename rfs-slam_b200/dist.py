@@ -90,3 +90,20 @@ class ShardedUpdater:
         allreduce_sums(self.sums, self.group)
         self.up.normalize()
         return so
+
+    def step_host(self, pose, pose_cov, weight, Z, flags: int = 0, w_out=None, unused_out=None, nfov_out=None):
+        """The host-facing step (what the drop-in RBPHDFilter::update() moves per step): poses / weights / Z in,
+        normalised weights / unused-measurement masks / in-FOV counts out.  Fused path: ONE ABI call with one
+        synchronisation; NCCL path: the same data through the separate calls around the collective."""
+        from . import capi
+        if self.fused:
+            return self.up.update_host(pose, pose_cov, weight, Z, flags=flags | capi.UPDATE_FUSED_ALLREDUCE,
+                                       w_out=w_out, unused_out=unused_out, nfov_out=nfov_out)
+        self.up.set_poses(pose, pose_cov, weight)
+        self.step(Z, flags=flags)
+        which = 1 if (flags & capi.UPDATE_NO_COMMIT) else 0
+        if w_out is not None:
+            self.up.get_weights(which, out=w_out)
+        if unused_out is not None or nfov_out is not None:
+            self.up.get_unused(unused_out, nfov_out)
+        return None

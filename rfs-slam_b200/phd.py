@@ -151,6 +151,18 @@ class PHDUpdater:
         _check(self.lib, self.ctx, rc, "update")
         return out
 
+    def update_host(self, pose, pose_cov, weight, Z, flags: int = capi.UPDATE_DEFAULT, w_out=None, unused_out=None,
+                    nfov_out=None, want_stats: bool = False):
+        """set_poses + update + get_weights + get_unused in one ABI call with one synchronisation
+        (rfsb200_update_host).  All arrays float64 / uint64 / int32, C-contiguous, ideally pinned_array()s."""
+        mode = 0 if pose_cov is None else (1 if pose_cov.ndim == 1 else 2)
+        out = capi.StepOut() if want_stats else None
+        rc = self.lib.rfsb200_update_host(self.ctx, capi.ptr(pose), capi.ptr(pose_cov), mode, capi.ptr(weight), capi.ptr(Z),
+                                          Z.shape[0], flags, capi.ptr(w_out), capi.ptr(unused_out), capi.ptr(nfov_out),
+                                          C.byref(out) if out is not None else None)
+        _check(self.lib, self.ctx, rc, "update_host")
+        return out
+
     # ---- the callers either side (predict's map part, resampling's data movement) -----------------
     def predict_maps(self, Q_lmk=None, add_births: bool = True, birth_weight: float = 0.0):
         """RBPHDFilter::predict() minus the particle propagation: births, then P += Q."""

@@ -267,3 +267,28 @@ def test_fused_normalisation_equals_two_launch_path(cuda_required):
     assert res[0][1] == res[1][1]
     assert np.array_equal(res[0][2], res[1][2])
     assert res[1][2].sum() == pytest.approx(1.0, abs=1e-12)
+
+
+def test_update_host_equals_the_separate_calls(cuda_required):
+    """rfsb200_update_host = set_poses + update + get_weights + get_unused in one call with one synchronisation."""
+    from rfs_slam_b200 import capi, synth
+    from rfs_slam_b200.phd import PHDUpdater, pinned_array
+    wl = synth.make_workload(N=512, nM=120, nZ=24, use_cluster_process=1, config_id=41, parity_extras=True)
+    a = PHDUpdater(wl.N, gm_capacity=192, z_capacity=32)
+    a.load_workload(wl)
+    a.update(wl.Z)
+    wa = a.get_weights()
+    ma, fa = a.get_unused()
+    b = PHDUpdater(wl.N, gm_capacity=192, z_capacity=32)
+    b.set_model(wl.model); b.set_filter_cfg(wl.cfg); b.upload_maps(wl.count, wl.mean, wl.cov, wl.w)
+    pose = pinned_array((wl.N, 3)); pose[:] = wl.pose
+    w_in = pinned_array((wl.N,)); w_in[:] = wl.weight
+    w_out = pinned_array((wl.N,)); mask = pinned_array((wl.N,), np.uint64); nfov = pinned_array((wl.N,), np.int32)
+    so = b.update_host(pose, wl.pose_cov, w_in, np.ascontiguousarray(wl.Z), w_out=w_out, unused_out=mask, nfov_out=nfov,
+                       want_stats=True)
+    assert np.array_equal(w_out, wa) and np.array_equal(mask, ma) and np.array_equal(nfov, fa)
+    assert so.n_launches == 3 and so.gm_total_in == int(wl.count.sum())
+    ca, cb = a.download_maps(), b.download_maps()
+    for x, y in zip(ca, cb):
+        assert np.array_equal(x, y)
+    a.close(); b.close()
