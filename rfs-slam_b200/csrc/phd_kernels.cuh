@@ -19,7 +19,8 @@
 
 namespace rfsb200 {
 
-constexpr int WARPS_PER_CTA = 4;
+constexpr int WARPS_PER_CTA = 4;       // default; the 2-D multi-feature kernel runs 5 (see mf_region_bytes)
+constexpr int MAX_WARPS_PER_CTA = 8;
 constexpr int MAX_Z = 64;
 constexpr int MAX_EVAL = 32;
 constexpr int DP_MAXB = 7;     // assignment-sum DP: the smaller side of a partition has <= 7 members
@@ -971,7 +972,7 @@ __device__ __forceinline__ void step_epilogue(const KParams<T>& p, int lane, int
 
   // ---------------- S8: deterministic [sum w, sum w^2] by the last CTA ----------------------------
   __shared__ bool is_last;
-  __shared__ double red[2][WARPS_PER_CTA];
+  __shared__ double red[2][MAX_WARPS_PER_CTA];
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
@@ -993,7 +994,7 @@ __device__ __forceinline__ void step_epilogue(const KParams<T>& p, int lane, int
     __syncthreads();
     if (threadIdx.x == 0) {
       double a = 0, b = 0;
-      for (int k = 0; k < WARPS_PER_CTA; k++) { a += red[0][k]; b += red[1][k]; }
+      for (int k = 0; k < (int)(blockDim.x >> 5); k++) { a += red[0][k]; b += red[1][k]; }
       if (p.comm_world > 1) {
         // ---- fused all-reduce: every rank writes its pair into slot [parity][rank] of EVERY rank's
         // mailbox (remote stores over NVLink), then waits until its own mailbox holds this epoch from
@@ -1056,25 +1057,36 @@ __device__ __forceinline__ void step_epilogue(const KParams<T>& p, int lane, int
 
 // ------------------------------------------------------------------------------------------------
 // shared-memory carve-up (bytes); host and device agree through these helpers
-//  per warp: planes [NPL][W] (NPL = 6, or 7 with weight_prev in multi-feature mode) | merge scratch | aux u32[W] |
-//            colsum T[MAX_Z] | evalIdx int[MAX_EVAL] | mbarrier | multi-feature scratch
+//  per warp: planes [NPL][W] (NPL = 6, or 7 with weight_prev in multi-feature mode) | work region | aux u32[W] |
+//            colsum T[MAX_Z] | evalIdx int[MAX_EVAL] | mbarrier
 //  per CTA : the measurement batch + the two window tables of the corrector
+// The work region is the merge scratch.  In multi-feature mode the stages of S5 run before the merge and
+// reuse the same bytes, one after the other (each stage's data is dead when the next one starts):
+//   sort       perm = order[], keys = keys[] (+ a temporary plane behind the keys in the fp64 build)
+//   intensity  4 planes T[W] (inverse covariance, log normaliser)
+//   L table    rowmask | compC | f1 | (f0) | compR | eval-point block | L    (f0 lives in aux[] when W >= 256)
+// so the region is max(merge scratch, 4 planes, L-table stage) — with the defaults (W = 256, 15 eval points,
+// <= 32 measurements, fp32) exactly the merge scratch, 14 kB per warp in total, and five warps per CTA give
+// 15 resident warps per SM instead of 8 with a separate multi-feature scratch.
 template <typename T>
-__host__ __device__ inline int mf_fixed_bytes(int n_eval, int zcap) {
+__host__ __device__ inline int mf_stage3_bytes(int W, int n_eval, int zcap) {
   const int ltab = (n_eval * zcap + 3) & ~3;
-  return (int)(8 * (MAX_EVAL + MAX_COMP + 2 * (1 << DP_MAXB)) + 4 * MAX_COMP + sizeof(T) * (MAX_EVAL * 8 + ltab) + 15) & ~15;
-}
-// multi-feature scratch: rowmask / components / DP tables / eval-point block / L table, then the 4
-// planes (inverse covariance, log normaliser) of the intensity evaluation
-template <typename T>
-__host__ __device__ inline int mf_scratch_bytes(int n_eval, int zcap, int W) {
-  return mf_fixed_bytes<T>(n_eval, zcap) + 4 * W * (int)sizeof(T);
+  const int f0 = (W * 4 >= 8 * (1 << DP_MAXB)) ? 0 : 8 * (1 << DP_MAXB);
+  return (int)(8 * (MAX_EVAL + MAX_COMP + (1 << DP_MAXB)) + f0 + 4 * MAX_COMP + sizeof(T) * (MAX_EVAL * 8 + ltab) + 15) & ~15;
 }
 template <typename T>
-__host__ __device__ inline int warp_bytes_for(int W, int multi_feature, int mf_bytes) {
+__host__ __device__ inline int mf_region_bytes(int W, int n_eval, int zcap) {
+  int r = merge_scratch_bytes<T>(W);
+  const int a = 4 * W * (int)sizeof(T), b = mf_stage3_bytes<T>(W, n_eval, zcap);
+  r = a > r ? a : r;
+  r = b > r ? b : r;
+  return (r + 15) & ~15;
+}
+// region_bytes: merge_scratch_bytes (single-cluster) or mf_region_bytes (multi-feature)
+template <typename T>
+__host__ __device__ inline int warp_bytes_for(int W, int multi_feature, int region_bytes) {
   const int planes = multi_feature ? 7 : 6;   // MF carries weight_prev as a 7th plane
-  int b = planes * W * (int)sizeof(T) + merge_scratch_bytes<T>(W) + W * 4 + MAX_Z * (int)sizeof(T) + MAX_EVAL * 4 + 16 +
-          (multi_feature ? mf_bytes : 0);
+  int b = planes * W * (int)sizeof(T) + region_bytes + W * 4 + MAX_Z * (int)sizeof(T) + MAX_EVAL * 4 + 16;
   return (b + 127) & ~127;
 }
 constexpr int NBINS = 256;   // bins of the range / bearing window tables
@@ -1085,7 +1097,7 @@ __host__ __device__ inline int z_bytes() {
 }
 
 template <typename T, bool MF>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4)
+__global__ void __launch_bounds__(MF ? 160 : 128, MF ? 3 : 4)
 phd_update_kernel(const __grid_constant__ KParams<T> p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
@@ -1102,12 +1114,13 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
   unsigned char* wb = smem_raw + z_bytes<T>() + (size_t)warp * p.warp_bytes;
   T* bufA = reinterpret_cast<T*>(wb);
   unsigned char* after = reinterpret_cast<unsigned char*>(bufA + NPL * W);
-  unsigned* aux = reinterpret_cast<unsigned*>(after + merge_scratch_bytes<T>(W));  // [W]
+  unsigned* aux = reinterpret_cast<unsigned*>(after + (MF ? p.mf_bytes : merge_scratch_bytes<T>(W)));  // [W]
   const MergeScratch<T> ms = carve_merge_scratch<T>(after, aux, W);
   T* colsum = reinterpret_cast<T*>(aux + W);                  // [MAX_Z]
   int* evalIdx = reinterpret_cast<int*>(colsum + MAX_Z);      // [MAX_EVAL]
   uint64_t* bar = reinterpret_cast<uint64_t*>(evalIdx + MAX_EVAL);
-  unsigned char* mfs = reinterpret_cast<unsigned char*>(bar + 2);   // multi-feature scratch (16-byte aligned)
+  unsigned char* mfs = after;   // multi-feature stages reuse the work region (see mf_region_bytes)
+  (void)bar;
 
   // ---- the measurement batch and the corrector's window tables (once per CTA) ------------------
   // tabR[b] = set of measurements whose range bin is < b, tabB likewise on the bearing: the
@@ -1506,7 +1519,7 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
           }
           __syncwarp();
           T* tmp = reinterpret_cast<T*>(aux);   // [W] words; T = double uses mf scratch instead
-          if constexpr (sizeof(T) == 8) tmp = reinterpret_cast<T*>(mfs);   // >= W doubles, see mf_scratch_bytes
+          if constexpr (sizeof(T) == 8) tmp = reinterpret_cast<T*>(ms.keys) + W;   // behind the keys, inside the merge scratch
           for (int pl = 0; pl < 7; pl++) {
             for (int k = lane; k < n; k += 32) tmp[k] = cur[pl * W + perm[k]];
             __syncwarp();
@@ -1547,7 +1560,7 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
         // scratch); then ONE LANE PER EVAL POINT (two lanes, splitting the components, when there are
         // at most 16 eval points) runs an online log-sum-exp over the components, whose data are
         // broadcast reads.
-        T* ia = reinterpret_cast<T*>(mfs + mf_fixed_bytes<T>(p.n_eval_cap, p.zcap));   // [4][W]
+        T* ia = reinterpret_cast<T*>(mfs);   // [4][W] (the sort's perm / keys are dead)
         for (int m = lane; m < n; m += 32) {
           const T a = cur[2 * W + m], b = cur[3 * W + m], c = cur[4 * W + m];
           const T det = a * c - b * b;
@@ -1605,11 +1618,13 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
         }
         __syncwarp();
         // rfsMeasurementLikelihood (:821-997): L table with the landmark covariance zeroed
+        // (the intensity planes are dead: the L-table stage takes the region over)
         unsigned long long* rowmask = reinterpret_cast<unsigned long long*>(mfs);   // [MAX_EVAL]
         unsigned long long* compC = rowmask + MAX_EVAL;                             // [MAX_COMP]
-        double* f0 = reinterpret_cast<double*>(compC + MAX_COMP);                   // [1<<DP_MAXB]
-        double* f1 = f0 + (1 << DP_MAXB);
-        unsigned* compR = reinterpret_cast<unsigned*>(f1 + (1 << DP_MAXB));         // [MAX_COMP]
+        double* f1 = reinterpret_cast<double*>(compC + MAX_COMP);                   // [1<<DP_MAXB]
+        const bool f0_in_aux = W * 4 >= 8 * (1 << DP_MAXB);
+        double* f0 = f0_in_aux ? reinterpret_cast<double*>(aux) : f1 + (1 << DP_MAXB);   // [1<<DP_MAXB]
+        unsigned* compR = reinterpret_cast<unsigned*>((f0_in_aux ? f1 : f0) + (1 << DP_MAXB));   // [MAX_COMP]
         T* ep = reinterpret_cast<T*>(compR + MAX_COMP);   // [MAX_EVAL][8]: zr, zb, i00, i01, i11, Pd*norm, -, Pd
         T* L = ep + MAX_EVAL * 8;                         // [nE][nZ]
         T* evalPd = ep + MAX_EVAL * 7;  // stride-1 array of Pd per eval point (slot 7 of the ep block region)

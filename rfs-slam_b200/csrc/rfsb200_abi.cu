@@ -91,6 +91,7 @@ struct rfsb200_ctx {
   std::vector<cudaEvent_t> prof_ev;   // event pairs around the update kernel (rfsb200_profile_*)
   int prof_cap = 0, prof_n = 0;
   int grid = 0;
+  int nwarps = 4;   // warps per CTA of the update kernel
   size_t smem_bytes = 0;
   int warp_bytes = 0;
   int mf_bytes = 0;
@@ -246,16 +247,27 @@ int configure_launch_t(rfsb200_ctx* c) {
   const int n_eval = (MF && c->have_cfg) ? std::max(1, c->cfg.eval_point_count) : MAX_EVAL;
   if (c->cfg_mode_mf == mf && (!MF || c->cfg_n_eval == n_eval)) return RFSB200_OK;
   c->cfg_n_eval = n_eval;
-  c->mf_bytes = mf ? mf_scratch_bytes<T>(n_eval, c->dims.z_capacity, c->W) : 0;
-  c->warp_bytes = warp_bytes_for<T>(c->W, mf, c->mf_bytes);
-  c->smem_bytes = (size_t)z_bytes<T>() + (size_t)WARPS_PER_CTA * c->warp_bytes;
-  if (c->smem_bytes > 227 * 1024) return fail(c, RFSB200_ECAPACITY, "work_capacity %d needs %zu B shared memory per CTA (> 227 KB)", c->W, c->smem_bytes);
+  c->mf_bytes = mf ? mf_region_bytes<T>(c->W, n_eval, c->dims.z_capacity) : 0;   // the work region in multi-feature mode
+  c->warp_bytes = warp_bytes_for<T>(c->W, mf, mf ? c->mf_bytes : merge_scratch_bytes<T>(c->W));
+  // warps per CTA: 4 (single-cluster); multi-feature: whatever puts most warps on an SM (the per-CTA block of
+  // window tables is shared, so five warps fit three times where four fit three times as well)
+  int best_nw = 0, best_occ = 0;
+  for (int nw = WARPS_PER_CTA; nw <= (MF ? 5 : WARPS_PER_CTA); nw++) {
+    const size_t smem = (size_t)z_bytes<T>() + (size_t)nw * c->warp_bytes;
+    if (smem > 227 * 1024) break;
+    CU(c, cudaFuncSetAttribute(phd_update_kernel<T, MF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, phd_update_kernel<T, MF>, nw * 32, smem));
+    if (occ * nw > best_occ * best_nw) { best_nw = nw; best_occ = occ; }
+  }
+  if (best_nw == 0 || best_occ < 1)
+    return fail(c, RFSB200_ECAPACITY, "work_capacity %d needs %zu B shared memory per CTA (> 227 KB)", c->W,
+                (size_t)z_bytes<T>() + (size_t)WARPS_PER_CTA * c->warp_bytes);
+  c->nwarps = best_nw;
+  c->smem_bytes = (size_t)z_bytes<T>() + (size_t)best_nw * c->warp_bytes;
   CU(c, cudaFuncSetAttribute(phd_update_kernel<T, MF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
-  int occ = 0;
-  CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, phd_update_kernel<T, MF>, WARPS_PER_CTA * 32, c->smem_bytes));
-  if (occ < 1) return fail(c, RFSB200_ECAPACITY, "kernel does not fit on an SM");
-  const int need = (c->N + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
-  c->grid = std::max(1, std::min(need, occ * c->sm_count));
+  const int need = (c->N + best_nw - 1) / best_nw;
+  c->grid = std::max(1, std::min(need, best_occ * c->sm_count));
   c->cfg_mode_mf = mf;
   return RFSB200_OK;
 }
@@ -275,6 +287,7 @@ int configure_launch_vp_t(rfsb200_ctx* c) {
   if (occ < 1) return fail(c, RFSB200_ECAPACITY, "kernel does not fit on an SM");
   const int need = (c->N + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
   c->grid = std::max(1, std::min(need, occ * c->sm_count));
+  c->nwarps = WARPS_PER_CTA;
   c->cfg_mode_mf = mf;
   return RFSB200_OK;
 }
@@ -343,8 +356,8 @@ int launch_update(rfsb200_ctx* c, int nZ, int out_idx, unsigned flags) {
     for (int k = 0; k < VP_PD_MAX; k++) v.pd_table[k] = k < m.pd_table_n ? m.pd_table[k] : 0.0;
     if (mf) phd_update_vp_kernel<T, true><<<c->grid, WARPS_PER_CTA * 32, c->smem_bytes, c->stream>>>(v);
     else phd_update_vp_kernel<T, false><<<c->grid, WARPS_PER_CTA * 32, c->smem_bytes, c->stream>>>(v);
-  } else if (mf) phd_update_kernel<T, true><<<c->grid, WARPS_PER_CTA * 32, c->smem_bytes, c->stream>>>(p);
-  else phd_update_kernel<T, false><<<c->grid, WARPS_PER_CTA * 32, c->smem_bytes, c->stream>>>(p);
+  } else if (mf) phd_update_kernel<T, true><<<c->grid, c->nwarps * 32, c->smem_bytes, c->stream>>>(p);
+  else phd_update_kernel<T, false><<<c->grid, c->nwarps * 32, c->smem_bytes, c->stream>>>(p);
   CU(c, cudaGetLastError());
   if (prof) {
     CU(c, cudaEventRecord(c->prof_ev[2 * c->prof_n + 1], c->stream));
