@@ -259,6 +259,7 @@ int configure_launch_t(rfsb200_ctx* c) {
     int occ = 0;
     CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, phd_update_kernel<T, MF>, nw * 32, smem));
     if (occ * nw > best_occ * best_nw) { best_nw = nw; best_occ = occ; }
+    if (c->N <= occ * nw * c->sm_count) break;   // the whole shard is resident already: smaller CTAs spread better
   }
   if (best_nw == 0 || best_occ < 1)
     return fail(c, RFSB200_ECAPACITY, "work_capacity %d needs %zu B shared memory per CTA (> 227 KB)", c->W,
