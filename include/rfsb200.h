@@ -232,6 +232,37 @@ int rfsb200_predict_maps(rfsb200_ctx* ctx, const double* Q_lmk /*[3] / [6] or NU
 int rfsb200_append_gaussians(rfsb200_ctx* ctx, const int32_t* count /*[N]*/, const double* mean,
                              const double* cov, const double* w);
 
+/* ---- particle propagation ------------------------------------------------
+ * ParticleFilter::propagate() (include/ParticleFilter.hpp:322-341) = ProcessModel::sample() for every particle
+ * (include/ProcessModel.hpp:125-150) on the device, in place on the poses of the ctx (fp64 copy kept next to the
+ * T copy the update kernel reads):
+ *   use_input_noise: the input is drawn from N(input, input_cov) per particle (RandomVec::sample, Cholesky factor);
+ *   step():          MotionModel_Odometry2d (src/ProcessModel_Odometry2D.cpp:41-89) or MotionModel_Ackerman2d
+ *                    (src/ProcessModel_Ackerman2D.cpp:49-77);
+ *   use_model_noise and Q != 0: N(0, Q) is added and the pose covariance of every particle becomes Q (Q1), otherwise
+ *                    the poses carry no covariance afterwards (the reference's x_k is default-constructed).
+ * Random numbers: Philox4x32-10 keyed by `seed`, counter (particle, step_counter): the stream does not depend on the
+ * launch shape.  The reference draws from one host mt19937 seeded by an unseeded rand(), so parity with it is
+ * statistical (moments) for the noise and exact for step(). */
+#define RFSB200_MOTION_ODOMETRY2D 1   /* input = (dx, dy, dtheta) in the frame of the previous pose          */
+#define RFSB200_MOTION_ACKERMAN2D 2   /* input = (velocity, steering angle)                                  */
+typedef struct rfsb200_motion_desc {
+  int32_t model_id;          /* RFSB200_MOTION_*                                                             */
+  int32_t use_model_noise;   /* useAdditiveWhiteGaussianNoise                                                */
+  int32_t use_input_noise;   /* useInputWhiteGaussianNoise                                                   */
+  int32_t reserved_i;
+  double  Q[9];              /* ProcessModel::Q_, 3x3 row-major (already scaled by the caller as it scales Q_) */
+  double  input[3];          /* Odometry2d: dx, dy, dtheta; Ackerman2d: velocity, steering, unused           */
+  double  input_cov[9];      /* covariance of the input, row-major n_in x n_in (3x3 / 2x2)                   */
+  double  dt;                /* dT (Ackerman2d only)                                                         */
+  double  ackerman_h, ackerman_l, ackerman_dx, ackerman_dy;   /* h_, l_, poi_offset_x_, poi_offset_y_          */
+  uint64_t seed;
+  uint64_t step_counter;
+  double  reserved[4];
+} rfsb200_motion_desc;
+int rfsb200_propagate(rfsb200_ctx* ctx, const rfsb200_motion_desc* m);
+int rfsb200_get_poses(rfsb200_ctx* ctx, double* pose /*[N][3]*/);
+
 /* The data movement of ParticleFilter::resample() (include/ParticleFilter.hpp:446-479): particle i
  * of the new set takes the map of particle map_src[i] and the unused-measurement mask / in-FOV count of
  * particle aux_src[i] (NULL = map_src, -1 = none; the reference looks those up through

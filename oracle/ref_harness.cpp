@@ -195,6 +195,20 @@ extern "C" int phd_ref_update(phd_io* io) {
   return rc;
 }
 
+/* MotionModel_Odometry2d::step (src/ProcessModel_Odometry2D.cpp:41-89): pose [3], u = (dx, dy, dtheta) */
+extern "C" void phd_ref_odometry2d_step(const double* pose, const double* u, double* out) {
+  MotionModel_Odometry2d mm;
+  Pose2d::Vec x;
+  x << pose[0], pose[1], pose[2];
+  Pose2d s_km(x, Pose2d::Mat::Zero()), s_k;
+  Odometry2d::Vec uv;
+  uv << u[0], u[1], u[2];
+  Odometry2d in(uv, Odometry2d::Mat::Zero());
+  TimeStamp dT(0.1);
+  mm.step(s_k, s_km, in, dT);
+  for (int k = 0; k < 3; k++) out[k] = s_k.get(k);
+}
+
 /* rfs::MatPerm::calc on a row-major n x n matrix */
 extern "C" double phd_ref_permanent(const double* A, int n) {
   Eigen::MatrixXd M(n, n);

@@ -233,3 +233,17 @@ extern "C" double phd_ref_vp_pd(const rfsb200_model_desc* md, const double* pose
   if (close_out) *close_out = close ? 1 : 0;
   return pd;
 }
+
+/* MotionModel_Ackerman2d::step (src/ProcessModel_Ackerman2D.cpp:49-77): params = (h, l, poi dx, poi dy), u = (v, steering) */
+extern "C" void phd_ref_ackerman2d_step(const double* params, const double* pose, const double* u, double dt, double* out) {
+  MotionModel_Ackerman2d mm(params[0], params[1], params[2], params[3]);
+  Pose2d::Vec x;
+  x << pose[0], pose[1], pose[2];
+  Pose2d s_km(x, Pose2d::Mat::Zero()), s_k;
+  AckermanInput::Vec uv;
+  uv << u[0], u[1];
+  AckermanInput in(uv, AckermanInput::Mat::Zero());
+  TimeStamp dT(dt);
+  mm.step(s_k, s_km, in, dT);
+  for (int k = 0; k < 3; k++) out[k] = s_k.get(k);
+}

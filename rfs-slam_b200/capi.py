@@ -55,6 +55,17 @@ class FilterCfg(C.Structure):
                 ("reserved", C.c_double * 6)]
 
 
+MOTION_ODOMETRY2D, MOTION_ACKERMAN2D = 1, 2
+
+
+class MotionDesc(C.Structure):
+    _fields_ = [("model_id", C.c_int32), ("use_model_noise", C.c_int32), ("use_input_noise", C.c_int32),
+                ("reserved_i", C.c_int32), ("Q", C.c_double * 9), ("input", C.c_double * 3),
+                ("input_cov", C.c_double * 9), ("dt", C.c_double), ("ackerman_h", C.c_double),
+                ("ackerman_l", C.c_double), ("ackerman_dx", C.c_double), ("ackerman_dy", C.c_double),
+                ("seed", C.c_uint64), ("step_counter", C.c_uint64), ("reserved", C.c_double * 4)]
+
+
 class StepOut(C.Structure):
     _fields_ = [("sum_w", C.c_double), ("sum_w2", C.c_double), ("n_eff", C.c_double),
                 ("gm_total_in", C.c_int64), ("gm_total_out", C.c_int64), ("gm_max_out", C.c_int32),
@@ -118,6 +129,8 @@ _SIGS = {
     "rfsb200_update": (C.c_int, [_P, _P, C.c_int32, C.c_uint32, C.POINTER(StepOut)]),
     "rfsb200_update_host": (C.c_int, [_P, _P, _P, C.c_int, _P, _P, C.c_int32, C.c_uint32, _P, _P, _P, C.POINTER(StepOut)]),
     "rfsb200_predict_maps": (C.c_int, [_P, _P, C.c_int32, C.c_double]),
+    "rfsb200_propagate": (C.c_int, [_P, C.POINTER(MotionDesc)]),
+    "rfsb200_get_poses": (C.c_int, [_P, _P]),
     "rfsb200_resample": (C.c_int, [_P, _P, _P, _P]),
     "rfsb200_comm_export": (C.c_int, [_P, _P]),
     "rfsb200_comm_connect": (C.c_int, [_P, C.c_int32, C.c_int32, _P]),

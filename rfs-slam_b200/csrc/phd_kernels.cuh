@@ -1856,6 +1856,7 @@ __global__ void resample_gather_kernel(const T* __restrict__ gm_in, const int* _
                                        double* __restrict__ w_out, int set_w, double w_value,
                                        const T* __restrict__ pose_in, const T* __restrict__ pcov_in,
                                        T* __restrict__ pose_out, T* __restrict__ pcov_out, int pose_cov_mode,
+                                       const double* __restrict__ pose64_in, double* __restrict__ pose64_out,
                                        int N, int cap, int npl) {
   const int lane = threadIdx.x & 31;
   const int pi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -1877,7 +1878,93 @@ __global__ void resample_gather_kernel(const T* __restrict__ gm_in, const int* _
   }
   // the copy carries the pose of its source (Particle::copy): the next predict's births use it
   if (lane < 4) pose_out[4 * pi + lane] = pose_in[4 * s + lane];
+  if (lane < 3) pose64_out[3 * pi + lane] = pose64_in[3 * s + lane];   // fp64 copy used by rfsb200_propagate
   if (pose_cov_mode == 2 && lane < 8) pcov_out[8 * pi + lane] = pcov_in[8 * s + lane];
+}
+
+// ------------------------------------------------------------------------------------------------
+// ParticleFilter::propagate(): ProcessModel::sample() for every particle (include/ProcessModel.hpp:125-150).
+// Philox4x32-10 (Salmon et al., SC'11): counter-based, so particle i of step s always sees the same numbers.
+__device__ __forceinline__ void philox4x32_10(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned k0, unsigned k1,
+                                              unsigned (&out)[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    const unsigned long long p0 = (unsigned long long)0xD2511F53u * c0, p1 = (unsigned long long)0xCD9E8D57u * c2;
+    const unsigned n0 = (unsigned)(p1 >> 32) ^ c1 ^ k0, n1 = (unsigned)p1, n2 = (unsigned)(p0 >> 32) ^ c3 ^ k1, n3 = (unsigned)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+// two independent N(0,1) from two 32-bit words (Box-Muller on uniforms in (0,1))
+__device__ __forceinline__ void box_muller(unsigned a, unsigned b, double& n0, double& n1) {
+  const double u1 = ((double)a + 0.5) * (1.0 / 4294967296.0), u2 = ((double)b + 0.5) * (1.0 / 4294967296.0);
+  const double r = sqrt(-2.0 * log(u1));
+  double sn, cs;
+  sincospi(2.0 * u2, &sn, &cs);
+  n0 = r * cs;
+  n1 = r * sn;
+}
+
+struct MotionParams {
+  int model_id, use_model_noise, use_input_noise, n_in;
+  double LQ[9];      // lower Cholesky factor of Q (row-major)
+  double Lu[9];      // lower Cholesky factor of the input covariance (row-major 3x3, zero padded)
+  double u[3];
+  double dt, h, l, pdx, pdy;
+  unsigned long long seed, step;
+};
+
+template <typename T>
+__global__ void propagate_kernel(double* __restrict__ pose64, T* __restrict__ pose, const MotionParams m, int N) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  double x = pose64[3 * i], y = pose64[3 * i + 1], th = pose64[3 * i + 2];
+  double z[6] = {0, 0, 0, 0, 0, 0};
+  if (m.use_model_noise || m.use_input_noise) {
+    unsigned r[4], q[4];
+    philox4x32_10((unsigned)i, (unsigned)m.step, (unsigned)(m.step >> 32), 0u, (unsigned)m.seed, (unsigned)(m.seed >> 32), r);
+    philox4x32_10((unsigned)i, (unsigned)m.step, (unsigned)(m.step >> 32), 1u, (unsigned)m.seed, (unsigned)(m.seed >> 32), q);
+    box_muller(r[0], r[1], z[0], z[1]);
+    box_muller(r[2], r[3], z[2], z[3]);
+    box_muller(q[0], q[1], z[4], z[5]);
+  }
+  double u0 = m.u[0], u1 = m.u[1], u2 = m.u[2];
+  if (m.use_input_noise) {   // input_k.sample(in): u + L xi (include/RandomVec.hpp:457-473)
+    u0 += m.Lu[0] * z[0];
+    u1 += m.Lu[3] * z[0] + m.Lu[4] * z[1];
+    if (m.n_in == 3) u2 += m.Lu[6] * z[0] + m.Lu[7] * z[1] + m.Lu[8] * z[2];
+  }
+  if (m.model_id == 1) {
+    // MotionModel_Odometry2d::step (src/ProcessModel_Odometry2D.cpp:41-89): p += C(theta)^T dp ; C_k = C(dtheta) C(theta)
+    double st, ct, sd, cd;
+    sincos(th, &st, &ct);
+    sincos(u2, &sd, &cd);
+    x += ct * u0 - st * u1;
+    y += st * u0 + ct * u1;
+    const double c00 = cd * ct - sd * st, c01 = cd * st + sd * ct;   // first row of C(dtheta) C(theta)
+    th = atan2(c01, c00);
+  } else {
+    // MotionModel_Ackerman2d::step (src/ProcessModel_Ackerman2D.cpp:49-77)
+    double sr, cr;
+    sincos(th, &sr, &cr);
+    const double tu = tan(u1);
+    const double v = u0 / (1 - tu * m.h / m.l);
+    x += m.dt * (v * cr - v / m.l * tu * (m.pdx * sr + m.pdy * cr));
+    y += m.dt * (v * sr + v / m.l * tu * (m.pdx * cr - m.pdy * sr));
+    th += m.dt * v / m.l * tu;
+    const double PI_ = 3.14159265358979323846;
+    if (th > PI_) th -= 2 * PI_;
+    else if (th < -PI_) th += 2 * PI_;
+  }
+  if (m.use_model_noise) {   // s_k.setCov(Q_); s_k.sample(): x += L_Q xi
+    const double a = z[3], b = z[4], c = z[5];
+    x += m.LQ[0] * a;
+    y += m.LQ[3] * a + m.LQ[4] * b;
+    th += m.LQ[6] * a + m.LQ[7] * b + m.LQ[8] * c;
+  }
+  pose64[3 * i] = x; pose64[3 * i + 1] = y; pose64[3 * i + 2] = th;
+  pose[4 * i] = (T)x; pose[4 * i + 1] = (T)y; pose[4 * i + 2] = (T)th; pose[4 * i + 3] = T(0);
 }
 
 // w_i /= sum  (ParticleFilter::normalizeWeights, include/ParticleFilter.hpp:352-363)

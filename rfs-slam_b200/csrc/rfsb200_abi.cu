@@ -843,6 +843,69 @@ int rfsb200_predict_maps(rfsb200_ctx* c, const double* Q, int32_t add_births, do
   return c->prec == 32 ? do_predict<float>(c, Q, add_births, birth_w) : do_predict<double>(c, Q, add_births, birth_w);
 }
 
+// lower Cholesky factor as Eigen::LLT computes it (n x n, row-major in / out, zero padded to 3x3)
+static void cholesky_lower(const double* A, int n, double* L) {
+  for (int k = 0; k < 9; k++) L[k] = 0;
+  for (int j = 0; j < n; j++) {
+    double s = A[j * n + j];
+    for (int k = 0; k < j; k++) s -= L[j * 3 + k] * L[j * 3 + k];
+    const double d = sqrt(s);
+    L[j * 3 + j] = d;
+    for (int i = j + 1; i < n; i++) {
+      double t = A[i * n + j];
+      for (int k = 0; k < j; k++) t -= L[i * 3 + k] * L[j * 3 + k];
+      L[i * 3 + j] = t / d;
+    }
+  }
+}
+
+int rfsb200_propagate(rfsb200_ctx* c, const rfsb200_motion_desc* m) {
+  if (!c || !m) return fail(c, RFSB200_EINVAL, "NULL argument");
+  if (m->model_id != RFSB200_MOTION_ODOMETRY2D && m->model_id != RFSB200_MOTION_ACKERMAN2D)
+    return fail(c, RFSB200_EUNSUPPORTED, "motion model id %d (MotionModel_Odometry2d = 1, MotionModel_Ackerman2d = 2)", m->model_id);
+  if (!c->have_poses) return fail(c, RFSB200_ESTATE, "propagate before set_poses");
+  if (m->model_id == RFSB200_MOTION_ACKERMAN2D && !(m->ackerman_l != 0)) return fail(c, RFSB200_EINVAL, "ackerman_l must be non-zero");
+  CU(c, cudaSetDevice(c->device));
+  MotionParams p{};
+  p.model_id = m->model_id;
+  p.n_in = m->model_id == RFSB200_MOTION_ODOMETRY2D ? 3 : 2;
+  bool q_nonzero = false;
+  for (int k = 0; k < 9; k++) q_nonzero = q_nonzero || (m->Q[k] != 0.0);
+  p.use_model_noise = (m->use_model_noise && q_nonzero) ? 1 : 0;   // ProcessModel.hpp:145: only if Q_ != 0
+  p.use_input_noise = m->use_input_noise ? 1 : 0;
+  if (p.use_model_noise) cholesky_lower(m->Q, 3, p.LQ);
+  if (p.use_input_noise) cholesky_lower(m->input_cov, p.n_in, p.Lu);
+  for (int k = 0; k < 3; k++) p.u[k] = m->input[k];
+  p.dt = m->dt; p.h = m->ackerman_h; p.l = m->ackerman_l; p.pdx = m->ackerman_dx; p.pdy = m->ackerman_dy;
+  p.seed = m->seed; p.step = m->step_counter;
+  const int blocks = (c->N + 255) / 256;
+  if (c->prec == 32) propagate_kernel<float><<<blocks, 256, 0, c->stream>>>(c->stg_small, (float*)c->pose, p, c->N);
+  else propagate_kernel<double><<<blocks, 256, 0, c->stream>>>(c->stg_small, (double*)c->pose, p, c->N);
+  CU(c, cudaGetLastError());
+  // the pose covariance after sample(): Q for every particle with model noise, none otherwise (Q1)
+  if (p.use_model_noise) {
+    unsigned char* h = c->hpin + 57344;
+    CU(c, cudaStreamSynchronize(c->stream));   // staging area reuse
+    const double q6[6] = {m->Q[0], m->Q[1], m->Q[2], m->Q[4], m->Q[5], m->Q[8]};
+    if (c->prec == 32) { float* f = (float*)h; for (int k = 0; k < 6; k++) f[k] = (float)q6[k]; f[6] = f[7] = 0.f; }
+    else { double* d = (double*)h; for (int k = 0; k < 6; k++) d[k] = q6[k]; d[6] = d[7] = 0.0; }
+    CU(c, cudaMemcpyAsync(c->pose_cov, h, 8 * c->tsize, cudaMemcpyHostToDevice, c->stream));
+    c->pose_cov_mode = 1;
+  } else {
+    c->pose_cov_mode = 0;
+  }
+  return RFSB200_OK;
+}
+
+int rfsb200_get_poses(rfsb200_ctx* c, double* pose) {
+  if (!c || !pose) return fail(c, RFSB200_EINVAL, "NULL argument");
+  if (!c->have_poses) return fail(c, RFSB200_ESTATE, "get_poses before set_poses");
+  CU(c, cudaSetDevice(c->device));
+  CU(c, cudaMemcpyAsync(pose, c->stg_small, (size_t)c->N * 3 * 8, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  return RFSB200_OK;
+}
+
 int rfsb200_resample(rfsb200_ctx* c, const int32_t* map_src, const int32_t* aux_src, const double* weight) {
   if (!c || !map_src) return fail(c, RFSB200_EINVAL, "NULL argument");
   if (!c->have_maps) return fail(c, RFSB200_ESTATE, "resample before upload_maps");
@@ -861,14 +924,15 @@ int rfsb200_resample(rfsb200_ctx* c, const int32_t* map_src, const int32_t* aux_
                                                                  (float*)out.gm, out.cnt, c->unused_alt, c->nfov_alt, out.weight,
                                                                  weight ? 1 : 0, weight ? *weight : 0.0,
                                                                  (const float*)c->pose, (const float*)c->pose_cov, (float*)c->pose_alt,
-                                                                 (float*)c->pose_cov_alt, c->pose_cov_mode, c->N, c->cap, c->npl);
+                                                                 (float*)c->pose_cov_alt, c->pose_cov_mode, c->stg_small, c->stg_small + (size_t)c->N * 9, c->N, c->cap, c->npl);
   else
     resample_gather_kernel<double><<<blocks, 128, 0, c->stream>>>((const double*)in.gm, in.cnt, c->unused, c->nfov, in.weight, c->src_dev, asrc,
                                                                   (double*)out.gm, out.cnt, c->unused_alt, c->nfov_alt, out.weight,
                                                                   weight ? 1 : 0, weight ? *weight : 0.0,
                                                                   (const double*)c->pose, (const double*)c->pose_cov, (double*)c->pose_alt,
-                                                                  (double*)c->pose_cov_alt, c->pose_cov_mode, c->N, c->cap, c->npl);
+                                                                  (double*)c->pose_cov_alt, c->pose_cov_mode, c->stg_small, c->stg_small + (size_t)c->N * 9, c->N, c->cap, c->npl);
   CU(c, cudaGetLastError());
+  CU(c, cudaMemcpyAsync(c->stg_small, c->stg_small + (size_t)c->N * 9, (size_t)c->N * 3 * 8, cudaMemcpyDeviceToDevice, c->stream));
   CU(c, cudaStreamSynchronize(c->stream));   // map_src / aux_src are the caller's (pageable) buffers
   std::swap(c->unused, c->unused_alt);
   std::swap(c->nfov, c->nfov_alt);

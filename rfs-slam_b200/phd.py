@@ -171,6 +171,32 @@ class PHDUpdater:
                self.lib.rfsb200_predict_maps(self.ctx, capi.ptr(q), 1 if add_births else 0, float(birth_weight)),
                "predict_maps")
 
+    def propagate(self, model: str, u, *, Q=None, input_cov=None, dt: float = 0.0, use_model_noise: bool = True,
+                  use_input_noise: bool = False, ackerman=(0.0, 1.0, 0.0, 0.0), seed: int = 0, step: int = 0):
+        """ParticleFilter::propagate() on the device: ProcessModel::sample() of MotionModel_Odometry2d ("odometry2d",
+        u = (dx, dy, dtheta)) or MotionModel_Ackerman2d ("ackerman2d", u = (velocity, steering), ackerman = (h, l,
+        poi_dx, poi_dy)) for every particle, in place on the device poses."""
+        m = capi.MotionDesc()
+        m.model_id = capi.MOTION_ODOMETRY2D if model == "odometry2d" else capi.MOTION_ACKERMAN2D
+        m.use_model_noise, m.use_input_noise = int(use_model_noise), int(use_input_noise)
+        if Q is not None:
+            for i, v in enumerate(np.asarray(Q, dtype=np.float64).reshape(9)):
+                m.Q[i] = float(v)
+        for i, v in enumerate(np.asarray(u, dtype=np.float64).ravel()):
+            m.input[i] = float(v)
+        if input_cov is not None:
+            for i, v in enumerate(np.asarray(input_cov, dtype=np.float64).ravel()):
+                m.input_cov[i] = float(v)
+        m.dt = float(dt)
+        m.ackerman_h, m.ackerman_l, m.ackerman_dx, m.ackerman_dy = (float(v) for v in ackerman)
+        m.seed, m.step_counter = int(seed), int(step)
+        _check(self.lib, self.ctx, self.lib.rfsb200_propagate(self.ctx, C.byref(m)), "propagate")
+
+    def get_poses(self) -> np.ndarray:
+        p = np.zeros((self.N, 3))
+        _check(self.lib, self.ctx, self.lib.rfsb200_get_poses(self.ctx, capi.ptr(p)), "get_poses")
+        return p
+
     def resample(self, map_src, aux_src=None, weight: float | None = 1.0):
         ms = np.ascontiguousarray(map_src, dtype=np.int32)
         au = None if aux_src is None else np.ascontiguousarray(aux_src, dtype=np.int32)
