@@ -271,6 +271,19 @@ int rfsb200_get_poses(rfsb200_ctx* ctx, double* pose /*[N][3]*/);
 int rfsb200_resample(rfsb200_ctx* ctx, const int32_t* map_src /*[N]*/, const int32_t* aux_src /*[N] or NULL*/,
                      const double* weight /*scalar or NULL*/);
 
+/* ---- cross-GPU particle exchange for resampling -----------------------------------
+ * A particle travels as one fixed-size record in DEVICE memory: its map planes, Gaussian count, pose (fp64 and
+ * device precision), pose covariance, unused-measurement mask and in-FOV count.  rfsb200_particle_record_bytes gives
+ * the record size of this ctx (identical on every rank with the same dims).  rfsb200_export_particles packs the
+ * particles idx[0..n) of the COMMITTED state into dev_buf (n records); rfsb200_import_particles unpacks n records into
+ * the slots slot[0..n) of the committed state (weights are set to `weight`).  dev_buf is a device pointer owned by the
+ * caller (e.g. the send / receive buffer of an all-to-all); both calls are queued on the ctx stream.  The resampling
+ * plan itself (which particle goes where) is host logic: rfs-slam_b200/dist.py:global_resample_plan. */
+int rfsb200_particle_record_bytes(rfsb200_ctx* ctx, int64_t* bytes);
+int rfsb200_export_particles(rfsb200_ctx* ctx, const int32_t* idx /*[n] host*/, int32_t n, void* dev_buf);
+int rfsb200_import_particles(rfsb200_ctx* ctx, const int32_t* slot /*[n] host*/, int32_t n, const void* dev_buf,
+                             double weight);
+
 /* ---- fused cross-GPU weight sum (one process per GPU on one node) ---------------------------------
  * rfsb200_comm_export writes a 64-byte CUDA IPC handle of this ctx's mailbox; the caller exchanges the
  * handles of all ranks (any transport: MPI, torch.distributed, files) and passes them, in rank

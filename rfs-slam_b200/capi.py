@@ -132,6 +132,9 @@ _SIGS = {
     "rfsb200_propagate": (C.c_int, [_P, C.POINTER(MotionDesc)]),
     "rfsb200_get_poses": (C.c_int, [_P, _P]),
     "rfsb200_resample": (C.c_int, [_P, _P, _P, _P]),
+    "rfsb200_particle_record_bytes": (C.c_int, [_P, C.POINTER(C.c_int64)]),
+    "rfsb200_export_particles": (C.c_int, [_P, _P, C.c_int32, _P]),
+    "rfsb200_import_particles": (C.c_int, [_P, _P, C.c_int32, _P, C.c_double]),
     "rfsb200_comm_export": (C.c_int, [_P, _P]),
     "rfsb200_comm_connect": (C.c_int, [_P, C.c_int32, C.c_int32, _P]),
     "rfsb200_comm_error": (C.c_int, [_P, C.POINTER(C.c_int32)]),

@@ -186,6 +186,81 @@ __global__ void append_soa_kernel(const int* __restrict__ add, const long long* 
   }
 }
 
+// ---- particle records for the cross-GPU exchange: [planes npl*cap T][header 128 B] per particle -----------------
+struct ParticleHeader {          // 128 bytes
+  double pose64[3];
+  double weight;
+  unsigned long long unused;
+  int cnt, nfov;
+  unsigned char pose_t[32];      // T[4]
+  unsigned char pcov_t[64];      // T[8]
+};
+static_assert(sizeof(ParticleHeader) % 16 == 0, "records must keep the planes 16-byte aligned");
+
+template <typename T>
+__global__ void export_particles_kernel(const int* __restrict__ idx, int n, const T* __restrict__ gm, const int* __restrict__ cnt,
+                                        const double* __restrict__ weight, const T* __restrict__ pose, const T* __restrict__ pcov,
+                                        int pose_cov_mode, const double* __restrict__ pose64,
+                                        const unsigned long long* __restrict__ unused, const int* __restrict__ nfov,
+                                        unsigned char* __restrict__ buf, long long rec, int cap, int npl, int N) {
+  const int lane = threadIdx.x & 31;
+  const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (k >= n) return;
+  int i = idx[k];
+  i = i < 0 ? 0 : (i >= N ? N - 1 : i);
+  unsigned char* r = buf + (size_t)k * rec;
+  T* planes = reinterpret_cast<T*>(r);
+  const T* g = gm + (size_t)i * npl * cap;
+  const int c = cnt[i];
+  for (int pl = 0; pl < npl; pl++)
+    for (int j = lane; j < c; j += 32) planes[(size_t)pl * cap + j] = g[(size_t)pl * cap + j];
+  if (lane == 0) {
+    ParticleHeader* h = reinterpret_cast<ParticleHeader*>(r + (size_t)npl * cap * sizeof(T));
+    for (int d = 0; d < 3; d++) h->pose64[d] = pose64[3 * i + d];
+    h->weight = weight[i];
+    h->unused = unused[i];
+    h->cnt = c;
+    h->nfov = nfov[i];
+    T* pt = reinterpret_cast<T*>(h->pose_t);
+    for (int d = 0; d < 4; d++) pt[d] = pose[4 * i + d];
+    T* pc = reinterpret_cast<T*>(h->pcov_t);
+    for (int d = 0; d < 8; d++) pc[d] = pose_cov_mode == 2 ? pcov[8 * i + d] : (pose_cov_mode == 1 ? pcov[d] : T(0));
+  }
+}
+
+template <typename T>
+__global__ void import_particles_kernel(const int* __restrict__ slot, int n, T* __restrict__ gm, int* __restrict__ cnt,
+                                        double* __restrict__ weight, T* __restrict__ pose, T* __restrict__ pcov,
+                                        int pose_cov_mode, double* __restrict__ pose64, unsigned long long* __restrict__ unused,
+                                        int* __restrict__ nfov, const unsigned char* __restrict__ buf, long long rec, int cap,
+                                        int npl, int N, double w_value) {
+  const int lane = threadIdx.x & 31;
+  const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (k >= n) return;
+  const int i = slot[k];
+  if (i < 0 || i >= N) return;
+  const unsigned char* r = buf + (size_t)k * rec;
+  const T* planes = reinterpret_cast<const T*>(r);
+  const ParticleHeader* h = reinterpret_cast<const ParticleHeader*>(r + (size_t)npl * cap * sizeof(T));
+  T* g = gm + (size_t)i * npl * cap;
+  const int c = h->cnt;
+  for (int pl = 0; pl < npl; pl++)
+    for (int j = lane; j < c; j += 32) g[(size_t)pl * cap + j] = planes[(size_t)pl * cap + j];
+  if (lane == 0) {
+    for (int d = 0; d < 3; d++) pose64[3 * i + d] = h->pose64[d];
+    weight[i] = w_value;
+    unused[i] = h->unused;
+    cnt[i] = c;
+    nfov[i] = h->nfov;
+    const T* pt = reinterpret_cast<const T*>(h->pose_t);
+    for (int d = 0; d < 4; d++) pose[4 * i + d] = pt[d];
+    if (pose_cov_mode == 2) {
+      const T* pc = reinterpret_cast<const T*>(h->pcov_t);
+      for (int d = 0; d < 8; d++) pcov[8 * i + d] = pc[d];
+    }
+  }
+}
+
 // exclusive scan of counts -> offsets[N+1]; single CTA (N is at most a few 10^5)
 __global__ void scan_counts_kernel(const int* __restrict__ cnt, long long* __restrict__ offs, int N) {
   __shared__ long long part[1024];
@@ -940,6 +1015,68 @@ int rfsb200_resample(rfsb200_ctx* c, const int32_t* map_src, const int32_t* aux_
   if (c->pose_cov_mode == 2) std::swap(c->pose_cov, c->pose_cov_alt);
   c->front ^= 1;
   c->last_out = c->front;
+  return RFSB200_OK;
+}
+
+static long long record_bytes(const rfsb200_ctx* c) {
+  return (long long)c->npl * c->cap * (long long)c->tsize + (long long)sizeof(ParticleHeader);
+}
+
+int rfsb200_particle_record_bytes(rfsb200_ctx* c, int64_t* bytes) {
+  if (!c || !bytes) return fail(c, RFSB200_EINVAL, "NULL argument");
+  *bytes = record_bytes(c);
+  return RFSB200_OK;
+}
+
+int rfsb200_export_particles(rfsb200_ctx* c, const int32_t* idx, int32_t n, void* dev_buf) {
+  if (!c || (n > 0 && (!idx || !dev_buf))) return fail(c, RFSB200_EINVAL, "NULL argument");
+  if (n < 0 || n > c->N) return fail(c, RFSB200_EINVAL, "n %d outside [0, N]", n);
+  if (!c->have_maps || !c->have_poses) return fail(c, RFSB200_ESTATE, "export before upload_maps / set_poses");
+  if (n == 0) return RFSB200_OK;
+  for (int k = 0; k < n; k++)
+    if (idx[k] < 0 || idx[k] >= c->N) return fail(c, RFSB200_EINVAL, "particle index %d out of range", idx[k]);
+  CU(c, cudaSetDevice(c->device));
+  CU(c, cudaStreamSynchronize(c->stream));   // src_dev is reused as index scratch
+  CU(c, cudaMemcpyAsync(c->src_dev, idx, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+  const StateBuf& s = c->st[c->front];
+  const int blocks = (n * 32 + 127) / 128;
+  if (c->prec == 32)
+    export_particles_kernel<float><<<blocks, 128, 0, c->stream>>>(c->src_dev, n, (const float*)s.gm, s.cnt, s.weight, (const float*)c->pose,
+                                                                  (const float*)c->pose_cov, c->pose_cov_mode, c->stg_small, c->unused, c->nfov,
+                                                                  (unsigned char*)dev_buf, record_bytes(c), c->cap, c->npl, c->N);
+  else
+    export_particles_kernel<double><<<blocks, 128, 0, c->stream>>>(c->src_dev, n, (const double*)s.gm, s.cnt, s.weight, (const double*)c->pose,
+                                                                   (const double*)c->pose_cov, c->pose_cov_mode, c->stg_small, c->unused, c->nfov,
+                                                                   (unsigned char*)dev_buf, record_bytes(c), c->cap, c->npl, c->N);
+  CU(c, cudaGetLastError());
+  CU(c, cudaStreamSynchronize(c->stream));   // idx is the caller's buffer; the records are complete on return
+  return RFSB200_OK;
+}
+
+int rfsb200_import_particles(rfsb200_ctx* c, const int32_t* slot, int32_t n, const void* dev_buf, double weight) {
+  if (!c || (n > 0 && (!slot || !dev_buf))) return fail(c, RFSB200_EINVAL, "NULL argument");
+  if (n < 0 || n > c->N) return fail(c, RFSB200_EINVAL, "n %d outside [0, N]", n);
+  if (!c->have_maps) return fail(c, RFSB200_ESTATE, "import before upload_maps");
+  if (n == 0) return RFSB200_OK;
+  for (int k = 0; k < n; k++)
+    if (slot[k] < 0 || slot[k] >= c->N) return fail(c, RFSB200_EINVAL, "slot %d out of range", slot[k]);
+  CU(c, cudaSetDevice(c->device));
+  CU(c, cudaStreamSynchronize(c->stream));
+  CU(c, cudaMemcpyAsync(c->src_dev, slot, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+  StateBuf& s = c->st[c->front];
+  const int blocks = (n * 32 + 127) / 128;
+  if (c->prec == 32)
+    import_particles_kernel<float><<<blocks, 128, 0, c->stream>>>(c->src_dev, n, (float*)s.gm, s.cnt, s.weight, (float*)c->pose, (float*)c->pose_cov,
+                                                                  c->pose_cov_mode, c->stg_small, c->unused, c->nfov, (const unsigned char*)dev_buf,
+                                                                  record_bytes(c), c->cap, c->npl, c->N, weight);
+  else
+    import_particles_kernel<double><<<blocks, 128, 0, c->stream>>>(c->src_dev, n, (double*)s.gm, s.cnt, s.weight, (double*)c->pose, (double*)c->pose_cov,
+                                                                   c->pose_cov_mode, c->stg_small, c->unused, c->nfov, (const unsigned char*)dev_buf,
+                                                                   record_bytes(c), c->cap, c->npl, c->N, weight);
+  CU(c, cudaGetLastError());
+  CU(c, cudaStreamSynchronize(c->stream));
+  c->last_out = c->front;
+  c->have_poses = true;
   return RFSB200_OK;
 }
 

@@ -48,6 +48,59 @@ def normalise_and_ess(weights: np.ndarray, sums) -> tuple[np.ndarray, float]:
     return weights / s1, (s1 * s1 / s2 if s2 > 0 else 0.0)
 
 
+# ---- resampling across shards ---------------------------------------------------------
+def reference_resample_sources(w: np.ndarray, r01: float) -> np.ndarray:
+    """Placement of ParticleFilter::resample() (include/ParticleFilter.hpp:419-479) for normalised weights w and the
+    single uniform draw r01: src[slot] = index of the particle whose copy ends up in `slot`.  Systematic sampling
+    (sample_point += 1/n, idx advances while sample_point > cumulative weight); a sampled particle keeps its own slot
+    the first time it is drawn, every further copy goes to the next slot nobody was drawn from, in ascending order."""
+    w = np.asarray(w, dtype=np.float64)
+    n = len(w)
+    interval = 1.0 / float(n)
+    steps = np.full(n, interval)
+    steps[0] = interval * float(r01)
+    sample_points = np.cumsum(steps)              # the reference accumulates sample_point += interval
+    cum = np.cumsum(w)                            # ... and cumulative_weight += w[idx], in this order
+    sampled = np.minimum(np.searchsorted(cum, sample_points, side="left"), n - 1)
+    counts = np.bincount(sampled, minlength=n)
+    src = np.arange(n, dtype=np.int64)
+    free = np.nonzero(counts == 0)[0]
+    extras = np.repeat(np.arange(n), np.maximum(counts - 1, 0))
+    src[free] = extras                            # both ascending, as the reference's next_unsampled_idx walk
+    return src
+
+
+def exchange_plan(src_global: np.ndarray, rank: int, world: int):
+    """What rank `rank` has to do for a global placement src_global[slot] with particles block-partitioned over
+    `world` ranks: (local_src [n_local] with own index as placeholder for remote sources, send = list per destination
+    rank of LOCAL particle indices to export in that order, recv = list per source rank of LOCAL slots to import into
+    in that order).  Sender and receiver enumerate the slots of a (source rank, destination rank) pair in ascending
+    slot order, so no indices travel with the payload."""
+    n = len(src_global)
+    bounds = [block_range(n, g, world) for g in range(world)]
+    owner = np.zeros(n, dtype=np.int64)
+    for g, (lo, hi) in enumerate(bounds):
+        owner[lo:hi] = g
+    lo, hi = bounds[rank]
+    slots = np.arange(n)
+    src_owner = owner[src_global]
+    local_src = np.arange(hi - lo, dtype=np.int32)
+    mine = slots[lo:hi]
+    is_local = src_owner[lo:hi] == rank
+    local_src[is_local] = (src_global[lo:hi][is_local] - lo).astype(np.int32)
+    send, recv = [], []
+    for g in range(world):
+        if g == rank:
+            send.append(np.zeros(0, np.int32)); recv.append(np.zeros(0, np.int32))
+            continue
+        glo, ghi = bounds[g]
+        to_g = slots[glo:ghi][src_owner[glo:ghi] == rank]          # slots of rank g fed by my particles
+        send.append((src_global[to_g] - lo).astype(np.int32))
+        from_g = mine[src_owner[lo:hi] == g]                        # my slots fed by rank g's particles
+        recv.append((from_g - lo).astype(np.int32))
+    return local_src, send, recv
+
+
 class ShardedUpdater:
     """RBPHDFilter::update() over particles sharded across ranks.
 
@@ -107,3 +160,50 @@ class ShardedUpdater:
         if unused_out is not None or nfov_out is not None:
             self.up.get_unused(unused_out, nfov_out)
         return None
+
+
+    # ---- resampling over ALL shards -----------------------------------------------------------------------------
+    def resample_global(self, r01: float, neff_threshold: float | None = None):
+        """ParticleFilter::resample() over the particles of all ranks: all-gather of the normalised weights, the
+        reference's systematic-sampling placement on the global index order (identical to what one process holding all
+        particles would do, so the result does not depend on the number of ranks), local copies on the device and ONE
+        all-to-all of packed particle records (maps, pose, unused-measurement mask) for the copies that change rank.
+        r01 must be the same number on every rank (one drand48() on rank 0, broadcast).  Returns the global source
+        index of every local slot, or None if N_eff is above neff_threshold (then the weights are left normalised)."""
+        import torch
+        import torch.distributed as dist
+        up = self.up
+        world = dist.get_world_size(self.group) if (dist.is_available() and dist.is_initialized()) else 1
+        rank = dist.get_rank(self.group) if world > 1 else 0
+        w_local = up.get_weights()
+        if world > 1:
+            t = torch.from_numpy(w_local).to(self.device)
+            parts = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(parts, t, group=self.group)          # equal shard sizes (block partition of a multiple of world)
+            w = torch.cat(parts).cpu().numpy()
+        else:
+            w = w_local
+        w = w / w.sum()
+        if neff_threshold is not None and 1.0 / float((w * w).sum()) > neff_threshold:
+            return None
+        src = reference_resample_sources(w, r01)
+        n_local = up.N
+        if world == 1:
+            up.resample(src.astype(np.int32), weight=1.0)
+            return src
+        assert len(w) == n_local * world, "resample_global needs equal shards"
+        local_src, send, recv = exchange_plan(src, rank, world)
+        rec = up.particle_record_bytes()
+        n_send = sum(len(x) for x in send)
+        n_recv = sum(len(x) for x in recv)
+        sbuf = torch.empty(max(1, n_send) * rec, dtype=torch.uint8, device=self.device)
+        rbuf = torch.empty(max(1, n_recv) * rec, dtype=torch.uint8, device=self.device)
+        if n_send:
+            up.export_particles(np.concatenate(send), sbuf.data_ptr())     # from the state BEFORE the local copies
+        dist.all_to_all_single(rbuf[:n_recv * rec], sbuf[:n_send * rec], [len(x) * rec for x in recv],
+                               [len(x) * rec for x in send], group=self.group)
+        up.resample(local_src, weight=1.0)
+        if n_recv:
+            up.import_particles(np.concatenate(recv), rbuf.data_ptr(), 1.0)
+        lo, hi = block_range(len(w), rank, world)
+        return src[lo:hi]

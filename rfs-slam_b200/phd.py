@@ -203,6 +203,23 @@ class PHDUpdater:
         wv = None if weight is None else np.array([weight], dtype=np.float64)
         _check(self.lib, self.ctx, self.lib.rfsb200_resample(self.ctx, capi.ptr(ms), capi.ptr(au), capi.ptr(wv)), "resample")
 
+    # ---- cross-GPU particle exchange (records in device memory) ---------------------------------------
+    def particle_record_bytes(self) -> int:
+        b = C.c_int64()
+        _check(self.lib, self.ctx, self.lib.rfsb200_particle_record_bytes(self.ctx, C.byref(b)), "particle_record_bytes")
+        return int(b.value)
+
+    def export_particles(self, idx, dev_ptr: int):
+        idx = np.ascontiguousarray(idx, dtype=np.int32)
+        _check(self.lib, self.ctx, self.lib.rfsb200_export_particles(self.ctx, capi.ptr(idx), len(idx), C.c_void_p(dev_ptr)),
+               "export_particles")
+
+    def import_particles(self, slot, dev_ptr: int, weight: float = 1.0):
+        slot = np.ascontiguousarray(slot, dtype=np.int32)
+        _check(self.lib, self.ctx,
+               self.lib.rfsb200_import_particles(self.ctx, capi.ptr(slot), len(slot), C.c_void_p(dev_ptr), float(weight)),
+               "import_particles")
+
     def comm_export(self) -> bytes:
         h = (C.c_ubyte * 64)()
         _check(self.lib, self.ctx, self.lib.rfsb200_comm_export(self.ctx, C.cast(h, C.c_void_p)), "comm_export")

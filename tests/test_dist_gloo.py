@@ -84,3 +84,87 @@ def test_block_range_covers_everything():
                 assert a[1] == b[0]
             sizes = [hi - lo for lo, hi in edges]
             assert max(sizes) - min(sizes) <= 1
+
+
+# ---- resampling across shards: host logic (placement + exchange plan) ------------------------------------------
+def _reference_resample_loop(w, r01):
+    """the reference's loops, literally (include/ParticleFilter.hpp:419-479)"""
+    n = len(w)
+    interval = 1.0 / float(n)
+    sample_point = interval * r01
+    idx = 0
+    cum = w[0]
+    flag = [0] * n
+    sampled = [0] * n
+    for i in range(n):
+        while sample_point > cum and idx < n - 1:
+            idx += 1
+            cum += w[idx]
+        sampled[i] = idx
+        flag[idx] = 1
+        sample_point += interval
+    src = list(range(n))
+    idx_prev, nxt = 0, 0
+    for i in range(n):
+        idx = sampled[i]
+        first = not (i > 0 and idx == idx_prev)
+        idx_prev = idx
+        if not (idx < n and first):
+            while flag[nxt] == 1:
+                nxt += 1
+            src[nxt] = idx
+            nxt += 1
+    return np.array(src)
+
+
+def test_resample_placement_matches_reference_loops():
+    from rfs_slam_b200 import dist as rd
+    rng = np.random.default_rng(3)
+    for n in (1, 2, 7, 64, 500):
+        for trial in range(4):
+            w = rng.random(n) ** (1 + 3 * trial)
+            w /= w.sum()
+            r01 = float(rng.random())
+            assert np.array_equal(rd.reference_resample_sources(w, r01), _reference_resample_loop(w, r01))
+
+
+def _exchange_worker(rank, world, port, n_total, seed, q):
+    import torch
+    import torch.distributed as dist
+    from rfs_slam_b200 import dist as rd
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(seed)
+    w = rng.random(n_total) ** 4
+    w /= w.sum()
+    src = rd.reference_resample_sources(w, 0.37)
+    lo, hi = rd.block_range(n_total, rank, world)
+    payload = np.arange(lo, hi, dtype=np.int64) * 10 + 7          # a "particle" is its global id here
+    local_src, send, recv = rd.exchange_plan(src, rank, world)
+    sbuf = torch.from_numpy(np.concatenate([payload[s] for s in send]) if sum(map(len, send)) else np.zeros(0, np.int64))
+    rbuf = torch.empty(sum(map(len, recv)), dtype=torch.int64)
+    dist.all_to_all_single(rbuf, sbuf, [len(x) for x in recv], [len(x) for x in send])
+    new = payload[local_src].copy()
+    if len(rbuf):
+        new[np.concatenate(recv)] = rbuf.numpy()
+    ok = np.array_equal(new, src[lo:hi] * 10 + 7)
+    q.put((rank, bool(ok), int(sum(map(len, send)))))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_exchange_plan_moves_every_copy_to_its_slot(world):
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29650 + world
+    n_total = 60 * world
+    ps = [ctx.Process(target=_exchange_worker, args=(r, world, port, n_total, 11, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in ps:
+        p.join(timeout=60)
+    assert all(ok for _, ok, _ in res), res
+    assert sum(n for _, _, n in res) > 0          # some copies did change rank
