@@ -275,7 +275,8 @@ int rfsb200_resample(rfsb200_ctx* ctx, const int32_t* map_src /*[N]*/, const int
  * A particle travels as one fixed-size record in DEVICE memory: its map planes, Gaussian count, pose (fp64 and
  * device precision), pose covariance, unused-measurement mask and in-FOV count.  rfsb200_particle_record_bytes gives
  * the record size of this ctx (identical on every rank with the same dims).  rfsb200_export_particles packs the
- * particles idx[0..n) of the COMMITTED state into dev_buf (n records); rfsb200_import_particles unpacks n records into
+ * particles idx[0..n) of the COMMITTED state into dev_buf (n records; an index may repeat and n may exceed the particle
+ * count: a heavy shard feeds many slots elsewhere); rfsb200_import_particles unpacks n <= N records into
  * the slots slot[0..n) of the committed state (weights are set to `weight`).  dev_buf is a device pointer owned by the
  * caller (e.g. the send / receive buffer of an all-to-all); both calls are queued on the ctx stream.  The resampling
  * plan itself (which particle goes where) is host logic: rfs-slam_b200/dist.py:global_resample_plan. */

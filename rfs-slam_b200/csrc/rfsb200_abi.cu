@@ -1030,25 +1030,31 @@ int rfsb200_particle_record_bytes(rfsb200_ctx* c, int64_t* bytes) {
 
 int rfsb200_export_particles(rfsb200_ctx* c, const int32_t* idx, int32_t n, void* dev_buf) {
   if (!c || (n > 0 && (!idx || !dev_buf))) return fail(c, RFSB200_EINVAL, "NULL argument");
-  if (n < 0 || n > c->N) return fail(c, RFSB200_EINVAL, "n %d outside [0, N]", n);
+  if (n < 0) return fail(c, RFSB200_EINVAL, "negative n");
   if (!c->have_maps || !c->have_poses) return fail(c, RFSB200_ESTATE, "export before upload_maps / set_poses");
   if (n == 0) return RFSB200_OK;
   for (int k = 0; k < n; k++)
     if (idx[k] < 0 || idx[k] >= c->N) return fail(c, RFSB200_EINVAL, "particle index %d out of range", idx[k]);
   CU(c, cudaSetDevice(c->device));
-  CU(c, cudaStreamSynchronize(c->stream));   // src_dev is reused as index scratch
-  CU(c, cudaMemcpyAsync(c->src_dev, idx, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
   const StateBuf& s = c->st[c->front];
-  const int blocks = (n * 32 + 127) / 128;
-  if (c->prec == 32)
-    export_particles_kernel<float><<<blocks, 128, 0, c->stream>>>(c->src_dev, n, (const float*)s.gm, s.cnt, s.weight, (const float*)c->pose,
-                                                                  (const float*)c->pose_cov, c->pose_cov_mode, c->stg_small, c->unused, c->nfov,
-                                                                  (unsigned char*)dev_buf, record_bytes(c), c->cap, c->npl, c->N);
-  else
-    export_particles_kernel<double><<<blocks, 128, 0, c->stream>>>(c->src_dev, n, (const double*)s.gm, s.cnt, s.weight, (const double*)c->pose,
-                                                                   (const double*)c->pose_cov, c->pose_cov_mode, c->stg_small, c->unused, c->nfov,
-                                                                   (unsigned char*)dev_buf, record_bytes(c), c->cap, c->npl, c->N);
-  CU(c, cudaGetLastError());
+  // a heavy shard may have to export more copies than it holds particles: in chunks of the 2N-entry index scratch
+  const int chunk = 2 * c->N;
+  for (int k0 = 0; k0 < n; k0 += chunk) {
+    const int m = std::min(chunk, n - k0);
+    CU(c, cudaStreamSynchronize(c->stream));   // src_dev is reused as index scratch
+    CU(c, cudaMemcpyAsync(c->src_dev, idx + k0, (size_t)m * 4, cudaMemcpyHostToDevice, c->stream));
+    unsigned char* dst = (unsigned char*)dev_buf + (size_t)k0 * record_bytes(c);
+    const int blocks = (m * 32 + 127) / 128;
+    if (c->prec == 32)
+      export_particles_kernel<float><<<blocks, 128, 0, c->stream>>>(c->src_dev, m, (const float*)s.gm, s.cnt, s.weight, (const float*)c->pose,
+                                                                    (const float*)c->pose_cov, c->pose_cov_mode, c->stg_small, c->unused, c->nfov,
+                                                                    dst, record_bytes(c), c->cap, c->npl, c->N);
+    else
+      export_particles_kernel<double><<<blocks, 128, 0, c->stream>>>(c->src_dev, m, (const double*)s.gm, s.cnt, s.weight, (const double*)c->pose,
+                                                                     (const double*)c->pose_cov, c->pose_cov_mode, c->stg_small, c->unused, c->nfov,
+                                                                     dst, record_bytes(c), c->cap, c->npl, c->N);
+    CU(c, cudaGetLastError());
+  }
   CU(c, cudaStreamSynchronize(c->stream));   // idx is the caller's buffer; the records are complete on return
   return RFSB200_OK;
 }
