@@ -252,8 +252,18 @@ def main():
     if rank == 0:
         clocks.start()
     t_wall0 = time.perf_counter()
-    for k in range(K):
+    align = torch.zeros(1, dtype=torch.float32, device=dev)
+
+    def flush_and_align():
         flush.zero_()                 # > L2 (126 MB): the step reads its inputs from HBM
+        if world > 1:
+            # the 512 MiB memset is a measurement artefact whose duration differs from GPU to GPU; back-to-back
+            # steps of a real run start aligned by the previous step's collective, so the ranks are re-aligned
+            # here (untimed, on the launch stream) before the step's first event
+            dist.all_reduce(align)
+
+    for k in range(K):
+        flush_and_align()
         ev[k][0].record()
         sh.step(wl.Z, flags=FLAGS)    # Z H2D (1.3 KB) + fused update kernel (+ cross-GPU sum + normalise inside)
         ev[k][1].record()
@@ -300,7 +310,7 @@ def main():
         te = 0.0
         tw0 = time.perf_counter()
         for _ in range(Ke):
-            flush.zero_()
+            flush_and_align()
             e0.record()
             e2e_step()
             e1.record()
@@ -357,7 +367,9 @@ def main():
                     ms_per_step=1e3 * t_max / K, higher_is_better=True, scaling="weak", vs_baseline=None,
                     dtype="f32", data="synthetic",
                     config=dict(workload=desc, particles_total=N * world, particles_per_gpu=N, gm_per_particle=nM_in,
-                                gm_out_per_particle=nM_out_mean, meas=nZ, l2="flushed between steps (512 MiB memset, untimed)",
+                                gm_out_per_particle=nM_out_mean, meas=nZ,
+                                l2="flushed between steps (512 MiB memset, untimed"
+                                   + (", followed by an untimed 4-byte all-reduce that re-aligns the ranks)" if world > 1 else ")"),
                                 timing="CUDA events per step on the launch stream, summed; max over ranks",
                                 parallelism=f"particles block-partitioned over {world} GPU(s); one all-reduce of [sum w, sum w^2] per step "
                                             + ("inside the update kernel over NVLink peer memory" if fused else "by NCCL")),

@@ -982,55 +982,86 @@ __device__ __forceinline__ void step_epilogue(const KParams<T>& p, int lane, int
   __syncthreads();
   if (is_last) {
     __threadfence();
-    double s1 = 0, s2 = 0;
-    for (int i = threadIdx.x; i < p.N; i += blockDim.x) {
-      const double w = __ldcg(p.w_out + i);
-      s1 += w;
-      s2 += w * w;
+    // fixed summation order (bit-reproducible): thread t owns particles t, t + nt, ...; four loads in flight
+    // per thread, because this loop runs on ONE CTA at the end of every step and is pure L2 latency
+    double s1, s2;
+    {
+      const int nt = blockDim.x;
+      double a0 = 0, a1 = 0, a2 = 0, a3 = 0, b0 = 0, b1 = 0, b2 = 0, b3 = 0;
+      int i = threadIdx.x;
+      for (; i + 3 * nt < p.N; i += 4 * nt) {
+        const double w0 = __ldcg(p.w_out + i), w1 = __ldcg(p.w_out + i + nt), w2 = __ldcg(p.w_out + i + 2 * nt),
+                     w3 = __ldcg(p.w_out + i + 3 * nt);
+        a0 += w0; a1 += w1; a2 += w2; a3 += w3;
+        b0 += w0 * w0; b1 += w1 * w1; b2 += w2 * w2; b3 += w3 * w3;
+      }
+      for (; i < p.N; i += nt) {
+        const double w = __ldcg(p.w_out + i);
+        a0 += w;
+        b0 += w * w;
+      }
+      s1 = (a0 + a1) + (a2 + a3);
+      s2 = (b0 + b1) + (b2 + b3);
     }
     s1 = warp_sum(s1);
     s2 = warp_sum(s2);
     if (lane == 0) { red[0][warp] = s1; red[1][warp] = s2; }
     __syncthreads();
+    __shared__ double xs[2][8];
+    __shared__ int xok;
     if (threadIdx.x == 0) {
       double a = 0, b = 0;
       for (int k = 0; k < (int)(blockDim.x >> 5); k++) { a += red[0][k]; b += red[1][k]; }
-      if (p.comm_world > 1) {
-        // ---- fused all-reduce: every rank writes its pair into slot [parity][rank] of EVERY rank's
-        // mailbox (remote stores over NVLink), then waits until its own mailbox holds this epoch from
-        // all ranks and adds them in rank order — the same bits on every GPU, no extra launch.
-        // Slots are double-buffered on the epoch's parity: a rank can be at most one step ahead.
-        const unsigned long long e = p.comm_epoch;
-        const int par = (int)(e & 1ull);
-        for (int r = 0; r < p.comm_world; r++) {
-          CommSlot* dst = reinterpret_cast<CommSlot*>(p.comm_peer[r]) + par * 8 + p.comm_rank;
-          *reinterpret_cast<volatile double*>(&dst->s1) = a;
-          *reinterpret_cast<volatile double*>(&dst->s2) = b;
-          __threadfence_system();
-          asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(&dst->epoch), "l"(e) : "memory");
-        }
+      red[0][0] = a;
+      red[1][0] = b;
+      xok = 1;
+    }
+    if (p.comm_world > 1) {
+      // ---- fused all-reduce: every rank writes its pair into slot [parity][rank] of EVERY rank's
+      // mailbox (remote stores over NVLink), then waits until its own mailbox holds this epoch from
+      // all ranks and adds them in rank order — the same bits on every GPU, no extra launch.
+      // Slots are double-buffered on the epoch's parity: a rank can be at most one step ahead.
+      // Thread r talks to rank r, so the remote stores and the waits of the (up to 8) peers overlap.
+      __syncthreads();
+      const unsigned long long e = p.comm_epoch;
+      const int par = (int)(e & 1ull);
+      if ((int)threadIdx.x < p.comm_world) {
+        const int r = threadIdx.x;
+        CommSlot* dst = reinterpret_cast<CommSlot*>(p.comm_peer[r]) + par * 8 + p.comm_rank;
+        *reinterpret_cast<volatile double*>(&dst->s1) = red[0][0];
+        *reinterpret_cast<volatile double*>(&dst->s2) = red[1][0];
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(&dst->epoch), "l"(e) : "memory");
         const CommSlot* mine = reinterpret_cast<const CommSlot*>(p.comm_peer[p.comm_rank]) + par * 8;
-        double ta = 0, tb = 0;
-        bool ok = true;
         unsigned long long t0;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-        for (int r = 0; r < p.comm_world && ok; r++) {
-          while (true) {
-            unsigned long long got;
-            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(got) : "l"(&mine[r].epoch) : "memory");
-            if (got == e) break;
-            unsigned long long t1;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-            if (t1 - t0 > 2000000000ull) { ok = false; break; }   // 2 s: a peer never launched
-          }
-          if (ok) {
-            ta += *reinterpret_cast<const volatile double*>(&mine[r].s1);
-            tb += *reinterpret_cast<const volatile double*>(&mine[r].s2);
-          }
+        bool ok = true;
+        while (true) {
+          unsigned long long got;
+          asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(got) : "l"(&mine[r].epoch) : "memory");
+          if (got == e) break;
+          unsigned long long t1;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+          if (t1 - t0 > 2000000000ull) { ok = false; break; }   // 2 s: a peer never launched
         }
-        if (ok) { a = ta; b = tb; }
-        else { *p.comm_error = 1; a = __longlong_as_double(0x7ff8000000000000LL); b = a; }
+        if (ok) {
+          xs[0][r] = *reinterpret_cast<const volatile double*>(&mine[r].s1);
+          xs[1][r] = *reinterpret_cast<const volatile double*>(&mine[r].s2);
+        } else {
+          atomicAnd(&xok, 0);
+        }
       }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        double ta = 0, tb = 0;
+        for (int r = 0; r < p.comm_world; r++) { ta += xs[0][r]; tb += xs[1][r]; }
+        if (!xok) { *p.comm_error = 1; ta = __longlong_as_double(0x7ff8000000000000LL); tb = ta; }
+        red[0][0] = ta;
+        red[1][0] = tb;
+      }
+    }
+    if (threadIdx.x == 0) {
+      const double a = red[0][0], b = red[1][0];
       p.sums[0] = a;
       p.sums[1] = b;
       red[0][0] = a;
@@ -1050,7 +1081,14 @@ __device__ __forceinline__ void step_epilogue(const KParams<T>& p, int lane, int
     if (p.fused_normalize) {   // ParticleFilter::normalizeWeights, in the same launch
       __syncthreads();
       const double total = red[0][0];
-      for (int i = threadIdx.x; i < p.N; i += blockDim.x) p.w_out[i] = __ldcg(p.w_out + i) / total;
+      const int nt = blockDim.x;
+      int i = threadIdx.x;
+      for (; i + 3 * nt < p.N; i += 4 * nt) {
+        const double w0 = __ldcg(p.w_out + i), w1 = __ldcg(p.w_out + i + nt), w2 = __ldcg(p.w_out + i + 2 * nt),
+                     w3 = __ldcg(p.w_out + i + 3 * nt);
+        p.w_out[i] = w0 / total; p.w_out[i + nt] = w1 / total; p.w_out[i + 2 * nt] = w2 / total; p.w_out[i + 3 * nt] = w3 / total;
+      }
+      for (; i < p.N; i += nt) p.w_out[i] = __ldcg(p.w_out + i) / total;
     }
   }
 }
