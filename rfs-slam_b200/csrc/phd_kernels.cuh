@@ -20,7 +20,7 @@
 namespace rfsb200 {
 
 constexpr int WARPS_PER_CTA = 4;       // default; the 2-D multi-feature kernel runs 5 (see mf_region_bytes)
-constexpr int MAX_WARPS_PER_CTA = 8;
+constexpr int MAX_WARPS_PER_CTA = 16;
 constexpr int MAX_Z = 64;
 constexpr int MAX_EVAL = 32;
 constexpr int DP_MAXB = 7;     // assignment-sum DP: the smaller side of a partition has <= 7 members
@@ -1135,7 +1135,7 @@ __host__ __device__ inline int z_bytes() {
 }
 
 template <typename T, bool MF>
-__global__ void __launch_bounds__(MF ? 160 : 128, MF ? 3 : 4)
+__global__ void __launch_bounds__(512, 1)
 phd_update_kernel(const __grid_constant__ KParams<T> p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;

@@ -198,7 +198,7 @@ __device__ __forceinline__ void vp_row_refresh(VPRow<T>& r, T tt) {
 }
 
 template <typename T, bool MF>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 2)
+__global__ void __launch_bounds__(512, 1)
 phd_update_vp_kernel(const __grid_constant__ VPParams<T> vp) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const KParams<T>& p = vp.k;
