@@ -164,10 +164,9 @@ __device__ __forceinline__ void load_sym3(Sym3<T>& s, const T* cur, int W, int i
 
 // ---- shared memory layout ------------------------------------------------------------------------------
 //  per CTA : lidar scan double[720] | P_D table double[16] | Z T[3 * MAX_Z]
-//  per warp: planes T[NPL][W] (NPL = 10, +1 weight_prev in multi-feature mode) | aux u32[W] | keys u64[W]
-//            (sort keys; merge reach T[W] aliases them) | order u16[W] | colsum T[MAX_Z] | evalIdx int[MAX_EVAL] |
-//            mbarrier | multi-feature scratch: rowmask / components / DP tables / eval block / L table |
-//            7 planes T[W] (inverse covariance + log normaliser; also the permutation temporary)
+//  per warp: planes T[NPL][W] (NPL = 10, +1 weight_prev in multi-feature mode) | aux u32[W] | colsum T[MAX_Z] |
+//            evalIdx int[MAX_EVAL] | mbarrier | work region (vp_region_bytes).  The eval points' P_D, which the
+//            intensity and the L-table stages both need, lives in colsum[] (dead after S3).
 template <typename T>
 __host__ __device__ inline int vp_cta_bytes() {
   return (int)((VP_SCAN_MAX * 8 + VP_PD_MAX * 8 + 3 * MAX_Z * sizeof(T) + 127) & ~127);
@@ -177,11 +176,26 @@ __host__ __device__ inline int vp_mf_fixed_bytes(int n_eval, int zcap) {
   const int ltab = (n_eval * zcap + 3) & ~3;
   return (int)(8 * (MAX_EVAL + MAX_COMP + 2 * (1 << DP_MAXB)) + 4 * MAX_COMP + sizeof(T) * (MAX_EVAL * VP_EP + ltab) + 15) & ~15;
 }
+// work region of a warp, used by stages that follow each other:
+//   sort of S5 / prune   keys u64[W] | order u16[W] | one temporary plane T[W]    (merge: reach T[W] aliases the keys,
+//                                                                                  firstCand aliases order)
+//   intensity of S5      7 planes T[W]
+//   L-table stage of S5  rowmask / components / DP tables / eval block / L table
+template <typename T>
+__host__ __device__ inline int vp_region_bytes(int W, int mf, int n_eval, int zcap) {
+  int r = W * 8 + ((W * 2 + 15) & ~15) + W * (int)sizeof(T);
+  if (mf) {
+    const int a = vp_mf_fixed_bytes<T>(n_eval, zcap), i7 = 7 * W * (int)sizeof(T);
+    r = a > r ? a : r;
+    r = i7 > r ? i7 : r;
+  }
+  return (r + 15) & ~15;
+}
 template <typename T>
 __host__ __device__ inline int vp_warp_bytes(int W, int mf, int n_eval, int zcap) {
   const int planes = mf ? VP_NPL + 1 : VP_NPL;
-  int b = planes * W * (int)sizeof(T) + W * 4 + W * 8 + ((W * 2 + 15) & ~15) + MAX_Z * (int)sizeof(T) + MAX_EVAL * 4 + 16;
-  if (mf) b += vp_mf_fixed_bytes<T>(n_eval, zcap) + 7 * W * (int)sizeof(T);
+  const int b = planes * W * (int)sizeof(T) + W * 4 + MAX_Z * (int)sizeof(T) + MAX_EVAL * 4 + 16 +
+                vp_region_bytes<T>(W, mf, n_eval, zcap);
   return (b + 127) & ~127;
 }
 
@@ -215,13 +229,14 @@ phd_update_vp_kernel(const __grid_constant__ VPParams<T> vp) {
   unsigned char* wb = smem_raw + vp_cta_bytes<T>() + (size_t)warp * p.warp_bytes;
   T* cur = reinterpret_cast<T*>(wb);
   unsigned* aux = reinterpret_cast<unsigned*>(cur + NPL * W);
-  unsigned long long* k64 = reinterpret_cast<unsigned long long*>(aux + W);
-  T* rad2 = reinterpret_cast<T*>(k64);                                  // merge only
-  unsigned short* order = reinterpret_cast<unsigned short*>(k64 + W);
-  T* colsum = reinterpret_cast<T*>(reinterpret_cast<unsigned char*>(order) + ((W * 2 + 15) & ~15));
+  T* colsum = reinterpret_cast<T*>(aux + W);
   int* evalIdx = reinterpret_cast<int*>(colsum + MAX_Z);
   uint64_t* bar = reinterpret_cast<uint64_t*>(evalIdx + MAX_EVAL);
-  unsigned char* mfs = reinterpret_cast<unsigned char*>(bar + 2);
+  unsigned char* mfs = reinterpret_cast<unsigned char*>(bar + 2);       // the work region (vp_region_bytes)
+  unsigned long long* k64 = reinterpret_cast<unsigned long long*>(mfs);
+  T* rad2 = reinterpret_cast<T*>(k64);                                  // merge only
+  unsigned short* order = reinterpret_cast<unsigned short*>(k64 + W);
+  T* sort_tmp = reinterpret_cast<T*>(reinterpret_cast<unsigned char*>(order) + ((W * 2 + 15) & ~15));
 
   for (int k = threadIdx.x; k < VP_SCAN_MAX; k += blockDim.x) scan_s[k] = k < vp.scan_n ? vp.scan[k] : 0.0;
   for (int k = threadIdx.x; k < VP_PD_MAX; k += blockDim.x) pd_s[k] = k < vp.pd_n ? vp.pd_table[k] : 0.0;
@@ -446,7 +461,7 @@ phd_update_vp_kernel(const __grid_constant__ VPParams<T> vp) {
       if (nEvalCfg == 0) {
         weight_new = 4.9406564584124654e-324;   // denorm_min (:742-745, Q10)
       } else {
-        T* ia = reinterpret_cast<T*>(mfs + vp_mf_fixed_bytes<T>(p.n_eval_cap, p.zcap));   // [7][W]
+        T* ia = reinterpret_cast<T*>(mfs);   // [7][W]; dead before the L-table stage takes the region over
         {  // sortByWeight (:746): weight descending, ties by position
           const int P2 = next_pow2(n);
           if constexpr (sizeof(T) == 4) {
@@ -468,7 +483,7 @@ phd_update_vp_kernel(const __grid_constant__ VPParams<T> vp) {
             for (int k = lane; k < n; k += 32) order[k] = (unsigned short)aux[k];
           }
           __syncwarp();
-          T* tmp = ia;
+          T* tmp = sort_tmp;
           for (int pl = 0; pl < NPL; pl++) {
             for (int k = lane; k < n; k += 32) tmp[k] = cur[pl * W + order[k]];
             __syncwarp();
@@ -483,7 +498,7 @@ phd_update_vp_kernel(const __grid_constant__ VPParams<T> vp) {
         double* f1 = f0 + (1 << DP_MAXB);
         unsigned* compR = reinterpret_cast<unsigned*>(f1 + (1 << DP_MAXB));         // [MAX_COMP]
         T* ep = reinterpret_cast<T*>(compR + MAX_COMP);   // [MAX_EVAL][VP_EP - 1] eval-point block
-        T* evalPd = ep + MAX_EVAL * (VP_EP - 1);          // [MAX_EVAL]
+        T* evalPd = colsum;                               // [MAX_EVAL] (colsum is dead after S3; MAX_EVAL <= MAX_Z)
         T* L = ep + MAX_EVAL * VP_EP;                     // [nE][nZ]
         int nE = 0;
         for (int base = 0; base < n && nE < nEvalCfg; base += 32) {
