@@ -810,6 +810,11 @@ static int enqueue_update(rfsb200_ctx* c, const double* Z, int32_t nZ, uint32_t 
     }
   }
   int launches = 0;
+  {  // launch configuration (occupancy queries on the first call of a mode): host work, kept out of the timed span
+    const int mf = c->cfg.use_cluster_process ? 0 : 1;
+    const int rc0 = (c->prec == 32) ? configure_launch<float>(c, mf) : configure_launch<double>(c, mf);
+    if (rc0) return rc0;
+  }
   if (timed) CU(c, cudaEventRecord(c->ev0, c->stream));
   CU(c, cudaMemcpyAsync(c->Zdev, zsrc, (size_t)c->ld * nZ * c->tsize, cudaMemcpyHostToDevice, c->stream));
   CU(c, cudaEventRecord(c->zev[zslot_used], c->stream));
