@@ -1101,11 +1101,11 @@ __device__ __forceinline__ void step_epilogue(const KParams<T>& p, int lane, int
 // The work region is the merge scratch.  In multi-feature mode the stages of S5 run before the merge and
 // reuse the same bytes, one after the other (each stage's data is dead when the next one starts):
 //   sort       perm = order[], keys = keys[] (+ a temporary plane behind the keys in the fp64 build)
-//   intensity  4 planes T[W] (inverse covariance, log normaliser)
+//   intensity  6 planes T[W] (inverse covariance, log normaliser, two bound coefficients)
 //   L table    rowmask | compC | f1 | (f0) | compR | eval-point block | L    (f0 lives in aux[] when W >= 256)
-// so the region is max(merge scratch, 4 planes, L-table stage) — with the defaults (W = 256, 15 eval points,
-// <= 32 measurements, fp32) exactly the merge scratch, 14 kB per warp in total, and five warps per CTA give
-// 15 resident warps per SM instead of 8 with a separate multi-feature scratch.
+// so the region is max(merge scratch, 6 planes, L-table stage) — with the defaults (W = 256, 15 eval points,
+// <= 32 measurements, fp32) 6 kB, 14.5 kB per warp in total: 15 resident warps per SM instead of 8 with a
+// separate multi-feature scratch.
 template <typename T>
 __host__ __device__ inline int mf_stage3_bytes(int W, int n_eval, int zcap) {
   const int ltab = (n_eval * zcap + 3) & ~3;
@@ -1115,7 +1115,7 @@ __host__ __device__ inline int mf_stage3_bytes(int W, int n_eval, int zcap) {
 template <typename T>
 __host__ __device__ inline int mf_region_bytes(int W, int n_eval, int zcap) {
   int r = merge_scratch_bytes<T>(W);
-  const int a = 4 * W * (int)sizeof(T), b = mf_stage3_bytes<T>(W, n_eval, zcap);
+  const int a = 6 * W * (int)sizeof(T), b = mf_stage3_bytes<T>(W, n_eval, zcap);
   r = a > r ? a : r;
   r = b > r ? b : r;
   return (r + 15) & ~15;
@@ -1158,7 +1158,6 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
   int* evalIdx = reinterpret_cast<int*>(colsum + MAX_Z);      // [MAX_EVAL]
   uint64_t* bar = reinterpret_cast<uint64_t*>(evalIdx + MAX_EVAL);
   unsigned char* mfs = after;   // multi-feature stages reuse the work region (see mf_region_bytes)
-  (void)bar;
 
   // ---- the measurement batch and the corrector's window tables (once per CTA) ------------------
   // tabR[b] = set of measurements whose range bin is < b, tabB likewise on the bearing: the
@@ -1594,17 +1593,23 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
         sw_now = warp_sum(sw_now);
         // intensity at the eval points before / after the update (:776-800):
         //   v(e) = denorm_min + sum_m w_m N(x_e; x_m, P_m), once with the previous and once with the new weights.
-        // Per-component inverse covariance and log normaliser are precomputed (4 planes in the MF
-        // scratch); then ONE LANE PER EVAL POINT (two lanes, splitting the components, when there are
+        // Per-component inverse covariance, log normaliser and two bound coefficients are precomputed (6 planes in
+        // the work region); then ONE LANE PER EVAL POINT (two lanes, splitting the components, when there are
         // at most 16 eval points) runs an online log-sum-exp over the components, whose data are
         // broadcast reads.
-        T* ia = reinterpret_cast<T*>(mfs);   // [4][W] (the sort's perm / keys are dead)
+        T* ia = reinterpret_cast<T*>(mfs);   // [6][W] (the sort's perm / keys are dead)
         for (int m = lane; m < n; m += 32) {
           const T a = cur[2 * W + m], b = cur[3 * W + m], c = cur[4 * W + m];
           const T det = a * c - b * b;
           const T invdet = T(1) / det;
           ia[m] = c * invdet; ia[W + m] = -b * invdet; ia[2 * W + m] = a * invdet;
           ia[3 * W + m] = M<T>::log_(M<T>::TWO_PI * M<T>::sqrt_(det));
+          // |d|^2 / lambda_max <= md2 <= |d|^2 / lambda_min with lambda_max <= trace and lambda_min >= det / trace for
+          // a PD covariance: two coefficients that bound the exponent of the component at distance |d| from above
+          // and from below (0.1 % slack against rounding); 0 / inf = no bound
+          const bool pd = (a > T(0)) && (c > T(0)) && (det > T(0));
+          ia[4 * W + m] = pd ? T(0.4995) / (a + c) : T(0);
+          ia[5 * W + m] = pd ? T(0.5005) * (a + c) * invdet : M<T>::inf();
         }
         __syncwarp();
         double lp_before = 0, lp_after = 0;
@@ -1615,16 +1620,36 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
           const int e = groups == 2 ? (lane & 15) : lane;
           const int h = groups == 2 ? (lane >> 4) : 0;
           T mb = -M<T>::inf(), sb = 0, ma = -M<T>::inf(), sa = 0;
+          // pass 1 (cheap): a LOWER bound on the largest exponent of each sum, from the lower bound of every
+          // component's exponent; pass 2 skips the components whose UPPER bound is more than CUT below it — they
+          // could not contribute to either sum — before touching their inverse covariance or an exp
+          const int ei = (e < nE) ? evalIdx[e] : 0;
+          const T xe = cur[ei], ye = cur[W + ei];
+          const int half = (n + groups - 1) / groups;
+          const int m0 = h * half, m1 = (m0 + half < n) ? m0 + half : n;
+          T lob = -M<T>::inf(), loa = -M<T>::inf();
           if (e < nE) {
-            const int ei = evalIdx[e];
-            const T xe = cur[ei], ye = cur[W + ei];
-            const int half = (n + groups - 1) / groups;
-            const int m0 = h * half, m1 = (m0 + half < n) ? m0 + half : n;
             for (int m = m0; m < m1; m++) {
               const T dx = xe - cur[m], dy = ye - cur[W + m];
+              const T l = -ia[5 * W + m] * (dx * dx + dy * dy) - ia[3 * W + m];
+              if (cur[6 * W + m] > T(0) && l > lob) lob = l;
+              if (cur[5 * W + m] > T(0) && l > loa) loa = l;
+            }
+          }
+          if (groups == 2) {
+            const T ob = __shfl_xor_sync(FULL, lob, 16), oa = __shfl_xor_sync(FULL, loa, 16);
+            lob = ob > lob ? ob : lob;
+            loa = oa > loa ? oa : loa;
+          }
+          const T skip_below = (lob < loa ? lob : loa) - CUT;   // -inf (no skipping) while a sum has no term at all
+          if (e < nE) {
+            for (int m = m0; m < m1; m++) {
+              const T dx = xe - cur[m], dy = ye - cur[W + m];
+              const T lnm = ia[3 * W + m];
+              if (-ia[4 * W + m] * (dx * dx + dy * dy) - lnm <= skip_below) continue;
               const T i01 = ia[W + m];
               const T md2 = (dx * ia[m] + dy * i01) * dx + (dx * i01 + dy * ia[2 * W + m]) * dy;
-              const T t = T(-0.5) * md2 - ia[3 * W + m];
+              const T t = T(-0.5) * md2 - lnm;
               const T wp = cur[6 * W + m], wn = cur[5 * W + m];
               if (wp > T(0)) {
                 if (t > mb) { sb = sb * M<T>::exp_(mb - t) + wp; mb = t; }
