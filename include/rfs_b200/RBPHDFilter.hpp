@@ -272,7 +272,7 @@ class RBPHDFilter : public ParticleFilter<RobotProcessModel, MeasurementModel,
   int cacheIdx_;
   std::vector<double> cMean_, cCov_, cW_;
   int cN_;
-  std::vector<double> hPose_, hPoseCov_, hW_;
+  std::vector<double> hPose_, hPoseCov_, hW_, hWout_;
 
   void ensureCtx();
   void check(int rc, const char* what) {
@@ -281,7 +281,7 @@ class RBPHDFilter : public ParticleFilter<RobotProcessModel, MeasurementModel,
       throw std::runtime_error(msg);
     }
   }
-  void uploadPoses();
+  bool gatherPoses();   /* particleSet_ -> hPose_, hPoseCov_, hW_; true if some particle carries a pose covariance */
   void invalidateCache() { cacheIdx_ = -1; }
   /* ParticleFilter declares this pure virtual; the weighting of every particle happens inside
    * rfsb200_update (reference :728-819), so the per-particle host hook has nothing to do */
@@ -365,11 +365,12 @@ void RBPHDFilter<R, L, M, K>::ensureCtx() {
 }
 
 template <class R, class L, class M, class K>
-void RBPHDFilter<R, L, M, K>::uploadPoses() {
+bool RBPHDFilter<R, L, M, K>::gatherPoses() {
   const int N = this->nParticles_;
   hPose_.resize((size_t)N * 3);
   hPoseCov_.resize((size_t)N * 6);
   hW_.resize(N);
+  hWout_.resize(N);
   bool anyCov = false;
   for (int i = 0; i < N; i++) {
     typename TPose::Vec x;
@@ -381,8 +382,7 @@ void RBPHDFilter<R, L, M, K>::uploadPoses() {
     for (int k = 0; k < 6; k++) anyCov = anyCov || (c[k] != 0.0);
     hW_[i] = this->particleSet_[i]->getWeight();
   }
-  check(rfsb200_set_poses(ctx_, hPose_.data(), anyCov ? hPoseCov_.data() : NULL, anyCov ? 2 : 0, hW_.data()),
-        "rfsb200_set_poses");
+  return anyCov;
 }
 
 template <class R, class L, class M, class K>
@@ -437,7 +437,7 @@ void RBPHDFilter<R, L, M, K>::update(std::vector<TMeasurement>& Z) {
   fc.use_cluster_process = config.useClusterProcess_ ? 1 : 0;
   check(rfsb200_set_filter_cfg(ctx_, &fc), "rfsb200_set_filter_cfg");
 
-  uploadPoses();
+  const bool anyCov = gatherPoses();
   std::vector<double> z((size_t)nZ * LD);
   for (unsigned k = 0; k < nZ; k++) {
     typename TMeasurement::Vec v;
@@ -482,15 +482,17 @@ void RBPHDFilter<R, L, M, K>::update(std::vector<TMeasurement>& Z) {
   }
   /* all particles: map update, weighting, merge, prune, weight sums — no normalisation yet, the
    * resampling gate needs the unnormalised weights exactly like the reference */
-  check(rfsb200_update(ctx_, z.data(), (int32_t)nZ, RFSB200_UPDATE_NO_NORMALIZE, &lastStep_), "rfsb200_update");
+  /* one ABI call, one synchronisation: poses / pose covariances / weights / Z in, unnormalised weights out */
+  check(rfsb200_update_host(ctx_, hPose_.data(), anyCov ? hPoseCov_.data() : NULL, anyCov ? 2 : 0, hW_.data(), z.data(),
+                            (int32_t)nZ, RFSB200_UPDATE_NO_NORMALIZE, hWout_.data(), NULL, NULL, &lastStep_),
+        "rfsb200_update_host");
   ns_update_ += (long long)(lastStep_.elapsed_us * 1000.0);
   unusedFresh_ = true;
   if (getenv("RFSB200_TRACE"))   /* diagnostics for unchanged drivers: one line per update on stderr */
     fprintf(stderr, "[rfsb200] update nZ=%u gm_in=%lld gm_out=%lld max_out=%d overflow=%d murty=%d device_us=%.1f\n", nZ,
             (long long)lastStep_.gm_total_in, (long long)lastStep_.gm_total_out, lastStep_.gm_max_out, lastStep_.n_overflow,
             lastStep_.n_murty, lastStep_.elapsed_us);
-  check(rfsb200_get_weights(ctx_, 0, hW_.data()), "rfsb200_get_weights");
-  for (int i = 0; i < this->nParticles_; i++) this->particleSet_[i]->setWeight(hW_[i]);
+  for (int i = 0; i < this->nParticles_; i++) this->particleSet_[i]->setWeight(hWout_[i]);
 
   timer_particleResample_.resume();
   resampleOccured_ = false;
@@ -502,7 +504,7 @@ void RBPHDFilter<R, L, M, K>::update(std::vector<TMeasurement>& Z) {
     nUpdatesSinceResample_ = 0;
     nMeasurementsSinceResample_ = 0;
   } else {
-    this->normalizeWeights();   /* host copy; the device copy is refreshed by the next uploadPoses() */
+    this->normalizeWeights();   /* host copy; the device copy is refreshed by the next update() */
   }
   timer_particleResample_.stop();
 }
