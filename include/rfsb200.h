@@ -131,7 +131,10 @@ typedef struct rfsb200_filter_cfg {
   int32_t use_cluster_process;                   /* useClusterProcess_                            */
   int32_t assignment_sum_method;                 /* 0 = enumeration order of the reference
                                                     (PermutationLexicographic / Murty-200),
-                                                    1 = matrix-permanent identity (MatPerm path)  */
+                                                    1 = matrix-permanent identity (MatPerm path) for
+                                                    partitions of up to 11 members whose Ryser-type sum is
+                                                    numerically safe (a-posteriori cancellation bound),
+                                                    the subset DP otherwise                           */
   int32_t reserved_i[3];
   double  reserved[6];
 } rfsb200_filter_cfg;

@@ -918,10 +918,10 @@ __device__ __forceinline__ double mf_partition_loglik(const T* L, const T* evalP
         const int bsmall = nR < nC ? nR : nC;
         if (bsmall > DP_MAXB) { flags |= FLAG_DP_OVERFLOW; continue; }
         __syncwarp();
-        if (sum_method == 1 && nR + nC <= 12) {
+        if (sum_method == 1 && nR + nC <= 11) {
           // MatPerm path: sum = (prod kappa) * perm([[L/kappa, diag(1-Pd)],[ones]]) / nC!
           const int nn = nR + nC;
-          double* Am = f0;   // nn*nn <= 144 doubles  (f0/f1 hold 256)
+          double* Am = f0;   // nn*nn <= 121 doubles: f0 alone holds 128 (f0 and f1 are not adjacent in every layout)
           int ridx[12], cidx[12];
           { int k = 0; unsigned m = cr; while (m) { ridx[k++] = __ffs(m) - 1; m &= m - 1; }
             k = 0; unsigned long long mc = cc; while (mc) { cidx[k++] = __ffsll((long long)mc) - 1; mc &= mc - 1; } }
@@ -936,8 +936,23 @@ __device__ __forceinline__ double mf_partition_loglik(const T* L, const T* evalP
           }
           __syncwarp();
           const double perm = warp_permanent(Am, nn, lane);
-          double fact = 1; for (int k = 2; k <= nC; k++) fact *= k;
-          logL += log(perm / fact) + (double)nC * log_kappa;
+          // The Gray-code / Ryser-type formula (the reference's MatPerm::calc) adds 2^(nn-1) signed products, each
+          // bounded by the product of the row sums: with L / kappa spanning many decades the cancellation eats the
+          // result.  A-posteriori bound on the relative error; if it is not negligible the partition is summed by
+          // the subset DP instead (all terms non-negative, no cancellation).
+          double rs = 0;
+          if (lane < nn) for (int c = 0; c < nn; c++) rs += fabs(Am[lane * nn + c]);
+          double bound = 1;
+          for (int r = 0; r < nn; r++) bound *= __shfl_sync(FULL, rs, r);
+          const double rel_err = ldexp(1.2e-16, nn - 1) * bound / fabs(perm);
+          __syncwarp();
+          if (rel_err < 1e-11) {
+            double fact = 1; for (int k = 2; k <= nC; k++) fact *= k;
+            logL += log(perm / fact) + (double)nC * log_kappa;
+          } else {
+            const double pl = partition_dp<T>(L, nZ, cr, cc, evalPd, kap, f0, f1, lane);
+            logL += log(pl);
+          }
           __syncwarp();
         } else {
           const double pl = partition_dp<T>(L, nZ, cr, cc, evalPd, kap, f0, f1, lane);
@@ -1191,8 +1206,8 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
     atomicOr(&tab[(int)zbin[k] + 1], 1ull << (k >> 1));
   }
   __syncthreads();
-  if (warp < 2) {
-    unsigned long long* tab = warp ? tabB : tabR;
+  for (int tsel = warp; tsel < 2; tsel += (int)(blockDim.x >> 5)) {   // one warp per table (a 1-warp CTA does both)
+    unsigned long long* tab = tsel ? tabB : tabR;
     unsigned long long loc[8];
     unsigned long long acc = 0;
 #pragma unroll

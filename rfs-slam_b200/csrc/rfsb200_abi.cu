@@ -324,7 +324,7 @@ template <typename K>
 int choose_warps_per_cta(rfsb200_ctx* c, K kernel, size_t cta_bytes, size_t warp_bytes) {
   int best_nw = 0, best_occ = 0, best_sms = -1;
   long long best_res = -1;
-  int nw_lo = WARPS_PER_CTA, nw_hi = MAX_WARPS_PER_CTA;
+  int nw_lo = 1, nw_hi = MAX_WARPS_PER_CTA;   // large work capacities / the fp64 build may only fit a few warps
   if (const char* e = getenv("RFSB200_WARPS_PER_CTA")) { nw_lo = nw_hi = std::max(1, std::min(MAX_WARPS_PER_CTA, atoi(e))); }   // tuning aid
   for (int nw = nw_lo; nw <= nw_hi; nw++) {
     const size_t smem = cta_bytes + (size_t)nw * warp_bytes;

@@ -324,7 +324,7 @@ def make_vp_workload(N: int, nM: int, nZ: int, *, use_cluster_process: int = 0, 
     vis = np.nonzero(visible)[0]
     n_real = min(int(math.floor(0.8 * nZ)), len(vis))
     sel = vis[rng.g.permutation(len(vis))[:n_real]]
-    if parity_extras and n_real >= 2 and visible[5]:
+    if parity_extras and nM >= 12 and n_real >= 2 and visible[5]:
         sel[0] = 5
     zr = r[sel] + 0.15 * rng.normal(n_real)
     zb = b[sel] + 0.005 * rng.normal(n_real)

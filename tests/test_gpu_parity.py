@@ -292,3 +292,16 @@ def test_update_host_equals_the_separate_calls(cuda_required):
     for x, y in zip(ca, cb):
         assert np.array_equal(x, y)
     a.close(); b.close()
+
+
+def test_randomised_sweep_fp64(cuda_required):
+    """tools/fuzz_parity.py: random sizes / thresholds / detection and clutter levels / world types for both plugin sets,
+    fp64 device build against the oracle, exact structure (this sweep found the 1-warp-CTA table bug and the
+    cancellation of the matrix-permanent path)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_parity.py"), "60", "4242"], capture_output=True,
+                       text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
