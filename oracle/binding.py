@@ -165,6 +165,10 @@ def run(wl, *, which: str = "oracle", stage: int = STAGE_FULL, sort_mode: int = 
     for k, a in out.items():
         setattr(io, k, a.ctypes.data)
     rc = fn(C.byref(io))
+    if rc == -4 and cap_total < total_in * (1 + io.nZ) + N:
+        # output arrays too small (few Gaussians, many measurements): every Gaussian can spawn one per measurement
+        return run(wl, which=which, stage=stage, sort_mode=sort_mode, n_threads=n_threads,
+                   cap_factor=float(2 + io.nZ))
     if rc != 0:
         raise RuntimeError(f"{which} update failed rc={rc}")
     tot = int(out["count_out"].sum())

@@ -128,6 +128,18 @@ def robust_mask(wl, eps=1e-3):
 
     base, up, dn = run(0), run(+1), run(-1)
     ok = np.ones(wl.N, dtype=bool)
+    if not wl.cfg.get("use_cluster_process", 0):
+        # multi-feature weighting sorts the mixture by weight (include/GaussianMixture.hpp:523-534) and both the
+        # eval-point choice and the merge order follow that order: two weights closer than an fp32 rounding (but not
+        # identical) are one more discrete decision an fp32 build may take differently
+        s2 = ob.run(wl, stage=2, sort_mode=ob.SORT_STABLE)
+        off = offsets(s2.count)
+        for i in range(wl.N):
+            w = s2.w[off[i]:off[i + 1]]
+            if len(w) > 1:
+                gap = w[:-1] - w[1:]
+                if np.any((gap > 0) & (gap < 4e-6 * np.maximum(w[:-1], 1e-30))):
+                    ok[i] = False
     for a, b, c in zip(base, up, dn):
         ok &= (a.count == b.count) & (a.count == c.count)
         ok &= (a.unused_mask == b.unused_mask) & (a.unused_mask == c.unused_mask)

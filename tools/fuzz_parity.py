@@ -12,6 +12,8 @@ import helpers
 
 n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 60
 rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 2026)
+PREC = 32 if (len(sys.argv) > 3 and sys.argv[3] == "fp32") else 64   # fp32: SURVEY tolerances, epsilon-band particles excluded
+n_excluded = n_particles = 0
 bad = 0
 for case in range(n_cases):
     vp = bool(rng.random() < 0.4)
@@ -36,19 +38,28 @@ for case in range(n_cases):
         wl = synth.make_workload(world=str(rng.choice(["dense", "sparse", "clumped"])), model=model, **kw)
     o = ob.run(wl, sort_mode=ob.SORT_STABLE)
     cap = int(max(64, (int(wl.count.max()) + int(nZ) * 8 + 63) // 8 * 8))
-    so, cnt, mean, cov, w, pw, up = helpers.run_device(wl, precision=64, gm_capacity=min(cap, 512), work_capacity=min(1024, 2 * cap))
+    so, cnt, mean, cov, w, pw, up = helpers.run_device(wl, precision=PREC, gm_capacity=min(cap, 512), work_capacity=min(1024, 2 * cap))
     flags = up.get_flags()
     mask, nfov = up.get_unused()
-    r = helpers.compare_maps(cnt, mean, cov, w, o.count, o.mean, o.cov, o.w, helpers.TOL64)
+    tol = helpers.TOL64 if PREC == 64 else helpers.TOL32
+    r = helpers.compare_maps(cnt, mean, cov, w, o.count, o.mean, o.cov, o.w, tol)
     # particles where the reference took the truncated Murty-200 branch are allowed to differ in weight (documented)
     murty = (flags & 2) != 0
-    rw = helpers.compare_weights(pw, o.weight, helpers.TOL64, mask=~murty)
-    ok = (not r["bad"]) and rw["n_bad"] == 0 and np.array_equal(mask, o.unused_mask) and np.array_equal(nfov, o.n_in_fov) and so.n_overflow == 0
+    rw = helpers.compare_weights(pw, o.weight, tol, mask=~murty)
+    if PREC == 64:
+        ok = (not r["bad"]) and rw["n_bad"] == 0 and np.array_equal(mask, o.unused_mask) and np.array_equal(nfov, o.n_in_fov) and so.n_overflow == 0
+    else:
+        robust = helpers.robust_mask(wl)
+        diff = set(r["bad"]) | set(int(i) for i in rw["idx_bad"]) | set(np.nonzero((mask != o.unused_mask) | (nfov != o.n_in_fov))[0].tolist())
+        unexplained = [i for i in diff if robust[i]]
+        n_excluded += len(diff) - len(unexplained); n_particles += wl.N
+        ok = (not unexplained) and so.n_overflow == 0
+        r["bad"] = unexplained
     if not ok:
         bad += 1
         print(f"CASE {case} FAILED: maps {r['bad'][:5]} weights {list(rw['idx_bad'][:5])} overflow {so.n_overflow} murty {int(murty.sum())} "
               f"flags {sorted(set(flags.tolist()))} unused_eq {np.array_equal(mask, o.unused_mask)} nfov_eq {np.array_equal(nfov, o.n_in_fov)} "
               f"max dlog {rw['max_dlog']:.3e} vp={vp} kw={kw} model={model}")
     up.close()
-print(f"{n_cases} random workloads, {bad} with differences")
+print(f"{n_cases} random workloads, {bad} with differences" + (f" ({n_excluded} of {n_particles} particles inside an epsilon band of a threshold)" if PREC == 32 else ""))
 sys.exit(1 if bad else 0)
