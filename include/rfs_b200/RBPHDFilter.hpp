@@ -53,6 +53,8 @@
 #include "ParticleFilter.hpp"
 #include "Timer.hpp"
 #include "KalmanFilter_VictoriaPark.hpp"   /* reference header (also brings MeasurementModel_VictoriaPark.hpp) */
+#include "ProcessModel_Odometry2D.hpp"     /* reference headers: the two motion models rfsb200_propagate implements */
+#include "ProcessModel_Ackerman2D.hpp"
 
 #include "../rfsb200.h"
 
@@ -164,6 +166,63 @@ struct ModelTraits<MeasurementModel_VictoriaPark, KalmanFilter_VictoriaPark> {
 };
 }  // namespace b200
 
+/* ---- motion models for the OPTIONAL device-side propagation (env RFSB200_DEVICE_PROPAGATE=1) -----------------
+ * ParticleFilter::propagate() stays host code by default so that unchanged drivers reproduce the reference's random
+ * stream; with the switch the poses are propagated by rfsb200_propagate (Philox stream, statistical parity only). */
+namespace b200 {
+template <class RobotProcessModel>
+struct MotionTraits {
+  static const bool supported = false;
+  template <class PM, class U>
+  static void describe(PM&, U&, const TimeStamp&, rfsb200_motion_desc&) {}
+};
+template <>
+struct MotionTraits<MotionModel_Odometry2d> {
+  static const bool supported = true;
+  template <class PM, class U>
+  static void describe(PM& pm, U& u, const TimeStamp& dT, rfsb200_motion_desc& d) {
+    d.model_id = RFSB200_MOTION_ODOMETRY2D;
+    typename U::Vec uv;
+    typename U::Mat uS;
+    u.get(uv, uS);
+    for (int i = 0; i < 3; i++) d.input[i] = uv(i);
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) d.input_cov[i * 3 + j] = uS(i, j);
+    d.dt = dT.getTimeAsDouble();
+    (void)pm;
+  }
+};
+namespace detail {
+struct AckHTag { typedef double MotionModel_Ackerman2d::*type; };
+struct AckLTag { typedef double MotionModel_Ackerman2d::*type; };
+struct AckXTag { typedef double MotionModel_Ackerman2d::*type; };
+struct AckYTag { typedef double MotionModel_Ackerman2d::*type; };
+template struct MemberPtrInit<AckHTag, &MotionModel_Ackerman2d::h_>;
+template struct MemberPtrInit<AckLTag, &MotionModel_Ackerman2d::l_>;
+template struct MemberPtrInit<AckXTag, &MotionModel_Ackerman2d::poi_offset_x_>;
+template struct MemberPtrInit<AckYTag, &MotionModel_Ackerman2d::poi_offset_y_>;
+}  // namespace detail
+template <>
+struct MotionTraits<MotionModel_Ackerman2d> {
+  static const bool supported = true;
+  template <class PM, class U>
+  static void describe(PM& pm, U& u, const TimeStamp& dT, rfsb200_motion_desc& d) {
+    d.model_id = RFSB200_MOTION_ACKERMAN2D;
+    typename U::Vec uv;
+    typename U::Mat uS;
+    u.get(uv, uS);
+    for (int i = 0; i < 2; i++) d.input[i] = uv(i);
+    for (int i = 0; i < 2; i++)
+      for (int j = 0; j < 2; j++) d.input_cov[i * 2 + j] = uS(i, j);
+    d.dt = dT.getTimeAsDouble();
+    d.ackerman_h = pm.*detail::MemberPtr<detail::AckHTag>::ptr;
+    d.ackerman_l = pm.*detail::MemberPtr<detail::AckLTag>::ptr;
+    d.ackerman_dx = pm.*detail::MemberPtr<detail::AckXTag>::ptr;
+    d.ackerman_dy = pm.*detail::MemberPtr<detail::AckYTag>::ptr;
+  }
+};
+}  // namespace b200
+
 template <class RobotProcessModel, class LmkProcessModel, class MeasurementModel, class KalmanFilter>
 class RBPHDFilter : public ParticleFilter<RobotProcessModel, MeasurementModel,
                                           GaussianMixture<typename MeasurementModel::TLandmark> > {
@@ -265,6 +324,10 @@ class RBPHDFilter : public ParticleFilter<RobotProcessModel, MeasurementModel,
   bool unusedFresh_;                 /* the device holds unused-measurement masks nobody consumed yet */
   int nUpdateCalls_;                 /* update() calls with a non-empty measurement set (diagnostics) */
   void addBirthGaussiansHost();
+  /* optional device-side ParticleFilter::propagate (RFSB200_DEVICE_PROPAGATE=1; RFSB200_SEED selects the stream) */
+  bool devicePropagate_;
+  unsigned long long propagateSeed_, propagateCount_;
+  void propagateOnDevice(TInput& u, TimeStamp const& dT, bool useModelNoise, bool useInputNoise);
   rfsb200_step_out lastStep_;
   Timer timer_predict_, timer_particleResample_;
   long long ns_update_;
@@ -327,6 +390,11 @@ RBPHDFilter<R, L, M, K>::RBPHDFilter(int n)
   if (const char* e = getenv("RFSB200_DEVICE")) deviceConfig.device = atoi(e);
   if (const char* e = getenv("RFSB200_GM_CAPACITY")) deviceConfig.gmCapacity = atoi(e);
   if (const char* e = getenv("RFSB200_WORK_CAPACITY")) deviceConfig.workCapacity = atoi(e);
+  devicePropagate_ = false;
+  if (const char* e = getenv("RFSB200_DEVICE_PROPAGATE")) devicePropagate_ = (atoi(e) != 0) && b200::MotionTraits<R>::supported;
+  propagateSeed_ = 1;
+  if (const char* e = getenv("RFSB200_SEED")) propagateSeed_ = strtoull(e, NULL, 10);
+  propagateCount_ = 0;
   lastStep_ = rfsb200_step_out();
   timingInfo_ = TimingInfo();
 }
@@ -408,7 +476,8 @@ void RBPHDFilter<R, L, M, K>::predict(TInput u, TimeStamp const& dT, bool useMod
   check(rfsb200_predict_maps(ctx_, haveQ ? q : NULL, (birthGaussianCheck && !hostBirths) ? 1 : 0, config.birthGaussianWeight_),
         "rfsb200_predict_maps");
   if (birthGaussianCheck && !hostBirths) unusedFresh_ = false;
-  this->propagate(u, dT, useModelNoise, useInputNoise, true);
+  if (devicePropagate_) propagateOnDevice(u, dT, useModelNoise, useInputNoise);
+  else this->propagate(u, dT, useModelNoise, useInputNoise, true);
   timer_predict_.stop();
 }
 
@@ -616,6 +685,42 @@ bool RBPHDFilter<R, L, M, K>::getLandmark(const int i, const int m, typename TLa
     for (int c = r; c < LD; c++, k++) S(r, c) = S(c, r) = cCov_[NC * m + k];
   w = cW_[m];
   return true;
+}
+
+/* ParticleFilter::propagate(u, dT, ..., maintainTrajectory = true) (include/ParticleFilter.hpp:322-341) with
+ * ProcessModel::sample() evaluated on the device: the host poses go up (drivers may have overwritten them through
+ * setParticlePose), rfsb200_propagate draws the noise and steps the motion model for all particles, the poses come
+ * back and the trajectory chain is extended exactly as the reference does. */
+template <class R, class L, class M, class K>
+void RBPHDFilter<R, L, M, K>::propagateOnDevice(TInput& u, TimeStamp const& dT, bool useModelNoise, bool useInputNoise) {
+  const int N = this->nParticles_;
+  gatherPoses();
+  check(rfsb200_set_poses(ctx_, hPose_.data(), NULL, 0, NULL), "rfsb200_set_poses");
+  rfsb200_motion_desc md = rfsb200_motion_desc();
+  b200::MotionTraits<R>::describe(*this->pProcessModel_, u, dT, md);
+  typename TPose::Mat Q = TPose::Mat::Zero();
+  this->pProcessModel_->getNoise(Q);
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) md.Q[i * 3 + j] = Q(i, j);
+  md.use_model_noise = useModelNoise ? 1 : 0;
+  md.use_input_noise = useInputNoise ? 1 : 0;
+  md.seed = propagateSeed_;
+  md.step_counter = propagateCount_++;
+  check(rfsb200_propagate(ctx_, &md), "rfsb200_propagate");
+  check(rfsb200_get_poses(ctx_, hPose_.data()), "rfsb200_get_poses");
+  const bool withQ = useModelNoise && (Q != TPose::Mat::Zero());
+  for (int i = 0; i < N; i++) {
+    typename ParticleFilter<R, M, TGM>::pParticle p_km(new Particle<TPose, TGM>());
+    *p_km = *(this->particleSet_[i]);
+    this->particleSet_[i]->prev = p_km;
+    typename TPose::Vec x;
+    for (int k = 0; k < 3; k++) x(k) = hPose_[3 * i + k];
+    TPose x_k;
+    TimeStamp t_k = this->particleSet_[i]->getTime() + dT;
+    x_k.set(x, t_k);
+    if (withQ) x_k.setCov(Q);
+    *(this->particleSet_[i]) = x_k;
+  }
 }
 
 /* addBirthGaussians() of the reference (include/RBPHDFilter.hpp:1000-1080) for the candidate-list
