@@ -322,6 +322,7 @@ class RBPHDFilter : public ParticleFilter<RobotProcessModel, MeasurementModel,
   std::vector<std::list<BirthGaussianCandidate> > birthGaussians_;
   std::vector<int> birthParent_;     /* slot whose candidate list slot i takes over after a resample (or i) */
   bool unusedFresh_;                 /* the device holds unused-measurement masks nobody consumed yet */
+  bool overflowWarned_;
   int nUpdateCalls_;                 /* update() calls with a non-empty measurement set (diagnostics) */
   void addBirthGaussiansHost();
   /* optional device-side ParticleFilter::propagate (RFSB200_DEVICE_PROPAGATE=1; RFSB200_SEED selects the stream) */
@@ -357,7 +358,7 @@ template <class R, class L, class M, class K>
 RBPHDFilter<R, L, M, K>::RBPHDFilter(int n)
     : ParticleFilter<R, M, GaussianMixture<typename M::TLandmark> >(n),
       ctx_(NULL), nAlloc_(0), kf_(), lmkModelPtr_(new L), nUpdatesSinceResample_(0), nMeasurementsSinceResample_(0),
-      resampleOccured_(false), unusedFresh_(false), nUpdateCalls_(0), ns_update_(0), cacheIdx_(-1), cN_(0) {
+      resampleOccured_(false), unusedFresh_(false), overflowWarned_(false), nUpdateCalls_(0), ns_update_(0), cacheIdx_(-1), cN_(0) {
   kf_ = K(lmkModelPtr_, this->getMeasurementModel());
   for (int i = 0; i < n; i++) this->particleSet_[i]->setData(boost::shared_ptr<TGM>(new TGM()));
   birthGaussians_.resize(n);
@@ -557,6 +558,13 @@ void RBPHDFilter<R, L, M, K>::update(std::vector<TMeasurement>& Z) {
         "rfsb200_update_host");
   ns_update_ += (long long)(lastStep_.elapsed_us * 1000.0);
   unusedFresh_ = true;
+  if (lastStep_.n_overflow > 0 && !overflowWarned_) {
+    /* a map outgrew the device capacities: Gaussians were dropped, results differ from the reference from here on */
+    fprintf(stderr, "[rfsb200] WARNING: %d particle(s) exceeded the device capacities (gm %d / work %d Gaussians per particle); "
+                    "raise RFSB200_GM_CAPACITY / RFSB200_WORK_CAPACITY (<= 1024)\n", lastStep_.n_overflow,
+            deviceConfig.gmCapacity, deviceConfig.workCapacity);
+    overflowWarned_ = true;
+  }
   if (getenv("RFSB200_TRACE"))   /* diagnostics for unchanged drivers: one line per update on stderr */
     fprintf(stderr, "[rfsb200] update nZ=%u gm_in=%lld gm_out=%lld max_out=%d overflow=%d murty=%d device_us=%.1f\n", nZ,
             (long long)lastStep_.gm_total_in, (long long)lastStep_.gm_total_out, lastStep_.gm_max_out, lastStep_.n_overflow,
