@@ -234,9 +234,9 @@ phd_update_vp_kernel(const __grid_constant__ VPParams<T> vp) {
   uint64_t* bar = reinterpret_cast<uint64_t*>(evalIdx + MAX_EVAL);
   unsigned char* mfs = reinterpret_cast<unsigned char*>(bar + 2);       // the work region (vp_region_bytes)
   unsigned long long* k64 = reinterpret_cast<unsigned long long*>(mfs);
-  T* rad2 = reinterpret_cast<T*>(k64);                                  // merge only
   unsigned short* order = reinterpret_cast<unsigned short*>(k64 + W);
   T* sort_tmp = reinterpret_cast<T*>(reinterpret_cast<unsigned char*>(order) + ((W * 2 + 15) & ~15));
+  T* rad2 = sort_tmp;                                                   // merge only (the sort of S5 is over)
 
   for (int k = threadIdx.x; k < VP_SCAN_MAX; k += blockDim.x) scan_s[k] = k < vp.scan_n ? vp.scan[k] : 0.0;
   for (int k = threadIdx.x; k < VP_PD_MAX; k += blockDim.x) pd_s[k] = k < vp.pd_n ? vp.pd_table[k] : 0.0;
@@ -638,17 +638,57 @@ phd_update_vp_kernel(const __grid_constant__ VPParams<T> vp) {
       // modified while they are the absorbing row), so a row without such a partner cannot merge with
       // anything and is skipped; the others start their exact scan at that partner.
       unsigned short* firstCand = order;   // [W]: free between the sort of S5 and the prune
-      for (int ib = 0; ib < n; ib += 32) {
-        const int i = ib + lane;
-        unsigned short jm = 0xffffu;
-        if (i < n - 1) {
-          const T xi = cur[i], yi = cur[W + i], di = cur[2 * W + i], ri = rad2[i];
-          for (int j = i + 1; j < n; j++) {
-            const T ex = cur[j] - xi, ey = cur[W + j] - yi, ed = cur[2 * W + j] - di;
-            if (!(ex * ex + ey * ey + ed * ed > M<T>::max_(ri, rad2[j]))) { jm = (unsigned short)j; break; }
+      T rmax2 = T(0);
+      for (int j = lane; j < n; j += 32) rmax2 = M<T>::max_(rmax2, rad2[j]);
+      rmax2 = warp_max(rmax2);
+      if (rmax2 < M<T>::inf()) {
+        // every partner of a row lies within sqrt(rmax2) of it, in x in particular: sort the components by x (keys
+        // in the sort scratch, free during the merge) and look only at the neighbours inside that window
+        const int P2 = next_pow2(n);
+        for (int k = lane; k < P2; k += 32) {
+          unsigned long long key = 0ull;   // pads sort to the end (descending)
+          if (k < n) {
+            unsigned u = __float_as_uint((float)cur[k]);
+            u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);        // order-preserving map of the float to unsigned
+            key = ((unsigned long long)u << 32) | (unsigned long long)(k + 1);
+          }
+          k64[k] = key;
+        }
+        __syncwarp();
+        warp_bitonic_desc64(k64, P2, lane);
+        // the keys order by x rounded to fp32 (and the window bound is evaluated in T): widen the window a little
+        const T rwin = M<T>::sqrt_(rmax2) * T(1.001) + T(1e-3);
+        for (int sb = 0; sb < n; sb += 32) {
+          const int sp = sb + lane;
+          if (sp < n) {
+            const int i = (int)(k64[sp] & 0xffffffffull) - 1;
+            const T xi = cur[i], yi = cur[W + i], di = cur[2 * W + i], ri = rad2[i];
+            int best = 0xffff;
+            for (int dir = -1; dir <= 1; dir += 2) {
+              for (int t = sp + dir; t >= 0 && t < n; t += dir) {
+                const int j = (int)(k64[t] & 0xffffffffull) - 1;
+                const T ex = cur[j] - xi;
+                if (M<T>::abs_(ex) > rwin) break;
+                const T ey = cur[W + j] - yi, ed = cur[2 * W + j] - di;
+                if (j > i && j < best && !(ex * ex + ey * ey + ed * ed > M<T>::max_(ri, rad2[j]))) best = j;
+              }
+            }
+            firstCand[i] = (unsigned short)best;
           }
         }
-        if (i < n) firstCand[i] = jm;
+      } else {
+        for (int ib = 0; ib < n; ib += 32) {   // some covariance is not PD (infinite reach): every pair
+          const int i = ib + lane;
+          unsigned short jm = 0xffffu;
+          if (i < n - 1) {
+            const T xi = cur[i], yi = cur[W + i], di = cur[2 * W + i], ri = rad2[i];
+            for (int j = i + 1; j < n; j++) {
+              const T ex = cur[j] - xi, ey = cur[W + j] - yi, ed = cur[2 * W + j] - di;
+              if (!(ex * ex + ey * ey + ed * ed > M<T>::max_(ri, rad2[j]))) { jm = (unsigned short)j; break; }
+            }
+          }
+          if (i < n) firstCand[i] = jm;
+        }
       }
       __syncwarp();
       for (int i = 0; i < n - 1; i++) {
