@@ -129,8 +129,10 @@ def test_resample_placement_matches_reference_loops():
 
 
 def _exchange_worker(rank, world, port, n_total, seed, q):
+    sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
+    import rfs_slam_b200  # noqa: F401
     from rfs_slam_b200 import dist as rd
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -158,7 +160,7 @@ def test_exchange_plan_moves_every_copy_to_its_slot(world):
     import multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29650 + world
+    port = _free_port()
     n_total = 60 * world
     ps = [ctx.Process(target=_exchange_worker, args=(r, world, port, n_total, 11, q)) for r in range(world)]
     for p in ps:
