@@ -9,6 +9,14 @@ namespace rfsb200 {
 
 constexpr unsigned FULL = 0xffffffffu;
 
+#if defined(RFSB200_SIMT_HOST)
+// tests/simt/ — TEST INFRASTRUCTURE: the kernel sources of this directory interpreted lane by lane on the
+// host so that the CPU test suite can check their logic.  The product library is never built this way;
+// the wrappers below then come from tests/simt/simt_ptx.h (same names, host emulation of mbarrier / bulk copy).
+}  // namespace rfsb200
+#include "simt_ptx.h"
+namespace rfsb200 {
+#else
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
@@ -66,6 +74,22 @@ __device__ __forceinline__ void tma_store_wait_read() {
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 // order generic-proxy shared-memory accesses against the async proxy (TMA)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- system-scope release / acquire and the global timer (fused cross-GPU sum, step_epilogue) -----------
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#endif
 
 // ---- warp helpers -------------------------------------------------------------------------
 template <typename T>

@@ -1048,18 +1048,13 @@ __device__ __forceinline__ void step_epilogue(const KParams<T>& p, int lane, int
         *reinterpret_cast<volatile double*>(&dst->s1) = red[0][0];
         *reinterpret_cast<volatile double*>(&dst->s2) = red[1][0];
         __threadfence_system();
-        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(&dst->epoch), "l"(e) : "memory");
+        st_release_sys_u64(&dst->epoch, e);
         const CommSlot* mine = reinterpret_cast<const CommSlot*>(p.comm_peer[p.comm_rank]) + par * 8;
-        unsigned long long t0;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        const unsigned long long t0 = globaltimer_ns();
         bool ok = true;
         while (true) {
-          unsigned long long got;
-          asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(got) : "l"(&mine[r].epoch) : "memory");
-          if (got == e) break;
-          unsigned long long t1;
-          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-          if (t1 - t0 > 2000000000ull) { ok = false; break; }   // 2 s: a peer never launched
+          if (ld_acquire_sys_u64(&mine[r].epoch) == e) break;
+          if (globaltimer_ns() - t0 > 2000000000ull) { ok = false; break; }   // 2 s: a peer never launched
         }
         if (ok) {
           xs[0][r] = *reinterpret_cast<const volatile double*>(&mine[r].s1);

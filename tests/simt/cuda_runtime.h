@@ -1,0 +1,74 @@
+// cuda_runtime.h — TEST INFRASTRUCTURE ONLY (see simt.h).  The slice of the CUDA runtime API that
+// rfs-slam_b200/csrc/rfsb200_abi.cu uses, on host memory: "device" allocations are malloc'ed, copies are memcpy,
+// streams are in order and synchronous, events carry no time.  Found instead of the real header only by the build of
+// tests/simt/simt_build.py (-I tests/simt); the product build never sees it.
+#pragma once
+#include "simt.h"
+
+enum cudaError_t { cudaSuccess = 0, cudaErrorInvalidValue = 1, cudaErrorMemoryAllocation = 2, cudaErrorNotSupported = 801 };
+enum cudaMemcpyKind { cudaMemcpyHostToHost = 0, cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3, cudaMemcpyDefault = 4 };
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+typedef struct simt_stream_s* cudaStream_t;
+typedef struct simt_event_s* cudaEvent_t;
+struct cudaIpcMemHandle_t { char reserved[64]; };
+struct cudaDeviceProp { int major, minor, multiProcessorCount; char name[64]; };
+constexpr unsigned cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2, cudaIpcMemLazyEnablePeerAccess = 1;
+
+inline const char* cudaGetErrorString(cudaError_t e) {
+  switch (e) {
+    case cudaSuccess: return "no error";
+    case cudaErrorMemoryAllocation: return "out of memory";
+    case cudaErrorNotSupported: return "operation not supported by the host interpreter";
+    default: return "invalid value";
+  }
+}
+inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
+inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
+inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) {
+  memset(p, 0, sizeof(*p));
+  p->major = 10;
+  p->minor = 0;
+  const char* e = getenv("SIMT_SM_COUNT");   // few "SMs": several particles per warp, several CTAs per launch
+  p->multiProcessorCount = e ? atoi(e) : 148;
+  if (p->multiProcessorCount < 1) p->multiProcessorCount = 1;
+  snprintf(p->name, sizeof(p->name), "simt host interpreter");
+  return cudaSuccess;
+}
+template <typename T> inline cudaError_t cudaMalloc(T** p, size_t bytes) {
+  void* q = nullptr;
+  if (posix_memalign(&q, 256, bytes ? bytes : 1)) return cudaErrorMemoryAllocation;
+  memset(q, 0xa5, bytes);   // device memory is not zero-initialised
+  *p = static_cast<T*>(q);
+  return cudaSuccess;
+}
+template <typename T> inline cudaError_t cudaMallocHost(T** p, size_t bytes) { return cudaMalloc(p, bytes); }
+inline cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
+inline cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }
+inline cudaError_t cudaMemset(void* p, int v, size_t n) { memset(p, v, n); return cudaSuccess; }
+inline cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { memset(p, v, n); return cudaSuccess; }
+inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { memmove(d, s, n); return cudaSuccess; }
+inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { memmove(d, s, n); return cudaSuccess; }
+inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = reinterpret_cast<cudaStream_t>(malloc(8)); return cudaSuccess; }
+inline cudaError_t cudaStreamDestroy(cudaStream_t s) { free(s); return cudaSuccess; }
+inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = reinterpret_cast<cudaEvent_t>(malloc(8)); return cudaSuccess; }
+inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { return cudaEventCreate(e); }
+inline cudaError_t cudaEventDestroy(cudaEvent_t e) { free(e); return cudaSuccess; }
+inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
+inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return cudaSuccess; }
+template <typename K> inline cudaError_t cudaFuncSetAttribute(K, cudaFuncAttribute, int) { return cudaSuccess; }
+// shared memory is the only limit modelled: 228 KB per SM, 1 KB reserved per CTA, at most 2048 threads
+template <typename K> inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int* occ, K, int block, size_t smem) {
+  const long by_smem = (228L * 1024) / (long)(smem + 1024);
+  const long by_threads = 2048 / (block > 0 ? block : 1);
+  long o = by_smem < by_threads ? by_smem : by_threads;
+  *occ = (int)(o > 32 ? 32 : o);
+  return cudaSuccess;
+}
+// no peers on the host: the fused cross-GPU sum is not interpreted
+inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void*) { memset(h, 0, sizeof(*h)); return cudaErrorNotSupported; }
+inline cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t, unsigned) { *p = nullptr; return cudaErrorNotSupported; }
+inline cudaError_t cudaIpcCloseMemHandle(void*) { return cudaSuccess; }

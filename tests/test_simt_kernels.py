@@ -1,0 +1,157 @@
+"""The CUDA kernel SOURCES, interpreted on the host (tests/simt/: every thread a fiber, warp / CTA primitives as
+rendezvous points), against the reference's golden vectors and the pinned oracle — so that the CPU suite checks the
+kernel logic itself and not only the oracle and the host code.  This is test infrastructure: the package never loads
+the interpreter build, nothing here is a measurement, and the parity tests proper remain the `-m gpu` ones, which run
+the sm_100a build through the same C ABI.  What the interpreter adds to them: the most adversarial lane interleaving
+(a lane runs alone until its next rendezvous), NaN-filled dynamic shared memory and garbage-filled device memory,
+every warps-per-CTA shape, and randomised sweeps that cost no GPU time.
+"""
+import inspect
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import helpers
+from helpers import TOL32, TOL64
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+import importlib.util  # noqa: E402
+_spec = importlib.util.spec_from_file_location("simt_host", os.path.join(ROOT, "tests", "simt", "host.py"))
+host = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(host)
+
+
+@pytest.fixture(scope="module")
+def simt_lib():
+    return host.load()
+
+
+def _compare(wl, prec, ref, cnt, mean, cov, w, pw):
+    tol = TOL32 if prec == 32 else TOL64
+    r = helpers.compare_maps(cnt, mean, cov, w, ref["count"], ref["mean"], ref["cov"], ref["w"], tol)
+    rw = helpers.compare_weights(pw, ref["weight"], tol)
+    bad = set(r["bad"]) | set(int(i) for i in rw["idx_bad"])
+    if prec == 32 and bad:
+        robust = helpers.robust_mask(wl)
+        bad = {i for i in bad if robust[i]}
+    assert not bad, f"particles differ from the reference: {sorted(bad)[:10]}"
+
+
+def test_interpreter_primitives(tmp_path):
+    """the interpreter itself: shuffles, votes, partial masks, early exits, __syncthreads, atomics, mbarrier"""
+    exe = str(tmp_path / "selftest")
+    simt = os.path.join(ROOT, "tests", "simt")
+    subprocess.run([os.environ.get("CXX", "g++"), "-std=c++17", "-O1", "-I", simt, os.path.join(simt, "selftest.cpp"), "-o", exe],
+                   check=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "selftest OK" in r.stdout
+
+
+@pytest.mark.parametrize("nw", [1, 3, None], ids=["1warp", "3warps", "auto"])
+@pytest.mark.parametrize("prec", [32, 64])
+@pytest.mark.parametrize("case", helpers.GOLDEN_CASES + helpers.GOLDEN_CASES_VP)
+def test_interpreted_kernels_against_reference_golden(simt_lib, case, prec, nw):
+    """golden vectors written by the compiled reference (tests/golden/make_golden.py); CTAs of 1 and 3 warps and of
+    the automatic size (the largest that fits: 16 warps for the fp32 single-cluster kernel), two "SMs": several particles per warp, several CTAs per launch, the last-CTA epilogue"""
+    wl, g = helpers.load_golden(case)
+    ref = helpers.golden_stage(g, 4)
+    with host.interpreted(sm_count=2, warps_per_cta=nw):
+        so, cnt, mean, cov, w, pw, up = helpers.run_device(wl, precision=prec)
+        _compare(wl, prec, ref, cnt, mean, cov, w, pw)
+        mask, nfov = up.get_unused()
+        ok = helpers.robust_mask(wl) if prec == 32 else np.ones(wl.N, bool)
+        assert np.array_equal(mask[ok], ref["unused"][ok]) and np.array_equal(nfov[ok], ref["nfov"][ok])
+        assert so.n_launches >= 1 and so.n_overflow == 0
+        assert so.gm_total_in == int(wl.count.sum()) and so.gm_total_out == int(cnt.sum())
+        up.normalize()
+        wn = up.get_weights()
+        assert wn.sum() == pytest.approx(1.0, abs=1e-12)
+        assert np.allclose(wn, g["s5_weight"], rtol=1e-3 if prec == 32 else 1e-9, atol=1e-300)
+        up.close()
+
+
+@pytest.mark.parametrize("prec", [32, 64])
+@pytest.mark.parametrize("kw", [
+    dict(N=48, nM=200, nZ=30, use_cluster_process=1, config_id=11),
+    dict(N=48, nM=100, nZ=20, use_cluster_process=0, config_id=12),
+    dict(N=48, nM=200, nZ=30, use_cluster_process=1, config_id=13, parity_extras=True),
+    dict(N=48, nM=100, nZ=20, use_cluster_process=0, config_id=14, parity_extras=True, ragged=0.2),
+    dict(N=32, nM=180, nZ=30, use_cluster_process=1, config_id=15, world="sparse"),
+    dict(N=32, nM=120, nZ=24, use_cluster_process=0, config_id=16, world="sparse", ragged=0.3),
+    dict(N=32, nM=100, nZ=20, use_cluster_process=0, config_id=17, model=dict(Pd=0.6, clutter_intensity=5e-3)),
+    dict(N=24, nM=60, nZ=64, use_cluster_process=1, config_id=18),
+    dict(N=16, nM=1, nZ=1, use_cluster_process=0, config_id=19),
+], ids=lambda k: "sc%d_nM%d_nZ%d_id%d" % (k["use_cluster_process"], k["nM"], k["nZ"], k["config_id"]))
+def test_interpreted_kernels_against_oracle(simt_lib, kw, prec):
+    """the workloads of tests/test_gpu_parity.py::test_against_oracle at a fraction of the particles"""
+    from oracle import binding as ob
+    from rfs_slam_b200 import synth
+    wl = synth.make_workload(**kw)
+    o = ob.run(wl, sort_mode=ob.SORT_STABLE)
+    ref = dict(count=o.count, mean=o.mean, cov=o.cov, w=o.w, weight=o.weight)
+    with host.interpreted(sm_count=1, warps_per_cta=4):
+        so, cnt, mean, cov, w, pw, up = helpers.run_device(wl, precision=prec)
+        _compare(wl, prec, ref, cnt, mean, cov, w, pw)
+        if prec == 64:
+            assert np.array_equal(cnt, o.count)
+            assert np.allclose(mean, o.mean, rtol=0, atol=1e-9)
+            mask, nfov = up.get_unused()
+            assert np.array_equal(mask, o.unused_mask) and np.array_equal(nfov, o.n_in_fov)
+        assert so.sum_w == pytest.approx(float(pw.sum()), rel=1e-12)
+        up.close()
+
+
+def _gpu_tests(module_name, skip):
+    mod = __import__(module_name)
+    out = []
+    for name, fn in sorted(vars(mod).items()):
+        if name.startswith("test_") and callable(fn) and list(inspect.signature(fn).parameters) == ["cuda_required"] \
+                and not any(s in name for s in skip):
+            out.append(pytest.param(fn, id=f"{module_name}.{name}"))
+    return out
+
+
+@pytest.mark.parametrize("fn", _gpu_tests("test_gpu_parity", skip=("randomised", "culled_merge")) +
+                         _gpu_tests("test_gpu_vp", skip=("full_size",)))
+def test_gpu_test_bodies_on_the_interpreted_kernels(simt_lib, fn):
+    """the un-parametrised `-m gpu` tests (multi-step sequences, NO_COMMIT / empty Z, pose-covariance modes, capacity
+    overflow, API surface, matrix permanents, large partitions, fused normalisation, update_host, Victoria Park
+    predict / births), bodies unchanged, with the binding pointed at the interpreter build"""
+    with host.interpreted(sm_count=2):
+        fn(simt_lib)
+
+
+@pytest.mark.parametrize("sc", [0, 1])
+def test_interpreted_culled_merge_equals_exhaustive_merge(simt_lib, sc):
+    from rfs_slam_b200 import synth
+    wl = synth.make_workload(N=48, nM=150, nZ=30, use_cluster_process=sc, config_id=21 + sc, parity_extras=True)
+    with host.interpreted(sm_count=2, warps_per_cta=5):
+        a = helpers.run_device(wl, precision=32, brute=False)
+        b = helpers.run_device(wl, precision=32, brute=True)
+        for k in range(1, 6):
+            assert np.array_equal(a[k], b[k])
+        a[6].close(); b[6].close()
+
+
+def test_interpreted_randomised_sweep():
+    """tools/fuzz_parity.py --simt: random sizes / thresholds / models for both plugin sets and random CTA shapes,
+    fp64 kernels against the oracle, exact structure"""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fuzz_parity.py"), "40", "777", "fp64", "--simt"],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+def test_the_package_never_loads_the_interpreter_build():
+    """the product path binds csrc/librfsb200.so only: no reference to tests/simt anywhere in the package or bench.py"""
+    pkg = os.path.join(ROOT, "rfs-slam_b200")
+    files = [os.path.join(pkg, f) for f in os.listdir(pkg) if f.endswith(".py")] + [os.path.join(ROOT, "bench.py")]
+    for f in files:
+        text = open(f).read()
+        assert "simt" not in text.lower(), f
+    import rfs_slam_b200  # noqa: F401
+    from rfs_slam_b200 import capi
+    assert capi.LIB_PATH.endswith(os.path.join("csrc", "librfsb200.so"))

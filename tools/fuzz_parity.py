@@ -1,7 +1,9 @@
 """Randomised parity sweep: fp64 device build against the oracle on many small random workloads of both plugin sets
 (random sizes, thresholds, detection / clutter levels, world types, ragged maps).  Any structural or numerical
-difference beyond the fp64 tolerances is printed with its seed.  usage: fuzz_parity.py [n_cases] [seed]"""
-import os, sys
+difference beyond the fp64 tolerances is printed with its seed.  usage: fuzz_parity.py [n_cases] [seed] [fp64|fp32] [--simt]
+--simt: the kernel sources interpreted on the host (tests/simt, test infrastructure) instead of the GPU build, with a
+random CTA shape per case — a sweep that costs no GPU time."""
+import contextlib, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
@@ -10,6 +12,13 @@ from rfs_slam_b200 import synth
 from oracle import binding as ob
 import helpers
 
+SIMT = "--simt" in sys.argv
+if SIMT:
+    sys.argv.remove("--simt")
+    import importlib.util
+    _spec = importlib.util.spec_from_file_location("simt_host", os.path.join(ROOT, "tests", "simt", "host.py"))
+    simt_host = importlib.util.module_from_spec(_spec)
+    _spec.loader.exec_module(simt_host)
 n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 60
 rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 2026)
 PREC = 32 if (len(sys.argv) > 3 and sys.argv[3] == "fp32") else 64   # fp32: SURVEY tolerances, epsilon-band particles excluded
@@ -38,9 +47,12 @@ for case in range(n_cases):
         wl = synth.make_workload(world=str(rng.choice(["dense", "sparse", "clumped"])), model=model, **kw)
     o = ob.run(wl, sort_mode=ob.SORT_STABLE)
     cap = int(max(64, (int(wl.count.max()) + int(nZ) * 8 + 63) // 8 * 8))
-    so, cnt, mean, cov, w, pw, up = helpers.run_device(wl, precision=PREC, gm_capacity=min(cap, 512), work_capacity=min(1024, 2 * cap))
-    flags = up.get_flags()
-    mask, nfov = up.get_unused()
+    shape = dict(sm_count=int(rng.integers(1, 4)), warps_per_cta=[1, None][int(rng.integers(0, 2))]) if SIMT else {}   # None: the automatic choice (largest CTA that fits)
+    with (simt_host.interpreted(**shape) if SIMT else contextlib.nullcontext()):
+        so, cnt, mean, cov, w, pw, up = helpers.run_device(wl, precision=PREC, gm_capacity=min(cap, 512), work_capacity=min(1024, 2 * cap))
+        flags = up.get_flags()
+        mask, nfov = up.get_unused()
+        up.close()
     tol = helpers.TOL64 if PREC == 64 else helpers.TOL32
     r = helpers.compare_maps(cnt, mean, cov, w, o.count, o.mean, o.cov, o.w, tol)
     # particles where the reference took the truncated Murty-200 branch are allowed to differ in weight (documented)
@@ -59,7 +71,6 @@ for case in range(n_cases):
         bad += 1
         print(f"CASE {case} FAILED: maps {r['bad'][:5]} weights {list(rw['idx_bad'][:5])} overflow {so.n_overflow} murty {int(murty.sum())} "
               f"flags {sorted(set(flags.tolist()))} unused_eq {np.array_equal(mask, o.unused_mask)} nfov_eq {np.array_equal(nfov, o.n_in_fov)} "
-              f"max dlog {rw['max_dlog']:.3e} vp={vp} kw={kw} model={model}")
-    up.close()
+              f"max dlog {rw['max_dlog']:.3e} vp={vp} kw={kw} model={model} shape={shape}")
 print(f"{n_cases} random workloads, {bad} with differences" + (f" ({n_excluded} of {n_particles} particles inside an epsilon band of a threshold)" if PREC == 32 else ""))
 sys.exit(1 if bad else 0)
