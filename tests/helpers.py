@@ -144,6 +144,15 @@ def robust_mask(wl, eps=1e-3):
         ok &= (a.count == b.count) & (a.count == c.count)
         ok &= (a.unused_mask == b.unused_mask) & (a.unused_mask == c.unused_mask)
         ok &= (a.n_in_fov == b.n_in_fov) & (a.n_in_fov == c.n_in_fov)
+    # a merge decision can flip without changing the count (a small component joins another cluster): the merged
+    # weights of the final mixture move then, while moving a threshold alone leaves them untouched
+    a, off = base[2], offsets(base[2].count)
+    for o in (up[2], dn[2]):
+        off_o = offsets(o.count)
+        for i in np.nonzero(ok)[0]:
+            wa, wo = a.w[off[i]:off[i + 1]], o.w[off_o[i]:off_o[i + 1]]
+            if not np.allclose(wa, wo, rtol=1e-9, atol=1e-12):
+                ok[i] = False
     return ok
 
 

@@ -145,6 +145,28 @@ def test_interpreted_randomised_sweep():
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
 
 
+def test_unchanged_simulator_on_the_dropin_header_with_interpreted_kernels(simt_lib, tmp_path, monkeypatch):
+    """BASELINE config C1 end to end on the CPU: the body of tests/test_gpu_sim_c1.py (the reference's
+    src/rbphdslam2dSim.cpp UNCHANGED, once on the reference's filter header and once on the drop-in header over the
+    C ABI, 50 particles, 600 steps; identical particle poses, weights and best-particle maps with the fp64 kernels, same
+    final error with the fp32 kernels) with the ABI symbols of the drop-in binary bound to the interpreter build."""
+    import test_gpu_sim_c1 as c1
+    monkeypatch.setenv("LD_PRELOAD", simt_lib._name)
+    monkeypatch.setenv("SIMT_SM_COUNT", "2")
+    c1.test_unchanged_simulator_runs_on_the_dropin(simt_lib, tmp_path)
+
+
+def test_unchanged_victoria_park_driver_on_the_dropin_header_with_interpreted_kernels(simt_lib, tmp_path, monkeypatch):
+    """BASELINE config C5 end to end on the CPU: the body of tests/test_gpu_sim_c5.py (the reference's
+    src/rbphdslam_VictoriaPark.cpp UNCHANGED on both headers, head of the Victoria Park dataset, 100 particles:
+    identical poses / weights / best-particle maps for the first 60 updates with the fp64 kernels, the same
+    trajectory estimate afterwards and with the fp32 kernels)."""
+    import test_gpu_sim_c5 as c5
+    monkeypatch.setenv("LD_PRELOAD", simt_lib._name)
+    monkeypatch.setenv("SIMT_SM_COUNT", "2")
+    c5.test_unchanged_victoria_park_driver_runs_on_the_dropin(simt_lib, tmp_path)
+
+
 def test_the_package_never_loads_the_interpreter_build():
     """the product path binds csrc/librfsb200.so only: no reference to tests/simt anywhere in the package or bench.py"""
     pkg = os.path.join(ROOT, "rfs-slam_b200")
