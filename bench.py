@@ -326,9 +326,11 @@ def main():
         d2h = N * 8 + N * 8 + N * 4
         e2e = dict(value=units_total * Ke / te_max, unit=UNIT, h2d_bytes_per_step=h2d * world, d2h_bytes_per_step=d2h * world,
                    ms_per_step=1e3 * te_max / Ke, wall_ms_per_step_incl_flush=1e3 * tw / Ke,
-                   what=("per step: rfsb200_update_host = pinned host poses + particle weights + Z in, update (+ cross-GPU sum + "
-                         "normalisation), normalised weights + unused-measurement masks + in-FOV counts out into pinned host "
-                         "buffers, one synchronisation; maps stay resident in HBM" if fused else
+                   what=("per step: rfsb200_update_host = pinned host poses + particle weights + Z in (read over PCIe by one "
+                         "conversion kernel), update (+ cross-GPU sum + normalisation), normalised weights + unused-measurement "
+                         "masks + in-FOV counts out (stored by the update kernel straight into the pinned host buffers), one "
+                         "synchronisation; maps stay resident in HBM; RFSB200_ZERO_COPY=0 stages the same bytes through copies"
+                         if fused else
                          "per step: rfsb200_set_poses(pinned host poses+weights) + rfsb200_update(host Z) + NCCL all-reduce + "
                          "rfsb200_normalize + rfsb200_get_weights + rfsb200_get_unused into pinned host buffers; maps stay resident"))
 

@@ -201,8 +201,12 @@ int rfsb200_update(rfsb200_ctx* ctx, const double* Z /*[nZ][meas_dim]*/, int32_t
  * call with ONE synchronisation: the copies in, the kernels and the copies out are queued back to back on the
  * ctx stream.  This is what RBPHDFilter::update() moves per step when the maps stay resident: poses / pose
  * covariances / particle weights / Z in, particle weights (normalised unless NO_NORMALIZE), the
- * unused-measurement masks and nLandmarksInFOV_ out.  Host buffers should be page-locked
- * (rfsb200_host_alloc) so that the copies are asynchronous; w_out / unused_out / n_in_fov_out / out may be NULL. */
+ * unused-measurement masks and nLandmarksInFOV_ out.  w_out / unused_out / n_in_fov_out / out may be NULL.
+ * Page-locked buffers (rfsb200_host_alloc, cudaMallocHost, cudaHostRegister): nothing is copied at all — one
+ * conversion kernel reads pose / pose_cov / weight from the caller's memory over PCIe (Z travels as a kernel
+ * argument) and the update kernel stores the results straight into w_out / unused_out / n_in_fov_out, two launches
+ * and one synchronisation per step.  If ANY of the large buffers is pageable (or RFSB200_ZERO_COPY=0 is set when the
+ * ctx is created) the same bytes are staged through copies; the results are bit-identical either way. */
 int rfsb200_update_host(rfsb200_ctx* ctx, const double* pose /*[N][3]*/, const double* pose_cov, int pose_cov_mode,
                         const double* weight /*[N] or NULL = keep*/, const double* Z, int32_t nZ, uint32_t flags,
                         double* w_out /*[N]*/, uint64_t* unused_out /*[N]*/, int32_t* n_in_fov_out /*[N]*/,

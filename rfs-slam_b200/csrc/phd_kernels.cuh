@@ -79,6 +79,13 @@ struct KParams {
   void* comm_peer[8];               // mailbox of every rank (own included), mapped into this process
   int* comm_error;                  // set to 1 if a peer did not arrive in time
   unsigned long long* stats_out;  // [13] totals/istats/mstats of the finished step, published by the last CTA
+  // host-facing step (rfsb200_update_host with pinned, device-accessible caller buffers): the results are ALSO stored
+  // straight into the caller's host memory (posted writes over PCIe), so no device-to-host copy follows the kernel.
+  // NULL = not used.
+  double* w_host;                   // [N] particle weights as the launch leaves them (normalised on the fused path)
+  unsigned long long* unused_host;  // [N]
+  int* nfov_host;                   // [N]
+  unsigned long long* stats_host;   // [15] sums[2] (as bits) followed by stats_out[13]
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -968,6 +975,16 @@ __device__ __forceinline__ double mf_partition_loglik(const T* L, const T* evalP
   return logL;
 }
 
+// per-particle results into the caller's host buffers (see KParams::w_host); the weight only where no
+// normalisation follows in this launch (the fused path stores the normalised weights in the epilogue)
+template <typename T>
+__device__ __forceinline__ void store_host_results(const KParams<T>& p, int pi, double weight, unsigned long long unused_mask,
+                                                   int nfov) {
+  if (p.unused_host) p.unused_host[pi] = unused_mask;
+  if (p.nfov_host) p.nfov_host[pi] = nfov;
+  if (p.w_host && !p.fused_normalize) p.w_host[pi] = weight;
+}
+
 // ------------------------------------------------------------------------------------------------
 // End of a step, shared by the 2-D and the Victoria Park kernels: per-warp statistics, then S8 —
 // deterministic [sum w, sum w^2] by the last CTA (+ the fused cross-GPU sum and normalisation).
@@ -1085,6 +1102,11 @@ __device__ __forceinline__ void step_epilogue(const KParams<T>& p, int lane, int
       p.stats_out[4] = (unsigned long long)(unsigned)__ldcg(&p.istats[2]);
       p.stats_out[5] = (unsigned long long)(unsigned)__ldcg(&p.istats[3]);
       for (int k = 0; k < 7; k++) { p.stats_out[6 + k] = (unsigned long long)__ldcg(&p.mstats[k]); p.mstats[k] = 0u; }
+      if (p.stats_host) {
+        p.stats_host[0] = (unsigned long long)__double_as_longlong(a);
+        p.stats_host[1] = (unsigned long long)__double_as_longlong(b);
+        for (int k = 0; k < 13; k++) p.stats_host[2 + k] = p.stats_out[k];
+      }
       p.totals[0] = 0; p.totals[1] = 0;
       p.istats[0] = 0; p.istats[1] = 0; p.istats[2] = 0; p.istats[3] = 0;
       *p.ticket = 0;
@@ -1096,11 +1118,16 @@ __device__ __forceinline__ void step_epilogue(const KParams<T>& p, int lane, int
       const int nt = blockDim.x;
       int i = threadIdx.x;
       for (; i + 3 * nt < p.N; i += 4 * nt) {
-        const double w0 = __ldcg(p.w_out + i), w1 = __ldcg(p.w_out + i + nt), w2 = __ldcg(p.w_out + i + 2 * nt),
-                     w3 = __ldcg(p.w_out + i + 3 * nt);
-        p.w_out[i] = w0 / total; p.w_out[i + nt] = w1 / total; p.w_out[i + 2 * nt] = w2 / total; p.w_out[i + 3 * nt] = w3 / total;
+        const double w0 = __ldcg(p.w_out + i) / total, w1 = __ldcg(p.w_out + i + nt) / total,
+                     w2 = __ldcg(p.w_out + i + 2 * nt) / total, w3 = __ldcg(p.w_out + i + 3 * nt) / total;
+        p.w_out[i] = w0; p.w_out[i + nt] = w1; p.w_out[i + 2 * nt] = w2; p.w_out[i + 3 * nt] = w3;
+        if (p.w_host) { p.w_host[i] = w0; p.w_host[i + nt] = w1; p.w_host[i + 2 * nt] = w2; p.w_host[i + 3 * nt] = w3; }
       }
-      for (; i < p.N; i += nt) p.w_out[i] = __ldcg(p.w_out + i) / total;
+      for (; i < p.N; i += nt) {
+        const double w = __ldcg(p.w_out + i) / total;
+        p.w_out[i] = w;
+        if (p.w_host) p.w_host[i] = w;
+      }
     }
   }
 }
@@ -1842,6 +1869,7 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
       p.unused[pi] = unused_mask;
       p.nfov[pi] = nfov;
       p.flags[pi] = flags;
+      store_host_results(p, pi, weight_new, unused_mask, nfov);
     }
     tot_in += (unsigned long long)nM;
     tot_out += (unsigned long long)n_out;
@@ -2043,9 +2071,45 @@ __global__ void propagate_kernel(double* __restrict__ pose64, T* __restrict__ po
 }
 
 // w_i /= sum  (ParticleFilter::normalizeWeights, include/ParticleFilter.hpp:352-363)
-__global__ void normalize_kernel(double* w, const double* sums, int N) {
+__global__ void normalize_kernel(double* w, const double* sums, int N, double* w_host) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < N) w[i] = w[i] / sums[0];
+  if (i < N) {
+    const double v = w[i] / sums[0];
+    w[i] = v;
+    if (w_host) w_host[i] = v;   // the caller's pinned buffer (KParams::w_host)
+  }
+}
+
+// Inputs of a host-facing step read straight from the caller's pinned host memory (zero-copy loads over PCIe) and
+// converted to the device layout: poses (fp64 copy kept for export / propagate), pose covariance, particle weights and
+// the measurement batch (passed by value) — one launch instead of four copies and a conversion kernel.
+struct HostInParams {
+  const double* pose;     // host [N][3]
+  const double* weight;   // host [N] or NULL
+  const double* pcov;     // host [N][6] (mode 2) or NULL
+  int mode, N, nz_vals;
+  double cov6[6];         // mode 1
+  double Z[MAX_Z * 3];
+};
+template <typename T>
+__global__ void host_in_kernel(const HostInParams h, double* __restrict__ pose64, T* __restrict__ pose, T* __restrict__ pcov,
+                               double* __restrict__ w_dev, T* __restrict__ Zdev) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < h.N) {
+    const double x = h.pose[3 * i], y = h.pose[3 * i + 1], th = h.pose[3 * i + 2];
+    pose64[3 * i] = x; pose64[3 * i + 1] = y; pose64[3 * i + 2] = th;
+    pose[4 * i] = (T)x; pose[4 * i + 1] = (T)y; pose[4 * i + 2] = (T)th; pose[4 * i + 3] = T(0);
+    if (h.mode == 2) {
+      for (int k = 0; k < 6; k++) pcov[8 * i + k] = (T)h.pcov[6 * i + k];
+      pcov[8 * i + 6] = pcov[8 * i + 7] = T(0);
+    }
+    if (h.weight) w_dev[i] = h.weight[i];
+  }
+  if (h.mode == 1 && i == 0) {
+    for (int k = 0; k < 6; k++) pcov[k] = (T)h.cov6[k];
+    pcov[6] = pcov[7] = T(0);
+  }
+  if (i < h.nz_vals) Zdev[i] = (T)h.Z[i];
 }
 
 }  // namespace rfsb200

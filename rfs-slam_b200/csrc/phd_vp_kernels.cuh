@@ -828,6 +828,7 @@ phd_update_vp_kernel(const __grid_constant__ VPParams<T> vp) {
       p.unused[pi] = unused_mask;
       p.nfov[pi] = nfov;
       p.flags[pi] = flags;
+      store_host_results(p, pi, weight_new, unused_mask, nfov);
     }
     tot_in += (unsigned long long)nM;
     tot_out += (unsigned long long)n_out;

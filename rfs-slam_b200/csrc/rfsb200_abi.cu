@@ -88,6 +88,11 @@ struct rfsb200_ctx {
   rfsb200_model_desc model{};
   rfsb200_filter_cfg cfg{};
   int merge_algo = 1;
+  bool zero_copy = true;                     // rfsb200_update_host: pinned caller buffers are read / written by the kernels directly
+  double* w_host = nullptr;                  // device views of the caller's result buffers for the NEXT launch (or NULL)
+  unsigned long long* unused_host = nullptr;
+  int* nfov_host = nullptr;
+  unsigned long long* stats_host = nullptr;
   std::vector<cudaEvent_t> prof_ev;   // event pairs around the update kernel (rfsb200_profile_*)
   int prof_cap = 0, prof_n = 0;
   int grid = 0;
@@ -413,6 +418,11 @@ int launch_update(rfsb200_ctx* c, int nZ, int out_idx, unsigned flags) {
   p.sums = c->sums; p.totals = c->totals; p.istats = c->istats; p.ticket = c->ticket; p.mstats = c->mstats;
   p.work_counter = c->work_counter; p.stats_out = c->stats_out;
   p.comm_rank = c->comm_rank; p.comm_world = 1; p.fused_normalize = 0; p.comm_epoch = 0; p.comm_error = c->comm_error;
+  p.unused_host = c->unused_host; p.nfov_host = c->nfov_host; p.stats_host = c->stats_host;
+  // the weights go to the host from whichever launch leaves them final: this kernel (fused normalisation, or none at
+  // all), else normalize_kernel
+  const bool normalize_follows = !(flags & (RFSB200_UPDATE_NO_NORMALIZE | RFSB200_UPDATE_FUSED_ALLREDUCE));
+  p.w_host = normalize_follows ? nullptr : c->w_host;
   if (flags & RFSB200_UPDATE_FUSED_ALLREDUCE) {
     p.comm_world = c->comm_world;
     p.fused_normalize = 1;
@@ -449,6 +459,16 @@ int launch_update(rfsb200_ctx* c, int nZ, int out_idx, unsigned flags) {
     c->prof_n++;
   }
   return RFSB200_OK;
+}
+
+// device-accessible alias of a pinned / registered host pointer (unified addressing), or NULL for pageable memory
+template <typename P>
+P* device_view(P* host_ptr) {
+  if (!host_ptr) return nullptr;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, (const void*)host_ptr) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  if (a.type != cudaMemoryTypeHost || !a.devicePointer) return nullptr;
+  return (P*)a.devicePointer;
 }
 
 int ensure_pinned(rfsb200_ctx* c, size_t bytes) {
@@ -610,6 +630,7 @@ int rfsb200_create(rfsb200_ctx** out, const rfsb200_dims* d) {
     CU(c, cudaMemset(c->scan_dev, 0, VP_SCAN_MAX * 8));
     CU(c, cudaMalloc((void**)&c->offs, (size_t)(c->N + 1) * 8));
     CU(c, cudaMalloc((void**)&c->stg_small, (size_t)c->N * 16 * 8));
+    if (const char* e = getenv("RFSB200_ZERO_COPY")) c->zero_copy = atoi(e) != 0;   // 0: always stage through copies
     int r = ensure_pinned(c, 1 << 16);
     if (r) return r;
     if (c->prec == 32) r = configure_launch<float>(c, 0);
@@ -787,7 +808,8 @@ int rfsb200_set_poses(rfsb200_ctx* c, const double* pose, const double* pose_cov
 }
 
 // queue one update on the ctx stream (Z copy + kernels); no synchronisation
-static int enqueue_update(rfsb200_ctx* c, const double* Z, int32_t nZ, uint32_t flags, bool timed, int* launches_out) {
+static int enqueue_update(rfsb200_ctx* c, const double* Z, int32_t nZ, uint32_t flags, bool timed, int* launches_out,
+                          bool z_resident = false) {
   if (!c->have_model || !c->have_cfg || !c->have_maps || !c->have_poses)
     return fail(c, RFSB200_ESTATE, "update before set_model / set_filter_cfg / upload_maps / set_poses");
   if (nZ < 0 || nZ > c->dims.z_capacity) return fail(c, RFSB200_ECAPACITY, "nZ %d > z_capacity %d", nZ, c->dims.z_capacity);
@@ -795,7 +817,7 @@ static int enqueue_update(rfsb200_ctx* c, const double* Z, int32_t nZ, uint32_t 
   // Z -> T in a pinned staging slot -> device
   unsigned char* zsrc = nullptr;
   unsigned zslot_used = 0;
-  {
+  if (!z_resident) {   // (a host-facing step has already put the batch into Zdev: host_in_kernel)
     const unsigned slot = (c->zslot++) & 7u;
     CU(c, cudaEventSynchronize(c->zev[slot]));   // the copy that last read this slot has finished
     unsigned char* hb = c->hpin + 16384 + (size_t)slot * 4096;
@@ -816,8 +838,10 @@ static int enqueue_update(rfsb200_ctx* c, const double* Z, int32_t nZ, uint32_t 
     if (rc0) return rc0;
   }
   if (timed) CU(c, cudaEventRecord(c->ev0, c->stream));
-  CU(c, cudaMemcpyAsync(c->Zdev, zsrc, (size_t)c->ld * nZ * c->tsize, cudaMemcpyHostToDevice, c->stream));
-  CU(c, cudaEventRecord(c->zev[zslot_used], c->stream));
+  if (!z_resident) {
+    CU(c, cudaMemcpyAsync(c->Zdev, zsrc, (size_t)c->ld * nZ * c->tsize, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaEventRecord(c->zev[zslot_used], c->stream));
+  }
   const int out_idx = c->front ^ 1;
   if ((flags & RFSB200_UPDATE_FUSED_ALLREDUCE) && c->comm_world > 1 && !c->comm_peer[0])
     return fail(c, RFSB200_ESTATE, "RFSB200_UPDATE_FUSED_ALLREDUCE before rfsb200_comm_connect");
@@ -827,7 +851,7 @@ static int enqueue_update(rfsb200_ctx* c, const double* Z, int32_t nZ, uint32_t 
   c->last_out = out_idx;
   c->last_nZ = nZ;
   if (!(flags & (RFSB200_UPDATE_NO_NORMALIZE | RFSB200_UPDATE_FUSED_ALLREDUCE))) {
-    normalize_kernel<<<(c->N + 255) / 256, 256, 0, c->stream>>>(c->st[out_idx].weight, c->sums, c->N);
+    normalize_kernel<<<(c->N + 255) / 256, 256, 0, c->stream>>>(c->st[out_idx].weight, c->sums, c->N, c->w_host);
     CU(c, cudaGetLastError());
     launches++;
   }
@@ -891,6 +915,51 @@ int rfsb200_update_host(rfsb200_ctx* c, const double* pose, const double* pose_c
                         int32_t* nfov_out, rfsb200_step_out* out) {
   if (!c || !pose) return fail(c, RFSB200_EINVAL, "NULL argument");
   if (out) memset(out, 0, sizeof(*out));
+  if (c->zero_copy && nZ > 0 && nZ <= c->dims.z_capacity && Z && mode >= 0 && mode <= 2 && (mode == 0 || pose_cov)) {
+    // Pinned (device-accessible) caller buffers: ONE small kernel reads poses / weights / covariance / Z from host
+    // memory, and the update kernel (or normalize_kernel) stores weights, unused masks, in-FOV counts and the step
+    // scalars straight into the caller's buffers: no copies on either side of the update, one synchronisation.
+    // Any pageable buffer (or RFSB200_ZERO_COPY=0) takes the staged path below.
+    CU(c, cudaSetDevice(c->device));
+    const double* d_pose = device_view(pose);
+    const double* d_w = device_view(weight);
+    const double* d_cov = mode == 2 ? device_view(pose_cov) : nullptr;
+    double* d_wout = device_view(w_out);
+    unsigned long long* d_unused = device_view((unsigned long long*)unused_out);
+    int* d_nfov = device_view((int*)nfov_out);
+    const bool ok = d_pose && (!weight || d_w) && (mode != 2 || d_cov) && (!w_out || d_wout) && (!unused_out || d_unused) &&
+                    (!nfov_out || d_nfov);
+    if (ok) {
+      int rc = ensure_pinned(c, 1 << 16);
+      if (rc) return rc;
+      HostInParams h{};
+      h.pose = d_pose; h.weight = d_w; h.pcov = d_cov; h.mode = mode; h.N = c->N; h.nz_vals = c->ld * nZ;
+      if (mode == 1) for (int k = 0; k < 6; k++) h.cov6[k] = pose_cov[k];
+      for (int k = 0; k < c->ld * nZ; k++) h.Z[k] = Z[k];
+      const int n_thr = std::max(c->N, c->ld * nZ);
+      double* w_dev = c->st[c->front].weight;
+      if (c->prec == 32) host_in_kernel<float><<<(n_thr + 255) / 256, 256, 0, c->stream>>>(h, c->stg_small, (float*)c->pose, (float*)c->pose_cov, w_dev, (float*)c->Zdev);
+      else host_in_kernel<double><<<(n_thr + 255) / 256, 256, 0, c->stream>>>(h, c->stg_small, (double*)c->pose, (double*)c->pose_cov, w_dev, (double*)c->Zdev);
+      CU(c, cudaGetLastError());
+      c->pose_cov_mode = mode;
+      c->have_poses = true;
+      unsigned long long* stats_h = (unsigned long long*)(c->hpin + 8192);   // where fill_stats reads the step scalars
+      c->w_host = d_wout; c->unused_host = d_unused; c->nfov_host = d_nfov;
+      c->stats_host = out ? device_view(stats_h) : nullptr;
+      const bool stats_direct = out && c->stats_host;
+      int l = 0;
+      rc = enqueue_update(c, Z, nZ, flags, out != nullptr, &l, /*z_resident=*/true);
+      c->w_host = nullptr; c->unused_host = nullptr; c->nfov_host = nullptr; c->stats_host = nullptr;
+      if (rc) return rc;
+      if (out && !stats_direct) {
+        rc = enqueue_stats(c);
+        if (rc) return rc;
+      }
+      CU(c, cudaStreamSynchronize(c->stream));
+      if (out) return fill_stats(c, 1 + l, out);
+      return RFSB200_OK;
+    }
+  }
   int rc = rfsb200_set_poses(c, pose, pose_cov, mode, weight);   // queued, no synchronisation
   if (rc) return rc;
   int launches = 1;   // pose_convert_kernel
@@ -1149,7 +1218,7 @@ int rfsb200_weight_sums_device(rfsb200_ctx* c, void** p) {
 int rfsb200_normalize(rfsb200_ctx* c) {
   if (!c) return fail(nullptr, RFSB200_EINVAL, "NULL ctx");
   CU(c, cudaSetDevice(c->device));
-  normalize_kernel<<<(c->N + 255) / 256, 256, 0, c->stream>>>(c->st[c->last_out].weight, c->sums, c->N);
+  normalize_kernel<<<(c->N + 255) / 256, 256, 0, c->stream>>>(c->st[c->last_out].weight, c->sums, c->N, nullptr);
   CU(c, cudaGetLastError());
   return RFSB200_OK;
 }

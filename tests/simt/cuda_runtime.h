@@ -68,6 +68,18 @@ template <typename K> inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultipro
   *occ = (int)(o > 32 ? 32 : o);
   return cudaSuccess;
 }
+// every pointer is "pinned host memory" here (SIMT_PAGEABLE=1: none is, the staged path of rfsb200_update_host runs)
+enum cudaMemoryType { cudaMemoryTypeUnregistered = 0, cudaMemoryTypeHost = 1, cudaMemoryTypeDevice = 2, cudaMemoryTypeManaged = 3 };
+struct cudaPointerAttributes { cudaMemoryType type; int device; void* devicePointer; void* hostPointer; };
+inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes* a, const void* p) {
+  const char* e = getenv("SIMT_PAGEABLE");
+  const bool pageable = e && atoi(e) != 0;
+  a->type = pageable ? cudaMemoryTypeUnregistered : cudaMemoryTypeHost;
+  a->device = 0;
+  a->devicePointer = pageable ? nullptr : const_cast<void*>(p);
+  a->hostPointer = const_cast<void*>(p);
+  return cudaSuccess;
+}
 // no peers on the host: the fused cross-GPU sum is not interpreted
 inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void*) { memset(h, 0, sizeof(*h)); return cudaErrorNotSupported; }
 inline cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t, unsigned) { *p = nullptr; return cudaErrorNotSupported; }

@@ -294,6 +294,68 @@ def test_update_host_equals_the_separate_calls(cuda_required):
     a.close(); b.close()
 
 
+def test_update_host_zero_copy_equals_the_staged_path(cuda_required):
+    """rfsb200_update_host with pinned caller buffers (inputs read and results written by the kernels directly, no
+    copies) against the same call staged through copies (RFSB200_ZERO_COPY=0; also what pageable buffers get): same
+    bits in every output, for every normalisation mode, pose-covariance mode, precision and both plugin sets."""
+    from rfs_slam_b200 import capi, synth
+    import os
+    from rfs_slam_b200.phd import PHDUpdater, pinned_array
+    saved = os.environ.get("RFSB200_ZERO_COPY")
+    try:
+        _zero_copy_cases(capi, synth, PHDUpdater, pinned_array)
+    finally:
+        if saved is None:
+            os.environ.pop("RFSB200_ZERO_COPY", None)
+        else:
+            os.environ["RFSB200_ZERO_COPY"] = saved
+
+
+def _zero_copy_cases(capi, synth, PHDUpdater, pinned_array):
+    import os
+    for dim, sc, prec, mode, flags in [(2, 1, 32, 1, capi.UPDATE_DEFAULT), (2, 0, 32, 2, capi.UPDATE_FUSED_ALLREDUCE),
+                                       (2, 1, 64, 0, capi.UPDATE_NO_NORMALIZE), (3, 0, 32, 0, capi.UPDATE_FUSED_ALLREDUCE),
+                                       (3, 1, 64, 0, capi.UPDATE_DEFAULT), (2, 1, 32, 1, capi.UPDATE_NO_COMMIT)]:
+        mk = synth.make_vp_workload if dim == 3 else synth.make_workload
+        wl = mk(N=96, nM=60, nZ=14, use_cluster_process=sc, config_id=70 + dim + 2 * sc)
+        pcov = None
+        if dim == 2:
+            pcov = [None, wl.pose_cov, None][mode] if mode < 2 else None
+        res = []
+        for zero_copy in (1, 0):
+            os.environ["RFSB200_ZERO_COPY"] = str(zero_copy)   # read by rfsb200_create
+            up = PHDUpdater(wl.N, gm_capacity=128, z_capacity=16, precision=prec, lmk_dim=dim)
+            up.set_model(wl.model); up.set_filter_cfg(wl.cfg); up.upload_maps(wl.count, wl.mean, wl.cov, wl.w)
+            pose = pinned_array((wl.N, 3)); pose[:] = wl.pose
+            w_in = pinned_array((wl.N,)); w_in[:] = wl.weight * np.linspace(0.5, 2.0, wl.N)
+            cov = pcov
+            if mode == 2:   # one covariance per particle
+                cov = pinned_array((wl.N, 6)); cov[:] = np.asarray(wl.pose_cov).reshape(1, 6) * np.linspace(0.5, 1.5, wl.N)[:, None]
+            w_out = pinned_array((wl.N,)); mask = pinned_array((wl.N,), np.uint64); nfov = pinned_array((wl.N,), np.int32)
+            w_out[:] = -1; mask[:] = 12345; nfov[:] = -1
+            so = up.update_host(pose, cov, w_in, np.ascontiguousarray(wl.Z), flags=flags, w_out=w_out, unused_out=mask,
+                                nfov_out=nfov, want_stats=True)
+            which = 1 if (flags & capi.UPDATE_NO_COMMIT) else 0
+            res.append((w_out.copy(), mask.copy(), nfov.copy(), up.get_weights(which), up.download_maps(which), up.get_poses(),
+                        (so.sum_w, so.sum_w2, so.gm_total_in, so.gm_total_out, so.gm_max_out, so.n_overflow, so.n_murty, so.n_launches)))
+            # a second step on the same context, without statistics and without the optional outputs
+            up.update_host(pose, cov, None, np.ascontiguousarray(wl.Z), flags=flags, w_out=w_out)
+            res[-1] += (w_out.copy(), up.get_weights(which))
+            up.close()
+        a, b = res
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+        assert np.array_equal(a[0], a[3]) and np.array_equal(a[3], b[3])          # host copy == device state
+        for x, y in zip(a[4], b[4]):
+            assert np.array_equal(x, y)
+        assert np.array_equal(a[5], b[5]) and np.array_equal(a[5], wl.pose)
+        assert a[6] == b[6] and a[6][2] == int(wl.count.sum())
+        assert np.array_equal(a[7], b[7]) and np.array_equal(a[8], b[8]) and np.array_equal(a[7], a[8])
+        if flags & capi.UPDATE_NO_NORMALIZE:
+            assert a[6][0] == pytest.approx(float(a[0].sum()), rel=1e-12)
+        elif not (flags & capi.UPDATE_NO_COMMIT):
+            assert a[0].sum() == pytest.approx(1.0, abs=1e-12)
+
+
 def test_randomised_sweep_fp64(cuda_required):
     """tools/fuzz_parity.py: random sizes / thresholds / detection and clutter levels / world types for both plugin sets,
     fp64 device build against the oracle, exact structure (this sweep found the 1-warp-CTA table bug and the
