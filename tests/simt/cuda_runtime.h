@@ -36,16 +36,46 @@ inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) {
   snprintf(p->name, sizeof(p->name), "simt host interpreter");
   return cudaSuccess;
 }
-template <typename T> inline cudaError_t cudaMalloc(T** p, size_t bytes) {
+// Allocations carry a 256-byte canary on either side, checked when they are freed: a kernel that writes outside its
+// buffers aborts the test instead of corrupting the heap quietly.  Contents start as garbage (0xa5), not zeros.
+namespace simt {
+constexpr size_t GUARD = 256;
+inline void* guarded_alloc(size_t bytes) {
   void* q = nullptr;
-  if (posix_memalign(&q, 256, bytes ? bytes : 1)) return cudaErrorMemoryAllocation;
-  memset(q, 0xa5, bytes);   // device memory is not zero-initialised
+  const size_t body = (bytes + 255) & ~size_t(255);
+  if (posix_memalign(&q, 256, GUARD + body + GUARD)) return nullptr;
+  unsigned char* b = static_cast<unsigned char*>(q);
+  memset(b, 0xc7, GUARD);
+  memset(b + GUARD, 0xa5, body);
+  memset(b + GUARD + bytes, 0xc7, body - bytes + GUARD);
+  memcpy(b, &bytes, sizeof(bytes));   // the size lives in the first bytes of the front guard
+  return b + GUARD;
+}
+inline void guarded_free(void* p) {
+  if (!p) return;
+  unsigned char* b = static_cast<unsigned char*>(p) - GUARD;
+  size_t bytes;
+  memcpy(&bytes, b, sizeof(bytes));
+  const size_t body = (bytes + 255) & ~size_t(255);
+  bool ok = true;
+  for (size_t k = sizeof(bytes); k < GUARD; k++) ok = ok && b[k] == 0xc7;
+  for (size_t k = GUARD + bytes; k < GUARD + body + GUARD; k++) ok = ok && b[k] == 0xc7;
+  if (!ok) {
+    fprintf(stderr, "simt: a kernel or copy wrote outside a %zu-byte allocation (guard bytes damaged)\n", bytes);
+    abort();
+  }
+  free(b);
+}
+}  // namespace simt
+template <typename T> inline cudaError_t cudaMalloc(T** p, size_t bytes) {
+  void* q = simt::guarded_alloc(bytes);
+  if (!q) return cudaErrorMemoryAllocation;
   *p = static_cast<T*>(q);
   return cudaSuccess;
 }
 template <typename T> inline cudaError_t cudaMallocHost(T** p, size_t bytes) { return cudaMalloc(p, bytes); }
-inline cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
-inline cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }
+inline cudaError_t cudaFree(void* p) { simt::guarded_free(p); return cudaSuccess; }
+inline cudaError_t cudaFreeHost(void* p) { simt::guarded_free(p); return cudaSuccess; }
 inline cudaError_t cudaMemset(void* p, int v, size_t n) { memset(p, v, n); return cudaSuccess; }
 inline cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { memset(p, v, n); return cudaSuccess; }
 inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { memmove(d, s, n); return cudaSuccess; }

@@ -82,7 +82,26 @@ static void k_bulk(const float* src, float* dst, int n) {
   }
 }
 
-int main() {
+static void k_oob_smem(int n) {
+  unsigned char* smem = simt::dyn_smem();
+  if (threadIdx.x == 0) smem[n] = 1;   // one byte behind the launch's dynamic shared memory
+}
+static void k_oob_global(float* buf, int n) {
+  if (threadIdx.x == 0) buf[n] = 1.f;  // one element behind the allocation
+}
+
+int main(int argc, char** argv) {
+  if (argc > 1 && !strcmp(argv[1], "oob-smem")) {   // must abort
+    simt::Launcher(1, 32, 1024, 0, "k_oob_smem")(k_oob_smem, 1024);
+    return 0;
+  }
+  if (argc > 1 && !strcmp(argv[1], "oob-global")) {   // must abort at cudaFree
+    float* b;
+    cudaMalloc(&b, 100 * 4);
+    simt::Launcher(1, 32, 0, 0, "k_oob_global")(k_oob_global, b, 100);
+    cudaFree(b);
+    return 0;
+  }
   {
     std::vector<int> out(8 * 96, 0);
     simt::Launcher(1, 96, 0, 0, "k_shuffles")(k_shuffles, out.data());

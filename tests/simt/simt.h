@@ -216,9 +216,10 @@ inline void run_cta(unsigned block_idx, unsigned grid, int nthreads, size_t smem
   cta.entry = entry;
   cta.entry_arg = arg;
   // dynamic shared memory, 128-byte aligned, NaN / garbage pattern
-  std::vector<unsigned char> dyn(smem_bytes + 256);
+  std::vector<unsigned char> dyn(smem_bytes + 256 + 512);
   memset(dyn.data(), 0xff, dyn.size());
   cta.dyn = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(dyn.data()) + 127) & ~uintptr_t(127));
+  memset(cta.dyn + smem_bytes, 0xc7, 256);   // canary behind the launch's dynamic shared memory, checked below
   if (g_stack_count < nthreads) {
     if (g_stacks) munmap(g_stacks, (size_t)g_stack_count * g_stack_bytes);
     g_stacks = (unsigned char*)mmap(nullptr, (size_t)nthreads * g_stack_bytes, PROT_READ | PROT_WRITE,
@@ -253,6 +254,11 @@ inline void run_cta(unsigned block_idx, unsigned grid, int nthreads, size_t smem
     }
     if (!progress && remaining > 0) deadlock(&cta);
   }
+  for (int k = 0; k < 256; k++)
+    if (cta.dyn[smem_bytes + k] != 0xc7) {
+      fprintf(stderr, "simt: kernel %s, block %u wrote behind its %zu bytes of dynamic shared memory\n", g_kernel_name, block_idx, smem_bytes);
+      abort();
+    }
   g_cta = nullptr;
 }
 

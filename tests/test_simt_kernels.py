@@ -49,6 +49,10 @@ def test_interpreter_primitives(tmp_path):
     r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "selftest OK" in r.stdout
+    # writes behind the dynamic shared memory of a launch / behind a device allocation are caught
+    for mode, msg in (("oob-smem", "dynamic shared memory"), ("oob-global", "outside a 400-byte allocation")):
+        r = subprocess.run([exe, mode], capture_output=True, text=True, timeout=120)
+        assert r.returncode != 0 and msg in r.stderr, (mode, r.returncode, r.stderr)
 
 
 @pytest.mark.parametrize("nw", [1, 3, None], ids=["1warp", "3warps", "auto"])
@@ -165,6 +169,66 @@ def test_unchanged_victoria_park_driver_on_the_dropin_header_with_interpreted_ke
     monkeypatch.setenv("LD_PRELOAD", simt_lib._name)
     monkeypatch.setenv("SIMT_SM_COUNT", "2")
     c5.test_unchanged_victoria_park_driver_runs_on_the_dropin(simt_lib, tmp_path)
+
+
+def _sharded_worker(rank, world, port, out_dir):
+    """one rank of the N > 1 path on the CPU: the interpreted update kernel on this rank's block of particles
+    (no normalisation), the ONE data-path collective — a SUM all-reduce of [sum w, sum w^2], here over gloo, in place on
+    the buffer the kernel wrote — then the normalisation kernel; exactly the sequence of dist.ShardedUpdater.step()"""
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import rfs_slam_b200  # noqa: F401
+    from rfs_slam_b200 import capi, dist as rd, synth
+    from rfs_slam_b200.phd import PHDUpdater
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    wl = synth.make_workload(N=45, nM=60, nZ=12, use_cluster_process=1, config_id=78)
+    sh = wl.shard(rank, world)
+    with host.interpreted(sm_count=1, warps_per_cta=3):
+        up = PHDUpdater(sh.N, gm_capacity=128, precision=64)
+        up.load_workload(sh)
+        up.update(sh.Z, flags=capi.UPDATE_NO_NORMALIZE)
+        buf = (C.c_double * 2).from_address(up.weight_sums_device_ptr())   # "device" memory is host memory here
+        sums = torch.from_numpy(np.frombuffer(buf, dtype=np.float64))
+        local = sums.clone()
+        rd.allreduce_sums(sums)
+        up.normalize()
+        wn = up.get_weights()
+        cnt, mean, cov, w = up.download_maps()
+        up.close()
+    lo, hi = rd.block_range(wl.N, rank, world)
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), lo=lo, hi=hi, wn=wn, local=local.numpy(), sums=sums.numpy(), count=cnt, w=w)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_interpreted_update_with_gloo_allreduce(simt_lib, tmp_path, world):
+    import socket
+    import torch.multiprocessing as mp
+    from oracle import binding as ob
+    from rfs_slam_b200 import synth
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mp.spawn(_sharded_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    wl = synth.make_workload(N=45, nM=60, nZ=12, use_cluster_process=1, config_id=78)
+    ref = ob.run(wl, sort_mode=ob.SORT_STABLE)
+    got, cnt, covered, partial = np.zeros(wl.N), np.zeros(wl.N, dtype=np.int64), 0, np.zeros(2)
+    for r in range(world):
+        z = np.load(tmp_path / f"rank{r}.npz")
+        lo, hi = int(z["lo"]), int(z["hi"])
+        assert lo == covered
+        covered = hi
+        got[lo:hi], cnt[lo:hi] = z["wn"], z["count"]
+        partial += z["local"]
+        assert np.allclose(z["sums"], [ref.weight.sum(), (ref.weight ** 2).sum()], rtol=1e-12)   # every rank: the global sums
+    assert covered == wl.N and np.allclose(partial, [ref.weight.sum(), (ref.weight ** 2).sum()], rtol=1e-12)
+    assert np.allclose(got, ref.weight / ref.weight.sum(), rtol=1e-10)
+    assert got.sum() == pytest.approx(1.0, abs=1e-12)
+    assert np.array_equal(cnt, ref.count)   # the maps do not depend on the sharding
 
 
 def test_the_package_never_loads_the_interpreter_build():
