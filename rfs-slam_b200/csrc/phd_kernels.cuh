@@ -25,7 +25,8 @@ constexpr int WARPS_PER_CTA = 4;       // default; the 2-D multi-feature kernel 
 constexpr int MAX_WARPS_PER_CTA = 16;
 constexpr int MAX_Z = 64;
 constexpr int MAX_EVAL = 32;
-constexpr int DP_MAXB = 7;     // assignment-sum DP: the smaller side of a partition has <= 7 members
+constexpr int DP_MAXB = 7;     // assignment-sum DP in shared memory: the smaller side of a partition has <= 7 members
+constexpr int DP_GMAXB = 15;   // ... in the per-warp global workspace (KParams::dp_scratch): <= 15 members
 constexpr int MAX_COMP = 96;   // connected components of the (eval point, measurement) graph
 constexpr int MAX_PAIRS = 160; // merge: passing pairs (+ cluster links) kept per particle
 
@@ -79,6 +80,10 @@ struct KParams {
   void* comm_peer[8];               // mailbox of every rank (own included), mapped into this process
   int* comm_error;                  // set to 1 if a peer did not arrive in time
   unsigned long long* stats_out;  // [13] totals/istats/mstats of the finished step, published by the last CTA
+  // multi-feature weighting: global workspace of the assignment-sum DP for partitions beyond the on-chip tables,
+  // 2 x (1 << dp_gmaxb) doubles per warp of the grid (NULL: none); dp_onchip = largest smaller side summed on chip
+  double* dp_scratch;
+  int dp_gmaxb, dp_onchip;
   // host-facing step (rfsb200_update_host with pinned, device-accessible caller buffers): the results are ALSO stored
   // straight into the caller's host memory (posted writes over PCIe), so no device-to-host copy follows the kernel.
   // NULL = not used.
@@ -693,11 +698,11 @@ __device__ double partition_dp(const T* L, int nZ, unsigned rmask, unsigned long
   int b = rowsSmall ? nR : nC;
   int S = 1 << b;
   // index lists
-  int small[DP_MAXB];
+  int small[DP_GMAXB];
   {
     int k = 0;
-    if (rowsSmall) { unsigned m = rmask; while (m) { int r = __ffs(m) - 1; m &= m - 1; if (k < DP_MAXB) small[k] = r; k++; } }
-    else { unsigned long long m = cmask; while (m) { int c = __ffsll((long long)m) - 1; m &= m - 1; if (k < DP_MAXB) small[k] = c; k++; } }
+    if (rowsSmall) { unsigned m = rmask; while (m) { int r = __ffs(m) - 1; m &= m - 1; if (k < DP_GMAXB) small[k] = r; k++; } }
+    else { unsigned long long m = cmask; while (m) { int c = __ffsll((long long)m) - 1; m &= m - 1; if (k < DP_GMAXB) small[k] = c; k++; } }
   }
   for (int s = lane; s < S; s += 32) f0[s] = (s == 0) ? 1.0 : 0.0;
   __syncwarp();
@@ -782,12 +787,15 @@ __device__ inline double warp_permanent(const double* A, int n, int lane) {
 // logic (include/RBPHDFilter.hpp:866-994, src/CostMatrix.cpp:92-227) on a likelihood table
 // L [nE][nZ] (0 = no edge) held in shared memory.  Returns sum over the visited partitions of
 // log(partition likelihood) — the caller subtracts log(clutter integral).  Whole warp; scratch:
-// rowmask [MAX_EVAL], compC [MAX_COMP], f0 / f1 [1 << DP_MAXB], compR [MAX_COMP].
+// rowmask [MAX_EVAL], compC [MAX_COMP], f0 / f1 [1 << DP_MAXB], compR [MAX_COMP].  Partitions whose smaller side has
+// more than dp_onchip members (<= DP_MAXB) are summed in this warp's block of the global workspace gdp
+// (2 x (1 << gmaxb) doubles; NULL: such partitions are skipped and the particle is flagged FLAG_DP_OVERFLOW).
 template <typename T>
 __device__ __forceinline__ double mf_partition_loglik(const T* L, const T* evalPd, int nE, int nZ,
                                                       unsigned long long* rowmask, unsigned long long* compC,
                                                       double* f0, double* f1, unsigned* compR, int sum_method,
-                                                      double log_kappa, int& flags, int lane) {
+                                                      double log_kappa, int& flags, int lane, double* gdp, int gmaxb,
+                                                      int dp_onchip) {
   double logL = 0;
   if (lane < nE) {
     unsigned long long rm = 0;
@@ -925,7 +933,10 @@ __device__ __forceinline__ double mf_partition_loglik(const T* L, const T* evalP
         const unsigned long long cc = compC[hp];
         const int nR = __popc(cr), nC = __popcll(cc);
         const int bsmall = nR < nC ? nR : nC;
-        if (bsmall > DP_MAXB) { flags |= FLAG_DP_OVERFLOW; continue; }
+        const bool offchip = bsmall > dp_onchip;
+        if (offchip && (gdp == nullptr || bsmall > gmaxb)) { flags |= FLAG_DP_OVERFLOW; continue; }
+        double* const d0 = offchip ? gdp : f0;
+        double* const d1 = offchip ? gdp + (1 << gmaxb) : f1;
         __syncwarp();
         if (sum_method == 1 && nR + nC <= 11) {
           // MatPerm path: sum = (prod kappa) * perm([[L/kappa, diag(1-Pd)],[ones]]) / nC!
@@ -959,12 +970,12 @@ __device__ __forceinline__ double mf_partition_loglik(const T* L, const T* evalP
             double fact = 1; for (int k = 2; k <= nC; k++) fact *= k;
             logL += log(perm / fact) + (double)nC * log_kappa;
           } else {
-            const double pl = partition_dp<T>(L, nZ, cr, cc, evalPd, kap, f0, f1, lane);
+            const double pl = partition_dp<T>(L, nZ, cr, cc, evalPd, kap, d0, d1, lane);
             logL += log(pl);
           }
           __syncwarp();
         } else {
-          const double pl = partition_dp<T>(L, nZ, cr, cc, evalPd, kap, f0, f1, lane);
+          const double pl = partition_dp<T>(L, nZ, cr, cc, evalPd, kap, d0, d1, lane);
           logL += log(pl);
         }
       }
@@ -1769,8 +1780,9 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
           L[k] = l;
         }
         __syncwarp();
+        double* gdp = p.dp_scratch ? p.dp_scratch + ((size_t)(blockIdx.x * (blockDim.x >> 5) + warp) << (p.dp_gmaxb + 1)) : nullptr;
         double logL = mf_partition_loglik<T>(L, evalPd, nE, nZ, rowmask, compC, f0, f1, compR, p.sum_method,
-                                            p.log_kappa, flags, lane);
+                                            p.log_kappa, flags, lane, gdp, p.dp_gmaxb, p.dp_onchip);
         logL -= p.log_clutter_integral;
         // :808-812
         weight_new = exp(logL + (lp_before - lp_after) + (sw_now - sw_prev)) * w_prev_particle;

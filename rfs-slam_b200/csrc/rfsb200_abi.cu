@@ -88,6 +88,10 @@ struct rfsb200_ctx {
   rfsb200_model_desc model{};
   rfsb200_filter_cfg cfg{};
   int merge_algo = 1;
+  double* dp_scratch = nullptr;              // multi-feature: global workspace of the assignment-sum DP (see KParams)
+  size_t dp_scratch_bytes = 0;
+  int dp_gmaxb = 0;
+  int dp_onchip = DP_MAXB;                   // RFSB200_DP_ONCHIP_MAXB (test aid): smaller partitions take the workspace too
   bool zero_copy = true;                     // rfsb200_update_host: pinned caller buffers are read / written by the kernels directly
   double* w_host = nullptr;                  // device views of the caller's result buffers for the NEXT launch (or NULL)
   unsigned long long* unused_host = nullptr;
@@ -355,6 +359,32 @@ int choose_warps_per_cta(rfsb200_ctx* c, K kernel, size_t cta_bytes, size_t warp
   return RFSB200_OK;
 }
 
+// Multi-feature weighting: the exact assignment sum of a partition is a DP over the subsets of its smaller side, 2^b
+// states.  Up to b = 7 the two tables live in shared memory; beyond, in a per-warp block of this workspace, sized for
+// b <= min(eval points, z capacity, 15) and capped at 2 GiB (a smaller b then).  Without it (allocation failed, or
+// nothing can exceed 7) larger partitions are skipped and flagged as before.
+int ensure_dp_scratch(rfsb200_ctx* c, int n_eval) {
+  int b = std::min(std::min(n_eval, (int)c->dims.z_capacity), DP_GMAXB);
+  const size_t warps = (size_t)c->grid * c->nwarps;
+  while (b > DP_MAXB && warps * (size_t(16) << b) > (size_t(2) << 30)) b--;
+  if (b <= c->dp_onchip) b = 0;
+  const size_t need = b ? warps * (size_t(16) << b) : 0;
+  if (need > c->dp_scratch_bytes) {
+    if (c->dp_scratch) cudaFree(c->dp_scratch);
+    c->dp_scratch = nullptr;
+    c->dp_scratch_bytes = 0;
+    if (cudaMalloc((void**)&c->dp_scratch, need) != cudaSuccess) {
+      cudaGetLastError();
+      c->dp_scratch = nullptr;
+      c->dp_gmaxb = 0;
+      return RFSB200_OK;   // not fatal: the flag tells the caller which particles were affected
+    }
+    c->dp_scratch_bytes = need;
+  }
+  c->dp_gmaxb = (b && c->dp_scratch) ? b : 0;
+  return RFSB200_OK;
+}
+
 template <typename T, bool MF>
 int configure_launch_t(rfsb200_ctx* c) {
   const int mf = MF ? 1 : 0;
@@ -365,6 +395,7 @@ int configure_launch_t(rfsb200_ctx* c) {
   c->warp_bytes = warp_bytes_for<T>(c->W, mf, mf ? c->mf_bytes : merge_scratch_bytes<T>(c->W));
   int rc = choose_warps_per_cta(c, phd_update_kernel<T, MF>, (size_t)z_bytes<T>(), (size_t)c->warp_bytes);
   if (rc) return rc;
+  if (MF) ensure_dp_scratch(c, n_eval);
   c->cfg_mode_mf = mf;
   return RFSB200_OK;
 }
@@ -378,6 +409,7 @@ int configure_launch_vp_t(rfsb200_ctx* c) {
   c->warp_bytes = vp_warp_bytes<T>(c->W, mf, n_eval, c->dims.z_capacity);
   int rc = choose_warps_per_cta(c, phd_update_vp_kernel<T, MF>, (size_t)vp_cta_bytes<T>(), (size_t)c->warp_bytes);
   if (rc) return rc;
+  if (MF) ensure_dp_scratch(c, n_eval);
   c->cfg_mode_mf = mf;
   return RFSB200_OK;
 }
@@ -437,6 +469,9 @@ int launch_update(rfsb200_ctx* c, int nZ, int out_idx, unsigned flags) {
     p.mf_bytes = c->mf_bytes;
     p.n_eval_cap = c->cfg_n_eval;
     p.zcap = c->dims.z_capacity;
+    p.dp_scratch = (mf && c->dp_gmaxb) ? c->dp_scratch : nullptr;
+    p.dp_gmaxb = c->dp_gmaxb;
+    p.dp_onchip = c->dp_onchip;
   }
   const bool prof = c->prof_n < c->prof_cap;
   if (prof) CU(c, cudaEventRecord(c->prof_ev[2 * c->prof_n], c->stream));
@@ -631,6 +666,7 @@ int rfsb200_create(rfsb200_ctx** out, const rfsb200_dims* d) {
     CU(c, cudaMalloc((void**)&c->offs, (size_t)(c->N + 1) * 8));
     CU(c, cudaMalloc((void**)&c->stg_small, (size_t)c->N * 16 * 8));
     if (const char* e = getenv("RFSB200_ZERO_COPY")) c->zero_copy = atoi(e) != 0;   // 0: always stage through copies
+    if (const char* e = getenv("RFSB200_DP_ONCHIP_MAXB")) c->dp_onchip = std::max(0, std::min(DP_MAXB, atoi(e)));   // test aid
     int r = ensure_pinned(c, 1 << 16);
     if (r) return r;
     if (c->prec == 32) r = configure_launch<float>(c, 0);
@@ -665,7 +701,7 @@ int rfsb200_destroy(rfsb200_ctx* c) {
   cudaFree(c->comm_mail); cudaFree(c->comm_error);
   cudaFree(c->sums); cudaFree(c->totals); cudaFree(c->istats); cudaFree(c->ticket);
   cudaFree(c->work_counter); cudaFree(c->stats_out); cudaFree(c->mstats);
-  cudaFree(c->stg); cudaFree(c->offs); cudaFree(c->stg_small); cudaFree(c->scan_dev);
+  cudaFree(c->stg); cudaFree(c->offs); cudaFree(c->stg_small); cudaFree(c->scan_dev); cudaFree(c->dp_scratch);
   if (c->hpin) cudaFreeHost(c->hpin);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);

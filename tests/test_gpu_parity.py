@@ -250,6 +250,47 @@ def test_large_partitions_are_flagged_and_summed_exactly(cuda_required):
     up.close()
 
 
+def test_partitions_beyond_the_on_chip_tables_are_summed_in_the_global_workspace(cuda_required):
+    """A partition whose smaller side has 8..15 members does not fit the shared-memory tables of the assignment-sum
+    DP: it is summed in the warp's block of the global workspace instead of being skipped (found by the randomised
+    sweep: 24 eval points, P_D 0.5, clumped world).  No overflow is reported, the flagged set is the oracle's Murty set,
+    the exact sum is >= the reference's truncated one — and forcing EVERY partition through the workspace
+    (RFSB200_DP_ONCHIP_MAXB=0 / 2, a test aid) gives bit-identical particle weights, for both plugin sets."""
+    import os
+    from oracle import binding as ob
+    from rfs_slam_b200 import synth
+    cfg = dict(merging_threshold=0.5, merging_cov_inflation_factor=1.5, pruning_threshold=0.01, eval_point_count=24,
+               eval_point_gaussian_weight=0.2, new_gaussian_create_innov_md_threshold=5.0, meas_likelihood_md_threshold=3.0)
+    wl = synth.make_workload(N=11, nM=46, nZ=30, use_cluster_process=0, cfg=cfg, seed=522333278, ragged=0.3, parity_extras=True,
+                             world="clumped", model=dict(Pd=0.5, clutter_intensity=1e-4, innov_thr_bearing=-1.0))
+    wv = synth.make_vp_workload(N=24, nM=60, nZ=14, use_cluster_process=0, config_id=83, cfg=dict(eval_point_count=15))
+    saved = os.environ.get("RFSB200_DP_ONCHIP_MAXB")
+    try:
+        for w_, caps in ((wl, dict(gm_capacity=512, work_capacity=1024)), (wv, dict(gm_capacity=128))):
+            o = ob.run(w_, sort_mode=ob.SORT_STABLE)
+            murty = (o.flags & 2) > 0
+            got = {}
+            for onchip in (None, 2, 0):
+                if onchip is None:
+                    os.environ.pop("RFSB200_DP_ONCHIP_MAXB", None)
+                else:
+                    os.environ["RFSB200_DP_ONCHIP_MAXB"] = str(onchip)   # read by rfsb200_create
+                so, cnt, mean, cov, w, pw, up = helpers.run_device(w_, precision=64, **caps)
+                f = up.get_flags()
+                up.close()
+                assert so.n_overflow == 0 and not (f & 4).any()
+                assert np.array_equal((f & 2) > 0, murty)
+                assert np.allclose(pw[~murty], o.weight[~murty], rtol=1e-9)
+                assert np.isfinite(pw).all() and (pw[murty] >= o.weight[murty] * (1 - 1e-9)).all()
+                got[onchip] = pw
+            assert np.array_equal(got[None], got[2]) and np.array_equal(got[None], got[0])
+    finally:
+        if saved is None:
+            os.environ.pop("RFSB200_DP_ONCHIP_MAXB", None)
+        else:
+            os.environ["RFSB200_DP_ONCHIP_MAXB"] = saved
+
+
 def test_fused_normalisation_equals_two_launch_path(cuda_required):
     """RFSB200_UPDATE_FUSED_ALLREDUCE on one rank: sums + normalisation inside the update kernel."""
     from rfs_slam_b200 import capi, synth
