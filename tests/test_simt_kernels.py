@@ -129,6 +129,16 @@ def test_gpu_test_bodies_on_the_interpreted_kernels(simt_lib, fn):
         fn(simt_lib)
 
 
+@pytest.mark.parametrize("name", ["C2", "C3"])
+def test_full_size_configs_on_the_interpreted_kernels(simt_lib, name):
+    """BASELINE.json's full sizes (C2: 1 000 x 100 x 20 multi-feature, C3: 8 000 x 200 x 30 single-cluster) through the
+    body of tests/test_gpu_fullsize.py: size-independent properties, run-to-run and sharding invariance (bit-exact),
+    and the oracle on a quarter of the particles — 8 "SMs", so every warp works through several hundred particles"""
+    import test_gpu_fullsize as tf
+    with host.interpreted(sm_count=8):
+        tf.test_full_size_properties(simt_lib, name)
+
+
 @pytest.mark.parametrize("sc", [0, 1])
 def test_interpreted_culled_merge_equals_exhaustive_merge(simt_lib, sc):
     from rfs_slam_b200 import synth
@@ -147,6 +157,30 @@ def test_interpreted_randomised_sweep():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fuzz_parity.py"), "40", "777", "fp64", "--simt"],
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+_DROPIN_SCRIPT = """
+import sys
+sys.path.insert(0, {root!r}); sys.path.insert(0, {tests!r})
+import test_gpu_dropin as t
+for sc in (1, 0):
+    for resample in (False, True):
+        t.test_dropin_header_matches_reference_class(None, sc, resample)
+print("dropin sequences OK")
+"""
+
+
+def test_dropin_header_against_the_reference_class_with_interpreted_kernels(simt_lib):
+    """the body of tests/test_gpu_dropin.py — the drop-in C++ header against the reference class it replaces on scripted
+    sequences (births, landmark process noise, resampling with the same drand48 stream, an empty measurement set), both
+    weightings, both precisions — in a fresh process whose rfsb200_* symbols are bound to the interpreter build"""
+    from oracle import binding as ob
+    if not ob.have_seq():
+        pytest.skip("oracle/_ref/libseq_{ref,b200}.so not built (needs /root/reference at build time)")
+    env = dict(os.environ, LD_PRELOAD=simt_lib._name, SIMT_SM_COUNT="2")
+    r = subprocess.run([sys.executable, "-c", _DROPIN_SCRIPT.format(root=ROOT, tests=os.path.join(ROOT, "tests"))],
+                       env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "dropin sequences OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
 
 
 def test_unchanged_simulator_on_the_dropin_header_with_interpreted_kernels(simt_lib, tmp_path, monkeypatch):
