@@ -129,6 +129,15 @@ def test_gpu_test_bodies_on_the_interpreted_kernels(simt_lib, fn):
         fn(simt_lib)
 
 
+def test_smoke_body_on_the_interpreted_kernels(simt_lib, capsys):
+    """__graft_entry__.smoke() — what the driver runs on cuda:0 before the bench — with the binding pointed at the
+    interpreter build: both weightings of the 2-D model and the Victoria Park model against the oracle"""
+    import __graft_entry__ as g
+    with host.interpreted(sm_count=2):
+        g.smoke()
+    assert "smoke OK" in capsys.readouterr().out
+
+
 @pytest.mark.parametrize("name", ["C2", "C3"])
 def test_full_size_configs_on_the_interpreted_kernels(simt_lib, name):
     """BASELINE.json's full sizes (C2: 1 000 x 100 x 20 multi-feature, C3: 8 000 x 200 x 30 single-cluster) through the
