@@ -78,55 +78,51 @@ def test_interpreted_kernels_against_reference_golden(simt_lib, case, prec, nw):
         up.close()
 
 
-@pytest.mark.parametrize("prec", [32, 64])
-@pytest.mark.parametrize("kw", [
-    dict(N=48, nM=200, nZ=30, use_cluster_process=1, config_id=11),
-    dict(N=48, nM=100, nZ=20, use_cluster_process=0, config_id=12),
-    dict(N=48, nM=200, nZ=30, use_cluster_process=1, config_id=13, parity_extras=True),
-    dict(N=48, nM=100, nZ=20, use_cluster_process=0, config_id=14, parity_extras=True, ragged=0.2),
-    dict(N=32, nM=180, nZ=30, use_cluster_process=1, config_id=15, world="sparse"),
-    dict(N=32, nM=120, nZ=24, use_cluster_process=0, config_id=16, world="sparse", ragged=0.3),
-    dict(N=32, nM=100, nZ=20, use_cluster_process=0, config_id=17, model=dict(Pd=0.6, clutter_intensity=5e-3)),
-    dict(N=24, nM=60, nZ=64, use_cluster_process=1, config_id=18),
-    dict(N=16, nM=1, nZ=1, use_cluster_process=0, config_id=19),
-], ids=lambda k: "sc%d_nM%d_nZ%d_id%d" % (k["use_cluster_process"], k["nM"], k["nZ"], k["config_id"]))
-def test_interpreted_kernels_against_oracle(simt_lib, kw, prec):
-    """the workloads of tests/test_gpu_parity.py::test_against_oracle at a fraction of the particles"""
-    from oracle import binding as ob
-    from rfs_slam_b200 import synth
-    wl = synth.make_workload(**kw)
-    o = ob.run(wl, sort_mode=ob.SORT_STABLE)
-    ref = dict(count=o.count, mean=o.mean, cov=o.cov, w=o.w, weight=o.weight)
-    with host.interpreted(sm_count=1, warps_per_cta=4):
-        so, cnt, mean, cov, w, pw, up = helpers.run_device(wl, precision=prec)
-        _compare(wl, prec, ref, cnt, mean, cov, w, pw)
-        if prec == 64:
-            assert np.array_equal(cnt, o.count)
-            assert np.allclose(mean, o.mean, rtol=0, atol=1e-9)
-            mask, nfov = up.get_unused()
-            assert np.array_equal(mask, o.unused_mask) and np.array_equal(nfov, o.n_in_fov)
-        assert so.sum_w == pytest.approx(float(pw.sum()), rel=1e-12)
-        up.close()
+def _param_sets(fn):
+    """the cartesian product of a test function's pytest.mark.parametrize marks, as keyword dictionaries"""
+    combos = [({}, "")]
+    for m in [m for m in getattr(fn, "pytestmark", []) if m.name == "parametrize"]:
+        names = [n.strip() for n in m.args[0].split(",")] if isinstance(m.args[0], str) else list(m.args[0])
+        ids = m.kwargs.get("ids")
+        nxt = []
+        for c, cid in combos:
+            for v in m.args[1]:
+                vals = tuple(v.values) if isinstance(v, type(pytest.param(0))) else (tuple(v) if len(names) > 1 else (v,))
+                d = dict(c)
+                d.update(zip(names, vals))
+                label = ids(vals[0]) if callable(ids) else "-".join(str(x) for x in vals)
+                nxt.append((d, (cid + "-" if cid else "") + str(label)))
+        combos = nxt
+    return combos
 
 
 def _gpu_tests(module_name, skip):
+    """every `-m gpu` test of a module whose only fixture is cuda_required, one pytest.param per parametrisation"""
     mod = __import__(module_name)
     out = []
     for name, fn in sorted(vars(mod).items()):
-        if name.startswith("test_") and callable(fn) and list(inspect.signature(fn).parameters) == ["cuda_required"] \
-                and not any(s in name for s in skip):
-            out.append(pytest.param(fn, id=f"{module_name}.{name}"))
+        if not (name.startswith("test_") and callable(fn)) or any(s in name for s in skip):
+            continue
+        params = list(inspect.signature(fn).parameters)
+        if not params or params[0] != "cuda_required":
+            continue
+        for kw, cid in _param_sets(fn):
+            if set(params[1:]) == set(kw):
+                out.append(pytest.param(fn, kw, id=f"{module_name}.{name}" + (f"[{cid}]" if cid else "")))
     return out
 
 
-@pytest.mark.parametrize("fn", _gpu_tests("test_gpu_parity", skip=("randomised", "culled_merge")) +
-                         _gpu_tests("test_gpu_vp", skip=("full_size",)))
-def test_gpu_test_bodies_on_the_interpreted_kernels(simt_lib, fn):
-    """the un-parametrised `-m gpu` tests (multi-step sequences, NO_COMMIT / empty Z, pose-covariance modes, capacity
-    overflow, API surface, matrix permanents, large partitions, fused normalisation, update_host, Victoria Park
-    predict / births), bodies unchanged, with the binding pointed at the interpreter build"""
-    with host.interpreted(sm_count=2):
-        fn(simt_lib)
+@pytest.mark.parametrize("fn,kw", _gpu_tests("test_gpu_parity", skip=("randomised",)) + _gpu_tests("test_gpu_vp", skip=()) +
+                         _gpu_tests("test_gpu_fullsize", skip=()) + _gpu_tests("test_motion", skip=()))
+def test_gpu_test_bodies_on_the_interpreted_kernels(simt_lib, fn, kw):
+    """The `-m gpu` parity tests, bodies and sizes unchanged, with the binding pointed at the interpreter build: the
+    reference's golden vectors and the oracle for both plugin sets and precisions, culled against exhaustive merge,
+    multi-step sequences, NO_COMMIT / empty Z, pose-covariance modes, capacity overflow, API surface, matrix
+    permanents, large partitions, the DP workspace, fused normalisation, update_host with and without copies, Victoria
+    Park predict / births, the full-size C2 / C3 / C5 property tests (8 "SMs": every warp works through hundreds of
+    particles), particle propagation."""
+    with host.interpreted(sm_count=8 if "full_size" in fn.__name__ else 2):
+        fn(simt_lib, **kw)
 
 
 def test_smoke_body_on_the_interpreted_kernels(simt_lib, capsys):
@@ -136,28 +132,6 @@ def test_smoke_body_on_the_interpreted_kernels(simt_lib, capsys):
     with host.interpreted(sm_count=2):
         g.smoke()
     assert "smoke OK" in capsys.readouterr().out
-
-
-@pytest.mark.parametrize("name", ["C2", "C3"])
-def test_full_size_configs_on_the_interpreted_kernels(simt_lib, name):
-    """BASELINE.json's full sizes (C2: 1 000 x 100 x 20 multi-feature, C3: 8 000 x 200 x 30 single-cluster) through the
-    body of tests/test_gpu_fullsize.py: size-independent properties, run-to-run and sharding invariance (bit-exact),
-    and the oracle on a quarter of the particles — 8 "SMs", so every warp works through several hundred particles"""
-    import test_gpu_fullsize as tf
-    with host.interpreted(sm_count=8):
-        tf.test_full_size_properties(simt_lib, name)
-
-
-@pytest.mark.parametrize("sc", [0, 1])
-def test_interpreted_culled_merge_equals_exhaustive_merge(simt_lib, sc):
-    from rfs_slam_b200 import synth
-    wl = synth.make_workload(N=48, nM=150, nZ=30, use_cluster_process=sc, config_id=21 + sc, parity_extras=True)
-    with host.interpreted(sm_count=2, warps_per_cta=5):
-        a = helpers.run_device(wl, precision=32, brute=False)
-        b = helpers.run_device(wl, precision=32, brute=True)
-        for k in range(1, 6):
-            assert np.array_equal(a[k], b[k])
-        a[6].close(); b[6].close()
 
 
 def test_interpreted_randomised_sweep():
@@ -195,9 +169,20 @@ def test_dropin_header_against_the_reference_class_with_interpreted_kernels(simt
 def test_unchanged_simulator_on_the_dropin_header_with_interpreted_kernels(simt_lib, tmp_path, monkeypatch):
     """BASELINE config C1 end to end on the CPU: the body of tests/test_gpu_sim_c1.py (the reference's
     src/rbphdslam2dSim.cpp UNCHANGED, once on the reference's filter header and once on the drop-in header over the
-    C ABI, 50 particles, 600 steps; identical particle poses, weights and best-particle maps with the fp64 kernels, same
+    C ABI, 50 particles, the first 250 steps; identical particle poses, weights and best-particle maps with the fp64 kernels, same
     final error with the fp32 kernels) with the ABI symbols of the drop-in binary bound to the interpreter build."""
     import test_gpu_sim_c1 as c1
+    if not os.path.exists(os.path.join(c1.REFDIR, "rbphdslam2dSim_b200")):
+        pytest.skip("oracle/_ref/rbphdslam2dSim_{ref,b200} not built (needs /root/reference at build time)")
+    # the first 250 of the 600 steps keep the CPU suite short (the -m gpu test runs all of them)
+    short = tmp_path / "refdir"
+    short.mkdir()
+    for f in ("rbphdslam2dSim_ref", "rbphdslam2dSim_b200"):
+        os.symlink(os.path.join(c1.REFDIR, f), short / f)
+    xml = open(os.path.join(c1.REFDIR, "rbphdslam2dSim.xml")).read()
+    assert "<timesteps>600</timesteps>" in xml
+    (short / "rbphdslam2dSim.xml").write_text(xml.replace("<timesteps>600</timesteps>", "<timesteps>250</timesteps>"))
+    monkeypatch.setattr(c1, "REFDIR", str(short))
     monkeypatch.setenv("LD_PRELOAD", simt_lib._name)
     monkeypatch.setenv("SIMT_SM_COUNT", "2")
     c1.test_unchanged_simulator_runs_on_the_dropin(simt_lib, tmp_path)
