@@ -350,7 +350,19 @@ def main():
             traffic = json.load(open(tp)).get(a.config)
         except Exception:
             traffic = None
-    roofline = dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic,
+    # the roof that actually bounds this kernel: warp instructions per launch (ncu, same capture
+    # as `traffic`) against the issue slots of the launch, 148 SMs x 4 schedulers x SM clock x kernel time
+    issue = None
+    try:
+        n_inst = json.load(open(tp)).get(a.config + "_warp_instructions")
+        if n_inst and N == WORKLOADS[a.config][1] and clk is not None:
+            sm_hz = 1e6 * float(clk.get("sm_mhz") or clk.get("sm_max_mhz") or 1965.0)
+            slots = 148 * 4 * sm_hz * k_us * 1e-6
+            issue = dict(warp_instructions=int(n_inst), issue_slots=slots, frac=n_inst / slots,
+                         note="instruction-issue roofline: the kernel is issue / latency bound, not HBM bound")
+    except Exception:
+        issue = None
+    roofline = dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic, issue=issue,
                     kernel=("phd_update_kernel<float>" if D == 2 else "phd_update_vp_kernel<float>"), kernel_us=k_us, algorithmic_bytes=b_alg, peak_source=peak_src,
                     kernel_share_of_step=k_us * 1e-3 / (1e3 * t_local / K))
 
