@@ -157,11 +157,28 @@ class PHDUpdater:
         (rfsb200_update_host).  All arrays float64 / uint64 / int32, C-contiguous, ideally pinned_array()s."""
         mode = 0 if pose_cov is None else (1 if pose_cov.ndim == 1 else 2)
         out = capi.StepOut() if want_stats else None
-        rc = self.lib.rfsb200_update_host(self.ctx, capi.ptr(pose), capi.ptr(pose_cov), mode, capi.ptr(weight), capi.ptr(Z),
-                                          Z.shape[0], flags, capi.ptr(w_out), capi.ptr(unused_out), capi.ptr(nfov_out),
+        p = self._host_ptr   # building a ctypes pointer costs ~2.5 us per array: the per-step buffers are bound once
+        rc = self.lib.rfsb200_update_host(self.ctx, p(pose), p(pose_cov), mode, p(weight), p(Z),
+                                          Z.shape[0], flags, p(w_out), p(unused_out), p(nfov_out),
                                           C.byref(out) if out is not None else None)
-        _check(self.lib, self.ctx, rc, "update_host")
+        if rc != 0:
+            _check(self.lib, self.ctx, rc, "update_host")
         return out
+
+    def _host_ptr(self, a):
+        """ctypes pointer of a host array, cached per array object (the cache holds a reference, so an id cannot be
+        recycled while its pointer is cached; numpy never moves the data of a live array)."""
+        if a is None:
+            return None
+        cache = self.__dict__.setdefault("_ptr_cache", {})
+        hit = cache.get(id(a))
+        if hit is not None and hit[0] is a:
+            return hit[1]
+        if len(cache) >= 64:
+            cache.clear()
+        ptr = capi.ptr(a)
+        cache[id(a)] = (a, ptr)
+        return ptr
 
     # ---- the callers either side (predict's map part, resampling's data movement) -----------------
     def predict_maps(self, Q_lmk=None, add_births: bool = True, birth_weight: float = 0.0):
