@@ -44,6 +44,7 @@
 #include <iostream>
 #include <limits>
 #include <list>
+#include <new>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -57,6 +58,58 @@
 #include "ProcessModel_Ackerman2D.hpp"
 
 #include "../rfsb200.h"
+
+namespace rfs {
+namespace b200 {
+namespace detail {
+/* Host array of doubles in page-locked memory (rfsb200_host_alloc): with such buffers rfsb200_update_host stages
+ * nothing — one conversion kernel reads the inputs over PCIe and the update kernel stores the results into them.
+ * Falls back to pageable memory (and the staged copies) if pinning is not possible.  Contents are not initialised
+ * and not preserved by a growing resize(): every user fills the array completely before it is read. */
+class PinnedDoubles {
+ public:
+  PinnedDoubles() : p_(NULL), n_(0), cap_(0), pinned_(false) {}
+  ~PinnedDoubles() { release(); }
+  void resize(size_t n) {
+    if (n > cap_) {
+      release();
+      void* q = NULL;
+      if (rfsb200_host_alloc(&q, (uint64_t)n * sizeof(double)) == RFSB200_OK && q) {
+        p_ = static_cast<double*>(q);
+        pinned_ = true;
+      } else {
+        p_ = static_cast<double*>(malloc(n * sizeof(double)));
+        pinned_ = false;
+        if (!p_) throw std::bad_alloc();
+      }
+      cap_ = n;
+    }
+    n_ = n;
+  }
+  double* data() { return p_; }
+  const double* data() const { return p_; }
+  double& operator[](size_t i) { return p_[i]; }
+  const double& operator[](size_t i) const { return p_[i]; }
+  size_t size() const { return n_; }
+
+ private:
+  PinnedDoubles(const PinnedDoubles&);              /* not copyable */
+  PinnedDoubles& operator=(const PinnedDoubles&);
+  void release() {
+    if (p_) {
+      if (pinned_) rfsb200_host_free(p_);
+      else free(p_);
+    }
+    p_ = NULL;
+    n_ = cap_ = 0;
+  }
+  double* p_;
+  size_t n_, cap_;
+  bool pinned_;
+};
+}  // namespace detail
+}  // namespace b200
+}  // namespace rfs
 
 namespace rfs {
 
@@ -336,7 +389,8 @@ class RBPHDFilter : public ParticleFilter<RobotProcessModel, MeasurementModel,
   int cacheIdx_;
   std::vector<double> cMean_, cCov_, cW_;
   int cN_;
-  std::vector<double> hPose_, hPoseCov_, hW_, hWout_;
+  /* page-locked (rfsb200_host_alloc): rfsb200_update_host lets the kernels read / write such buffers directly */
+  b200::detail::PinnedDoubles hPose_, hPoseCov_, hW_, hWout_;
 
   void ensureCtx();
   void check(int rc, const char* what) {
