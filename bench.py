@@ -158,11 +158,18 @@ def run_reference_arm(a):
     units = int(sub.count.sum()) * sub.nZ
     v = units / t
     sample = f"{sub.N} of {wl.N} particles of the workload per step ({'oracle/_ref: reference sources, OpenMP' if kind == 'reference' else 'oracle port'}, {threads} threads)"
+    single = None
+    try:   # the same path on ONE host thread, on a quarter of the sample
+        _, sub1, t1 = cpu_reference_run(wl, max(1, n_s // 4), 1, 1)
+        single = dict(value=int(sub1.count.sum()) * sub1.nZ / t1[0], unit=UNIT, cores=1,
+                      sample=f"{sub1.N} particles, one run ({t1[0]:.3f} s)")
+    except Exception:
+        single = None
     line = dict(metric=METRIC, value=v, unit=UNIT, n_gpus=a.gpus, steps=a.steps, warmup=a.warmup,
                 ms_per_step=1e3 * t, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
                 data="synthetic", impl="reference",
                 config=dict(workload=desc, particles_per_step=sub.N, gm_per_particle=nM, meas=sub.nZ),
-                cpu_baseline=dict(value=v, unit=UNIT, cores=threads, kind=kind, sample=sample),
+                cpu_baseline=dict(value=v, unit=UNIT, cores=threads, kind=kind, sample=sample, single_thread=single),
                 e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 gpu_launches=0)
     emit(line)
