@@ -110,7 +110,7 @@ inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes* a, const void
   a->hostPointer = const_cast<void*>(p);
   return cudaSuccess;
 }
-// no peers on the host: the fused cross-GPU sum is not interpreted
-inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void*) { memset(h, 0, sizeof(*h)); return cudaErrorNotSupported; }
-inline cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t, unsigned) { *p = nullptr; return cudaErrorNotSupported; }
+// "peers" are other contexts of the same process, driven by other host threads: an IPC handle is the pointer itself
+inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p) { memset(h, 0, sizeof(*h)); memcpy(h->reserved, &p, sizeof(p)); return cudaSuccess; }
+inline cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned) { memcpy(p, h.reserved, sizeof(*p)); return *p ? cudaSuccess : cudaErrorInvalidValue; }
 inline cudaError_t cudaIpcCloseMemHandle(void*) { return cudaSuccess; }

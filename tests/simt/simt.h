@@ -83,7 +83,9 @@ inline void make_context(Context* c, void* stack, size_t bytes, void (*entry)())
 #define __launch_bounds__(...)
 #define __grid_constant__
 #define __align__(n) alignas(n)
-#define __shared__ static   // the CTAs of a launch run one after the other, so one static instance per variable
+// the CTAs of a launch run one after the other, so one static instance per variable; per host thread, because
+// every host thread is one "GPU" (two ranks of the fused cross-GPU sum run on two threads)
+#define __shared__ static thread_local
 
 namespace simt {
 
@@ -138,18 +140,19 @@ struct Cta {
   void* entry_arg = nullptr;
 };
 
-inline Cta* g_cta = nullptr;
-inline unsigned char* g_stacks = nullptr;
+// interpreter state is per host thread: a host thread is one "GPU" that runs its launches one after the other
+inline thread_local Cta* g_cta = nullptr;
+inline thread_local unsigned char* g_stacks = nullptr;
 inline size_t g_stack_bytes = 256 * 1024;
-inline int g_stack_count = 0;
-inline uint64_t g_switches = 0;   // statistics
-inline const char* g_kernel_name = "";
+inline thread_local int g_stack_count = 0;
+inline thread_local uint64_t g_switches = 0;   // statistics
+inline thread_local const char* g_kernel_name = "";
 
 }  // namespace simt
 
 // the CUDA built-in coordinates (set by the scheduler whenever a fiber is resumed)
 using dim3 = simt::Dim3;
-inline simt::Dim3 threadIdx, blockIdx, blockDim, gridDim;
+inline thread_local simt::Dim3 threadIdx, blockIdx, blockDim, gridDim;
 
 namespace simt {
 

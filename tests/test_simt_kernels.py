@@ -199,6 +199,65 @@ def test_unchanged_victoria_park_driver_on_the_dropin_header_with_interpreted_ke
     c5.test_unchanged_victoria_park_driver_runs_on_the_dropin(simt_lib, tmp_path)
 
 
+@pytest.mark.parametrize("world", [2, 3])
+def test_fused_cross_gpu_sum_between_interpreted_ranks(simt_lib, world):
+    """RFSB200_UPDATE_FUSED_ALLREDUCE with more than one rank, on the CPU: every rank is a context driven by its own
+    host thread (the interpreter's state is per thread), the "IPC handles" of the mailboxes are plain pointers, and the
+    last CTA of each rank's update kernel stores its [sum w, sum w^2] into every rank's mailbox, waits for the others
+    and normalises its shard — the exchange that otherwise only runs over NVLink peer memory.  Several steps, so both
+    epoch parities of the double-buffered slots are used; the host-facing zero-copy step on top of it."""
+    import threading
+    from oracle import binding as ob
+    from rfs_slam_b200 import capi, synth
+    from rfs_slam_b200.phd import PHDUpdater, pinned_array
+    wl = synth.make_workload(N=41, nM=50, nZ=10, use_cluster_process=1, config_id=79)
+    ref = ob.run(wl, sort_mode=ob.SORT_STABLE)
+    wn_ref = ref.weight / ref.weight.sum()
+    with host.interpreted(sm_count=2, warps_per_cta=2):
+        shards = [wl.shard(r, world) for r in range(world)]
+        ups = []
+        for sh in shards:
+            u = PHDUpdater(sh.N, gm_capacity=128, precision=64)
+            u.load_workload(sh)
+            ups.append(u)
+        handles = [u.comm_export() for u in ups]
+        for r, u in enumerate(ups):
+            u.comm_connect(r, world, handles)
+        w_host = [pinned_array((sh.N,)) for sh in shards]
+        pose = [pinned_array((sh.N, 3)) for sh in shards]
+        for r, sh in enumerate(shards):
+            pose[r][:] = sh.pose
+        for step in range(4):
+            outs, errs = [None] * world, []
+
+            def run(r):
+                try:
+                    f = capi.UPDATE_FUSED_ALLREDUCE | capi.UPDATE_NO_COMMIT
+                    if step < 3:
+                        outs[r] = ups[r].update(shards[r].Z, flags=f, want_stats=True)
+                    else:   # the host-facing step: results stored into the pinned buffer by the same launch
+                        outs[r] = ups[r].update_host(pose[r], shards[r].pose_cov, None, np.ascontiguousarray(shards[r].Z), flags=f,
+                                                     w_out=w_host[r], want_stats=True)
+                except Exception as e:   # noqa: BLE001
+                    errs.append((r, e))
+            ts = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+            for t in ts:
+                t.start()
+            for t in ts:
+                t.join(timeout=120)
+            assert not errs, errs
+            assert not any(u.comm_error() for u in ups)
+            # every rank holds the same global sums, bit for bit (added in rank order on every rank)
+            assert len({(o.sum_w, o.sum_w2) for o in outs}) == 1
+            assert outs[0].sum_w == pytest.approx(float(ref.weight.sum()), rel=1e-12)
+            got = np.concatenate([u.get_weights(1) for u in ups])
+            assert np.allclose(got, wn_ref, rtol=1e-10) and got.sum() == pytest.approx(1.0, abs=1e-12)
+            if step == 3:
+                assert np.array_equal(np.concatenate(w_host), got)
+        for u in ups:
+            u.close()
+
+
 def _sharded_worker(rank, world, port, out_dir):
     """one rank of the N > 1 path on the CPU: the interpreted update kernel on this rank's block of particles
     (no normalisation), the ONE data-path collective — a SUM all-reduce of [sum w, sum w^2], here over gloo, in place on
