@@ -11,10 +11,13 @@ if [ "$2" != "notests" ]; then
 fi
 timeout 600 python bench.py --steps 50 --warmup 5 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err
 echo "bench rc=$?"; cat gpurun_out/bench_$TAG.json; tail -3 gpurun_out/bench_$TAG.err
-for C in C2 C3mf C5; do
+for C in C2 C3mf C5 N1k N64k C3sparse; do
   timeout 300 python bench.py --steps 20 --warmup 5 --config $C > gpurun_out/bench_${C}_$TAG.json 2>> gpurun_out/bench_$TAG.err
   cat gpurun_out/bench_${C}_$TAG.json
 done
+# the host-facing step staged through copies, for comparison with the default (kernels read / write the pinned buffers)
+RFSB200_ZERO_COPY=0 timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu-baseline > gpurun_out/bench_staged_$TAG.json 2>> gpurun_out/bench_$TAG.err
+cat gpurun_out/bench_staged_$TAG.json
 timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref_$TAG.json 2>> gpurun_out/bench_$TAG.err
 cat gpurun_out/bench_ref_$TAG.json
 # launch list of the same bench command (cold-cache, serialised: shares only)
