@@ -141,7 +141,7 @@ int main(int argc, char** argv) {
   {
     const int n = 64;
     std::vector<float> src(2 * n), dst(6 * n, -1.f);
-    float* s16; float* d16;
+    float* s16 = nullptr; float* d16 = nullptr;
     cudaMalloc(&s16, 2 * n * 4); cudaMalloc(&d16, 6 * n * 4);
     for (int k = 0; k < 2 * n; k++) s16[k] = (float)k;
     simt::Launcher(1, 32, 8192, 0, "k_bulk")(k_bulk, (const float*)s16, d16, n);

@@ -20,6 +20,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <tuple>
 #include <type_traits>
 #include <utility>
@@ -105,14 +106,12 @@ struct Rendezvous {
 
 struct Warp {
   uint32_t exited = 0;
-  std::vector<Rendezvous*> rv;
-  ~Warp() { for (Rendezvous* r : rv) delete r; }
+  std::vector<std::unique_ptr<Rendezvous>> rv;   // one per mask in use (almost always only the full mask)
   Rendezvous* get(uint32_t key) {
-    for (Rendezvous* r : rv) if (r->key == key) return r;
-    Rendezvous* r = new Rendezvous();
-    r->key = key;
-    rv.push_back(r);
-    return r;
+    for (auto& r : rv) if (r->key == key) return r.get();
+    rv.emplace_back(new Rendezvous());
+    rv.back()->key = key;
+    return rv.back().get();
   }
 };
 
@@ -170,7 +169,7 @@ inline void check_release_cta(Cta* c) {
   }
 }
 inline void check_release_warp(Warp& w) {
-  for (Rendezvous* r : w.rv) {
+  for (auto& r : w.rv) {
     const uint32_t need = r->key & ~w.exited;
     if (r->arrived && (r->arrived & need) == need) {
       r->part[r->gen & 1] = r->arrived;
