@@ -96,7 +96,7 @@ int main(int argc, char** argv) {
     return 0;
   }
   if (argc > 1 && !strcmp(argv[1], "oob-global")) {   // must abort at cudaFree
-    float* b;
+    float* b = nullptr;
     cudaMalloc(&b, 100 * 4);
     simt::Launcher(1, 32, 0, 0, "k_oob_global")(k_oob_global, b, 100);
     cudaFree(b);
