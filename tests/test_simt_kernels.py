@@ -166,6 +166,18 @@ def test_dropin_header_against_the_reference_class_with_interpreted_kernels(simt
     assert r.returncode == 0 and "dropin sequences OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
 
 
+def test_randomised_sequences_dropin_against_reference_class(simt_lib):
+    """tools/fuzz_sequences.py: random scenarios (particle counts, lengths, landmark densities, both weightings, with and
+    without resampling) through predict / births / update / resample of the drop-in header and of the reference class"""
+    from oracle import binding as ob
+    if not ob.have_seq():
+        pytest.skip("oracle/_ref/libseq_{ref,b200}.so not built (needs /root/reference at build time)")
+    env = dict(os.environ, LD_PRELOAD=simt_lib._name, SIMT_SM_COUNT="2")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fuzz_sequences.py"), "25", "5"], env=env,
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
 def test_unchanged_simulator_on_the_dropin_header_with_interpreted_kernels(simt_lib, tmp_path, monkeypatch):
     """BASELINE config C1 end to end on the CPU: the body of tests/test_gpu_sim_c1.py (the reference's
     src/rbphdslam2dSim.cpp UNCHANGED, once on the reference's filter header and once on the drop-in header over the
