@@ -103,7 +103,7 @@ def robust_mask(wl, eps=1e-3):
     import copy
     from oracle import binding as ob
 
-    def run(scale):
+    def run(scale, geometry=True, stages=(1, 3, 4)):
         w2 = copy.copy(wl)
         w2.cfg = dict(wl.cfg)
         w2.model = dict(wl.model)
@@ -117,14 +117,14 @@ def robust_mask(wl, eps=1e-3):
         w2.model["range_buffer"] = wl.model["range_buffer"] + 2e-5 * scale
         for k in ("innov_thr_range", "innov_thr_bearing"):
             w2.model[k] = wl.model[k] * (1 + 1e-5 * scale)
-        if wl.dim == 3:
+        if wl.dim == 3 and geometry:
             # Victoria Park: the detection probability is a chain of floor / ceil / table look-ups on the
             # scan geometry; move its limits and the pose by far more than an fp32 rounding
             w2.model["bearing_max"] = wl.model["bearing_max"] + 1e-5 * scale
             w2.model["bearing_min"] = wl.model["bearing_min"] - 1e-5 * scale
             w2.model["scan"] = [v + 2e-5 * scale if v > 0 else v for v in wl.model["scan"]]
             w2.pose = wl.pose + np.array([3e-6, -3e-6, 2e-6]) * scale
-        return [ob.run(w2, stage=s, sort_mode=ob.SORT_STABLE) for s in (1, 3, 4)]
+        return [ob.run(w2, stage=s, sort_mode=ob.SORT_STABLE) for s in stages]
 
     base, up, dn = run(0), run(+1), run(-1)
     ok = np.ones(wl.N, dtype=bool)
@@ -145,9 +145,25 @@ def robust_mask(wl, eps=1e-3):
         ok &= (a.unused_mask == b.unused_mask) & (a.unused_mask == c.unused_mask)
         ok &= (a.n_in_fov == b.n_in_fov) & (a.n_in_fov == c.n_in_fov)
     # a merge decision can flip without changing the count (a small component joins another cluster): the merged
-    # weights of the final mixture move then, while moving a threshold alone leaves them untouched
-    a, off = base[2], offsets(base[2].count)
-    for o in (up[2], dn[2]):
+    # weights of the final mixture move then, while moving a threshold alone leaves them untouched.  (Thresholds only:
+    # the Victoria Park runs above also move the geometry, which changes every weight a little.)
+    if wl.dim == 3:
+        final = [run(sc, geometry=False, stages=(4,))[0] for sc in (0, +1, -1)]
+    else:
+        final = [base[2], up[2], dn[2]]
+        # Q3: the likelihood uses the UNWRAPPED bearing difference, so which side of +-pi a predicted bearing is wrapped to
+        # decides whether a measurement near -+pi can pass the gate: a component whose predicted bearing lies within an
+        # fp32 rounding of +-pi is one more discrete decision
+        off_in = offsets(wl.count)
+        for i in range(wl.N):
+            m = wl.mean[off_in[i]:off_in[i + 1]]
+            if len(m):
+                b = np.arctan2(m[:, 1] - wl.pose[i, 1], m[:, 0] - wl.pose[i, 0]) - wl.pose[i, 2]
+                b = np.abs((b + np.pi) % (2 * np.pi) - np.pi)
+                if np.any(np.pi - b < 2e-6):
+                    ok[i] = False
+    a, off = final[0], offsets(final[0].count)
+    for o in final[1:]:
         off_o = offsets(o.count)
         for i in np.nonzero(ok)[0]:
             wa, wo = a.w[off[i]:off[i + 1]], o.w[off_o[i]:off_o[i + 1]]
