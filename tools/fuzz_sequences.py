@@ -27,10 +27,10 @@ for case in range(n_cases):
     resample = bool(rng.random() < 0.5)
     md, fc, poses, Z, nZ = td._scenario(**kw)
     run = dict(pose_cov=[3e-5, 0, 0, 3e-5, 0, 3e-5], Q_lmk=[1e-5, 0, 0, 1e-5],
-               # "resample (almost) always": N - 0.25 rather than N itself — with N the gate N_eff > N is decided by the
+               # "resample (almost) always": 0.98 N rather than N itself — with N the gate N_eff > N is decided by the
                # last bit of 1 / sum w^2 whenever all weights are equal (e.g. every map still empty), which a 1e-13
                # relative difference in the common weight flips
-               neff_threshold=(float(poses.shape[1]) - 0.25 if resample else 0.0), seed48=int(rng.integers(1, 1000)))
+               neff_threshold=(0.98 * float(poses.shape[1]) if resample else 0.0), seed48=int(rng.integers(1, 1000)))
     ref, nres_ref, trace_ref = ob.run_sequence("ref", poses, Z, nZ, md, fc, **run)
     got, nres, trace = ob.run_sequence("b200", poses, Z, nZ, md, fc, precision=64, **run)
     ok = nres == nres_ref and np.array_equal(trace, trace_ref) and np.array_equal(got.count, ref.count)
