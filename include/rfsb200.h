@@ -339,7 +339,9 @@ int rfsb200_permanent(rfsb200_ctx* ctx, const double* A /*[batch][n][n]*/, int32
 int rfsb200_profile_begin(rfsb200_ctx* ctx, int32_t max_updates);
 int rfsb200_profile_read(rfsb200_ctx* ctx, float* kernel_us /*[cap]*/, int32_t cap, int32_t* n);
 
-/* Pinned host memory helpers (so H2D/D2H copies can overlap and run at PCIe speed). */
+/* Pinned host memory helpers (so H2D/D2H copies can overlap and run at PCIe speed, and so that rfsb200_update_host
+ * can let the kernels read / write the buffers directly).  The library remembers the ranges it hands out together with
+ * their device aliases: release them with rfsb200_host_free, not with cudaFreeHost. */
 int rfsb200_host_alloc(void** ptr, uint64_t bytes);
 int rfsb200_host_free(void* ptr);
 

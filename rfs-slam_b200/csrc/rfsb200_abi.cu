@@ -9,6 +9,8 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -496,10 +498,42 @@ int launch_update(rfsb200_ctx* c, int nZ, int out_idx, unsigned flags) {
   return RFSB200_OK;
 }
 
+// Page-locked ranges this library handed out (rfsb200_host_alloc, the ctx staging area) with their device aliases:
+// the per-step buffers of rfsb200_update_host are looked up here instead of asking the driver seven times per step.
+struct PinnedRange { uintptr_t host, dev; size_t bytes; };
+std::mutex g_pinned_mu;
+std::map<uintptr_t, PinnedRange> g_pinned;
+
+void* query_device_alias(const void* host_ptr) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, host_ptr) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  if (a.type != cudaMemoryTypeHost || !a.devicePointer) return nullptr;
+  return a.devicePointer;
+}
+void remember_pinned(void* host_ptr, size_t bytes) {
+  void* dev = query_device_alias(host_ptr);
+  if (!dev) return;
+  std::lock_guard<std::mutex> lk(g_pinned_mu);
+  g_pinned[(uintptr_t)host_ptr] = PinnedRange{(uintptr_t)host_ptr, (uintptr_t)dev, bytes};
+}
+void forget_pinned(void* host_ptr) {
+  std::lock_guard<std::mutex> lk(g_pinned_mu);
+  g_pinned.erase((uintptr_t)host_ptr);
+}
+
 // device-accessible alias of a pinned / registered host pointer (unified addressing), or NULL for pageable memory
 template <typename P>
 P* device_view(P* host_ptr) {
   if (!host_ptr) return nullptr;
+  {
+    const uintptr_t h = (uintptr_t)host_ptr;
+    std::lock_guard<std::mutex> lk(g_pinned_mu);
+    auto it = g_pinned.upper_bound(h);
+    if (it != g_pinned.begin()) {
+      --it;
+      if (h < it->second.host + it->second.bytes) return (P*)(it->second.dev + (h - it->second.host));
+    }
+  }
   cudaPointerAttributes a;
   if (cudaPointerGetAttributes(&a, (const void*)host_ptr) != cudaSuccess) { cudaGetLastError(); return nullptr; }
   if (a.type != cudaMemoryTypeHost || !a.devicePointer) return nullptr;
@@ -508,11 +542,12 @@ P* device_view(P* host_ptr) {
 
 int ensure_pinned(rfsb200_ctx* c, size_t bytes) {
   if (c->hpin_bytes >= bytes) return RFSB200_OK;
-  if (c->hpin) cudaFreeHost(c->hpin);
+  if (c->hpin) { forget_pinned(c->hpin); cudaFreeHost(c->hpin); }
   c->hpin = nullptr;
   c->hpin_bytes = 0;
   CU(c, cudaMallocHost((void**)&c->hpin, bytes));
   c->hpin_bytes = bytes;
+  remember_pinned(c->hpin, bytes);
   return RFSB200_OK;
 }
 
@@ -702,7 +737,7 @@ int rfsb200_destroy(rfsb200_ctx* c) {
   cudaFree(c->sums); cudaFree(c->totals); cudaFree(c->istats); cudaFree(c->ticket);
   cudaFree(c->work_counter); cudaFree(c->stats_out); cudaFree(c->mstats);
   cudaFree(c->stg); cudaFree(c->offs); cudaFree(c->stg_small); cudaFree(c->scan_dev); cudaFree(c->dp_scratch);
-  if (c->hpin) cudaFreeHost(c->hpin);
+  if (c->hpin) { forget_pinned(c->hpin); cudaFreeHost(c->hpin); }
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   for (int k = 0; k < 8; k++) if (c->zev[k]) cudaEventDestroy(c->zev[k]);
@@ -1403,11 +1438,15 @@ int rfsb200_host_alloc(void** ptr, uint64_t bytes) {
   if (!ptr) return fail(nullptr, RFSB200_EINVAL, "NULL argument");
   cudaError_t e = cudaMallocHost(ptr, bytes);
   if (e != cudaSuccess) return fail(nullptr, RFSB200_ENOMEM, "cudaMallocHost(%llu): %s", (unsigned long long)bytes, cudaGetErrorString(e));
+  remember_pinned(*ptr, (size_t)bytes);   // rfsb200_update_host finds its device alias without a driver query
   return RFSB200_OK;
 }
 
 int rfsb200_host_free(void* ptr) {
-  if (ptr) cudaFreeHost(ptr);
+  if (ptr) {
+    forget_pinned(ptr);
+    cudaFreeHost(ptr);
+  }
   return RFSB200_OK;
 }
 

@@ -134,6 +134,33 @@ def test_smoke_body_on_the_interpreted_kernels(simt_lib, capsys):
     assert "smoke OK" in capsys.readouterr().out
 
 
+def test_pageable_buffers_take_the_staged_path_with_the_same_results(simt_lib, monkeypatch):
+    """rfsb200_update_host decides per call: buffers of rfsb200_host_alloc (known ranges) and other page-locked memory
+    are read / written by the kernels, a pageable buffer anywhere sends the whole step through the staged copies"""
+    from rfs_slam_b200 import capi, synth
+    from rfs_slam_b200.phd import PHDUpdater, pinned_array
+    wl = synth.make_workload(N=40, nM=50, nZ=10, use_cluster_process=0, config_id=81)
+    res = []
+    with host.interpreted(sm_count=2):
+        for pinned in (True, False):
+            monkeypatch.setenv("SIMT_PAGEABLE", "0" if pinned else "1")   # what the interpreter's cudaPointerGetAttributes reports
+            alloc = pinned_array if pinned else (lambda shape, dtype=np.float64: np.zeros(shape, dtype))
+            up = PHDUpdater(wl.N, gm_capacity=128, z_capacity=16)
+            up.set_model(wl.model); up.set_filter_cfg(wl.cfg); up.upload_maps(wl.count, wl.mean, wl.cov, wl.w)
+            pose = alloc((wl.N, 3)); pose[:] = wl.pose
+            w_in = alloc((wl.N,)); w_in[:] = wl.weight
+            w_out, mask, nfov = alloc((wl.N,)), alloc((wl.N,), np.uint64), alloc((wl.N,), np.int32)
+            so = up.update_host(pose, wl.pose_cov, w_in, np.ascontiguousarray(wl.Z), flags=capi.UPDATE_FUSED_ALLREDUCE,
+                                w_out=w_out, unused_out=mask, nfov_out=nfov, want_stats=True)
+            res.append((w_out.copy(), mask.copy(), nfov.copy(), so.sum_w, so.n_launches, up.download_maps()))
+            up.close()
+    a, b = res
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]) and a[3] == b[3]
+    assert a[4] == 2 and b[4] == 2            # conversion kernel + update kernel either way (pose_convert / host_in)
+    for x, y in zip(a[5], b[5]):
+        assert np.array_equal(x, y)
+
+
 def test_interpreted_randomised_sweep():
     """tools/fuzz_parity.py --simt: random sizes / thresholds / models for both plugin sets and random CTA shapes,
     fp64 kernels against the oracle, exact structure"""
