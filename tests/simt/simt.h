@@ -139,19 +139,22 @@ struct Cta {
   void* entry_arg = nullptr;
 };
 
-// interpreter state is per host thread: a host thread is one "GPU" that runs its launches one after the other
-inline thread_local Cta* g_cta = nullptr;
+// interpreter state is per host thread: a host thread is one "GPU" that runs its launches one after the other.
+// Hidden visibility lets the compiler address the hot variables relative to the library's own TLS block (one
+// descriptor call per function, -mtls-dialect=gnu2 in simt_build.py, instead of one __tls_get_addr per access).
+#define SIMT_HOT_TLS __attribute__((visibility("hidden")))
+inline thread_local Cta* g_cta SIMT_HOT_TLS = nullptr;
 inline thread_local unsigned char* g_stacks = nullptr;
 inline size_t g_stack_bytes = 256 * 1024;
 inline thread_local int g_stack_count = 0;
-inline thread_local uint64_t g_switches = 0;   // statistics
+inline thread_local uint64_t g_switches SIMT_HOT_TLS = 0;   // statistics
 inline thread_local const char* g_kernel_name = "";
 
 }  // namespace simt
 
 // the CUDA built-in coordinates (set by the scheduler whenever a fiber is resumed)
 using dim3 = simt::Dim3;
-inline thread_local simt::Dim3 threadIdx, blockIdx, blockDim, gridDim;
+inline thread_local simt::Dim3 threadIdx SIMT_HOT_TLS, blockIdx SIMT_HOT_TLS, blockDim SIMT_HOT_TLS, gridDim SIMT_HOT_TLS;
 
 namespace simt {
 

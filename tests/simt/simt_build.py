@@ -62,7 +62,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     cmd = [os.environ.get("CXX", "g++"), "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-fno-strict-aliasing",
            # the product library may already be loaded RTLD_GLOBAL in the same process (same symbol names):
            # bind this library's references to its own definitions
-           "-Wl,-Bsymbolic",
+           "-Wl,-Bsymbolic", "-mtls-dialect=gnu2",
            "-DRFSB200_SIMT_HOST", "-Wno-unknown-pragmas", "-Wno-attributes", "-Wno-subobject-linkage",
            "-I", HERE, "-I", src, "-include", os.path.join(HERE, "simt.h"),
            os.path.join(src, "rfsb200_abi.cpp"), "-o", LIB + ".tmp"]
