@@ -27,9 +27,11 @@ bad = 0
 for case in range(n_cases):
     vp = bool(rng.random() < 0.4)
     sc = int(rng.random() < 0.4)
-    N = int(rng.integers(8, 64))
+    # (the interpreted sweep also covers the corners: one particle, the full 64-measurement batch; same number of draws,
+    #  so the cases of the GPU sweep are unchanged)
+    N = int(rng.integers(1 if SIMT else 8, 64))
     nM = int(rng.integers(1, 180))
-    nZ = int(rng.integers(1, 40 if not vp else 24))
+    nZ = int(rng.integers(1, (65 if SIMT else 40) if not vp else (33 if SIMT else 24)))
     cfg = dict(merging_threshold=float(rng.choice([0.3, 0.5, 1.0, 2.0])), merging_cov_inflation_factor=float(rng.choice([1.0, 1.5])),
                pruning_threshold=float(rng.choice([0.003, 0.01, 0.05])), eval_point_count=int(rng.choice([0, 1, 4, 15, 24])),
                eval_point_gaussian_weight=float(rng.choice([0.2, 0.75])), new_gaussian_create_innov_md_threshold=float(rng.choice([2.0, 3.0, 5.0])),
