@@ -169,7 +169,7 @@ def robust_mask(wl, eps=1e-3):
         off_o = offsets(o.count)
         for i in np.nonzero(ok)[0]:
             wa, wo = a.w[off[i]:off[i + 1]], o.w[off_o[i]:off_o[i + 1]]
-            if not np.allclose(wa, wo, rtol=1e-9, atol=1e-12):
+            if len(wa) != len(wo) or not np.allclose(wa, wo, rtol=1e-9, atol=1e-12):
                 ok[i] = False
     return ok
 
