@@ -1,6 +1,6 @@
 // common.cuh — sm_100a building blocks used by the PHD update kernels:
-// 1-D TMA bulk copies (cp.async.bulk, SASS UBLKCP) completing on an mbarrier, bulk-group
-// stores, proxy fences, warp reductions / scans.
+// 1-D TMA bulk copies (cp.async.bulk, SASS UBLKCP) completing on an mbarrier, L2 bulk prefetch,
+// proxy fences, warp reductions / scans.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -60,18 +60,10 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src
       "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
       : "memory");
 }
-// shared -> global, tracked by the per-thread bulk async-group.
-__device__ __forceinline__ void tma_store_1d(void* gmem_dst, const void* smem_src, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst),
-               "r"(smem_u32(smem_src)), "r"(bytes)
-               : "memory");
+// global -> L2 only (no destination, no completion): warms the lines a later bulk load will fetch
+__device__ __forceinline__ void tma_prefetch_l2(const void* gmem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem_src), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-// wait until the bulk stores of this thread have finished READING shared memory
-__device__ __forceinline__ void tma_store_wait_read() {
-  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-}
-__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 // order generic-proxy shared-memory accesses against the async proxy (TMA)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 

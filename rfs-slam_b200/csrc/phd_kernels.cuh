@@ -22,13 +22,13 @@
 namespace rfsb200 {
 
 constexpr int WARPS_PER_CTA = 4;       // default; the 2-D multi-feature kernel runs 5 (see mf_region_bytes)
-constexpr int MAX_WARPS_PER_CTA = 16;
+constexpr int MAX_WARPS_PER_CTA = 20;
 constexpr int MAX_Z = 64;
 constexpr int MAX_EVAL = 32;
 constexpr int DP_MAXB = 7;     // assignment-sum DP in shared memory: the smaller side of a partition has <= 7 members
 constexpr int DP_GMAXB = 15;   // ... in the per-warp global workspace (KParams::dp_scratch): <= 15 members
 constexpr int MAX_COMP = 96;   // connected components of the (eval point, measurement) graph
-constexpr int MAX_PAIRS = 160; // merge: passing pairs (+ cluster links) kept per particle
+constexpr int MAX_PAIRS = 144; // merge: passing pairs (+ cluster links) kept per particle
 
 // flag bits written per particle
 constexpr int FLAG_OVERFLOW = 1;
@@ -296,9 +296,10 @@ __device__ void merge_bruteforce(T* cur, int W, int n, T t2, T f, int lane) {
 constexpr int MERGE_OK = 0;
 constexpr int MERGE_FALLBACK = 1;   // nothing modified: run the exhaustive merge instead
 constexpr int MAX_CLUSTERS = 64;
-constexpr int MAX_MEMBERS = 12;
 constexpr int MAX_ROWLOG = 48;
+constexpr int MEMBERS_CAP = 2 * MAX_PAIRS;   // members of all clusters together (every member is an end of a passing pair)
 constexpr int MAX_MERGE_ROUNDS = 4;
+constexpr int MERGE_MSTART = (MAX_CLUSTERS + 2 + 3) & ~3;   // entries of memberStart[]
 constexpr unsigned NO_OWNER = 0xffffffffu;
 
 template <typename T>
@@ -306,38 +307,45 @@ struct XY { T x, y; };
 
 template <typename T>
 struct MergeScratch {
-  unsigned* label;           // [W] cluster label (smallest member index) / NO_OWNER   (aliases aux)
+  unsigned* label;           // [W] cluster label (smallest member index) / NO_OWNER   (aliases aux; M2: candidate list)
   unsigned short* order;     // [W] cell order -> component index
-  unsigned short* slot;      // [W] M1/M2: cell of a component; M3+: cluster slot of a cluster head
   unsigned short* cellStart; // [264]
   unsigned* counters;        // [4]: 0 = number of pairs, 1 = logged rows
   // --- region that is dead outside the merge (the prune sort keys alias all of it) ---
   XY<T>* sxy;                // [W] M1/M2 only: (x, y) in cell order   } same storage
-  T* rowLog;                 // [MAX_ROWLOG][6]                         } (rowLog, members, rowIdx
-  unsigned short* members;   // [MAX_CLUSTERS][MAX_MEMBERS]             }  are M3+ only)
+  unsigned short* members;   // [MEMBERS_CAP] members of cluster c at memberStart[c] .. memberStart[c + 1]   } (M3+ only)
+  unsigned short* memberStart; // [MAX_CLUSTERS + 2]                    }
+  T* rowLog;                 // [MAX_ROWLOG][6]                         }
   unsigned short* rowIdx;    // [MAX_ROWLOG]                            }
-  unsigned* pairs;           // [MAX_PAIRS]
+  unsigned short* headPre;   // [32] cluster heads in front of each word of headBits   }
+  unsigned* pairs;           // [MAX_PAIRS]   (M1: the scatter cursors, 128 words)
   unsigned* memberCount;     // [MAX_CLUSTERS]
-  unsigned* deadBits;        // [32] bit per component (W <= 1024)
+  unsigned* deadBits;        // [W / 32] bit per component
+  unsigned* headBits;        // [W / 32] cluster heads
+  unsigned* seenBits;        // [W / 32] first-visit marks of the pair ends
+  int nwords;                // W / 32
   T* keys;                   // [W] prune sort keys (fp64) / packed u64 keys (fp32)
 };
 
 template <typename T>
 __host__ __device__ inline int merge_region_a_bytes(int W) {
-  const int a = MAX_ROWLOG * 6 * (int)sizeof(T) + MAX_CLUSTERS * MAX_MEMBERS * 2 + MAX_ROWLOG * 2;
+  const int rl = (MAX_ROWLOG * 6 * (int)sizeof(T) + 7) & ~7;
+  const int a = rl + MEMBERS_CAP * 2 + MERGE_MSTART * 2 + MAX_ROWLOG * 2 + 32 * 2;
   const int b = 2 * W * (int)sizeof(T);
   return ((a > b ? a : b) + 15) & ~15;
 }
 template <typename T>
 __host__ __device__ inline int merge_only_bytes(int W) {
-  const int a = merge_region_a_bytes<T>(W) + MAX_PAIRS * 4 + MAX_CLUSTERS * 4 + 32 * 4;
+  const int a = merge_region_a_bytes<T>(W) + MAX_PAIRS * 4 + MAX_CLUSTERS * 4 + 3 * ((W + 31) >> 5) * 4;
   const int b = W * 8;   // prune sort keys: T[W] (fp64) or packed u64[W] (fp32)
   return ((a > b ? a : b) + 15) & ~15;
 }
+// bytes in front of the merge-only region: order u16[W] | cellStart u16[264] | counters u32[4]
+__host__ __device__ inline int merge_head_bytes(int W) { return (2 * W + 264 * 2 + 16 + 15) & ~15; }
 // label[] is the caller's aux array and is not counted here
 template <typename T>
 __host__ __device__ inline int merge_scratch_bytes(int W) {
-  return (int)((2 * W * 2 + 264 * 2 + 16 + 15) & ~15) + merge_only_bytes<T>(W);
+  return merge_head_bytes(W) + merge_only_bytes<T>(W);
 }
 
 template <typename T>
@@ -346,17 +354,21 @@ __device__ __forceinline__ MergeScratch<T> carve_merge_scratch(unsigned char* ba
   m.label = aux;
   m.counters = reinterpret_cast<unsigned*>(base);
   m.order = reinterpret_cast<unsigned short*>(m.counters + 4);
-  m.slot = m.order + W;
-  m.cellStart = m.slot + W;
-  unsigned char* r = base + ((2 * W * 2 + 264 * 2 + 16 + 15) & ~15);
+  m.cellStart = m.order + W;
+  unsigned char* r = base + merge_head_bytes(W);
   m.keys = reinterpret_cast<T*>(r);
   m.sxy = reinterpret_cast<XY<T>*>(r);
   m.rowLog = reinterpret_cast<T*>(r);
-  m.members = reinterpret_cast<unsigned short*>(m.rowLog + MAX_ROWLOG * 6);
-  m.rowIdx = m.members + MAX_CLUSTERS * MAX_MEMBERS;
+  m.members = reinterpret_cast<unsigned short*>(r + ((MAX_ROWLOG * 6 * (int)sizeof(T) + 7) & ~7));
+  m.memberStart = m.members + MEMBERS_CAP;
+  m.rowIdx = m.memberStart + MERGE_MSTART;
+  m.headPre = m.rowIdx + MAX_ROWLOG;
   m.pairs = reinterpret_cast<unsigned*>(r + merge_region_a_bytes<T>(W));
   m.memberCount = m.pairs + MAX_PAIRS;
+  m.nwords = (W + 31) >> 5;
   m.deadBits = m.memberCount + MAX_CLUSTERS;
+  m.headBits = m.deadBits + m.nwords;
+  m.seenBits = m.headBits + m.nwords;
   return m;
 }
 
@@ -393,20 +405,25 @@ __device__ __forceinline__ bool lane_absorb(MergeRow<T>& r, const T* cur, int W,
   return true;
 }
 
+// 16-byte fill of a word array (n4 = number of uint4 entries) by the warp
+struct alignas(16) Word4 { unsigned a, b, c, d; };
+__device__ __forceinline__ void warp_fill4(void* dst, unsigned v, int n4, int lane) {
+  Word4* d = reinterpret_cast<Word4*>(dst);
+  const Word4 q{v, v, v, v};
+  for (int k = lane; k < n4; k += 32) d[k] = q;
+}
+
 template <typename T>
 __device__ int merge_clustered(T* cur, const MergeScratch<T>& ms, int W, int n, T t2, T f, bool has_wprev,
                                int lane, unsigned (&mstat)[8], T xmin, T xmax, T trmax, bool bad) {
   // ---- M1: counting sort on cells.  xmin / xmax / trmax (largest trace(P)) / bad (some covariance
   //      is not PD) over the n components were gathered by the corrector (warp-uniform values). ----
-  for (int j = lane; j < n; j += 32) ms.label[j] = NO_OWNER;
-  for (int c = lane; c < 132; c += 32) reinterpret_cast<unsigned*>(ms.cellStart)[c] = 0u;
-  for (int c = lane; c < MAX_CLUSTERS; c += 32) ms.memberCount[c] = 0u;
-  ms.deadBits[lane] = 0u;
-  if (lane < 4) ms.counters[lane] = 0u;
   if (bad) { mstat[0]++; return MERGE_FALLBACK; }   // a non-PD covariance has no finite reach
   const T tt = t2 * T(1.001);                // reach^2 of a component = tt * trace(P)
   const T rmax2 = trmax * tt;
   if (!(rmax2 < M<T>::inf()) || !(xmax - xmin < M<T>::inf())) { mstat[0]++; return MERGE_FALLBACK; }
+  const unsigned lt = (1u << lane) - 1u;
+  for (int c = lane; c < 132; c += 32) reinterpret_cast<unsigned*>(ms.cellStart)[c] = 0u;
   const T span = xmax - xmin;
   const T rmax = M<T>::sqrt_(rmax2) * T(1.001);
   T cw = span * T(1.0 / 255.5);
@@ -419,9 +436,8 @@ __device__ int merge_clustered(T* cur, const MergeScratch<T>& ms, int W, int n, 
   };
   __syncwarp();
   for (int j = lane; j < n; j += 32) {   // histogram at cell+1; 16-bit counters packed in words
-    const int c = cell_of(cur[j]);
-    ms.slot[j] = (unsigned short)c;
-    atomicAdd(reinterpret_cast<unsigned*>(ms.cellStart) + ((c + 1) >> 1), ((c + 1) & 1) ? 0x10000u : 1u);
+    const int c1 = cell_of(cur[j]) + 1;
+    atomicAdd(reinterpret_cast<unsigned*>(ms.cellStart) + (c1 >> 1), (c1 & 1) ? 0x10000u : 1u);
   }
   __syncwarp();
   {  // inclusive prefix over entries 1..256: lane owns 8 consecutive entries
@@ -439,81 +455,88 @@ __device__ int merge_clustered(T* cur, const MergeScratch<T>& ms, int W, int n, 
   }
   // scatter: per-cell cursors (cell c -> next free position), 16-bit counters packed in words
   unsigned* cursor = ms.pairs;   // the pair list is not in use yet (MAX_PAIRS >= 128 words)
-  for (int c = lane; c < 128; c += 32) {
-    cursor[c] = (unsigned)ms.cellStart[2 * c] | ((unsigned)ms.cellStart[2 * c + 1] << 16);
-  }
+  for (int c = lane; c < 128; c += 32) cursor[c] = reinterpret_cast<const unsigned*>(ms.cellStart)[c];
   __syncwarp();
   for (int j = lane; j < n; j += 32) {
-    const int c = ms.slot[j];
+    XY<T> q;
+    q.x = cur[j]; q.y = cur[W + j];
+    const int c = cell_of(q.x);
     const unsigned old = atomicAdd(cursor + (c >> 1), (c & 1) ? 0x10000u : 1u);
     const unsigned pos = (c & 1) ? (old >> 16) : (old & 0xffffu);
     ms.order[pos] = (unsigned short)j;
-    XY<T> q;
-    q.x = cur[j]; q.y = cur[W + j];
     ms.sxy[pos] = q;
   }
   __syncwarp();
   // (the order inside a cell is schedule dependent; nothing below depends on it: M2 visits every
   //  pair of one cell or of adjacent cells exactly once, M4 takes minima over index)
-  // ---- M2: candidate pairs by distance, then the exact test lane-parallel over the candidates ------
+  // ---- M2: candidate pairs ------------------------------------------------------------------------
+  //  a) by distance: position s against the positions behind it up to the end of the next cell, four at a time,
+  //     branch-free; the hits (|d|^2 <= largest reach^2) are compacted into a list in label[] (not in use yet)
+  //  b) lane-parallel over that list: the two components' own reaches, then the exact test on the original
+  //     parameters -> list of passing pairs
+  unsigned* cand = ms.label;   // [W] (position s << 16) | position t
+  int ncand = 0;
   for (int sb = 0; sb < n; sb += 32) {
     const int s = sb + lane;
-    if (s < n) {
-      const XY<T> me = ms.sxy[s];
-      const int j = ms.order[s];
-      const int end = ms.cellStart[ms.slot[j] + 2];
-      auto consider = [&](int t, const XY<T>& q) {
+    const int sc = s < n ? s : n - 1;
+    const XY<T> me = ms.sxy[sc];
+    const int end = s < n ? (int)ms.cellStart[cell_of(me.x) + 2] : 0;
+    for (int t0 = s + 1; __any_sync(FULL, t0 < end); t0 += 4) {
+      bool h[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int t = t0 + u;
+        const XY<T> q = ms.sxy[t < n ? t : n - 1];
         const T dx = q.x - me.x, dy = q.y - me.y;
-        const T d2 = dx * dx + dy * dy;
-        if (t < end && !(d2 > rmax2)) {
-          const int k = ms.order[t];
-          const T rj = tt * (cur[2 * W + j] + cur[4 * W + j]);
-          if (!(d2 > M<T>::max_(rj, tt * (cur[2 * W + k] + cur[4 * W + k])))) {
-            const unsigned slotq = atomicAdd(&ms.counters[0], 1u);
-            const int a = j < k ? j : k, b = j < k ? k : j;
-            if (slotq < (unsigned)MAX_PAIRS) ms.pairs[slotq] = ((unsigned)a << 16) | (unsigned)b;
-          }
+        h[u] = (t < end) && !(dx * dx + dy * dy > rmax2);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const unsigned bh = __ballot_sync(FULL, h[u]);
+        if (bh) {
+          const int pos = ncand + __popc(bh & lt);
+          if (h[u] && pos < W) cand[pos] = ((unsigned)s << 16) | (unsigned)(t0 + u);
+          ncand += __popc(bh);
         }
-      };
-      // the usual case is 0-3 components behind s in its two cells: look at four positions at once
-      // (loads issued together; positions past `end` are ignored), then a loop for the rare rest
-      {
-        const int t0 = s + 1;
-        const int c1 = t0 + 1 < n ? t0 + 1 : n - 1, c2 = t0 + 2 < n ? t0 + 2 : n - 1, c3 = t0 + 3 < n ? t0 + 3 : n - 1;
-        const int c0 = t0 < n ? t0 : n - 1;
-        const XY<T> q0 = ms.sxy[c0], q1 = ms.sxy[c1], q2 = ms.sxy[c2], q3 = ms.sxy[c3];
-        consider(t0, q0);
-        consider(t0 + 1, q1);
-        consider(t0 + 2, q2);
-        consider(t0 + 3, q3);
       }
-      for (int t = s + 5; t < end; t++) consider(t, ms.sxy[t]);
     }
-    __syncwarp();
   }
-  {
-    const int ncand = (int)ms.counters[0];
-    if (ncand > MAX_PAIRS) { mstat[1]++; return MERGE_FALLBACK; }
-    int npass = 0;
-    for (int base = 0; base < ncand; base += 32) {
-      const int k = base + lane;
-      unsigned key = 0;
-      bool pass = false;
-      if (k < ncand) {
-        key = ms.pairs[k];
-        pass = merge_test_pair(cur, W, (int)(key >> 16), (int)(key & 0xffffu), t2);
+  __syncwarp();
+  if (ncand > W) { mstat[1]++; return MERGE_FALLBACK; }
+  int npass = 0;
+  for (int base = 0; base < ncand; base += 32) {
+    const int q = base + lane;
+    unsigned key = 0;
+    bool pass = false;
+    if (q < ncand) {
+      const unsigned st = cand[q];
+      const int j = ms.order[st >> 16], k = ms.order[st & 0xffffu];
+      const XY<T> a = ms.sxy[st >> 16], b = ms.sxy[st & 0xffffu];
+      const T dx = b.x - a.x, dy = b.y - a.y;
+      const T d2 = dx * dx + dy * dy;
+      const T rj = tt * (cur[2 * W + j] + cur[4 * W + j]), rk = tt * (cur[2 * W + k] + cur[4 * W + k]);
+      if (!(d2 > M<T>::max_(rj, rk))) {
+        const int lo = j < k ? j : k, hi = j < k ? k : j;
+        key = ((unsigned)lo << 16) | (unsigned)hi;
+        pass = merge_test_pair(cur, W, lo, hi, t2);
       }
-      __syncwarp();
-      const unsigned bp = __ballot_sync(FULL, pass);
-      if (pass) ms.pairs[npass + __popc(bp & ((1u << lane) - 1u))] = key;
+    }
+    const unsigned bp = __ballot_sync(FULL, pass);
+    if (bp) {
+      const int pos = npass + __popc(bp & lt);
+      if (pass && pos < MAX_PAIRS) ms.pairs[pos] = key;
       npass += __popc(bp);
     }
-    __syncwarp();
-    if (lane == 0) ms.counters[0] = (unsigned)npass;
-    __syncwarp();
-    if (npass == 0) return MERGE_OK;
-    mstat[5] += (unsigned)npass;
   }
+  if (npass == 0) return MERGE_OK;
+  if (npass > MAX_PAIRS) { mstat[1]++; return MERGE_FALLBACK; }
+  mstat[5] += (unsigned)npass;
+  // the candidate list is dead: label[] takes its array over
+  warp_fill4(ms.label, NO_OWNER, W >> 2, lane);
+  if (lane < 4) ms.counters[lane] = lane == 0 ? (unsigned)npass : 0u;
+  for (int c = lane; c < MAX_CLUSTERS; c += 32) ms.memberCount[c] = 0u;
+  if (lane < ms.nwords) { ms.deadBits[lane] = 0u; ms.headBits[lane] = 0u; ms.seenBits[lane] = 0u; }
+  __syncwarp();
 
   for (int round = 0; round < MAX_MERGE_ROUNDS; round++) {
     const int np = (int)ms.counters[0];
@@ -540,28 +563,63 @@ __device__ int merge_clustered(T* cur, const MergeScratch<T>& ms, int W, int n, 
       __syncwarp();
       if (!__any_sync(FULL, changed)) break;
     }
-    // ---- cluster slots (heads in ascending order) and member lists ----------------------------------
-    int nclusters = 0;
-    for (int jb = 0; jb < n; jb += 32) {
-      const int j = jb + lane;
-      const bool head = (j < n) && (ms.label[j] == (unsigned)j);
-      const unsigned bh = __ballot_sync(FULL, head);
-      if (head) ms.slot[j] = (unsigned short)(nclusters + __popc(bh & ((1u << lane) - 1u)));
-      nclusters += __popc(bh);
+    // ---- cluster slots and member lists, through the ends of the pairs (every member is one): the first visit
+    //      of a component is detected on a bitmap.  Slot of a cluster = rank of its head among the heads. --------
+    for (int k = lane; k < np; k += 32) {
+      const unsigned key = ms.pairs[k];
+#pragma unroll
+      for (int side = 0; side < 2; side++) {
+        const unsigned e = side ? (key & 0xffffu) : (key >> 16);
+        if (ms.label[e] == e) atomicOr(&ms.headBits[e >> 5], 1u << (e & 31));
+      }
+    }
+    __syncwarp();
+    int nclusters;
+    {
+      const int cnt = lane < ms.nwords ? __popc(ms.headBits[lane]) : 0;
+      const int incl = warp_incl_scan(cnt, lane);
+      nclusters = __shfl_sync(FULL, incl, 31);
+      ms.headPre[lane] = (unsigned short)(incl - cnt);   // heads in front of word `lane`
     }
     if (nclusters > MAX_CLUSTERS) { mstat[2]++; return MERGE_FALLBACK; }
     __syncwarp();
-    bool big = false;
-    for (int j = lane; j < n; j += 32) {
-      const unsigned l = ms.label[j];
-      if (l != NO_OWNER) {
-        const int sl = ms.slot[l];
-        const unsigned pos = atomicAdd(&ms.memberCount[sl], 1u);
-        if (pos < (unsigned)MAX_MEMBERS) ms.members[sl * MAX_MEMBERS + pos] = (unsigned short)j;
-        else big = true;
+    auto slot_of = [&](unsigned head) -> int {
+      return (int)ms.headPre[head >> 5] + __popc(ms.headBits[head >> 5] & ((1u << (head & 31)) - 1u));
+    };
+    for (int k = lane; k < np; k += 32) {   // member counts
+      const unsigned key = ms.pairs[k];
+#pragma unroll
+      for (int side = 0; side < 2; side++) {
+        const unsigned e = side ? (key & 0xffffu) : (key >> 16);
+        const unsigned bit = 1u << (e & 31);
+        if (!(atomicOr(&ms.seenBits[e >> 5], bit) & bit)) atomicAdd(&ms.memberCount[slot_of(ms.label[e])], 1u);
       }
     }
-    if (__any_sync(FULL, big)) { mstat[3]++; return MERGE_FALLBACK; }
+    __syncwarp();
+    {  // exclusive scan of the counts -> memberStart; the counts become the fill cursors
+      const int c0 = 2 * lane < nclusters ? (int)ms.memberCount[2 * lane] : 0;
+      const int c1 = 2 * lane + 1 < nclusters ? (int)ms.memberCount[2 * lane + 1] : 0;
+      const int incl = warp_incl_scan(c0 + c1, lane);
+      const int ex = incl - (c0 + c1);
+      ms.memberStart[2 * lane] = (unsigned short)ex;
+      ms.memberStart[2 * lane + 1] = (unsigned short)(ex + c0);
+      if (lane == 31) ms.memberStart[64] = (unsigned short)incl;
+      ms.memberCount[2 * lane] = (unsigned)ex;
+      ms.memberCount[2 * lane + 1] = (unsigned)(ex + c0);
+    }
+    __syncwarp();
+    for (int k = lane; k < np; k += 32) {   // fill (a set bit is cleared by its first visitor)
+      const unsigned key = ms.pairs[k];
+#pragma unroll
+      for (int side = 0; side < 2; side++) {
+        const unsigned e = side ? (key & 0xffffu) : (key >> 16);
+        const unsigned bit = 1u << (e & 31);
+        if (atomicAnd(&ms.seenBits[e >> 5], ~bit) & bit) {
+          const unsigned pos = atomicAdd(&ms.memberCount[slot_of(ms.label[e])], 1u);
+          ms.members[pos] = (unsigned short)e;
+        }
+      }
+    }
     __syncwarp();
     // ---- M4: one lane per cluster; read-only on the mixture -----------------------------------------
     bool conflict = false, logfull = false;
@@ -569,8 +627,8 @@ __device__ int merge_clustered(T* cur, const MergeScratch<T>& ms, int W, int n, 
     for (int cb = 0; cb < nclusters; cb += 32) {
       const int sl = cb + lane;
       if (sl < nclusters) {
-        unsigned short* mem = ms.members + sl * MAX_MEMBERS;
-        const int nm = (int)ms.memberCount[sl];
+        unsigned short* mem = ms.members + ms.memberStart[sl];
+        const int nm = (int)ms.memberStart[sl + 1] - (int)ms.memberStart[sl];
         for (int u = 1; u < nm; u++) {   // members ascending
           const unsigned short v = mem[u];
           int q = u - 1;
@@ -668,16 +726,22 @@ __device__ int merge_clustered(T* cur, const MergeScratch<T>& ms, int W, int n, 
         cur[5 * W + i] = e[5];
         if (has_wprev) cur[6 * W + i] = T(0);
       }
-      for (int j = lane; j < n; j += 32)
-        if (is_dead(j)) cur[5 * W + j] = T(-1);   // hole
+      {  // holes: lane = word of the death bitmap
+        unsigned d = lane < ms.nwords ? ms.deadBits[lane] : 0u;
+        while (d) {
+          const int j = lane * 32 + __ffs(d) - 1;
+          d &= d - 1;
+          cur[5 * W + j] = T(-1);
+        }
+      }
       __syncwarp();
       return MERGE_OK;
     }
     // interacting clusters: their heads were linked in the pair list; reset and go round again
     mstat[4]++;
-    for (int j = lane; j < n; j += 32) ms.label[j] = NO_OWNER;
+    warp_fill4(ms.label, NO_OWNER, W >> 2, lane);
     for (int c = lane; c < MAX_CLUSTERS; c += 32) ms.memberCount[c] = 0u;
-    ms.deadBits[lane] = 0u;
+    if (lane < ms.nwords) { ms.deadBits[lane] = 0u; ms.headBits[lane] = 0u; ms.seenBits[lane] = 0u; }
     if (lane == 0) ms.counters[1] = 0u;
     __syncwarp();
     if ((int)ms.counters[0] > MAX_PAIRS) { mstat[1]++; return MERGE_FALLBACK; }
@@ -1174,8 +1238,9 @@ __host__ __device__ inline int mf_region_bytes(int W, int n_eval, int zcap) {
 template <typename T>
 __host__ __device__ inline int warp_bytes_for(int W, int multi_feature, int region_bytes) {
   const int planes = multi_feature ? 7 : 6;   // MF carries weight_prev as a 7th plane
-  int b = planes * W * (int)sizeof(T) + region_bytes + W * 4 + MAX_Z * (int)sizeof(T) + MAX_EVAL * 4 + 16;
-  return (b + 127) & ~127;
+  // colsum[] aliases the merge's cell table (dead outside the merge); evalIdx[] exists in multi-feature mode only
+  int b = planes * W * (int)sizeof(T) + region_bytes + W * 4 + (multi_feature ? MAX_EVAL * 4 : 0) + 16;
+  return (b + 15) & ~15;
 }
 constexpr int NBINS = 256;   // bins of the range / bearing window tables
 // Z block: (zr,zb) pairs T[2*MAX_Z] | range table u64[NBINS+1] | bearing table u64[NBINS+1] | bin params T[4] | bins u8[2*MAX_Z]
@@ -1184,8 +1249,13 @@ __host__ __device__ inline int z_bytes() {
   return (int)((2 * MAX_Z * sizeof(T) + 2 * (NBINS + 1) * 8 + 4 * sizeof(T) + 2 * MAX_Z + 127) & ~127);
 }
 
+// threads per CTA the kernel is compiled for: the fp32 single-cluster kernel fits 96 registers (20 warps per SM),
+// the multi-feature and the fp64 kernels need 128 (16 warps)
 template <typename T, bool MF>
-__global__ void __launch_bounds__(512, 1)
+constexpr int update_max_threads() { return (sizeof(T) == 4 && !MF) ? 32 * MAX_WARPS_PER_CTA : 512; }
+
+template <typename T, bool MF>
+__global__ void __launch_bounds__((update_max_threads<T, MF>()), 1)
 phd_update_kernel(const __grid_constant__ KParams<T> p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
@@ -1204,9 +1274,9 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
   unsigned char* after = reinterpret_cast<unsigned char*>(bufA + NPL * W);
   unsigned* aux = reinterpret_cast<unsigned*>(after + (MF ? p.mf_bytes : merge_scratch_bytes<T>(W)));  // [W]
   const MergeScratch<T> ms = carve_merge_scratch<T>(after, aux, W);
-  T* colsum = reinterpret_cast<T*>(aux + W);                  // [MAX_Z]
-  int* evalIdx = reinterpret_cast<int*>(colsum + MAX_Z);      // [MAX_EVAL]
-  uint64_t* bar = reinterpret_cast<uint64_t*>(evalIdx + MAX_EVAL);
+  T* colsum = reinterpret_cast<T*>(ms.cellStart);             // [MAX_Z] S2 / S3 only (528 bytes; the merge's table is dead)
+  int* evalIdx = reinterpret_cast<int*>(aux + W);             // [MAX_EVAL] multi-feature mode only
+  uint64_t* bar = reinterpret_cast<uint64_t*>(evalIdx + (MF ? MAX_EVAL : 0));
   unsigned char* mfs = after;   // multi-feature stages reuse the work region (see mf_region_bytes)
 
   // ---- the measurement batch and the corrector's window tables (once per CTA) ------------------
@@ -1275,12 +1345,14 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
   int max_out = 0, n_over = 0, n_murty = 0, n_fallback = 0;
   unsigned mstat[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // merge statistics: fallbacks by reason, pairs, clusters
 
-  while (true) {
-    // dynamic particle queue: one atomic per particle, broadcast to the warp
-    int pi = 0;
-    if (lane == 0) pi = (int)atomicAdd(p.work_counter, 1u);
-    pi = __shfl_sync(FULL, pi, 0);
-    if (pi >= p.N) break;
+  // dynamic particle queue: one atomic per particle (lane 0), broadcast to the warp.  The NEXT particle is drawn
+  // while the current one is being merged, and its planes are prefetched into L2 before the current one is stored,
+  // so neither the atomic nor the HBM latency of the bulk loads sits on the warp's critical path.
+  int pi = 0;
+  if (lane == 0) pi = (int)atomicAdd(p.work_counter, 1u);
+  pi = __shfl_sync(FULL, pi, 0);
+  while (pi < p.N) {
+    int pi_next = 0;   // lane 0 only until the end of the iteration
 
     const double w_prev_particle = p.w_in[pi];
     T* cur = bufA;
@@ -1322,7 +1394,9 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
     // widened windows hold no measurement is finished here.  The others are queued for S1b.
     unsigned short* candIdx = ms.order;   // [W] (free until the merge)
     T* candW = ms.keys;                    // [W] pre-update weight of the queued components
-    int ncand = 0;
+    // components under the sensing-limit heuristic of S4 (few): their indices; aux[m] = (first child << 8) | children
+    unsigned short* fixList = reinterpret_cast<unsigned short*>(ms.keys + W);   // [W] (behind candW, inside the work region)
+    int ncand = 0, nfix = 0;
     // statistics the merge needs over all n components (gathered here while the data is in registers)
     T g_xmin = M<T>::inf(), g_xmax = -M<T>::inf(), g_trmax = T(0);
     bool g_bad = false;
@@ -1330,7 +1404,7 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
     const bool pc_ok = (c00 >= T(0)) && (c11 >= T(0)) && (c22 >= T(0));
     for (int base = 0; base < nM; base += 32) {
       const int m = base + lane;
-      bool queue = false;
+      bool queue = false, fix = false;
       T w = 0;
       if (m < nM) {
         const T x = cur[m], y = cur[W + m];
@@ -1361,9 +1435,8 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
         // missed-detection weight (:686-706); the sensing-limit heuristic is patched in S4,
         // which still finds the pre-update weight of the flagged components in the weight plane
         if (MF) cur[6 * W + m] = w;              // weight_prev (only importanceWeighting reads it)
-        const bool fix = close && (w > p.birth_w);
+        fix = close && (w > p.birth_w);
         cur[5 * W + m] = fix ? w : (T(1) - Pd) * w;
-        aux[m] = fix ? 1u : 0u;
         if (Pd != T(0) && inrange) {              // measure() returns false outside [rmin,rmax]
           queue = true;
           if (pd && pc_ok) {
@@ -1387,6 +1460,14 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
         candW[pos] = w;
       }
       ncand += __popc(bq);
+      const unsigned bf = __ballot_sync(FULL, fix);
+      if (bf) {
+        if (fix) {
+          fixList[nfix + __popc(bf & ((1u << lane) - 1u))] = (unsigned short)m;
+          aux[m] = 0u;   // no children (S1b fills it in for the queued ones)
+        }
+        nfix += __popc(bf);
+      }
     }
     __syncwarp();
     // S1b: the queued components (ascending m) — EKF innovation, exact gate, posterior Gaussians
@@ -1397,6 +1478,7 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
       T x = 0, y = 0, pxx = 0, pxy = 0, pyy = 0;
       T zr_hat = 0, zb_hat = 0, i00 = 0, i01 = 0, i11 = 0, norm = 0, Pdw = 0;
       T hp00 = 0, hp01 = 0, hp10 = 0, hp11 = 0;
+      bool fixq = false;
       if (q < ncand) {
         m = candIdx[q];
         const T w = candW[q];
@@ -1407,6 +1489,7 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
         const T r = M<T>::sqrt_(r2);
         const bool close = (r >= p.rmax - p.rbuf) || (r <= p.rmin + p.rbuf);   // in range here
         const T Pd = close ? T(1) : p.Pd;
+        fixq = close && (w > p.birth_w);
         {
           const T invr = T(1) / r;
           const T c = dx * invr, s = dy * invr;
@@ -1469,6 +1552,11 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
       const int incl = warp_incl_scan(cnt, lane);
       int off = nM + nS + incl - cnt;
       nS += __shfl_sync(FULL, incl, 31);
+      if (cnt && fixq) {   // children of a component under the sensing-limit heuristic: [off, off + stored)
+        const int room = W - off;
+        const int stored = room < 0 ? 0 : (cnt < room ? cnt : room);
+        aux[m] = ((unsigned)off << 8) | (unsigned)stored;
+      }
       if (cnt) {
         // K = P H^T S^-1 ; P+ = sym((I-KH)P)  (include/KalmanFilter.hpp:297-302)
         const T k00 = hp00 * i00 + hp10 * i01, k01 = hp00 * i01 + hp10 * i11;
@@ -1532,7 +1620,7 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
             if ((int)(u & 0xffu) == z) { sum += cur[5 * W + s]; used = true; }
           }
           colsum[z] = sum;
-          ll += log((double)sum);
+          ll += (double)M<T>::log_(sum);   // fp32 build: MUFU log (|error| ~1e-7 per term, the weight tolerance is 2e-3)
         }
         const unsigned b = __ballot_sync(FULL, (z < nZ) && !used);
         unused_mask |= ((unsigned long long)b) << zb0;
@@ -1549,24 +1637,20 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
       }
       __syncwarp();
       // ---------------- S4: sensing-limit heuristic (:692-703, Q2) --------------------------
-      for (int mb = 0; mb < nM; mb += 32) {
-        const int m = mb + lane;
-        const unsigned am = (m < nM) ? aux[m] : 0u;
-        if (__any_sync(FULL, am != 0u)) {
-          if (am) {
-            const T w_km = cur[5 * W + m];   // still the pre-update weight (see S1)
-            T rowsum = T(0);
-            for (int s = nM; s < n; s++)
-              if ((int)(aux[s] >> 8) == m) rowsum += cur[5 * W + s];
-            const T delta = w_km - rowsum;   // Pd[m] == 1 here
-            T w_k = (T(1) - T(1)) * w_km;
-            if (delta > T(0)) {
-              w_k += delta;
-              if (w_k > T(1)) w_k = T(1);
-            }
-            cur[5 * W + m] = w_k;
-          }
+      for (int q = lane; q < nfix; q += 32) {   // the flagged components (S1a); their children are contiguous (S1b)
+        const int m = fixList[q];
+        const unsigned ch = aux[m];
+        const int s0 = (int)(ch >> 8), s1 = s0 + (int)(ch & 0xffu);
+        const T w_km = cur[5 * W + m];   // still the pre-update weight (see S1)
+        T rowsum = T(0);
+        for (int s = s0; s < s1; s++) rowsum += cur[5 * W + s];
+        const T delta = w_km - rowsum;   // Pd[m] == 1 here
+        T w_k = (T(1) - T(1)) * w_km;
+        if (delta > T(0)) {
+          w_k += delta;
+          if (w_k > T(1)) w_k = T(1);
         }
+        cur[5 * W + m] = w_k;
       }
       __syncwarp();
     }
@@ -1791,6 +1875,7 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
     }
 
     // ---------------- S6: merge ------------------------------------------------------------------
+    if (lane == 0) pi_next = (int)atomicAdd(p.work_counter, 1u);   // first needed after the merge
     if (n > 1) {
       int st = MERGE_FALLBACK;
       if (p.merge_algo != 0) st = merge_clustered<T>(cur, ms, W, n, p.merge_t2, p.merge_f, MF, lane, mstat, g_xmin, g_xmax, g_trmax, g_bad);
@@ -1801,6 +1886,8 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
     __syncwarp();
 
     // ---------------- S7: prune + store ------------------------------------------------------------
+    int nM_next = 0;
+    if (lane == 0 && pi_next < p.N) nM_next = p.cnt_in[pi_next];   // first needed after the sort
     int n_out = 0;
     {
       T* kw = ms.keys;   // [W] sort keys (the merge-only scratch is dead)
@@ -1827,13 +1914,30 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
           const unsigned long long k0 = lane < n_out ? k64[lane] : 0ull;
           const unsigned long long k1 = lane + 32 < n_out ? k64[lane + 32] : 0ull;
           int r0 = 0, r1 = 0;
-          if (n_out <= 32) {
-            for (int q = 0; q < n_out; q++) r0 += (k64[q] > k0) ? 1 : 0;
-          } else {
-            for (int q = 0; q < n_out; q++) {
-              const unsigned long long kq = k64[q];
-              r0 += (kq > k0) ? 1 : 0;
-              r1 += (kq > k1) ? 1 : 0;
+          {
+            // on the weights alone first (32-bit compares); equal weights show up as colliding ranks
+            const unsigned* kw32 = reinterpret_cast<const unsigned*>(k64);
+            const unsigned w0 = (unsigned)(k0 >> 32), w1 = (unsigned)(k1 >> 32);
+            if (n_out <= 32) {
+              for (int q = 0; q < n_out; q++) r0 += (kw32[2 * q + 1] > w0) ? 1 : 0;
+            } else {
+              for (int q = 0; q < n_out; q++) {
+                const unsigned wq = kw32[2 * q + 1];
+                r0 += (wq > w0) ? 1 : 0;
+                r1 += (wq > w1) ? 1 : 0;
+              }
+            }
+            const unsigned long long mine = (lane < n_out ? 1ull << r0 : 0ull) | (lane + 32 < n_out ? 1ull << r1 : 0ull);
+            const unsigned long long all = (unsigned long long)__reduce_or_sync(FULL, (unsigned)mine) |
+                                           ((unsigned long long)__reduce_or_sync(FULL, (unsigned)(mine >> 32)) << 32);
+            const unsigned long long want = n_out == 64 ? ~0ull : (1ull << n_out) - 1ull;
+            if (all != want) {   // ties: the full (weight, position) keys decide
+              r0 = 0; r1 = 0;
+              for (int q = 0; q < n_out; q++) {
+                const unsigned long long kq = k64[q];
+                r0 += (kq > k0) ? 1 : 0;
+                r1 += (kq > k1) ? 1 : 0;
+              }
             }
           }
           if (lane < n_out) sorted[r0] = (unsigned short)(0xffffffffu - (unsigned)(k0 & 0xffffffffull));
@@ -1867,6 +1971,13 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
       }
       __syncwarp();
       if (n_out > p.cap) { n_out = p.cap; flags |= FLAG_OVERFLOW; }
+      if (lane == 0 && nM_next > 0) {   // the next particle's planes on their way into L2
+        nM_next = nM_next > p.cap ? p.cap : nM_next;
+        const uint32_t bytes = (uint32_t)(((nM_next + 3) & ~3) * sizeof(T));
+        const T* src = p.gm_in + (size_t)pi_next * 6 * p.cap;
+#pragma unroll
+        for (int k = 0; k < 6; k++) tma_prefetch_l2(src + (size_t)k * p.cap, bytes);
+      }
       // gather from shared memory, 128-byte coalesced stores to the particle's planes in HBM
       T* dst = p.gm_out + (size_t)pi * 6 * p.cap;
       for (int k = lane; k < n_out; k += 32) {
@@ -1888,7 +1999,7 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
     max_out = n_out > max_out ? n_out : max_out;
     if (flags & (FLAG_OVERFLOW | FLAG_DP_OVERFLOW)) n_over++;
     if (flags & FLAG_MURTY) n_murty++;
-    __syncwarp();
+    pi = __shfl_sync(FULL, pi_next, 0);
   }
   step_epilogue<T>(p, lane, warp, tot_in, tot_out, max_out, n_over, n_murty, n_fallback, mstat);
 }

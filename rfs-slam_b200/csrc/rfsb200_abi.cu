@@ -332,11 +332,11 @@ int round_pow2(int v) {
 // C3, 16 warps in one CTA per SM run the step in 141 us, 4 CTAs of 4 warps in 172 us.  Choose, in this order: most
 // particles in flight, most SMs in use (small shards), then the largest CTA.
 template <typename K>
-int choose_warps_per_cta(rfsb200_ctx* c, K kernel, size_t cta_bytes, size_t warp_bytes) {
+int choose_warps_per_cta(rfsb200_ctx* c, K kernel, size_t cta_bytes, size_t warp_bytes, int max_warps) {
   int best_nw = 0, best_occ = 0, best_sms = -1;
   long long best_res = -1;
-  int nw_lo = 1, nw_hi = MAX_WARPS_PER_CTA;   // large work capacities / the fp64 build may only fit a few warps
-  if (const char* e = getenv("RFSB200_WARPS_PER_CTA")) { nw_lo = nw_hi = std::max(1, std::min(MAX_WARPS_PER_CTA, atoi(e))); }   // tuning aid
+  int nw_lo = 1, nw_hi = max_warps;   // (the kernel's launch bounds) large work capacities / the fp64 build may only fit a few warps
+  if (const char* e = getenv("RFSB200_WARPS_PER_CTA")) { nw_lo = nw_hi = std::max(1, std::min(max_warps, atoi(e))); }   // tuning aid
   for (int nw = nw_lo; nw <= nw_hi; nw++) {
     const size_t smem = cta_bytes + (size_t)nw * warp_bytes;
     if (smem > 227 * 1024) break;
@@ -395,7 +395,7 @@ int configure_launch_t(rfsb200_ctx* c) {
   c->cfg_n_eval = n_eval;
   c->mf_bytes = mf ? mf_region_bytes<T>(c->W, n_eval, c->dims.z_capacity) : 0;   // the work region in multi-feature mode
   c->warp_bytes = warp_bytes_for<T>(c->W, mf, mf ? c->mf_bytes : merge_scratch_bytes<T>(c->W));
-  int rc = choose_warps_per_cta(c, phd_update_kernel<T, MF>, (size_t)z_bytes<T>(), (size_t)c->warp_bytes);
+  int rc = choose_warps_per_cta(c, phd_update_kernel<T, MF>, (size_t)z_bytes<T>(), (size_t)c->warp_bytes, update_max_threads<T, MF>() / 32);
   if (rc) return rc;
   if (MF) ensure_dp_scratch(c, n_eval);
   c->cfg_mode_mf = mf;
@@ -409,7 +409,7 @@ int configure_launch_vp_t(rfsb200_ctx* c) {
   c->cfg_n_eval = n_eval;
   c->mf_bytes = 0;
   c->warp_bytes = vp_warp_bytes<T>(c->W, mf, n_eval, c->dims.z_capacity);
-  int rc = choose_warps_per_cta(c, phd_update_vp_kernel<T, MF>, (size_t)vp_cta_bytes<T>(), (size_t)c->warp_bytes);
+  int rc = choose_warps_per_cta(c, phd_update_vp_kernel<T, MF>, (size_t)vp_cta_bytes<T>(), (size_t)c->warp_bytes, 16);
   if (rc) return rc;
   if (MF) ensure_dp_scratch(c, n_eval);
   c->cfg_mode_mf = mf;

@@ -59,6 +59,11 @@ inline void tma_store_1d(void* gmem_dst, const void* smem_src, uint32_t bytes) {
   simt_check_bulk(gmem_dst, smem_src, bytes);
   memcpy(gmem_dst, smem_src, bytes);
 }
+inline void tma_prefetch_l2(const void* gmem_src, uint32_t bytes) {   // no effect on the host; the alignment rules still hold
+  simt_check_bulk(gmem_src, gmem_src, bytes);
+  volatile unsigned char sink = reinterpret_cast<const volatile unsigned char*>(gmem_src)[bytes - 1];   // inside an allocation
+  (void)sink;
+}
 inline void tma_store_commit() {}
 inline void tma_store_wait_read() {}
 inline void tma_store_wait_all() {}
