@@ -147,6 +147,7 @@ template <> struct M<float> {
   }
   static __device__ __forceinline__ float abs_(float x) { return fabsf(x); }
   static __device__ __forceinline__ float max_(float a, float b) { return fmaxf(a, b); }
+  static __device__ __forceinline__ float min_(float a, float b) { return fminf(a, b); }
   static __device__ __forceinline__ float inf() { return __int_as_float(0x7f800000); }
   static constexpr float PI = 3.14159265358979323846f;
   static constexpr float TWO_PI = 6.28318530717958647692f;
@@ -158,6 +159,7 @@ template <> struct M<double> {
   static __device__ __forceinline__ double atan2_(double y, double x) { return atan2(y, x); }
   static __device__ __forceinline__ double abs_(double x) { return fabs(x); }
   static __device__ __forceinline__ double max_(double a, double b) { return fmax(a, b); }
+  static __device__ __forceinline__ double min_(double a, double b) { return fmin(a, b); }
   static __device__ __forceinline__ double inf() { return __longlong_as_double(0x7ff0000000000000LL); }
   static constexpr double PI = 3.14159265358979323846;
   static constexpr double TWO_PI = 6.28318530717958647692;

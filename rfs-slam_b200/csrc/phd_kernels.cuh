@@ -312,7 +312,7 @@ struct MergeScratch {
   unsigned short* cellStart; // [264]
   unsigned* counters;        // [4]: 0 = number of pairs, 1 = logged rows
   // --- region that is dead outside the merge (the prune sort keys alias all of it) ---
-  XY<T>* sxy;                // [W] M1/M2 only: (x, y) in cell order   } same storage
+  XY<T>* sxy;                // [W + 4] M1/M2 only: (x, y) in cell order, four sentinels behind   } same storage
   unsigned short* members;   // [MEMBERS_CAP] members of cluster c at memberStart[c] .. memberStart[c + 1]   } (M3+ only)
   unsigned short* memberStart; // [MAX_CLUSTERS + 2]                    }
   T* rowLog;                 // [MAX_ROWLOG][6]                         }
@@ -331,7 +331,7 @@ template <typename T>
 __host__ __device__ inline int merge_region_a_bytes(int W) {
   const int rl = (MAX_ROWLOG * 6 * (int)sizeof(T) + 7) & ~7;
   const int a = rl + MEMBERS_CAP * 2 + MERGE_MSTART * 2 + MAX_ROWLOG * 2 + 32 * 2;
-  const int b = 2 * W * (int)sizeof(T);
+  const int b = 2 * (W + 4) * (int)sizeof(T);   // sxy[W] + four sentinels
   return ((a > b ? a : b) + 15) & ~15;
 }
 template <typename T>
@@ -429,10 +429,8 @@ __device__ int merge_clustered(T* cur, const MergeScratch<T>& ms, int W, int n, 
   T cw = span * T(1.0 / 255.5);
   cw = cw > rmax ? cw : rmax;
   const T invw = cw > T(0) ? T(1) / cw : T(0);
-  auto cell_of = [&](T x) -> int {
-    const T v = (x - xmin) * invw;
-    int c = (v >= T(255)) ? 255 : (int)v;
-    return c < 0 ? 0 : c;
+  auto cell_of = [&](T x) -> int {   // monotone in x; NaN -> 0
+    return (int)M<T>::min_(M<T>::max_((x - xmin) * invw, T(0)), T(255));
   };
   __syncwarp();
   for (int j = lane; j < n; j += 32) {   // histogram at cell+1; 16-bit counters packed in words
@@ -466,68 +464,89 @@ __device__ int merge_clustered(T* cur, const MergeScratch<T>& ms, int W, int n, 
     ms.order[pos] = (unsigned short)j;
     ms.sxy[pos] = q;
   }
+  if (lane < 4) { XY<T> far; far.x = M<T>::inf(); far.y = M<T>::inf(); ms.sxy[n + lane] = far; }   // sentinels (see M2a)
   __syncwarp();
   // (the order inside a cell is schedule dependent; nothing below depends on it: M2 visits every
   //  pair of one cell or of adjacent cells exactly once, M4 takes minima over index)
   // ---- M2: candidate pairs ------------------------------------------------------------------------
   //  a) by distance: position s against the positions behind it up to the end of the next cell, four at a time,
-  //     branch-free; the hits (|d|^2 <= largest reach^2) are compacted into a list in label[] (not in use yet)
+  //     branch-free; the hits (|d|^2 <= largest reach^2) are compacted into a list in label[] (not in use yet).
+  //     Positions past the end of the next cell need no test of their own: they are at least one cell width
+  //     (>= the largest reach) away in x and cannot hit; four sentinels at infinity follow the last position.
   //  b) lane-parallel over that list: the two components' own reaches, then the exact test on the original
-  //     parameters -> list of passing pairs
-  unsigned* cand = ms.label;   // [W] (position s << 16) | position t
+  //     parameters -> list of passing pairs (collected in the storage of sxy[], which is dead by then, and copied
+  //     to pairs[] at the end: the positions of the list live in pairs[] until then)
+  unsigned* candHits = ms.label;   // [W] per position with a hit: bit b = position s + 1 + b is within the largest reach
+  unsigned short* candPos = reinterpret_cast<unsigned short*>(ms.pairs);   // [2 * MAX_PAIRS] its position s (the cursors are dead)
+  constexpr int CAND_CAP = 2 * MAX_PAIRS;
   int ncand = 0;
+  bool far_window = false;
   for (int sb = 0; sb < n; sb += 32) {
     const int s = sb + lane;
-    const int sc = s < n ? s : n - 1;
-    const XY<T> me = ms.sxy[sc];
-    const int end = s < n ? (int)ms.cellStart[cell_of(me.x) + 2] : 0;
-    for (int t0 = s + 1; __any_sync(FULL, t0 < end); t0 += 4) {
-      bool h[4];
+    const bool live = s < n;
+    XY<T> me;
+    me.x = M<T>::inf(); me.y = M<T>::inf();   // (inf - inf = NaN: a dead lane never hits)
+    if (live) me = ms.sxy[s];
+    const int end = live ? (int)ms.cellStart[cell_of(me.x) + 2] : 0;
+    unsigned hits = 0;
+    int sh = 0;
+    for (int t0 = s + 1; __any_sync(FULL, t0 < end); t0 += 4, sh += 4) {
+      const int tb = t0 < end ? t0 : n;   // a lane that is through reads the sentinels
+      unsigned hm = 0;
 #pragma unroll
       for (int u = 0; u < 4; u++) {
-        const int t = t0 + u;
-        const XY<T> q = ms.sxy[t < n ? t : n - 1];
+        const XY<T> q = ms.sxy[tb + u];
         const T dx = q.x - me.x, dy = q.y - me.y;
-        h[u] = (t < end) && !(dx * dx + dy * dy > rmax2);
+        hm |= (dx * dx + dy * dy <= rmax2) ? (1u << u) : 0u;
       }
-#pragma unroll
-      for (int u = 0; u < 4; u++) {
-        const unsigned bh = __ballot_sync(FULL, h[u]);
-        if (bh) {
-          const int pos = ncand + __popc(bh & lt);
-          if (h[u] && pos < W) cand[pos] = ((unsigned)s << 16) | (unsigned)(t0 + u);
-          ncand += __popc(bh);
+      if (sh < 32) hits |= hm << sh;
+      else far_window |= hm != 0u;   // more than 32 positions inside one window: not handled here
+    }
+    const unsigned bh = __ballot_sync(FULL, hits != 0u);
+    if (bh) {
+      const int pos = ncand + __popc(bh & lt);
+      if (hits != 0u && pos < W && pos < CAND_CAP) { candHits[pos] = hits; candPos[pos] = (unsigned short)s; }
+      ncand += __popc(bh);
+    }
+  }
+  __syncwarp();
+  if (ncand > W || ncand > CAND_CAP || __any_sync(FULL, far_window)) { mstat[1]++; return MERGE_FALLBACK; }
+  int npass = 0;
+  unsigned* passing = reinterpret_cast<unsigned*>(ms.sxy);   // [MAX_PAIRS]
+  for (int base = 0; base < ncand; base += 32) {
+    const int q = base + lane;
+    unsigned hits = 0;
+    int sp = 0;
+    if (q < ncand) { hits = candHits[q]; sp = candPos[q]; }
+    const int j = ms.order[sp];
+    const T ax = cur[j], ay = cur[W + j];
+    const T rj = tt * (cur[2 * W + j] + cur[4 * W + j]);
+    while (__any_sync(FULL, hits != 0u)) {
+      unsigned key = 0;
+      bool pass = false;
+      if (hits) {
+        const int tp = sp + __ffs(hits);
+        hits &= hits - 1;
+        const int k = ms.order[tp];
+        const T dx = cur[k] - ax, dy = cur[W + k] - ay;
+        const T d2 = dx * dx + dy * dy;
+        const T rk = tt * (cur[2 * W + k] + cur[4 * W + k]);
+        if (!(d2 > M<T>::max_(rj, rk))) {
+          const int lo = j < k ? j : k, hi = j < k ? k : j;
+          key = ((unsigned)lo << 16) | (unsigned)hi;
+          pass = merge_test_pair(cur, W, lo, hi, t2);
         }
+      }
+      const unsigned bp = __ballot_sync(FULL, pass);
+      if (bp) {
+        const int pos = npass + __popc(bp & lt);
+        if (pass && pos < MAX_PAIRS) passing[pos] = key;
+        npass += __popc(bp);
       }
     }
   }
   __syncwarp();
-  if (ncand > W) { mstat[1]++; return MERGE_FALLBACK; }
-  int npass = 0;
-  for (int base = 0; base < ncand; base += 32) {
-    const int q = base + lane;
-    unsigned key = 0;
-    bool pass = false;
-    if (q < ncand) {
-      const unsigned st = cand[q];
-      const int j = ms.order[st >> 16], k = ms.order[st & 0xffffu];
-      const XY<T> a = ms.sxy[st >> 16], b = ms.sxy[st & 0xffffu];
-      const T dx = b.x - a.x, dy = b.y - a.y;
-      const T d2 = dx * dx + dy * dy;
-      const T rj = tt * (cur[2 * W + j] + cur[4 * W + j]), rk = tt * (cur[2 * W + k] + cur[4 * W + k]);
-      if (!(d2 > M<T>::max_(rj, rk))) {
-        const int lo = j < k ? j : k, hi = j < k ? k : j;
-        key = ((unsigned)lo << 16) | (unsigned)hi;
-        pass = merge_test_pair(cur, W, lo, hi, t2);
-      }
-    }
-    const unsigned bp = __ballot_sync(FULL, pass);
-    if (bp) {
-      const int pos = npass + __popc(bp & lt);
-      if (pass && pos < MAX_PAIRS) ms.pairs[pos] = key;
-      npass += __popc(bp);
-    }
-  }
+  for (int k = lane; k < npass && k < MAX_PAIRS; k += 32) ms.pairs[k] = passing[k];
   if (npass == 0) return MERGE_OK;
   if (npass > MAX_PAIRS) { mstat[1]++; return MERGE_FALLBACK; }
   mstat[5] += (unsigned)npass;
@@ -656,9 +675,8 @@ __device__ int merge_clustered(T* cur, const MergeScratch<T>& ms, int W, int n, 
               if (!pd) { logfull = true; break; }
               const T R2 = M<T>::max_(ri2, rmax2);
               const T R = M<T>::sqrt_(R2) * T(1.001);
-              int clo = cell_of(r.x - R) - 1, chi = cell_of(r.x + R) + 1;
-              clo = clo < 0 ? 0 : clo;
-              chi = chi > 255 ? 255 : chi;
+              // a partner k has |x_k - x_row| <= R and cell_of is monotone: its cell lies in [cell(x - R), cell(x + R)]
+              const int clo = cell_of(r.x - R), chi = cell_of(r.x + R);
               const int t0 = ms.cellStart[clo], t1 = ms.cellStart[chi + 1];
               for (int t = t0; t < t1; t++) {
                 const int k = ms.order[t];
@@ -1334,11 +1352,10 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
   }
   __syncthreads();
   const T binR0 = binp[0], binRi = binp[1], binB0 = binp[2], binBi = binp[3];
-  auto bin_of = [](T v, T v0, T inv) -> int {
-    const T u = (v - v0) * inv;
-    const int b = (u >= T(NBINS - 1)) ? NBINS - 1 : (int)u;
-    return b < 0 ? 0 : b;
+  auto bin_of = [](T v, T v0, T inv) -> int {   // monotone in v; NaN -> 0
+    return (int)M<T>::min_(M<T>::max_((v - v0) * inv, T(0)), T(NBINS - 1));
   };
+  const T r_hi_in = p.rmax - p.rbuf, r_lo_in = p.rmin + p.rbuf, r_hi_out = p.rmax + p.rbuf, r_lo_out = p.rmin - p.rbuf;
 
   uint32_t phase = 0;
   unsigned long long tot_in = 0, tot_out = 0;
@@ -1425,10 +1442,10 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
         const bool inrange = (r <= p.rmax) && (r >= p.rmin);
         if (inrange) {
           Pd = p.Pd;
-          close = (r >= p.rmax - p.rbuf) || (r <= p.rmin + p.rbuf);
+          close = (r >= r_hi_in) || (r <= r_lo_in);
         } else {
           Pd = T(0);
-          close = (r <= p.rmax + p.rbuf) && (r >= p.rmin - p.rbuf);
+          close = (r <= r_hi_out) && (r >= r_lo_out);
         }
         if (close) Pd = T(1);
         if (Pd != T(0)) nfov++;
@@ -1487,7 +1504,7 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
         const T dx = x - px, dy = y - py;
         const T r2 = dx * dx + dy * dy;
         const T r = M<T>::sqrt_(r2);
-        const bool close = (r >= p.rmax - p.rbuf) || (r <= p.rmin + p.rbuf);   // in range here
+        const bool close = (r >= r_hi_in) || (r <= r_lo_in);   // in range here
         const T Pd = close ? T(1) : p.Pd;
         fixq = close && (w > p.birth_w);
         {
@@ -1615,6 +1632,7 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
         bool used = false;
         if (z < nZ) {
           T sum = p.kappa;
+#pragma unroll 4
           for (int s = nM; s < n; s++) {
             const unsigned u = aux[s];
             if ((int)(u & 0xffu) == z) { sum += cur[5 * W + s]; used = true; }
