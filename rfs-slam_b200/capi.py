@@ -12,6 +12,8 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "librfsb200.so")
+if os.environ.get("RFSB200_LIB"):   # development aid: A/B builds of the same library
+    LIB_PATH = os.environ["RFSB200_LIB"]
 
 OK = 0
 UPDATE_DEFAULT = 0

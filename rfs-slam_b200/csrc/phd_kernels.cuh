@@ -414,7 +414,7 @@ __device__ __forceinline__ void warp_fill4(void* dst, unsigned v, int n4, int la
 }
 
 template <typename T>
-__device__ int merge_clustered(T* cur, const MergeScratch<T>& ms, int W, int n, T t2, T f, bool has_wprev,
+__device__ __forceinline__ int merge_clustered(T* cur, const MergeScratch<T>& ms, int W, int n, T t2, T f, bool has_wprev,
                                int lane, unsigned (&mstat)[8], T xmin, T xmax, T trmax, bool bad) {
   // ---- M1: counting sort on cells.  xmin / xmax / trmax (largest trace(P)) / bad (some covariance
   //      is not PD) over the n components were gathered by the corrector (warp-uniform values). ----
@@ -1109,10 +1109,29 @@ __device__ __forceinline__ void step_epilogue(const KParams<T>& p, int lane, int
   __syncthreads();
   if (is_last) {
     __threadfence();
-    // fixed summation order (bit-reproducible): thread t owns particles t, t + nt, ...; four loads in flight
-    // per thread, because this loop runs on ONE CTA at the end of every step and is pure L2 latency
+    // fixed summation order (bit-reproducible): thread t owns particles t, t + nt, ...  This runs on ONE CTA at the
+    // end of every step and is pure L2 latency, so a shard of up to EPI_REG particles per thread is loaded in one
+    // round trip and stays in registers for the normalisation below; larger shards stream, four loads in flight.
+    constexpr int EPI_REG = 16;
+    const bool in_regs = p.N <= EPI_REG * (int)blockDim.x;
+    double wreg[EPI_REG];
     double s1, s2;
-    {
+    if (in_regs) {
+      const int nt = blockDim.x;
+#pragma unroll
+      for (int k = 0; k < EPI_REG; k++) {
+        const int i = threadIdx.x + k * nt;
+        wreg[k] = i < p.N ? __ldcg(p.w_out + i) : 0.0;
+      }
+      double a0 = 0, a1 = 0, b0 = 0, b1 = 0;
+#pragma unroll
+      for (int k = 0; k < EPI_REG; k += 2) {
+        a0 += wreg[k]; a1 += wreg[k + 1];
+        b0 += wreg[k] * wreg[k]; b1 += wreg[k + 1] * wreg[k + 1];
+      }
+      s1 = a0 + a1;
+      s2 = b0 + b1;
+    } else {
       const int nt = blockDim.x;
       double a0 = 0, a1 = 0, a2 = 0, a3 = 0, b0 = 0, b1 = 0, b2 = 0, b3 = 0;
       int i = threadIdx.x;
@@ -1205,7 +1224,20 @@ __device__ __forceinline__ void step_epilogue(const KParams<T>& p, int lane, int
       *p.ticket = 0;
       *p.work_counter = 0;
     }
-    if (p.fused_normalize) {   // ParticleFilter::normalizeWeights, in the same launch
+    if (p.fused_normalize && in_regs) {   // ParticleFilter::normalizeWeights, in the same launch
+      __syncthreads();
+      const double total = red[0][0];
+      const int nt = blockDim.x;
+#pragma unroll
+      for (int k = 0; k < EPI_REG; k++) {
+        const int i = threadIdx.x + k * nt;
+        if (i < p.N) {
+          const double w = wreg[k] / total;
+          p.w_out[i] = w;
+          if (p.w_host) p.w_host[i] = w;
+        }
+      }
+    } else if (p.fused_normalize) {
       __syncthreads();
       const double total = red[0][0];
       const int nt = blockDim.x;
@@ -1272,13 +1304,15 @@ __host__ __device__ inline int z_bytes() {
 template <typename T, bool MF>
 constexpr int update_max_threads() { return (sizeof(T) == 4 && !MF) ? 32 * MAX_WARPS_PER_CTA : 512; }
 
-template <typename T, bool MF>
+// WT: the work capacity W as a compile-time constant (0: p.W at run time).  With W known, every plane of a warp's
+// block is addressed as one register plus an immediate offset; the fp32 kernels are instantiated for W = 256.
+template <typename T, bool MF, int WT>
 __global__ void __launch_bounds__((update_max_threads<T, MF>()), 1)
 phd_update_kernel(const __grid_constant__ KParams<T> p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  const int W = p.W;
+  const int W = WT ? WT : p.W;
   const int nZ = p.nZ;
   constexpr int NPL = MF ? 7 : 6;   // MF = multi-feature weighting (p.use_sc == 0)
 

@@ -395,7 +395,13 @@ int configure_launch_t(rfsb200_ctx* c) {
   c->cfg_n_eval = n_eval;
   c->mf_bytes = mf ? mf_region_bytes<T>(c->W, n_eval, c->dims.z_capacity) : 0;   // the work region in multi-feature mode
   c->warp_bytes = warp_bytes_for<T>(c->W, mf, mf ? c->mf_bytes : merge_scratch_bytes<T>(c->W));
-  int rc = choose_warps_per_cta(c, phd_update_kernel<T, MF>, (size_t)z_bytes<T>(), (size_t)c->warp_bytes, update_max_threads<T, MF>() / 32);
+  int rc;
+  if constexpr (sizeof(T) == 4) {
+    rc = c->W == 256 ? choose_warps_per_cta(c, phd_update_kernel<T, MF, 256>, (size_t)z_bytes<T>(), (size_t)c->warp_bytes, update_max_threads<T, MF>() / 32)
+                     : choose_warps_per_cta(c, phd_update_kernel<T, MF, 0>, (size_t)z_bytes<T>(), (size_t)c->warp_bytes, update_max_threads<T, MF>() / 32);
+  } else {
+    rc = choose_warps_per_cta(c, phd_update_kernel<T, MF, 0>, (size_t)z_bytes<T>(), (size_t)c->warp_bytes, update_max_threads<T, MF>() / 32);
+  }
   if (rc) return rc;
   if (MF) ensure_dp_scratch(c, n_eval);
   c->cfg_mode_mf = mf;
@@ -488,8 +494,13 @@ int launch_update(rfsb200_ctx* c, int nZ, int out_idx, unsigned flags) {
     for (int k = 0; k < VP_PD_MAX; k++) v.pd_table[k] = k < m.pd_table_n ? m.pd_table[k] : 0.0;
     if (mf) phd_update_vp_kernel<T, true><<<c->grid, c->nwarps * 32, c->smem_bytes, c->stream>>>(v);
     else phd_update_vp_kernel<T, false><<<c->grid, c->nwarps * 32, c->smem_bytes, c->stream>>>(v);
-  } else if (mf) phd_update_kernel<T, true><<<c->grid, c->nwarps * 32, c->smem_bytes, c->stream>>>(p);
-  else phd_update_kernel<T, false><<<c->grid, c->nwarps * 32, c->smem_bytes, c->stream>>>(p);
+  } else if (sizeof(T) == 4 && c->W == 256) {   // the work capacity as a compile-time constant (fp32 kernels)
+    if constexpr (sizeof(T) == 4) {
+      if (mf) phd_update_kernel<T, true, 256><<<c->grid, c->nwarps * 32, c->smem_bytes, c->stream>>>(p);
+      else phd_update_kernel<T, false, 256><<<c->grid, c->nwarps * 32, c->smem_bytes, c->stream>>>(p);
+    }
+  } else if (mf) phd_update_kernel<T, true, 0><<<c->grid, c->nwarps * 32, c->smem_bytes, c->stream>>>(p);
+  else phd_update_kernel<T, false, 0><<<c->grid, c->nwarps * 32, c->smem_bytes, c->stream>>>(p);
   CU(c, cudaGetLastError());
   if (prof) {
     CU(c, cudaEventRecord(c->prof_ev[2 * c->prof_n + 1], c->stream));
