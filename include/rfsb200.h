@@ -61,6 +61,10 @@ extern "C" {
                                          [sum w, sum w^2] pairs of all ranks through peer memory (NVLink)
                                          and normalises, in the same launch; every rank must call
                                          rfsb200_update with this flag the same number of times      */
+#define RFSB200_UPDATE_STAGE_TIMES 8u   /* run the stage-timing build of the update kernel (same results): fills what
+                                         rfsb200_get_stage_times() returns — the reference's per-phase TimingInfo
+                                         (include/RBPHDFilter.hpp:152-167,1219-1232).  fp32 build; a measurement
+                                         aid, a few percent slower than the product kernel                   */
 #define RFSB200_UPDATE_NO_NORMALIZE 2u /* stop after the local [sum w, sum w^2] reduction so the
                                          caller can all-reduce rfsb200_weight_sums_device() across
                                          GPUs and then call rfsb200_normalize()               */
@@ -226,7 +230,8 @@ int rfsb200_update_host(rfsb200_ctx* ctx, const double* pose /*[N][3]*/, const d
  *     rfsb200_append_gaussians).
  * For RFSB200_MODEL_VICTORIAPARK the births are at MeasurementModel_VictoriaPark::inverseMeasure
  * (src/MeasurementModel_VictoriaPark.cpp:75-102) and Q_lmk has 6 entries (xx, xy, xz, yy, yz, zz).
- * Runs on the committed state, in place.  Births that do not fit gm_capacity set flag bit 1. */
+ * Runs on the committed state, in place.  Births that do not fit gm_capacity set flag bits 1 and 8 of the particle;
+ * the next update carries the drop into its own result: flag bit 1 and rfsb200_step_out::n_overflow. */
 int rfsb200_predict_maps(rfsb200_ctx* ctx, const double* Q_lmk /*[3] / [6] or NULL*/, int32_t add_births,
                          double birth_weight);
 
@@ -235,7 +240,7 @@ int rfsb200_predict_maps(rfsb200_ctx* ctx, const double* Q_lmk /*[3] / [6] or NU
  * for the birth Gaussians the HOST decides on — the candidate-list form of addBirthGaussians()
  * (include/RBPHDFilter.hpp:1023-1080, used when birthGaussianMeasurementCountThreshold_ != 1, e.g. the
  * Victoria Park configuration) keeps its per-particle candidate lists on the host.  Gaussians that do not
- * fit gm_capacity are dropped and set flag bit 1 of the particle. */
+ * fit gm_capacity are dropped and set flag bits 1 and 8 of the particle (counted by the next update, see above). */
 int rfsb200_append_gaussians(rfsb200_ctx* ctx, const int32_t* count /*[N]*/, const double* mean,
                              const double* cov, const double* w);
 
@@ -321,7 +326,9 @@ int rfsb200_download_maps(rfsb200_ctx* ctx, int which, int64_t cap_total, int32_
 /* unused_measurements_[i] and nLandmarksInFOV_[i] (include/RBPHDFilter.hpp:269-272,709-720),
  * consumed by addBirthGaussians on the host. unused_mask bit z set = measurement z unused. */
 int rfsb200_get_unused(rfsb200_ctx* ctx, uint64_t* unused_mask /*[N]*/, int32_t* n_in_fov /*[N]*/);
-/* per-particle status bits of the last update: 1 = capacity overflow, 2 = Murty branch taken */
+/* per-particle status bits of the last update: 1 = capacity overflow (of the update, or of a predict / append since the
+ * update before), 2 = Murty branch taken, 4 = a partition beyond the assignment-sum tables, 8 = births dropped by the
+ * last predict / append (cleared by the next update) */
 int rfsb200_get_flags(rfsb200_ctx* ctx, int32_t* flags /*[N]*/);
 
 /* ---- utilities --------------------------------------------------------------------
@@ -337,6 +344,28 @@ int rfsb200_permanent(rfsb200_ctx* ctx, const double* A /*[batch][n][n]*/, int32
  * microseconds (n = number recorded, at most cap are written) and disarms the ring.  Used by
  * bench.py for the live roofline figure; costs nothing when not armed. */
 int rfsb200_profile_begin(rfsb200_ctx* ctx, int32_t max_updates);
+/* Per-phase times of the last update that ran with RFSB200_UPDATE_STAGE_TIMES.  The update is ONE fused kernel, so a
+ * phase has no wall time of its own: the kernel's wall time (device global timer, first CTA in to last CTA out) is
+ * split into set-up (measurement tables), the particle loop and the weight-sum epilogue, and the particle loop is
+ * attributed to the phases by their share of the warp cycles spent in them (SM clock read by every warp at the
+ * phase boundaries of every particle). */
+typedef struct rfsb200_stage_times {
+  double kernel_us;          /* first CTA in -> last CTA out                                                         */
+  double setup_us;           /* ... -> last CTA has built its measurement tables                                      */
+  double particles_us;       /* ... -> last warp is out of particles                                                  */
+  double epilogue_us;        /* ... -> end: [sum w, sum w^2], cross-GPU sum, normalisation                            */
+  double share_load;         /* shares of the warp cycles inside the particle loop (sum = 1):  queue + bulk loads     */
+  double share_map_update_kf;/*   GM-PHD corrector incl. the EKF updates          (TimingInfo::mapUpdate_kf)          */
+  double share_weighting;    /*   normalisers, SC-PHD weight, posterior weights + multi-feature importanceWeighting
+                                  (TimingInfo::particleWeighting)                                                    */
+  double share_merge;        /*   GaussianMixture::merge                          (TimingInfo::mapMerge)              */
+  double share_prune;        /*   prune + sort + store                            (TimingInfo::mapPrune)              */
+  double warp_cycles;        /* total warp cycles inside the particle loop                                            */
+  int32_t warps_per_cta;     /* launch shape of the stage-timing kernel                                               */
+  int32_t reserved_i;
+  double reserved[4];
+} rfsb200_stage_times;
+int rfsb200_get_stage_times(rfsb200_ctx* ctx, rfsb200_stage_times* out);
 int rfsb200_profile_read(rfsb200_ctx* ctx, float* kernel_us /*[cap]*/, int32_t cap, int32_t* n);
 
 /* Pinned host memory helpers (so H2D/D2H copies can overlap and run at PCIe speed, and so that rfsb200_update_host

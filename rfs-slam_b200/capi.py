@@ -20,6 +20,7 @@ UPDATE_DEFAULT = 0
 UPDATE_NO_COMMIT = 1
 UPDATE_NO_NORMALIZE = 2
 UPDATE_FUSED_ALLREDUCE = 4
+UPDATE_STAGE_TIMES = 8
 
 ERRORS = {0: "OK", -1: "EINVAL", -2: "ECUDA", -3: "ENOMEM", -4: "ECAPACITY", -5: "EUNSUPPORTED",
           -6: "ESTATE", -7: "ENODEVICE"}
@@ -113,6 +114,14 @@ def filter_cfg(fc: dict) -> FilterCfg:
     return c
 
 
+class StageTimes(C.Structure):
+    """rfsb200_stage_times"""
+    _fields_ = [("kernel_us", C.c_double), ("setup_us", C.c_double), ("particles_us", C.c_double), ("epilogue_us", C.c_double),
+                ("share_load", C.c_double), ("share_map_update_kf", C.c_double), ("share_weighting", C.c_double),
+                ("share_merge", C.c_double), ("share_prune", C.c_double), ("warp_cycles", C.c_double),
+                ("warps_per_cta", C.c_int32), ("reserved_i", C.c_int32), ("reserved", C.c_double * 4)]
+
+
 # name -> (restype, argtypes); the not-gpu test checks every symbol of include/rfsb200.h is here
 _P = C.c_void_p
 _SIGS = {
@@ -151,6 +160,7 @@ _SIGS = {
     "rfsb200_permanent": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P]),
     "rfsb200_profile_begin": (C.c_int, [_P, C.c_int32]),
     "rfsb200_profile_read": (C.c_int, [_P, _P, C.c_int32, C.POINTER(C.c_int32)]),
+    "rfsb200_get_stage_times": (C.c_int, [_P, C.POINTER(StageTimes)]),
     "rfsb200_host_alloc": (C.c_int, [C.POINTER(_P), C.c_uint64]),
     "rfsb200_host_free": (C.c_int, [_P]),
 }

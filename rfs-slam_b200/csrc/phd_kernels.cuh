@@ -32,6 +32,8 @@ constexpr int MAX_PAIRS = 144; // merge: passing pairs (+ cluster links) kept pe
 
 // flag bits written per particle
 constexpr int FLAG_OVERFLOW = 1;
+constexpr int FLAG_BIRTH_OVERFLOW = 8;   // set by predict / append when births did not fit gm_capacity; the next update turns
+                                         // it into FLAG_OVERFLOW of its own result (and counts it), so the drop is not lost
 constexpr int FLAG_MURTY = 2;       // a partition with nR + nC > 8 (reference would use Murty-200)
 constexpr int FLAG_DP_OVERFLOW = 4; // partition too large for the on-chip DP
 
@@ -91,7 +93,12 @@ struct KParams {
   unsigned long long* unused_host;  // [N]
   int* nfov_host;                   // [N]
   unsigned long long* stats_host;   // [15] sums[2] (as bits) followed by stats_out[13]
+  // stage-timing build of the kernels only (RFSB200_UPDATE_STAGE_TIMES): [0..11] SM cycles of all warps per stage
+  // (see StageClock), [12] first CTA start, [13] last CTA past its set-up, [14] last warp out of particles, [15] last
+  // CTA done — %globaltimer ns
+  unsigned long long* prof;
 };
+
 
 // ------------------------------------------------------------------------------------------------
 template <typename T>
@@ -156,6 +163,41 @@ __device__ __forceinline__ int next_pow2(int n) {
   while (p < n) p <<= 1;
   return p;
 }
+
+// Stage timing (the reference's TimingInfo, include/RBPHDFilter.hpp:152-167: mapUpdate_kf, particleWeighting, mapMerge,
+// mapPrune): lane 0 of every warp reads the SM clock at the stage boundaries of every particle and accumulates the
+// differences; the totals of all warps go to KParams::prof at the end of the launch.  Compiled in only in the PROF
+// instantiations of the kernels; the product kernels carry none of it.
+constexpr int STAGE_LOAD = 0, STAGE_CORRECT = 1, STAGE_WEIGHT = 2, STAGE_MFWEIGHT = 3, STAGE_MERGE = 4, STAGE_PRUNE = 5,
+              STAGE_M1 = 6, STAGE_M2 = 7, STAGE_M3 = 8, STAGE_M4 = 9, N_STAGES = 10;   // M1..M4: inside the merge (STAGE_MERGE = the rest of it)
+template <bool PROF>
+struct StageClock {
+  long long t;
+  unsigned long long acc[N_STAGES];
+  __device__ __forceinline__ void start() {
+    if constexpr (PROF) {
+      t = clock64();
+#pragma unroll
+      for (int k = 0; k < N_STAGES; k++) acc[k] = 0ull;
+    }
+  }
+  __device__ __forceinline__ void mark(int k) {
+    if constexpr (PROF) {
+      const long long n = clock64();
+      acc[k] += (unsigned long long)(n - t);
+      t = n;
+    }
+  }
+  __device__ __forceinline__ void flush(unsigned long long* prof, int lane) {
+    if constexpr (PROF) {
+      if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < N_STAGES; k++) atomicAdd(&prof[k], acc[k]);
+        atomicMax(&prof[14], globaltimer_ns());
+      }
+    }
+  }
+};
 
 // ------------------------------------------------------------------------------------------------
 // S6: GaussianMixture::merge.  cur = 7 planes of W; holes are marked by weight < 0.
@@ -413,9 +455,9 @@ __device__ __forceinline__ void warp_fill4(void* dst, unsigned v, int n4, int la
   for (int k = lane; k < n4; k += 32) d[k] = q;
 }
 
-template <typename T>
+template <typename T, bool PROF>
 __device__ __forceinline__ int merge_clustered(T* cur, const MergeScratch<T>& ms, int W, int n, T t2, T f, bool has_wprev,
-                               int lane, unsigned (&mstat)[8], T xmin, T xmax, T trmax, bool bad) {
+                               int lane, unsigned (&mstat)[8], T xmin, T xmax, T trmax, bool bad, StageClock<PROF>& clk) {
   // ---- M1: counting sort on cells.  xmin / xmax / trmax (largest trace(P)) / bad (some covariance
   //      is not PD) over the n components were gathered by the corrector (warp-uniform values). ----
   if (bad) { mstat[0]++; return MERGE_FALLBACK; }   // a non-PD covariance has no finite reach
@@ -468,6 +510,7 @@ __device__ __forceinline__ int merge_clustered(T* cur, const MergeScratch<T>& ms
   __syncwarp();
   // (the order inside a cell is schedule dependent; nothing below depends on it: M2 visits every
   //  pair of one cell or of adjacent cells exactly once, M4 takes minima over index)
+  clk.mark(STAGE_M1);
   // ---- M2: candidate pairs ------------------------------------------------------------------------
   //  a) by distance: position s against the positions behind it up to the end of the next cell, four at a time,
   //     branch-free; the hits (|d|^2 <= largest reach^2) are compacted into a list in label[] (not in use yet).
@@ -547,6 +590,7 @@ __device__ __forceinline__ int merge_clustered(T* cur, const MergeScratch<T>& ms
   }
   __syncwarp();
   for (int k = lane; k < npass && k < MAX_PAIRS; k += 32) ms.pairs[k] = passing[k];
+  clk.mark(STAGE_M2);
   if (npass == 0) return MERGE_OK;
   if (npass > MAX_PAIRS) { mstat[1]++; return MERGE_FALLBACK; }
   mstat[5] += (unsigned)npass;
@@ -640,6 +684,7 @@ __device__ __forceinline__ int merge_clustered(T* cur, const MergeScratch<T>& ms
       }
     }
     __syncwarp();
+    clk.mark(STAGE_M3);
     // ---- M4: one lane per cluster; read-only on the mixture -----------------------------------------
     bool conflict = false, logfull = false;
     auto is_dead = [&](int k) -> bool { return (ms.deadBits[k >> 5] >> (k & 31)) & 1u; };
@@ -731,6 +776,7 @@ __device__ __forceinline__ int merge_clustered(T* cur, const MergeScratch<T>& ms
       }
       __syncwarp();
     }
+    clk.mark(STAGE_M4);
     if (__any_sync(FULL, logfull)) { mstat[3]++; return MERGE_FALLBACK; }
     if (!__any_sync(FULL, conflict)) {
       // ---- M5: commit --------------------------------------------------------------------------------
@@ -1201,29 +1247,6 @@ __device__ __forceinline__ void step_epilogue(const KParams<T>& p, int lane, int
         red[1][0] = tb;
       }
     }
-    if (threadIdx.x == 0) {
-      const double a = red[0][0], b = red[1][0];
-      p.sums[0] = a;
-      p.sums[1] = b;
-      red[0][0] = a;
-      // publish the step statistics and re-arm the accumulators / queue for the next launch
-      p.stats_out[0] = __ldcg(&p.totals[0]);
-      p.stats_out[1] = __ldcg(&p.totals[1]);
-      p.stats_out[2] = (unsigned long long)(unsigned)__ldcg(&p.istats[0]);
-      p.stats_out[3] = (unsigned long long)(unsigned)__ldcg(&p.istats[1]);
-      p.stats_out[4] = (unsigned long long)(unsigned)__ldcg(&p.istats[2]);
-      p.stats_out[5] = (unsigned long long)(unsigned)__ldcg(&p.istats[3]);
-      for (int k = 0; k < 7; k++) { p.stats_out[6 + k] = (unsigned long long)__ldcg(&p.mstats[k]); p.mstats[k] = 0u; }
-      if (p.stats_host) {
-        p.stats_host[0] = (unsigned long long)__double_as_longlong(a);
-        p.stats_host[1] = (unsigned long long)__double_as_longlong(b);
-        for (int k = 0; k < 13; k++) p.stats_host[2 + k] = p.stats_out[k];
-      }
-      p.totals[0] = 0; p.totals[1] = 0;
-      p.istats[0] = 0; p.istats[1] = 0; p.istats[2] = 0; p.istats[3] = 0;
-      *p.ticket = 0;
-      *p.work_counter = 0;
-    }
     if (p.fused_normalize && in_regs) {   // ParticleFilter::normalizeWeights, in the same launch
       __syncthreads();
       const double total = red[0][0];
@@ -1253,6 +1276,29 @@ __device__ __forceinline__ void step_epilogue(const KParams<T>& p, int lane, int
         p.w_out[i] = w;
         if (p.w_host) p.w_host[i] = w;
       }
+    }
+    // (after the normalisation, which every thread of the CTA is waiting for)
+    if (threadIdx.x == 0) {
+      const double a = red[0][0], b = red[1][0];
+      p.sums[0] = a;
+      p.sums[1] = b;
+      // publish the step statistics and re-arm the accumulators / queue for the next launch
+      p.stats_out[0] = __ldcg(&p.totals[0]);
+      p.stats_out[1] = __ldcg(&p.totals[1]);
+      p.stats_out[2] = (unsigned long long)(unsigned)__ldcg(&p.istats[0]);
+      p.stats_out[3] = (unsigned long long)(unsigned)__ldcg(&p.istats[1]);
+      p.stats_out[4] = (unsigned long long)(unsigned)__ldcg(&p.istats[2]);
+      p.stats_out[5] = (unsigned long long)(unsigned)__ldcg(&p.istats[3]);
+      for (int k = 0; k < 7; k++) { p.stats_out[6 + k] = (unsigned long long)__ldcg(&p.mstats[k]); p.mstats[k] = 0u; }
+      if (p.stats_host) {
+        p.stats_host[0] = (unsigned long long)__double_as_longlong(a);
+        p.stats_host[1] = (unsigned long long)__double_as_longlong(b);
+        for (int k = 0; k < 13; k++) p.stats_host[2 + k] = p.stats_out[k];
+      }
+      p.totals[0] = 0; p.totals[1] = 0;
+      p.istats[0] = 0; p.istats[1] = 0; p.istats[2] = 0; p.istats[3] = 0;
+      *p.ticket = 0;
+      *p.work_counter = 0;
     }
   }
 }
@@ -1301,13 +1347,13 @@ __host__ __device__ inline int z_bytes() {
 
 // threads per CTA the kernel is compiled for: the fp32 single-cluster kernel fits 96 registers (20 warps per SM),
 // the multi-feature and the fp64 kernels need 128 (16 warps)
-template <typename T, bool MF>
-constexpr int update_max_threads() { return (sizeof(T) == 4 && !MF) ? 32 * MAX_WARPS_PER_CTA : 512; }
+template <typename T, bool MF, bool PROF = false>
+constexpr int update_max_threads() { return (sizeof(T) == 4 && !MF && !PROF) ? 32 * MAX_WARPS_PER_CTA : 512; }
 
 // WT: the work capacity W as a compile-time constant (0: p.W at run time).  With W known, every plane of a warp's
 // block is addressed as one register plus an immediate offset; the fp32 kernels are instantiated for W = 256.
-template <typename T, bool MF, int WT>
-__global__ void __launch_bounds__((update_max_threads<T, MF>()), 1)
+template <typename T, bool MF, int WT, bool PROF = false>
+__global__ void __launch_bounds__((update_max_threads<T, MF, PROF>()), 1)
 phd_update_kernel(const __grid_constant__ KParams<T> p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
@@ -1315,6 +1361,9 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
   const int W = WT ? WT : p.W;
   const int nZ = p.nZ;
   constexpr int NPL = MF ? 7 : 6;   // MF = multi-feature weighting (p.use_sc == 0)
+  if constexpr (PROF) {
+    if (threadIdx.x == 0) atomicMin(&p.prof[12], globaltimer_ns());
+  }
 
   T* zs = reinterpret_cast<T*>(smem_raw);          // [2*MAX_Z]: zr[z] at 2z, zb[z] at 2z+1
   unsigned long long* tabR = reinterpret_cast<unsigned long long*>(zs + 2 * MAX_Z);   // [NBINS+1]
@@ -1385,12 +1434,17 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
     fence_mbar_init();
   }
   __syncthreads();
+  if constexpr (PROF) {
+    if (threadIdx.x == 0) atomicMax(&p.prof[13], globaltimer_ns());
+  }
   const T binR0 = binp[0], binRi = binp[1], binB0 = binp[2], binBi = binp[3];
   auto bin_of = [](T v, T v0, T inv) -> int {   // monotone in v; NaN -> 0
     return (int)M<T>::min_(M<T>::max_((v - v0) * inv, T(0)), T(NBINS - 1));
   };
   const T r_hi_in = p.rmax - p.rbuf, r_lo_in = p.rmin + p.rbuf, r_hi_out = p.rmax + p.rbuf, r_lo_out = p.rmin - p.rbuf;
 
+  StageClock<PROF> clk;
+  clk.start();
   uint32_t phase = 0;
   unsigned long long tot_in = 0, tot_out = 0;
   int max_out = 0, n_over = 0, n_murty = 0, n_fallback = 0;
@@ -1409,7 +1463,7 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
     T* cur = bufA;
     int nM = p.cnt_in[pi];
     nM = nM < 0 ? 0 : (nM > p.cap ? p.cap : nM);
-    int flags = 0;
+    int flags = (p.flags[pi] & FLAG_BIRTH_OVERFLOW) ? FLAG_OVERFLOW : 0;
     if (nM > W) { nM = W; flags |= FLAG_OVERFLOW; }
 
     // ---------------- S0: TMA bulk loads -------------------------------------------------
@@ -1434,6 +1488,7 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
       phase ^= 1;
     }
 
+    clk.mark(STAGE_LOAD);
     // ---------------- S1: corrector --------------------------------------------------------
     int nS = 0;                 // survivors appended so far
     double wsum_d = 0;          // sum of pre-update weights (SC-PHD)
@@ -1653,6 +1708,7 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
     g_bad = __any_sync(FULL, g_bad);
     __syncwarp();
 
+    clk.mark(STAGE_CORRECT);
     double weight_new = w_prev_particle;
     unsigned long long unused_mask = 0;
     if (nM == 0) {
@@ -1707,6 +1763,7 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
       __syncwarp();
     }
 
+    clk.mark(STAGE_WEIGHT);
     // ---------------- S5: multi-feature importance weighting ----------------------------------
     if constexpr (MF) {
       int nEvalCfg = p.n_eval < n ? p.n_eval : n;
@@ -1926,17 +1983,19 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
       }
     }
 
+    clk.mark(STAGE_MFWEIGHT);
     // ---------------- S6: merge ------------------------------------------------------------------
     if (lane == 0) pi_next = (int)atomicAdd(p.work_counter, 1u);   // first needed after the merge
     if (n > 1) {
       int st = MERGE_FALLBACK;
-      if (p.merge_algo != 0) st = merge_clustered<T>(cur, ms, W, n, p.merge_t2, p.merge_f, MF, lane, mstat, g_xmin, g_xmax, g_trmax, g_bad);
+      if (p.merge_algo != 0) st = merge_clustered<T, PROF>(cur, ms, W, n, p.merge_t2, p.merge_f, MF, lane, mstat, g_xmin, g_xmax, g_trmax, g_bad, clk);
       __syncwarp();
       if (st == MERGE_FALLBACK && p.merge_algo != 0) n_fallback++;
       if (st == MERGE_FALLBACK) merge_bruteforce<T>(cur, W, n, p.merge_t2, p.merge_f, lane);
     }
     __syncwarp();
 
+    clk.mark(STAGE_MERGE);
     // ---------------- S7: prune + store ------------------------------------------------------------
     int nM_next = 0;
     if (lane == 0 && pi_next < p.N) nM_next = p.cnt_in[pi_next];   // first needed after the sort
@@ -2052,8 +2111,13 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
     if (flags & (FLAG_OVERFLOW | FLAG_DP_OVERFLOW)) n_over++;
     if (flags & FLAG_MURTY) n_murty++;
     pi = __shfl_sync(FULL, pi_next, 0);
+    clk.mark(STAGE_PRUNE);
   }
+  clk.flush(p.prof, lane);
   step_epilogue<T>(p, lane, warp, tot_in, tot_out, max_out, n_over, n_murty, n_fallback, mstat);
+  if constexpr (PROF) {
+    if (threadIdx.x == 0) atomicMax(&p.prof[15], globaltimer_ns());
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -2111,7 +2175,7 @@ __global__ void predict_maps_kernel(const PredictParams<T> p) {
     if (lane == 0) {
       p.cnt[pi] = n;
       p.unused[pi] = 0ull;
-      if (over) p.flags[pi] |= FLAG_OVERFLOW;
+      if (over) p.flags[pi] |= FLAG_OVERFLOW | FLAG_BIRTH_OVERFLOW;
     }
     __syncwarp();
   }

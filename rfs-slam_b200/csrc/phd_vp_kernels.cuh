@@ -265,7 +265,7 @@ phd_update_vp_kernel(const __grid_constant__ VPParams<T> vp) {
     const double w_prev_particle = p.w_in[pi];
     int nM = p.cnt_in[pi];
     nM = nM < 0 ? 0 : (nM > p.cap ? p.cap : nM);
-    int flags = 0;
+    int flags = (p.flags[pi] & FLAG_BIRTH_OVERFLOW) ? FLAG_OVERFLOW : 0;
     if (nM > W) { nM = W; flags |= FLAG_OVERFLOW; }
 
     // ---------------- S0: TMA bulk loads ---------------------------------------------------------
@@ -899,7 +899,7 @@ __global__ void predict_maps_vp_kernel(const VPPredictParams<T> p) {
     if (lane == 0) {
       p.cnt[pi] = n;
       p.unused[pi] = 0ull;
-      if (over) p.flags[pi] |= FLAG_OVERFLOW;
+      if (over) p.flags[pi] |= FLAG_OVERFLOW | FLAG_BIRTH_OVERFLOW;
     }
     __syncwarp();
   }

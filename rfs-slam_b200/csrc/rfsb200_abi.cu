@@ -101,6 +101,9 @@ struct rfsb200_ctx {
   unsigned long long* stats_host = nullptr;
   std::vector<cudaEvent_t> prof_ev;   // event pairs around the update kernel (rfsb200_profile_*)
   int prof_cap = 0, prof_n = 0;
+  unsigned long long* prof_dev = nullptr;   // [16] stage-timing build (KParams::prof)
+  bool prof_valid = false;                  // an update with RFSB200_UPDATE_STAGE_TIMES ran since the last read
+  int prof_nwarps = 0;
   int grid = 0;
   int nwarps = 4;   // warps per CTA of the update kernel
   size_t smem_bytes = 0;
@@ -193,7 +196,7 @@ __global__ void append_soa_kernel(const int* __restrict__ add, const long long* 
   __syncwarp();
   if (lane == 0) {
     cnt[pi] = n0 + fit;
-    if (fit < na) flags[pi] |= FLAG_OVERFLOW;
+    if (fit < na) flags[pi] |= FLAG_OVERFLOW | FLAG_BIRTH_OVERFLOW;
   }
 }
 
@@ -331,8 +334,10 @@ int round_pow2(int v) {
 // CTA ends with a block-wide barrier, so FEWER, LARGER CTAs are better as long as the SMs hold as many warps: measured on
 // C3, 16 warps in one CTA per SM run the step in 141 us, 4 CTAs of 4 warps in 172 us.  Choose, in this order: most
 // particles in flight, most SMs in use (small shards), then the largest CTA.
+struct LaunchShape { int nwarps = 0, grid = 0; size_t smem = 0; };
+
 template <typename K>
-int choose_warps_per_cta(rfsb200_ctx* c, K kernel, size_t cta_bytes, size_t warp_bytes, int max_warps) {
+int choose_launch_shape(rfsb200_ctx* c, K kernel, size_t cta_bytes, size_t warp_bytes, int max_warps, LaunchShape* out) {
   int best_nw = 0, best_occ = 0, best_sms = -1;
   long long best_res = -1;
   int nw_lo = 1, nw_hi = max_warps;   // (the kernel's launch bounds) large work capacities / the fp64 build may only fit a few warps
@@ -353,11 +358,21 @@ int choose_warps_per_cta(rfsb200_ctx* c, K kernel, size_t cta_bytes, size_t warp
   if (best_nw == 0 || best_occ < 1)
     return fail(c, RFSB200_ECAPACITY, "work_capacity %d needs %zu B shared memory per CTA (> 227 KB)", c->W,
                 cta_bytes + (size_t)nw_lo * warp_bytes);
-  c->nwarps = best_nw;
-  c->smem_bytes = cta_bytes + (size_t)best_nw * warp_bytes;
-  CU(c, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
+  out->nwarps = best_nw;
+  out->smem = cta_bytes + (size_t)best_nw * warp_bytes;
+  CU(c, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)out->smem));
   const int need = (c->N + best_nw - 1) / best_nw;
-  c->grid = std::max(1, std::min(need, best_occ * c->sm_count));
+  out->grid = std::max(1, std::min(need, best_occ * c->sm_count));
+  return RFSB200_OK;
+}
+template <typename K>
+int choose_warps_per_cta(rfsb200_ctx* c, K kernel, size_t cta_bytes, size_t warp_bytes, int max_warps) {
+  LaunchShape sh;
+  const int rc = choose_launch_shape(c, kernel, cta_bytes, warp_bytes, max_warps, &sh);
+  if (rc) return rc;
+  c->nwarps = sh.nwarps;
+  c->smem_bytes = sh.smem;
+  c->grid = sh.grid;
   return RFSB200_OK;
 }
 
@@ -483,7 +498,30 @@ int launch_update(rfsb200_ctx* c, int nZ, int out_idx, unsigned flags) {
   }
   const bool prof = c->prof_n < c->prof_cap;
   if (prof) CU(c, cudaEventRecord(c->prof_ev[2 * c->prof_n], c->stream));
-  if (c->ld == 3) {
+  if (flags & RFSB200_UPDATE_STAGE_TIMES) {
+    // the stage-timing build of the kernel (fp32, 2-D model): same results, clocks read at the stage boundaries
+    if constexpr (sizeof(T) == 4) {
+      if (c->ld != 2) return fail(c, RFSB200_EUNSUPPORTED, "RFSB200_UPDATE_STAGE_TIMES: 2-D model only");
+      if (!c->prof_dev) CU(c, cudaMalloc((void**)&c->prof_dev, 16 * 8));
+      unsigned long long init[16] = {};
+      init[12] = ~0ull;
+      // (pageable source: the copy is staged before the call returns)
+      CU(c, cudaMemcpyAsync(c->prof_dev, init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
+      p.prof = c->prof_dev;
+      LaunchShape sh;
+      int rc;
+      if (mf) rc = choose_launch_shape(c, phd_update_kernel<T, true, 0, true>, (size_t)z_bytes<T>(), (size_t)c->warp_bytes, update_max_threads<T, true, true>() / 32, &sh);
+      else rc = choose_launch_shape(c, phd_update_kernel<T, false, 0, true>, (size_t)z_bytes<T>(), (size_t)c->warp_bytes, update_max_threads<T, false, true>() / 32, &sh);
+      if (rc) return rc;
+      if (mf && c->dp_gmaxb && (size_t)sh.grid * sh.nwarps > (size_t)c->grid * c->nwarps) p.dp_scratch = nullptr;   // workspace sized for the product launch
+      if (mf) phd_update_kernel<T, true, 0, true><<<sh.grid, sh.nwarps * 32, sh.smem, c->stream>>>(p);
+      else phd_update_kernel<T, false, 0, true><<<sh.grid, sh.nwarps * 32, sh.smem, c->stream>>>(p);
+      c->prof_valid = true;
+      c->prof_nwarps = sh.nwarps;
+    } else {
+      return fail(c, RFSB200_EUNSUPPORTED, "RFSB200_UPDATE_STAGE_TIMES: fp32 build only");
+    }
+  } else if (c->ld == 3) {
     VPParams<T> v{};
     v.k = p;
     v.R00 = (T)m.R[0]; v.R01 = (T)m.R[1]; v.R10 = (T)m.R[3]; v.R11 = (T)m.R[4]; v.R22 = (T)m.R[8];
@@ -747,7 +785,7 @@ int rfsb200_destroy(rfsb200_ctx* c) {
   cudaFree(c->comm_mail); cudaFree(c->comm_error);
   cudaFree(c->sums); cudaFree(c->totals); cudaFree(c->istats); cudaFree(c->ticket);
   cudaFree(c->work_counter); cudaFree(c->stats_out); cudaFree(c->mstats);
-  cudaFree(c->stg); cudaFree(c->offs); cudaFree(c->stg_small); cudaFree(c->scan_dev); cudaFree(c->dp_scratch);
+  cudaFree(c->stg); cudaFree(c->offs); cudaFree(c->stg_small); cudaFree(c->scan_dev); cudaFree(c->dp_scratch); cudaFree(c->prof_dev);
   if (c->hpin) { forget_pinned(c->hpin); cudaFreeHost(c->hpin); }
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
@@ -1427,6 +1465,38 @@ int rfsb200_profile_begin(rfsb200_ctx* c, int32_t max_updates) {
   }
   c->prof_cap = max_updates;
   c->prof_n = 0;
+  return RFSB200_OK;
+}
+
+int rfsb200_get_stage_times(rfsb200_ctx* c, rfsb200_stage_times* out) {
+  if (!c) return fail(nullptr, RFSB200_EINVAL, "NULL ctx");
+  if (!out) return fail(c, RFSB200_EINVAL, "rfsb200_get_stage_times: NULL argument");
+  if (!c->prof_valid || !c->prof_dev) return fail(c, RFSB200_ESTATE, "no update ran with RFSB200_UPDATE_STAGE_TIMES");
+  CU(c, cudaSetDevice(c->device));
+  unsigned long long h[16];
+  CU(c, cudaStreamSynchronize(c->stream));
+  CU(c, cudaMemcpy(h, c->prof_dev, sizeof(h), cudaMemcpyDeviceToHost));
+  *out = rfsb200_stage_times{};
+  const double t0 = (double)h[12];
+  out->kernel_us = ((double)h[15] - t0) * 1e-3;
+  out->setup_us = ((double)h[13] - t0) * 1e-3;
+  out->particles_us = ((double)h[14] - (double)h[13]) * 1e-3;
+  out->epilogue_us = ((double)h[15] - (double)h[14]) * 1e-3;
+  double tot = 0;
+  for (int k = 0; k < N_STAGES; k++) tot += (double)h[k];
+  out->warp_cycles = tot;
+  if (tot > 0) {
+    out->share_load = (double)h[STAGE_LOAD] / tot;
+    out->share_map_update_kf = (double)h[STAGE_CORRECT] / tot;
+    out->share_weighting = ((double)h[STAGE_WEIGHT] + (double)h[STAGE_MFWEIGHT]) / tot;
+    out->share_merge = ((double)h[STAGE_MERGE] + (double)h[STAGE_M1] + (double)h[STAGE_M2] + (double)h[STAGE_M3] + (double)h[STAGE_M4]) / tot;
+    out->reserved[0] = (double)h[STAGE_M1] / tot;   // inside the merge: cell sort, pair search, clusters, per-cluster greedy loops
+    out->reserved[1] = (double)h[STAGE_M2] / tot;
+    out->reserved[2] = (double)h[STAGE_M3] / tot;
+    out->reserved[3] = (double)h[STAGE_M4] / tot;
+    out->share_prune = (double)h[STAGE_PRUNE] / tot;
+  }
+  out->warps_per_cta = c->prof_nwarps;
   return RFSB200_OK;
 }
 

@@ -327,6 +327,14 @@ class PHDUpdater:
         _check(self.lib, self.ctx, self.lib.rfsb200_profile_read(self.ctx, capi.ptr(us), 4096, C.byref(n)), "profile_read")
         return us[:n.value].copy()
 
+    def stage_times(self) -> dict:
+        """Per-phase times of the last update that ran with capi.UPDATE_STAGE_TIMES (rfsb200_get_stage_times)."""
+        st = capi.StageTimes()
+        _check(self.lib, self.ctx, self.lib.rfsb200_get_stage_times(self.ctx, C.byref(st)), "stage_times")
+        d = {k: getattr(st, k) for k, _ in capi.StageTimes._fields_ if not k.startswith("reserved")}
+        d["merge_parts"] = dict(zip(("cell_sort", "pair_search", "clusters", "cluster_loops"), list(st.reserved)))
+        return d
+
     def permanent(self, A) -> np.ndarray:
         A = np.ascontiguousarray(A, dtype=np.float64)
         if A.ndim == 2:

@@ -74,6 +74,11 @@ inline unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
   simt::spin_yield();
   return v;
 }
+inline long long clock64() {   // the SM clock of the stage-timing kernels: host nanoseconds here
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (long long)ts.tv_sec * 1000000000ll + (long long)ts.tv_nsec;
+}
 inline unsigned long long globaltimer_ns() {
   timespec ts;
   clock_gettime(CLOCK_MONOTONIC, &ts);

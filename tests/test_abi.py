@@ -57,14 +57,15 @@ def test_bad_arguments_are_rejected_without_a_device():
 
 def test_struct_layout_matches_c(tmp_path):
     prog = tmp_path / "sz.c"
-    prog.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "rfsb200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu\\n",'
+    prog.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "rfsb200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",'
                     'sizeof(rfsb200_dims),sizeof(rfsb200_model_desc),sizeof(rfsb200_filter_cfg),sizeof(rfsb200_step_out),'
-                    'offsetof(rfsb200_model_desc,Pd),offsetof(rfsb200_filter_cfg,eval_point_count),offsetof(rfsb200_step_out,elapsed_us));return 0;}\n')
+                    'offsetof(rfsb200_model_desc,Pd),offsetof(rfsb200_filter_cfg,eval_point_count),offsetof(rfsb200_step_out,elapsed_us),sizeof(rfsb200_stage_times),offsetof(rfsb200_stage_times,warps_per_cta));return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(prog), "-o", str(exe)], check=True)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
     got = [C.sizeof(capi.Dims), C.sizeof(capi.ModelDesc), C.sizeof(capi.FilterCfg), C.sizeof(capi.StepOut),
-           capi.ModelDesc.Pd.offset, capi.FilterCfg.eval_point_count.offset, capi.StepOut.elapsed_us.offset]
+           capi.ModelDesc.Pd.offset, capi.FilterCfg.eval_point_count.offset, capi.StepOut.elapsed_us.offset,
+           C.sizeof(capi.StageTimes), capi.StageTimes.warps_per_cta.offset]
     assert [int(x) for x in out] == got
 
 
