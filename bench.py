@@ -151,7 +151,7 @@ def run_reference_arm(a):
     wl, desc = make_workload(a.config, 0)
     nM = int(round(wl.count.mean()))
     threads = len(os.sched_getaffinity(0))
-    n_s = min(wl.N, a.ref_particles)
+    n_s = min(wl.N, a.ref_particles)   # the whole C3 shard (8000 particles, about 0.6 s per step on 16 threads)
     kind, sub, _ = cpu_reference_run(wl, n_s, threads, max(0, a.warmup))
     _, _, ts = cpu_reference_run(wl, n_s, threads, a.steps)
     t = sum(ts) / len(ts)
@@ -166,7 +166,7 @@ def run_reference_arm(a):
     except Exception:
         single = None
     line = dict(metric=METRIC, value=v, unit=UNIT, n_gpus=a.gpus, steps=a.steps, warmup=a.warmup,
-                ms_per_step=1e3 * t, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
+                ms_per_step=1e3 * t, higher_is_better=True, scaling=a.scaling, vs_baseline=None, dtype="f64",
                 data="synthetic", impl="reference",
                 config=dict(workload=desc, particles_per_step=sub.N, gm_per_particle=nM, meas=sub.nZ),
                 cpu_baseline=dict(value=v, unit=UNIT, cores=threads, kind=kind, sample=sample, single_thread=single),
@@ -177,64 +177,59 @@ def run_reference_arm(a):
 
 
 # ------------------------------------------------------------------------------------------------
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", default="C3", choices=sorted(WORKLOADS))
-    ap.add_argument("--particles", type=int, default=0, help="override particles per GPU")
-    ap.add_argument("--ref-particles", type=int, default=2000, help="--impl reference: particles per step")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-fused", action="store_true", help="NCCL all-reduce + normalise kernel instead of the in-kernel sum over peer memory")
-    a = ap.parse_args()
-    a.warmup = max(a.warmup, 0)
-    # stdout carries exactly ONE JSON line: everything libraries print (NCCL's version banner, ...)
-    # goes to stderr, the line itself is written to the saved descriptor at the end
-    sys.stdout.flush()
-    global _REAL_STDOUT
-    _REAL_STDOUT = os.dup(1)
-    os.dup2(2, 1)
-    if a.impl == "reference":
-        return run_reference_arm(a)
-    if a.warmup < 3:
-        a.warmup = 3   # timing rule: at least 3 warm-up steps
+def _kernel_fingerprint():
+    """sha256 of the kernel sources: an ncu figure recorded for another build of the kernel is never reported."""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "rfs-slam_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh")):
+            h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
 
+
+def _ncu_record(config):
+    """(dram bytes per launch, warp instructions per launch) of the last committed ncu capture of this workload — only if
+    it was taken from the kernel sources that are running now (profiles/traffic.json carries their fingerprint)."""
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        d = json.load(open(tp))
+    except Exception:
+        return None, None, "no capture"
+    rec = d.get(config)
+    if not isinstance(rec, dict):
+        return None, None, "no capture of this workload"
+    if rec.get("kernel_fingerprint") != _kernel_fingerprint():
+        return None, None, "the committed ncu capture is of another build of the kernel"
+    return rec.get("dram_bytes"), rec.get("warp_instructions"), rec.get("capture")
+
+
+def run_workload(a, name, ctx, steps, warmup, headline):
+    """One workload on this rank's GPU: device-resident steps, the host-facing step, the stage times, the live roofline.
+    Returns the JSON line (rank 0) or None."""
     import numpy as np
     import torch
     import torch.distributed as dist
-    import rfs_slam_b200  # noqa: F401
     from rfs_slam_b200 import capi
     from rfs_slam_b200.dist import ShardedUpdater
     from rfs_slam_b200.phd import PHDUpdater, pinned_array
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device — the PHD update path has no CPU fallback")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-
-    # one non-default stream carries the library's kernels, torch's events / memsets and NCCL
-    stream = torch.cuda.Stream(dev)
-    torch.cuda.set_stream(stream)
-
-    wl, desc = make_workload(a.config, rank, a.particles)
+    rank, world, local, dev, flush = ctx["rank"], ctx["world"], ctx["local"], ctx["dev"], ctx["flush"]
+    n_override = a.particles
+    if a.scaling == "strong":   # the total is fixed, every GPU owns 1 / world of it
+        total = a.particles_total or WORKLOADS[name][1]
+        n_override = max(1, total // world)
+    wl, desc = make_workload(name, rank, n_override)
     N, nZ = wl.N, wl.nZ
     units_local = int(wl.count.sum()) * nZ
     D = wl.dim                                  # 2: RngBrg, 3: VictoriaPark
     gbytes = 4.0 * (D + D * (D + 1) // 2 + 1)   # fp32 bytes per Gaussian: 24 (2-D) / 40 (3-D)
     up = PHDUpdater(N, gm_capacity=256, z_capacity=32, device=local, precision=32, lmk_dim=D)
     up.load_workload(wl)
-    sh = ShardedUpdater(up, device=dev, fused=not a.no_fused)
     fused = not a.no_fused
+    sh = ShardedUpdater(up, device=dev, fused=fused)
+    fused = sh.fused
     up.synchronize()
-    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
     FLAGS = capi.UPDATE_NO_COMMIT   # every step starts from the same state, so nM_in is constant
 
     def barrier():
@@ -243,15 +238,35 @@ def main():
         torch.cuda.synchronize()
 
     # ---- warm-up (also warms NCCL) -------------------------------------------------------------
-    for _ in range(a.warmup):
+    for _ in range(warmup):
         flush.zero_()
         sh.step(wl.Z, flags=FLAGS)
     torch.cuda.synchronize()
     so = up.update(wl.Z, flags=FLAGS | capi.UPDATE_NO_NORMALIZE)   # statistics of one step
     nM_out_mean = so.gm_total_out / N
+    n_murty = int(so.n_murty)
+    n_overflow = int(so.n_overflow)
+
+    # ---- cross-GPU check (untimed): the in-kernel sum over peer memory against the NCCL all-reduce ----------------
+    collective_check = None
+    if world > 1 and fused:
+        sh.step(wl.Z, flags=FLAGS)
+        w_f = up.get_weights(1).copy()
+        s_f = sh.sums.cpu().numpy().copy()
+        sh.fused = False
+        sh.step(wl.Z, flags=FLAGS)
+        w_n = up.get_weights(1).copy()
+        s_n = sh.sums.cpu().numpy().copy()
+        sh.fused = True
+        same = bool(np.array_equal(w_f.view(np.uint64), w_n.view(np.uint64)) and np.array_equal(s_f.view(np.uint64), s_n.view(np.uint64)))
+        t = torch.tensor([1 if same else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        collective_check = "bit-identical" if int(t.item()) == 1 else "DIFFERS"
+        if up.comm_error():
+            collective_check = "comm_error"
 
     # ---- timed region: K steps, device-timed, L2 flushed between steps -----------------------------
-    K = a.steps
+    K = steps
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     up.profile_begin(K)
     clocks = ClockSampler(local)
@@ -259,15 +274,18 @@ def main():
     if rank == 0:
         clocks.start()
     t_wall0 = time.perf_counter()
-    align = torch.zeros(1, dtype=torch.float32, device=dev)
 
     def flush_and_align():
         flush.zero_()                 # > L2 (126 MB): the step reads its inputs from HBM
         if world > 1:
             # the 512 MiB memset is a measurement artefact whose duration differs from GPU to GPU; back-to-back
-            # steps of a real run start aligned by the previous step's collective, so the ranks are re-aligned
-            # here (untimed, on the launch stream) before the step's first event
-            dist.all_reduce(align)
+            # steps of a real run start aligned by the previous step's exchange, so the ranks are re-aligned here
+            # (untimed, on the launch stream) before the step's first event: the library's own mailbox barrier when the
+            # peer mailboxes are connected (ranks leave it within an NVLink round trip), else a 4-byte all-reduce
+            if fused:
+                up.comm_barrier()
+            else:
+                dist.all_reduce(ctx["align"])
 
     for k in range(K):
         flush_and_align()
@@ -288,8 +306,9 @@ def main():
     t_max = float(tt.item())
     units_total = float(uu.item())
     value = units_total * K / t_max
+    comm_err = int(up.comm_error()) if world > 1 and fused else 0
 
-    # ---- e2e: the same step through the C ABI with HOST buffers -------------------------------------
+    # ---- e2e: the same step through the C ABI with HOST buffers, timed on the HOST clock ------------------------
     e2e = None
     if not a.no_e2e:
         h_pose = pinned_array((N, 3)); h_pose[:] = wl.pose
@@ -298,7 +317,6 @@ def main():
         h_mask = pinned_array((N,), np.uint64)
         h_nfov = pinned_array((N,), np.int32)
         pc = wl.pose_cov
-
         md_desc = capi.model_desc(wl.model)
         Zc = np.ascontiguousarray(wl.Z, dtype=np.float64)
 
@@ -314,32 +332,47 @@ def main():
         barrier()
         Ke = K
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        te = 0.0
-        tw0 = time.perf_counter()
+        te_host, te_dev = 0.0, 0.0
         for _ in range(Ke):
             flush_and_align()
+            torch.cuda.synchronize()          # the flush (and the alignment) are over: nothing of the step can hide under them
             e0.record()
-            e2e_step()
+            t0 = time.perf_counter()
+            e2e_step()                        # returns after its own synchronisation: the results are in the host buffers
+            te_host += time.perf_counter() - t0
             e1.record()
             e1.synchronize()
-            te += e0.elapsed_time(e1) / 1e3
+            te_dev += e0.elapsed_time(e1) / 1e3
         barrier()
-        tw = time.perf_counter() - tw0
-        tt = torch.tensor([te], dtype=torch.float64, device=dev)
+        tt = torch.tensor([te_host, te_dev], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        te_max = float(tt.item())
+        te_max, td_max = float(tt[0].item()), float(tt[1].item())
         h2d = N * 3 * 8 + N * 8 + (6 * 8 if pc is not None else 0) + nZ * D * 8 + (len(wl.model["scan"]) * 8 if D == 3 else 0)
         d2h = N * 8 + N * 8 + N * 4
         e2e = dict(value=units_total * Ke / te_max, unit=UNIT, h2d_bytes_per_step=h2d * world, d2h_bytes_per_step=d2h * world,
-                   ms_per_step=1e3 * te_max / Ke, wall_ms_per_step_incl_flush=1e3 * tw / Ke,
-                   what=("per step: rfsb200_update_host = pinned host poses + particle weights + Z in (read over PCIe by one "
-                         "conversion kernel), update (+ cross-GPU sum + normalisation), normalised weights + unused-measurement "
-                         "masks + in-FOV counts out (stored by the update kernel straight into the pinned host buffers), one "
-                         "synchronisation; maps stay resident in HBM; RFSB200_ZERO_COPY=0 stages the same bytes through copies"
+                   ms_per_step=1e3 * te_max / Ke, timer="host", device_ms=1e3 * td_max / Ke,
+                   what=("host perf_counter around ONE rfsb200_update_host call per step (L2 flush finished and synchronised "
+                         "before the clock starts): pinned host poses + particle weights + Z in, update (+ cross-GPU sum + "
+                         "normalisation), normalised weights + unused-measurement masks + in-FOV counts out in pinned host "
+                         "buffers when the call returns; maps stay resident in HBM; max over ranks. device_ms = the same "
+                         "span between CUDA events"
                          if fused else
-                         "per step: rfsb200_set_poses(pinned host poses+weights) + rfsb200_update(host Z) + NCCL all-reduce + "
-                         "rfsb200_normalize + rfsb200_get_weights + rfsb200_get_unused into pinned host buffers; maps stay resident"))
+                         "host perf_counter around rfsb200_set_poses(pinned host poses+weights) + rfsb200_update(host Z) + NCCL "
+                         "all-reduce + rfsb200_normalize + rfsb200_get_weights + rfsb200_get_unused into pinned host buffers; maps stay resident"))
+
+    # ---- stage times (untimed extra steps with the stage-timing build of the kernel) ------------------------------
+    stages = None
+    if D == 2 and not a.no_stages:
+        try:
+            for _ in range(2):
+                flush.zero_()
+                up.update(wl.Z, flags=FLAGS | capi.UPDATE_NO_NORMALIZE | capi.UPDATE_STAGE_TIMES)
+            stages = up.stage_times()
+            stages["note"] = ("one fused kernel: wall time split into set-up / particle loop / epilogue by the device global "
+                              "timer, the particle loop attributed to the phases by warp cycles (TimingInfo of the reference)")
+        except Exception as e:   # noqa: BLE001
+            stages = dict(error=str(e))
 
     # ---- roofline of the dominant kernel (phd_update_kernel), live ------------------------------------
     peak, peak_src = _peaks()
@@ -350,57 +383,132 @@ def main():
         b_alg += 8.0 * len(wl.model["scan"])
     k_us = float(np.mean(kern_us)) if len(kern_us) else float("nan")
     achieved = b_alg / (k_us * 1e-6) / 1e9
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tp):
-        try:
-            traffic = json.load(open(tp)).get(a.config)
-        except Exception:
-            traffic = None
-    # the roof that actually bounds this kernel: warp instructions per launch (ncu, same capture
-    # as `traffic`) against the issue slots of the launch, 148 SMs x 4 schedulers x SM clock x kernel time
+    traffic, n_inst, cap_src = (None, None, None)
+    if N == WORKLOADS[name][1] and a.scaling == "weak":
+        traffic, n_inst, cap_src = _ncu_record(name)
     issue = None
-    try:
-        n_inst = json.load(open(tp)).get(a.config + "_warp_instructions")
-        if n_inst and N == WORKLOADS[a.config][1] and clk is not None:
-            sm_hz = 1e6 * float(clk.get("sm_mhz") or clk.get("sm_max_mhz") or 1965.0)
-            slots = 148 * 4 * sm_hz * k_us * 1e-6
-            issue = dict(warp_instructions=int(n_inst), issue_slots=slots, frac=n_inst / slots,
-                         note="instruction-issue roofline: the kernel is issue / latency bound, not HBM bound")
-    except Exception:
-        issue = None
+    if n_inst and clk is not None:
+        sm_hz = 1e6 * float(clk.get("sm_mhz") or clk.get("sm_max_mhz") or 1965.0)
+        slots = 148 * 4 * sm_hz * k_us * 1e-6
+        issue = dict(warp_instructions=int(n_inst), issue_slots=slots, frac=n_inst / slots,
+                     note="instruction-issue roofline: the kernel is issue / latency bound, not HBM bound")
     roofline = dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic, issue=issue,
+                    ncu_capture=cap_src,
                     kernel=("phd_update_kernel<float>" if D == 2 else "phd_update_vp_kernel<float>"), kernel_us=k_us, algorithmic_bytes=b_alg, peak_source=peak_src,
                     kernel_share_of_step=k_us * 1e-3 / (1e3 * t_local / K))
 
     line = None
     if rank == 0:
         cpu = None
-        if world == 1 and not a.no_cpu_baseline:
+        if world == 1 and headline and not a.no_cpu_baseline:
             threads = len(os.sched_getaffinity(0))
             n_s = min(N, 8000)
             kind, sub, ts = cpu_reference_run(wl, n_s, threads, 2)
             t = min(ts)
             cpu = dict(value=int(sub.count.sum()) * nZ / t, unit=UNIT, cores=threads, kind=kind,
                        sample=f"{sub.N} particles of the same workload, best of {len(ts)} runs of the reference's OpenMP "
-                              f"RBPHDFilter::update() ({t:.3f} s per step, {threads} threads)")
-        line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=a.warmup,
-                    ms_per_step=1e3 * t_max / K, higher_is_better=True, scaling="weak", vs_baseline=None,
+                              f"RBPHDFilter::update() ({t:.3f} s per step, {threads} threads; built -O3 -march=x86-64-v3 -fopenmp: the "
+                              f"library travels to the GPU box, so not -march=native)")
+        line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=warmup,
+                    ms_per_step=1e3 * t_max / K, higher_is_better=True, scaling=a.scaling, vs_baseline=None,
                     dtype="f32", data="synthetic",
                     config=dict(workload=desc, particles_total=N * world, particles_per_gpu=N, gm_per_particle=nM_in,
                                 gm_out_per_particle=nM_out_mean, meas=nZ,
                                 l2="flushed between steps (512 MiB memset, untimed"
-                                   + (", followed by an untimed 4-byte all-reduce that re-aligns the ranks)" if world > 1 else ")"),
+                                   + (", followed by an untimed barrier that re-aligns the ranks)" if world > 1 else ")"),
                                 timing="CUDA events per step on the launch stream, summed; max over ranks",
                                 parallelism=f"particles block-partitioned over {world} GPU(s); one all-reduce of [sum w, sum w^2] per step "
                                             + ("inside the update kernel over NVLink peer memory" if fused else "by NCCL")),
                     e2e=e2e, gpu_launches=(1 if fused else 2) * K, roofline=roofline, cpu_baseline=cpu, clocks=clk,
+                    stages=stages, n_murty_per_step=n_murty, n_overflow_per_step=n_overflow,
                     wall_s_timed_region_incl_flush=t_wall)
+        if world > 1:
+            line["collective_check"] = collective_check
+            line["comm_error"] = comm_err
+    up.close()
+    return line
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="C3", choices=sorted(WORKLOADS))
+    ap.add_argument("--particles", type=int, default=0, help="override particles per GPU")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: every GPU owns the workload's particle count; strong: the total is fixed and split over the GPUs")
+    ap.add_argument("--particles-total", type=int, default=0, help="--scaling strong: total particles (default: the workload's count)")
+    ap.add_argument("--ref-particles", type=int, default=8000, help="--impl reference: particles per step (capped at the workload's)")
+    ap.add_argument("--extras", default="auto",
+                    help="other workloads appended to the headline line as `extra` sub-lines: 'auto' = C2,C3mf,C5,N1k,N64k on the "
+                         "default single-GPU C3 run, 'none', or a comma-separated list")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-stages", action="store_true")
+    ap.add_argument("--no-fused", action="store_true", help="NCCL all-reduce + normalise kernel instead of the in-kernel sum over peer memory")
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 0)
+    # stdout carries exactly ONE JSON line: everything libraries print (NCCL's version banner, ...)
+    # goes to stderr, the line itself is written to the saved descriptor at the end
+    sys.stdout.flush()
+    global _REAL_STDOUT
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+    if a.impl == "reference":
+        return run_reference_arm(a)
+    if a.warmup < 3:
+        a.warmup = 3   # timing rule: at least 3 warm-up steps
+
+    import torch
+    import torch.distributed as dist
+    import rfs_slam_b200  # noqa: F401
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the PHD update path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # one non-default stream carries the library's kernels, torch's events / memsets and NCCL
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
+    ctx = dict(rank=rank, world=world, local=local, dev=dev,
+               flush=torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev),
+               align=torch.zeros(1, dtype=torch.float32, device=dev))
+
+    line = run_workload(a, a.config, ctx, a.steps, a.warmup, headline=True)
+
+    # ---- the other workloads of the north_star sweep, as sub-lines of the same record -----------------------------
+    extras = []
+    if a.extras == "auto":
+        if world == 1 and a.config == "C3" and a.scaling == "weak" and not a.particles:
+            extras = ["C2", "C3mf", "C5", "N1k", "N64k"]
+    elif a.extras != "none":
+        extras = [x for x in a.extras.split(",") if x in WORKLOADS]
+    if extras:
+        sub = {}
+        for name in extras:
+            try:
+                l = run_workload(a, name, ctx, max(5, min(a.steps, 20)), max(3, min(a.warmup, 5)), headline=False)
+            except Exception as e:   # noqa: BLE001  (a failing extra must not take the headline with it)
+                l = dict(error=f"{type(e).__name__}: {e}") if rank == 0 else None
+            if rank == 0 and l is not None:
+                keep = ("value", "unit", "ms_per_step", "steps", "warmup", "e2e", "roofline", "stages", "config", "n_murty_per_step",
+                        "n_overflow_per_step", "error")
+                sub[name] = {k: l[k] for k in keep if k in l}
+        if rank == 0 and line is not None:
+            line["extra"] = sub
+    if rank == 0 and line is not None:
         emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    up.close()
     return 0
 
 

@@ -304,7 +304,11 @@ int rfsb200_import_particles(rfsb200_ctx* ctx, const int32_t* slot /*[n] host*/,
  * RFSB200_UPDATE_FUSED_ALLREDUCE replaces the caller's all-reduce + rfsb200_normalize(). */
 int rfsb200_comm_export(rfsb200_ctx* ctx, void* handle64);
 int rfsb200_comm_connect(rfsb200_ctx* ctx, int32_t rank, int32_t world, const void* handles /*[world][64]*/);
-/* 1 if a peer did not arrive within 2 s in some fused update since the last call (sums are NaN then) */
+/* Queues a barrier of the connected ranks on the ctx stream (one tiny kernel, flags through the peer mailboxes): every
+ * rank leaves it within an NVLink round trip of the last one to arrive.  No-op for a single rank. */
+int rfsb200_comm_barrier(rfsb200_ctx* ctx);
+/* 1 if a peer did not arrive in time (2 s, or RFSB200_COMM_TIMEOUT_MS when the ctx was created) in some fused update or
+ * barrier since the last call (the sums of that update are NaN) */
 int rfsb200_comm_error(rfsb200_ctx* ctx, int32_t* flag);
 
 /* Device address of the double[2] {sum w, sum w^2} of the last update, for the caller's

@@ -149,6 +149,7 @@ _SIGS = {
     "rfsb200_comm_export": (C.c_int, [_P, _P]),
     "rfsb200_comm_connect": (C.c_int, [_P, C.c_int32, C.c_int32, _P]),
     "rfsb200_comm_error": (C.c_int, [_P, C.POINTER(C.c_int32)]),
+    "rfsb200_comm_barrier": (C.c_int, [_P]),
     "rfsb200_weight_sums_device": (C.c_int, [_P, C.POINTER(_P)]),
     "rfsb200_normalize": (C.c_int, [_P]),
     "rfsb200_get_weights": (C.c_int, [_P, C.c_int, _P]),

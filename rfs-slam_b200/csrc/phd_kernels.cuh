@@ -37,7 +37,9 @@ constexpr int FLAG_BIRTH_OVERFLOW = 8;   // set by predict / append when births 
 constexpr int FLAG_MURTY = 2;       // a partition with nR + nC > 8 (reference would use Murty-200)
 constexpr int FLAG_DP_OVERFLOW = 4; // partition too large for the on-chip DP
 
-struct CommSlot { double s1, s2; unsigned long long epoch; unsigned long long pad; };   // 32 B; mailbox = [2][8]
+struct CommSlot { double s1, s2; unsigned long long epoch; unsigned long long pad; };   // 32 B; mailbox = [4][8]: banks 0 / 1 the
+                                                                                         // weight sums of even / odd update epochs, 2 / 3 rfsb200_comm_barrier
+constexpr int COMM_BANKS = 4;
 
 template <typename T>
 struct KParams {
@@ -81,6 +83,7 @@ struct KParams {
   unsigned long long comm_epoch;
   void* comm_peer[8];               // mailbox of every rank (own included), mapped into this process
   int* comm_error;                  // set to 1 if a peer did not arrive in time
+  unsigned long long comm_timeout_ns;   // how long the last CTA waits for the peers (RFSB200_COMM_TIMEOUT_MS, default 2 s)
   unsigned long long* stats_out;  // [13] totals/istats/mstats of the finished step, published by the last CTA
   // multi-feature weighting: global workspace of the assignment-sum DP for partitions beyond the on-chip tables,
   // 2 x (1 << dp_gmaxb) doubles per warp of the grid (NULL: none); dp_onchip = largest smaller side summed on chip
@@ -1229,7 +1232,7 @@ __device__ __forceinline__ void step_epilogue(const KParams<T>& p, int lane, int
         bool ok = true;
         while (true) {
           if (ld_acquire_sys_u64(&mine[r].epoch) == e) break;
-          if (globaltimer_ns() - t0 > 2000000000ull) { ok = false; break; }   // 2 s: a peer never launched
+          if (globaltimer_ns() - t0 > p.comm_timeout_ns) { ok = false; break; }   // a peer never launched
         }
         if (ok) {
           xs[0][r] = *reinterpret_cast<const volatile double*>(&mine[r].s1);
@@ -1299,6 +1302,24 @@ __device__ __forceinline__ void step_epilogue(const KParams<T>& p, int lane, int
       p.istats[0] = 0; p.istats[1] = 0; p.istats[2] = 0; p.istats[3] = 0;
       *p.ticket = 0;
       *p.work_counter = 0;
+    }
+  }
+}
+
+// rfsb200_comm_barrier: the ranks of a connected group meet on the stream (one warp, thread r talks to rank r): a
+// flag in banks 2 / 3 of every rank's mailbox, written over NVLink peer memory; a rank leaves when it has seen all of them.
+struct CommPeers { void* p[8]; };
+__global__ void comm_barrier_kernel(const CommPeers peers, int rank, int world, unsigned long long epoch, int* comm_error,
+                                    unsigned long long timeout_ns) {
+  const int r = threadIdx.x;
+  if (r < world) {
+    const int bank = 2 + (int)(epoch & 1ull);
+    CommSlot* dst = reinterpret_cast<CommSlot*>(peers.p[r]) + bank * 8 + rank;
+    st_release_sys_u64(&dst->epoch, epoch);
+    const CommSlot* mine = reinterpret_cast<const CommSlot*>(peers.p[rank]) + bank * 8;
+    const unsigned long long t0 = globaltimer_ns();
+    while (ld_acquire_sys_u64(&mine[r].epoch) != epoch) {
+      if (globaltimer_ns() - t0 > timeout_ns) { *comm_error = 1; break; }
     }
   }
 }

@@ -67,6 +67,8 @@ struct rfsb200_ctx {
   void* comm_peer[8] = {};        // every rank's mailbox as seen from this process
   int comm_rank = 0, comm_world = 1;
   unsigned long long comm_epoch = 0;
+  unsigned long long comm_bar_epoch = 0;      // rfsb200_comm_barrier
+  unsigned long long comm_timeout_ns = 2000000000ull;   // RFSB200_COMM_TIMEOUT_MS
   int* comm_error = nullptr;
   int last_nZ = 0;                            // size of the measurement batch still held in Zdev
   int* flags = nullptr;
@@ -473,6 +475,7 @@ int launch_update(rfsb200_ctx* c, int nZ, int out_idx, unsigned flags) {
   p.sums = c->sums; p.totals = c->totals; p.istats = c->istats; p.ticket = c->ticket; p.mstats = c->mstats;
   p.work_counter = c->work_counter; p.stats_out = c->stats_out;
   p.comm_rank = c->comm_rank; p.comm_world = 1; p.fused_normalize = 0; p.comm_epoch = 0; p.comm_error = c->comm_error;
+  p.comm_timeout_ns = c->comm_timeout_ns;
   p.unused_host = c->unused_host; p.nfov_host = c->nfov_host; p.stats_host = c->stats_host;
   // the weights go to the host from whichever launch leaves them final: this kernel (fused normalisation, or none at
   // all), else normalize_kernel
@@ -481,7 +484,7 @@ int launch_update(rfsb200_ctx* c, int nZ, int out_idx, unsigned flags) {
   if (flags & RFSB200_UPDATE_FUSED_ALLREDUCE) {
     p.comm_world = c->comm_world;
     p.fused_normalize = 1;
-    p.comm_epoch = ++c->comm_epoch;
+    p.comm_epoch = c->comm_epoch + 1;   // the ctx moves on only when the launch has succeeded (below)
     for (int r = 0; r < 8; r++) p.comm_peer[r] = c->comm_peer[r];
   }
   const int mf = f.use_cluster_process ? 0 : 1;
@@ -540,6 +543,7 @@ int launch_update(rfsb200_ctx* c, int nZ, int out_idx, unsigned flags) {
   } else if (mf) phd_update_kernel<T, true, 0><<<c->grid, c->nwarps * 32, c->smem_bytes, c->stream>>>(p);
   else phd_update_kernel<T, false, 0><<<c->grid, c->nwarps * 32, c->smem_bytes, c->stream>>>(p);
   CU(c, cudaGetLastError());
+  if (flags & RFSB200_UPDATE_FUSED_ALLREDUCE) c->comm_epoch++;
   if (prof) {
     CU(c, cudaEventRecord(c->prof_ev[2 * c->prof_n + 1], c->stream));
     c->prof_n++;
@@ -718,8 +722,9 @@ int rfsb200_create(rfsb200_ctx** out, const rfsb200_dims* d) {
     CU(c, cudaMalloc((void**)&c->unused, (size_t)c->N * 8));
     CU(c, cudaMalloc((void**)&c->nfov, (size_t)c->N * 4));
     CU(c, cudaMalloc((void**)&c->flags, (size_t)c->N * 4));
-    CU(c, cudaMalloc(&c->comm_mail, 2 * 8 * sizeof(CommSlot)));
-    CU(c, cudaMemset(c->comm_mail, 0xff, 2 * 8 * sizeof(CommSlot)));   // epoch = ~0: never matches
+    CU(c, cudaMalloc(&c->comm_mail, COMM_BANKS * 8 * sizeof(CommSlot)));
+    CU(c, cudaMemset(c->comm_mail, 0xff, COMM_BANKS * 8 * sizeof(CommSlot)));   // epoch = ~0: never matches
+    if (const char* e = getenv("RFSB200_COMM_TIMEOUT_MS")) c->comm_timeout_ns = (unsigned long long)std::max(1, atoi(e)) * 1000000ull;
     CU(c, cudaMalloc((void**)&c->comm_error, 4));
     CU(c, cudaMemset(c->comm_error, 0, 4));
     CU(c, cudaMalloc((void**)&c->unused_alt, (size_t)c->N * 8));
@@ -1293,6 +1298,12 @@ int rfsb200_comm_export(rfsb200_ctx* c, void* handle64) {
   if (!c || !handle64) return fail(c, RFSB200_EINVAL, "NULL argument");
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle is 64 bytes");
   CU(c, cudaSetDevice(c->device));
+  // a (re)connection starts from epoch 0 with an empty mailbox; cleared HERE, before any peer can hold the handle
+  CU(c, cudaStreamSynchronize(c->stream));
+  CU(c, cudaMemset(c->comm_mail, 0xff, COMM_BANKS * 8 * sizeof(CommSlot)));
+  CU(c, cudaMemset(c->comm_error, 0, 4));
+  c->comm_epoch = 0;
+  c->comm_bar_epoch = 0;
   cudaIpcMemHandle_t h;
   CU(c, cudaIpcGetMemHandle(&h, c->comm_mail));
   memcpy(handle64, &h, 64);
@@ -1314,7 +1325,19 @@ int rfsb200_comm_connect(rfsb200_ctx* c, int32_t rank, int32_t world, const void
   }
   c->comm_rank = rank;
   c->comm_world = world;
-  c->comm_epoch = 0;
+  return RFSB200_OK;
+}
+
+int rfsb200_comm_barrier(rfsb200_ctx* c) {
+  if (!c) return fail(nullptr, RFSB200_EINVAL, "NULL ctx");
+  if (c->comm_world <= 1) return RFSB200_OK;
+  if (!c->comm_peer[0]) return fail(c, RFSB200_ESTATE, "rfsb200_comm_barrier before rfsb200_comm_connect");
+  CU(c, cudaSetDevice(c->device));
+  CommPeers peers{};
+  for (int r = 0; r < 8; r++) peers.p[r] = c->comm_peer[r];
+  comm_barrier_kernel<<<1, 32, 0, c->stream>>>(peers, c->comm_rank, c->comm_world, c->comm_bar_epoch + 1, c->comm_error, c->comm_timeout_ns);
+  CU(c, cudaGetLastError());
+  c->comm_bar_epoch++;
   return RFSB200_OK;
 }
 

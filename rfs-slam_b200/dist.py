@@ -138,7 +138,10 @@ class ShardedUpdater:
     def step(self, Z, flags: int = 0, want_stats: bool = False):
         from . import capi
         if self.fused:   # one launch: update + cross-GPU sum over NVLink + normalisation
-            return self.up.update(Z, flags=flags | capi.UPDATE_FUSED_ALLREDUCE, want_stats=want_stats)
+            so = self.up.update(Z, flags=flags | capi.UPDATE_FUSED_ALLREDUCE, want_stats=want_stats)
+            if so is not None and not np.isfinite(so.sum_w):
+                self.check_comm()
+            return so
         so = self.up.update(Z, flags=flags | capi.UPDATE_NO_NORMALIZE, want_stats=want_stats)
         allreduce_sums(self.sums, self.group)
         self.up.normalize()
@@ -150,8 +153,11 @@ class ShardedUpdater:
         synchronisation; NCCL path: the same data through the separate calls around the collective."""
         from . import capi
         if self.fused:
-            return self.up.update_host(pose, pose_cov, weight, Z, flags=flags | capi.UPDATE_FUSED_ALLREDUCE,
-                                       w_out=w_out, unused_out=unused_out, nfov_out=nfov_out)
+            so = self.up.update_host(pose, pose_cov, weight, Z, flags=flags | capi.UPDATE_FUSED_ALLREDUCE,
+                                     w_out=w_out, unused_out=unused_out, nfov_out=nfov_out)
+            if w_out is not None and len(w_out) and w_out[0] != w_out[0]:   # NaN weights: a peer missed the exchange
+                self.check_comm()
+            return so
         self.up.set_poses(pose, pose_cov, weight)
         self.step(Z, flags=flags)
         which = 1 if (flags & capi.UPDATE_NO_COMMIT) else 0
@@ -161,6 +167,15 @@ class ShardedUpdater:
             self.up.get_unused(unused_out, nfov_out)
         return None
 
+
+    def check_comm(self):
+        """Raises if a peer did not arrive in some fused update since the last check (the sums of that step are NaN).
+        step() / step_host() call it whenever they see non-finite results; an asynchronous caller (step() without
+        statistics) should call it before it consumes the weights."""
+        if self.fused and self.up.comm_error():
+            raise RuntimeError("rfs_slam_b200.dist: a peer GPU did not reach the in-kernel weight-sum exchange in time "
+                               "(RFSB200_COMM_TIMEOUT_MS); the particle weights of that step are NaN — rerun the step with "
+                               "fused=False (NCCL all-reduce) or raise the timeout")
 
     # ---- resampling over ALL shards -----------------------------------------------------------------------------
     def resample_global(self, r01: float, neff_threshold: float | None = None):

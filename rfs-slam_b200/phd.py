@@ -246,6 +246,10 @@ class PHDUpdater:
         buf = (C.c_ubyte * (64 * world)).from_buffer_copy(b"".join(handles))
         _check(self.lib, self.ctx, self.lib.rfsb200_comm_connect(self.ctx, rank, world, C.cast(buf, C.c_void_p)), "comm_connect")
 
+    def comm_barrier(self):
+        """Barrier of the connected ranks on the ctx stream (rfsb200_comm_barrier)."""
+        _check(self.lib, self.ctx, self.lib.rfsb200_comm_barrier(self.ctx), "comm_barrier")
+
     def comm_error(self) -> bool:
         f = C.c_int32()
         _check(self.lib, self.ctx, self.lib.rfsb200_comm_error(self.ctx, C.byref(f)), "comm_error")
