@@ -219,7 +219,7 @@ def run_workload(a, name, ctx, steps, warmup, headline):
     if a.scaling == "strong":   # the total is fixed, every GPU owns 1 / world of it
         total = a.particles_total or WORKLOADS[name][1]
         n_override = max(1, total // world)
-    wl, desc = make_workload(name, rank, n_override)
+    wl, desc = make_workload(name, rank if world > 1 else int(os.environ.get("RFSB200_BENCH_SHARD", "0")), n_override)
     N, nZ = wl.N, wl.nZ
     units_local = int(wl.count.sum()) * nZ
     D = wl.dim                                  # 2: RngBrg, 3: VictoriaPark
@@ -306,6 +306,12 @@ def run_workload(a, name, ctx, steps, warmup, headline):
     t_max = float(tt.item())
     units_total = float(uu.item())
     value = units_total * K / t_max
+    per_rank = None
+    if world > 1:   # what every rank saw: its own step time and its kernel time (the wait for the slowest peer included)
+        mine = torch.tensor([1e3 * t_local / K, float(np.mean(kern_us)) if len(kern_us) else 0.0], dtype=torch.float64, device=dev)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = dict(ms_per_step=[float(x[0]) for x in allr], kernel_us=[float(x[1]) for x in allr])
     comm_err = int(up.comm_error()) if world > 1 and fused else 0
 
     # ---- e2e: the same step through the C ABI with HOST buffers, timed on the HOST clock ------------------------
@@ -425,6 +431,7 @@ def run_workload(a, name, ctx, steps, warmup, headline):
         if world > 1:
             line["collective_check"] = collective_check
             line["comm_error"] = comm_err
+            line["per_rank"] = per_rank
     up.close()
     return line
 

@@ -40,6 +40,28 @@ constexpr int FLAG_DP_OVERFLOW = 4; // partition too large for the on-chip DP
 struct CommSlot { double s1, s2; unsigned long long epoch; unsigned long long pad; };   // 32 B; mailbox = [4][8]: banks 0 / 1 the
                                                                                          // weight sums of even / odd update epochs, 2 / 3 rfsb200_comm_barrier
 constexpr int COMM_BANKS = 4;
+// A slot travels as four 8-byte words, each = 32 bits of payload | (epoch tag << 32): every word is written atomically
+// and carries its own arrival flag, so the sender needs no fence between data and flag and the receiver simply polls
+// until all four tags match (the "LL" protocol of collective libraries: one NVLink traversal of latency).
+__device__ __forceinline__ void comm_send(CommSlot* dst, double s1, double s2, unsigned long long epoch) {
+  const unsigned long long a = (unsigned long long)__double_as_longlong(s1), b = (unsigned long long)__double_as_longlong(s2);
+  const unsigned long long tag = (epoch & 0xffffffffull) << 32;
+  unsigned long long* q = reinterpret_cast<unsigned long long*>(dst);
+  st_relaxed_sys_u64(q + 0, (a & 0xffffffffull) | tag);
+  st_relaxed_sys_u64(q + 1, (a >> 32) | tag);
+  st_relaxed_sys_u64(q + 2, (b & 0xffffffffull) | tag);
+  st_relaxed_sys_u64(q + 3, (b >> 32) | tag);
+}
+__device__ __forceinline__ bool comm_recv(const CommSlot* src, unsigned long long epoch, double& s1, double& s2) {
+  const unsigned long long* q = reinterpret_cast<const unsigned long long*>(src);
+  const unsigned long long w0 = ld_relaxed_sys_u64(q + 0), w1 = ld_relaxed_sys_u64(q + 1), w2 = ld_relaxed_sys_u64(q + 2),
+                           w3 = ld_relaxed_sys_u64(q + 3);
+  const unsigned long long tag = epoch & 0xffffffffull;
+  if ((w0 >> 32) != tag || (w1 >> 32) != tag || (w2 >> 32) != tag || (w3 >> 32) != tag) return false;
+  s1 = __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
+  s2 = __longlong_as_double((long long)((w2 & 0xffffffffull) | (w3 << 32)));
+  return true;
+}
 
 template <typename T>
 struct KParams {
@@ -1223,20 +1245,17 @@ __device__ __forceinline__ void step_epilogue(const KParams<T>& p, int lane, int
       if ((int)threadIdx.x < p.comm_world) {
         const int r = threadIdx.x;
         CommSlot* dst = reinterpret_cast<CommSlot*>(p.comm_peer[r]) + par * 8 + p.comm_rank;
-        *reinterpret_cast<volatile double*>(&dst->s1) = red[0][0];
-        *reinterpret_cast<volatile double*>(&dst->s2) = red[1][0];
-        __threadfence_system();
-        st_release_sys_u64(&dst->epoch, e);
+        comm_send(dst, red[0][0], red[1][0], e);
         const CommSlot* mine = reinterpret_cast<const CommSlot*>(p.comm_peer[p.comm_rank]) + par * 8;
         const unsigned long long t0 = globaltimer_ns();
+        double a1 = 0, a2 = 0;
         bool ok = true;
-        while (true) {
-          if (ld_acquire_sys_u64(&mine[r].epoch) == e) break;
+        while (!comm_recv(mine + r, e, a1, a2)) {
           if (globaltimer_ns() - t0 > p.comm_timeout_ns) { ok = false; break; }   // a peer never launched
         }
         if (ok) {
-          xs[0][r] = *reinterpret_cast<const volatile double*>(&mine[r].s1);
-          xs[1][r] = *reinterpret_cast<const volatile double*>(&mine[r].s2);
+          xs[0][r] = a1;
+          xs[1][r] = a2;
         } else {
           atomicAnd(&xok, 0);
         }
@@ -1315,10 +1334,11 @@ __global__ void comm_barrier_kernel(const CommPeers peers, int rank, int world, 
   if (r < world) {
     const int bank = 2 + (int)(epoch & 1ull);
     CommSlot* dst = reinterpret_cast<CommSlot*>(peers.p[r]) + bank * 8 + rank;
-    st_release_sys_u64(&dst->epoch, epoch);
+    comm_send(dst, 0.0, 0.0, epoch);
     const CommSlot* mine = reinterpret_cast<const CommSlot*>(peers.p[rank]) + bank * 8;
     const unsigned long long t0 = globaltimer_ns();
-    while (ld_acquire_sys_u64(&mine[r].epoch) != epoch) {
+    double a1, a2;
+    while (!comm_recv(mine + r, epoch, a1, a2)) {
       if (globaltimer_ns() - t0 > timeout_ns) { *comm_error = 1; break; }
     }
   }

@@ -69,6 +69,12 @@ inline void tma_store_wait_read() {}
 inline void tma_store_wait_all() {}
 inline void fence_proxy_async() {}
 inline void st_release_sys_u64(unsigned long long* p, unsigned long long v) { *reinterpret_cast<volatile unsigned long long*>(p) = v; }
+inline void st_relaxed_sys_u64(unsigned long long* p, unsigned long long v) { *reinterpret_cast<volatile unsigned long long*>(p) = v; }
+inline unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) {
+  const unsigned long long v = *reinterpret_cast<const volatile unsigned long long*>(p);
+  simt::spin_yield();
+  return v;
+}
 inline unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
   const unsigned long long v = *reinterpret_cast<const volatile unsigned long long*>(p);
   simt::spin_yield();
