@@ -86,7 +86,24 @@ struct KParams {
   const double* w_in;
   const T* pose;      // [N][4]
   const T* pose_cov;  // [8] or [N][8]
-  const T* Z;         // [nZ][2]
+  const T* Z;         // [nZ][2] device copy of the batch (written by CTA 0 of the update kernel, read by predict_maps)
+  // the measurement batch travels BY VALUE, fp64 as the caller holds it: no copy precedes the launch
+  double Zval[MAX_Z * 3];
+  T* Zdev_w;          // where CTA 0 leaves the T copy
+  // host-facing step (rfsb200_update_host, pinned caller buffers): poses / particle weights / pose covariances are read
+  // straight from the caller's memory over PCIe by the update kernel (host_in_convert), which leaves the device copies
+  // every stage reads (NULL pose_h: the device arrays are current)
+  const double* pose_h;     // [N][3]
+  const double* weight_h;   // [N] or NULL = keep
+  const double* pcov_h;     // [N][6] (pose_cov_mode 2) or NULL
+  double cov6[6];           // pose_cov_mode 1 with pose_h: the shared covariance by value
+  T* pose_w;                // [N][4]
+  double* pose64_w;         // [N][3]
+  T* pcov_w;                // [N][8] / [8]
+  double* w_front;          // [N] particle weights of the state the step starts from
+  unsigned long long* hin_ready;   // [grid] slice flags of the host-facing step (see host_in_convert)
+  unsigned long long* done_host;   // pinned flag the last CTA sets to done_value when every result is in host memory
+  unsigned long long done_value;   // number of this host-facing launch (> 0)
   T* gm_out;
   int* cnt_out;
   double* w_out;
@@ -1322,6 +1339,16 @@ __device__ __forceinline__ void step_epilogue(const KParams<T>& p, int lane, int
       *p.ticket = 0;
       *p.work_counter = 0;
     }
+    if (p.done_host) {
+      // host-facing step: every result of the launch is in the caller's memory (the other CTAs' stores are ordered
+      // before their tickets, this CTA's before the barrier): tell the host, which polls this word instead of
+      // waiting for the stream
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned long long*>(p.done_host) = p.done_value;
+      }
+    }
   }
 }
 
@@ -1386,6 +1413,62 @@ __host__ __device__ inline int z_bytes() {
   return (int)((2 * MAX_Z * sizeof(T) + 2 * (NBINS + 1) * 8 + 4 * sizeof(T) + 2 * MAX_Z + 127) & ~127);
 }
 
+// Host-facing step (rfsb200_update_host with pinned caller buffers): poses, particle weights and pose covariances are read
+// from the CALLER's memory by the update kernel itself.  The particles are cut into one slice per CTA; every CTA converts
+// its slice when it starts — the reads over PCIe are issued before the measurement tables are built and consumed after,
+// so their latency is hidden — and publishes it through hin_ready[slice] = number of the launch.  The particle queue is
+// global, so a warp may draw a particle of another CTA's slice: if that flag is not up yet the warp gives the owner 20 us
+// (CTAs do not start at the same instant) and then converts the slice itself (a grid that is not fully resident; the CPU
+// interpreter of tests/simt, which runs the CTAs one after the other).  Conversions are idempotent — every converter
+// writes the same bits — so no claim protocol is needed and nobody can wait forever.
+template <typename T>
+__device__ __forceinline__ void host_in_store(const KParams<T>& p, int i, double x, double y, double th) {
+  p.pose64_w[3 * (size_t)i] = x; p.pose64_w[3 * (size_t)i + 1] = y; p.pose64_w[3 * (size_t)i + 2] = th;
+  T* q = p.pose_w + 4 * (size_t)i;
+  q[0] = (T)x; q[1] = (T)y; q[2] = (T)th; q[3] = T(0);
+}
+// particles [lo + first, hi) of slice s (tid strides by nthreads); skip_pose_below: particles below this index already
+// have pose and weight (the CTA's early reads) and only need their covariance
+template <typename T>
+__device__ __forceinline__ void host_in_convert(const KParams<T>& p, int s, int slice, int tid, int nthreads, int skip_pose_below) {
+  const int lo = s * slice, hi = (lo + slice < p.N) ? lo + slice : p.N;
+  for (int i = lo + tid; i < hi; i += nthreads) {
+    if (i >= skip_pose_below) {
+      host_in_store(p, i, p.pose_h[3 * (size_t)i], p.pose_h[3 * (size_t)i + 1], p.pose_h[3 * (size_t)i + 2]);
+      if (p.weight_h) p.w_front[i] = p.weight_h[i];
+    }
+    if (p.pcov_h) {
+      T* c = p.pcov_w + 8 * (size_t)i;
+#pragma unroll
+      for (int k = 0; k < 6; k++) c[k] = (T)p.pcov_h[6 * (size_t)i + k];
+      c[6] = T(0); c[7] = T(0);
+    }
+  }
+  if (s == 0 && tid == 0 && p.pose_cov_mode == 1) {
+#pragma unroll
+    for (int k = 0; k < 6; k++) p.pcov_w[k] = (T)p.cov6[k];
+    p.pcov_w[6] = T(0); p.pcov_w[7] = T(0);
+  }
+}
+// whole warp, slice s not published when the warp looked: convert it (again) and publish
+template <typename T>
+__device__ __forceinline__ void host_in_self_service(const KParams<T>& p, int s, int slice, int lane) {
+  {  // the owner is usually a few microseconds from publishing (CTAs do not start at the same instant): give it that long
+    int up = 0;
+    if (lane == 0) {
+      const unsigned long long t0 = globaltimer_ns();
+      while (!(up = (ld_acquire_gpu_u64(p.hin_ready + s) == p.done_value)) && globaltimer_ns() - t0 < 20000ull) {
+      }
+    }
+    if (__shfl_sync(FULL, up, 0)) return;
+  }
+  host_in_convert(p, s, slice, lane, 32, 0);
+  __threadfence();
+  __syncwarp();
+  if (lane == 0) st_release_gpu_u64(p.hin_ready + s, p.done_value);
+  __syncwarp();
+}
+
 // threads per CTA the kernel is compiled for: the fp32 single-cluster kernel fits 96 registers (20 warps per SM),
 // the multi-feature and the fp64 kernels need 128 (16 warps)
 template <typename T, bool MF, bool PROF = false>
@@ -1421,10 +1504,30 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
   uint64_t* bar = reinterpret_cast<uint64_t*>(evalIdx + (MF ? MAX_EVAL : 0));
   unsigned char* mfs = after;   // multi-feature stages reuse the work region (see mf_region_bytes)
 
+  // ---- host-facing step: this CTA's slice of the caller's pinned inputs (see host_in_convert): the reads are issued
+  //      here, the values are stored and published behind the table set-up below --------------------------------------
+  const int hin_slice = (p.N + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int hin_lo = (int)blockIdx.x * hin_slice;
+  int hin_early = 0;   // particles of the slice whose pose and weight are read here: flat, fully coalesced 8-byte loads
+  double hin_v0 = 0, hin_v1 = 0, hin_w = 0;
+  if (p.pose_h) {
+    const int nt = (int)blockDim.x, tid = (int)threadIdx.x;
+    int cnt = p.N - hin_lo;
+    cnt = cnt < 0 ? 0 : (cnt > hin_slice ? hin_slice : cnt);
+    hin_early = cnt < (2 * nt) / 3 ? cnt : (2 * nt) / 3;
+    const double* src = p.pose_h + 3 * (size_t)hin_lo;
+    if (tid < 3 * hin_early) hin_v0 = src[tid];
+    if (tid + nt < 3 * hin_early) hin_v1 = src[tid + nt];
+    if (p.weight_h && tid < hin_early) hin_w = p.weight_h[hin_lo + tid];
+  }
   // ---- the measurement batch and the corrector's window tables (once per CTA) ------------------
   // tabR[b] = set of measurements whose range bin is < b, tabB likewise on the bearing: the
   // measurements with range in [lo,hi] are a subset of tabR[bin(hi)+1] & ~tabR[bin(lo)].
-  for (int k = threadIdx.x; k < 2 * nZ; k += blockDim.x) zs[k] = p.Z[k];
+  for (int k = threadIdx.x; k < 2 * nZ; k += blockDim.x) {
+    const T v = (T)p.Zval[k];
+    zs[k] = v;
+    if (blockIdx.x == 0) p.Zdev_w[k] = v;
+  }
   __syncthreads();
   if (threadIdx.x < 2) {
     T lo = M<T>::inf(), hi = -M<T>::inf();
@@ -1474,7 +1577,21 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
     mbar_init(bar, 1);
     fence_mbar_init();
   }
+  if (p.pose_h) {
+    const int nt = (int)blockDim.x, tid = (int)threadIdx.x;
+    double* stage = reinterpret_cast<double*>(smem_raw + z_bytes<T>());   // the warps' blocks are not in use yet
+    if (tid < 3 * hin_early) stage[tid] = hin_v0;
+    if (tid + nt < 3 * hin_early) stage[tid + nt] = hin_v1;
+    __syncthreads();
+    if (tid < hin_early) {
+      host_in_store(p, hin_lo + tid, stage[3 * tid], stage[3 * tid + 1], stage[3 * tid + 2]);
+      if (p.weight_h) p.w_front[hin_lo + tid] = hin_w;
+    }
+    host_in_convert(p, (int)blockIdx.x, hin_slice, tid, nt, hin_lo + hin_early);   // the rest of the slice, covariances
+    __threadfence();
+  }
   __syncthreads();
+  if (p.pose_h && threadIdx.x == 0) st_release_gpu_u64(p.hin_ready + blockIdx.x, p.done_value);
   if constexpr (PROF) {
     if (threadIdx.x == 0) atomicMax(&p.prof[13], globaltimer_ns());
   }
@@ -1491,16 +1608,36 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
   int max_out = 0, n_over = 0, n_murty = 0, n_fallback = 0;
   unsigned mstat[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // merge statistics: fallbacks by reason, pairs, clusters
 
-  // dynamic particle queue: one atomic per particle (lane 0), broadcast to the warp.  The NEXT particle is drawn
-  // while the current one is being merged, and its planes are prefetched into L2 before the current one is stored,
+  // Particle queue.  The particles are cut into one slice of S per CTA (the slices of the host-facing step, above).  A
+  // warp's FIRST particle is static — particle `warp` of its CTA's slice: no atomic, and in a host-facing step no
+  // dependency on another CTA's conversion while the grid is still starting up.  Everything else (the particles
+  // warps .. S-1 of every slice) goes through one global queue, one atomic per particle (lane 0): the NEXT particle is
+  // drawn while the current one is being merged, and its planes are prefetched into L2 before the current one is stored,
   // so neither the atomic nor the HBM latency of the bulk loads sits on the warp's critical path.
-  int pi = 0;
-  if (lane == 0) pi = (int)atomicAdd(p.work_counter, 1u);
-  pi = __shfl_sync(FULL, pi, 0);
+  const int q_first = (int)(blockDim.x >> 5);                          // static particles per slice
+  const int q_per_slice = hin_slice > q_first ? hin_slice - q_first : 0;   // queued particles of a full slice
+  auto queue_particle = [&](int q) -> int {   // queue ticket -> particle index (>= N: the queue is empty)
+    if (q_per_slice == 0) return p.N;
+    const int sl = q / q_per_slice;
+    const int i = sl * hin_slice + q_first + (q - sl * q_per_slice);
+    return (sl < (int)gridDim.x && i < p.N) ? i : p.N;
+  };
+  int pi = (int)blockIdx.x * hin_slice + warp;
+  if (warp >= hin_slice || pi >= p.N) {   // no static particle for this warp (a small shard): straight to the queue
+    int q = 0;
+    if (lane == 0) q = (int)atomicAdd(p.work_counter, 1u);
+    pi = queue_particle(__shfl_sync(FULL, q, 0));
+  }
+  int hin_ok = 0;   // lane 0: the slice of the particle in hand was published when it was looked up
+  if (p.pose_h && lane == 0 && pi < p.N)   // (this CTA's own slice is on the device: the barrier above)
+    hin_ok = (pi / hin_slice == (int)blockIdx.x) || ld_acquire_gpu_u64(p.hin_ready + pi / hin_slice) == p.done_value;
   while (pi < p.N) {
     int pi_next = 0;   // lane 0 only until the end of the iteration
-
+    if (p.pose_h) {   // (host-facing step) the inputs of this particle are on the device?  (flag read one particle ahead)
+      if (!__shfl_sync(FULL, hin_ok, 0)) host_in_self_service(p, pi / hin_slice, hin_slice, lane);
+    }
     const double w_prev_particle = p.w_in[pi];
+
     T* cur = bufA;
     int nM = p.cnt_in[pi];
     nM = nM < 0 ? 0 : (nM > p.cap ? p.cap : nM);
@@ -1520,7 +1657,9 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
     }
     const T px = p.pose[4 * pi], py = p.pose[4 * pi + 1], pth = p.pose[4 * pi + 2];
     T c00 = 0, c01 = 0, c02 = 0, c11 = 0, c12 = 0, c22 = 0;
-    if (p.pose_cov_mode) {
+    if (p.pose_cov_mode == 1 && p.pose_h) {   // host-facing step: the shared covariance came by value (its device copy is slice 0's)
+      c00 = (T)p.cov6[0]; c01 = (T)p.cov6[1]; c02 = (T)p.cov6[2]; c11 = (T)p.cov6[3]; c12 = (T)p.cov6[4]; c22 = (T)p.cov6[5];
+    } else if (p.pose_cov_mode) {
       const T* pc = p.pose_cov + (p.pose_cov_mode == 2 ? (size_t)pi * 8 : 0);
       c00 = pc[0]; c01 = pc[1]; c02 = pc[2]; c11 = pc[3]; c12 = pc[4]; c22 = pc[5];
     }
@@ -2026,7 +2165,7 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
 
     clk.mark(STAGE_MFWEIGHT);
     // ---------------- S6: merge ------------------------------------------------------------------
-    if (lane == 0) pi_next = (int)atomicAdd(p.work_counter, 1u);   // first needed after the merge
+    if (lane == 0) pi_next = queue_particle((int)atomicAdd(p.work_counter, 1u));   // first needed after the merge
     if (n > 1) {
       int st = MERGE_FALLBACK;
       if (p.merge_algo != 0) st = merge_clustered<T, PROF>(cur, ms, W, n, p.merge_t2, p.merge_f, MF, lane, mstat, g_xmin, g_xmax, g_trmax, g_bad, clk);
@@ -2039,7 +2178,10 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
     clk.mark(STAGE_MERGE);
     // ---------------- S7: prune + store ------------------------------------------------------------
     int nM_next = 0;
-    if (lane == 0 && pi_next < p.N) nM_next = p.cnt_in[pi_next];   // first needed after the sort
+    if (lane == 0 && pi_next < p.N) {
+      nM_next = p.cnt_in[pi_next];   // first needed after the sort
+      if (p.pose_h) hin_ok = ld_acquire_gpu_u64(p.hin_ready + pi_next / hin_slice) == p.done_value;
+    }
     int n_out = 0;
     {
       T* kw = ms.keys;   // [W] sort keys (the merge-only scratch is dead)

@@ -240,7 +240,11 @@ phd_update_vp_kernel(const __grid_constant__ VPParams<T> vp) {
 
   for (int k = threadIdx.x; k < VP_SCAN_MAX; k += blockDim.x) scan_s[k] = k < vp.scan_n ? vp.scan[k] : 0.0;
   for (int k = threadIdx.x; k < VP_PD_MAX; k += blockDim.x) pd_s[k] = k < vp.pd_n ? vp.pd_table[k] : 0.0;
-  for (int k = threadIdx.x; k < 3 * nZ; k += blockDim.x) zs[k] = p.Z[k];
+  for (int k = threadIdx.x; k < 3 * nZ; k += blockDim.x) {
+    const T v = (T)p.Zval[k];
+    zs[k] = v;
+    if (blockIdx.x == 0) p.Zdev_w[k] = v;
+  }
   if (lane == 0) {
     mbar_init(bar, 1);
     fence_mbar_init();

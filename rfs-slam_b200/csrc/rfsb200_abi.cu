@@ -101,6 +101,13 @@ struct rfsb200_ctx {
   unsigned long long* unused_host = nullptr;
   int* nfov_host = nullptr;
   unsigned long long* stats_host = nullptr;
+  // host-facing step: device views of the caller's INPUT buffers for the next launch (or NULL), and the completion word
+  const double* hin_pose = nullptr; const double* hin_weight = nullptr; const double* hin_pcov = nullptr;
+  double hin_cov6[6] = {};
+  unsigned long long* hin_ready = nullptr;   // [HIN_SLICES] slice flags of the host-facing step (KParams::hin_ready)
+  unsigned long long* done_host = nullptr;   // device view of the pinned completion word for the next launch (or NULL)
+  unsigned long long done_seq = 0;
+  double Zval[MAX_Z * 3] = {};               // the measurement batch of the next launch, fp64
   std::vector<cudaEvent_t> prof_ev;   // event pairs around the update kernel (rfsb200_profile_*)
   int prof_cap = 0, prof_n = 0;
   unsigned long long* prof_dev = nullptr;   // [16] stage-timing build (KParams::prof)
@@ -470,6 +477,12 @@ int launch_update(rfsb200_ctx* c, int nZ, int out_idx, unsigned flags) {
   p.gm_in = (const T*)in.gm; p.cnt_in = in.cnt; p.w_in = in.weight;
   p.pose = (const T*)c->pose; p.pose_cov = (const T*)c->pose_cov;
   p.Z = (const T*)c->Zdev;
+  p.Zdev_w = (T*)c->Zdev;
+  for (int k = 0; k < c->ld * nZ; k++) p.Zval[k] = c->Zval[k];
+  p.pose_h = c->hin_pose; p.weight_h = c->hin_weight; p.pcov_h = c->hin_pcov;
+  for (int k = 0; k < 6; k++) p.cov6[k] = c->hin_cov6[k];
+  p.pose_w = (T*)c->pose; p.pose64_w = c->stg_small; p.pcov_w = (T*)c->pose_cov; p.w_front = (double*)in.weight;
+  p.done_host = c->done_host; p.done_value = c->done_seq; p.hin_ready = c->hin_ready;
   p.gm_out = (T*)out.gm; p.cnt_out = out.cnt; p.w_out = out.weight;
   p.unused = c->unused; p.nfov = c->nfov; p.flags = c->flags;
   p.sums = c->sums; p.totals = c->totals; p.istats = c->istats; p.ticket = c->ticket; p.mstats = c->mstats;
@@ -599,6 +612,7 @@ int ensure_pinned(rfsb200_ctx* c, size_t bytes) {
   c->hpin = nullptr;
   c->hpin_bytes = 0;
   CU(c, cudaMallocHost((void**)&c->hpin, bytes));
+  memset(c->hpin, 0, bytes);   // (the completion word of rfsb200_update_host lives here)
   c->hpin_bytes = bytes;
   remember_pinned(c->hpin, bytes);
   return RFSB200_OK;
@@ -725,6 +739,8 @@ int rfsb200_create(rfsb200_ctx** out, const rfsb200_dims* d) {
     CU(c, cudaMalloc(&c->comm_mail, COMM_BANKS * 8 * sizeof(CommSlot)));
     CU(c, cudaMemset(c->comm_mail, 0xff, COMM_BANKS * 8 * sizeof(CommSlot)));   // epoch = ~0: never matches
     if (const char* e = getenv("RFSB200_COMM_TIMEOUT_MS")) c->comm_timeout_ns = (unsigned long long)std::max(1, atoi(e)) * 1000000ull;
+    CU(c, cudaMalloc((void**)&c->hin_ready, 4096 * 8));   // one flag per CTA of the update kernel (grid <= SMs x CTAs per SM)
+    CU(c, cudaMemset(c->hin_ready, 0, 4096 * 8));
     CU(c, cudaMalloc((void**)&c->comm_error, 4));
     CU(c, cudaMemset(c->comm_error, 0, 4));
     CU(c, cudaMalloc((void**)&c->unused_alt, (size_t)c->N * 8));
@@ -790,7 +806,7 @@ int rfsb200_destroy(rfsb200_ctx* c) {
   cudaFree(c->comm_mail); cudaFree(c->comm_error);
   cudaFree(c->sums); cudaFree(c->totals); cudaFree(c->istats); cudaFree(c->ticket);
   cudaFree(c->work_counter); cudaFree(c->stats_out); cudaFree(c->mstats);
-  cudaFree(c->stg); cudaFree(c->offs); cudaFree(c->stg_small); cudaFree(c->scan_dev); cudaFree(c->dp_scratch); cudaFree(c->prof_dev);
+  cudaFree(c->stg); cudaFree(c->offs); cudaFree(c->stg_small); cudaFree(c->scan_dev); cudaFree(c->dp_scratch); cudaFree(c->prof_dev); cudaFree(c->hin_ready);
   if (c->hpin) { forget_pinned(c->hpin); cudaFreeHost(c->hpin); }
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
@@ -933,29 +949,14 @@ int rfsb200_set_poses(rfsb200_ctx* c, const double* pose, const double* pose_cov
 }
 
 // queue one update on the ctx stream (Z copy + kernels); no synchronisation
-static int enqueue_update(rfsb200_ctx* c, const double* Z, int32_t nZ, uint32_t flags, bool timed, int* launches_out,
-                          bool z_resident = false) {
+static int enqueue_update(rfsb200_ctx* c, const double* Z, int32_t nZ, uint32_t flags, bool timed, int* launches_out) {
   if (!c->have_model || !c->have_cfg || !c->have_maps || !c->have_poses)
     return fail(c, RFSB200_ESTATE, "update before set_model / set_filter_cfg / upload_maps / set_poses");
   if (nZ < 0 || nZ > c->dims.z_capacity) return fail(c, RFSB200_ECAPACITY, "nZ %d > z_capacity %d", nZ, c->dims.z_capacity);
   if (!Z) return fail(c, RFSB200_EINVAL, "NULL Z");
-  // Z -> T in a pinned staging slot -> device
-  unsigned char* zsrc = nullptr;
-  unsigned zslot_used = 0;
-  if (!z_resident) {   // (a host-facing step has already put the batch into Zdev: host_in_kernel)
-    const unsigned slot = (c->zslot++) & 7u;
-    CU(c, cudaEventSynchronize(c->zev[slot]));   // the copy that last read this slot has finished
-    unsigned char* hb = c->hpin + 16384 + (size_t)slot * 4096;
-    zsrc = hb;
-    zslot_used = slot;
-    if (c->prec == 32) {
-      float* h = (float*)hb;
-      for (int k = 0; k < c->ld * nZ; k++) h[k] = (float)Z[k];
-    } else {
-      double* h = (double*)hb;
-      for (int k = 0; k < c->ld * nZ; k++) h[k] = Z[k];
-    }
-  }
+  // the measurement batch travels by value in the kernel's parameter block (fp64; converted by the kernel, whose first
+  // CTA also leaves the device copy the births of the next predict read): no copy, no staging slot
+  for (int k = 0; k < c->ld * nZ; k++) c->Zval[k] = Z[k];
   int launches = 0;
   {  // launch configuration (occupancy queries on the first call of a mode): host work, kept out of the timed span
     const int mf = c->cfg.use_cluster_process ? 0 : 1;
@@ -963,10 +964,6 @@ static int enqueue_update(rfsb200_ctx* c, const double* Z, int32_t nZ, uint32_t 
     if (rc0) return rc0;
   }
   if (timed) CU(c, cudaEventRecord(c->ev0, c->stream));
-  if (!z_resident) {
-    CU(c, cudaMemcpyAsync(c->Zdev, zsrc, (size_t)c->ld * nZ * c->tsize, cudaMemcpyHostToDevice, c->stream));
-    CU(c, cudaEventRecord(c->zev[zslot_used], c->stream));
-  }
   const int out_idx = c->front ^ 1;
   if ((flags & RFSB200_UPDATE_FUSED_ALLREDUCE) && c->comm_world > 1 && !c->comm_peer[0])
     return fail(c, RFSB200_ESTATE, "RFSB200_UPDATE_FUSED_ALLREDUCE before rfsb200_comm_connect");
@@ -1057,31 +1054,63 @@ int rfsb200_update_host(rfsb200_ctx* c, const double* pose, const double* pose_c
     if (ok) {
       int rc = ensure_pinned(c, 1 << 16);
       if (rc) return rc;
-      HostInParams h{};
-      h.pose = d_pose; h.weight = d_w; h.pcov = d_cov; h.mode = mode; h.N = c->N; h.nz_vals = c->ld * nZ;
-      if (mode == 1) for (int k = 0; k < 6; k++) h.cov6[k] = pose_cov[k];
-      for (int k = 0; k < c->ld * nZ; k++) h.Z[k] = Z[k];
-      const int n_thr = std::max(c->N, c->ld * nZ);
-      double* w_dev = c->st[c->front].weight;
-      if (c->prec == 32) host_in_kernel<float><<<(n_thr + 255) / 256, 256, 0, c->stream>>>(h, c->stg_small, (float*)c->pose, (float*)c->pose_cov, w_dev, (float*)c->Zdev);
-      else host_in_kernel<double><<<(n_thr + 255) / 256, 256, 0, c->stream>>>(h, c->stg_small, (double*)c->pose, (double*)c->pose_cov, w_dev, (double*)c->Zdev);
-      CU(c, cudaGetLastError());
+      unsigned long long* stats_h = (unsigned long long*)(c->hpin + 8192);   // where fill_stats reads the step scalars
+      volatile unsigned long long* done_h = (volatile unsigned long long*)(c->hpin + 8192 + 256);
+      const bool fused_in = c->ld == 2;   // the 2-D kernels read the inputs themselves; the Victoria Park kernels get them converted
+      if (fused_in) {
+        c->hin_pose = d_pose; c->hin_weight = d_w; c->hin_pcov = d_cov;
+        if (mode == 1) for (int k = 0; k < 6; k++) c->hin_cov6[k] = pose_cov[k];
+      } else {
+        HostInParams h{};
+        h.pose = d_pose; h.weight = d_w; h.pcov = d_cov; h.mode = mode; h.N = c->N; h.nz_vals = 0;
+        if (mode == 1) for (int k = 0; k < 6; k++) h.cov6[k] = pose_cov[k];
+        double* w_dev = c->st[c->front].weight;
+        if (c->prec == 32) host_in_kernel<float><<<(c->N + 255) / 256, 256, 0, c->stream>>>(h, c->stg_small, (float*)c->pose, (float*)c->pose_cov, w_dev, (float*)c->Zdev);
+        else host_in_kernel<double><<<(c->N + 255) / 256, 256, 0, c->stream>>>(h, c->stg_small, (double*)c->pose, (double*)c->pose_cov, w_dev, (double*)c->Zdev);
+        CU(c, cudaGetLastError());
+      }
       c->pose_cov_mode = mode;
       c->have_poses = true;
-      unsigned long long* stats_h = (unsigned long long*)(c->hpin + 8192);   // where fill_stats reads the step scalars
       c->w_host = d_wout; c->unused_host = d_unused; c->nfov_host = d_nfov;
       c->stats_host = out ? device_view(stats_h) : nullptr;
       const bool stats_direct = out && c->stats_host;
+      // completion word: the last CTA of the update kernel sets it when every result is in host memory — possible when
+      // that kernel is the last launch of the step (no separate normalisation) and nothing else has to be copied back
+      const bool poll = (flags & (RFSB200_UPDATE_NO_NORMALIZE | RFSB200_UPDATE_FUSED_ALLREDUCE)) && (!out || stats_direct) &&
+                        !(flags & RFSB200_UPDATE_STAGE_TIMES);
+      c->done_host = poll ? device_view((unsigned long long*)done_h) : nullptr;
+      const unsigned long long seq = ++c->done_seq;
       int l = 0;
-      rc = enqueue_update(c, Z, nZ, flags, out != nullptr, &l, /*z_resident=*/true);
+      rc = enqueue_update(c, Z, nZ, flags, out != nullptr, &l);
+      const bool polling = c->done_host != nullptr;
       c->w_host = nullptr; c->unused_host = nullptr; c->nfov_host = nullptr; c->stats_host = nullptr;
+      c->hin_pose = nullptr; c->hin_weight = nullptr; c->hin_pcov = nullptr; c->done_host = nullptr;
       if (rc) return rc;
       if (out && !stats_direct) {
         rc = enqueue_stats(c);
         if (rc) return rc;
       }
-      CU(c, cudaStreamSynchronize(c->stream));
-      if (out) return fill_stats(c, 1 + l, out);
+      if (polling) {
+        // wait on the word instead of the stream (a stream synchronisation costs several microseconds of wake-up);
+        // the stream is queried now and then so that a failed launch cannot hang the caller
+        unsigned spins = 0;
+        while (*done_h != seq) {
+          if ((++spins & 0x3fffu) == 0u) {
+            const cudaError_t q = cudaStreamQuery(c->stream);
+            if (q == cudaSuccess) break;
+            if (q != cudaErrorNotReady) { CU(c, q); }
+          }
+#if defined(__x86_64__) || defined(_M_X64)
+          __builtin_ia32_pause();
+#endif
+        }
+        if (out) {   // the events of the timed span: recorded long ago, complete with the kernel
+          CU(c, cudaEventSynchronize(c->ev1));
+        }
+      } else {
+        CU(c, cudaStreamSynchronize(c->stream));
+      }
+      if (out) return fill_stats(c, (fused_in ? 0 : 1) + l, out);
       return RFSB200_OK;
     }
   }

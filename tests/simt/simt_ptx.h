@@ -75,6 +75,12 @@ inline unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) {
   simt::spin_yield();
   return v;
 }
+inline void st_release_gpu_u64(unsigned long long* p, unsigned long long v) { *reinterpret_cast<volatile unsigned long long*>(p) = v; }
+inline unsigned long long ld_acquire_gpu_u64(const unsigned long long* p) {
+  const unsigned long long v = *reinterpret_cast<const volatile unsigned long long*>(p);
+  simt::spin_yield();
+  return v;
+}
 inline unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
   const unsigned long long v = *reinterpret_cast<const volatile unsigned long long*>(p);
   simt::spin_yield();

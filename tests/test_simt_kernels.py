@@ -156,7 +156,7 @@ def test_pageable_buffers_take_the_staged_path_with_the_same_results(simt_lib, m
             up.close()
     a, b = res
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]) and a[3] == b[3]
-    assert a[4] == 2 and b[4] == 2            # conversion kernel + update kernel either way (pose_convert / host_in)
+    assert a[4] == 1 and b[4] == 2            # pinned: the update kernel alone; pageable: pose_convert + update
     for x, y in zip(a[5], b[5]):
         assert np.array_equal(x, y)
 
