@@ -311,7 +311,9 @@ class RBPHDFilter : public ParticleFilter<RobotProcessModel, MeasurementModel,
     bool useClusterProcess_;
   } config;
 
-  /** include/RBPHDFilter.hpp:152-167; the *_wall fields are filled from CUDA events (ns). */
+  /** include/RBPHDFilter.hpp:152-167; the *_wall fields are filled from CUDA events / the device timers (ns).  The update
+   *  is ONE fused kernel, so with deviceConfig.stageTiming its wall time is attributed to the phases by the warp cycles
+   *  spent in them (rfsb200_get_stage_times); mapUpdate_wall is always the whole device step. */
   struct TimingInfo {
     long long predict_wall, predict_cpu;
     long long mapUpdate_wall, mapUpdate_cpu;
@@ -335,6 +337,10 @@ class RBPHDFilter : public ParticleFilter<RobotProcessModel, MeasurementModel,
     int zCapacity;      /**< measurements per update (<= 64) */
     int device;         /**< CUDA device ordinal */
     int precision;      /**< 32 (product) or 64 (verification build) */
+    int stageTiming;    /**< != 0 (or RFSB200_STAGE_TIMES=1 in the environment): every update runs the stage-timing build of
+                             the kernel (RFSB200_UPDATE_STAGE_TIMES, a few percent slower) and getTimingInfo() fills
+                             mapUpdate_kf / particleWeighting / mapMerge / mapPrune as the reference's single-thread run
+                             does (include/RBPHDFilter.hpp:1219-1232); 0: the whole step is booked under mapUpdate */
   } deviceConfig;
 
   RBPHDFilter(int n);
@@ -385,6 +391,7 @@ class RBPHDFilter : public ParticleFilter<RobotProcessModel, MeasurementModel,
   rfsb200_step_out lastStep_;
   Timer timer_predict_, timer_particleResample_;
   long long ns_update_;
+  long long ns_kf_ = 0, ns_weighting_ = 0, ns_merge_ = 0, ns_prune_ = 0;   /* deviceConfig.stageTiming */
   /* one-particle cache for getLandmark */
   int cacheIdx_;
   std::vector<double> cMean_, cCov_, cW_;
@@ -440,6 +447,7 @@ RBPHDFilter<R, L, M, K>::RBPHDFilter(int n)
   deviceConfig.zCapacity = 64;
   deviceConfig.device = 0;
   deviceConfig.precision = 32;
+  deviceConfig.stageTiming = 0;
   /* unchanged drivers cannot reach deviceConfig: the environment can (verification runs) */
   if (const char* e = getenv("RFSB200_PRECISION")) deviceConfig.precision = atoi(e);
   if (const char* e = getenv("RFSB200_DEVICE")) deviceConfig.device = atoi(e);
@@ -607,10 +615,22 @@ void RBPHDFilter<R, L, M, K>::update(std::vector<TMeasurement>& Z) {
   /* all particles: map update, weighting, merge, prune, weight sums — no normalisation yet, the
    * resampling gate needs the unnormalised weights exactly like the reference */
   /* one ABI call, one synchronisation: poses / pose covariances / weights / Z in, unnormalised weights out */
+  const bool stageTiming = (deviceConfig.stageTiming != 0 || getenv("RFSB200_STAGE_TIMES") != NULL) && deviceConfig.precision == 32 &&
+                           md.model_id == RFSB200_MODEL_RNGBRG;
   check(rfsb200_update_host(ctx_, hPose_.data(), anyCov ? hPoseCov_.data() : NULL, anyCov ? 2 : 0, hW_.data(), z.data(),
-                            (int32_t)nZ, RFSB200_UPDATE_NO_NORMALIZE, hWout_.data(), NULL, NULL, &lastStep_),
+                            (int32_t)nZ, RFSB200_UPDATE_NO_NORMALIZE | (stageTiming ? RFSB200_UPDATE_STAGE_TIMES : 0u),
+                            hWout_.data(), NULL, NULL, &lastStep_),
         "rfsb200_update_host");
   ns_update_ += (long long)(lastStep_.elapsed_us * 1000.0);
+  if (stageTiming) {
+    rfsb200_stage_times st;
+    check(rfsb200_get_stage_times(ctx_, &st), "rfsb200_get_stage_times");
+    const double loop_ns = st.particles_us * 1000.0;
+    ns_kf_ += (long long)(loop_ns * st.share_map_update_kf);
+    ns_weighting_ += (long long)(loop_ns * st.share_weighting);
+    ns_merge_ += (long long)(loop_ns * st.share_merge);
+    ns_prune_ += (long long)(loop_ns * st.share_prune);
+  }
   unusedFresh_ = true;
   if (lastStep_.n_overflow > 0 && !overflowWarned_) {
     /* a map outgrew the device capacities: Gaussians were dropped, results differ from the reference from here on */
@@ -875,6 +895,10 @@ typename RBPHDFilter<R, L, M, K>::TimingInfo* RBPHDFilter<R, L, M, K>::getTiming
    * than one thread (include/RBPHDFilter.hpp:466-468,521-523) */
   timingInfo_.mapUpdate_wall = ns_update_;
   timingInfo_.mapUpdate_cpu = 0;
+  timingInfo_.mapUpdate_kf_wall = ns_kf_;            /* 0 unless deviceConfig.stageTiming */
+  timingInfo_.particleWeighting_wall = ns_weighting_;
+  timingInfo_.mapMerge_wall = ns_merge_;
+  timingInfo_.mapPrune_wall = ns_prune_;
   return &timingInfo_;
 }
 

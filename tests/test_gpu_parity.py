@@ -409,3 +409,33 @@ def test_randomised_sweep_fp64(cuda_required):
     r = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_parity.py"), "60", "4242"], capture_output=True,
                        text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("sc", [1, 0], ids=["sc", "mf"])
+def test_stage_timing_build_equals_the_product_kernel(cuda_required, sc):
+    """RFSB200_UPDATE_STAGE_TIMES runs the stage-timing instantiation of the update kernel (TimingInfo per phase,
+    include/RBPHDFilter.hpp:152-167): same bits in every output, shares that add up, a wall-time split that adds up."""
+    from rfs_slam_b200 import capi, synth
+    from rfs_slam_b200.phd import PHDUpdater
+    wl = synth.make_workload(N=600, nM=90, nZ=18, use_cluster_process=sc, config_id=33 + sc)
+    res = []
+    for flag in (0, capi.UPDATE_STAGE_TIMES):
+        up = PHDUpdater(wl.N, gm_capacity=160, z_capacity=32)
+        up.load_workload(wl)
+        up.update(wl.Z, flags=capi.UPDATE_NO_NORMALIZE | flag)
+        res.append((up.get_weights(), up.download_maps(), up.get_unused()))
+        if flag:
+            st = up.stage_times()
+            shares = [st[k] for k in ("share_load", "share_map_update_kf", "share_weighting", "share_merge", "share_prune")]
+            assert all(s >= 0 for s in shares) and sum(shares) == pytest.approx(1.0, abs=1e-9)
+            assert st["share_map_update_kf"] > 0.02 and st["share_merge"] > 0.02
+            assert st["kernel_us"] > 0 and st["kernel_us"] == pytest.approx(st["setup_us"] + st["particles_us"] + st["epilogue_us"], rel=1e-6)
+            assert sum(st["merge_parts"].values()) <= st["share_merge"] + 1e-9
+            if sc == 0:
+                assert st["share_weighting"] > 0.1
+        up.close()
+    a, b = res
+    assert np.array_equal(a[0], b[0])
+    for x, y in zip(a[1], b[1]):
+        assert np.array_equal(x, y)
+    assert np.array_equal(a[2][0], b[2][0]) and np.array_equal(a[2][1], b[2][1])
