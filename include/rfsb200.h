@@ -61,7 +61,8 @@ extern "C" {
                                          [sum w, sum w^2] pairs of all ranks through peer memory (NVLink)
                                          and normalises, in the same launch; every rank must call
                                          rfsb200_update with this flag the same number of times      */
-#define RFSB200_UPDATE_STAGE_TIMES 8u   /* run the stage-timing build of the update kernel (same results): fills what
+#define RFSB200_UPDATE_STAGE_TIMES 8u   /* run the stage-timing build of the update kernel (same results up to the last
+                                         bits of fp32: another instantiation of the same source): fills what
                                          rfsb200_get_stage_times() returns — the reference's per-phase TimingInfo
                                          (include/RBPHDFilter.hpp:152-167,1219-1232).  fp32 build; a measurement
                                          aid, a few percent slower than the product kernel                   */

@@ -95,13 +95,18 @@ def golden_stage(g, st):
 
 
 # ---- epsilon-band exclusion (SURVEY.md §8d "structural decisions must agree except ...") ---------
-def robust_mask(wl, eps=1e-3):
+def robust_mask(wl, eps=1e-3, rules=None):
     """Particles whose discrete decisions (gate, sensing limit, merge, prune, eval-point cut) do
     not change when every threshold is moved by +-eps (relative; absolute 1e-5 on range limits):
     for those an fp32 device result must agree STRUCTURALLY with the fp64 oracle.  The others sit
-    inside the epsilon band of some threshold and are listed / excluded by the caller."""
+    inside the epsilon band of some threshold and are listed / excluded by the caller.
+    rules (a dict, optional) receives how many particles each rule was the FIRST to exclude."""
     import copy
     from oracle import binding as ob
+    rules = {} if rules is None else rules
+
+    def note(name, before):
+        rules[name] = rules.get(name, 0) + int(before.sum() - ok.sum())
 
     def run(scale, geometry=True, stages=(1, 3, 4)):
         w2 = copy.copy(wl)
@@ -142,10 +147,14 @@ def robust_mask(wl, eps=1e-3):
                 #  swap at 5.9e-6)
                 if np.any((gap > 0) & (gap < 2e-5 * np.maximum(w[:-1], 1e-30))):
                     ok[i] = False
+    note("weight_sort_near_tie", np.ones(wl.N, dtype=bool))
+    prev = ok.copy()
     for a, b, c in zip(base, up, dn):
         ok &= (a.count == b.count) & (a.count == c.count)
         ok &= (a.unused_mask == b.unused_mask) & (a.unused_mask == c.unused_mask)
         ok &= (a.n_in_fov == b.n_in_fov) & (a.n_in_fov == c.n_in_fov)
+    note("count_or_mask_changes_under_threshold_move", prev)
+    prev = ok.copy()
     # a merge decision can flip without changing the count (a small component joins another cluster): the merged
     # weights of the final mixture move then, while moving a threshold alone leaves them untouched.  (Thresholds only:
     # the Victoria Park runs above also move the geometry, which changes every weight a little.)
@@ -164,6 +173,8 @@ def robust_mask(wl, eps=1e-3):
                 b = np.abs((b + np.pi) % (2 * np.pi) - np.pi)
                 if np.any(np.pi - b < 2e-6):
                     ok[i] = False
+        note("predicted_bearing_at_pi", prev)
+        prev = ok.copy()
     a, off = final[0], offsets(final[0].count)
     for o in final[1:]:
         off_o = offsets(o.count)
@@ -171,7 +182,27 @@ def robust_mask(wl, eps=1e-3):
             wa, wo = a.w[off[i]:off[i + 1]], o.w[off_o[i]:off_o[i + 1]]
             if len(wa) != len(wo) or not np.allclose(wa, wo, rtol=1e-9, atol=1e-12):
                 ok[i] = False
+    note("final_weights_move_under_threshold_move", prev)
     return ok
+
+
+# ---- parity report (tests/conftest.py writes it to gpurun_out/parity_report.json at the end of a GPU session) ----------
+PARITY_RECORDS = []
+
+
+def parity_record(test, wl, robust, bad, rules=None, tol="fp32 vs fp64 reference (TOL32)"):
+    """One line of the parity report: particles compared, particles inside an epsilon band (by the rule that put them
+    there), particles that differ from the reference, and how many of those no rule explains (must be 0)."""
+    bad = set(int(i) for i in bad)
+    n = int(wl.N)
+    if test is None:
+        test = os.environ.get("PYTEST_CURRENT_TEST", "?").split(" ")[0]
+    in_band = int(n - int(np.asarray(robust).sum())) if robust is not None else 0
+    rec = dict(test=test, particles=n, in_epsilon_band=in_band, in_epsilon_band_by_rule=dict(rules or {}),
+               differing=len(bad), differing_unexplained=len([i for i in bad if robust is None or robust[i]]),
+               differing_frac=len(bad) / max(n, 1), tolerance=tol)
+    PARITY_RECORDS.append(rec)
+    return rec
 
 
 def run_device(wl, precision=32, flags=None, gm_capacity=None, work_capacity=0, brute=False, z_capacity=None):

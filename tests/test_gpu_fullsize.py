@@ -37,15 +37,18 @@ def test_full_size_properties(cuda_required, name):
     # normalisation: sum to one
     up.normalize()
     assert up.get_weights().sum() == pytest.approx(1.0, abs=1e-12)
-    # the oracle on the shard
-    o = ob.run(sh, sort_mode=ob.SORT_STABLE)
+    # the oracle on EVERY particle of the configuration (C3: 8 000 particles in 0.7 s; the epsilon-band classification
+    # re-runs it ten times): at most 0.5 % may differ, each of them inside an epsilon band of a threshold
+    o = ob.run(wl, sort_mode=ob.SORT_STABLE)
     ref = dict(count=o.count, mean=o.mean, cov=o.cov, w=o.w, weight=o.weight)
-    robust = helpers.robust_mask(sh)
-    r = helpers.compare_maps(cnt3, mean3, cov3, w3, ref["count"], ref["mean"], ref["cov"], ref["w"], helpers.TOL32)
-    rw = helpers.compare_weights(pw3, ref["weight"], helpers.TOL32)
+    rules = {}
+    robust = helpers.robust_mask(wl, rules=rules)
+    r = helpers.compare_maps(cnt, mean, cov, w, ref["count"], ref["mean"], ref["cov"], ref["w"], helpers.TOL32)
+    rw = helpers.compare_weights(pw, ref["weight"], helpers.TOL32)
     bad = set(r["bad"]) | set(int(i) for i in rw["idx_bad"])
+    helpers.parity_record(None, wl, robust, bad, rules)
     assert not [i for i in bad if robust[i]]
-    assert len(bad) <= max(2, sh.N // 50)
+    assert len(bad) <= max(2, int(0.005 * wl.N))
     for u in (up, up2, up3):
         u.close()
 

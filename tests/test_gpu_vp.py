@@ -17,8 +17,9 @@ def test_vp_against_reference_golden(cuda_required, case, prec):
     wl, g = helpers.load_golden(case)
     ref = helpers.golden_stage(g, 4)
     so, cnt, mean, cov, w, pw, up = helpers.run_device(wl, precision=prec, gm_capacity=128)
-    robust = helpers.robust_mask(wl) if prec == 32 else None
-    _check(wl, prec, ref, so, cnt, mean, cov, w, pw, robust)
+    rules = {}
+    robust = helpers.robust_mask(wl, rules=rules) if prec == 32 else None
+    _check(wl, prec, ref, so, cnt, mean, cov, w, pw, robust, rules=rules)
     mask, nfov = up.get_unused()
     ok = robust if robust is not None else np.ones(wl.N, bool)
     assert np.array_equal(mask[ok], ref["unused"][ok])
@@ -49,8 +50,9 @@ def test_vp_against_oracle(cuda_required, kw, prec):
     o = ob.run(wl, sort_mode=ob.SORT_STABLE)
     ref = dict(count=o.count, mean=o.mean, cov=o.cov, w=o.w, weight=o.weight)
     so, cnt, mean, cov, w, pw, up = helpers.run_device(wl, precision=prec, gm_capacity=256)
-    robust = helpers.robust_mask(wl) if prec == 32 else None
-    _check(wl, prec, ref, so, cnt, mean, cov, w, pw, robust)
+    rules = {}
+    robust = helpers.robust_mask(wl, rules=rules) if prec == 32 else None
+    _check(wl, prec, ref, so, cnt, mean, cov, w, pw, robust, rules=rules)
     if prec == 64:
         assert np.array_equal(cnt, o.count)
         assert np.allclose(mean, o.mean, rtol=0, atol=1e-9)
@@ -62,8 +64,8 @@ def test_vp_against_oracle(cuda_required, kw, prec):
 
 
 def test_vp_full_size_c5_properties(cuda_required):
-    """BASELINE config 5 shape (4 000 particles): run-to-run bit determinism, sharding invariance, and a
-    sample of particles against the oracle."""
+    """BASELINE config 5 shape (4 000 particles): run-to-run bit determinism, sharding invariance, and every particle
+    against the oracle (at most 0.5 % may differ, each of them inside an epsilon band)."""
     from oracle import binding as ob
     from rfs_slam_b200 import synth
     wl = synth.make_config("C5")
@@ -77,14 +79,12 @@ def test_vp_full_size_c5_properties(cuda_required):
     lo, hi = wl.N // 4, wl.N // 2
     assert np.array_equal(c[1], a[1][lo:hi]) and np.array_equal(c[5], a[5][lo:hi])
     c[6].close()
-    sub = wl.shard(0, 40)   # 100 particles
-    o = ob.run(sub, sort_mode=ob.SORT_STABLE)
-    robust = helpers.robust_mask(sub)
-    n = sub.N
-    off = helpers.offsets(a[1])
-    t = int(off[n])
-    _check(sub, 32, dict(count=o.count, mean=o.mean, cov=o.cov, w=o.w, weight=o.weight), a[0], a[1][:n], a[2][:t],
-           a[3][:t], a[4][:t], a[5][:n], robust)
+    # ALL 4 000 particles against the oracle (0.4 s; the epsilon-band classification re-runs it ten times)
+    o = ob.run(wl, sort_mode=ob.SORT_STABLE)
+    rules = {}
+    robust = helpers.robust_mask(wl, rules=rules)
+    _check(wl, 32, dict(count=o.count, mean=o.mean, cov=o.cov, w=o.w, weight=o.weight), a[0], a[1], a[2], a[3], a[4], a[5],
+           robust, max_excluded=0.005, rules=rules)
 
 
 def test_vp_predict_maps_births_and_process_noise(cuda_required):
