@@ -224,7 +224,10 @@ def run_workload(a, name, ctx, steps, warmup, headline):
     units_local = int(wl.count.sum()) * nZ
     D = wl.dim                                  # 2: RngBrg, 3: VictoriaPark
     gbytes = 4.0 * (D + D * (D + 1) // 2 + 1)   # fp32 bytes per Gaussian: 24 (2-D) / 40 (3-D)
-    up = PHDUpdater(N, gm_capacity=256, z_capacity=32, device=local, precision=32, lmk_dim=D)
+    # capacities per particle: 256 Gaussians (2-D workloads: up to 200 in + the corrector's); C5 holds 150 in, 192 is enough
+    # and buys the Victoria Park kernel three more resident warps per SM (overflows would show in n_overflow_per_step)
+    cap = 192 if name == "C5" else 256
+    up = PHDUpdater(N, gm_capacity=cap, z_capacity=32, device=local, precision=32, lmk_dim=D)
     up.load_workload(wl)
     fused = not a.no_fused
     sh = ShardedUpdater(up, device=dev, fused=fused)

@@ -125,6 +125,137 @@ __device__ __forceinline__ double vp_pd(const VPGeom& g, double px, double py, d
   return pmax;
 }
 
+// ---- probabilityOfDetection, fp32 with error bounds (fp32 kernels) -----------------------------------------------
+// The detection probability is a chain of discrete decisions (range / bearing limits, floor / ceil onto the half-degree
+// beams, "is this return behind the trunk") whose outcome must be the reference's, and a table look-up.  The fp32 kernels
+// evaluate the geometry in fp32 together with a bound on the rounding error of every compared quantity; a decision that
+// lies inside its bound is "too close to call" and the whole component is re-evaluated in fp64 (vp_pd above) — a few
+// components in a thousand.  The values returned are entries of the fp64 table either way, so a decisive fp32
+// evaluation returns the same bits as the fp64 one.
+struct VPFast {
+  float rmin, rmax, bmin, bmax;
+  const float* scan;   // [scan_n] float copy of the scan (shared memory); exact zeros stay exact
+};
+
+// probabilityOfDetection2 at the point pose + (dx, dy); e_pos = bound on the error of dx and dy.  false: undecided.
+__device__ __forceinline__ bool vp_pd2_fast(const VPGeom& g, const VPFast& f, float dx, float dy, float th, float ld,
+                                            float e_pos, double& val, bool& close) {
+  constexpr float PI_F = 3.14159265358979323846f;
+  close = false;
+  const float d2 = dx * dx + dy * dy;
+  const float dist = sqrtf(d2);
+  if (!(dist > 1e-3f)) return false;
+  const float e_dist = 1.5f * e_pos + 3e-7f * dist;
+  float angle = M<float>::atan2_(dy, dx) - th;
+  const float e_ang = 1.5f * e_pos / dist + 1.2e-6f;   // atan2 (1.1e-7 + input error), th and the subtraction (|angle| < 8)
+  if (angle > PI_F) angle -= 2 * PI_F;
+  if (angle < -PI_F) angle += 2 * PI_F;
+  if (!(fabsf(angle) < PI_F - e_ang)) return false;   // at the wrap (or |th| beyond one turn)
+  if (fabsf(angle - f.bmax) < e_ang || fabsf(angle - f.bmin) < e_ang || fabsf(dist - f.rmin) < e_dist || fabsf(dist - f.rmax) < e_dist)
+    return false;
+  if (angle > f.bmax || angle < f.bmin || dist < f.rmin || dist > f.rmax) { val = 0.0; return true; }
+  const float mr = 0.5f * ld;
+  const float gamma = M<float>::atan2_(mr, dist);   // = atan(mr / dist), both positive
+  const float e_gam = mr * e_dist / d2 + 3e-7f;
+  const float v = gamma * 229.18311805232929f;       // 2 gamma 720 / (2 pi)
+  const float e_v = 229.2f * e_gam + 3e-7f * v + 1e-6f;
+  const float fl = floorf(v);
+  if (v - fl < e_v || fl + 1.0f - v < e_v) return false;
+  const int maxNumPoints = (int)fl;
+  const bool in_tab = maxNumPoints >= 0 && g.pd_n > maxNumPoints;
+  if (in_tab && g.pd[maxNumPoints] == 0.0) { val = 0.0; return true; }
+  if (in_tab && g.pd[maxNumPoints] < g.buf_pd) close = true;
+  const float u = (angle - gamma) * 114.59155902616465f;   // 720 / (2 pi)
+  const float e_u = 114.6f * (e_ang + e_gam) + 3e-7f * fabsf(u) + 1e-5f;
+  const float cu = ceilf(u);
+  if (cu - u < e_u || u - (cu - 1.0f) < e_u) return false;
+  int minb = (int)cu;
+  int maxb = minb + maxNumPoints;
+  while (minb >= 720) minb -= 720;
+  while (minb < 0) minb += 720;
+  while (maxb >= 720) maxb -= 720;
+  while (maxb < 0) maxb += 720;
+  int numPoints = 0;
+  const float minrange = dist - mr - 0.18f;
+  const float e_s = e_dist + 2e-6f;
+  if ((maxb - minb + 720) % 720 > 0) {
+    for (int b = minb; b != maxb; b = (b + 1) % 720) {
+      if (b >= g.scan_n) continue;   // (see vp_pd2: such a beam counts no point)
+      const float s = f.scan[b];
+      if (s == 0.0f) { numPoints++; continue; }
+      if (fabsf(s - minrange) < e_s + 3e-7f * s) return false;
+      if (s > minrange) numPoints++;
+    }
+  }
+  if (numPoints >= g.pd_n) numPoints = g.pd_n - 1;
+  if (g.pd[numPoints] == 0.0) close = false;
+  val = g.pd[numPoints];
+  return true;
+}
+
+// probabilityOfDetection in fp32; false: something was too close to call (the caller runs vp_pd in fp64)
+__device__ __forceinline__ bool vp_pd_fast(const VPGeom& g, const VPFast& f, float px, float py, float pth, float lx, float ly,
+                                           float ld, float pxx, float pxy, float pyy, double& pd, bool& close) {
+  constexpr float PI_F = 3.14159265358979323846f;
+  const float th = pth - 0.5f * PI_F;
+  const float dx = lx - px, dy = ly - py;             // fp32 inputs: rounded once (half an ulp of the result)
+  const float e0 = 4e-8f * (fabsf(dx) + fabsf(dy)) + 1e-7f;
+  const float r0 = sqrtf(dx * dx + dy * dy);
+  float b0 = M<float>::atan2_(dy, dx) - th;
+  if (b0 > PI_F) b0 -= 2 * PI_F;
+  if (b0 < -PI_F) b0 += 2 * PI_F;
+  if (!(fabsf(b0) < PI_F - 2e-6f)) return false;      // the reference's wrap decides the evaluation direction here
+  const float angle = M<float>::atan2_(b0, r0) + pth;
+  float sn, cs;
+  __sincosf(angle, &sn, &cs);
+  const float ex = -sn, ey = cs;                      // direction error ~2e-6 (atan2 inputs, __sincosf)
+  float sd = (ex * pxx + ey * pxy) * ex + (ex * pxy + ey * pyy) * ey;
+  if (!(sd >= 0.0f) || !(ld > 0.0f)) return false;
+  sd = 3.0f * sqrtf(sd);
+  sd = sd < 0.2f ? 0.2f : sd;
+  if (!(sd < 1e30f)) return false;
+  close = false;
+  {
+    const float reach = (sd + 2.0f * ld) * 1.001f + 1e-3f;   // wider than the fp64 bound: skipping less is always right
+    if (r0 > f.rmax + reach || r0 < f.rmin - reach) { pd = 0.0; return true; }
+  }
+  double pmin = 1e300, pmax = -1e300;
+  const float step = 2.0f * ld;
+  const float e_sd = 2e-5f * sd + 1e-6f;
+  for (int i = 1; i <= 4096; i++) {
+    const float lim = (float)(i - 1) * step;
+    if (fabsf(lim - sd) < e_sd) return false;        // how many evaluation points there are is a decision too
+    if (!(lim < sd)) break;
+    const float s = (float)i * step;
+    const float e_pos = e0 + 4e-6f * s + 2e-6f;       // direction error x offset, roundings of the sums
+    double v;
+    if (!vp_pd2_fast(g, f, dx + s * ex, dy + s * ey, th, ld, e_pos, v, close)) return false;
+    pmin = v < pmin ? v : pmin;
+    pmax = v > pmax ? v : pmax;
+    if (!vp_pd2_fast(g, f, dx - s * ex, dy - s * ey, th, ld, e_pos, v, close)) return false;
+    pmin = v < pmin ? v : pmin;
+    pmax = v > pmax ? v : pmax;
+  }
+  double v;
+  if (!vp_pd2_fast(g, f, dx, dy, th, ld, e0, v, close)) return false;
+  pmin = v < pmin ? v : pmin;
+  pmax = v > pmax ? v : pmax;
+  if (pmin == 0.0 && pmax > 0.0) close = true;
+  pd = pmax;
+  return true;
+}
+
+template <typename T>
+__device__ __forceinline__ double vp_pd_any(const VPGeom& g, const VPFast& f, T px, T py, T pth, T lx, T ly, T ld, T pxx, T pxy,
+                                            T pyy, bool& close) {
+  if constexpr (sizeof(T) == 4) {
+    double pd;
+    if (vp_pd_fast(g, f, px, py, pth, lx, ly, ld, pxx, pxy, pyy, pd, close)) return pd;
+  }
+  return vp_pd(g, (double)px, (double)py, (double)pth, (double)lx, (double)ly, (double)ld, (double)pxx, (double)pxy,
+               (double)pyy, close);
+}
+
 // ---- 3x3 symmetric helpers (upper triangle a00 a01 a02 a11 a12 a22) ---------------------------------
 template <typename T>
 struct Sym3 {
@@ -169,21 +300,28 @@ __device__ __forceinline__ void load_sym3(Sym3<T>& s, const T* cur, int W, int i
 //            intensity and the L-table stages both need, lives in colsum[] (dead after S3).
 template <typename T>
 __host__ __device__ inline int vp_cta_bytes() {
-  return (int)((VP_SCAN_MAX * 8 + VP_PD_MAX * 8 + 3 * MAX_Z * sizeof(T) + 127) & ~127);
+  return (int)((VP_SCAN_MAX * 8 + VP_PD_MAX * 8 + 3 * MAX_Z * sizeof(T) + (sizeof(T) == 4 ? VP_SCAN_MAX * 4 : 0) + 127) & ~127);
 }
 template <typename T>
 __host__ __device__ inline int vp_mf_fixed_bytes(int n_eval, int zcap) {
   const int ltab = (n_eval * zcap + 3) & ~3;
-  return (int)(8 * (MAX_EVAL + MAX_COMP + 2 * (1 << DP_MAXB)) + 4 * MAX_COMP + sizeof(T) * (MAX_EVAL * VP_EP + ltab) + 15) & ~15;
+  return (int)(8 * (MAX_EVAL + MAX_COMP + 2 * (1 << DP_MAXB)) + 4 * MAX_COMP + sizeof(T) * (n_eval * VP_EP + ltab) + 15) & ~15;
 }
 // work region of a warp, used by stages that follow each other:
 //   sort of S5 / prune   keys u64[W] | order u16[W] | one temporary plane T[W]    (merge: reach T[W] aliases the keys,
 //                                                                                  firstCand aliases order)
 //   intensity of S5      7 planes T[W]
 //   L-table stage of S5  rowmask / components / DP tables / eval block / L table
+// (the fp32 kernels accept any work capacity W that is a multiple of 32; the bitonic sorts pad to a power of two, so
+//  the key array holds vp_key_cap(W) entries)
+__host__ __device__ inline int vp_key_cap(int W) {
+  int p = 32;
+  while (p < W) p <<= 1;
+  return p;
+}
 template <typename T>
 __host__ __device__ inline int vp_region_bytes(int W, int mf, int n_eval, int zcap) {
-  int r = W * 8 + ((W * 2 + 15) & ~15) + W * (int)sizeof(T);
+  int r = vp_key_cap(W) * 8 + ((W * 2 + 15) & ~15) + W * (int)sizeof(T);
   if (mf) {
     const int a = vp_mf_fixed_bytes<T>(n_eval, zcap), i7 = 7 * W * (int)sizeof(T);
     r = a > r ? a : r;
@@ -226,6 +364,7 @@ phd_update_vp_kernel(const __grid_constant__ VPParams<T> vp) {
   double* scan_s = reinterpret_cast<double*>(smem_raw);
   double* pd_s = scan_s + VP_SCAN_MAX;
   T* zs = reinterpret_cast<T*>(pd_s + VP_PD_MAX);   // [3 * MAX_Z]: (zr, zb, zd) per measurement
+  float* scan_f = reinterpret_cast<float*>(zs + 3 * MAX_Z);   // [720] fp32 kernels only: the scan for vp_pd_fast
   unsigned char* wb = smem_raw + vp_cta_bytes<T>() + (size_t)warp * p.warp_bytes;
   T* cur = reinterpret_cast<T*>(wb);
   unsigned* aux = reinterpret_cast<unsigned*>(cur + NPL * W);
@@ -234,11 +373,15 @@ phd_update_vp_kernel(const __grid_constant__ VPParams<T> vp) {
   uint64_t* bar = reinterpret_cast<uint64_t*>(evalIdx + MAX_EVAL);
   unsigned char* mfs = reinterpret_cast<unsigned char*>(bar + 2);       // the work region (vp_region_bytes)
   unsigned long long* k64 = reinterpret_cast<unsigned long long*>(mfs);
-  unsigned short* order = reinterpret_cast<unsigned short*>(k64 + W);
+  unsigned short* order = reinterpret_cast<unsigned short*>(k64 + vp_key_cap(W));
   T* sort_tmp = reinterpret_cast<T*>(reinterpret_cast<unsigned char*>(order) + ((W * 2 + 15) & ~15));
   T* rad2 = sort_tmp;                                                   // merge only (the sort of S5 is over)
 
-  for (int k = threadIdx.x; k < VP_SCAN_MAX; k += blockDim.x) scan_s[k] = k < vp.scan_n ? vp.scan[k] : 0.0;
+  for (int k = threadIdx.x; k < VP_SCAN_MAX; k += blockDim.x) {
+    const double v = k < vp.scan_n ? vp.scan[k] : 0.0;
+    scan_s[k] = v;
+    if constexpr (sizeof(T) == 4) scan_f[k] = (float)v;
+  }
   for (int k = threadIdx.x; k < VP_PD_MAX; k += blockDim.x) pd_s[k] = k < vp.pd_n ? vp.pd_table[k] : 0.0;
   for (int k = threadIdx.x; k < 3 * nZ; k += blockDim.x) {
     const T v = (T)p.Zval[k];
@@ -253,6 +396,9 @@ phd_update_vp_kernel(const __grid_constant__ VPParams<T> vp) {
   VPGeom geom;
   geom.rmin = vp.rmin; geom.rmax = vp.rmax; geom.bmin = vp.bmin; geom.bmax = vp.bmax; geom.buf_pd = vp.buf_pd;
   geom.pd = pd_s; geom.scan = scan_s; geom.pd_n = vp.pd_n; geom.scan_n = vp.scan_n > VP_SCAN_MAX ? VP_SCAN_MAX : vp.scan_n;
+  VPFast fast;
+  fast.rmin = (float)vp.rmin; fast.rmax = (float)vp.rmax; fast.bmin = (float)vp.bmin; fast.bmax = (float)vp.bmax;
+  fast.scan = scan_f;
 
   uint32_t phase = 0;
   unsigned long long tot_in = 0, tot_out = 0;
@@ -306,8 +452,7 @@ phd_update_vp_kernel(const __grid_constant__ VPParams<T> vp) {
         const T w = cur[VP_WP * W + m];
         wsum_d += (double)w;
         bool close = false;
-        T Pd = (T)vp_pd(geom, (double)px, (double)py, (double)pth, (double)x, (double)y, (double)d, (double)P.a00,
-                        (double)P.a01, (double)P.a11, close);
+        T Pd = (T)vp_pd_any<T>(geom, fast, px, py, pth, x, y, d, P.a00, P.a01, P.a11, close);
         if (close) Pd = T(1);   // Q2 (include/RBPHDFilter.hpp:604-606)
         if (Pd != T(0)) nfov++;
         if (MF) cur[WPREV * W + m] = w;
@@ -501,9 +646,9 @@ phd_update_vp_kernel(const __grid_constant__ VPParams<T> vp) {
         double* f0 = reinterpret_cast<double*>(compC + MAX_COMP);                   // [1<<DP_MAXB]
         double* f1 = f0 + (1 << DP_MAXB);
         unsigned* compR = reinterpret_cast<unsigned*>(f1 + (1 << DP_MAXB));         // [MAX_COMP]
-        T* ep = reinterpret_cast<T*>(compR + MAX_COMP);   // [MAX_EVAL][VP_EP - 1] eval-point block
+        T* ep = reinterpret_cast<T*>(compR + MAX_COMP);   // [n_eval_cap][VP_EP - 1] eval-point block
         T* evalPd = colsum;                               // [MAX_EVAL] (colsum is dead after S3; MAX_EVAL <= MAX_Z)
-        T* L = ep + MAX_EVAL * VP_EP;                     // [nE][nZ]
+        T* L = ep + p.n_eval_cap * VP_EP;                 // [nE][nZ]
         int nE = 0;
         for (int base = 0; base < n && nE < nEvalCfg; base += 32) {
           const int m = base + lane;
@@ -513,9 +658,8 @@ phd_update_vp_kernel(const __grid_constant__ VPParams<T> vp) {
             heavy = !(wpl[m] < p.eval_min_w);
             if (heavy) {
               bool close;
-              pdm = (T)vp_pd(geom, (double)px, (double)py, (double)pth, (double)cur[m], (double)cur[W + m],
-                             (double)cur[2 * W + m], (double)cur[3 * W + m], (double)cur[4 * W + m],
-                             (double)cur[6 * W + m], close);
+              pdm = (T)vp_pd_any<T>(geom, fast, px, py, pth, cur[m], cur[W + m], cur[2 * W + m], cur[3 * W + m], cur[4 * W + m],
+                                    cur[6 * W + m], close);
               elig = pdm > T(0);
             }
           }

@@ -699,6 +699,9 @@ int rfsb200_create(rfsb200_ctx** out, const rfsb200_dims* d) {
   c->npl = c->ld + c->nc + 1;
   c->cap = (d->gm_capacity + 7) & ~7;
   c->W = round_pow2(std::max(d->work_capacity, c->cap));
+  // the fp32 Victoria Park kernels take any multiple of 32: their planes are 11 x W words per warp, and W = 192 instead
+  // of 256 is the difference between 11 and 14 resident warps per SM
+  if (d->lmk_dim == 3 && d->precision == 32) c->W = (std::max(d->work_capacity, c->cap) + 31) & ~31;
   c->prec = d->precision;
   c->tsize = d->precision == 32 ? 4 : 8;
   c->device = d->device;

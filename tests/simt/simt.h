@@ -487,3 +487,4 @@ inline void sincospi(double x, double* s, double* c) { sincos(3.1415926535897932
 inline void sincospif(float x, float* s, float* c) { sincosf(3.14159265358979323846f * x, s, c); }
 inline double rsqrt(double x) { return 1.0 / sqrt(x); }
 inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
+inline void __sincosf(float x, float* s, float* c) { *s = sinf(x); *c = cosf(x); }
