@@ -566,7 +566,12 @@ void RBPHDFilter<R, L, M, K>::update(std::vector<TMeasurement>& Z) {
   fc.merging_cov_inflation_factor = config.gaussianMergingCovarianceInflationFactor_;
   fc.pruning_threshold = config.gaussianPruningThreshold_;
   fc.eval_point_count = config.importanceWeightingEvalPointCount_ < 0 ? 32 : config.importanceWeightingEvalPointCount_;  /* Q14 */
+  /* (the device evaluates at most 32 eval points, MAX_EVAL: the reference's -1 means "as many as qualify"; a count above 32
+   *  makes rfsb200_set_filter_cfg fail with RFSB200_EUNSUPPORTED rather than truncate silently) */
   fc.use_cluster_process = config.useClusterProcess_ ? 1 : 0;
+  /* quirk Q7: partitions with nR + nC > 8 contribute the sum of Murty's 200 best assignments, as in the reference
+   * (include/RBPHDFilter.hpp:904-959); RFSB200_EXACT_SUMS=1 keeps the device's exact sums (such particles are flagged) */
+  fc.murty_compat = getenv("RFSB200_EXACT_SUMS") ? 0 : 1;
   check(rfsb200_set_filter_cfg(ctx_, &fc), "rfsb200_set_filter_cfg");
 
   const bool anyCov = gatherPoses();

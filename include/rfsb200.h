@@ -140,7 +140,15 @@ typedef struct rfsb200_filter_cfg {
                                                     partitions of up to 11 members whose Ryser-type sum is
                                                     numerically safe (a-posteriori cancellation bound),
                                                     the subset DP otherwise                           */
-  int32_t reserved_i[3];
+  int32_t murty_compat;                          /* != 0 (multi-feature weighting): reproduce quirk Q7 — a partition with
+                                                    nR + nC > 8 contributes the sum of Murty's 200 best assignments
+                                                    (include/RBPHDFilter.hpp:904-959) instead of the exact sum: the device
+                                                    writes such partitions out, the host replaces their sums (own k-best
+                                                    enumeration, csrc/murty_compat.hpp) before the weights are added up.
+                                                    The update is synchronous then, and not available together with
+                                                    RFSB200_UPDATE_FUSED_ALLREDUCE on more than one rank.  0: exact sums,
+                                                    flag bit 2 marks the particles whose weight the reference truncates */
+  int32_t reserved_i[2];
   double  reserved[6];
 } rfsb200_filter_cfg;
 

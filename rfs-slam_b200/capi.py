@@ -54,7 +54,7 @@ class FilterCfg(C.Structure):
                 ("merging_cov_inflation_factor", C.c_double),
                 ("pruning_threshold", C.c_double),
                 ("eval_point_count", C.c_int32), ("use_cluster_process", C.c_int32),
-                ("assignment_sum_method", C.c_int32), ("reserved_i", C.c_int32 * 3),
+                ("assignment_sum_method", C.c_int32), ("murty_compat", C.c_int32), ("reserved_i", C.c_int32 * 2),
                 ("reserved", C.c_double * 6)]
 
 
@@ -109,7 +109,7 @@ def filter_cfg(fc: dict) -> FilterCfg:
               "eval_point_gaussian_weight", "meas_likelihood_md_threshold", "merging_threshold",
               "merging_cov_inflation_factor", "pruning_threshold"):
         setattr(c, k, float(fc[k]))
-    for k in ("eval_point_count", "use_cluster_process", "assignment_sum_method"):
+    for k in ("eval_point_count", "use_cluster_process", "assignment_sum_method", "murty_compat"):
         setattr(c, k, int(fc.get(k, 0)))
     return c
 

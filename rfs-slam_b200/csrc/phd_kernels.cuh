@@ -36,6 +36,18 @@ constexpr int FLAG_BIRTH_OVERFLOW = 8;   // set by predict / append when births 
                                          // it into FLAG_OVERFLOW of its own result (and counts it), so the drop is not lost
 constexpr int FLAG_MURTY = 2;       // a partition with nR + nC > 8 (reference would use Murty-200)
 constexpr int FLAG_DP_OVERFLOW = 4; // partition too large for the on-chip DP
+constexpr int FLAG_MURTY_DROPPED = 16;   // Murty compatibility: the record of a partition did not fit the record buffer
+
+// Murty compatibility (rfsb200_filter_cfg::murty_compat, quirk Q7): for a partition with nR + nC > 8 the reference adds up
+// Murty's 200 best assignments only (include/RBPHDFilter.hpp:904-959).  The device always adds up ALL assignments; with
+// the switch on it also writes the partition out — eval points' P_D, the likelihood block, the log of its exact sum —
+// and the host replaces the exact sum by the truncated one (murty_compat.hpp) before the weights are summed.
+struct MurtyOut {
+  unsigned long long* buf;   // records: [pi | nR << 32] [nC] [log exact sum] [P_D x nR] [L x nR x nC], 8-byte words
+  unsigned int* count;       // [0] words used, [1] records written
+  unsigned int cap_words;
+  int pi;
+};
 
 struct CommSlot { double s1, s2; unsigned long long epoch; unsigned long long pad; };   // 32 B; mailbox = [4][8]: banks 0 / 1 the
                                                                                          // weight sums of even / odd update epochs, 2 / 3 rfsb200_comm_barrier
@@ -120,6 +132,9 @@ struct KParams {
   // fused cross-GPU sum of [sum w, sum w^2] over peer memory (NVLink / NVSwitch), see S8
   int comm_rank, comm_world, fused_normalize;
   unsigned long long comm_epoch;
+  unsigned long long* murty_buf;    // Murty compatibility (see MurtyOut); NULL = off
+  unsigned int* murty_count;
+  unsigned int murty_cap_words;
   void* comm_peer[8];               // mailbox of every rank (own included), mapped into this process
   int* comm_error;                  // set to 1 if a peer did not arrive in time
   unsigned long long comm_timeout_ns;   // how long the last CTA waits for the peers (RFSB200_COMM_TIMEOUT_MS, default 2 s)
@@ -965,7 +980,7 @@ __device__ __forceinline__ double mf_partition_loglik(const T* L, const T* evalP
                                                       unsigned long long* rowmask, unsigned long long* compC,
                                                       double* f0, double* f1, unsigned* compR, int sum_method,
                                                       double log_kappa, int& flags, int lane, double* gdp, int gmaxb,
-                                                      int dp_onchip) {
+                                                      int dp_onchip, const MurtyOut& mo) {
   double logL = 0;
   if (lane < nE) {
     unsigned long long rm = 0;
@@ -1108,6 +1123,7 @@ __device__ __forceinline__ double mf_partition_loglik(const T* L, const T* evalP
         double* const d0 = offchip ? gdp : f0;
         double* const d1 = offchip ? gdp + (1 << gmaxb) : f1;
         __syncwarp();
+        double plog;
         if (sum_method == 1 && nR + nC <= 11) {
           // MatPerm path: sum = (prod kappa) * perm([[L/kappa, diag(1-Pd)],[ones]]) / nC!
           const int nn = nR + nC;
@@ -1138,15 +1154,44 @@ __device__ __forceinline__ double mf_partition_loglik(const T* L, const T* evalP
           __syncwarp();
           if (rel_err < 1e-11) {
             double fact = 1; for (int k = 2; k <= nC; k++) fact *= k;
-            logL += log(perm / fact) + (double)nC * log_kappa;
+            plog = log(perm / fact) + (double)nC * log_kappa;
           } else {
-            const double pl = partition_dp<T>(L, nZ, cr, cc, evalPd, kap, d0, d1, lane);
-            logL += log(pl);
+            plog = log(partition_dp<T>(L, nZ, cr, cc, evalPd, kap, d0, d1, lane));
           }
           __syncwarp();
         } else {
-          const double pl = partition_dp<T>(L, nZ, cr, cc, evalPd, kap, d0, d1, lane);
-          logL += log(pl);
+          plog = log(partition_dp<T>(L, nZ, cr, cc, evalPd, kap, d0, d1, lane));
+        }
+        logL += plog;
+        if (mo.buf != nullptr && nR + nC > 8) {   // Murty compatibility: the partition goes to the host
+          const unsigned words = 3u + (unsigned)nR + (unsigned)(nR * nC);
+          unsigned base = 0;
+          if (lane == 0) base = atomicAdd(&mo.count[0], words);
+          base = __shfl_sync(FULL, base, 0);
+          if (base + words <= mo.cap_words) {
+            unsigned long long* rec = mo.buf + base;
+            if (lane == 0) {
+              rec[0] = (unsigned long long)(unsigned)mo.pi | ((unsigned long long)(unsigned)nR << 32);
+              rec[1] = (unsigned long long)(unsigned)nC;
+              rec[2] = (unsigned long long)__double_as_longlong(plog);
+            }
+            for (int k = lane; k < nR; k += 32) {
+              const int r = (int)__fns(cr, 0, k + 1);
+              rec[3 + k] = (unsigned long long)__double_as_longlong((double)evalPd[r]);
+            }
+            for (int k = lane; k < nR * nC; k += 32) {
+              const int ri = k / nC, ci = k - ri * nC;
+              const int r = (int)__fns(cr, 0, ri + 1);
+              const unsigned lo = (unsigned)(cc & 0xffffffffull), hi = (unsigned)(cc >> 32);
+              const int nlo = __popc(lo);
+              const int c = ci < nlo ? (int)__fns(lo, 0, ci + 1) : 32 + (int)__fns(hi, 0, ci - nlo + 1);
+              rec[3 + nR + k] = (unsigned long long)__double_as_longlong((double)L[r * nZ + c]);
+            }
+            __threadfence();
+            if (lane == 0) atomicAdd(&mo.count[1], 1u);
+          } else {
+            flags |= FLAG_MURTY_DROPPED;
+          }
         }
       }
     }
@@ -2154,8 +2199,10 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
         }
         __syncwarp();
         double* gdp = p.dp_scratch ? p.dp_scratch + ((size_t)(blockIdx.x * (blockDim.x >> 5) + warp) << (p.dp_gmaxb + 1)) : nullptr;
+        MurtyOut mo;
+        mo.buf = p.murty_buf; mo.count = p.murty_count; mo.cap_words = p.murty_cap_words; mo.pi = pi;
         double logL = mf_partition_loglik<T>(L, evalPd, nE, nZ, rowmask, compC, f0, f1, compR, p.sum_method,
-                                            p.log_kappa, flags, lane, gdp, p.dp_gmaxb, p.dp_onchip);
+                                            p.log_kappa, flags, lane, gdp, p.dp_gmaxb, p.dp_onchip, mo);
         logL -= p.log_clutter_integral;
         // :808-812
         weight_new = exp(logL + (lp_before - lp_after) + (sw_now - sw_prev)) * w_prev_particle;
@@ -2490,6 +2537,28 @@ __global__ void propagate_kernel(double* __restrict__ pose64, T* __restrict__ po
   }
   pose64[3 * i] = x; pose64[3 * i + 1] = y; pose64[3 * i + 2] = th;
   pose[4 * i] = (T)x; pose[4 * i + 1] = (T)y; pose[4 * i + 2] = (T)th; pose[4 * i + 3] = T(0);
+}
+
+// Murty compatibility: w[idx[k]] *= ratio[k] (the truncated sums of the flagged particles), then the shard's
+// [sum w, sum w^2] again, in a fixed order (one CTA)
+__global__ void murty_patch_kernel(double* w, const int* idx, const double* ratio, int n) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) w[idx[k]] *= ratio[k];
+}
+__global__ void weight_sums_kernel(const double* w, int N, double* sums) {
+  __shared__ double r1[32], r2[32];
+  double a = 0, b = 0;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) { const double v = w[i]; a += v; b += v * v; }
+  a = warp_sum(a);
+  b = warp_sum(b);
+  if ((threadIdx.x & 31) == 0) { r1[threadIdx.x >> 5] = a; r2[threadIdx.x >> 5] = b; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s1 = 0, s2 = 0;
+    for (int k = 0; k < (int)(blockDim.x >> 5); k++) { s1 += r1[k]; s2 += r2[k]; }
+    sums[0] = s1;
+    sums[1] = s2;
+  }
 }
 
 // w_i /= sum  (ParticleFilter::normalizeWeights, include/ParticleFilter.hpp:352-363)

@@ -764,8 +764,10 @@ phd_update_vp_kernel(const __grid_constant__ VPParams<T> vp) {
         }
         __syncwarp();
         double* gdp = p.dp_scratch ? p.dp_scratch + ((size_t)(blockIdx.x * (blockDim.x >> 5) + warp) << (p.dp_gmaxb + 1)) : nullptr;
+        MurtyOut mo;
+        mo.buf = p.murty_buf; mo.count = p.murty_count; mo.cap_words = p.murty_cap_words; mo.pi = pi;
         double logL = mf_partition_loglik<T>(L, evalPd, nE, nZ, rowmask, compC, f0, f1, compR, p.sum_method,
-                                            p.log_kappa, flags, lane, gdp, p.dp_gmaxb, p.dp_onchip);
+                                            p.log_kappa, flags, lane, gdp, p.dp_gmaxb, p.dp_onchip, mo);
         logL -= p.log_clutter_integral;
         weight_new = exp(logL + (lp_before - lp_after) + (sw_now - sw_prev)) * w_prev_particle;   // :808-812
         __syncwarp();

@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "../../include/rfsb200.h"
+#include "murty_compat.hpp"
 #include "phd_kernels.cuh"
 #include "phd_vp_kernels.cuh"
 
@@ -104,6 +105,12 @@ struct rfsb200_ctx {
   // host-facing step: device views of the caller's INPUT buffers for the next launch (or NULL), and the completion word
   const double* hin_pose = nullptr; const double* hin_weight = nullptr; const double* hin_pcov = nullptr;
   double hin_cov6[6] = {};
+  // Murty compatibility (rfsb200_filter_cfg::murty_compat): partitions written out by the kernel, patch lists
+  unsigned long long* murty_buf = nullptr;   // [MURTY_WORDS]
+  unsigned int* murty_count = nullptr;       // [2]
+  int* murty_idx = nullptr;                  // [N]
+  double* murty_ratio = nullptr;             // [N]
+  int last_murty_terms = 0;                  // diagnostics: assignments enumerated by the last update
   unsigned long long* hin_ready = nullptr;   // [HIN_SLICES] slice flags of the host-facing step (KParams::hin_ready)
   unsigned long long* done_host = nullptr;   // device view of the pinned completion word for the next launch (or NULL)
   unsigned long long done_seq = 0;
@@ -451,6 +458,11 @@ int configure_launch(rfsb200_ctx* c, int mf) {
   return mf ? configure_launch_t<T, true>(c) : configure_launch_t<T, false>(c);
 }
 
+constexpr unsigned MURTY_WORDS = 1u << 20;   // 8 MB of partition records per update
+
+// Murty compatibility is in force for this update (multi-feature weighting with rfsb200_filter_cfg::murty_compat)
+inline bool murty_active(const rfsb200_ctx* c) { return c->have_cfg && c->cfg.murty_compat != 0 && !c->cfg.use_cluster_process; }
+
 template <typename T>
 int launch_update(rfsb200_ctx* c, int nZ, int out_idx, unsigned flags) {
   KParams<T> p{};
@@ -494,6 +506,20 @@ int launch_update(rfsb200_ctx* c, int nZ, int out_idx, unsigned flags) {
   // all), else normalize_kernel
   const bool normalize_follows = !(flags & (RFSB200_UPDATE_NO_NORMALIZE | RFSB200_UPDATE_FUSED_ALLREDUCE));
   p.w_host = normalize_follows ? nullptr : c->w_host;
+  if (murty_active(c)) {
+    // the host replaces the sums of the large partitions before the weights are added up (enqueue_update): this launch
+    // stops at the unnormalised weights
+    if (!c->murty_buf) {
+      CU(c, cudaMalloc((void**)&c->murty_buf, (size_t)MURTY_WORDS * 8));
+      CU(c, cudaMalloc((void**)&c->murty_count, 8));
+      CU(c, cudaMalloc((void**)&c->murty_idx, (size_t)c->N * 4));
+      CU(c, cudaMalloc((void**)&c->murty_ratio, (size_t)c->N * 8));
+    }
+    CU(c, cudaMemsetAsync(c->murty_count, 0, 8, c->stream));
+    p.murty_buf = c->murty_buf; p.murty_count = c->murty_count; p.murty_cap_words = MURTY_WORDS;
+    p.w_host = nullptr;
+    flags = (flags & ~RFSB200_UPDATE_FUSED_ALLREDUCE) | RFSB200_UPDATE_NO_NORMALIZE;
+  }
   if (flags & RFSB200_UPDATE_FUSED_ALLREDUCE) {
     p.comm_world = c->comm_world;
     p.fused_normalize = 1;
@@ -810,6 +836,7 @@ int rfsb200_destroy(rfsb200_ctx* c) {
   cudaFree(c->sums); cudaFree(c->totals); cudaFree(c->istats); cudaFree(c->ticket);
   cudaFree(c->work_counter); cudaFree(c->stats_out); cudaFree(c->mstats);
   cudaFree(c->stg); cudaFree(c->offs); cudaFree(c->stg_small); cudaFree(c->scan_dev); cudaFree(c->dp_scratch); cudaFree(c->prof_dev); cudaFree(c->hin_ready);
+  cudaFree(c->murty_buf); cudaFree(c->murty_count); cudaFree(c->murty_idx); cudaFree(c->murty_ratio);
   if (c->hpin) { forget_pinned(c->hpin); cudaFreeHost(c->hpin); }
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
@@ -952,6 +979,53 @@ int rfsb200_set_poses(rfsb200_ctx* c, const double* pose, const double* pose_cov
 }
 
 // queue one update on the ctx stream (Z copy + kernels); no synchronisation
+// Murty compatibility, after the update kernel: fetch the partitions it wrote out, replace each exact sum by the sum of
+// the 200 best assignments (murty_compat.hpp), patch the weights of the particles concerned and add the weights up again.
+static int murty_postprocess(rfsb200_ctx* c, int out_idx) {
+  unsigned int cnt[2] = {0, 0};
+  CU(c, cudaMemcpyAsync(cnt, c->murty_count, 8, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  c->last_murty_terms = 0;
+  if (cnt[1] == 0) return RFSB200_OK;
+  const unsigned words = std::min(cnt[0], MURTY_WORDS);
+  std::vector<unsigned long long> rec(words);
+  CU(c, cudaMemcpy(rec.data(), c->murty_buf, (size_t)words * 8, cudaMemcpyDeviceToHost));
+  const double log_kappa = log(c->model.clutter_intensity);
+  std::map<int, double> log_ratio;   // particle -> sum over its large partitions of log(truncated / exact)
+  std::vector<double> pd, L;
+  size_t at = 0;
+  for (unsigned k = 0; k < cnt[1] && at + 3 <= words; k++) {
+    const int pi = (int)(rec[at] & 0xffffffffull), nR = (int)(rec[at] >> 32), nC = (int)rec[at + 1];
+    double plog;
+    memcpy(&plog, &rec[at + 2], 8);
+    const size_t need = 3 + (size_t)nR + (size_t)nR * nC;
+    if (nR <= 0 || nC <= 0 || at + need > words || pi < 0 || pi >= c->N) break;   // (a record cut off by the buffer's end)
+    pd.resize(nR);
+    L.resize((size_t)nR * nC);
+    memcpy(pd.data(), &rec[at + 3], (size_t)nR * 8);
+    memcpy(L.data(), &rec[at + 3 + nR], (size_t)nR * nC * 8);
+    int terms = 0;
+    const double s200 = murty::k_best_sum(L.data(), pd.data(), nR, nC, log_kappa, 200, &terms);
+    c->last_murty_terms += terms;
+    log_ratio[pi] += log(s200) - plog;
+    at += need;
+  }
+  std::vector<int> idx;
+  std::vector<double> ratio;
+  for (auto& kv : log_ratio) { idx.push_back(kv.first); ratio.push_back(exp(kv.second)); }
+  const int n = (int)idx.size();
+  if (n > 0) {
+    CU(c, cudaMemcpyAsync(c->murty_idx, idx.data(), (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(c->murty_ratio, ratio.data(), (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+    murty_patch_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(c->st[out_idx].weight, c->murty_idx, c->murty_ratio, n);
+    CU(c, cudaGetLastError());
+    weight_sums_kernel<<<1, 512, 0, c->stream>>>(c->st[out_idx].weight, c->N, c->sums);
+    CU(c, cudaGetLastError());
+    CU(c, cudaStreamSynchronize(c->stream));   // idx / ratio are pageable host vectors
+  }
+  return RFSB200_OK;
+}
+
 static int enqueue_update(rfsb200_ctx* c, const double* Z, int32_t nZ, uint32_t flags, bool timed, int* launches_out) {
   if (!c->have_model || !c->have_cfg || !c->have_maps || !c->have_poses)
     return fail(c, RFSB200_ESTATE, "update before set_model / set_filter_cfg / upload_maps / set_poses");
@@ -970,11 +1044,19 @@ static int enqueue_update(rfsb200_ctx* c, const double* Z, int32_t nZ, uint32_t 
   const int out_idx = c->front ^ 1;
   if ((flags & RFSB200_UPDATE_FUSED_ALLREDUCE) && c->comm_world > 1 && !c->comm_peer[0])
     return fail(c, RFSB200_ESTATE, "RFSB200_UPDATE_FUSED_ALLREDUCE before rfsb200_comm_connect");
+  if ((flags & RFSB200_UPDATE_FUSED_ALLREDUCE) && c->comm_world > 1 && murty_active(c))
+    return fail(c, RFSB200_EUNSUPPORTED, "murty_compat needs the weights on the host before they are summed: use "
+                                         "RFSB200_UPDATE_NO_NORMALIZE + all-reduce + rfsb200_normalize across ranks");
   int rc = (c->prec == 32) ? launch_update<float>(c, nZ, out_idx, flags) : launch_update<double>(c, nZ, out_idx, flags);
   if (rc) return rc;
   launches++;
   c->last_out = out_idx;
   c->last_nZ = nZ;
+  if (murty_active(c)) {
+    rc = murty_postprocess(c, out_idx);
+    if (rc) return rc;
+    flags &= ~RFSB200_UPDATE_FUSED_ALLREDUCE;   // (one rank: the normalisation below replaces the fused one)
+  }
   if (!(flags & (RFSB200_UPDATE_NO_NORMALIZE | RFSB200_UPDATE_FUSED_ALLREDUCE))) {
     normalize_kernel<<<(c->N + 255) / 256, 256, 0, c->stream>>>(c->st[out_idx].weight, c->sums, c->N, c->w_host);
     CU(c, cudaGetLastError());
@@ -1040,7 +1122,7 @@ int rfsb200_update_host(rfsb200_ctx* c, const double* pose, const double* pose_c
                         int32_t* nfov_out, rfsb200_step_out* out) {
   if (!c || !pose) return fail(c, RFSB200_EINVAL, "NULL argument");
   if (out) memset(out, 0, sizeof(*out));
-  if (c->zero_copy && nZ > 0 && nZ <= c->dims.z_capacity && Z && mode >= 0 && mode <= 2 && (mode == 0 || pose_cov)) {
+  if (c->zero_copy && !murty_active(c) && nZ > 0 && nZ <= c->dims.z_capacity && Z && mode >= 0 && mode <= 2 && (mode == 0 || pose_cov)) {
     // Pinned (device-accessible) caller buffers: ONE small kernel reads poses / weights / covariance / Z from host
     // memory, and the update kernel (or normalize_kernel) stores weights, unused masks, in-FOV counts and the step
     // scalars straight into the caller's buffers: no copies on either side of the update, one synchronisation.

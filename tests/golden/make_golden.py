@@ -27,6 +27,9 @@ CASES = {
     "mf_extras": dict(N=16, nM=60, nZ=12, use_cluster_process=0, config_id=104, parity_extras=True),
     "mf_sparse_ragged": dict(N=12, nM=80, nZ=14, use_cluster_process=0, config_id=105, world="sparse", ragged=0.3),
     "mf_lowpd": dict(N=12, nM=60, nZ=12, use_cluster_process=0, config_id=106, model=dict(Pd=0.5, clutter_intensity=1e-2)),
+    # partitions with nR + nC > 8: the reference's Murty-200 branch (include/RBPHDFilter.hpp:904-959, quirk Q7)
+    "mf_murty": dict(N=16, nM=48, nZ=24, use_cluster_process=0, config_id=23, world="clumped",
+                     model=dict(Pd=0.7, clutter_intensity=5e-3), cfg=dict(eval_point_gaussian_weight=0.1)),
 }
 
 
@@ -41,7 +44,10 @@ VP_CASES = {
 def main():
     assert ob.have_ref(), "oracle/_ref/libphd_ref.so missing: run `make -C oracle ref` in the build container"
     lib = C.CDLL(ob.REF_LIB)
+    only = set(sys.argv[1:])   # optional: regenerate just these cases
     for name, kw in list(CASES.items()) + list(VP_CASES.items()):
+        if only and name not in only:
+            continue
         wl = synth.make_vp_workload(**kw) if name in VP_CASES else synth.make_workload(**kw)
         out = dict(kw_repr=repr(kw), count_in=wl.count, mean_in=wl.mean, cov_in=wl.cov, w_in=wl.w, pose=wl.pose,
                    pose_cov=(np.zeros(0) if wl.pose_cov is None else wl.pose_cov), weight_in=wl.weight, Z=wl.Z,
@@ -73,6 +79,8 @@ def main():
     lib.phd_ref_partition.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.phd_ref_murty_sum.restype = C.c_double
     lib.phd_ref_murty_sum.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    if only:
+        return
     kat = {}
     # MeasurementModel_VictoriaPark::probabilityOfDetection on individual landmarks (the scan geometry)
     wl = synth.make_vp_workload(N=4, nM=160, nZ=10, config_id=154, parity_extras=True)

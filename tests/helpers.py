@@ -74,7 +74,7 @@ import json
 import os
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-GOLDEN_CASES = ["sc_dense", "sc_extras", "mf_dense", "mf_extras", "mf_sparse_ragged", "mf_lowpd"]
+GOLDEN_CASES = ["sc_dense", "sc_extras", "mf_dense", "mf_extras", "mf_sparse_ragged", "mf_lowpd", "mf_murty"]
 GOLDEN_CASES_VP = ["vp_sc", "vp_mf", "vp_mf_ragged"]   # Victoria Park plugin set (3-D landmarks)
 
 
@@ -86,6 +86,9 @@ def load_golden(name):
                         pose=g["pose"], pose_cov=(g["pose_cov"] if g["pose_cov"].size else None),
                         weight=g["weight_in"], Z=g["Z"],
                         model=json.loads(str(g["model_json"])), cfg=json.loads(str(g["cfg_json"])))
+    if name == "mf_murty":   # the reference's Murty-200 sums (quirk Q7) are reproduced behind this switch
+        wl.cfg["murty_compat"] = 1
+        wl.device_caps = dict(gm_capacity=128, work_capacity=256)   # the clumped world creates up to 168 Gaussians per particle
     return wl, g
 
 
@@ -209,6 +212,9 @@ def run_device(wl, precision=32, flags=None, gm_capacity=None, work_capacity=0, 
     """One update through the C ABI; returns (step_out, count, mean, cov, w, particle_weights, updater)."""
     from rfs_slam_b200 import capi
     from rfs_slam_b200.phd import PHDUpdater
+    caps = getattr(wl, "device_caps", {})
+    gm_capacity = gm_capacity or caps.get("gm_capacity")
+    work_capacity = work_capacity or caps.get("work_capacity", 0)
     cap = gm_capacity or int(max(64, (int(wl.count.max()) + 63) // 8 * 8))
     up = PHDUpdater(wl.N, gm_capacity=cap, work_capacity=work_capacity, precision=precision,
                     z_capacity=z_capacity or max(8, wl.nZ), lmk_dim=wl.dim)

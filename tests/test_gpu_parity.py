@@ -231,9 +231,10 @@ def test_device_permanent_known_answers(cuda_required):
 
 def test_large_partitions_are_flagged_and_summed_exactly(cuda_required):
     """Partitions with nR + nC > 8: the reference sums Murty's 200 best assignments (Q7, a truncated
-    sum); the device computes the exact sum and flags the particle (bit 2).  The flagged set must be
+    sum).  Default: the device computes the exact sum and flags the particle (bit 2) — the flagged set must be
     the oracle's Murty set, the exact weight can only be >= the truncated one (same maps), and
-    unflagged particles agree to tolerance."""
+    unflagged particles agree to tolerance.  With rfsb200_filter_cfg::murty_compat the truncated sum is reproduced:
+    every particle weight equals the reference's to 1e-9 (fp64 build)."""
     from oracle import binding as ob
     from rfs_slam_b200 import synth
     wl = synth.make_workload(N=64, nM=48, nZ=24, use_cluster_process=0, config_id=23, world="clumped",
@@ -251,6 +252,23 @@ def test_large_partitions_are_flagged_and_summed_exactly(cuda_required):
     assert (pw[murty] >= o.weight[murty] * (1 - 1e-9)).all()
     ratio = pw[murty] / o.weight[murty]                      # how much mass the 200 best miss
     assert np.isfinite(ratio).all() and ratio.max() < 1e3
+    up.close()
+    # murty_compat: the host replaces the exact sums of those partitions by the sums of Murty's 200 best assignments
+    # (own k-best enumeration in the library, csrc/murty_compat.hpp): now EVERY particle weight is the reference's
+    import copy
+    wq = copy.copy(wl)
+    wq.cfg = dict(wl.cfg, murty_compat=1)
+    so, cnt, mean, cov, w, pw, up = helpers.run_device(wq, precision=64, gm_capacity=128, work_capacity=256, z_capacity=24)
+    assert np.array_equal((up.get_flags() & 2) > 0, murty) and so.n_murty == int(murty.sum())
+    assert np.allclose(pw, o.weight, rtol=1e-9, atol=0)
+    assert so.sum_w == pytest.approx(float(pw.sum()), rel=1e-12)
+    assert not helpers.compare_maps(cnt, mean, cov, w, o.count, o.mean, o.cov, o.w, TOL64)["bad"]
+    up.normalize()
+    assert up.get_weights().sum() == pytest.approx(1.0, abs=1e-12)
+    up.close()
+    so, cnt, mean, cov, w, pw32, up = helpers.run_device(wq, precision=32, gm_capacity=128, work_capacity=256, z_capacity=24)
+    rw = helpers.compare_weights(pw32, o.weight, TOL32)
+    assert rw["n_bad"] <= 1, rw
     up.close()
 
 
