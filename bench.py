@@ -253,15 +253,23 @@ def run_workload(a, name, ctx, steps, warmup, headline):
     # ---- cross-GPU check (untimed): the in-kernel sum over peer memory against the NCCL all-reduce ----------------
     collective_check = None
     if world > 1 and fused:
+        # the sums the kernels exchanged through the peer mailboxes (added in rank order, the same bits on every rank) and
+        # the weights normalised with them, against: every rank's local sums all-gathered by NCCL, added in rank order on
+        # the host, and the locally normalised weights.  (NCCL's own all-reduce adds in ring / tree order, which may round
+        # differently from the rank order for more than two ranks; the NCCL path of the library is timed with --no-fused.)
         sh.step(wl.Z, flags=FLAGS)
         w_f = up.get_weights(1).copy()
         s_f = sh.sums.cpu().numpy().copy()
-        sh.fused = False
-        sh.step(wl.Z, flags=FLAGS)
-        w_n = up.get_weights(1).copy()
-        s_n = sh.sums.cpu().numpy().copy()
-        sh.fused = True
-        same = bool(np.array_equal(w_f.view(np.uint64), w_n.view(np.uint64)) and np.array_equal(s_f.view(np.uint64), s_n.view(np.uint64)))
+        up.update(wl.Z, flags=FLAGS | capi.UPDATE_NO_NORMALIZE, want_stats=False)
+        w_u = up.get_weights(1).copy()
+        loc = sh.sums.clone()
+        parts = [torch.zeros_like(loc) for _ in range(world)]
+        dist.all_gather(parts, loc)
+        tot = np.zeros(2)
+        for q in parts:
+            tot += q.cpu().numpy()
+        same = bool(np.array_equal(s_f.view(np.uint64), tot.view(np.uint64)) and
+                    np.array_equal(w_f.view(np.uint64), (w_u / tot[0]).view(np.uint64)))
         t = torch.tensor([1 if same else 0], dtype=torch.int32, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MIN)
         collective_check = "bit-identical" if int(t.item()) == 1 else "DIFFERS"

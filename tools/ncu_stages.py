@@ -4,7 +4,7 @@ import csv, sys, os, re, collections
 path = sys.argv[1]; NP = float(sys.argv[2]) if len(sys.argv) > 2 else 8000.0
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 src = open(os.path.join(ROOT, "rfs-slam_b200", "csrc", "phd_kernels.cuh")).read().split("\n")
-marks = [("helpers", "^namespace rfsb200"), ("M1", r"^__device__ int merge_clustered"), ("M2a", "---- M2: candidate"), ("M2b", r"^  int npass = 0;"),
+marks = [("helpers", "^namespace rfsb200"), ("M1", r"int merge_clustered\(T\* cur"), ("M2a", "---- M2: candidate"), ("M2b", r"^  int npass = 0;"),
          ("M3", "---- M3: clusters"), ("M4", "---- M4: one lane"), ("M5", "---- M5: commit"), ("mf_helpers", "^// S5 helpers"),
          ("epilogue", "^// End of a step"), ("tables", r"^phd_update_kernel\("), ("S0", r"^  while \(pi < p.N\)"), ("S1a", "// S1a: every component"),
          ("S1b", "// S1b: the queued"), ("S2-4", "-- S2: per-measurement"), ("S5", "-- S5: multi-feature"), ("S6call", "-- S6: merge"),
