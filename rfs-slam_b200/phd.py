@@ -61,6 +61,7 @@ class PHDUpdater:
             self.ctx = None
             raise RFSB200Error(f"rfsb200_create: {capi.ERRORS.get(rc, rc)}: {msg.decode() if msg else ''}")
         self._keep = []
+        self._keep_pose = []
 
     # ---- lifetime -------------------------------------------------------------------------
     def close(self):
@@ -130,7 +131,7 @@ class PHDUpdater:
             pc = np.ascontiguousarray(pose_cov, dtype=np.float64)
             mode = 1 if pc.ndim == 1 else 2
         wt = None if weight is None else np.ascontiguousarray(weight, dtype=np.float64)
-        self._keep += [pose, pc, wt]
+        self._keep_pose = [pose, pc, wt]   # the async copies read these until the next sync; replaced, not accumulated
         _check(self.lib, self.ctx,
                self.lib.rfsb200_set_poses(self.ctx, capi.ptr(pose), capi.ptr(pc), mode, capi.ptr(wt)),
                "set_poses")

@@ -81,6 +81,7 @@ inline void make_context(Context* c, void* stack, size_t bytes, void (*entry)())
 #define __host__
 #define __global__
 #define __forceinline__ inline
+#define __noinline__
 #define __launch_bounds__(...)
 #define __grid_constant__
 #define __align__(n) alignas(n)
