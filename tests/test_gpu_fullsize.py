@@ -54,3 +54,34 @@ def test_full_size_properties(cuda_required, name):
 
 
 CONFIG_NM = {"C2": 100, "C3": 200}
+
+
+def test_c4_every_shard_against_the_oracle(cuda_required):
+    """BASELINE config C4 = 64 000 particles as 8 shards of 8 000 (what `bench.py --gpus 8` gives the eight ranks): every
+    shard through the device, EVERY particle against the oracle — on one GPU, shard after shard, so that the comparison
+    is in the record of a single-GPU test run too.  At most 0.5 % of a shard may differ, each of them inside an epsilon
+    band; the shards' [sum w, sum w^2] added in rank order are what the fused exchange must produce."""
+    import bench
+    from oracle import binding as ob
+    total = np.zeros(2)
+    n_diff = 0
+    for rank in range(8):
+        wl, _ = bench.make_workload("C3", rank)
+        assert wl.N == 8000
+        so, cnt, mean, cov, w, pw, up = helpers.run_device(wl, precision=32, gm_capacity=256)
+        assert so.n_overflow == 0
+        o = ob.run(wl, sort_mode=ob.SORT_STABLE)
+        rules = {}
+        robust = helpers.robust_mask(wl, rules=rules)
+        r = helpers.compare_maps(cnt, mean, cov, w, o.count, o.mean, o.cov, o.w, helpers.TOL32)
+        rw = helpers.compare_weights(pw, o.weight, helpers.TOL32)
+        bad = set(r["bad"]) | set(int(i) for i in rw["idx_bad"])
+        helpers.parity_record("tests/test_gpu_fullsize.py::test_c4_every_shard_against_the_oracle[shard %d]" % rank, wl, robust, bad, rules)
+        assert not [i for i in bad if robust[i]], f"shard {rank}: robust particles differ"
+        assert len(bad) <= int(0.005 * wl.N), f"shard {rank}: {len(bad)} particles differ"
+        n_diff += len(bad)
+        assert so.sum_w == pytest.approx(float(pw.sum()), rel=1e-12)
+        total += np.array([so.sum_w, so.sum_w2])
+        up.close()
+    assert np.isfinite(total).all() and total[0] > 0
+    assert n_diff <= int(0.002 * 64000)
