@@ -37,3 +37,73 @@ def test_global_resampling_is_independent_of_the_number_of_ranks(cuda_required):
     rc, out = _torchrun("resample_check.py", 2, 29532)
     assert rc == 0, out
     assert out.count("identical to the single-process result") == 4, out
+
+
+@pytest.mark.parametrize("dim", [2, 3], ids=["rngbrg", "victoriapark"])
+def test_particle_exchange_between_two_contexts_on_one_gpu(cuda_required, dim):
+    """The cross-GPU resampling path with both "ranks" as contexts on ONE device (so that it runs, and is recorded, on a
+    single-GPU box): the reference's placement on the global particle order (dist.reference_resample_sources), the
+    exchange plan of each rank (dist.exchange_plan), packed particle records from rfsb200_export_particles into a device
+    buffer, the local gather (rfsb200_resample), rfsb200_import_particles — against one context that holds all particles
+    and resamples alone: maps, poses, unused-measurement masks and weights identical bit for bit."""
+    import numpy as np
+    import torch
+    from rfs_slam_b200 import capi, synth
+    from rfs_slam_b200.dist import block_range, exchange_plan, reference_resample_sources
+    from rfs_slam_b200.phd import PHDUpdater
+    mk = synth.make_vp_workload if dim == 3 else synth.make_workload
+    wl = mk(N=96, nM=50, nZ=10, use_cluster_process=1, config_id=91 + dim)
+    caps = dict(gm_capacity=128, z_capacity=16, lmk_dim=dim)
+
+    def fresh(sub):
+        up = PHDUpdater(sub.N, **caps)
+        up.load_workload(sub)
+        up.update(sub.Z, flags=capi.UPDATE_NO_NORMALIZE)   # maps, masks and weights of a real step
+        return up
+
+    one = fresh(wl)
+    w = one.get_weights()
+    w = w / w.sum()
+    src = reference_resample_sources(w, 0.37)
+    assert len(np.unique(src)) < wl.N, "the draw must duplicate some particles"
+    one.resample(src.astype(np.int32), weight=1.0)
+    ref = (one.download_maps(), one.get_poses(), one.get_unused(), one.get_weights())
+
+    world = 2
+    ranks = [fresh(wl.shard(r, world)) for r in range(world)]
+    plans = [exchange_plan(src, r, world) for r in range(world)]
+    rec = ranks[0].particle_record_bytes()
+    assert rec == ranks[1].particle_record_bytes() and rec > 0
+    bufs = {}
+    for r in range(world):            # every rank packs what the others need, from its state BEFORE the local copies
+        local_src, send, recv = plans[r]
+        for dst in range(world):
+            if len(send[dst]):
+                b = torch.empty(len(send[dst]) * rec, dtype=torch.uint8, device="cuda")
+                ranks[r].export_particles(send[dst], b.data_ptr())
+                ranks[r].synchronize()
+                bufs[(r, dst)] = b
+    n_moved = 0
+    for r in range(world):
+        local_src, send, recv = plans[r]
+        ranks[r].resample(local_src, weight=1.0)
+        for s in range(world):
+            if len(recv[s]):
+                assert len(recv[s]) * rec == bufs[(s, r)].numel()
+                ranks[r].import_particles(recv[s], bufs[(s, r)].data_ptr(), 1.0)
+                n_moved += len(recv[s])
+        ranks[r].synchronize()
+    assert n_moved > 0, "no particle changed rank: the exchange was not exercised"
+    got_cnt, got_mean, got_cov, got_w = [], [], [], []
+    for r in range(world):
+        c, m, cv, ww = ranks[r].download_maps()
+        got_cnt.append(c); got_mean.append(m); got_cov.append(cv); got_w.append(ww)
+    (rc, rm, rcv, rw), rpose, (rmask, rnfov), rweights = ref
+    assert np.array_equal(np.concatenate(got_cnt), rc)
+    assert np.array_equal(np.concatenate(got_mean), rm) and np.array_equal(np.concatenate(got_cov), rcv)
+    assert np.array_equal(np.concatenate(got_w), rw)
+    assert np.array_equal(np.concatenate([ranks[r].get_poses() for r in range(world)]), rpose)
+    assert np.array_equal(np.concatenate([ranks[r].get_unused()[0] for r in range(world)]), rmask)
+    assert np.array_equal(np.concatenate([ranks[r].get_weights() for r in range(world)]), rweights)
+    for u in ranks + [one]:
+        u.close()
