@@ -1,7 +1,8 @@
 // phd_kernels.cuh — the fused per-particle PHD measurement update for sm_100a.
 //
-// One launch processes every particle of the shard: ONE WARP PER PARTICLE, persistent CTAs (one CTA of up to 16
-// warps per SM, chosen at configure time), particles handed out by a global atomic queue.
+// One launch processes every particle of the shard: ONE WARP PER PARTICLE, persistent CTAs (one CTA per SM of up to 20
+// warps — the fp32 single-cluster kernel — chosen at configure time); a warp's first particle is static, the rest are
+// handed out by a global atomic queue, drawn one particle ahead with the next particle's planes prefetched into L2.
 // Per particle (reference include/RBPHDFilter.hpp):
 //   S0  TMA bulk loads (cp.async.bulk + mbarrier) of the particle's 6 SoA planes HBM -> smem
 //   S1  GM-PHD corrector, updateMap :597-641 — EKF innovation / likelihood between every Gaussian
@@ -15,13 +16,12 @@
 //   S8  deterministic [sum w, sum w^2] reduction by the last CTA (ParticleFilter.hpp:352-363,406-411)
 //
 // No tensor cores: the 2x2 / 2x3 EKF blocks are register math; the kernel is instruction-issue / latency bound
-// (8.1 k warp instructions per particle against 5.8 kB of HBM traffic).
+// (7.6 k warp instructions per particle against 5.8 kB of HBM traffic).
 #pragma once
 #include "common.cuh"
 
 namespace rfsb200 {
 
-constexpr int WARPS_PER_CTA = 4;       // default; the 2-D multi-feature kernel runs 5 (see mf_region_bytes)
 constexpr int MAX_WARPS_PER_CTA = 20;
 constexpr int MAX_Z = 64;
 constexpr int MAX_EVAL = 32;
@@ -2627,20 +2627,20 @@ __global__ void normalize_kernel(double* w, const double* sums, int N, double* w
   }
 }
 
-// Inputs of a host-facing step read straight from the caller's pinned host memory (zero-copy loads over PCIe) and
-// converted to the device layout: poses (fp64 copy kept for export / propagate), pose covariance, particle weights and
-// the measurement batch (passed by value) — one launch instead of four copies and a conversion kernel.
+// Inputs of a host-facing step of the Victoria Park kernels, read straight from the caller's pinned host memory
+// (zero-copy loads over PCIe) and converted to the device layout: poses (fp64 copy kept for export / propagate), pose
+// covariance, particle weights.  (The 2-D update kernels do this themselves, host_in_convert; the measurement batch
+// travels by value in the update kernel's parameters either way.)
 struct HostInParams {
   const double* pose;     // host [N][3]
   const double* weight;   // host [N] or NULL
   const double* pcov;     // host [N][6] (mode 2) or NULL
-  int mode, N, nz_vals;
+  int mode, N;
   double cov6[6];         // mode 1
-  double Z[MAX_Z * 3];
 };
 template <typename T>
 __global__ void host_in_kernel(const HostInParams h, double* __restrict__ pose64, T* __restrict__ pose, T* __restrict__ pcov,
-                               double* __restrict__ w_dev, T* __restrict__ Zdev) {
+                               double* __restrict__ w_dev) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < h.N) {
     const double x = h.pose[3 * i], y = h.pose[3 * i + 1], th = h.pose[3 * i + 2];
@@ -2656,7 +2656,6 @@ __global__ void host_in_kernel(const HostInParams h, double* __restrict__ pose64
     for (int k = 0; k < 6; k++) pcov[k] = (T)h.cov6[k];
     pcov[6] = pcov[7] = T(0);
   }
-  if (i < h.nz_vals) Zdev[i] = (T)h.Z[i];
 }
 
 }  // namespace rfsb200

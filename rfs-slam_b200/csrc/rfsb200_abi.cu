@@ -47,8 +47,6 @@ struct rfsb200_ctx {
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  cudaEvent_t zev[8] = {};   // one per pinned Z staging slot: the H2D copy that last read it
-  unsigned zslot = 0;
   StateBuf st[2];
   int front = 0;     // committed state
   int last_out = 0;  // buffer written by the last update (== front unless NO_COMMIT)
@@ -743,7 +741,6 @@ int rfsb200_create(rfsb200_ctx** out, const rfsb200_dims* d) {
     c->stream = c->own_stream;
     CU(c, cudaEventCreate(&c->ev0));
     CU(c, cudaEventCreate(&c->ev1));
-    for (int k = 0; k < 8; k++) CU(c, cudaEventCreateWithFlags(&c->zev[k], cudaEventDisableTiming));
     const size_t gm_bytes = (size_t)c->N * c->npl * c->cap * c->tsize;
     for (int k = 0; k < 2; k++) {
       CU(c, cudaMalloc(&c->st[k].gm, gm_bytes));
@@ -840,7 +837,6 @@ int rfsb200_destroy(rfsb200_ctx* c) {
   if (c->hpin) { forget_pinned(c->hpin); cudaFreeHost(c->hpin); }
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
-  for (int k = 0; k < 8; k++) if (c->zev[k]) cudaEventDestroy(c->zev[k]);
   for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
@@ -1147,11 +1143,11 @@ int rfsb200_update_host(rfsb200_ctx* c, const double* pose, const double* pose_c
         if (mode == 1) for (int k = 0; k < 6; k++) c->hin_cov6[k] = pose_cov[k];
       } else {
         HostInParams h{};
-        h.pose = d_pose; h.weight = d_w; h.pcov = d_cov; h.mode = mode; h.N = c->N; h.nz_vals = 0;
+        h.pose = d_pose; h.weight = d_w; h.pcov = d_cov; h.mode = mode; h.N = c->N;
         if (mode == 1) for (int k = 0; k < 6; k++) h.cov6[k] = pose_cov[k];
         double* w_dev = c->st[c->front].weight;
-        if (c->prec == 32) host_in_kernel<float><<<(c->N + 255) / 256, 256, 0, c->stream>>>(h, c->stg_small, (float*)c->pose, (float*)c->pose_cov, w_dev, (float*)c->Zdev);
-        else host_in_kernel<double><<<(c->N + 255) / 256, 256, 0, c->stream>>>(h, c->stg_small, (double*)c->pose, (double*)c->pose_cov, w_dev, (double*)c->Zdev);
+        if (c->prec == 32) host_in_kernel<float><<<(c->N + 255) / 256, 256, 0, c->stream>>>(h, c->stg_small, (float*)c->pose, (float*)c->pose_cov, w_dev);
+        else host_in_kernel<double><<<(c->N + 255) / 256, 256, 0, c->stream>>>(h, c->stg_small, (double*)c->pose, (double*)c->pose_cov, w_dev);
         CU(c, cudaGetLastError());
       }
       c->pose_cov_mode = mode;
