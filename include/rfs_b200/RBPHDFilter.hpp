@@ -165,23 +165,28 @@ struct ModelTraits<MeasurementModel_RngBrg, KalmanFilter_RngBrg> {
  * arguments of an explicit instantiation, [temp.spec]). */
 namespace b200 {
 namespace detail {
-template <class Tag>
-struct MemberPtr {
-  static typename Tag::type ptr;
-};
-template <class Tag>
-typename Tag::type MemberPtr<Tag>::ptr;
+/* Read access to private members of reference classes that have no getter (the class is reused unmodified): the address
+ * of a private member may be named in an explicit instantiation (access checking does not apply to its arguments), and
+ * the instantiation defines a friend function that hands the member pointer out.  The pointer is a constant expression:
+ * nothing is initialised at run time, so there is no static-initialisation order to get wrong.  The tags live in an
+ * unnamed namespace, i.e. every translation unit that includes this header instantiates ITS OWN specialisations and no
+ * explicit instantiation definition appears twice in a program. */
+namespace {
 template <class Tag, typename Tag::type P>
-struct MemberPtrInit {
-  MemberPtrInit() { MemberPtr<Tag>::ptr = P; }
-  static MemberPtrInit instance;
+struct MemberAccess {
+  friend typename Tag::type member_ptr(Tag) { return P; }
 };
-template <class Tag, typename Tag::type P>
-MemberPtrInit<Tag, P> MemberPtrInit<Tag, P>::instance;
-struct VPScanTag { typedef std::vector<double> MeasurementModel_VictoriaPark::*type; };
-struct VPSlbTag { typedef double MeasurementModel_VictoriaPark::*type; };
-template struct MemberPtrInit<VPScanTag, &MeasurementModel_VictoriaPark::laserscan_>;
-template struct MemberPtrInit<VPSlbTag, &MeasurementModel_VictoriaPark::Slb_>;
+struct VPScanTag {
+  typedef std::vector<double> MeasurementModel_VictoriaPark::*type;
+  friend type member_ptr(VPScanTag);
+};
+struct VPSlbTag {
+  typedef double MeasurementModel_VictoriaPark::*type;
+  friend type member_ptr(VPSlbTag);
+};
+template struct MemberAccess<VPScanTag, &MeasurementModel_VictoriaPark::laserscan_>;
+template struct MemberAccess<VPSlbTag, &MeasurementModel_VictoriaPark::Slb_>;
+}  // namespace
 }  // namespace detail
 
 template <>
@@ -196,7 +201,7 @@ struct ModelTraits<MeasurementModel_VictoriaPark, KalmanFilter_VictoriaPark> {
     mm.getNoise(R);
     for (int i = 0; i < 3; i++)
       for (int j = 0; j < 3; j++) d.R[i * 3 + j] = R(i, j);
-    d.Slb = mm.*detail::MemberPtr<detail::VPSlbTag>::ptr;
+    d.Slb = mm.*member_ptr(detail::VPSlbTag());
     const std::vector<double>& tab = mm.config.probabilityOfDetection_;
     if (tab.empty() || tab.size() > 16)
       throw std::runtime_error("rfs::RBPHDFilter (B200): config.probabilityOfDetection_ must hold 1..16 entries");
@@ -210,7 +215,7 @@ struct ModelTraits<MeasurementModel_VictoriaPark, KalmanFilter_VictoriaPark> {
     d.bearing_min = mm.config.bearingLimitMin_;
     d.bearing_max = mm.config.bearingLimitMax_;
     d.buffer_zone_pd = mm.config.bufferZonePd_;
-    const std::vector<double>& scan = mm.*detail::MemberPtr<detail::VPScanTag>::ptr;
+    const std::vector<double>& scan = mm.*member_ptr(detail::VPScanTag());
     d.scan = scan.empty() ? NULL : &scan[0];
     d.scan_n = (int32_t)(scan.size() > 720 ? 720 : scan.size());
     d.innov_thr_range = kf.config.rangeInnovationThreshold_;
@@ -246,14 +251,16 @@ struct MotionTraits<MotionModel_Odometry2d> {
   }
 };
 namespace detail {
-struct AckHTag { typedef double MotionModel_Ackerman2d::*type; };
-struct AckLTag { typedef double MotionModel_Ackerman2d::*type; };
-struct AckXTag { typedef double MotionModel_Ackerman2d::*type; };
-struct AckYTag { typedef double MotionModel_Ackerman2d::*type; };
-template struct MemberPtrInit<AckHTag, &MotionModel_Ackerman2d::h_>;
-template struct MemberPtrInit<AckLTag, &MotionModel_Ackerman2d::l_>;
-template struct MemberPtrInit<AckXTag, &MotionModel_Ackerman2d::poi_offset_x_>;
-template struct MemberPtrInit<AckYTag, &MotionModel_Ackerman2d::poi_offset_y_>;
+namespace {
+struct AckHTag { typedef double MotionModel_Ackerman2d::*type; friend type member_ptr(AckHTag); };
+struct AckLTag { typedef double MotionModel_Ackerman2d::*type; friend type member_ptr(AckLTag); };
+struct AckXTag { typedef double MotionModel_Ackerman2d::*type; friend type member_ptr(AckXTag); };
+struct AckYTag { typedef double MotionModel_Ackerman2d::*type; friend type member_ptr(AckYTag); };
+template struct MemberAccess<AckHTag, &MotionModel_Ackerman2d::h_>;
+template struct MemberAccess<AckLTag, &MotionModel_Ackerman2d::l_>;
+template struct MemberAccess<AckXTag, &MotionModel_Ackerman2d::poi_offset_x_>;
+template struct MemberAccess<AckYTag, &MotionModel_Ackerman2d::poi_offset_y_>;
+}  // namespace
 }  // namespace detail
 template <>
 struct MotionTraits<MotionModel_Ackerman2d> {
@@ -268,10 +275,10 @@ struct MotionTraits<MotionModel_Ackerman2d> {
     for (int i = 0; i < 2; i++)
       for (int j = 0; j < 2; j++) d.input_cov[i * 2 + j] = uS(i, j);
     d.dt = dT.getTimeAsDouble();
-    d.ackerman_h = pm.*detail::MemberPtr<detail::AckHTag>::ptr;
-    d.ackerman_l = pm.*detail::MemberPtr<detail::AckLTag>::ptr;
-    d.ackerman_dx = pm.*detail::MemberPtr<detail::AckXTag>::ptr;
-    d.ackerman_dy = pm.*detail::MemberPtr<detail::AckYTag>::ptr;
+    d.ackerman_h = pm.*member_ptr(detail::AckHTag());
+    d.ackerman_l = pm.*member_ptr(detail::AckLTag());
+    d.ackerman_dx = pm.*member_ptr(detail::AckXTag());
+    d.ackerman_dy = pm.*member_ptr(detail::AckYTag());
   }
 };
 }  // namespace b200
