@@ -376,7 +376,7 @@ int choose_launch_shape(rfsb200_ctx* c, K kernel, size_t cta_bytes, size_t warp_
   out->smem = cta_bytes + (size_t)best_nw * warp_bytes;
   CU(c, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)out->smem));
   const int need = (c->N + best_nw - 1) / best_nw;
-  out->grid = std::max(1, std::min(need, best_occ * c->sm_count));
+  out->grid = std::max(1, std::min(std::min(need, best_occ * c->sm_count), 8192));   // (8192: slice flags of the host-facing step)
   return RFSB200_OK;
 }
 template <typename K>
@@ -765,8 +765,8 @@ int rfsb200_create(rfsb200_ctx** out, const rfsb200_dims* d) {
     CU(c, cudaMalloc(&c->comm_mail, COMM_BANKS * 8 * sizeof(CommSlot)));
     CU(c, cudaMemset(c->comm_mail, 0xff, COMM_BANKS * 8 * sizeof(CommSlot)));   // epoch = ~0: never matches
     if (const char* e = getenv("RFSB200_COMM_TIMEOUT_MS")) c->comm_timeout_ns = (unsigned long long)std::max(1, atoi(e)) * 1000000ull;
-    CU(c, cudaMalloc((void**)&c->hin_ready, 4096 * 8));   // one flag per CTA of the update kernel (grid <= SMs x CTAs per SM)
-    CU(c, cudaMemset(c->hin_ready, 0, 4096 * 8));
+    CU(c, cudaMalloc((void**)&c->hin_ready, 8192 * 8));   // one flag per CTA of the update kernel (grid <= SMs x 32 CTAs per SM)
+    CU(c, cudaMemset(c->hin_ready, 0, 8192 * 8));
     CU(c, cudaMalloc((void**)&c->comm_error, 4));
     CU(c, cudaMemset(c->comm_error, 0, 4));
     CU(c, cudaMalloc((void**)&c->unused_alt, (size_t)c->N * 8));
