@@ -38,6 +38,7 @@
 #include <stdio.h>
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 #include <ctime>
 #include <fstream>
 #include <iomanip>
@@ -348,6 +349,9 @@ class RBPHDFilter : public ParticleFilter<RobotProcessModel, MeasurementModel,
                              the kernel (RFSB200_UPDATE_STAGE_TIMES, a few percent slower) and getTimingInfo() fills
                              mapUpdate_kf / particleWeighting / mapMerge / mapPrune as the reference's single-thread run
                              does (include/RBPHDFilter.hpp:1219-1232); 0: the whole step is booked under mapUpdate */
+    int hostBirthCandidates;  /**< != 0 (or RFSB200_HOST_BIRTHS=1 in the environment): the candidate lists of addBirthGaussians()
+                                   (birthGaussianMeasurementCountThreshold_ != 1) are kept on the host and evaluated with the
+                                   live plugin objects (verification); 0: rfsb200_birth_candidates keeps them on the device */
   } deviceConfig;
 
   RBPHDFilter(int n);
@@ -391,6 +395,7 @@ class RBPHDFilter : public ParticleFilter<RobotProcessModel, MeasurementModel,
   bool overflowWarned_;
   int nUpdateCalls_;                 /* update() calls with a non-empty measurement set (diagnostics) */
   void addBirthGaussiansHost();
+  void addBirthGaussiansDevice();
   /* optional device-side ParticleFilter::propagate (RFSB200_DEVICE_PROPAGATE=1; RFSB200_SEED selects the stream) */
   bool devicePropagate_;
   unsigned long long propagateSeed_, propagateCount_;
@@ -455,6 +460,7 @@ RBPHDFilter<R, L, M, K>::RBPHDFilter(int n)
   deviceConfig.device = 0;
   deviceConfig.precision = 32;
   deviceConfig.stageTiming = 0;
+  deviceConfig.hostBirthCandidates = getenv("RFSB200_HOST_BIRTHS") != NULL ? atoi(getenv("RFSB200_HOST_BIRTHS")) : 0;
   /* unchanged drivers cannot reach deviceConfig: the environment can (verification runs) */
   if (const char* e = getenv("RFSB200_PRECISION")) deviceConfig.precision = atoi(e);
   if (const char* e = getenv("RFSB200_DEVICE")) deviceConfig.device = atoi(e);
@@ -529,8 +535,12 @@ void RBPHDFilter<R, L, M, K>::predict(TInput u, TimeStamp const& dT, bool useMod
   timer_predict_.resume();
   ensureCtx();
   invalidateCache();
+  /* candidate-list form of addBirthGaussians (:1023-1080); "hostBirths" = the births are not rfsb200_predict_maps' */
   const bool hostBirths = birthGaussianCheck && config.birthGaussianMeasurementCountThreshold_ != 1;
-  if (hostBirths) addBirthGaussiansHost();
+  if (hostBirths) {
+    if (deviceConfig.hostBirthCandidates) addBirthGaussiansHost();
+    else addBirthGaussiansDevice();
+  }
   /* landmark process noise: StaticProcessModel::step adds Q only if it was set (ProcessModel.hpp:198) */
   typename TLandmark::Mat Q;
   const double nan = std::numeric_limits<double>::quiet_NaN();
@@ -896,6 +906,26 @@ void RBPHDFilter<R, L, M, K>::addBirthGaussiansHost() {
                                  aW.empty() ? NULL : &aW[0]),
         "rfsb200_append_gaussians");
   if (unusedFresh_) check(rfsb200_predict_maps(ctx_, NULL, -1, 0.0), "rfsb200_predict_maps(clear)");   /* masks consumed */
+  unusedFresh_ = false;
+}
+
+/* The same on the device (rfsb200_birth_candidates): the candidate lists, the unused-measurement masks,
+ * nLandmarksInFOV_ and the maps stay where the update left them; only the poses (which a driver may have
+ * overwritten through setParticlePose since the update) and, after a resampling, the parent slots go up. */
+template <class R, class L, class M, class K>
+void RBPHDFilter<R, L, M, K>::addBirthGaussiansDevice() {
+  const bool anyCov = gatherPoses();
+  check(rfsb200_set_poses(ctx_, &hPose_[0], anyCov ? &hPoseCov_[0] : NULL, anyCov ? 2 : 0, NULL), "rfsb200_set_poses");
+  rfsb200_birth_cfg b;
+  memset(&b, 0, sizeof(b));
+  b.birth_weight = config.birthGaussianWeight_;
+  b.support_dist = config.birthGaussianMeasurementSupportDist_;
+  b.count_threshold = config.birthGaussianMeasurementCountThreshold_;
+  b.check_threshold = config.birthGaussianMeasurementCheckThreshold_;
+  b.current_count_threshold = config.birthGaussianCurrentMeasurementCountThreshold_;
+  std::vector<int32_t> parent;
+  if (resampleOccured_) parent.assign(birthParent_.begin(), birthParent_.end());
+  check(rfsb200_birth_candidates(ctx_, &b, resampleOccured_ ? parent.data() : NULL), "rfsb200_birth_candidates");
   unusedFresh_ = false;
 }
 

@@ -253,6 +253,39 @@ int rfsb200_predict_maps(rfsb200_ctx* ctx, const double* Q_lmk /*[3] / [6] or NU
 int rfsb200_append_gaussians(rfsb200_ctx* ctx, const int32_t* count /*[N]*/, const double* mean,
                              const double* cov, const double* w);
 
+/* addBirthGaussians() in its candidate-list form ON THE DEVICE (include/RBPHDFilter.hpp:1000-1080; the setting of
+ * cfg/rbphdslam_VictoriaPark_artificialClutter.xml:71-77, birthGaussianMeasurementCountThreshold_ != 1) for the two
+ * built-in plugin sets.  The ctx keeps birthGaussians_[i] (up to RFSB200_BIRTH_CAND_CAP candidates per particle: mean,
+ * covariance, nSupportingMeasurements, nChecks).  One call = one addBirthGaussians(): per particle, the unused
+ * measurements of the last update (descending index) support the first candidate within support_dist (Mahalanobis
+ * distance of measure(pose, candidate), which then takes KalmanFilter::correct) or open a new candidate at
+ * inverseMeasure(pose, z) — a real Gaussian straight away if count_threshold == 1 or nLandmarksInFOV_[i] <=
+ * current_count_threshold; then every candidate is checked (nChecks++) and leaves the list with enough support or few
+ * landmarks in view (appended to the map with birth_weight) or when nChecks > check_threshold (dropped), including the
+ * second pass the reference makes when the last list element is erased.  The masks are cleared.
+ * parent: NULL, or after a resampling (resampleOccured_) the parent slot of every particle (:1005-1011): a copy takes
+ *   the list its parent slot holds when the reference's ascending loop reaches it — the parent's list as it was for a
+ *   higher slot, the parent's list after its own turn for a lower one.  (The masks were routed by rfsb200_resample's
+ *   aux_src.)  rfsb200_export/import_particles do not carry candidate lists.
+ * Gaussians beyond gm_capacity set flag bits 1 and 8, a candidate beyond RFSB200_BIRTH_CAND_CAP is dropped with flag
+ * bit 32.  Arithmetic is fp64 whatever the ctx precision; the appended Gaussians are rounded to the map's type. */
+#define RFSB200_BIRTH_CAND_CAP 64
+typedef struct rfsb200_birth_cfg {
+  double   birth_weight;             /* birthGaussianWeight_                              */
+  double   support_dist;             /* birthGaussianMeasurementSupportDist_              */
+  uint32_t count_threshold;          /* birthGaussianMeasurementCountThreshold_           */
+  uint32_t check_threshold;          /* birthGaussianMeasurementCheckThreshold_           */
+  uint32_t current_count_threshold;  /* birthGaussianCurrentMeasurementCountThreshold_    */
+  uint32_t reserved;
+} rfsb200_birth_cfg;
+int rfsb200_birth_candidates(rfsb200_ctx* ctx, const rfsb200_birth_cfg* cfg, const int32_t* parent /*[N] or NULL*/);
+/* The candidate lists, [N][RFSB200_BIRTH_CAND_CAP] slots: mean [..][landmark_dim], cov [..][upper triangle],
+ * support / checks [..]; n[i] = length of the list of particle i.  Arrays other than n may be NULL in the getter. */
+int rfsb200_get_birth_candidates(rfsb200_ctx* ctx, int32_t* n /*[N]*/, double* mean, double* cov, int32_t* support,
+                                 int32_t* checks);
+int rfsb200_set_birth_candidates(rfsb200_ctx* ctx, const int32_t* n /*[N]*/, const double* mean, const double* cov,
+                                 const int32_t* support, const int32_t* checks);
+
 /* ---- particle propagation ------------------------------------------------
  * ParticleFilter::propagate() (include/ParticleFilter.hpp:322-341) = ProcessModel::sample() for every particle
  * (include/ProcessModel.hpp:125-150) on the device, in place on the poses of the ctx (fp64 copy kept next to the

@@ -191,6 +191,82 @@ def vp_pd(model: dict, pose, lx, lcov6, which: str = "oracle"):
     return float(pd), bool(close.value)
 
 
+class PhdBirthIO(C.Structure):
+    _fields_ = [
+        ("model", C.c_void_p), ("N", C.c_int32), ("nZ", C.c_int32), ("cand_cap", C.c_int32), ("add_cap", C.c_int32),
+        ("resample_occurred", C.c_int32), ("count_thr", C.c_uint32), ("check_thr", C.c_uint32),
+        ("cur_count_thr", C.c_uint32), ("support_dist", C.c_double),
+        ("pose", C.c_void_p), ("pose_cov", C.c_void_p), ("Z", C.c_void_p), ("parent", C.c_void_p),
+        ("unused", C.c_void_p), ("nfov", C.c_void_p), ("cand_n", C.c_void_p), ("cand_mean", C.c_void_p),
+        ("cand_cov", C.c_void_p), ("cand_support", C.c_void_p), ("cand_checks", C.c_void_p),
+        ("add_n", C.c_void_p), ("add_mean", C.c_void_p), ("add_cov", C.c_void_p),
+    ]
+
+
+class BirthState:
+    """Candidate lists of all particles (birthGaussians_, include/RBPHDFilter.hpp:255): n [N], mean [N][cap][D],
+    cov [N][cap][NC] (upper triangle), support / checks [N][cap]."""
+
+    def __init__(self, N: int, D: int, cap: int = 32):
+        self.N, self.D, self.cap = N, D, cap
+        NC = D * (D + 1) // 2
+        self.n = np.zeros(N, np.int32)
+        self.mean = np.zeros((N, cap, D))
+        self.cov = np.zeros((N, cap, NC))
+        self.support = np.zeros((N, cap), np.int32)
+        self.checks = np.zeros((N, cap), np.int32)
+
+    def copy(self):
+        o = BirthState(self.N, self.D, self.cap)
+        o.n, o.mean, o.cov, o.support, o.checks = (self.n.copy(), self.mean.copy(), self.cov.copy(),
+                                                     self.support.copy(), self.checks.copy())
+        return o
+
+
+def birth_candidates(model: dict, bcfg: dict, state: BirthState, pose, Z, unused, nfov, *, parent=None, pose_cov=None,
+                     which: str = "oracle", add_cap: int = 96):
+    """addBirthGaussians() in its candidate-list form (include/RBPHDFilter.hpp:1000-1080) for all particles, in place
+    on `state`.  bcfg: count_thr / check_thr / cur_count_thr / support_dist.  parent != None <=> resampleOccured_.
+    Returns (add_n [N], add_mean [N][add_cap][D], add_cov [N][add_cap][NC]): the Gaussians that became real."""
+    capi = _capi()
+    lib, _ = _load(which)
+    D = state.D
+    NC = D * (D + 1) // 2
+    N = state.N
+    md = capi.model_desc(model)
+    pose = np.ascontiguousarray(pose, dtype=np.float64)
+    Z = np.ascontiguousarray(Z, dtype=np.float64).reshape(-1, D)
+    un = np.ascontiguousarray(unused, dtype=np.uint64).copy()
+    nf = np.ascontiguousarray(nfov, dtype=np.int32)
+    par = None if parent is None else np.ascontiguousarray(parent, dtype=np.int32)
+    pc = None if pose_cov is None else np.ascontiguousarray(pose_cov, dtype=np.float64)
+    add_n = np.zeros(N, np.int32)
+    add_mean = np.zeros((N, add_cap, D))
+    add_cov = np.zeros((N, add_cap, NC))
+    io = PhdBirthIO()
+    io.model = C.addressof(md)
+    io.N, io.nZ, io.cand_cap, io.add_cap = N, Z.shape[0], state.cap, add_cap
+    io.resample_occurred = 0 if par is None else 1
+    io.count_thr, io.check_thr, io.cur_count_thr = bcfg["count_thr"], bcfg["check_thr"], bcfg["cur_count_thr"]
+    io.support_dist = bcfg["support_dist"]
+    io.pose, io.Z, io.unused, io.nfov = pose.ctypes.data, Z.ctypes.data, un.ctypes.data, nf.ctypes.data
+    io.pose_cov = None if pc is None else pc.ctypes.data
+    io.parent = None if par is None else par.ctypes.data
+    io.cand_n, io.cand_mean, io.cand_cov = state.n.ctypes.data, state.mean.ctypes.data, state.cov.ctypes.data
+    io.cand_support, io.cand_checks = state.support.ctypes.data, state.checks.ctypes.data
+    io.add_n, io.add_mean, io.add_cov = add_n.ctypes.data, add_mean.ctypes.data, add_cov.ctypes.data
+    if which == "oracle":
+        fn = lib.phd_oracle_birth_candidates
+    else:
+        fn = lib.phd_ref_birth_candidates_vp if D == 3 else lib.phd_ref_birth_candidates
+    fn.restype = C.c_int
+    fn.argtypes = [C.POINTER(PhdBirthIO)]
+    rc = fn(C.byref(io))
+    if rc != 0:
+        raise RuntimeError(f"{which} birth_candidates failed rc={rc}")
+    return add_n, add_mean, add_cov
+
+
 def permanent(A: np.ndarray, which: str = "oracle") -> float:
     lib, _ = _load(which)
     A = np.ascontiguousarray(A, dtype=np.float64)

@@ -96,6 +96,37 @@ int phd_oracle_partition(const double* L, int nR, int nC, int* nRows, int* nCols
 double phd_oracle_murty_sum(const double* Lp, int nR, int nC, const double* rowPd,
                             const double* colClutter);
 
+/* addBirthGaussians() in its candidate-list form (include/RBPHDFilter.hpp:1000-1080), all particles.
+ * The model decides the dimensions: RngBrg ld = 2 / nc = 3 / md = 2, Victoria Park ld = 3 / nc = 6 / md = 3.
+ *   phd_oracle_birth_candidates (oracle/phd_oracle_births.cpp)   restatement
+ *   phd_ref_birth_candidates    (oracle/ref_harness*.cpp)        the reference's own addBirthGaussians() */
+typedef struct phd_birth_io {
+  const rfsb200_model_desc* model;
+  int32_t N, nZ;
+  int32_t cand_cap;            /* slots per particle in the cand_* arrays                                  */
+  int32_t add_cap;             /* slots per particle in the add_* arrays                                   */
+  int32_t resample_occurred;   /* resampleOccured_: lists are looked up through parent[] (:1005-1011)      */
+  uint32_t count_thr;          /* birthGaussianMeasurementCountThreshold_                                  */
+  uint32_t check_thr;          /* birthGaussianMeasurementCheckThreshold_                                  */
+  uint32_t cur_count_thr;      /* birthGaussianCurrentMeasurementCountThreshold_                           */
+  double support_dist;         /* birthGaussianMeasurementSupportDist_                                     */
+  const double* pose;          /* [N][3]                                                                   */
+  const double* pose_cov;      /* [N][6] upper triangle or NULL (RngBrg only)                              */
+  const double* Z;             /* [nZ][md]                                                                 */
+  const int32_t* parent;       /* [N] getParentId() of the particle in slot i                              */
+  uint64_t* unused;            /* [N] in: unused_measurements_ as bit masks; out: 0                        */
+  const int32_t* nfov;         /* [N] nLandmarksInFOV_                                                     */
+  int32_t* cand_n;             /* [N] in / out: length of birthGaussians_[i]                               */
+  double* cand_mean;           /* [N][cand_cap][ld] in / out                                               */
+  double* cand_cov;            /* [N][cand_cap][nc] in / out, upper triangle                               */
+  int32_t* cand_support;       /* [N][cand_cap] nSupportingMeasurements                                    */
+  int32_t* cand_checks;        /* [N][cand_cap] nChecks                                                    */
+  int32_t* add_n;              /* [N] out: Gaussians that became real, in the order of the addGaussian calls */
+  double* add_mean;            /* [N][add_cap][ld] out                                                     */
+  double* add_cov;             /* [N][add_cap][nc] out                                                     */
+} phd_birth_io;
+int phd_oracle_birth_candidates(phd_birth_io* io);
+
 #ifdef __cplusplus
 }
 #endif

@@ -279,3 +279,22 @@ extern "C" double phd_ref_murty_sum(const double* Lp, int nR, int nC, const doub
   delete[] Cp;
   return pl;
 }
+
+/* The reference's own addBirthGaussians() (include/RBPHDFilter.hpp:1000-1080), range-bearing plugin set. */
+#include "ref_births.hpp"
+extern "C" int phd_ref_birth_candidates(phd_birth_io* io) {
+  if (!io || !io->model || io->N <= 0 || io->model->model_id != RFSB200_MODEL_RNGBRG) return -1;
+  Filter* f = new Filter(io->N);
+  const rfsb200_model_desc& md = *io->model;
+  Eigen::Matrix2d R;
+  R << md.R[0], md.R[1], md.R[2], md.R[3];
+  MeasurementModel_RngBrg* mm = f->getMeasurementModel();
+  mm->setNoise(R);
+  mm->config.rangeLimMax_ = md.range_max;
+  mm->config.rangeLimMin_ = md.range_min;
+  f->getKalmanFilter()->config.rangeInnovationThreshold_ = md.innov_thr_range;
+  f->getKalmanFilter()->config.bearingInnovationThreshold_ = md.innov_thr_bearing;
+  const int rc = ref_birth_candidates_run<Filter, 2>(f, io, R);
+  delete f;
+  return rc;
+}

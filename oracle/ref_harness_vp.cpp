@@ -247,3 +247,19 @@ extern "C" void phd_ref_ackerman2d_step(const double* params, const double* pose
   mm.step(s_k, s_km, in, dT);
   for (int k = 0; k < 3; k++) out[k] = s_k.get(k);
 }
+
+/* The reference's own addBirthGaussians() (include/RBPHDFilter.hpp:1000-1080), Victoria Park plugin set. */
+#include "ref_births.hpp"
+extern "C" int phd_ref_birth_candidates_vp(phd_birth_io* io) {
+  if (!io || !io->model || io->N <= 0 || io->model->model_id != RFSB200_MODEL_VICTORIAPARK) return -1;
+  FilterVP* f = new FilterVP(io->N);
+  const rfsb200_model_desc& md = *io->model;
+  Eigen::Matrix3d R;
+  R << md.R[0], md.R[1], md.R[2], md.R[3], md.R[4], md.R[5], md.R[6], md.R[7], md.R[8];
+  f->getMeasurementModel()->setNoise(R, md.Slb);
+  f->getKalmanFilter()->config.rangeInnovationThreshold_ = md.innov_thr_range;
+  f->getKalmanFilter()->config.bearingInnovationThreshold_ = md.innov_thr_bearing;
+  const int rc = ref_birth_candidates_run<FilterVP, 3>(f, io, R);
+  delete f;
+  return rc;
+}

@@ -114,6 +114,15 @@ def filter_cfg(fc: dict) -> FilterCfg:
     return c
 
 
+BIRTH_CAND_CAP = 64
+
+
+class BirthCfg(C.Structure):
+    """rfsb200_birth_cfg"""
+    _fields_ = [("birth_weight", C.c_double), ("support_dist", C.c_double), ("count_threshold", C.c_uint32),
+                ("check_threshold", C.c_uint32), ("current_count_threshold", C.c_uint32), ("reserved", C.c_uint32)]
+
+
 class StageTimes(C.Structure):
     """rfsb200_stage_times"""
     _fields_ = [("kernel_us", C.c_double), ("setup_us", C.c_double), ("particles_us", C.c_double), ("epilogue_us", C.c_double),
@@ -140,6 +149,9 @@ _SIGS = {
     "rfsb200_update": (C.c_int, [_P, _P, C.c_int32, C.c_uint32, C.POINTER(StepOut)]),
     "rfsb200_update_host": (C.c_int, [_P, _P, _P, C.c_int, _P, _P, C.c_int32, C.c_uint32, _P, _P, _P, C.POINTER(StepOut)]),
     "rfsb200_predict_maps": (C.c_int, [_P, _P, C.c_int32, C.c_double]),
+    "rfsb200_birth_candidates": (C.c_int, [_P, C.POINTER(BirthCfg), _P]),
+    "rfsb200_get_birth_candidates": (C.c_int, [_P, _P, _P, _P, _P, _P]),
+    "rfsb200_set_birth_candidates": (C.c_int, [_P, _P, _P, _P, _P, _P]),
     "rfsb200_propagate": (C.c_int, [_P, C.POINTER(MotionDesc)]),
     "rfsb200_get_poses": (C.c_int, [_P, _P]),
     "rfsb200_resample": (C.c_int, [_P, _P, _P, _P]),

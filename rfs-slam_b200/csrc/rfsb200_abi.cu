@@ -19,6 +19,7 @@
 #include "murty_compat.hpp"
 #include "phd_kernels.cuh"
 #include "phd_vp_kernels.cuh"
+#include "birth_kernels.cuh"
 
 using namespace rfsb200;
 
@@ -113,6 +114,10 @@ struct rfsb200_ctx {
   unsigned long long* done_host = nullptr;   // device view of the pinned completion word for the next launch (or NULL)
   unsigned long long done_seq = 0;
   double Zval[MAX_Z * 3] = {};               // the measurement batch of the next launch, fp64
+  // candidate-list births (rfsb200_birth_candidates): per-particle lists, double-buffered; allocated on first use
+  double* cand[2] = {nullptr, nullptr};      // [N][BIRTH_CAND_CAP][cand_rec(ld)]
+  int* cand_n[2] = {nullptr, nullptr};       // [N]
+  int cand_front = 0;
   std::vector<cudaEvent_t> prof_ev;   // event pairs around the update kernel (rfsb200_profile_*)
   int prof_cap = 0, prof_n = 0;
   unsigned long long* prof_dev = nullptr;   // [16] stage-timing build (KParams::prof)
@@ -834,6 +839,7 @@ int rfsb200_destroy(rfsb200_ctx* c) {
   cudaFree(c->work_counter); cudaFree(c->stats_out); cudaFree(c->mstats);
   cudaFree(c->stg); cudaFree(c->offs); cudaFree(c->stg_small); cudaFree(c->scan_dev); cudaFree(c->dp_scratch); cudaFree(c->prof_dev); cudaFree(c->hin_ready);
   cudaFree(c->murty_buf); cudaFree(c->murty_count); cudaFree(c->murty_idx); cudaFree(c->murty_ratio);
+  for (int k = 0; k < 2; k++) { cudaFree(c->cand[k]); cudaFree(c->cand_n[k]); }
   if (c->hpin) { forget_pinned(c->hpin); cudaFreeHost(c->hpin); }
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
@@ -1234,6 +1240,112 @@ int rfsb200_predict_maps(rfsb200_ctx* c, const double* Q, int32_t add_births, do
   c->last_out = c->front;
   if (c->ld == 3) return c->prec == 32 ? do_predict_vp<float>(c, Q, add_births, birth_w) : do_predict_vp<double>(c, Q, add_births, birth_w);
   return c->prec == 32 ? do_predict<float>(c, Q, add_births, birth_w) : do_predict<double>(c, Q, add_births, birth_w);
+}
+
+static int ensure_candidates(rfsb200_ctx* c) {
+  if (c->cand[0]) return RFSB200_OK;
+  const size_t rec = (size_t)cand_rec(c->ld);
+  for (int k = 0; k < 2; k++) {
+    CU(c, cudaMalloc(&c->cand[k], (size_t)c->N * RFSB200_BIRTH_CAND_CAP * rec * 8));
+    CU(c, cudaMalloc(&c->cand_n[k], (size_t)c->N * 4));
+    CU(c, cudaMemsetAsync(c->cand_n[k], 0, (size_t)c->N * 4, c->stream));
+  }
+  c->cand_front = 0;
+  return RFSB200_OK;
+}
+
+int rfsb200_birth_candidates(rfsb200_ctx* c, const rfsb200_birth_cfg* b, const int32_t* parent) {
+  if (!c || !b) return fail(c, RFSB200_EINVAL, "NULL argument");
+  if (!c->have_maps) return fail(c, RFSB200_ESTATE, "birth_candidates before upload_maps");
+  if (c->last_nZ > 0 && !c->have_model) return fail(c, RFSB200_ESTATE, "birth_candidates before set_model");
+  if (!(b->support_dist >= 0.0)) return fail(c, RFSB200_EINVAL, "support_dist must be >= 0");
+  CU(c, cudaSetDevice(c->device));
+  if (int rc = ensure_candidates(c)) return rc;
+  if (c->last_nZ > 0 && !c->have_poses) return fail(c, RFSB200_ESTATE, "birth_candidates needs the poses of the last update");
+  if (parent) {
+    for (int i = 0; i < c->N; i++)
+      if (parent[i] < 0 || parent[i] >= c->N) return fail(c, RFSB200_EINVAL, "parent %d of particle %d out of range", parent[i], i);
+    CU(c, cudaMemcpyAsync(c->src_dev, parent, (size_t)c->N * 4, cudaMemcpyHostToDevice, c->stream));
+  }
+  BirthCandParams p{};
+  const StateBuf& st = c->st[c->front];
+  p.N = c->N; p.cap = c->cap; p.cand_cap = RFSB200_BIRTH_CAND_CAP; p.nZ = c->last_nZ;
+  p.pcov_mode = c->ld == 2 ? c->pose_cov_mode : 0;
+  p.parent = parent ? c->src_dev : nullptr;
+  p.pose64 = c->stg_small; p.pcov = c->pose_cov;
+  p.unused = c->unused; p.nfov = c->nfov;
+  p.cand_in = c->cand[c->cand_front]; p.cand_n_in = c->cand_n[c->cand_front];
+  p.cand_out = c->cand[c->cand_front ^ 1]; p.cand_n_out = c->cand_n[c->cand_front ^ 1];
+  p.gm = st.gm; p.cnt = st.cnt; p.flags = c->flags;
+  for (int k = 0; k < 9; k++) p.R[k] = c->model.R[k];
+  p.Slb = c->model.Slb; p.range_min = c->model.range_min; p.range_max = c->model.range_max;
+  p.thr_r = c->model.innov_thr_range; p.thr_b = c->model.innov_thr_bearing;
+  p.support_d2 = b->support_dist * b->support_dist; p.birth_w = b->birth_weight;
+  p.count_thr = b->count_threshold; p.check_thr = b->check_threshold; p.cur_thr = b->current_count_threshold;
+  const int md = c->ld;   // measurement dimension of both built-in plugin sets
+  for (int k = 0; k < c->last_nZ * md; k++) p.Z[k] = c->Zval[k];
+  const int blocks = (c->N + 127) / 128;
+  for (int pass = 0; pass < (parent ? 2 : 1); pass++) {
+    p.pass = pass;
+    if (c->ld == 3) {
+      if (c->prec == 32) birth_candidates_kernel<float, 3><<<blocks, 128, 0, c->stream>>>(p);
+      else birth_candidates_kernel<double, 3><<<blocks, 128, 0, c->stream>>>(p);
+    } else {
+      if (c->prec == 32) birth_candidates_kernel<float, 2><<<blocks, 128, 0, c->stream>>>(p);
+      else birth_candidates_kernel<double, 2><<<blocks, 128, 0, c->stream>>>(p);
+    }
+    CU(c, cudaGetLastError());
+  }
+  if (parent) CU(c, cudaStreamSynchronize(c->stream));   // parent[] is the caller's (pageable) buffer
+  c->cand_front ^= 1;
+  c->last_out = c->front;
+  return RFSB200_OK;
+}
+
+int rfsb200_get_birth_candidates(rfsb200_ctx* c, int32_t* n, double* mean, double* cov, int32_t* support, int32_t* checks) {
+  if (!c || !n) return fail(c, RFSB200_EINVAL, "NULL argument");
+  CU(c, cudaSetDevice(c->device));
+  if (int rc = ensure_candidates(c)) return rc;
+  const int rec = cand_rec(c->ld), cap = RFSB200_BIRTH_CAND_CAP;
+  std::vector<double> h((size_t)c->N * cap * rec);
+  CU(c, cudaMemcpyAsync(n, c->cand_n[c->cand_front], (size_t)c->N * 4, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaMemcpyAsync(h.data(), c->cand[c->cand_front], h.size() * 8, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < c->N; i++)
+    for (int k = 0; k < n[i] && k < cap; k++) {
+      const size_t s = (size_t)i * cap + k;
+      const double* r = &h[s * rec];
+      if (mean) for (int d = 0; d < c->ld; d++) mean[s * c->ld + d] = r[d];
+      if (cov) for (int q = 0; q < c->nc; q++) cov[s * c->nc + q] = r[c->ld + q];
+      if (support) support[s] = (int32_t)r[rec - 2];
+      if (checks) checks[s] = (int32_t)r[rec - 1];
+    }
+  return RFSB200_OK;
+}
+
+int rfsb200_set_birth_candidates(rfsb200_ctx* c, const int32_t* n, const double* mean, const double* cov, const int32_t* support,
+                                 const int32_t* checks) {
+  if (!c || !n) return fail(c, RFSB200_EINVAL, "NULL argument");
+  CU(c, cudaSetDevice(c->device));
+  if (int rc = ensure_candidates(c)) return rc;
+  const int rec = cand_rec(c->ld), cap = RFSB200_BIRTH_CAND_CAP;
+  std::vector<double> h((size_t)c->N * cap * rec, 0.0);
+  for (int i = 0; i < c->N; i++) {
+    if (n[i] < 0 || n[i] > cap) return fail(c, RFSB200_ECAPACITY, "%d candidates for particle %d (capacity %d)", n[i], i, cap);
+    if (n[i] > 0 && (!mean || !cov || !support || !checks)) return fail(c, RFSB200_EINVAL, "NULL candidate arrays");
+    for (int k = 0; k < n[i]; k++) {
+      const size_t s = (size_t)i * cap + k;
+      double* r = &h[s * rec];
+      for (int d = 0; d < c->ld; d++) r[d] = mean[s * c->ld + d];
+      for (int q = 0; q < c->nc; q++) r[c->ld + q] = cov[s * c->nc + q];
+      r[rec - 2] = (double)support[s];
+      r[rec - 1] = (double)checks[s];
+    }
+  }
+  CU(c, cudaMemcpyAsync(c->cand_n[c->cand_front], n, (size_t)c->N * 4, cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaMemcpyAsync(c->cand[c->cand_front], h.data(), h.size() * 8, cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  return RFSB200_OK;
 }
 
 // lower Cholesky factor as Eigen::LLT computes it (n x n, row-major in / out, zero padded to 3x3)

@@ -189,6 +189,39 @@ class PHDUpdater:
                self.lib.rfsb200_predict_maps(self.ctx, capi.ptr(q), 1 if add_births else 0, float(birth_weight)),
                "predict_maps")
 
+    def birth_candidates(self, birth_weight: float, support_dist: float, count_thr: int, check_thr: int, cur_count_thr: int,
+                         parent=None):
+        """addBirthGaussians() in its candidate-list form on the device (include/RBPHDFilter.hpp:1000-1080): the unused
+        measurements of the last update feed the per-particle candidate lists kept by the ctx; candidates that become
+        real are appended to the maps.  parent = the parent slots after a resampling (resampleOccured_), else None."""
+        b = capi.BirthCfg()
+        b.birth_weight, b.support_dist = float(birth_weight), float(support_dist)
+        b.count_threshold, b.check_threshold, b.current_count_threshold = int(count_thr), int(check_thr), int(cur_count_thr)
+        par = None if parent is None else np.ascontiguousarray(parent, dtype=np.int32)
+        _check(self.lib, self.ctx, self.lib.rfsb200_birth_candidates(self.ctx, C.byref(b), capi.ptr(par)), "birth_candidates")
+
+    def get_birth_candidates(self):
+        """-> (n [N], mean [N][64][D], cov [N][64][NC], support [N][64], checks [N][64])"""
+        cap = capi.BIRTH_CAND_CAP
+        n = np.zeros(self.N, np.int32)
+        mean = np.zeros((self.N, cap, self.D))
+        cov = np.zeros((self.N, cap, self.NC))
+        sup = np.zeros((self.N, cap), np.int32)
+        chk = np.zeros((self.N, cap), np.int32)
+        _check(self.lib, self.ctx, self.lib.rfsb200_get_birth_candidates(self.ctx, capi.ptr(n), capi.ptr(mean), capi.ptr(cov),
+                                                                         capi.ptr(sup), capi.ptr(chk)), "get_birth_candidates")
+        return n, mean, cov, sup, chk
+
+    def set_birth_candidates(self, n, mean, cov, support, checks):
+        cap = capi.BIRTH_CAND_CAP
+        n = np.ascontiguousarray(n, dtype=np.int32)
+        mean = np.ascontiguousarray(mean, dtype=np.float64).reshape(self.N, cap, self.D)
+        cov = np.ascontiguousarray(cov, dtype=np.float64).reshape(self.N, cap, self.NC)
+        sup = np.ascontiguousarray(support, dtype=np.int32).reshape(self.N, cap)
+        chk = np.ascontiguousarray(checks, dtype=np.int32).reshape(self.N, cap)
+        _check(self.lib, self.ctx, self.lib.rfsb200_set_birth_candidates(self.ctx, capi.ptr(n), capi.ptr(mean), capi.ptr(cov),
+                                                                         capi.ptr(sup), capi.ptr(chk)), "set_birth_candidates")
+
     def propagate(self, model: str, u, *, Q=None, input_cov=None, dt: float = 0.0, use_model_noise: bool = True,
                   use_input_noise: bool = False, ackerman=(0.0, 1.0, 0.0, 0.0), seed: int = 0, step: int = 0):
         """ParticleFilter::propagate() on the device: ProcessModel::sample() of MotionModel_Odometry2d ("odometry2d",

@@ -228,3 +228,62 @@ def run_device(wl, precision=32, flags=None, gm_capacity=None, work_capacity=0, 
     cnt, mean, cov, w = up.download_maps(which)
     pw = up.get_weights(which)
     return so, cnt, mean, cov, w, pw, up
+
+
+# ---- candidate-list births (include/RBPHDFilter.hpp:1000-1080): synthetic sequences without a device ---------------
+BIRTH_CFG = dict(count_thr=3, check_thr=4, cur_count_thr=2, support_dist=2.0)
+
+
+def birth_model(dim):
+    """plugin descriptor of the range-bearing (dim 2) / Victoria Park (dim 3) set, as the update workloads use it"""
+    from rfs_slam_b200 import synth
+    return (synth.make_vp_workload(2, 8, 4, seed=1) if dim == 3 else synth.make_workload(2, 8, 4, seed=1)).model
+
+
+def birth_scenario(dim, N, steps, seed, pose_cov=False):
+    """Per step: poses, a measurement batch of noisy sightings of a few fixed objects plus clutter, random
+    unused-measurement masks and nLandmarksInFOV_, and on two of the steps the parent slots of a resampling.
+    Objects are re-observed over the steps, so candidates gather support, get promoted, age out or are erased."""
+    rng = np.random.default_rng(seed)
+    model = birth_model(dim)
+    rlo, rhi = model["range_min"] + 1.0, min(model["range_max"] - 1.0, 30.0)
+    off = np.pi / 2 if dim == 3 else 0.0                 # the Victoria Park sensor looks along theta - pi / 2
+    n_obj = 8
+    obj_r = rng.uniform(rlo, rhi, n_obj)
+    obj_b = rng.uniform(0.4, 2.6, n_obj) if dim == 3 else rng.uniform(-2.5, 2.5, n_obj)
+    th0 = 0.3 + off
+    obj = np.stack([obj_r * np.cos(obj_b + th0 - off), obj_r * np.sin(obj_b + th0 - off), rng.uniform(0.3, 1.5, n_obj)], axis=1)
+    pose = np.zeros((N, 3))
+    pose[:, 2] = th0
+    pose += rng.normal(0.0, [0.05, 0.05, 0.01], (N, 3))
+    pcov = None
+    if pose_cov and dim == 2:
+        pcov = np.tile(np.array([0.02, 0.001, 0.0, 0.03, 0.0, 0.004]), (N, 1)) * rng.uniform(0.5, 1.5, (N, 1))
+    out = []
+    for t in range(steps):
+        pose = pose + rng.normal(0.0, [0.02, 0.02, 0.002], (N, 3))
+        seen = np.nonzero(rng.random(n_obj) < 0.75)[0]
+        d = obj[seen, :2]
+        zr = np.hypot(d[:, 0], d[:, 1]) + rng.normal(0.0, 0.05, len(seen))
+        zb = np.arctan2(d[:, 1], d[:, 0]) - (th0 - off) + rng.normal(0.0, 0.01, len(seen))
+        Z = np.stack([zr, zb, obj[seen, 2] + rng.normal(0.0, 0.05, len(seen))], axis=1)
+        n_clutter = int(rng.integers(0, 4))
+        clutter = np.stack([rng.uniform(rlo, rhi, n_clutter), rng.uniform(0.4, 2.6, n_clutter), rng.uniform(0.3, 1.5, n_clutter)], axis=1)
+        Z = np.concatenate([Z, clutter])[:, :dim]
+        Z = Z[rng.permutation(len(Z))]
+        nZ = len(Z)
+        mask = np.zeros(N, np.uint64)
+        for z in range(nZ):
+            mask |= (rng.random(N) < 0.6).astype(np.uint64) << np.uint64(z)
+        nfov = rng.integers(0, 7, N).astype(np.int32)
+        parent = None
+        if t in (3, 5):
+            keep = rng.random(N) < 0.6
+            keep[rng.integers(N)] = True
+            parent = np.arange(N, dtype=np.int32)
+            parent[~keep] = rng.choice(np.nonzero(keep)[0], size=int((~keep).sum()))
+            pose = pose[parent]
+            if pcov is not None:
+                pcov = pcov[parent]
+        out.append(dict(pose=pose.copy(), Z=Z, mask=mask, nfov=nfov, parent=parent, pose_cov=None if pcov is None else pcov.copy()))
+    return model, out

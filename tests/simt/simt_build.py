@@ -21,7 +21,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "rfs-slam_b200", "csrc")
 OUT = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT, "librfsb200_simt.so")
-SOURCES = ["rfsb200_abi.cu", "phd_kernels.cuh", "phd_vp_kernels.cuh", "common.cuh", "murty_compat.hpp"]
+SOURCES = ["rfsb200_abi.cu", "phd_kernels.cuh", "phd_vp_kernels.cuh", "birth_kernels.cuh", "common.cuh", "murty_compat.hpp"]
 
 _LAUNCH = re.compile(r"([A-Za-z_]\w*(?:<[^<>;()]*>)?)<<<(.*?)>>>\(")
 _DYN_SMEM = re.compile(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?unsigned char (\w+)\[\];")

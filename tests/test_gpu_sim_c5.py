@@ -2,8 +2,8 @@
 (MotionModel_Ackerman2d + MeasurementModel_VictoriaPark + KalmanFilter_VictoriaPark), compiled once against
 the reference's RBPHDFilter.hpp (CPU) and once against the drop-in header + librfsb200 (GPU) by
 `make -C oracle simvp`; both run the shipped artificial-clutter configuration on the head of the Victoria
-Park dataset (2 500 sensor messages, 100 particles, -s 1).  Particle propagation, the resampling draw and the
-candidate-list birth logic are host code in both builds, so with the fp64 device build the two runs log the
+Park dataset (2 500 sensor messages, 100 particles, -s 1).  Particle propagation and the resampling draw are host code in both
+builds and the candidate-list births run on the device in fp64, so with the fp64 device build the two runs log the
 same particle poses, weights and best-particle maps until an exact tie in Gaussian weights is ordered differently
 by the reference's unstable std::sort (Q9), and the same trajectory estimate afterwards."""
 import os
@@ -74,6 +74,12 @@ def test_unchanged_victoria_park_driver_runs_on_the_dropin(cuda_required, tmp_pa
     n_ref = np.array([(lm_ref[:, 0] == t).sum() for t in np.unique(lm_ref[:, 0])])
     n_64 = np.array([(lm64[:, 0] == t).sum() for t in np.unique(lm64[:, 0])])
     assert len(n_ref) == len(n_64) and np.abs(n_ref - n_64).max() <= 6
+    # the candidate lists of addBirthGaussians live on the device (rfsb200_birth_candidates); kept on the host and
+    # evaluated with the live plugin objects instead (RFSB200_HOST_BIRTHS=1), the run logs the same numbers
+    pph, lmh = _run("rbphdslam_VictoriaPark_b200", str(tmp_path / "b64h"), {"RFSB200_PRECISION": "64", "RFSB200_HOST_BIRTHS": "1"})
+    assert pph.shape == pp64.shape and lmh.shape == lm64.shape
+    assert np.allclose(pph[early], pp64[early], rtol=1e-9, atol=1e-9)
+    assert np.allclose(pph[:, :5], pp64[:, :5], atol=2e-3) and np.allclose(lmh, lm64, atol=2e-3)
     # fp32 product build: same trajectory estimate
     pp32, lm32 = _run("rbphdslam_VictoriaPark_b200", str(tmp_path / "b32"), {"RFSB200_PRECISION": "32"})
     assert pp32.shape == pp_ref.shape

@@ -113,13 +113,14 @@ def _gpu_tests(module_name, skip):
 
 
 @pytest.mark.parametrize("fn,kw", _gpu_tests("test_gpu_parity", skip=("randomised",)) + _gpu_tests("test_gpu_vp", skip=()) +
-                         _gpu_tests("test_gpu_fullsize", skip=("c4_every_shard",)) + _gpu_tests("test_motion", skip=()))
+                         _gpu_tests("test_gpu_fullsize", skip=("c4_every_shard",)) + _gpu_tests("test_motion", skip=()) +
+                         _gpu_tests("test_gpu_births", skip=()))
 def test_gpu_test_bodies_on_the_interpreted_kernels(simt_lib, fn, kw):
     """The `-m gpu` parity tests, bodies and sizes unchanged, with the binding pointed at the interpreter build: the
     reference's golden vectors and the oracle for both plugin sets and precisions, culled against exhaustive merge,
     multi-step sequences, NO_COMMIT / empty Z, pose-covariance modes, capacity overflow, API surface, matrix
     permanents, large partitions, the DP workspace, fused normalisation, update_host with and without copies, Victoria
-    Park predict / births, the full-size C2 / C3 / C5 property tests (8 "SMs": every warp works through hundreds of
+    Park predict / births, the candidate-list births, the full-size C2 / C3 / C5 property tests (8 "SMs": every warp works through hundreds of
     particles), particle propagation."""
     with host.interpreted(sm_count=8 if "full_size" in fn.__name__ else 2):
         fn(simt_lib, **kw)
