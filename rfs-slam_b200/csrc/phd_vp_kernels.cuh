@@ -138,8 +138,11 @@ struct VPFast {
 };
 
 // probabilityOfDetection2 at the point pose + (dx, dy); e_pos = bound on the error of dx and dy.  false: undecided.
-__device__ __forceinline__ bool vp_pd2_fast(const VPGeom& g, const VPFast& f, float dx, float dy, float th, float ld,
-                                            float e_pos, double& val, bool& close) {
+// The value is an entry of the P_D table or the literal 0: returned as `code` (table index, VP_PD_ZERO = literal 0) so
+// that a lane can hand its result to another one in a single word (vp_pd_warp).
+constexpr int VP_PD_ZERO = 63;
+__device__ __forceinline__ bool vp_pd2_fast_code(const VPGeom& g, const VPFast& f, float dx, float dy, float th, float ld,
+                                                 float e_pos, int& code, bool& close) {
   constexpr float PI_F = 3.14159265358979323846f;
   close = false;
   const float d2 = dx * dx + dy * dy;
@@ -153,7 +156,7 @@ __device__ __forceinline__ bool vp_pd2_fast(const VPGeom& g, const VPFast& f, fl
   if (!(fabsf(angle) < PI_F - e_ang)) return false;   // at the wrap (or |th| beyond one turn)
   if (fabsf(angle - f.bmax) < e_ang || fabsf(angle - f.bmin) < e_ang || fabsf(dist - f.rmin) < e_dist || fabsf(dist - f.rmax) < e_dist)
     return false;
-  if (angle > f.bmax || angle < f.bmin || dist < f.rmin || dist > f.rmax) { val = 0.0; return true; }
+  if (angle > f.bmax || angle < f.bmin || dist < f.rmin || dist > f.rmax) { code = VP_PD_ZERO; return true; }
   const float mr = 0.5f * ld;
   const float gamma = M<float>::atan2_(mr, dist);   // = atan(mr / dist), both positive
   const float e_gam = mr * e_dist / d2 + 3e-7f;
@@ -163,7 +166,7 @@ __device__ __forceinline__ bool vp_pd2_fast(const VPGeom& g, const VPFast& f, fl
   if (v - fl < e_v || fl + 1.0f - v < e_v) return false;
   const int maxNumPoints = (int)fl;
   const bool in_tab = maxNumPoints >= 0 && g.pd_n > maxNumPoints;
-  if (in_tab && g.pd[maxNumPoints] == 0.0) { val = 0.0; return true; }
+  if (in_tab && g.pd[maxNumPoints] == 0.0) { code = VP_PD_ZERO; return true; }
   if (in_tab && g.pd[maxNumPoints] < g.buf_pd) close = true;
   const float u = (angle - gamma) * 114.59155902616465f;   // 720 / (2 pi)
   const float e_u = 114.6f * (e_ang + e_gam) + 3e-7f * fabsf(u) + 1e-5f;
@@ -189,7 +192,15 @@ __device__ __forceinline__ bool vp_pd2_fast(const VPGeom& g, const VPFast& f, fl
   }
   if (numPoints >= g.pd_n) numPoints = g.pd_n - 1;
   if (g.pd[numPoints] == 0.0) close = false;
-  val = g.pd[numPoints];
+  code = numPoints;
+  return true;
+}
+
+__device__ __forceinline__ bool vp_pd2_fast(const VPGeom& g, const VPFast& f, float dx, float dy, float th, float ld,
+                                            float e_pos, double& val, bool& close) {
+  int code;
+  if (!vp_pd2_fast_code(g, f, dx, dy, th, ld, e_pos, code, close)) return false;
+  val = code == VP_PD_ZERO ? 0.0 : g.pd[code];
   return true;
 }
 
@@ -254,6 +265,128 @@ __device__ __forceinline__ double vp_pd_any(const VPGeom& g, const VPFast& f, T 
   }
   return vp_pd(g, (double)px, (double)py, (double)pth, (double)lx, (double)ly, (double)ld, (double)pxx, (double)pxy,
                (double)pyy, close);
+}
+
+// probabilityOfDetection for the (up to 32) landmarks a warp holds, one per lane (have = this lane has one).  Same
+// decisions and the same values as vp_pd_any per lane, organised for the warp: a landmark is evaluated at 2 K + 1 points
+// across its 3-sigma extent (vp_pd_fast), K differs from landmark to landmark and most landmarks of a chunk are out of
+// reach altogether — evaluated lane by lane, a handful of lanes would walk through their points while the others wait.
+// Instead every lane first runs the cheap part for its own landmark (reach test, direction, K), the evaluation points
+// of all landmarks of the chunk are numbered through (warp scan), lane i evaluates point i, i + 32, ... whoever it
+// belongs to (parameters fetched from the owner by shuffle), and the owners collect the coded results of their points
+// by shuffle again.  A point too close to call sends its landmark to the fp64 evaluation, as before.
+template <typename T>
+__device__ __forceinline__ double vp_pd_warp(const VPGeom& g, const VPFast& f, T px_, T py_, T pth_, bool have, T lx_, T ly_, T ld_,
+                                             T pxx_, T pxy_, T pyy_, bool& close, int lane) {
+  close = false;
+  if constexpr (sizeof(T) != 4) {
+    if (!have) return 0.0;
+    return vp_pd(g, (double)px_, (double)py_, (double)pth_, (double)lx_, (double)ly_, (double)ld_, (double)pxx_, (double)pxy_,
+                 (double)pyy_, close);
+  } else {
+    constexpr float PI_F = 3.14159265358979323846f;
+    const float px = px_, py = py_, pth = pth_, lx = lx_, ly = ly_, ld = ld_, pxx = pxx_, pxy = pxy_, pyy = pyy_;
+    const float th = pth - 0.5f * PI_F;
+    // ---- own landmark: the part of vp_pd_fast before its evaluation loop ----
+    enum { NONE = 0, DECIDED = 1, FP64 = 2, EVAL = 3 };
+    int state = have ? EVAL : NONE;
+    const float dx = lx - px, dy = ly - py;
+    const float e0 = 4e-8f * (fabsf(dx) + fabsf(dy)) + 1e-7f;
+    float ex = 0.0f, ey = 0.0f;
+    int K = 0;
+    if (have) {
+      const float r0 = sqrtf(dx * dx + dy * dy);
+      float b0 = M<float>::atan2_(dy, dx) - th;
+      if (b0 > PI_F) b0 -= 2 * PI_F;
+      if (b0 < -PI_F) b0 += 2 * PI_F;
+      if (!(fabsf(b0) < PI_F - 2e-6f)) state = FP64;
+      const float angle = M<float>::atan2_(b0, r0) + pth;
+      float sn, cs;
+      __sincosf(angle, &sn, &cs);
+      ex = -sn; ey = cs;
+      float sd = (ex * pxx + ey * pxy) * ex + (ex * pxy + ey * pyy) * ey;
+      if (!(sd >= 0.0f) || !(ld > 0.0f)) state = FP64;
+      sd = 3.0f * sqrtf(sd);
+      sd = sd < 0.2f ? 0.2f : sd;
+      if (!(sd < 1e30f)) state = FP64;
+      if (state == EVAL) {
+        const float reach = (sd + 2.0f * ld) * 1.001f + 1e-3f;
+        if (r0 > f.rmax + reach || r0 < f.rmin - reach) state = DECIDED;   // P_D = 0, not close
+      }
+      if (state == EVAL) {
+        const float step = 2.0f * ld;
+        const float e_sd = 2e-5f * sd + 1e-6f;
+        for (int i = 1; i <= 64; i++) {
+          const float lim = (float)(i - 1) * step;
+          if (fabsf(lim - sd) < e_sd) { state = FP64; break; }   // how many evaluation points there are is a decision too
+          if (!(lim < sd)) break;
+          K = i;
+          if (i == 64) state = FP64;                             // a very thin trunk under a very wide covariance
+        }
+      }
+    }
+    // ---- the evaluation points of the chunk, numbered through ----
+    const int cnt = state == EVAL ? 2 * K + 1 : 0;
+    const int incl = warp_incl_scan(cnt, lane);
+    const int excl = incl - cnt;
+    const int total = __shfl_sync(FULL, incl, 31);
+    double pmin = 1e300, pmax = -1e300;
+    bool bad = false, close_c = false;
+    for (int it0 = 0; it0 < total; it0 += 32) {
+      const int item = it0 + lane;
+      int owner = 0;
+#pragma unroll
+      for (int sh = 16; sh > 0; sh >>= 1) {   // smallest lane whose inclusive count exceeds the item
+        const int v = __shfl_sync(FULL, incl, owner + sh - 1);
+        if (item >= v) owner += sh;
+      }
+      owner &= 31;
+      const int t = item - __shfl_sync(FULL, excl, owner);
+      const float odx = __shfl_sync(FULL, dx, owner), ody = __shfl_sync(FULL, dy, owner);
+      const float oex = __shfl_sync(FULL, ex, owner), oey = __shfl_sync(FULL, ey, owner);
+      const float old = __shfl_sync(FULL, ld, owner), oe0 = __shfl_sync(FULL, e0, owner);
+      const int oK = __shfl_sync(FULL, K, owner);
+      int res = 1;
+      if (item < total) {
+        int code = VP_PD_ZERO;
+        bool cl = false;
+        // t == 2 K: the landmark itself (offset 0: the sums below return odx, ody unchanged), evaluated last by the
+        // reference, so its "close" flag is the one that stays; the others: +-(i * 2 ld) along the perpendicular
+        const bool centre = t == 2 * oK;
+        const float s = centre ? 0.0f : (float)(t / 2 + 1) * (2.0f * old);
+        const float e_pos = centre ? oe0 : oe0 + 4e-6f * s + 2e-6f;   // direction error x offset, roundings of the sums
+        const float sg = (t & 1) ? -s : s;
+        const bool ok = vp_pd2_fast_code(g, f, odx + sg * oex, ody + sg * oey, th, old, e_pos, code, cl);
+        res = centre ? 256 : 0;
+        res |= (ok ? 1 : 0) | (cl ? 2 : 0) | (code << 2);
+      }
+      // owners collect: the points of a landmark sit in consecutive lanes
+      int first = excl > it0 ? excl - it0 : 0;
+      int last = incl < it0 + 32 ? incl - it0 : 32;
+      const int mine = last > first ? last - first : 0;
+      const int most = 32 - __clz((int)__reduce_or_sync(FULL, mine ? 1u << (mine - 1) : 0u));   // max over the lanes
+      for (int j = 0; j < most; j++) {
+        const int r = __shfl_sync(FULL, res, (first + j) & 31);
+        if (j < mine) {
+          if (!(r & 1)) bad = true;
+          const int code = (r >> 2) & 63;
+          const double v = code == VP_PD_ZERO ? 0.0 : g.pd[code];
+          pmin = v < pmin ? v : pmin;
+          pmax = v > pmax ? v : pmax;
+          if (r & 256) close_c = (r & 2) != 0;
+        }
+      }
+    }
+    if (state == EVAL && !bad) {
+      close = close_c;
+      if (pmin == 0.0 && pmax > 0.0) close = true;
+      return pmax;
+    }
+    if (state == FP64 || (state == EVAL && bad))
+      return vp_pd(g, (double)px, (double)py, (double)pth, (double)lx, (double)ly, (double)ld, (double)pxx, (double)pxy, (double)pyy,
+                   close);
+    return 0.0;   // out of reach, or no landmark in this lane
+  }
 }
 
 // ---- 3x3 symmetric helpers (upper triangle a00 a01 a02 a11 a12 a22) ---------------------------------
@@ -449,10 +582,12 @@ phd_update_vp_kernel(const __grid_constant__ VPParams<T> vp) {
       if (m < nM) {
         x = cur[m]; y = cur[W + m]; d = cur[2 * W + m];
         load_sym3(P, cur, W, m);
+      }
+      bool close = false;
+      T Pd = (T)vp_pd_warp<T>(geom, fast, px, py, pth, m < nM, x, y, d, P.a00, P.a01, P.a11, close, lane);
+      if (m < nM) {
         const T w = cur[VP_WP * W + m];
         wsum_d += (double)w;
-        bool close = false;
-        T Pd = (T)vp_pd_any<T>(geom, fast, px, py, pth, x, y, d, P.a00, P.a01, P.a11, close);
         if (close) Pd = T(1);   // Q2 (include/RBPHDFilter.hpp:604-606)
         if (Pd != T(0)) nfov++;
         if (MF) cur[WPREV * W + m] = w;
@@ -654,14 +789,13 @@ phd_update_vp_kernel(const __grid_constant__ VPParams<T> vp) {
           const int m = base + lane;
           bool elig = false, heavy = false;
           T pdm = 0;
-          if (m < n) {
-            heavy = !(wpl[m] < p.eval_min_w);
-            if (heavy) {
-              bool close;
-              pdm = (T)vp_pd_any<T>(geom, fast, px, py, pth, cur[m], cur[W + m], cur[2 * W + m], cur[3 * W + m], cur[4 * W + m],
-                                    cur[6 * W + m], close);
-              elig = pdm > T(0);
-            }
+          if (m < n) heavy = !(wpl[m] < p.eval_min_w);
+          {
+            const int mm = heavy ? m : 0;
+            bool close;
+            pdm = (T)vp_pd_warp<T>(geom, fast, px, py, pth, heavy, cur[mm], cur[W + mm], cur[2 * W + mm], cur[3 * W + mm],
+                                   cur[4 * W + mm], cur[6 * W + mm], close, lane);
+            elig = heavy && pdm > T(0);
           }
           const unsigned be = __ballot_sync(FULL, elig);
           const int rank = nE + __popc(be & ((1u << lane) - 1u));
