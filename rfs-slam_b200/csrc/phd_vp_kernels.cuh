@@ -754,7 +754,7 @@ phd_update_vp_kernel(const __grid_constant__ VPParams<T> vp) {
                                   (unsigned long long)(0xffffffffu - (unsigned)k))
                                : 0ull;
             __syncwarp();
-            warp_bitonic_desc64(k64, P2, lane);
+            warp_sort_desc64(k64, P2, lane);
             for (int k = lane; k < n; k += 32) order[k] = (unsigned short)(0xffffffffu - (unsigned)(k64[k] & 0xffffffffull));
           } else {
             T* kw = reinterpret_cast<T*>(k64);
@@ -940,7 +940,7 @@ phd_update_vp_kernel(const __grid_constant__ VPParams<T> vp) {
           k64[k] = key;
         }
         __syncwarp();
-        warp_bitonic_desc64(k64, P2, lane);
+        warp_sort_desc64(k64, P2, lane);
         // the keys order by x rounded to fp32 (and the window bound is evaluated in T): widen the window a little
         const T rwin = M<T>::sqrt_(rmax2) * T(1.001) + T(1e-3);
         for (int sb = 0; sb < n; sb += 32) {
@@ -1075,7 +1075,7 @@ phd_update_vp_kernel(const __grid_constant__ VPParams<T> vp) {
         const int P2 = next_pow2(n_out);
         for (int k = n_out + lane; k < P2; k += 32) k64[k] = 0ull;
         __syncwarp();
-        if (n_out > 1) warp_bitonic_desc64(k64, P2, lane);
+        if (n_out > 1) warp_sort_desc64(k64, P2, lane);
         for (int k = lane; k < n_out; k += 32) order[k] = (unsigned short)(0xffffffffu - (unsigned)(k64[k] & 0xffffffffull));
       } else {
         T* kw = reinterpret_cast<T*>(k64);
