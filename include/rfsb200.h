@@ -265,8 +265,10 @@ int rfsb200_append_gaussians(rfsb200_ctx* ctx, const int32_t* count /*[N]*/, con
  * second pass the reference makes when the last list element is erased.  The masks are cleared.
  * parent: NULL, or after a resampling (resampleOccured_) the parent slot of every particle (:1005-1011): a copy takes
  *   the list its parent slot holds when the reference's ascending loop reaches it — the parent's list as it was for a
- *   higher slot, the parent's list after its own turn for a lower one.  (The masks were routed by rfsb200_resample's
- *   aux_src.)  rfsb200_export/import_particles do not carry candidate lists.
+ *   higher slot, the parent's list after its own turn for a lower one (which may itself be a copy from a still lower
+ *   slot: parent ids are not slot numbers after the first resampling; chains are resolved level by level, one launch
+ *   per level).  (The masks were routed by rfsb200_resample's aux_src.)  rfsb200_export/import_particles do not carry
+ *   candidate lists.
  * Gaussians beyond gm_capacity set flag bits 1 and 8, a candidate beyond RFSB200_BIRTH_CAND_CAP is dropped with flag
  * bit 32.  Arithmetic is fp64 whatever the ctx precision; the appended Gaussians are rounded to the map's type. */
 #define RFSB200_BIRTH_CAND_CAP 64

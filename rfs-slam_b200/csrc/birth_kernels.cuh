@@ -31,6 +31,7 @@ __host__ __device__ constexpr int cand_rec(int D) { return D + D * (D + 1) / 2 +
 struct BirthCandParams {
   int N, cap, cand_cap, nZ, pass, pcov_mode;
   const int* parent;                 // [N] or NULL (no resampling since the last call)
+  const int* level;                  // [N] with parent: the launch (pass) in which the particle is processed
   const double* pose64;              // [N][3] pose of the last update
   const void* pcov;                  // T[8] per particle (mode 2) or shared (mode 1): 2-D model only
   unsigned long long* unused;        // [N]
@@ -219,10 +220,12 @@ __device__ __forceinline__ void store_cand(double* rec, const BCand<D>& c) {
 }
 }  // namespace bc
 
-// pass 0: particles whose list is their own or comes from a HIGHER slot (still untouched when the reference's
-//         ascending loop reaches them): read from the input buffer;
-// pass 1: particles whose parent slot is LOWER: the reference copies the parent's list AFTER the parent's own turn
-//         (its unused measurements are gone by then, so only the check loop acts): read the parent's pass-0 result.
+// After a resampling the reference's loop (ascending i, in place) lets particle i take over the list its parent slot
+// holds AT THAT MOMENT: a parent slot above i is still untouched (its list as it was: the input buffer), a parent slot
+// below i has had its own turn already (the list AFTER it, and no unused measurements are left to copy, so only the
+// check loop acts).  Parent ids are not slot numbers after the first resampling, so the lower parent may itself have
+// taken its list from a still lower slot: level[i] = 0 if parent >= i, else level[parent] + 1 (computed by the host),
+// one launch per level, a particle of level l reads the result its parent wrote in an earlier launch.
 template <typename T, int D>
 __global__ void birth_candidates_kernel(const BirthCandParams p) {
   constexpr int NC = D * (D + 1) / 2;
@@ -232,14 +235,15 @@ __global__ void birth_candidates_kernel(const BirthCandParams p) {
   if (i >= p.N) return;
   int par = p.parent ? p.parent[i] : i;
   if (par < 0 || par >= p.N) par = i;
-  if (p.pass == 0 ? (par < i) : (par >= i)) return;
-  const double* src = (p.pass == 0 ? p.cand_in : p.cand_out) + (size_t)par * p.cand_cap * REC;
-  int n = (p.pass == 0 ? p.cand_n_in : p.cand_n_out)[par];
+  if ((p.parent ? p.level[i] : 0) != p.pass) return;
+  const bool after = par < i;   // the parent slot has had its turn: take its result
+  const double* src = (after ? p.cand_out : p.cand_in) + (size_t)par * p.cand_cap * REC;
+  int n = (after ? p.cand_n_out : p.cand_n_in)[par];
   n = n < 0 ? 0 : (n > p.cand_cap ? p.cand_cap : n);
   double* dst = p.cand_out + (size_t)i * p.cand_cap * REC;
   for (int k = 0; k < n * REC; k++) dst[k] = src[k];
 
-  unsigned long long mask = p.pass == 0 ? p.unused[i] : 0ull;
+  unsigned long long mask = after ? 0ull : p.unused[i];
   if (p.nZ < 64) mask &= (1ull << p.nZ) - 1ull;
   const double pose[3] = {p.pose64[3 * i], p.pose64[3 * i + 1], p.pose64[3 * i + 2]};
   double Sx[9];
@@ -339,7 +343,7 @@ __global__ void birth_candidates_kernel(const BirthCandParams p) {
       }
     }
   }
-  if (p.pass == 0) p.unused[i] = 0ull;
+  p.unused[i] = 0ull;
 
   // the check pass (:1056-1075).  Erasing the LAST element of the list ends the reference's inner loop with the
   // iterator at end(); its for statement then increments end(), which on libstdc++'s circular list is begin(): the

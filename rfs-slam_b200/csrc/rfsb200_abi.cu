@@ -1262,16 +1262,25 @@ int rfsb200_birth_candidates(rfsb200_ctx* c, const rfsb200_birth_cfg* b, const i
   CU(c, cudaSetDevice(c->device));
   if (int rc = ensure_candidates(c)) return rc;
   if (c->last_nZ > 0 && !c->have_poses) return fail(c, RFSB200_ESTATE, "birth_candidates needs the poses of the last update");
+  int n_pass = 1;
   if (parent) {
-    for (int i = 0; i < c->N; i++)
+    // level[i] = how many lower parent slots have to be finished before particle i can take over its list
+    std::vector<int> level(c->N);
+    for (int i = 0; i < c->N; i++) {
       if (parent[i] < 0 || parent[i] >= c->N) return fail(c, RFSB200_EINVAL, "parent %d of particle %d out of range", parent[i], i);
+      level[i] = parent[i] < i ? level[parent[i]] + 1 : 0;
+      n_pass = std::max(n_pass, level[i] + 1);
+    }
     CU(c, cudaMemcpyAsync(c->src_dev, parent, (size_t)c->N * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(c->src_dev + c->N, level.data(), (size_t)c->N * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));   // parent[] and level[] are pageable host buffers
   }
   BirthCandParams p{};
   const StateBuf& st = c->st[c->front];
   p.N = c->N; p.cap = c->cap; p.cand_cap = RFSB200_BIRTH_CAND_CAP; p.nZ = c->last_nZ;
   p.pcov_mode = c->ld == 2 ? c->pose_cov_mode : 0;
   p.parent = parent ? c->src_dev : nullptr;
+  p.level = parent ? c->src_dev + c->N : nullptr;
   p.pose64 = c->stg_small; p.pcov = c->pose_cov;
   p.unused = c->unused; p.nfov = c->nfov;
   p.cand_in = c->cand[c->cand_front]; p.cand_n_in = c->cand_n[c->cand_front];
@@ -1285,7 +1294,7 @@ int rfsb200_birth_candidates(rfsb200_ctx* c, const rfsb200_birth_cfg* b, const i
   const int md = c->ld;   // measurement dimension of both built-in plugin sets
   for (int k = 0; k < c->last_nZ * md; k++) p.Z[k] = c->Zval[k];
   const int blocks = (c->N + 127) / 128;
-  for (int pass = 0; pass < (parent ? 2 : 1); pass++) {
+  for (int pass = 0; pass < n_pass; pass++) {
     p.pass = pass;
     if (c->ld == 3) {
       if (c->prec == 32) birth_candidates_kernel<float, 3><<<blocks, 128, 0, c->stream>>>(p);
@@ -1296,7 +1305,6 @@ int rfsb200_birth_candidates(rfsb200_ctx* c, const rfsb200_birth_cfg* b, const i
     }
     CU(c, cudaGetLastError());
   }
-  if (parent) CU(c, cudaStreamSynchronize(c->stream));   // parent[] is the caller's (pageable) buffer
   c->cand_front ^= 1;
   c->last_out = c->front;
   return RFSB200_OK;

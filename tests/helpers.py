@@ -278,10 +278,12 @@ def birth_scenario(dim, N, steps, seed, pose_cov=False):
         nfov = rng.integers(0, 7, N).astype(np.int32)
         parent = None
         if t in (3, 5):
-            keep = rng.random(N) < 0.6
+            # parent ids are not slot numbers after the first resampling (the reference indexes its per-slot lists with
+            # getParentId() all the same): any slot can be named, including one that is itself a copy (chains)
+            keep = rng.random(N) < 0.5
             keep[rng.integers(N)] = True
             parent = np.arange(N, dtype=np.int32)
-            parent[~keep] = rng.choice(np.nonzero(keep)[0], size=int((~keep).sum()))
+            parent[~keep] = rng.integers(0, N, size=int((~keep).sum()))
             pose = pose[parent]
             if pcov is not None:
                 pcov = pcov[parent]

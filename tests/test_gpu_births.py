@@ -34,6 +34,10 @@ def _resample_plan(N, rng):
     src = np.arange(N, dtype=np.int32)
     src[~keep] = rng.choice(survivors, size=int((~keep).sum()))
     parent = src.copy()
+    # the lists follow getParentId(), which after the first resampling need not be the slot the map came from and may
+    # name a slot that is itself a copy: chains towards lower slots have to be resolved in the reference's order
+    chain = (~keep) & (rng.random(N) < 0.5)
+    parent[chain] = rng.integers(0, N, size=int(chain.sum()))
     aux = np.where(parent == np.arange(N), np.arange(N), np.where(parent > np.arange(N), parent, -1)).astype(np.int32)
     return src, parent, aux
 
@@ -55,7 +59,7 @@ def _run_sequence(dim, prec, N=48, steps=7, seed=11, pose_cov=False, bcfg=None):
     if pose_cov and dim == 2:
         pcov = np.tile(np.array([0.02, 0.001, 0.0, 0.03, 0.0, 0.004]), (N, 1)) * rng.uniform(0.5, 1.5, (N, 1))
     tol = 2e-6 if prec == 32 else 1e-11
-    n_real = n_support = n_dropped = n_copies = 0
+    n_real = n_support = n_dropped = n_copies = n_chain = 0
     for t in range(steps):
         pose = pose + rng.normal(0.0, [0.02, 0.02, 0.002], pose.shape)
         Z = wl.Z.reshape(-1, dim) + rng.normal(0.0, 0.02 if t % 3 else 0.3, (wl.nZ, dim))
@@ -73,6 +77,8 @@ def _run_sequence(dim, prec, N=48, steps=7, seed=11, pose_cov=False, bcfg=None):
             if pcov is not None:
                 pcov = pcov[src]
             n_copies += int((parent != np.arange(N)).sum())
+            lower = parent < np.arange(N)
+            n_chain += int((lower & (parent[parent] < parent)).sum())   # the lower parent is itself a copy from below
         cnt0, mean0, cov0, w0 = up.download_maps(0)
         before = state.copy()
         add_n, add_mean, add_cov = binding.birth_candidates(wl.model, bcfg, state, pose, Z, mask, nfov, parent=parent,
@@ -104,7 +110,7 @@ def _run_sequence(dim, prec, N=48, steps=7, seed=11, pose_cov=False, bcfg=None):
         q = np.array([1e-4, 0.0, 1e-4]) if dim == 2 else np.array([1e-4, 0, 0, 1e-4, 0, 1e-5])
         up.predict_maps(Q_lmk=q, add_births=False)
     up.close()
-    return dict(real=n_real, support=n_support, dropped=n_dropped, copies=n_copies, lists=int(state.n.sum()))
+    return dict(real=n_real, support=n_support, dropped=n_dropped, copies=n_copies, lists=int(state.n.sum()), chains=n_chain)
 
 
 @pytest.mark.parametrize("prec", [32, 64])
@@ -112,7 +118,7 @@ def _run_sequence(dim, prec, N=48, steps=7, seed=11, pose_cov=False, bcfg=None):
 def test_candidate_list_births_follow_the_reference_through_a_sequence(cuda_required, dim, prec):
     r = _run_sequence(dim, prec)
     # the sequence exercises every branch: candidates opened, supported, promoted, aged out, copied after a resampling
-    assert r["real"] > 0 and r["support"] > 0 and r["dropped"] > 0 and r["copies"] > 0, r
+    assert r["real"] > 0 and r["support"] > 0 and r["dropped"] > 0 and r["copies"] > 0 and r["chains"] > 0, r
 
 
 def test_candidate_list_births_with_the_victoria_park_thresholds(cuda_required):
