@@ -252,6 +252,7 @@ def run_workload(a, name, ctx, steps, warmup, headline):
 
     # ---- cross-GPU check (untimed): the in-kernel sum over peer memory against the NCCL all-reduce ----------------
     collective_check = None
+    w_f = None
     if world > 1 and fused:
         # the sums the kernels exchanged through the peer mailboxes (added in rank order, the same bits on every rank) and
         # the weights normalised with them, against: every rank's local sums all-gathered by NCCL, added in rank order on
@@ -298,16 +299,48 @@ def run_workload(a, name, ctx, steps, warmup, headline):
             else:
                 dist.all_reduce(ctx["align"])
 
+    # More than one GPU, peer mailboxes connected: the steps run with the cross-GPU sums DEFERRED
+    # (RFSB200_UPDATE_DEFER_NORMALIZE): a step sends its [sum w, sum w^2] and ends, the next one picks the pairs up during
+    # set-up (they arrived a step ago; with the committed state it would divide the weights by their total on the way in
+    # — here every step restarts from the same state, so the open weights are those of the back buffer, which the next
+    # step overwrites), and the LAST step's normalisation is closed inside the timed region (rfsb200_comm_resolve).
+    # --eager-exchange times the variant in which every step waits for all peers and normalises before it ends.
+    defer = world > 1 and fused and not a.eager_exchange
+    ev_close = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
     for k in range(K):
         flush_and_align()
         ev[k][0].record()
-        sh.step(wl.Z, flags=FLAGS)    # Z H2D (1.3 KB) + fused update kernel (+ cross-GPU sum + normalise inside)
+        sh.step(wl.Z, flags=FLAGS, defer=defer)    # fused update kernel (+ cross-GPU sum, + normalise unless deferred)
         ev[k][1].record()
+    ev_close[0].record()
+    if defer:
+        sh.resolve()
+    ev_close[1].record()
     barrier()
     t_wall = time.perf_counter() - t_wall0
     clk = clocks.stop() if rank == 0 else None
     step_ms = [e0.elapsed_time(e1) for e0, e1 in ev]
-    t_local = sum(step_ms) / 1e3
+    close_ms = ev_close[0].elapsed_time(ev_close[1]) if defer else 0.0
+    t_local = (sum(step_ms) + close_ms) / 1e3
+    deferred_check = None
+    if defer and w_f is not None:   # the last deferred step, closed by rfsb200_comm_resolve, against the eager step of the check above
+        same = bool(np.array_equal(up.get_weights(1).view(np.uint64), w_f.view(np.uint64)))
+        t = torch.tensor([1 if same else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        deferred_check = "bit-identical" if int(t.item()) == 1 else "DIFFERS"
+    eager_ms = None
+    if defer:   # the eager exchange beside it (untimed for `value`): same steps, every one waits for the slowest rank
+        ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+        barrier()
+        for k in range(K):
+            flush_and_align()
+            ev2[k][0].record()
+            sh.step(wl.Z, flags=FLAGS)
+            ev2[k][1].record()
+        barrier()
+        te = torch.tensor([sum(e0.elapsed_time(e1) for e0, e1 in ev2) / K], dtype=torch.float64, device=dev)
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        eager_ms = float(te.item())
     kern_us = up.profile_read()
     tt = torch.tensor([t_local], dtype=torch.float64, device=dev)
     uu = torch.tensor([float(units_local)], dtype=torch.float64, device=dev)
@@ -435,7 +468,9 @@ def run_workload(a, name, ctx, steps, warmup, headline):
                                    + (", followed by an untimed barrier that re-aligns the ranks)" if world > 1 else ")"),
                                 timing="CUDA events per step on the launch stream, summed; max over ranks",
                                 parallelism=f"particles block-partitioned over {world} GPU(s); one all-reduce of [sum w, sum w^2] per step "
-                                            + ("inside the update kernel over NVLink peer memory" if fused else "by NCCL")),
+                                            + ("inside the update kernel over NVLink peer memory" if fused else "by NCCL")
+                                            + ("; consumed DEFERRED: a step sends its pair and ends, the next step picks the peers' pairs up during "
+                                               "set-up, the last step's normalisation is closed inside the timed region (see `exchange`)" if defer else "")),
                     e2e=e2e, gpu_launches=(1 if fused else 2) * K, roofline=roofline, cpu_baseline=cpu, clocks=clk,
                     stages=stages, n_murty_per_step=n_murty, n_overflow_per_step=n_overflow,
                     wall_s_timed_region_incl_flush=t_wall)
@@ -443,6 +478,16 @@ def run_workload(a, name, ctx, steps, warmup, headline):
             line["collective_check"] = collective_check
             line["comm_error"] = comm_err
             line["per_rank"] = per_rank
+            if fused:
+                line["exchange"] = dict(
+                    mode="deferred" if defer else "eager",
+                    close_ms=close_ms if defer else None,
+                    deferred_check=deferred_check,
+                    eager_ms_per_step=eager_ms,
+                    note="deferred: RFSB200_UPDATE_DEFER_NORMALIZE — no rank waits for the slowest one inside a step; results bit-identical to the "
+                         "eager exchange (tests/test_gpu_multi.py); `close_ms` = rfsb200_comm_resolve after the last step, inside the timed "
+                         "region and inside `value`; `eager_ms_per_step` = the same steps with the wait + normalisation in every launch "
+                         "(--eager-exchange), max over ranks")
     up.close()
     return line
 
@@ -466,6 +511,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-stages", action="store_true")
     ap.add_argument("--no-fused", action="store_true", help="NCCL all-reduce + normalise kernel instead of the in-kernel sum over peer memory")
+    ap.add_argument("--eager-exchange", action="store_true", help="N > 1: every step waits for the peers' sums and normalises before it ends "
+                    "(default: deferred — the next step picks them up, the last one is closed inside the timed region)")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 0)
     # stdout carries exactly ONE JSON line: everything libraries print (NCCL's version banner, ...)

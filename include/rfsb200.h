@@ -66,6 +66,20 @@ extern "C" {
                                          rfsb200_get_stage_times() returns — the reference's per-phase TimingInfo
                                          (include/RBPHDFilter.hpp:152-167,1219-1232).  fp32 build; a measurement
                                          aid, a few percent slower than the product kernel                   */
+#define RFSB200_UPDATE_DEFER_NORMALIZE 16u /* with RFSB200_UPDATE_FUSED_ALLREDUCE on more than one rank: the kernel sends
+                                         its [sum w, sum w^2] pair to the peers and ends WITHOUT waiting for theirs; the
+                                         particle weights stay unnormalised until somebody needs them: the next
+                                         rfsb200_update (2-D plugin set) picks the pairs up from its mailbox during set-up
+                                         — they arrived a step ago — and divides the weights by the total while it loads
+                                         them (same division, same operands: bit-identical to the eager step); any other
+                                         consumer (rfsb200_get_weights, _update_host, _resample, _export_particles, ...)
+                                         or rfsb200_comm_resolve() runs the open normalisation first.  No rank waits for
+                                         the slowest one inside a step any more; ranks may drift by one step.  Meant for
+                                         the steps between two resampling decisions (minUpdatesBeforeResample_), where the
+                                         host does not look at the weights.  rfsb200_step_out of such a step holds the
+                                         LOCAL sums.  With RFSB200_UPDATE_NO_COMMIT the open weights are those of the
+                                         back buffer: a reader of that result closes them, the next update overwrites
+                                         them and only picks the pairs up.                                            */
 #define RFSB200_UPDATE_NO_NORMALIZE 2u /* stop after the local [sum w, sum w^2] reduction so the
                                          caller can all-reduce rfsb200_weight_sums_device() across
                                          GPUs and then call rfsb200_normalize()               */
@@ -348,6 +362,13 @@ int rfsb200_import_particles(rfsb200_ctx* ctx, const int32_t* slot /*[n] host*/,
  * RFSB200_UPDATE_FUSED_ALLREDUCE replaces the caller's all-reduce + rfsb200_normalize(). */
 int rfsb200_comm_export(rfsb200_ctx* ctx, void* handle64);
 int rfsb200_comm_connect(rfsb200_ctx* ctx, int32_t rank, int32_t world, const void* handles /*[world][64]*/);
+/* The same for contexts that live in ONE process (a host thread per GPU, or several shards on one device): the peers'
+ * mailboxes are reached by plain device pointers (peer access is enabled between different devices).  peers[rank] must be
+ * ctx; call it on every ctx of the group before the first fused update of any of them. */
+int rfsb200_comm_connect_local(rfsb200_ctx* ctx, int32_t rank, int32_t world, rfsb200_ctx* const* peers /*[world]*/);
+/* Runs the normalisation a RFSB200_UPDATE_DEFER_NORMALIZE step left open (one small kernel on the ctx stream; no-op if
+ * nothing is open).  Afterwards rfsb200_weight_sums_device() holds the global pair of that step. */
+int rfsb200_comm_resolve(rfsb200_ctx* ctx);
 /* Queues a barrier of the connected ranks on the ctx stream (one tiny kernel, flags through the peer mailboxes): every
  * rank leaves it within an NVLink round trip of the last one to arrive.  No-op for a single rank. */
 int rfsb200_comm_barrier(rfsb200_ctx* ctx);

@@ -21,6 +21,7 @@ UPDATE_NO_COMMIT = 1
 UPDATE_NO_NORMALIZE = 2
 UPDATE_FUSED_ALLREDUCE = 4
 UPDATE_STAGE_TIMES = 8
+UPDATE_DEFER_NORMALIZE = 16
 
 ERRORS = {0: "OK", -1: "EINVAL", -2: "ECUDA", -3: "ENOMEM", -4: "ECAPACITY", -5: "EUNSUPPORTED",
           -6: "ESTATE", -7: "ENODEVICE"}
@@ -162,6 +163,8 @@ _SIGS = {
     "rfsb200_comm_connect": (C.c_int, [_P, C.c_int32, C.c_int32, _P]),
     "rfsb200_comm_error": (C.c_int, [_P, C.POINTER(C.c_int32)]),
     "rfsb200_comm_barrier": (C.c_int, [_P]),
+    "rfsb200_comm_resolve": (C.c_int, [_P]),
+    "rfsb200_comm_connect_local": (C.c_int, [_P, C.c_int32, C.c_int32, _P]),
     "rfsb200_weight_sums_device": (C.c_int, [_P, C.POINTER(_P)]),
     "rfsb200_normalize": (C.c_int, [_P]),
     "rfsb200_get_weights": (C.c_int, [_P, C.c_int, _P]),

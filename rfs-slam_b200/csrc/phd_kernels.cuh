@@ -138,6 +138,14 @@ struct KParams {
   void* comm_peer[8];               // mailbox of every rank (own included), mapped into this process
   int* comm_error;                  // set to 1 if a peer did not arrive in time
   unsigned long long comm_timeout_ns;   // how long the last CTA waits for the peers (RFSB200_COMM_TIMEOUT_MS, default 2 s)
+  // deferred consumption of the cross-GPU sums (RFSB200_UPDATE_DEFER_NORMALIZE): a launch with comm_defer sends its pair
+  // to the peers and ends without waiting (weights stay unnormalised); the NEXT launch (comm_pending) finds the pairs of
+  // epoch comm_prev_epoch in its mailbox during set-up — they have been there for a whole step — and divides the incoming
+  // particle weights by their total while it loads them: the same division on the same operands as the eager
+  // normalisation, so the results are bit-identical, but no rank ever waits for the slowest one inside a step.
+  int comm_defer, comm_pending;   // comm_pending = number of ranks whose pair is to be picked up (0: nothing is open)
+  int comm_pending_scale;         // the open normalisation is that of the weights this launch reads (else: of a buffer it overwrites)
+  unsigned long long comm_prev_epoch;
   unsigned long long* stats_out;  // [13] totals/istats/mstats of the finished step, published by the last CTA
   // multi-feature weighting: global workspace of the assignment-sum DP for partitions beyond the on-chip tables,
   // 2 x (1 << dp_gmaxb) doubles per warp of the grid (NULL: none); dp_onchip = largest smaller side summed on chip
@@ -1364,22 +1372,24 @@ __device__ __forceinline__ void step_epilogue(const KParams<T>& p, int lane, int
         const int r = threadIdx.x;
         CommSlot* dst = reinterpret_cast<CommSlot*>(p.comm_peer[r]) + par * 8 + p.comm_rank;
         comm_send(dst, red[0][0], red[1][0], e);
-        const CommSlot* mine = reinterpret_cast<const CommSlot*>(p.comm_peer[p.comm_rank]) + par * 8;
-        const unsigned long long t0 = globaltimer_ns();
-        double a1 = 0, a2 = 0;
-        bool ok = true;
-        while (!comm_recv(mine + r, e, a1, a2)) {
-          if (globaltimer_ns() - t0 > p.comm_timeout_ns) { ok = false; break; }   // a peer never launched
-        }
-        if (ok) {
-          xs[0][r] = a1;
-          xs[1][r] = a2;
-        } else {
-          atomicAnd(&xok, 0);
+        if (!p.comm_defer) {
+          const CommSlot* mine = reinterpret_cast<const CommSlot*>(p.comm_peer[p.comm_rank]) + par * 8;
+          const unsigned long long t0 = globaltimer_ns();
+          double a1 = 0, a2 = 0;
+          bool ok = true;
+          while (!comm_recv(mine + r, e, a1, a2)) {
+            if (globaltimer_ns() - t0 > p.comm_timeout_ns) { ok = false; break; }   // a peer never launched
+          }
+          if (ok) {
+            xs[0][r] = a1;
+            xs[1][r] = a2;
+          } else {
+            atomicAnd(&xok, 0);
+          }
         }
       }
       __syncthreads();
-      if (threadIdx.x == 0) {
+      if (threadIdx.x == 0 && !p.comm_defer) {   // (deferred: the pair stays the local one; the next launch adds them up)
         double ta = 0, tb = 0;
         for (int r = 0; r < p.comm_world; r++) { ta += xs[0][r]; tb += xs[1][r]; }
         if (!xok) { *p.comm_error = 1; ta = __longlong_as_double(0x7ff8000000000000LL); tb = ta; }
@@ -1470,6 +1480,33 @@ __global__ void comm_barrier_kernel(const CommPeers peers, int rank, int world, 
       if (globaltimer_ns() - t0 > timeout_ns) { *comm_error = 1; break; }
     }
   }
+}
+
+// rfsb200_comm_resolve: the normalisation a deferred step (KParams::comm_defer) left open, for a consumer other than
+// the next update (the weights are read, resampled, exported ...): one CTA picks up the pairs of that epoch from the
+// mailbox, adds them in rank order and divides the weights by the total — the eager epilogue's arithmetic.
+__global__ void comm_resolve_kernel(const CommPeers peers, int rank, int world, unsigned long long epoch, double* w, int N,
+                                    double* sums, int* comm_error, unsigned long long timeout_ns) {
+  __shared__ double xs[2][8];
+  if ((int)threadIdx.x < world) {
+    const CommSlot* mine = reinterpret_cast<const CommSlot*>(peers.p[rank]) + (int)(epoch & 1ull) * 8;
+    const unsigned long long t0 = globaltimer_ns();
+    double a1 = 0, a2 = 0;
+    while (!comm_recv(mine + threadIdx.x, epoch, a1, a2)) {
+      if (globaltimer_ns() - t0 > timeout_ns) {
+        *comm_error = 1;
+        a1 = a2 = __longlong_as_double(0x7ff8000000000000LL);
+        break;
+      }
+    }
+    xs[0][threadIdx.x] = a1;
+    xs[1][threadIdx.x] = a2;
+  }
+  __syncthreads();
+  double ta = 0, tb = 0;
+  for (int r = 0; r < world; r++) { ta += xs[0][r]; tb += xs[1][r]; }
+  for (int i = threadIdx.x; i < N; i += blockDim.x) w[i] = w[i] / ta;
+  if (threadIdx.x == 0) { sums[0] = ta; sums[1] = tb; }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1621,6 +1658,22 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
     if (tid + nt < 3 * hin_early) hin_v1 = src[tid + nt];
     if (p.weight_h && tid < hin_early) hin_w = p.weight_h[hin_lo + tid];
   }
+  // ---- deferred cross-GPU sums of the previous step (KParams::comm_pending): thread r picks up rank r's pair from this
+  //      GPU's own mailbox (it arrived while the previous launch was still running or long before this one started)
+  __shared__ double prev_sum[8];
+  if ((int)threadIdx.x < p.comm_pending) {
+    const CommSlot* mine = reinterpret_cast<const CommSlot*>(p.comm_peer[p.comm_rank]) + (int)(p.comm_prev_epoch & 1ull) * 8;
+    const unsigned long long t0 = globaltimer_ns();
+    double a1 = 0, a2 = 0;
+    while (!comm_recv(mine + threadIdx.x, p.comm_prev_epoch, a1, a2)) {
+      if (globaltimer_ns() - t0 > p.comm_timeout_ns) {   // a peer never finished the previous step
+        *p.comm_error = 1;
+        a1 = __longlong_as_double(0x7ff8000000000000LL);
+        break;
+      }
+    }
+    prev_sum[threadIdx.x] = a1;
+  }
   // ---- the measurement batch and the corrector's window tables (once per CTA) ------------------
   // tabR[b] = set of measurements whose range bin is < b, tabB likewise on the bearing: the
   // measurements with range in [lo,hi] are a subset of tabR[bin(hi)+1] & ~tabR[bin(lo)].
@@ -1737,7 +1790,12 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
     if (p.pose_h) {   // (host-facing step) the inputs of this particle are on the device?  (flag read one particle ahead)
       if (!__shfl_sync(FULL, hin_ok, 0)) host_in_self_service(p, pi / hin_slice, hin_slice, lane);
     }
-    const double w_prev_particle = p.w_in[pi];
+    double w_prev_particle = p.w_in[pi];
+    if (p.comm_pending_scale) {   // ParticleFilter::normalizeWeights of the previous step, applied on the way in (rank order: same bits everywhere)
+      double total = 0;
+      for (int r = 0; r < p.comm_pending; r++) total += prev_sum[r];
+      w_prev_particle = w_prev_particle / total;
+    }
 
     T* cur = bufA;
     int nM = p.cnt_in[pi];

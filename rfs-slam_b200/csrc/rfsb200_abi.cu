@@ -70,6 +70,13 @@ struct rfsb200_ctx {
   unsigned long long comm_bar_epoch = 0;      // rfsb200_comm_barrier
   unsigned long long comm_timeout_ns = 2000000000ull;   // RFSB200_COMM_TIMEOUT_MS
   int* comm_error = nullptr;
+  // RFSB200_UPDATE_DEFER_NORMALIZE: the weights of st[comm_pending_buf] still wait for the sums of comm_pending_epoch
+  bool comm_local = false;                    // peers connected by rfsb200_comm_connect_local (plain pointers, nothing to close)
+  bool comm_pending = false;
+  unsigned long long comm_pending_epoch = 0;
+  int comm_pending_buf = 0;
+  bool consume_pending = false;               // the launch being prepared applies them on the way in (KParams::comm_pending)
+  bool consume_scale = false;                 //   ... to the weights it reads (else it only picks the pairs up: the open buffer is overwritten)
   int last_nZ = 0;                            // size of the measurement batch still held in Zdev
   int* flags = nullptr;
   double* sums = nullptr;                 // [2]
@@ -523,10 +530,18 @@ int launch_update(rfsb200_ctx* c, int nZ, int out_idx, unsigned flags) {
     p.w_host = nullptr;
     flags = (flags & ~RFSB200_UPDATE_FUSED_ALLREDUCE) | RFSB200_UPDATE_NO_NORMALIZE;
   }
+  p.comm_defer = 0; p.comm_pending = 0; p.comm_pending_scale = 0; p.comm_prev_epoch = 0;
   if (flags & RFSB200_UPDATE_FUSED_ALLREDUCE) {
     p.comm_world = c->comm_world;
     p.fused_normalize = 1;
     p.comm_epoch = c->comm_epoch + 1;   // the ctx moves on only when the launch has succeeded (below)
+    for (int r = 0; r < 8; r++) p.comm_peer[r] = c->comm_peer[r];
+    if ((flags & RFSB200_UPDATE_DEFER_NORMALIZE) && c->comm_world > 1) { p.comm_defer = 1; p.fused_normalize = 0; }
+  }
+  if (c->consume_pending) {   // the sums of the previous (deferred) step, applied to the weights on the way in
+    p.comm_pending = c->comm_world;
+    p.comm_pending_scale = c->consume_scale ? 1 : 0;
+    p.comm_prev_epoch = c->comm_pending_epoch;
     for (int r = 0; r < 8; r++) p.comm_peer[r] = c->comm_peer[r];
   }
   const int mf = f.use_cluster_process ? 0 : 1;
@@ -692,6 +707,8 @@ int do_predict_vp(rfsb200_ctx* c, const double* Q, int add_births, double birth_
 // ================================================================================================
 extern "C" {
 
+static int resolve_pending(rfsb200_ctx* c);
+
 int rfsb200_abi_version(void) { return RFSB200_ABI_VERSION; }
 
 int rfsb200_device_count(void) {
@@ -833,7 +850,7 @@ int rfsb200_destroy(rfsb200_ctx* c) {
   cudaFree(c->unused); cudaFree(c->nfov); cudaFree(c->flags);
   cudaFree(c->unused_alt); cudaFree(c->nfov_alt); cudaFree(c->src_dev);
   for (int r = 0; r < c->comm_world; r++)
-    if (r != c->comm_rank && c->comm_peer[r]) cudaIpcCloseMemHandle(c->comm_peer[r]);
+    if (r != c->comm_rank && c->comm_peer[r] && !c->comm_local) cudaIpcCloseMemHandle(c->comm_peer[r]);
   cudaFree(c->comm_mail); cudaFree(c->comm_error);
   cudaFree(c->sums); cudaFree(c->totals); cudaFree(c->istats); cudaFree(c->ticket);
   cudaFree(c->work_counter); cudaFree(c->stats_out); cudaFree(c->mstats);
@@ -966,6 +983,7 @@ int rfsb200_set_poses(rfsb200_ctx* c, const double* pose, const double* pose_cov
   if (mode < 0 || mode > 2 || (mode > 0 && !pose_cov)) return fail(c, RFSB200_EINVAL, "bad pose_cov_mode");
   CU(c, cudaSetDevice(c->device));
   double* dp = c->stg_small;
+  if (weight) { if (int rcp = resolve_pending(c)) return rcp; }   // (the new weights replace normalised ones)
   double* dcov = dp + (size_t)c->N * 3;
   CU(c, cudaMemcpyAsync(dp, pose, (size_t)c->N * 3 * 8, cudaMemcpyHostToDevice, c->stream));
   if (mode == 1) CU(c, cudaMemcpyAsync(dcov, pose_cov, 6 * 8, cudaMemcpyHostToDevice, c->stream));
@@ -1028,6 +1046,18 @@ static int murty_postprocess(rfsb200_ctx* c, int out_idx) {
   return RFSB200_OK;
 }
 
+// the normalisation a RFSB200_UPDATE_DEFER_NORMALIZE step left open (see KParams::comm_defer)
+static int resolve_pending(rfsb200_ctx* c) {
+  if (!c->comm_pending) return RFSB200_OK;
+  CommPeers peers{};
+  for (int r = 0; r < 8; r++) peers.p[r] = c->comm_peer[r];
+  comm_resolve_kernel<<<1, 1024, 0, c->stream>>>(peers, c->comm_rank, c->comm_world, c->comm_pending_epoch,
+                                                 c->st[c->comm_pending_buf].weight, c->N, c->sums, c->comm_error, c->comm_timeout_ns);
+  CU(c, cudaGetLastError());
+  c->comm_pending = false;
+  return RFSB200_OK;
+}
+
 static int enqueue_update(rfsb200_ctx* c, const double* Z, int32_t nZ, uint32_t flags, bool timed, int* launches_out) {
   if (!c->have_model || !c->have_cfg || !c->have_maps || !c->have_poses)
     return fail(c, RFSB200_ESTATE, "update before set_model / set_filter_cfg / upload_maps / set_poses");
@@ -1042,6 +1072,21 @@ static int enqueue_update(rfsb200_ctx* c, const double* Z, int32_t nZ, uint32_t 
     const int rc0 = (c->prec == 32) ? configure_launch<float>(c, mf) : configure_launch<double>(c, mf);
     if (rc0) return rc0;
   }
+  if ((flags & RFSB200_UPDATE_DEFER_NORMALIZE) && !(flags & RFSB200_UPDATE_FUSED_ALLREDUCE))
+    return fail(c, RFSB200_EINVAL, "RFSB200_UPDATE_DEFER_NORMALIZE needs RFSB200_UPDATE_FUSED_ALLREDUCE");
+  // Sums a deferred step left open.  The 2-D kernels pick the pairs up during set-up (that wait is what keeps the ranks
+  // within one step of each other) and, if the open weights are the ones this step reads (the committed state), divide
+  // them by the total on the way in; if they are those of the back buffer (a NO_COMMIT step) this launch overwrites them
+  // and there is nothing to apply.  Everything else closes the open normalisation first.
+  const bool open_front = c->comm_pending && c->comm_pending_buf == c->front;
+  c->consume_pending = c->comm_pending && c->ld == 2 && !c->hin_weight &&
+                       !(open_front && (flags & RFSB200_UPDATE_NO_COMMIT) && (flags & RFSB200_UPDATE_DEFER_NORMALIZE));   // (two would be open)
+  c->consume_scale = c->consume_pending && open_front;
+  if (c->comm_pending && !c->consume_pending) {
+    const int rc0 = resolve_pending(c);
+    if (rc0) return rc0;
+    launches++;
+  }
   if (timed) CU(c, cudaEventRecord(c->ev0, c->stream));
   const int out_idx = c->front ^ 1;
   if ((flags & RFSB200_UPDATE_FUSED_ALLREDUCE) && c->comm_world > 1 && !c->comm_peer[0])
@@ -1050,7 +1095,15 @@ static int enqueue_update(rfsb200_ctx* c, const double* Z, int32_t nZ, uint32_t 
     return fail(c, RFSB200_EUNSUPPORTED, "murty_compat needs the weights on the host before they are summed: use "
                                          "RFSB200_UPDATE_NO_NORMALIZE + all-reduce + rfsb200_normalize across ranks");
   int rc = (c->prec == 32) ? launch_update<float>(c, nZ, out_idx, flags) : launch_update<double>(c, nZ, out_idx, flags);
+  const bool consumed = c->consume_pending;
+  c->consume_pending = false;
   if (rc) return rc;
+  if (consumed && !(c->consume_scale && (flags & RFSB200_UPDATE_NO_COMMIT))) c->comm_pending = false;   // (an uncommitted step leaves the state open)
+  if ((flags & RFSB200_UPDATE_FUSED_ALLREDUCE) && (flags & RFSB200_UPDATE_DEFER_NORMALIZE) && c->comm_world > 1 && !murty_active(c)) {
+    c->comm_pending = true;
+    c->comm_pending_epoch = c->comm_epoch;   // (already advanced by the launch)
+    c->comm_pending_buf = out_idx;
+  }
   launches++;
   c->last_out = out_idx;
   c->last_nZ = nZ;
@@ -1124,6 +1177,11 @@ int rfsb200_update_host(rfsb200_ctx* c, const double* pose, const double* pose_c
                         int32_t* nfov_out, rfsb200_step_out* out) {
   if (!c || !pose) return fail(c, RFSB200_EINVAL, "NULL argument");
   if (out) memset(out, 0, sizeof(*out));
+  if (flags & RFSB200_UPDATE_DEFER_NORMALIZE) return fail(c, RFSB200_EINVAL, "the host-facing step returns normalised weights: no RFSB200_UPDATE_DEFER_NORMALIZE");
+  if (c->comm_pending) {
+    CU(c, cudaSetDevice(c->device));
+    if (int rcp = resolve_pending(c)) return rcp;
+  }
   if (c->zero_copy && !murty_active(c) && nZ > 0 && nZ <= c->dims.z_capacity && Z && mode >= 0 && mode <= 2 && (mode == 0 || pose_cov)) {
     // Pinned (device-accessible) caller buffers: ONE small kernel reads poses / weights / covariance / Z from host
     // memory, and the update kernel (or normalize_kernel) stores weights, unused masks, in-FOV counts and the step
@@ -1426,6 +1484,7 @@ int rfsb200_resample(rfsb200_ctx* c, const int32_t* map_src, const int32_t* aux_
     if (map_src[i] < 0 || map_src[i] >= c->N || (aux_src && (aux_src[i] < -1 || aux_src[i] >= c->N)))
       return fail(c, RFSB200_EINVAL, "resample source %d of particle %d out of range", map_src[i], i);
   CU(c, cudaSetDevice(c->device));
+  if (int rcp = resolve_pending(c)) return rcp;
   CU(c, cudaMemcpyAsync(c->src_dev, map_src, (size_t)c->N * 4, cudaMemcpyHostToDevice, c->stream));
   if (aux_src) CU(c, cudaMemcpyAsync(c->src_dev + c->N, aux_src, (size_t)c->N * 4, cudaMemcpyHostToDevice, c->stream));
   const StateBuf& in = c->st[c->front];
@@ -1474,6 +1533,7 @@ int rfsb200_export_particles(rfsb200_ctx* c, const int32_t* idx, int32_t n, void
   for (int k = 0; k < n; k++)
     if (idx[k] < 0 || idx[k] >= c->N) return fail(c, RFSB200_EINVAL, "particle index %d out of range", idx[k]);
   CU(c, cudaSetDevice(c->device));
+  if (int rcp = resolve_pending(c)) return rcp;
   const StateBuf& s = c->st[c->front];
   // a heavy shard may have to export more copies than it holds particles: in chunks of the 2N-entry index scratch
   const int chunk = 2 * c->N;
@@ -1505,6 +1565,7 @@ int rfsb200_import_particles(rfsb200_ctx* c, const int32_t* slot, int32_t n, con
   for (int k = 0; k < n; k++)
     if (slot[k] < 0 || slot[k] >= c->N) return fail(c, RFSB200_EINVAL, "slot %d out of range", slot[k]);
   CU(c, cudaSetDevice(c->device));
+  if (int rcp = resolve_pending(c)) return rcp;
   CU(c, cudaStreamSynchronize(c->stream));
   CU(c, cudaMemcpyAsync(c->src_dev, slot, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
   StateBuf& s = c->st[c->front];
@@ -1534,6 +1595,7 @@ int rfsb200_comm_export(rfsb200_ctx* c, void* handle64) {
   CU(c, cudaMemset(c->comm_error, 0, 4));
   c->comm_epoch = 0;
   c->comm_bar_epoch = 0;
+  c->comm_pending = false;
   cudaIpcMemHandle_t h;
   CU(c, cudaIpcGetMemHandle(&h, c->comm_mail));
   memcpy(handle64, &h, 64);
@@ -1553,9 +1615,49 @@ int rfsb200_comm_connect(rfsb200_ctx* c, int32_t rank, int32_t world, const void
     CU(c, cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
     c->comm_peer[r] = ptr;
   }
+  c->comm_local = false;
   c->comm_rank = rank;
   c->comm_world = world;
   return RFSB200_OK;
+}
+
+int rfsb200_comm_connect_local(rfsb200_ctx* c, int32_t rank, int32_t world, rfsb200_ctx* const* peers) {
+  if (!c || !peers) return fail(c, RFSB200_EINVAL, "NULL argument");
+  if (world < 1 || world > 8 || rank < 0 || rank >= world) return fail(c, RFSB200_EINVAL, "rank %d / world %d out of range (world <= 8)", rank, world);
+  if (peers[rank] != c) return fail(c, RFSB200_EINVAL, "peers[rank] must be this ctx");
+  CU(c, cudaSetDevice(c->device));
+  CU(c, cudaStreamSynchronize(c->stream));
+  // a (re)connection starts from epoch 0 with an empty mailbox (as rfsb200_comm_export does for the IPC route); every
+  // ctx of the group must be connected before the first of them runs a fused update
+  CU(c, cudaMemset(c->comm_mail, 0xff, COMM_BANKS * 8 * sizeof(CommSlot)));
+  CU(c, cudaMemset(c->comm_error, 0, 4));
+  c->comm_epoch = 0;
+  c->comm_bar_epoch = 0;
+  c->comm_pending = false;
+  for (int r = 0; r < world; r++) {
+    if (!peers[r]) return fail(c, RFSB200_EINVAL, "NULL peer %d", r);
+#if !defined(RFSB200_SIMT_HOST)   // (the host interpreter of tests/simt has one "device")
+    if (peers[r]->device != c->device) {
+      int can = 0;
+      CU(c, cudaDeviceCanAccessPeer(&can, c->device, peers[r]->device));
+      if (!can) return fail(c, RFSB200_EUNSUPPORTED, "no peer access from device %d to device %d", c->device, peers[r]->device);
+      const cudaError_t e = cudaDeviceEnablePeerAccess(peers[r]->device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CU(c, e);
+      (void)cudaGetLastError();
+    }
+#endif
+    c->comm_peer[r] = peers[r]->comm_mail;
+  }
+  c->comm_local = true;
+  c->comm_rank = rank;
+  c->comm_world = world;
+  return RFSB200_OK;
+}
+
+int rfsb200_comm_resolve(rfsb200_ctx* c) {
+  if (!c) return fail(nullptr, RFSB200_EINVAL, "NULL ctx");
+  CU(c, cudaSetDevice(c->device));
+  return resolve_pending(c);
 }
 
 int rfsb200_comm_barrier(rfsb200_ctx* c) {
@@ -1591,6 +1693,7 @@ int rfsb200_weight_sums_device(rfsb200_ctx* c, void** p) {
 int rfsb200_normalize(rfsb200_ctx* c) {
   if (!c) return fail(nullptr, RFSB200_EINVAL, "NULL ctx");
   CU(c, cudaSetDevice(c->device));
+  if (int rcp = resolve_pending(c)) return rcp;
   normalize_kernel<<<(c->N + 255) / 256, 256, 0, c->stream>>>(c->st[c->last_out].weight, c->sums, c->N, nullptr);
   CU(c, cudaGetLastError());
   return RFSB200_OK;
@@ -1601,6 +1704,7 @@ static int which_buf(rfsb200_ctx* c, int which) { return which == 0 ? c->front :
 int rfsb200_get_weights(rfsb200_ctx* c, int which, double* w) {
   if (!c || !w) return fail(c, RFSB200_EINVAL, "NULL argument");
   CU(c, cudaSetDevice(c->device));
+  if (int rcp = resolve_pending(c)) return rcp;
   CU(c, cudaMemcpyAsync(w, c->st[which_buf(c, which)].weight, (size_t)c->N * 8, cudaMemcpyDeviceToHost, c->stream));
   CU(c, cudaStreamSynchronize(c->stream));
   return RFSB200_OK;

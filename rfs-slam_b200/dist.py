@@ -135,9 +135,14 @@ class ShardedUpdater:
         # run the library on torch's current stream so kernels and the collective are ordered
         self.up.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
 
-    def step(self, Z, flags: int = 0, want_stats: bool = False):
+    def step(self, Z, flags: int = 0, want_stats: bool = False, defer: bool = False):
+        """defer (fused path only): the kernel sends its sums and ends without waiting for the peers'; the next step() picks
+        them up while it loads the weights (bit-identical results), resolve() or any reader of the weights closes the last
+        one.  For the steps between two resampling decisions, where nobody looks at the weights."""
         from . import capi
         if self.fused:   # one launch: update + cross-GPU sum over NVLink + normalisation
+            if defer and not want_stats:
+                return self.up.update(Z, flags=flags | capi.UPDATE_FUSED_ALLREDUCE | capi.UPDATE_DEFER_NORMALIZE, want_stats=False)
             so = self.up.update(Z, flags=flags | capi.UPDATE_FUSED_ALLREDUCE, want_stats=want_stats)
             if so is not None and not np.isfinite(so.sum_w):
                 self.check_comm()
@@ -167,6 +172,11 @@ class ShardedUpdater:
             self.up.get_unused(unused_out, nfov_out)
         return None
 
+
+    def resolve(self):
+        """Closes a deferred step: afterwards the weights are normalised and the sums are the global ones."""
+        if self.fused:
+            self.up.comm_resolve()
 
     def check_comm(self):
         """Raises if a peer did not arrive in some fused update since the last check (the sums of that step are NaN).

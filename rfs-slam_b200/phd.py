@@ -284,6 +284,15 @@ class PHDUpdater:
         """Barrier of the connected ranks on the ctx stream (rfsb200_comm_barrier)."""
         _check(self.lib, self.ctx, self.lib.rfsb200_comm_barrier(self.ctx), "comm_barrier")
 
+    def comm_connect_local(self, rank: int, world: int, updaters):
+        """Connects contexts of this process (rfsb200_comm_connect_local); updaters = the PHDUpdater of every rank, in order."""
+        arr = (C.c_void_p * world)(*[u.ctx for u in updaters])
+        _check(self.lib, self.ctx, self.lib.rfsb200_comm_connect_local(self.ctx, rank, world, C.cast(arr, C.c_void_p)), "comm_connect_local")
+
+    def comm_resolve(self):
+        """Runs the normalisation a deferred step (UPDATE_DEFER_NORMALIZE) left open, if any (rfsb200_comm_resolve)."""
+        _check(self.lib, self.ctx, self.lib.rfsb200_comm_resolve(self.ctx), "comm_resolve")
+
     def comm_error(self) -> bool:
         f = C.c_int32()
         _check(self.lib, self.ctx, self.lib.rfsb200_comm_error(self.ctx, C.byref(f)), "comm_error")

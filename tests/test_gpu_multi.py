@@ -107,3 +107,83 @@ def test_particle_exchange_between_two_contexts_on_one_gpu(cuda_required, dim):
     assert np.array_equal(np.concatenate([ranks[r].get_weights() for r in range(world)]), rweights)
     for u in ranks + [one]:
         u.close()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_deferred_cross_gpu_sums_between_contexts_on_one_gpu(cuda_required, world):
+    """RFSB200_UPDATE_DEFER_NORMALIZE with the "ranks" as contexts of this process on ONE device (rfsb200_comm_connect_local),
+    driven one after the other — possible because a deferred step never waits for a peer that is running at the same time:
+    it sends its [sum w, sum w^2] and ends; the next step finds the pairs of the previous epoch in its mailbox and divides
+    the weights by their total while it loads them.  Against the same shards stepped with the normalisation done between
+    the steps (local sums added in rank order on the host, w / total written back): weights and maps identical bit for
+    bit after every step, whether the open normalisation is closed by the next update, by rfsb200_comm_resolve or by a
+    reader of the weights."""
+    import numpy as np
+    from rfs_slam_b200 import capi, synth
+    from rfs_slam_b200.phd import PHDUpdater
+    wl = synth.make_workload(N=90, nM=40, nZ=10, use_cluster_process=1, config_id=97)
+    shards = [wl.shard(r, world) for r in range(world)]
+    rng = np.random.default_rng(5)
+    Zs = [wl.Z.reshape(-1, 2) + rng.normal(0, 0.01, (wl.nZ, 2)) for _ in range(5)]
+
+    def fresh():
+        ups = []
+        for sh in shards:
+            u = PHDUpdater(sh.N, gm_capacity=128, precision=32)
+            u.load_workload(sh)
+            ups.append(u)
+        return ups
+
+    # path B: eager arithmetic spelled out on the host
+    B = fresh()
+    want = []
+    for Z in Zs:
+        local = [u.update(Z, flags=capi.UPDATE_NO_NORMALIZE, want_stats=True).sum_w for u in B]
+        total = 0.0
+        for v in local:
+            total += v
+        ws = []
+        for u, sh in zip(B, shards):
+            w = u.get_weights() / total
+            u.set_poses(sh.pose, sh.pose_cov, w)
+            ws.append(w)
+        want.append((np.concatenate(ws), [u.download_maps() for u in B]))
+
+    A = fresh()
+    for r, u in enumerate(A):
+        u.comm_connect_local(r, world, A)
+    F = capi.UPDATE_FUSED_ALLREDUCE | capi.UPDATE_DEFER_NORMALIZE
+    for k, Z in enumerate(Zs):
+        for u in A:
+            u.update(Z, flags=F)          # step k of every rank; the previous step's sums are applied on the way in
+        if k == 1:                        # closed explicitly ...
+            for u in A:
+                u.comm_resolve()
+        if k in (1, 2, 4):                # ... or by reading the weights (k = 2, 4); k = 0, 3: by the next update
+            got = np.concatenate([u.get_weights() for u in A])
+            assert np.array_equal(got, want[k][0]), k
+            assert got.sum() == pytest.approx(1.0, abs=1e-12)
+        for u, (cnt, mean, cov, w) in zip(A, want[k][1]):
+            c2, m2, cv2, w2 = u.download_maps()
+            assert np.array_equal(c2, cnt) and np.array_equal(m2, mean) and np.array_equal(cv2, cov) and np.array_equal(w2, w), k
+    assert not any(u.comm_error() for u in A)
+    # an eager fused step cannot follow on one device (it would wait for a peer that cannot run): the flag combinations
+    # that make no sense are refused
+    with pytest.raises(RuntimeError):
+        A[0].update(Zs[0], flags=capi.UPDATE_DEFER_NORMALIZE)
+    # uncommitted deferred steps (what bench.py times): the open weights are those of the back buffer; the next step
+    # overwrites them after picking the pairs up, a reader of the result closes them
+    for u in A + B:
+        u.comm_resolve()
+    for k in range(3):
+        for u in A:
+            u.update(Zs[k], flags=F | capi.UPDATE_NO_COMMIT)
+    got = np.concatenate([u.get_weights(1) for u in A])
+    local = [u.update(Zs[2], flags=capi.UPDATE_NO_NORMALIZE | capi.UPDATE_NO_COMMIT, want_stats=True).sum_w for u in B]
+    total = 0.0
+    for v in local:
+        total += v
+    assert np.array_equal(got, np.concatenate([u.get_weights(1) / total for u in B]))
+    assert not any(u.comm_error() for u in A)
+    for u in A + B:
+        u.close()

@@ -114,7 +114,7 @@ def _gpu_tests(module_name, skip):
 
 @pytest.mark.parametrize("fn,kw", _gpu_tests("test_gpu_parity", skip=("randomised",)) + _gpu_tests("test_gpu_vp", skip=()) +
                          _gpu_tests("test_gpu_fullsize", skip=("c4_every_shard",)) + _gpu_tests("test_motion", skip=()) +
-                         _gpu_tests("test_gpu_births", skip=()))
+                         _gpu_tests("test_gpu_births", skip=()) + _gpu_tests("test_gpu_multi", skip=("equals_nccl", "independent_of_the_number", "particle_exchange")))
 def test_gpu_test_bodies_on_the_interpreted_kernels(simt_lib, fn, kw):
     """The `-m gpu` parity tests, bodies and sizes unchanged, with the binding pointed at the interpreter build: the
     reference's golden vectors and the oracle for both plugin sets and precisions, culled against exhaustive merge,
