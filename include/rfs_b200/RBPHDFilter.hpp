@@ -914,8 +914,10 @@ void RBPHDFilter<R, L, M, K>::addBirthGaussiansHost() {
  * overwritten through setParticlePose since the update) and, after a resampling, the parent slots go up. */
 template <class R, class L, class M, class K>
 void RBPHDFilter<R, L, M, K>::addBirthGaussiansDevice() {
-  const bool anyCov = gatherPoses();
-  check(rfsb200_set_poses(ctx_, &hPose_[0], anyCov ? &hPoseCov_[0] : NULL, anyCov ? 2 : 0, NULL), "rfsb200_set_poses");
+  if (unusedFresh_) {   /* (with every mask consumed only the check pass runs, which does not look at the poses) */
+    const bool anyCov = gatherPoses();
+    check(rfsb200_set_poses(ctx_, &hPose_[0], anyCov ? &hPoseCov_[0] : NULL, anyCov ? 2 : 0, NULL), "rfsb200_set_poses");
+  }
   rfsb200_birth_cfg b;
   memset(&b, 0, sizeof(b));
   b.birth_weight = config.birthGaussianWeight_;
