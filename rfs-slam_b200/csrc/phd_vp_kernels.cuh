@@ -181,14 +181,25 @@ __device__ __forceinline__ bool vp_pd2_fast_code(const VPGeom& g, const VPFast& 
   int numPoints = 0;
   const float minrange = dist - mr - 0.18f;
   const float e_s = e_dist + 2e-6f;
-  if ((maxb - minb + 720) % 720 > 0) {
-    for (int b = minb; b != maxb; b = (b + 1) % 720) {
-      if (b >= g.scan_n) continue;   // (see vp_pd2: such a beam counts no point)
-      const float s = f.scan[b];
-      if (s == 0.0f) { numPoints++; continue; }
-      if (fabsf(s - minrange) < e_s + 3e-7f * s) return false;
-      if (s > minrange) numPoints++;
+  {
+    // beams minb, minb + 1, ... (mod 720) up to maxb - 1: four per trip, their loads in flight together, no branches
+    // (a return too close to minrange makes the whole evaluation undecided wherever it sits, so it is only a flag)
+    const int len = (maxb - minb + 720) % 720;
+    bool undecided = false;
+    for (int i0 = 0; i0 < len; i0 += 4) {
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const int i = i0 + k;
+        int b = minb + i;
+        b = b >= 720 ? b - 720 : b;
+        const bool on = i < len && b < g.scan_n;   // (see vp_pd2: a beam beyond the scan counts no point)
+        const float s = f.scan[on ? b : 0];
+        const bool none = s == 0.0f;
+        undecided = undecided || (on && !none && fabsf(s - minrange) < e_s + 3e-7f * s);
+        numPoints += (on && (none || s > minrange)) ? 1 : 0;
+      }
     }
+    if (undecided) return false;
   }
   if (numPoints >= g.pd_n) numPoints = g.pd_n - 1;
   if (g.pd[numPoints] == 0.0) close = false;
