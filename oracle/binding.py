@@ -328,6 +328,8 @@ class SeqIO(C.Structure):
         ("neff_threshold", C.c_double), ("precision", C.c_int32), ("seed48", C.c_uint32),
         ("cap_total", C.c_int64), ("count_out", C.c_void_p), ("mean_out", C.c_void_p), ("cov_out", C.c_void_p),
         ("w_out", C.c_void_p), ("weight_out", C.c_void_p), ("n_resampled", C.c_void_p), ("gm_size_trace", C.c_void_p),
+        ("birth_count_thr", C.c_uint32), ("birth_check_thr", C.c_uint32), ("birth_cur_thr", C.c_uint32), ("birth_reserved", C.c_uint32),
+        ("birth_support_dist", C.c_double),
     ]
 
 
@@ -336,7 +338,7 @@ def have_seq() -> bool:
 
 
 def run_sequence(which: str, poses, Z, nZ, model: dict, cfg: dict, *, pose_cov, Q_lmk=None, neff_threshold=0.0,
-                 min_updates_before_resample=1, precision=64, seed48=1):
+                 min_updates_before_resample=1, precision=64, seed48=1, births=None):
     """which = 'ref' (the reference's RBPHDFilter.hpp) or 'b200' (include/rfs_b200/RBPHDFilter.hpp).
     poses [K][N][3], Z [K][nZmax][2], nZ [K].  Returns (Result, n_resampled, gm_size_trace)."""
     lib = C.CDLL(SEQ_REF_LIB if which == "ref" else SEQ_B200_LIB)
@@ -368,6 +370,9 @@ def run_sequence(which: str, poses, Z, nZ, model: dict, cfg: dict, *, pose_cov, 
     io.min_updates_before_resample = min_updates_before_resample
     io.neff_threshold, io.precision, io.seed48 = neff_threshold, precision, seed48
     io.cap_total = cap_total
+    if births:   # candidate-list births: dict(count_thr, check_thr, cur_count_thr, support_dist)
+        io.birth_count_thr, io.birth_check_thr = births["count_thr"], births["check_thr"]
+        io.birth_cur_thr, io.birth_support_dist = births["cur_count_thr"], births["support_dist"]
     for k, a in out.items():
         setattr(io, k, a.ctypes.data)
     rc = fn(C.byref(io))

@@ -60,6 +60,9 @@ struct seq_io {
   double* weight_out;      /* [N] */
   int32_t* n_resampled;    /* [1] number of updates after which a resampling happened */
   int32_t* gm_size_trace;  /* [n_steps] getGMSize(0) after each update */
+  /* candidate-list births (include/RBPHDFilter.hpp:1023-1080): birth_count_thr == 1 is the direct form */
+  uint32_t birth_count_thr, birth_check_thr, birth_cur_thr, birth_reserved;
+  double birth_support_dist;
 };
 
 #ifdef SEQ_B200
@@ -96,6 +99,12 @@ extern "C" int SEQ_ENTRY(seq_io* io) {
     f.getLmkProcessModel()->setNoise(Q);
   }
   f.config.birthGaussianWeight_ = io->birth_w;
+  if (io->birth_count_thr > 0) {
+    f.config.birthGaussianMeasurementCountThreshold_ = io->birth_count_thr;
+    f.config.birthGaussianMeasurementCheckThreshold_ = io->birth_check_thr;
+    f.config.birthGaussianCurrentMeasurementCountThreshold_ = io->birth_cur_thr;
+    f.config.birthGaussianMeasurementSupportDist_ = io->birth_support_dist;
+  }
   f.config.newGaussianCreateInnovMDThreshold_ = io->gate;
   f.config.importanceWeightingEvalPointCount_ = io->n_eval;
   f.config.importanceWeightingEvalPointGuassianWeight_ = io->eval_w;

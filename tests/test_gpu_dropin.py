@@ -47,15 +47,21 @@ def _scenario(N=40, K=10, n_lmk=60, nZ_max=16, seed=5, sc=1):
     return md, fc, poses, Z, nZ
 
 
+# births: None = the direct form (birthGaussianMeasurementCountThreshold_ == 1, the 2-D simulator's setting); a dict = the
+# candidate-list form (include/RBPHDFilter.hpp:1023-1080), which the drop-in runs on the device (rfsb200_birth_candidates)
+CANDIDATES = dict(count_thr=2, check_thr=3, cur_count_thr=1, support_dist=2.0)
+
+
+@pytest.mark.parametrize("births", [None, CANDIDATES], ids=["direct_births", "candidate_lists"])
 @pytest.mark.parametrize("sc", [1, 0])
 @pytest.mark.parametrize("resample", [False, True])
-def test_dropin_header_matches_reference_class(cuda_required, sc, resample):
+def test_dropin_header_matches_reference_class(cuda_required, sc, resample, births):
     from oracle import binding as ob
     if not ob.have_seq():
         pytest.skip("oracle/_ref/libseq_{ref,b200}.so not built (needs /root/reference at build time)")
     md, fc, poses, Z, nZ = _scenario(sc=sc)
     kw = dict(pose_cov=[3e-5, 0, 0, 3e-5, 0, 3e-5], Q_lmk=[1e-5, 0, 0, 1e-5],
-              neff_threshold=(float(poses.shape[1]) if resample else 0.0), seed48=7)
+              neff_threshold=(float(poses.shape[1]) if resample else 0.0), seed48=7, births=births)
     ref, nres_ref, trace_ref = ob.run_sequence("ref", poses, Z, nZ, md, fc, **kw)
     got, nres, trace = ob.run_sequence("b200", poses, Z, nZ, md, fc, precision=64, **kw)
     assert nres == nres_ref and (nres > 0) == resample

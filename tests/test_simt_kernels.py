@@ -174,17 +174,18 @@ _DROPIN_SCRIPT = """
 import sys
 sys.path.insert(0, {root!r}); sys.path.insert(0, {tests!r})
 import test_gpu_dropin as t
-for sc in (1, 0):
-    for resample in (False, True):
-        t.test_dropin_header_matches_reference_class(None, sc, resample)
+for births in (None, t.CANDIDATES):
+    for sc in (1, 0):
+        for resample in (False, True):
+            t.test_dropin_header_matches_reference_class(None, sc, resample, births)
 print("dropin sequences OK")
 """
 
 
 def test_dropin_header_against_the_reference_class_with_interpreted_kernels(simt_lib):
     """the body of tests/test_gpu_dropin.py — the drop-in C++ header against the reference class it replaces on scripted
-    sequences (births, landmark process noise, resampling with the same drand48 stream, an empty measurement set), both
-    weightings, both precisions — in a fresh process whose rfsb200_* symbols are bound to the interpreter build"""
+    sequences (births in the direct and in the candidate-list form, landmark process noise, resampling with the same
+    drand48 stream, an empty measurement set), both weightings, both precisions — in a fresh process whose rfsb200_* symbols are bound to the interpreter build"""
     from oracle import binding as ob
     if not ob.have_seq():
         pytest.skip("oracle/_ref/libseq_{ref,b200}.so not built (needs /root/reference at build time)")
