@@ -31,6 +31,9 @@ for case in range(n_cases):
                # last bit of 1 / sum w^2 whenever all weights are equal (e.g. every map still empty), which a 1e-13
                # relative difference in the common weight flips
                neff_threshold=(0.98 * float(poses.shape[1]) if resample else 0.0), seed48=int(rng.integers(1, 1000)))
+    if rng.random() < 0.5:   # the candidate-list form of addBirthGaussians (on the device in the drop-in) with random thresholds
+        run["births"] = dict(count_thr=int(rng.integers(2, 5)), check_thr=int(rng.integers(0, 6)), cur_count_thr=int(rng.integers(0, 4)),
+                             support_dist=float(rng.uniform(0.5, 3.0)))
     ref, nres_ref, trace_ref = ob.run_sequence("ref", poses, Z, nZ, md, fc, **run)
     got, nres, trace = ob.run_sequence("b200", poses, Z, nZ, md, fc, precision=64, **run)
     ok = nres == nres_ref and np.array_equal(trace, trace_ref) and np.array_equal(got.count, ref.count)
@@ -39,6 +42,6 @@ for case in range(n_cases):
         ok = (not r["bad"]) and np.allclose(got.weight, ref.weight, rtol=1e-8, atol=0)
     if not ok:
         bad += 1
-        print(f"CASE {case} FAILED: kw={kw} resample={resample} seed48={run['seed48']} nres {nres} / {nres_ref}")
+        print(f"CASE {case} FAILED: kw={kw} resample={resample} seed48={run['seed48']} births={run.get('births')} nres {nres} / {nres_ref}")
 print(f"{n_cases} random sequences, {bad} with differences")
 sys.exit(1 if bad else 0)
