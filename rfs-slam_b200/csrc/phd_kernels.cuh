@@ -2139,11 +2139,30 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
           __syncwarp();
           T* tmp = reinterpret_cast<T*>(aux);   // [W] words; T = double uses mf scratch instead
           if constexpr (sizeof(T) == 8) tmp = reinterpret_cast<T*>(ms.keys) + W;   // behind the keys, inside the merge scratch
-          for (int pl = 0; pl < 7; pl++) {
-            for (int k = lane; k < n; k += 32) tmp[k] = cur[pl * W + perm[k]];
-            __syncwarp();
-            for (int k = lane; k < n; k += 32) cur[pl * W + k] = tmp[k];
-            __syncwarp();
+          if constexpr (WT != 0 && WT <= 256 && sizeof(T) == 4) {
+            // compile-time capacity: a lane's (at most 8) source positions and the values of one plane live in
+            // registers — gather, barrier, store; no temporary plane, the permutation is read once for all planes
+            constexpr int KPL = WT / 32;
+            int pk[KPL];
+#pragma unroll
+            for (int j = 0; j < KPL; j++) pk[j] = (lane + 32 * j < n) ? (int)perm[lane + 32 * j] : 0;
+            for (int pl = 0; pl < 7; pl++) {
+              T v[KPL];
+#pragma unroll
+              for (int j = 0; j < KPL; j++) v[j] = cur[pl * W + pk[j]];
+              __syncwarp();
+#pragma unroll
+              for (int j = 0; j < KPL; j++)
+                if (lane + 32 * j < n) cur[pl * W + lane + 32 * j] = v[j];
+              __syncwarp();
+            }
+          } else {
+            for (int pl = 0; pl < 7; pl++) {
+              for (int k = lane; k < n; k += 32) tmp[k] = cur[pl * W + perm[k]];
+              __syncwarp();
+              for (int k = lane; k < n; k += 32) cur[pl * W + k] = tmp[k];
+              __syncwarp();
+            }
           }
         }
         // eval points (:747-762): sorted order, w >= min weight, raw Pd > 0, first nEvalCfg

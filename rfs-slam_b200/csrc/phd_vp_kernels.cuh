@@ -778,12 +778,30 @@ phd_update_vp_kernel(const __grid_constant__ VPParams<T> vp) {
             for (int k = lane; k < n; k += 32) order[k] = (unsigned short)aux[k];
           }
           __syncwarp();
-          T* tmp = sort_tmp;
-          for (int pl = 0; pl < NPL; pl++) {
-            for (int k = lane; k < n; k += 32) tmp[k] = cur[pl * W + order[k]];
-            __syncwarp();
-            for (int k = lane; k < n; k += 32) cur[pl * W + k] = tmp[k];
-            __syncwarp();
+          if (sizeof(T) == 4 && n <= 256) {
+            // a lane's (at most 8) source positions and its values of one plane in registers: gather, barrier, store —
+            // no temporary plane, the permutation is read once for all planes
+            int pk[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) pk[j] = (lane + 32 * j < n) ? (int)order[lane + 32 * j] : 0;
+            for (int pl = 0; pl < NPL; pl++) {
+              T v[8];
+#pragma unroll
+              for (int j = 0; j < 8; j++) v[j] = cur[pl * W + pk[j]];
+              __syncwarp();
+#pragma unroll
+              for (int j = 0; j < 8; j++)
+                if (lane + 32 * j < n) cur[pl * W + lane + 32 * j] = v[j];
+              __syncwarp();
+            }
+          } else {
+            T* tmp = sort_tmp;
+            for (int pl = 0; pl < NPL; pl++) {
+              for (int k = lane; k < n; k += 32) tmp[k] = cur[pl * W + order[k]];
+              __syncwarp();
+              for (int k = lane; k < n; k += 32) cur[pl * W + k] = tmp[k];
+              __syncwarp();
+            }
           }
         }
         // eval points (:747-762): sorted order, w >= min weight, model P_D > 0, the first nEvalCfg
