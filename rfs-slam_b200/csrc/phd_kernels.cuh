@@ -570,6 +570,7 @@ __device__ __forceinline__ bool lane_absorb(MergeRow<T>& r, const T* cur, int W,
 
 // 16-byte fill of a word array (n4 = number of uint4 entries) by the warp
 struct alignas(16) Word4 { unsigned a, b, c, d; };
+struct alignas(16) Quad { float v[4]; };   // four consecutive fp32 entries of a plane in one 16-byte shared-memory load
 __device__ __forceinline__ void warp_fill4(void* dst, unsigned v, int n4, int lane) {
   Word4* d = reinterpret_cast<Word4*>(dst);
   const Word4 q{v, v, v, v};
@@ -2226,15 +2227,32 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
           // could not contribute to either sum — before touching their inverse covariance or an exp
           const int ei = (e < nE) ? evalIdx[e] : 0;
           const T xe = cur[ei], ye = cur[W + ei];
-          const int half = (n + groups - 1) / groups;
+          const int half = (((n + groups - 1) / groups) + 3) & ~3;   // (a multiple of 4: the fp32 loops read 16 bytes at a time)
           const int m0 = h * half, m1 = (m0 + half < n) ? m0 + half : n;
           T lob = -M<T>::inf(), loa = -M<T>::inf();
           if (e < nE) {
-            for (int m = m0; m < m1; m++) {
-              const T dx = xe - cur[m], dy = ye - cur[W + m];
-              const T l = -ia[5 * W + m] * (dx * dx + dy * dy) - ia[3 * W + m];
-              if (cur[6 * W + m] > T(0) && l > lob) lob = l;
-              if (cur[5 * W + m] > T(0) && l > loa) loa = l;
+            if constexpr (sizeof(T) == 4) {
+              // the component data are the same for every lane (eval point): 16-byte broadcast loads, four components each
+              for (int m = m0; m < m1; m += 4) {
+                const Quad X = *reinterpret_cast<const Quad*>(cur + m), Y = *reinterpret_cast<const Quad*>(cur + W + m);
+                const Quad A5 = *reinterpret_cast<const Quad*>(ia + 5 * W + m), A3 = *reinterpret_cast<const Quad*>(ia + 3 * W + m);
+                const Quad WP = *reinterpret_cast<const Quad*>(cur + 6 * W + m), WN = *reinterpret_cast<const Quad*>(cur + 5 * W + m);
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                  const T dx = xe - X.v[k], dy = ye - Y.v[k];
+                  const T l = -A5.v[k] * (dx * dx + dy * dy) - A3.v[k];
+                  const bool in = m + k < m1;
+                  if (in && WP.v[k] > T(0) && l > lob) lob = l;
+                  if (in && WN.v[k] > T(0) && l > loa) loa = l;
+                }
+              }
+            } else {
+              for (int m = m0; m < m1; m++) {
+                const T dx = xe - cur[m], dy = ye - cur[W + m];
+                const T l = -ia[5 * W + m] * (dx * dx + dy * dy) - ia[3 * W + m];
+                if (cur[6 * W + m] > T(0) && l > lob) lob = l;
+                if (cur[5 * W + m] > T(0) && l > loa) loa = l;
+              }
             }
           }
           if (groups == 2) {
@@ -2243,22 +2261,38 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
             loa = oa > loa ? oa : loa;
           }
           const T skip_below = (lob < loa ? lob : loa) - CUT;   // -inf (no skipping) while a sum has no term at all
+          auto add_component = [&](int m, T dx, T dy, T lnm) {
+            const T i01 = ia[W + m];
+            const T md2 = (dx * ia[m] + dy * i01) * dx + (dx * i01 + dy * ia[2 * W + m]) * dy;
+            const T t = T(-0.5) * md2 - lnm;
+            const T wp = cur[6 * W + m], wn = cur[5 * W + m];
+            if (wp > T(0)) {
+              if (t > mb) { sb = sb * M<T>::exp_(mb - t) + wp; mb = t; }
+              else if (t > mb - CUT) sb += wp * M<T>::exp_(t - mb);
+            }
+            if (wn > T(0)) {
+              if (t > ma) { sa = sa * M<T>::exp_(ma - t) + wn; ma = t; }
+              else if (t > ma - CUT) sa += wn * M<T>::exp_(t - ma);
+            }
+          };
           if (e < nE) {
-            for (int m = m0; m < m1; m++) {
-              const T dx = xe - cur[m], dy = ye - cur[W + m];
-              const T lnm = ia[3 * W + m];
-              if (-ia[4 * W + m] * (dx * dx + dy * dy) - lnm <= skip_below) continue;
-              const T i01 = ia[W + m];
-              const T md2 = (dx * ia[m] + dy * i01) * dx + (dx * i01 + dy * ia[2 * W + m]) * dy;
-              const T t = T(-0.5) * md2 - lnm;
-              const T wp = cur[6 * W + m], wn = cur[5 * W + m];
-              if (wp > T(0)) {
-                if (t > mb) { sb = sb * M<T>::exp_(mb - t) + wp; mb = t; }
-                else if (t > mb - CUT) sb += wp * M<T>::exp_(t - mb);
+            if constexpr (sizeof(T) == 4) {
+              for (int m = m0; m < m1; m += 4) {
+                const Quad X = *reinterpret_cast<const Quad*>(cur + m), Y = *reinterpret_cast<const Quad*>(cur + W + m);
+                const Quad A4 = *reinterpret_cast<const Quad*>(ia + 4 * W + m), A3 = *reinterpret_cast<const Quad*>(ia + 3 * W + m);
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                  const T dx = xe - X.v[k], dy = ye - Y.v[k];
+                  const T lnm = A3.v[k];
+                  if (m + k < m1 && !(-A4.v[k] * (dx * dx + dy * dy) - lnm <= skip_below)) add_component(m + k, dx, dy, lnm);
+                }
               }
-              if (wn > T(0)) {
-                if (t > ma) { sa = sa * M<T>::exp_(ma - t) + wn; ma = t; }
-                else if (t > ma - CUT) sa += wn * M<T>::exp_(t - ma);
+            } else {
+              for (int m = m0; m < m1; m++) {
+                const T dx = xe - cur[m], dy = ye - cur[W + m];
+                const T lnm = ia[3 * W + m];
+                if (-ia[4 * W + m] * (dx * dx + dy * dy) - lnm <= skip_below) continue;
+                add_component(m, dx, dy, lnm);
               }
             }
           }
