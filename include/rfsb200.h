@@ -69,7 +69,7 @@ extern "C" {
 #define RFSB200_UPDATE_DEFER_NORMALIZE 16u /* with RFSB200_UPDATE_FUSED_ALLREDUCE on more than one rank: the kernel sends
                                          its [sum w, sum w^2] pair to the peers and ends WITHOUT waiting for theirs; the
                                          particle weights stay unnormalised until somebody needs them: the next
-                                         rfsb200_update (2-D plugin set) picks the pairs up from its mailbox during set-up
+                                         rfsb200_update picks the pairs up from its mailbox during set-up
                                          — they arrived a step ago — and divides the weights by the total while it loads
                                          them (same division, same operands: bit-identical to the eager step); any other
                                          consumer (rfsb200_get_weights, _update_host, _resample, _export_particles, ...)

@@ -536,6 +536,22 @@ phd_update_vp_kernel(const __grid_constant__ VPParams<T> vp) {
     mbar_init(bar, 1);
     fence_mbar_init();
   }
+  // deferred cross-GPU sums of the previous step (KParams::comm_pending, as in phd_update_kernel): thread r picks up rank
+  // r's pair from this GPU's own mailbox
+  __shared__ double prev_sum[8];
+  if ((int)threadIdx.x < p.comm_pending) {
+    const CommSlot* mine = reinterpret_cast<const CommSlot*>(p.comm_peer[p.comm_rank]) + (int)(p.comm_prev_epoch & 1ull) * 8;
+    const unsigned long long t0 = globaltimer_ns();
+    double a1 = 0, a2 = 0;
+    while (!comm_recv(mine + threadIdx.x, p.comm_prev_epoch, a1, a2)) {
+      if (globaltimer_ns() - t0 > p.comm_timeout_ns) {   // a peer never finished the previous step
+        *p.comm_error = 1;
+        a1 = __longlong_as_double(0x7ff8000000000000LL);
+        break;
+      }
+    }
+    prev_sum[threadIdx.x] = a1;
+  }
   __syncthreads();
   VPGeom geom;
   geom.rmin = vp.rmin; geom.rmax = vp.rmax; geom.bmin = vp.bmin; geom.bmax = vp.bmax; geom.buf_pd = vp.buf_pd;
@@ -556,7 +572,12 @@ phd_update_vp_kernel(const __grid_constant__ VPParams<T> vp) {
     pi = __shfl_sync(FULL, pi, 0);
     if (pi >= p.N) break;
 
-    const double w_prev_particle = p.w_in[pi];
+    double w_prev_particle = p.w_in[pi];
+    if (p.comm_pending_scale) {   // ParticleFilter::normalizeWeights of the previous step, applied on the way in
+      double total = 0;
+      for (int r = 0; r < p.comm_pending; r++) total += prev_sum[r];
+      w_prev_particle = w_prev_particle / total;
+    }
     int nM = p.cnt_in[pi];
     nM = nM < 0 ? 0 : (nM > p.cap ? p.cap : nM);
     int flags = (p.flags[pi] & FLAG_BIRTH_OVERFLOW) ? FLAG_OVERFLOW : 0;

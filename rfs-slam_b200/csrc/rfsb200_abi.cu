@@ -1074,12 +1074,12 @@ static int enqueue_update(rfsb200_ctx* c, const double* Z, int32_t nZ, uint32_t 
   }
   if ((flags & RFSB200_UPDATE_DEFER_NORMALIZE) && !(flags & RFSB200_UPDATE_FUSED_ALLREDUCE))
     return fail(c, RFSB200_EINVAL, "RFSB200_UPDATE_DEFER_NORMALIZE needs RFSB200_UPDATE_FUSED_ALLREDUCE");
-  // Sums a deferred step left open.  The 2-D kernels pick the pairs up during set-up (that wait is what keeps the ranks
+  // Sums a deferred step left open.  The update kernels pick the pairs up during set-up (that wait is what keeps the ranks
   // within one step of each other) and, if the open weights are the ones this step reads (the committed state), divide
   // them by the total on the way in; if they are those of the back buffer (a NO_COMMIT step) this launch overwrites them
   // and there is nothing to apply.  Everything else closes the open normalisation first.
   const bool open_front = c->comm_pending && c->comm_pending_buf == c->front;
-  c->consume_pending = c->comm_pending && c->ld == 2 && !c->hin_weight &&
+  c->consume_pending = c->comm_pending && !c->hin_weight &&
                        !(open_front && (flags & RFSB200_UPDATE_NO_COMMIT) && (flags & RFSB200_UPDATE_DEFER_NORMALIZE));   // (two would be open)
   c->consume_scale = c->consume_pending && open_front;
   if (c->comm_pending && !c->consume_pending) {

@@ -109,8 +109,9 @@ def test_particle_exchange_between_two_contexts_on_one_gpu(cuda_required, dim):
         u.close()
 
 
+@pytest.mark.parametrize("dim", [2, 3], ids=["rngbrg", "victoriapark"])
 @pytest.mark.parametrize("world", [2, 3])
-def test_deferred_cross_gpu_sums_between_contexts_on_one_gpu(cuda_required, world):
+def test_deferred_cross_gpu_sums_between_contexts_on_one_gpu(cuda_required, world, dim):
     """RFSB200_UPDATE_DEFER_NORMALIZE with the "ranks" as contexts of this process on ONE device (rfsb200_comm_connect_local),
     driven one after the other — possible because a deferred step never waits for a peer that is running at the same time:
     it sends its [sum w, sum w^2] and ends; the next step finds the pairs of the previous epoch in its mailbox and divides
@@ -121,15 +122,16 @@ def test_deferred_cross_gpu_sums_between_contexts_on_one_gpu(cuda_required, worl
     import numpy as np
     from rfs_slam_b200 import capi, synth
     from rfs_slam_b200.phd import PHDUpdater
-    wl = synth.make_workload(N=90, nM=40, nZ=10, use_cluster_process=1, config_id=97)
+    mk = synth.make_vp_workload if dim == 3 else synth.make_workload
+    wl = mk(N=90, nM=40, nZ=10, use_cluster_process=1, config_id=97)
     shards = [wl.shard(r, world) for r in range(world)]
     rng = np.random.default_rng(5)
-    Zs = [wl.Z.reshape(-1, 2) + rng.normal(0, 0.01, (wl.nZ, 2)) for _ in range(5)]
+    Zs = [wl.Z.reshape(-1, dim) + rng.normal(0, 0.01, (wl.nZ, dim)) for _ in range(5)]
 
     def fresh():
         ups = []
         for sh in shards:
-            u = PHDUpdater(sh.N, gm_capacity=128, precision=32)
+            u = PHDUpdater(sh.N, gm_capacity=128, precision=32, z_capacity=16, lmk_dim=dim)
             u.load_workload(sh)
             ups.append(u)
         return ups
