@@ -284,7 +284,7 @@ int rfsb200_append_gaussians(rfsb200_ctx* ctx, const int32_t* count /*[N]*/, con
  *   per level).  (The masks were routed by rfsb200_resample's aux_src.)  rfsb200_export/import_particles do not carry
  *   candidate lists.
  * Gaussians beyond gm_capacity set flag bits 1 and 8, a candidate beyond RFSB200_BIRTH_CAND_CAP is dropped with flag
- * bit 32.  Arithmetic is fp64 whatever the ctx precision; the appended Gaussians are rounded to the map's type. */
+ * bit 32; like bit 8 it is carried into the next update's result (flag bit 1, rfsb200_step_out::n_overflow).  Arithmetic is fp64 whatever the ctx precision; the appended Gaussians are rounded to the map's type. */
 #define RFSB200_BIRTH_CAND_CAP 64
 typedef struct rfsb200_birth_cfg {
   double   birth_weight;             /* birthGaussianWeight_                              */
@@ -397,7 +397,8 @@ int rfsb200_download_maps(rfsb200_ctx* ctx, int which, int64_t cap_total, int32_
 int rfsb200_get_unused(rfsb200_ctx* ctx, uint64_t* unused_mask /*[N]*/, int32_t* n_in_fov /*[N]*/);
 /* per-particle status bits of the last update: 1 = capacity overflow (of the update, or of a predict / append since the
  * update before), 2 = Murty branch taken, 4 = a partition beyond the assignment-sum tables, 8 = births dropped by the
- * last predict / append (cleared by the next update) */
+ * last predict / append (cleared by the next update), 16 = a Murty-compatibility record did not fit its buffer,
+ * 32 = a birth candidate did not fit the particle's candidate list (cleared by the next update) */
 int rfsb200_get_flags(rfsb200_ctx* ctx, int32_t* flags /*[N]*/);
 
 /* ---- utilities --------------------------------------------------------------------

@@ -23,8 +23,6 @@
 
 namespace rfsb200 {
 
-constexpr int FLAG_CAND_OVERFLOW = 32;   // a new candidate did not fit the particle's candidate list
-
 // one candidate record: mean[D] | covariance, upper triangle [D (D + 1) / 2] | nSupportingMeasurements | nChecks
 __host__ __device__ constexpr int cand_rec(int D) { return D + D * (D + 1) / 2 + 2; }
 

@@ -34,6 +34,7 @@ constexpr int MAX_PAIRS = 144; // merge: passing pairs (+ cluster links) kept pe
 constexpr int FLAG_OVERFLOW = 1;
 constexpr int FLAG_BIRTH_OVERFLOW = 8;   // set by predict / append when births did not fit gm_capacity; the next update turns
                                          // it into FLAG_OVERFLOW of its own result (and counts it), so the drop is not lost
+constexpr int FLAG_CAND_OVERFLOW = 32;  // rfsb200_birth_candidates: a new candidate did not fit the particle's candidate list (sticky like bit 8)
 constexpr int FLAG_MURTY = 2;       // a partition with nR + nC > 8 (reference would use Murty-200)
 constexpr int FLAG_DP_OVERFLOW = 4; // partition too large for the on-chip DP
 constexpr int FLAG_MURTY_DROPPED = 16;   // Murty compatibility: the record of a partition did not fit the record buffer
@@ -1801,7 +1802,7 @@ phd_update_kernel(const __grid_constant__ KParams<T> p) {
     T* cur = bufA;
     int nM = p.cnt_in[pi];
     nM = nM < 0 ? 0 : (nM > p.cap ? p.cap : nM);
-    int flags = (p.flags[pi] & FLAG_BIRTH_OVERFLOW) ? FLAG_OVERFLOW : 0;
+    int flags = (p.flags[pi] & (FLAG_BIRTH_OVERFLOW | FLAG_CAND_OVERFLOW)) ? FLAG_OVERFLOW : 0;
     if (nM > W) { nM = W; flags |= FLAG_OVERFLOW; }
 
     // ---------------- S0: TMA bulk loads -------------------------------------------------

@@ -580,7 +580,7 @@ phd_update_vp_kernel(const __grid_constant__ VPParams<T> vp) {
     }
     int nM = p.cnt_in[pi];
     nM = nM < 0 ? 0 : (nM > p.cap ? p.cap : nM);
-    int flags = (p.flags[pi] & FLAG_BIRTH_OVERFLOW) ? FLAG_OVERFLOW : 0;
+    int flags = (p.flags[pi] & (FLAG_BIRTH_OVERFLOW | FLAG_CAND_OVERFLOW)) ? FLAG_OVERFLOW : 0;
     if (nM > W) { nM = W; flags |= FLAG_OVERFLOW; }
 
     // ---------------- S0: TMA bulk loads ---------------------------------------------------------

@@ -173,10 +173,15 @@ class ShardedUpdater:
         return None
 
 
-    def resolve(self):
-        """Closes a deferred step: afterwards the weights are normalised and the sums are the global ones."""
+    def resolve(self, check: bool = False):
+        """Closes a deferred step: afterwards the weights are normalised and the sums are the global ones.  check: wait for
+        the stream and raise if a peer missed one of the exchanges since the last check (deferred steps are asynchronous,
+        so nothing else looks at rfsb200_comm_error in between)."""
         if self.fused:
             self.up.comm_resolve()
+            if check:
+                self.up.synchronize()
+                self.check_comm()
 
     def check_comm(self):
         """Raises if a peer did not arrive in some fused update since the last check (the sums of that step are NaN).

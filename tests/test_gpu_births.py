@@ -156,6 +156,8 @@ def test_candidate_list_overflow_and_capacity_flags(cuda_required):
     full = (mask != 0) & (nfov > 0)
     assert full.any() and ((fl[full] & 32) != 0).all()
     assert (up.get_birth_candidates()[0] == C).all()
+    so = up.update(wl.Z, want_stats=True)      # the drop shows in the next update's result
+    assert so.n_overflow >= int(full.sum())
     # now every candidate has enough support: 64 real Gaussians per particle do not fit the maps
     up.update(wl.Z)
     up.set_birth_candidates(n, mean, cov, np.full((wl.N, C), 5, np.int32), np.zeros((wl.N, C), np.int32))
