@@ -471,7 +471,7 @@ def run_workload(a, name, ctx, steps, warmup, headline):
                                             + ("inside the update kernel over NVLink peer memory" if fused else "by NCCL")
                                             + ("; consumed DEFERRED: a step sends its pair and ends, the next step picks the peers' pairs up during "
                                                "set-up, the last step's normalisation is closed inside the timed region (see `exchange`)" if defer else "")),
-                    e2e=e2e, gpu_launches=(1 if fused else 2) * K, roofline=roofline, cpu_baseline=cpu, clocks=clk,
+                    e2e=e2e, gpu_launches=(1 if fused else 2) * K + (1 if defer else 0), roofline=roofline, cpu_baseline=cpu, clocks=clk,
                     stages=stages, n_murty_per_step=n_murty, n_overflow_per_step=n_overflow,
                     wall_s_timed_region_incl_flush=t_wall)
         if world > 1:
